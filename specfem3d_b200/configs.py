@@ -1,0 +1,74 @@
+"""The workloads named in BASELINE.json ``configs`` (and scaled-down twins for tests).
+
+cfg1  default DATA/Par_file example: homogeneous elastic halfspace 134 km x 134 km x 60 km, 36x36x16 elements,
+      rho 2300 / vp 2800 / vs 1500, CMT at (67000, 67000, -30000) hdur 5 s, four stations, Stacey on 5 sides,
+      DT 0.05, NSTEP 5000, 4 ranks (EXAMPLES/applications/homogeneous_halfspace/DATA/{Par_file,CMTSOLUTION,STATIONS}).
+      Station x-coordinates are the ones REF_SEIS was generated with (REF_SEIS/output_solver.txt "original x").
+cfg2  same material scaled to 128x128x64 (~1M elements), 1 rank, irregular (non-cubic spacing) or regular twin.
+cfg3  layered viscoelastic (3 SLS) + C-PML.
+cfg4  water layer over elastic halfspace.
+cfg5  256x256x128 (~8M) elastic, partitioned.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+from .meshfem import BoxSpec, Material
+from .simulation import Simulation, make_simulation
+from .sources_receivers import CMTSource, ForceSource, Station
+
+HALFSPACE = Material(2300.0, 2800.0, 1500.0, 9999.0, 9999.0, 2)
+
+CMT_DEFAULT = CMTSource(
+    x=67000.0, y=67000.0, z=-30000.0,
+    moment_tensor=(-7.6e27, 7.7e27, -2.0e26, -2.5e28, 4.0e26, -2.5e27),  # Mrr Mtt Mpp Mrt Mrp Mtp (dyne-cm)
+    hdur=5.0, tshift=0.0)
+
+STATIONS_DEFAULT = [
+    Station("X20", "DB", 22732.10, 67000.0, 0.0),
+    Station("X30", "DB", 34696.40, 67000.0, 0.0),
+    Station("X40", "DB", 46660.70, 67000.0, 0.0),
+    Station("X50", "DB", 58625.00, 67000.0, 0.0),
+]
+
+
+def cfg1(nproc_xi: int = 2, nproc_eta: int = 2, NSTEP: int = 5000) -> Simulation:
+    spec = BoxSpec(36, 36, 16, nproc_xi=nproc_xi, nproc_eta=nproc_eta, materials=(HALFSPACE,))
+    return make_simulation(spec, DT=0.05, NSTEP=NSTEP, sources=[CMT_DEFAULT], stations=STATIONS_DEFAULT)
+
+
+def courant_dt(spec: BoxSpec, vp_max: float, courant: float = 0.3) -> float:
+    """DT from the Courant rule on the smallest GLL spacing (0.1727 of the element size for NGLL=5)."""
+    dx = min((spec.xmax - spec.xmin) / spec.nex_xi, (spec.ymax - spec.ymin) / spec.nex_eta,
+             (spec.zmax - spec.zmin) / spec.ner)
+    return courant * 0.172673 * dx / vp_max
+
+
+def halfspace_scaled(nex_xi: int, nex_eta: int, ner: int, nproc_xi: int = 1, nproc_eta: int = 1, NSTEP: int = 100,
+                     regular: bool = False, deform: float = 0.0, dt: Optional[float] = None,
+                     stations: bool = True) -> Simulation:
+    """cfg2 / cfg5 family: the cfg1 box re-meshed with nex_xi x nex_eta x ner elements."""
+    if regular:
+        # cubic spacing twin: keep dx of the x direction everywhere
+        dx = 134000.0 / nex_xi
+        spec = BoxSpec(nex_xi, nex_eta, ner, xmax=dx * nex_xi, ymax=dx * nex_eta, zmin=-dx * ner, nproc_xi=nproc_xi,
+                       nproc_eta=nproc_eta, materials=(HALFSPACE,))
+    else:
+        spec = BoxSpec(nex_xi, nex_eta, ner, nproc_xi=nproc_xi, nproc_eta=nproc_eta, materials=(HALFSPACE,),
+                       deform=deform)
+    DT = dt if dt is not None else courant_dt(spec, 2800.0)
+    src = CMTSource(x=0.5 * spec.xmax, y=0.5 * spec.ymax, z=0.5 * spec.zmin, moment_tensor=CMT_DEFAULT.moment_tensor,
+                    hdur=max(5.0 * 36.0 / nex_xi, 5.0 * DT), tshift=0.0)
+    sts = []
+    if stations:
+        for n, f in enumerate((0.17, 0.26, 0.35, 0.44)):
+            sts.append(Station(f"X{n}", "DB", f * spec.xmax, 0.5 * spec.ymax, spec.zmax))
+    return make_simulation(spec, DT=DT, NSTEP=NSTEP, sources=[src], stations=sts)
+
+
+def cfg2(NSTEP: int = 1000, regular: bool = False) -> Simulation:
+    return halfspace_scaled(128, 128, 64, NSTEP=NSTEP, regular=regular)
+
+
+def cfg5(nproc_xi: int, nproc_eta: int, NSTEP: int = 100) -> Simulation:
+    return halfspace_scaled(256, 256, 128, nproc_xi, nproc_eta, NSTEP=NSTEP)

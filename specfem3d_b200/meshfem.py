@@ -1,0 +1,668 @@
+"""Harness database generator: a structured hexahedral box, partitioned in NPROC_XI x NPROC_ETA slabs, turned into
+the per-rank solver arrays with the reference's semantics (what xmeshfem3D + xgenerate_databases would write and
+the Fortran solver would hand to ``prepare_constants_device`` / ``prepare_fields_*_device``).
+
+Restated rules (reference file:line in each function):
+
+* element order z-outer / y / x-inner                      src/meshfem3D/create_meshfem_mesh.f90:463-500
+* slice addressing iproc = iproc_eta*NPROC_XI + iproc_xi   src/meshfem3D/meshfem3D.F90:250-257
+* MPI interface order W,E,S,N,NW,NE,SE,SW                  src/meshfem3D/save_databases.F90:408-560
+* interface points sorted by (x,y,z)                       src/generate_databases/get_MPI.f90:28-200
+* inner/outer split, phase_ispec_inner_*                   src/generate_databases/create_regions_mesh.f90:1590-1807
+* regular/irregular element split                          src/generate_databases/calc_jacobian.f90:184-348
+* material arrays                                          src/generate_databases/get_model.F90:289-301
+* absorbing faces xmin,xmax,ymin,ymax,bottom(,top)         src/generate_databases/get_absorbing_boundary.F90:28-330
+* face GLL index order                                     src/shared/get_element_face.f90:169-279
+* 2-D jacobian * weights, unit outward normal              src/shared/get_jacobian_boundaries.f90:300-365
+* fluid/solid coupling faces (from the acoustic side)      src/generate_databases/get_coupling_surfaces.f90:197-405
+* mass matrices incl. Stacey C*dt/2 term                   src/shared/define_mass_matrices.f90:30-160,353-520
+                                                           src/specfem3D/prepare_timerun.F90:263-340
+
+All arrays are numpy C-order with *reversed* Fortran dimensions, i.e. ``ibool[ispec,k,j,i]`` is byte-identical to
+Fortran ``ibool(i,j,k,ispec)``; integer arrays are 1-based exactly as the Fortran solver passes them.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+
+from .gll import GLL, NGLL2, NGLL3
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_MG = None
+
+
+def _meshgen():
+    global _MG
+    if _MG is None:
+        path = os.path.join(_HERE, "_meshgen.so")
+        if not os.path.exists(path):
+            from .build import build_meshgen
+
+            build_meshgen()
+        lib = ctypes.CDLL(path)
+        lib.mg_box_ibool.restype = ctypes.c_int64
+        lib.mg_box_ibool.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        lib.mg_metrics.restype = None
+        lib.mg_metrics.argtypes = [ctypes.c_int64] + [ctypes.c_void_p] * 16
+        lib.mg_mass_matrix.restype = None
+        lib.mg_mass_matrix.argtypes = [ctypes.c_int64] + [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.c_void_p]
+        _MG = lib
+    return _MG
+
+
+def _p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+@dataclass
+class Material:
+    """One row of nummaterial_velocity_file: domain 1 = acoustic, 2 = elastic."""
+
+    rho: float
+    vp: float
+    vs: float
+    Qkappa: float = 9999.0
+    Qmu: float = 9999.0
+    domain: int = 2
+
+
+@dataclass
+class BoxSpec:
+    """Mesh_Par_file-like description of the structured box."""
+
+    nex_xi: int
+    nex_eta: int
+    ner: int
+    xmin: float = 0.0
+    xmax: float = 134000.0
+    ymin: float = 0.0
+    ymax: float = 134000.0
+    zmin: float = -60000.0
+    zmax: float = 0.0
+    nproc_xi: int = 1
+    nproc_eta: int = 1
+    materials: Sequence[Material] = (Material(2300.0, 2800.0, 1500.0),)
+    # material index (into ``materials``) of each element layer, bottom (0) to top (ner-1)
+    layer_material: Optional[Sequence[int]] = None
+    # optional smooth deformation of the corner nodes: amplitude as a fraction of the element size
+    deform: float = 0.0
+    stacey: bool = True
+    stacey_instead_of_free_surface: bool = False
+    # C-PML shell thickness in elements on xmin/xmax/ymin/ymax/bottom (0 = none)
+    pml_thickness: int = 0
+
+    @property
+    def nproc(self) -> int:
+        return self.nproc_xi * self.nproc_eta
+
+    @property
+    def nspec_total(self) -> int:
+        return self.nex_xi * self.nex_eta * self.ner
+
+
+@dataclass
+class Database:
+    """Per-rank solver database (names follow src/specfem3D/specfem3D_par.F90)."""
+
+    myrank: int = 0
+    NPROC: int = 1
+    NSPEC_AB: int = 0
+    NGLOB_AB: int = 0
+    nx: int = 0
+    ny: int = 0
+    nz: int = 0
+    ix0: int = 0  # element offset of this slab in the global box
+    iy0: int = 0
+    ibool: np.ndarray = None
+    grid_of_glob: np.ndarray = None  # global structured GLL grid id of each local point (harness only)
+    xstore: np.ndarray = None
+    ystore: np.ndarray = None
+    zstore: np.ndarray = None
+    NSPEC_IRREGULAR: int = 0
+    irregular_element_number: np.ndarray = None
+    xix_regular: float = 0.0
+    jacobian_regular: float = 0.0
+    xixstore: np.ndarray = None
+    xiystore: np.ndarray = None
+    xizstore: np.ndarray = None
+    etaxstore: np.ndarray = None
+    etaystore: np.ndarray = None
+    etazstore: np.ndarray = None
+    gammaxstore: np.ndarray = None
+    gammaystore: np.ndarray = None
+    gammazstore: np.ndarray = None
+    jacobianstore: np.ndarray = None
+    jacobian_full: np.ndarray = None  # (nspec,125) jacobian incl. regular elements (harness only)
+    kappastore: np.ndarray = None
+    mustore: np.ndarray = None
+    rhostore: np.ndarray = None
+    rho_vp: np.ndarray = None
+    rho_vs: np.ndarray = None
+    qkappa: np.ndarray = None  # per element (harness only)
+    qmu: np.ndarray = None
+    ispec_is_elastic: np.ndarray = None
+    ispec_is_acoustic: np.ndarray = None
+    nspec_elastic: int = 0
+    nspec_acoustic: int = 0
+    # boundaries
+    num_abs_boundary_faces: int = 0
+    abs_boundary_ispec: np.ndarray = None
+    abs_boundary_ijk: np.ndarray = None
+    abs_boundary_normal: np.ndarray = None
+    abs_boundary_jacobian2Dw: np.ndarray = None
+    num_free_surface_faces: int = 0
+    free_surface_ispec: np.ndarray = None
+    free_surface_ijk: np.ndarray = None
+    free_surface_normal: np.ndarray = None
+    free_surface_jacobian2Dw: np.ndarray = None
+    num_coupling_ac_el_faces: int = 0
+    coupling_ac_el_ispec: np.ndarray = None
+    coupling_ac_el_ijk: np.ndarray = None
+    coupling_ac_el_normal: np.ndarray = None
+    coupling_ac_el_jacobian2Dw: np.ndarray = None
+    # MPI
+    num_interfaces_ext_mesh: int = 0
+    max_nibool_interfaces_ext_mesh: int = 0
+    my_neighbors_ext_mesh: np.ndarray = None
+    nibool_interfaces_ext_mesh: np.ndarray = None
+    ibool_interfaces_ext_mesh: np.ndarray = None
+    ispec_is_inner: np.ndarray = None
+    nspec_inner_elastic: int = 0
+    nspec_outer_elastic: int = 0
+    num_phase_ispec_elastic: int = 0
+    phase_ispec_inner_elastic: np.ndarray = None
+    nspec_inner_acoustic: int = 0
+    nspec_outer_acoustic: int = 0
+    num_phase_ispec_acoustic: int = 0
+    phase_ispec_inner_acoustic: np.ndarray = None
+    # mass matrices (inverted, assembled) as passed to prepare_fields_*_device
+    rmassx: np.ndarray = None
+    rmassy: np.ndarray = None
+    rmassz: np.ndarray = None
+    rmass_acoustic: np.ndarray = None
+    # C-PML
+    is_CPML: np.ndarray = None
+    extra: dict = field(default_factory=dict)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def _deform(spec: BoxSpec, x, y, z):
+    """Smooth, boundary-preserving deformation of corner-node coordinates (harness feature, not in the reference):
+    makes all nine metric terms non-trivial so the irregular-element path is really exercised."""
+    if spec.deform == 0.0:
+        return x, y, z
+    Lx, Ly, Lz = spec.xmax - spec.xmin, spec.ymax - spec.ymin, spec.zmax - spec.zmin
+    dx, dy, dz = Lx / spec.nex_xi, Ly / spec.nex_eta, Lz / spec.ner
+    u, v, w = (x - spec.xmin) / Lx, (y - spec.ymin) / Ly, (z - spec.zmin) / Lz
+    bump = np.sin(np.pi * u) * np.sin(np.pi * v) * np.sin(np.pi * w)
+    a = spec.deform
+    xd = x + a * dx * bump * np.sin(2.3 * np.pi * v + 0.4) * np.cos(1.7 * np.pi * w)
+    yd = y + a * dy * bump * np.sin(1.9 * np.pi * w + 0.9) * np.cos(2.1 * np.pi * u)
+    zd = z + a * dz * bump * np.sin(2.7 * np.pi * u + 0.2) * np.cos(1.3 * np.pi * v)
+    return xd, yd, zd
+
+
+def _corner_coords(spec: BoxSpec, ix, iy, iz):
+    """Corner-node coordinates (double) at integer corner-grid positions (global indices)."""
+    x = spec.xmin + (spec.xmax - spec.xmin) * (ix / spec.nex_xi)
+    y = spec.ymin + (spec.ymax - spec.ymin) * (iy / spec.nex_eta)
+    z = spec.zmin + (spec.zmax - spec.zmin) * (iz / spec.ner)
+    return _deform(spec, x, y, z)
+
+
+# hex corner order of get_shape3D.f90 (offsets in x,y,z)
+_CORNER = np.array(
+    [[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], dtype=np.int64
+)
+
+
+def _face_ijk(iface: int) -> np.ndarray:
+    """(25,3) 1-based (i,j,k) of the face points, first face index fastest (get_element_face.f90:169-279)."""
+    out = np.zeros((25, 3), dtype=np.int32)
+    n = 0
+    for b in range(1, 6):
+        for a in range(1, 6):
+            if iface == 1:
+                out[n] = (1, a, b)
+            elif iface == 2:
+                out[n] = (5, a, b)
+            elif iface == 3:
+                out[n] = (a, 1, b)
+            elif iface == 4:
+                out[n] = (a, 5, b)
+            elif iface == 5:
+                out[n] = (a, b, 1)
+            else:
+                out[n] = (a, b, 5)
+            n += 1
+    return out
+
+
+# local corner indices (into _CORNER order) spanning each face, chosen so that (d/da x d/db) of the first two face
+# directions gives a consistent normal that we then orient outward explicitly.
+_FACE_CORNERS = {
+    1: (0, 3, 7, 4),  # x = xmin : a = y, b = z
+    2: (1, 2, 6, 5),
+    3: (0, 1, 5, 4),  # y = ymin : a = x, b = z
+    4: (3, 2, 6, 7),
+    5: (0, 1, 2, 3),  # z = zmin : a = x, b = y
+    6: (4, 5, 6, 7),
+}
+_FACE_OUTWARD = {1: (-1, 0, 0), 2: (1, 0, 0), 3: (0, -1, 0), 4: (0, 1, 0), 5: (0, 0, -1), 6: (0, 0, 1)}
+
+
+def _face_geometry(gll: GLL, corners_elem: np.ndarray, iface: int):
+    """jacobian2Dw (nf,25) float32 and outward unit normal (nf,25,3) float32 for face ``iface`` of the elements
+    whose 8 corners are ``corners_elem`` (nf,8,3) (get_jacobian_boundaries.f90:300-365)."""
+    c = corners_elem[:, _FACE_CORNERS[iface], :]  # (nf,4,3) ordered (0,0),(1,0),(1,1),(0,1) in (a,b)
+    xi = gll.xigll
+    A, B = np.meshgrid(xi, xi, indexing="ij")  # A[a,b]
+    # bilinear shape derivative
+    dNa = 0.25 * np.stack([-(1 - B), (1 - B), (1 + B), -(1 + B)], axis=0)  # (4,a,b)
+    dNb = 0.25 * np.stack([-(1 - A), -(1 + A), (1 + A), (1 - A)], axis=0)
+    ta = np.einsum("nab,fnc->fabc", dNa, c)  # d x / d a
+    tb = np.einsum("nab,fnc->fabc", dNb, c)
+    un = np.cross(ta, tb)
+    jac = np.sqrt((un * un).sum(-1))
+    normal = un / jac[..., None]
+    out = np.array(_FACE_OUTWARD[iface], dtype=np.float64)
+    sign = np.sign((normal * out).sum(-1))
+    normal = normal * sign[..., None]
+    ww = np.outer(gll.wgll, gll.wgll)
+    jw = (jac * ww[None]).astype(np.float32)
+    # igll = a + 5*b (a fastest)
+    jw = jw.transpose(0, 2, 1).reshape(-1, 25)
+    normal = normal.transpose(0, 2, 1, 3).reshape(-1, 25, 3).astype(np.float32)
+    return np.ascontiguousarray(jw), np.ascontiguousarray(normal)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def build_partition(spec: BoxSpec, myrank: int, gll: Optional[GLL] = None, with_metrics: bool = True) -> Database:
+    """Create the database of one slab (no mass matrices yet, see :func:`finalize_mass_matrices`)."""
+    gll = gll or GLL()
+    mg = _meshgen()
+    if spec.nex_xi % spec.nproc_xi or spec.nex_eta % spec.nproc_eta:
+        raise ValueError("NEX must be a multiple of NPROC in each direction (Mesh_Par_file rule)")
+    ipx, ipy = myrank % spec.nproc_xi, myrank // spec.nproc_xi
+    nx, ny, nz = spec.nex_xi // spec.nproc_xi, spec.nex_eta // spec.nproc_eta, spec.ner
+    ix0, iy0 = ipx * nx, ipy * ny
+    nspec = nx * ny * nz
+    db = Database(myrank=myrank, NPROC=spec.nproc, NSPEC_AB=nspec, nx=nx, ny=ny, nz=nz, ix0=ix0, iy0=iy0)
+
+    # --- ibool ------------------------------------------------------------------------------------------------
+    ibool = np.empty((nspec, 5, 5, 5), dtype=np.int32)
+    GX, GY, GZ = 4 * nx + 1, 4 * ny + 1, 4 * nz + 1
+    grid_local = np.empty(GX * GY * GZ, dtype=np.int64)
+    nglob = int(mg.mg_box_ibool(nx, ny, nz, _p(ibool), _p(grid_local)))
+    assert nglob == GX * GY * GZ
+    db.ibool, db.NGLOB_AB = ibool, nglob
+    lgx = grid_local % GX
+    lgy = (grid_local // GX) % GY
+    lgz = grid_local // (GX * GY)
+    GXg, GYg = 4 * spec.nex_xi + 1, 4 * spec.nex_eta + 1
+    ggx, ggy = lgx + 4 * ix0, lgy + 4 * iy0
+    db.grid_of_glob = ggx + GXg * (ggy + GYg * lgz)
+    db.extra["lg"] = (lgx.astype(np.int32), lgy.astype(np.int32), lgz.astype(np.int32))
+
+    # --- element corners ---------------------------------------------------------------------------------------
+    e = np.arange(nspec, dtype=np.int64)
+    eix, eiy, eiz = e % nx + ix0, (e // nx) % ny + iy0, e // (nx * ny)
+    db.extra["eijk"] = (eix, eiy, eiz)
+    cx, cy, cz = _corner_coords(
+        spec,
+        (eix[:, None] + _CORNER[None, :, 0]).astype(np.float64),
+        (eiy[:, None] + _CORNER[None, :, 1]).astype(np.float64),
+        (eiz[:, None] + _CORNER[None, :, 2]).astype(np.float64),
+    )
+    corners = np.ascontiguousarray(np.stack([cx, cy, cz], axis=-1))  # (nspec,8,3)
+    db.extra["corners"] = corners
+
+    # --- regular / irregular split (calc_jacobian.f90:184-348) ----------------------------------------------------
+    cf = corners.astype(np.float32).astype(np.float64)  # the reference tests single-precision node coordinates
+    d1 = ((cf[:, 1] - cf[:, 0]) ** 2).sum(-1)
+    d2 = ((cf[:, 4] - cf[:, 0]) ** 2).sum(-1)
+    d3 = ((cf[:, 3] - cf[:, 0]) ** 2).sum(-1)
+
+    def eq(a, b):
+        return np.abs(a - b) <= 1e-12 * np.maximum(1.0, np.maximum(np.abs(a), np.abs(b)))
+
+    X, Y, Z = cf[..., 0], cf[..., 1], cf[..., 2]
+    aligned = (
+        eq(X[:, 0], X[:, 3]) & eq(X[:, 0], X[:, 4]) & eq(X[:, 0], X[:, 7]) & eq(X[:, 1], X[:, 2])
+        & eq(X[:, 1], X[:, 5]) & eq(X[:, 1], X[:, 6]) & eq(Y[:, 0], Y[:, 1]) & eq(Y[:, 0], Y[:, 4])
+        & eq(Y[:, 0], Y[:, 5]) & eq(Y[:, 2], Y[:, 3]) & eq(Y[:, 2], Y[:, 6]) & eq(Y[:, 2], Y[:, 7])
+        & eq(Z[:, 0], Z[:, 1]) & eq(Z[:, 0], Z[:, 2]) & eq(Z[:, 0], Z[:, 3]) & eq(Z[:, 4], Z[:, 5])
+        & eq(Z[:, 4], Z[:, 6]) & eq(Z[:, 4], Z[:, 7])
+    )
+    cube = aligned & (np.abs(d2 - d1) < 1e-5 * d1) & (np.abs(d3 - d1) < 1e-5 * d1)
+    if cube.any():
+        first = int(np.argmax(cube))
+        regular = cube & (np.abs(d1 - d1[first]) <= 1e-5 * d1[first])
+    else:
+        regular = cube
+    irregular_element_number = np.zeros(nspec, dtype=np.int32)
+    irr = ~regular
+    irregular_element_number[irr] = np.arange(1, int(irr.sum()) + 1, dtype=np.int32)
+    db.irregular_element_number = irregular_element_number
+    db.NSPEC_IRREGULAR = int(irr.sum())
+
+    # --- metric terms -------------------------------------------------------------------------------------------
+    if with_metrics:
+        xs = np.empty((nspec, 125))
+        ys = np.empty((nspec, 125))
+        zs = np.empty((nspec, 125))
+        jac_full = np.empty((nspec, 125), dtype=np.float32)
+        nirr = db.NSPEC_IRREGULAR
+        names = ["xixstore", "xiystore", "xizstore", "etaxstore", "etaystore", "etazstore", "gammaxstore",
+                 "gammaystore", "gammazstore"]
+        bad = ctypes.c_int(0)
+        if nirr == nspec:
+            arrs = [np.empty((nspec, 5, 5, 5), dtype=np.float32) for _ in names]
+            mg.mg_metrics(nspec, _p(corners), _p(gll.xigll), *[_p(a) for a in arrs], _p(jac_full), _p(xs), _p(ys),
+                          _p(zs), ctypes.byref(bad))
+        else:
+            full = [np.empty((nspec, 125), dtype=np.float32) for _ in names]
+            mg.mg_metrics(nspec, _p(corners), _p(gll.xigll), *[_p(a) for a in full], _p(jac_full), _p(xs), _p(ys),
+                          _p(zs), ctypes.byref(bad))
+            if regular.any():
+                first = int(np.argmax(regular))
+                db.xix_regular = float(full[0][first, 0])
+                db.jacobian_regular = float(jac_full[first, 0])
+            if nirr > 0:
+                arrs = [np.ascontiguousarray(a[irr]).reshape(nirr, 5, 5, 5) for a in full]
+            else:  # the solver allocates (1,1,1,1) dummies (create_regions_mesh.f90)
+                arrs = [np.zeros((1, 1, 1, 1), dtype=np.float32) for _ in names]
+            del full
+        if bad.value:
+            raise ValueError(f"{bad.value} points with non-positive Jacobian: deformation too strong")
+        for n, a in zip(names, arrs):
+            setattr(db, n, a)
+        db.jacobian_full = jac_full
+        db.jacobianstore = (np.ascontiguousarray(jac_full[irr]).reshape(-1, 5, 5, 5) if nirr > 0
+                            else np.zeros((1, 1, 1, 1), dtype=np.float32))
+        flat = ibool.reshape(-1) - 1
+        for nm, loc in (("xstore", xs), ("ystore", ys), ("zstore", zs)):
+            g = np.empty(nglob, dtype=np.float32)
+            g[flat] = loc.reshape(-1).astype(np.float32)
+            setattr(db, nm, g)
+        del xs, ys, zs
+
+    # --- materials (get_model.F90:289-301, float arithmetic) -------------------------------------------------------
+    layer_mat = np.zeros(spec.ner, dtype=np.int64) if spec.layer_material is None else np.asarray(spec.layer_material)
+    mat_id = layer_mat[eiz]
+    rho = np.array([m.rho for m in spec.materials], dtype=np.float32)[mat_id]
+    vp = np.array([m.vp for m in spec.materials], dtype=np.float32)[mat_id]
+    vs = np.array([m.vs for m in spec.materials], dtype=np.float32)[mat_id]
+    dom = np.array([m.domain for m in spec.materials], dtype=np.int32)[mat_id]
+    db.qkappa = np.array([m.Qkappa for m in spec.materials], dtype=np.float32)[mat_id]
+    db.qmu = np.array([m.Qmu for m in spec.materials], dtype=np.float32)[mat_id]
+    FOUR_THIRDS = np.float32(4.0 / 3.0)
+    kappa = rho * (vp * vp - FOUR_THIRDS * vs * vs)
+    mu = rho * vs * vs
+    ones = np.ones((1, 5, 5, 5), dtype=np.float32)
+    db.rhostore = rho[:, None, None, None] * ones
+    db.kappastore = kappa[:, None, None, None] * ones
+    db.mustore = mu[:, None, None, None] * ones
+    db.rho_vp = (rho * vp)[:, None, None, None] * ones
+    db.rho_vs = (rho * vs)[:, None, None, None] * ones
+    db.ispec_is_elastic = (dom == 2).astype(np.int32)
+    db.ispec_is_acoustic = (dom == 1).astype(np.int32)
+    db.nspec_elastic = int(db.ispec_is_elastic.sum())
+    db.nspec_acoustic = int(db.ispec_is_acoustic.sum())
+
+    # --- absorbing / free-surface faces ----------------------------------------------------------------------------
+    def faces_on(iface):
+        if iface == 1:
+            m = eix == 0
+        elif iface == 2:
+            m = eix == spec.nex_xi - 1
+        elif iface == 3:
+            m = eiy == 0
+        elif iface == 4:
+            m = eiy == spec.nex_eta - 1
+        elif iface == 5:
+            m = eiz == 0
+        else:
+            m = eiz == spec.ner - 1
+        return np.nonzero(m)[0]
+
+    def face_set(face_ids):
+        isp, ijk, nrm, jw = [], [], [], []
+        for f in face_ids:
+            els = faces_on(f)
+            if len(els) == 0:
+                continue
+            j2, nn = _face_geometry(gll, corners[els], f)
+            isp.append(els.astype(np.int32) + 1)
+            ijk.append(np.broadcast_to(_face_ijk(f)[None], (len(els), 25, 3)))
+            nrm.append(nn)
+            jw.append(j2)
+        if not isp:
+            return 0, np.zeros(1, np.int32), np.zeros((1, 25, 3), np.int32), np.zeros((1, 25, 3), np.float32), \
+                np.zeros((1, 25), np.float32)
+        return (sum(len(a) for a in isp), np.concatenate(isp), np.ascontiguousarray(np.concatenate(ijk), dtype=np.int32),
+                np.concatenate(nrm), np.concatenate(jw))
+
+    abs_faces = []
+    if spec.stacey:
+        abs_faces = [1, 2, 3, 4, 5] + ([6] if spec.stacey_instead_of_free_surface else [])
+    (db.num_abs_boundary_faces, db.abs_boundary_ispec, db.abs_boundary_ijk, db.abs_boundary_normal,
+     db.abs_boundary_jacobian2Dw) = face_set(abs_faces)
+    (db.num_free_surface_faces, db.free_surface_ispec, db.free_surface_ijk, db.free_surface_normal,
+     db.free_surface_jacobian2Dw) = face_set([6])
+
+    # --- fluid/solid coupling faces (horizontal layering only: faces 5 and 6 of acoustic elements) ------------------
+    if db.nspec_acoustic and db.nspec_elastic:
+        dom_col = np.array([m.domain for m in spec.materials], dtype=np.int32)[layer_mat]  # per layer
+        isp, ijk, nrm, jw = [], [], [], []
+        ac = np.nonzero(db.ispec_is_acoustic)[0]
+        # ascending ispec, then face 5 before face 6
+        recs = []
+        for f, dz in ((5, -1), (6, 1)):
+            lz = eiz[ac] + dz
+            ok = (lz >= 0) & (lz < spec.ner)
+            okk = ok.copy()
+            okk[ok] = dom_col[lz[ok]] == 2
+            els = ac[okk]
+            if len(els):
+                j2, nn = _face_geometry(gll, corners[els], f)
+                for n_, el in enumerate(els):
+                    recs.append((int(el), f, nn[n_], j2[n_]))
+        recs.sort(key=lambda r: (r[0], r[1]))
+        if recs:
+            db.num_coupling_ac_el_faces = len(recs)
+            db.coupling_ac_el_ispec = np.array([r[0] + 1 for r in recs], dtype=np.int32)
+            db.coupling_ac_el_ijk = np.ascontiguousarray(np.stack([_face_ijk(r[1]) for r in recs]), dtype=np.int32)
+            db.coupling_ac_el_normal = np.ascontiguousarray(np.stack([r[2] for r in recs]))
+            db.coupling_ac_el_jacobian2Dw = np.ascontiguousarray(np.stack([r[3] for r in recs]))
+    if db.num_coupling_ac_el_faces == 0:
+        db.coupling_ac_el_ispec = np.zeros(1, np.int32)
+        db.coupling_ac_el_ijk = np.zeros((1, 25, 3), np.int32)
+        db.coupling_ac_el_normal = np.zeros((1, 25, 3), np.float32)
+        db.coupling_ac_el_jacobian2Dw = np.zeros((1, 25), np.float32)
+
+    # --- MPI interfaces ------------------------------------------------------------------------------------------
+    lgx32, lgy32, lgz32 = db.extra["lg"]
+    neigh = []  # (rank, mask)
+    W, E, S, N = ipx > 0, ipx < spec.nproc_xi - 1, ipy > 0, ipy < spec.nproc_eta - 1
+    rank_of = lambda a, b: b * spec.nproc_xi + a
+    on_w, on_e, on_s, on_n = lgx32 == 0, lgx32 == GX - 1, lgy32 == 0, lgy32 == GY - 1
+    if W:
+        neigh.append((rank_of(ipx - 1, ipy), on_w))
+    if E:
+        neigh.append((rank_of(ipx + 1, ipy), on_e))
+    if S:
+        neigh.append((rank_of(ipx, ipy - 1), on_s))
+    if N:
+        neigh.append((rank_of(ipx, ipy + 1), on_n))
+    if W and N:
+        neigh.append((rank_of(ipx - 1, ipy + 1), on_w & on_n))
+    if N and E:
+        neigh.append((rank_of(ipx + 1, ipy + 1), on_n & on_e))
+    if E and S:
+        neigh.append((rank_of(ipx + 1, ipy - 1), on_e & on_s))
+    if W and S:
+        neigh.append((rank_of(ipx - 1, ipy - 1), on_w & on_s))
+    db.num_interfaces_ext_mesh = len(neigh)
+    if neigh:
+        lists = []
+        for _, m in neigh:
+            idx = np.nonzero(m)[0]
+            order = np.lexsort((lgz32[idx], lgy32[idx], lgx32[idx]))  # x primary, then y, then z
+            lists.append((idx[order] + 1).astype(np.int32))
+        db.nibool_interfaces_ext_mesh = np.array([len(l) for l in lists], dtype=np.int32)
+        db.max_nibool_interfaces_ext_mesh = int(db.nibool_interfaces_ext_mesh.max())
+        ibi = np.zeros((len(lists), db.max_nibool_interfaces_ext_mesh), dtype=np.int32)
+        for n_, l in enumerate(lists):
+            ibi[n_, : len(l)] = l
+        db.ibool_interfaces_ext_mesh = ibi
+        db.my_neighbors_ext_mesh = np.array([r for r, _ in neigh], dtype=np.int32)
+    else:
+        db.nibool_interfaces_ext_mesh = np.zeros(1, np.int32)
+        db.ibool_interfaces_ext_mesh = np.zeros((1, 1), np.int32)
+        db.my_neighbors_ext_mesh = np.zeros(1, np.int32)
+        db.max_nibool_interfaces_ext_mesh = 0
+
+    # --- inner / outer (create_regions_mesh.f90:1590-1807) ---------------------------------------------------------
+    iglob_is_inner = np.ones(nglob, dtype=bool)
+    for n_ in range(db.num_interfaces_ext_mesh):
+        iglob_is_inner[db.ibool_interfaces_ext_mesh[n_, : db.nibool_interfaces_ext_mesh[n_]] - 1] = False
+    inner = iglob_is_inner[ibool.reshape(nspec, 125) - 1].all(axis=1)
+    db.ispec_is_inner = inner.astype(np.int32)
+
+    def phases(mask):
+        el = np.nonzero(mask)[0]
+        inn = el[inner[el]] + 1
+        out = el[~inner[el]] + 1
+        nph = max(len(inn), len(out))
+        ph = np.zeros((2, max(nph, 1)), dtype=np.int32)
+        ph[0, : len(out)] = out
+        ph[1, : len(inn)] = inn
+        return len(inn), len(out), nph, ph
+
+    (db.nspec_inner_elastic, db.nspec_outer_elastic, db.num_phase_ispec_elastic,
+     db.phase_ispec_inner_elastic) = phases(db.ispec_is_elastic.astype(bool))
+    (db.nspec_inner_acoustic, db.nspec_outer_acoustic, db.num_phase_ispec_acoustic,
+     db.phase_ispec_inner_acoustic) = phases(db.ispec_is_acoustic.astype(bool))
+
+    # --- C-PML flags (shell of given thickness on the five absorbing sides) ------------------------------------------
+    t = spec.pml_thickness
+    if t > 0:
+        pml = (eix < t) | (eix >= spec.nex_xi - t) | (eiy < t) | (eiy >= spec.nex_eta - t) | (eiz < t)
+        db.is_CPML = pml.astype(np.int32)
+    else:
+        db.is_CPML = np.zeros(nspec, dtype=np.int32)
+    return db
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def local_mass_matrices(spec: BoxSpec, db: Database, DT: float, gll: Optional[GLL] = None):
+    """Un-assembled, un-inverted mass matrices of one rank: returns dict with rmassx/y/z (elastic) and
+    rmass_acoustic (define_mass_matrices.f90 + the additions of prepare_timerun.F90:263-300)."""
+    gll = gll or GLL()
+    mg = _meshgen()
+    nglob = db.NGLOB_AB
+    w3 = (gll.wgll[None, None, :] * gll.wgll[None, :, None] * gll.wgll[:, None, None]).reshape(-1).copy()  # [k,j,i]
+    out = {}
+    flat_ibool = db.ibool.reshape(-1, 125)
+
+    if db.nspec_elastic:
+        rmass = np.zeros(nglob, dtype=np.float32)
+        mg.mg_mass_matrix(db.NSPEC_AB, _p(db.ibool), _p(db.jacobian_full), _p(db.rhostore), _p(w3),
+                          _p(db.ispec_is_elastic), 0, _p(rmass))
+        rx = np.zeros(nglob, dtype=np.float32)
+        ry = np.zeros(nglob, dtype=np.float32)
+        rz = np.zeros(nglob, dtype=np.float32)
+        if spec.stacey and db.num_abs_boundary_faces:
+            # define_mass_matrices_Stacey_elastic (define_mass_matrices.f90:353-442), float arithmetic, face order
+            dto2 = np.float32(0.5 * DT)
+            for f in range(db.num_abs_boundary_faces):
+                isp = db.abs_boundary_ispec[f] - 1
+                if not db.ispec_is_elastic[isp]:
+                    continue
+                ijk = db.abs_boundary_ijk[f] - 1
+                p = ijk[:, 0] + 5 * ijk[:, 1] + 25 * ijk[:, 2]
+                n = db.abs_boundary_normal[f]
+                nx_, ny_, nz_ = n[:, 0], n[:, 1], n[:, 2]
+                vn = dto2 * (nx_ + ny_ + nz_)
+                rvp = db.rho_vp.reshape(-1, 125)[isp, p]
+                rvs = db.rho_vs.reshape(-1, 125)[isp, p]
+                tx = rvp * vn * nx_ + rvs * (dto2 - vn * nx_)
+                ty = rvp * vn * ny_ + rvs * (dto2 - vn * ny_)
+                tz = rvp * vn * nz_ + rvs * (dto2 - vn * nz_)
+                jw = db.abs_boundary_jacobian2Dw[f]
+                ig = flat_ibool[isp, p] - 1
+                # points of one face are distinct -> plain fancy += is exact
+                rx[ig] += tx * jw
+                ry[ig] += ty * jw
+                rz[ig] += tz * jw
+            out["rmassx"], out["rmassy"], out["rmassz"] = rmass + rx, rmass + ry, rmass + rz
+        else:
+            out["rmassx"], out["rmassy"], out["rmassz"] = rmass.copy(), rmass.copy(), rmass.copy()
+
+    if db.nspec_acoustic:
+        rma = np.zeros(nglob, dtype=np.float32)
+        mg.mg_mass_matrix(db.NSPEC_AB, _p(db.ibool), _p(db.jacobian_full), _p(db.kappastore), _p(w3),
+                          _p(db.ispec_is_acoustic), 1, _p(rma))
+        if spec.stacey and db.num_abs_boundary_faces:
+            # define_mass_matrices_Stacey_acoustic (define_mass_matrices.f90:450-520): sl = dt/2 / (rho vp)
+            dto2 = np.float32(0.5 * DT)
+            rz = np.zeros(nglob, dtype=np.float32)
+            for f in range(db.num_abs_boundary_faces):
+                isp = db.abs_boundary_ispec[f] - 1
+                if not db.ispec_is_acoustic[isp]:
+                    continue
+                ijk = db.abs_boundary_ijk[f] - 1
+                p = ijk[:, 0] + 5 * ijk[:, 1] + 25 * ijk[:, 2]
+                sl = dto2 / db.rho_vp.reshape(-1, 125)[isp, p]
+                ig = flat_ibool[isp, p] - 1
+                rz[ig] += db.abs_boundary_jacobian2Dw[f] * sl
+            rma = rma + rz
+        out["rmass_acoustic"] = rma
+    return out
+
+
+def assemble_scalar_in_process(dbs: List[Database], arrays: List[np.ndarray]):
+    """assemble_MPI_scalar_blocking for partitions living in one process (src/specfem3D/assemble_MPI_scalar.f90):
+    every rank adds, interface by interface in its own interface order, the neighbour's *pre-assembly* values."""
+    sends = []
+    for db, a in zip(dbs, arrays):
+        s = {}
+        for n_ in range(db.num_interfaces_ext_mesh):
+            ids = db.ibool_interfaces_ext_mesh[n_, : db.nibool_interfaces_ext_mesh[n_]] - 1
+            s[int(db.my_neighbors_ext_mesh[n_])] = a[ids].copy()
+        sends.append(s)
+    for db, a in zip(dbs, arrays):
+        for n_ in range(db.num_interfaces_ext_mesh):
+            ids = db.ibool_interfaces_ext_mesh[n_, : db.nibool_interfaces_ext_mesh[n_]] - 1
+            a[ids] += sends[int(db.my_neighbors_ext_mesh[n_])][db.myrank]
+
+
+def invert_mass(a: np.ndarray) -> np.ndarray:
+    """``where(rmass <= 0) rmass = 1; rmass = 1/rmass`` (prepare_timerun.F90:300-338)."""
+    a = a.copy()
+    a[a <= 0] = 1.0
+    return (np.float32(1.0) / a).astype(np.float32)
+
+
+def build_all(spec: BoxSpec, DT: float, gll: Optional[GLL] = None) -> List[Database]:
+    """All partitions in one process with assembled + inverted mass matrices (used by tests and N=1 runs)."""
+    gll = gll or GLL()
+    dbs = [build_partition(spec, r, gll) for r in range(spec.nproc)]
+    loc = [local_mass_matrices(spec, db, DT, gll) for db in dbs]
+    for key in ("rmassx", "rmassy", "rmassz", "rmass_acoustic"):
+        if all(key in l for l in loc):
+            arrs = [l[key] for l in loc]
+            if spec.nproc > 1:
+                assemble_scalar_in_process(dbs, arrs)
+            for db, a in zip(dbs, arrs):
+                setattr(db, key, invert_mass(a))
+        elif any(key in l for l in loc):
+            raise NotImplementedError("harness: every partition must contain both domains or neither")
+    return dbs

@@ -1,0 +1,127 @@
+"""Host-side description of one forward run: what the Fortran solver knows after ``prepare_timerun`` and before
+``iterate_time`` (mesh databases, GLL constants, sources, receivers, time scheme constants, optional attenuation /
+C-PML arrays).  Both the device driver (:mod:`specfem3d_b200.time_loop`) and the CPU oracle (``oracle/solver.py``)
+consume this object, so they see byte-identical inputs.
+
+Time-scheme constants follow src/specfem3D/prepare_timerun.F90:412-414:
+``deltat = real(DT)``, ``deltatover2 = deltat/2``, ``deltatsqover2 = deltat*deltat/2`` in single precision.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from .gll import GLL
+from .meshfem import BoxSpec, Database, build_all
+from .sources_receivers import (CMTSource, ForceSource, ReceiverSet, SourceSet, Station, setup_receivers,
+                                setup_sources)
+
+
+@dataclass
+class Simulation:
+    spec: BoxSpec
+    DT: float
+    NSTEP: int
+    dbs: List[Database]
+    gll: GLL
+    sources: Optional[SourceSet]
+    receivers: Optional[ReceiverSet]
+    ATTENUATION: bool = False
+    PML_CONDITIONS: bool = False
+    NTSTEP_BETWEEN_OUTPUT_SAMPLE: int = 1
+    SAVE_SEISMOGRAMS_DISPLACEMENT: bool = True
+    SAVE_SEISMOGRAMS_VELOCITY: bool = False
+    SAVE_SEISMOGRAMS_ACCELERATION: bool = False
+    SAVE_SEISMOGRAMS_PRESSURE: bool = False
+    att: Optional[list] = None  # per-partition attenuation arrays (see attenuation.py)
+    pml: Optional[list] = None  # per-partition C-PML arrays (see pml.py)
+    initial_fields: Optional[list] = None  # per-partition dict(displ=, veloc=, accel=, pot=...) or None = zero
+
+    @property
+    def deltat(self) -> np.float32:
+        return np.float32(self.DT)
+
+    @property
+    def deltatover2(self) -> np.float32:
+        return np.float32(self.deltat / np.float32(2.0))
+
+    @property
+    def deltatsqover2(self) -> np.float32:
+        return np.float32(self.deltat * self.deltat / np.float32(2.0))
+
+    @property
+    def ELASTIC_SIMULATION(self) -> bool:
+        return any(db.nspec_elastic > 0 for db in self.dbs)
+
+    @property
+    def ACOUSTIC_SIMULATION(self) -> bool:
+        return any(db.nspec_acoustic > 0 for db in self.dbs)
+
+    @property
+    def nlength_seismogram(self) -> int:
+        return (self.NSTEP + self.NTSTEP_BETWEEN_OUTPUT_SAMPLE - 1) // self.NTSTEP_BETWEEN_OUTPUT_SAMPLE
+
+    def stf_pre_compute(self, it: int) -> np.ndarray:
+        """Elastic source time function values (double) for step ``it`` as the host passes them to
+        ``compute_add_sources_el_cuda`` (compute_add_sources_viscoelastic.F90: compute_add_sources_viscoelastic_GPU)."""
+        s = self.sources
+        return np.array([s.stf(i, it, self.DT) for i in range(s.NSOURCES)], dtype=np.float64)
+
+    def stf_pre_compute_acoustic(self, it: int) -> np.ndarray:
+        s = self.sources
+        return np.array([s.stf_acoustic(i, it, self.DT) for i in range(s.NSOURCES)], dtype=np.float64)
+
+    def time_axis(self) -> np.ndarray:
+        """Seismogram time axis: (it-1)*DT - t0 (write_seismograms.f90)."""
+        it = np.arange(1, self.NSTEP + 1, self.NTSTEP_BETWEEN_OUTPUT_SAMPLE)
+        t0 = self.sources.t0 if self.sources is not None else 0.0
+        return (it - 1) * self.DT - t0
+
+
+def make_simulation(spec: BoxSpec, DT: float, NSTEP: int, sources: Sequence = (), stations: Sequence[Station] = (),
+                    attenuation: bool = False, f0_attenuation: float = 0.0, **kw) -> Simulation:
+    gll = GLL()
+    dbs = build_all(spec, DT, gll)
+    acoustic_present = any(db.nspec_acoustic > 0 for db in dbs)
+    src = setup_sources(spec, dbs, sources, DT, gll, acoustic_present) if len(sources) else None
+    rec = setup_receivers(spec, dbs, stations, gll) if len(stations) else None
+    sim = Simulation(spec, DT, NSTEP, dbs, gll, src, rec, ATTENUATION=attenuation, **kw)
+    if src is not None and acoustic_present:
+        _acoustic_sourcearrays(sim, sources)
+    if attenuation:
+        from .attenuation import prepare_attenuation
+
+        sim.att = prepare_attenuation(sim, f0_attenuation)
+    if spec.pml_thickness > 0:
+        from .pml import prepare_pml
+
+        sim.PML_CONDITIONS = True
+        sim.pml = prepare_pml(sim)
+    return sim
+
+
+def _acoustic_sourcearrays(sim: Simulation, sources: Sequence) -> None:
+    """Sources located in fluid elements use a scalar (pressure-like) source array replicated on the three
+    components: factor * h_i h_j h_k with factor = sqrt(M:M/2)*sqrt(2/3) (setup_sources_receivers.f90:1165-1185)."""
+    from .gll import lagrange_any
+
+    s = sim.sources
+    for n, src in enumerate(sources):
+        db = sim.dbs[s.islice_selected_source[n]]
+        if not db.ispec_is_acoustic[s.ispec_selected_source[n] - 1]:
+            continue
+        xi, eta, gam = s.local[n]
+        hx, _ = lagrange_any(xi, sim.gll.xigll)
+        hy, _ = lagrange_any(eta, sim.gll.xigll)
+        hz, _ = lagrange_any(gam, sim.gll.xigll)
+        h3 = hz[:, None, None] * hy[None, :, None] * hx[None, None, :]
+        if isinstance(src, CMTSource):
+            Mrr, Mtt, Mpp, Mrt, Mrp, Mtp = (m * 1e-7 for m in src.moment_tensor)
+            Mzz, Mxx, Myy, Mxz, Myz, Mxy = Mrr, Mpp, Mtt, Mrp, -Mrt, -Mtp
+            f = 1.0 / np.sqrt(2.0) * np.sqrt(Mxx ** 2 + Myy ** 2 + Mzz ** 2 + 2.0 * (Myz ** 2 + Mxz ** 2 + Mxy ** 2))
+            f = f * np.sqrt(2.0) / np.sqrt(3.0)
+        else:
+            f = src.factor
+        s.sourcearrays[..., n] = (f * h3[..., None] * np.ones(3)[None, None, None, :]).astype(np.float32)

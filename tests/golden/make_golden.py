@@ -1,0 +1,37 @@
+"""Regenerates tests/golden/*.npz from the reference tree (run in the build container, where /root/reference exists).
+
+halfspace_ref_seis.npz : the reference's own golden seismograms for the default example (config 1),
+    EXAMPLES/applications/homogeneous_halfspace/REF_SEIS/DB.X{20,30,40,50}.BX{X,Y,Z}.semd, first NKEEP samples
+    (ASCII "time value" -> float32 arrays), plus the max-norm lines of REF_SEIS/output_solver.txt.
+"""
+import os
+import re
+import sys
+
+import numpy as np
+
+REF = "/root/reference/EXAMPLES/applications/homogeneous_halfspace/REF_SEIS"
+NKEEP = 1500
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    out = {}
+    for st in ("X20", "X30", "X40", "X50"):
+        for ch in "XYZ":
+            d = np.loadtxt(os.path.join(REF, f"DB.{st}.BX{ch}.semd"))
+            out[f"{st}_{ch}"] = d[:NKEEP, 1].astype(np.float32)
+            out["time"] = d[:NKEEP, 0].astype(np.float32)
+    steps, norms = [], []
+    txt = open(os.path.join(REF, "output_solver.txt")).read()
+    for m in re.finditer(r"Time step #\s+(\d+).*?Max norm displacement vector U in all slices \(m\) =\s+([0-9.E+-]+)", txt, re.S):
+        steps.append(int(m.group(1)))
+        norms.append(float(m.group(2)))
+    out["maxnorm_step"] = np.array(steps, dtype=np.int32)
+    out["maxnorm_value"] = np.array(norms, dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "halfspace_ref_seis.npz"), **out)
+    print("wrote halfspace_ref_seis.npz", {k: v.shape for k, v in out.items() if k.startswith("max")})
+
+
+if __name__ == "__main__":
+    sys.exit(main())
