@@ -1,0 +1,224 @@
+// device_mesh.h -- device-side state of one mesh partition (one MPI rank = one GPU) and host utilities.
+//
+// Plays the role of the reference's `Mesh` struct (src/gpu/mesh_constants_gpu.h:413-770): it is what the opaque
+// `long* Mesh_pointer` of every Fortran-callable entry point refers to.  The layout of device arrays is this
+// library's own (the Fortran side never sees device memory):
+//
+//   * per-element arrays (ibool, 9 inverse-metric terms, kappa, mu, rho) are strided 128 floats per element
+//     (125 GLL points + 3 pad) so that every element starts on a 512-byte boundary and a warp reads whole 128-byte
+//     lines; metric terms exist only for irregular elements (slot = irregular_element_number-1);
+//   * wavefields are [NGLOB][3] float (same as the Fortran (3,NGLOB) arrays) so the 8 transfer_* calls are plain copies;
+//   * attenuation memory variables are re-laid out as [element][sls][128] planes (the host layout is sls-fastest);
+//   * all index arrays keep the Fortran 1-based contents; kernels subtract 1.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+typedef float realw;
+
+#define NGLLX 5
+#define NGLL2 25
+#define NGLL3 125
+#define NGLL3_PADDED 128
+#define NDIM 3
+#define N_SLS 3
+
+namespace sb200 {
+
+// ---------------------------------------------------------------------------------------------------------------
+// error handling: same contract as the reference (src/gpu/mesh_constants_cuda.h:122-152, helper_functions.cu:265-350):
+// print, append to OUTPUT_FILES/error_message_%06d.txt, terminate the process.  No status codes cross the ABI.
+// ---------------------------------------------------------------------------------------------------------------
+extern int g_myrank;
+
+[[noreturn]] inline void exit_on_error(const char* msg) {
+  fprintf(stderr, "\nERROR (specfem3d_b200, rank %d): %s\n", g_myrank, msg);
+  fflush(stderr);
+  char fn[256];
+  snprintf(fn, sizeof(fn), "OUTPUT_FILES/error_message_%06d.txt", g_myrank);
+  FILE* fp = fopen(fn, "a+");
+  if (fp) {
+    fprintf(fp, "ERROR: %s\n", msg);
+    fclose(fp);
+  }
+  exit(EXIT_FAILURE);
+}
+
+inline void cuda_check(cudaError_t err, const char* what, int line) {
+  if (err != cudaSuccess) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "CUDA error '%s' in %s (line %d)", cudaGetErrorString(err), what, line);
+    exit_on_error(buf);
+  }
+}
+#define CUDA_CHECK(x) ::sb200::cuda_check((x), #x, __LINE__)
+
+inline bool very_slow_error_checking() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SPECFEM_B200_CHECK");
+    v = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  return v == 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+struct DeviceMesh {
+  int device = 0;
+  int myrank = 0;
+  // sizes / flags
+  int NSPEC_AB = 0, NGLOB_AB = 0, NSPEC_IRREGULAR = 0;
+  int simulation_type = 1, save_forward = 0;
+  int stacey_absorbing_conditions = 0, pml_conditions = 0, undo_attenuation = 0;
+  int use_mesh_coloring_gpu = 0;
+  int nspec_acoustic = 0, nspec_elastic = 0;
+  int attenuation = 0, compute_and_store_strain = 0, anisotropy = 0, gravity = 0, fault_simulation = 0;
+  int approximate_ocean_load = 0;
+  realw xix_regular = 0.f, jacobian_regular = 0.f;
+
+  cudaStream_t compute_stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev_pack_done = nullptr, ev_copy_done = nullptr;
+
+  // mesh
+  int* d_ibool = nullptr;                     // [NSPEC][128]
+  int* d_irregular_element_number = nullptr;  // [NSPEC]
+  realw* d_metric = nullptr;  // [NSPEC_IRREGULAR][9][128] : xix,xiy,xiz,etax,etay,etaz,gammax,gammay,gammaz planes
+  realw *d_kappav = nullptr, *d_muv = nullptr, *d_rhostore = nullptr;  // [NSPEC][128]
+  realw *d_rho_vp = nullptr, *d_rho_vs = nullptr;                      // [NSPEC][125]
+  realw* d_kappastore_unpadded = nullptr;                              // [NSPEC][125] (acoustic sources, Stacey)
+  int *d_ispec_is_inner = nullptr, *d_ispec_is_elastic = nullptr, *d_ispec_is_acoustic = nullptr;
+  int *d_phase_ispec_inner_elastic = nullptr, *d_phase_ispec_inner_acoustic = nullptr;
+  int num_phase_ispec_elastic = 0, num_phase_ispec_acoustic = 0;
+  // colouring (host pointers are *retained*, like the reference: prepare_mesh_constants_cuda.cu:986,563)
+  int num_colors_outer_elastic = 0, num_colors_inner_elastic = 0;
+  int* h_num_elem_colors_elastic = nullptr;
+  int num_colors_outer_acoustic = 0, num_colors_inner_acoustic = 0;
+  int* h_num_elem_colors_acoustic = nullptr;
+
+  // wavefields
+  realw *d_displ = nullptr, *d_veloc = nullptr, *d_accel = nullptr;                                       // [NGLOB][3]
+  realw *d_potential = nullptr, *d_potential_dot = nullptr, *d_potential_dot_dot = nullptr;               // [NGLOB]
+  realw *d_rmassx = nullptr, *d_rmassy = nullptr, *d_rmassz = nullptr, *d_rmass_acoustic = nullptr;       // [NGLOB]
+  realw* d_rmass_ocean_load = nullptr;
+
+  // attenuation (planes of 128 per element and SLS)
+  realw *d_R_xx = nullptr, *d_R_yy = nullptr, *d_R_xy = nullptr, *d_R_xz = nullptr, *d_R_yz = nullptr,
+        *d_R_trace = nullptr;                                              // [NSPEC][N_SLS][128]
+  realw *d_factor_common = nullptr, *d_factor_common_kappa = nullptr;      // [NSPEC][N_SLS][128]
+  realw *d_epsilondev_xx = nullptr, *d_epsilondev_yy = nullptr, *d_epsilondev_xy = nullptr,
+        *d_epsilondev_xz = nullptr, *d_epsilondev_yz = nullptr, *d_epsilondev_trace = nullptr;  // [NSPEC][128]
+  realw h_alphaval[N_SLS] = {0}, h_betaval[N_SLS] = {0}, h_gammaval[N_SLS] = {0};
+  int R_size = 0;
+
+  // boundaries
+  int num_abs_boundary_faces = 0;
+  int *d_abs_boundary_ispec = nullptr, *d_abs_boundary_ijk = nullptr;
+  realw *d_abs_boundary_normal = nullptr, *d_abs_boundary_jacobian2Dw = nullptr;
+  realw *d_b_absorb_field = nullptr, *d_b_absorb_potential = nullptr;
+  int b_reclen_field = 0, b_reclen_potential = 0;
+  int num_free_surface_faces = 0;
+  int *d_free_surface_ispec = nullptr, *d_free_surface_ijk = nullptr;
+  realw* d_free_surface_normal = nullptr;
+  int num_coupling_ac_el_faces = 0;
+  int *d_coupling_ac_el_ispec = nullptr, *d_coupling_ac_el_ijk = nullptr;
+  realw *d_coupling_ac_el_normal = nullptr, *d_coupling_ac_el_jacobian2Dw = nullptr;
+
+  // sources / receivers
+  int nsources = 0, nsources_local = 0, nrec = 0, nrec_local = 0, nlength_seismogram = 0;
+  realw* d_sourcearrays = nullptr;  // Fortran (NSOURCES,3,5,5,5)
+  realw* d_stf_pre_compute = nullptr;
+  realw* h_stf_pinned = nullptr;    // pinned staging ring for the per-step stf upload
+  int stf_ring = 0;
+  int *d_islice_selected_source = nullptr, *d_ispec_selected_source = nullptr;
+  int *d_ispec_selected_rec = nullptr, *d_ispec_selected_rec_loc = nullptr;
+  realw *d_hxir = nullptr, *d_hetar = nullptr, *d_hgammar = nullptr, *d_nu_rec = nullptr;
+  int save_seismograms_d = 0, save_seismograms_v = 0, save_seismograms_a = 0, save_seismograms_p = 0;
+  realw *d_seismograms_d = nullptr, *d_seismograms_v = nullptr, *d_seismograms_a = nullptr, *d_seismograms_p = nullptr;
+
+  // MPI interfaces
+  int num_interfaces_ext_mesh = 0, max_nibool_interfaces_ext_mesh = 0;
+  int *d_nibool_interfaces_ext_mesh = nullptr, *d_ibool_interfaces_ext_mesh = nullptr;
+  std::vector<int> h_nibool_interfaces;
+  int size_mpi_buffer = 0, size_mpi_buffer_potential = 0;
+  realw *d_send_accel_buffer = nullptr, *h_send_accel_buffer = nullptr, *h_recv_accel_buffer = nullptr;
+  realw *d_send_potential_buffer = nullptr;
+
+  // peer-to-peer halo over NVLink (extension, see halo_p2p.cuh)
+  struct P2P* p2p = nullptr;
+
+  // C-PML (see pml.cuh)
+  struct PML* pml = nullptr;
+  int NSPEC_CPML = 0;
+  int *d_is_CPML = nullptr;
+
+  // norms
+  realw* d_norm_partial = nullptr;
+  realw* h_norm_partial = nullptr;
+  int norm_blocks = 0;
+
+  // options
+  int force_kernel_variant = 0;  // 0 = default
+  long long kernel_launches = 0;
+};
+
+inline DeviceMesh* get_mesh(long* Mesh_pointer) {
+  DeviceMesh* mp = reinterpret_cast<DeviceMesh*>(*Mesh_pointer);
+  if (mp == nullptr) exit_on_error("NULL Mesh_pointer: prepare_constants_device must be called first");
+  int cur = -1;
+  cudaGetDevice(&cur);
+  if (cur != mp->device) CUDA_CHECK(cudaSetDevice(mp->device));
+  return mp;
+}
+
+// ---- allocation / copy helpers ------------------------------------------------------------------------------------
+template <typename T>
+inline T* dev_alloc(size_t n) {
+  T* p = nullptr;
+  CUDA_CHECK(cudaMalloc((void**)&p, (n > 0 ? n : 1) * sizeof(T)));
+  return p;
+}
+template <typename T>
+inline T* dev_alloc_zero(size_t n) {
+  T* p = dev_alloc<T>(n);
+  CUDA_CHECK(cudaMemset(p, 0, (n > 0 ? n : 1) * sizeof(T)));
+  return p;
+}
+template <typename T>
+inline T* dev_copy(const T* h, size_t n) {
+  T* p = dev_alloc<T>(n);
+  if (n > 0) CUDA_CHECK(cudaMemcpy(p, h, n * sizeof(T), cudaMemcpyHostToDevice));
+  return p;
+}
+// host [n][125] -> device [n][128] (pad entries zeroed / for ibool set to point 1 so that they stay valid indices)
+template <typename T>
+inline T* dev_copy_padded(const T* h, size_t nelem, T padval) {
+  T* p = dev_alloc<T>(nelem * NGLL3_PADDED);
+  if (nelem == 0) return p;
+  std::vector<T> tmp(nelem * NGLL3_PADDED, padval);
+  for (size_t e = 0; e < nelem; ++e) memcpy(&tmp[e * NGLL3_PADDED], h + e * NGLL3, NGLL3 * sizeof(T));
+  CUDA_CHECK(cudaMemcpy(p, tmp.data(), tmp.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return p;
+}
+inline void dev_free(void* p) {
+  if (p) cudaFree(p);
+}
+
+inline int grid_for(long long n, int block) { return (int)((n + block - 1) / block); }
+
+#define KERNEL_CHECK(mp, name)                                       \
+  do {                                                               \
+    (mp)->kernel_launches++;                                         \
+    CUDA_CHECK(cudaGetLastError());                                  \
+    if (::sb200::very_slow_error_checking()) {                       \
+      cudaError_t e_ = cudaDeviceSynchronize();                      \
+      if (e_ != cudaSuccess) ::sb200::cuda_check(e_, name, __LINE__); \
+    }                                                                \
+  } while (0)
+
+}  // namespace sb200

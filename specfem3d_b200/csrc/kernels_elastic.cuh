@@ -1,0 +1,260 @@
+// kernels_elastic.cuh -- elastic / viscoelastic internal-force kernels.
+//
+// Replaces the reference's Kernel_2_noatt_iso_impl / Kernel_2_att_impl
+// (src/gpu/kernels/Kernel_2_viscoelastic_impl.cu:725-1022, 2245-2659); the arithmetic follows the CPU routine
+// compute_forces_viscoelastic (src/specfem3D/compute_forces_viscoelastic.F90:247-962) with the two GPU-side
+// choices the reference also makes: the Jacobian is recomputed as 1/det of the inverse metric, and with
+// attenuation the strain of (u + dt v) is obtained by differentiating u + dt*v directly.
+//
+// Variant "pt" (one thread per GLL point, 128 threads per element) is the plain first path; variant "col"
+// (kernels_elastic_col.cuh) is the register-blocked one.
+#pragma once
+#include "kernels_common.cuh"
+
+namespace sb200 {
+
+struct ElasticArgs {
+  int nb_elements;             // elements in this launch
+  const int* phase_ispec;      // this phase's element list (1-based ids), or nullptr -> element = first_ispec + bx
+  int first_ispec;             // used when phase_ispec == nullptr (coloured launches)
+  const int* ibool;            // [NSPEC][128]
+  const int* irregular_element_number;
+  const realw* metric;         // [NSPEC_IRREGULAR][9][128]
+  realw xix_regular, jacobian_regular;
+  const realw* kappav;         // [NSPEC][128]
+  const realw* muv;
+  const realw* displ;
+  const realw* veloc;
+  realw* accel;
+  const int* is_CPML;          // nullptr when no PML
+  realw deltat;
+  int use_atomics;             // 0 for coloured launches
+  // attenuation
+  realw *R_xx, *R_yy, *R_xy, *R_xz, *R_yz, *R_trace;                    // [NSPEC][N_SLS][128]
+  const realw *factor_common, *factor_common_kappa;                      // [NSPEC][N_SLS][128]
+  realw *eps_xx, *eps_yy, *eps_xy, *eps_xz, *eps_yz, *eps_trace;         // [NSPEC][128]
+};
+
+// One thread per GLL point.  ATT: attenuation (implies strain storage).  STRAIN: store epsilondev without attenuation.
+template <bool ATT, bool STRAIN>
+__global__ void __launch_bounds__(NGLL3_PADDED) k_elastic_forces_pt(const ElasticArgs a) {
+  const int bx = blockIdx.x;
+  if (bx >= a.nb_elements) return;
+  const int tx = threadIdx.x;
+  const bool active = tx < NGLL3;
+  const int t = active ? tx : NGLL3 - 1;
+  const int K = t / NGLL2, J = (t - K * NGLL2) / NGLLX, I = t - K * NGLL2 - J * NGLLX;
+
+  __shared__ realw s_x[NGLL3_PADDED], s_y[NGLL3_PADDED], s_z[NGLL3_PADDED];
+  __shared__ realw s_ax[ATT ? NGLL3_PADDED : 1], s_ay[ATT ? NGLL3_PADDED : 1], s_az[ATT ? NGLL3_PADDED : 1];
+  __shared__ realw s_hp[NGLL2], s_hw[NGLL2];
+
+  const int ispec = a.phase_ispec ? a.phase_ispec[bx] - 1 : a.first_ispec + bx;
+  if (a.is_CPML && a.is_CPML[ispec]) return;  // PML elements are handled by the PML kernel
+  const int irr = a.irregular_element_number[ispec] - 1;
+  const size_t off = (size_t)ispec * NGLL3_PADDED + t;
+  const int iglob = a.ibool[off] - 1;
+
+  {
+    const realw ux = a.displ[3 * (size_t)iglob], uy = a.displ[3 * (size_t)iglob + 1], uz = a.displ[3 * (size_t)iglob + 2];
+    s_x[t] = ux; s_y[t] = uy; s_z[t] = uz;
+    if (ATT) {
+      s_ax[t] = ux + a.deltat * a.veloc[3 * (size_t)iglob];
+      s_ay[t] = uy + a.deltat * a.veloc[3 * (size_t)iglob + 1];
+      s_az[t] = uz + a.deltat * a.veloc[3 * (size_t)iglob + 2];
+    }
+  }
+  if (tx < NGLL2) {
+    s_hp[tx] = c_hprime_xx[tx];
+    s_hw[tx] = c_hprimewgll_xx[tx];
+  }
+  const realw kappal = a.kappav[off], mul = a.muv[off];
+  Metric m;
+  if (irr >= 0) {
+    const realw* mp = a.metric + (size_t)irr * 9 * NGLL3_PADDED + t;
+    m.xix = mp[0]; m.xiy = mp[NGLL3_PADDED]; m.xiz = mp[2 * NGLL3_PADDED];
+    m.etax = mp[3 * NGLL3_PADDED]; m.etay = mp[4 * NGLL3_PADDED]; m.etaz = mp[5 * NGLL3_PADDED];
+    m.gammax = mp[6 * NGLL3_PADDED]; m.gammay = mp[7 * NGLL3_PADDED]; m.gammaz = mp[8 * NGLL3_PADDED];
+  }
+  __syncthreads();
+
+  // gradient in the reference element
+  realw t1x = 0.f, t2x = 0.f, t3x = 0.f, t1y = 0.f, t2y = 0.f, t3y = 0.f, t1z = 0.f, t2z = 0.f, t3z = 0.f;
+#pragma unroll
+  for (int l = 0; l < NGLLX; ++l) {
+    const realw h1 = s_hp[l * NGLLX + I], h2 = s_hp[l * NGLLX + J], h3 = s_hp[l * NGLLX + K];
+    const int o1 = K * NGLL2 + J * NGLLX + l, o2 = K * NGLL2 + l * NGLLX + I, o3 = l * NGLL2 + J * NGLLX + I;
+    t1x += s_x[o1] * h1; t1y += s_y[o1] * h1; t1z += s_z[o1] * h1;
+    t2x += s_x[o2] * h2; t2y += s_y[o2] * h2; t2z += s_z[o2] * h2;
+    t3x += s_x[o3] * h3; t3y += s_y[o3] * h3; t3z += s_z[o3] * h3;
+  }
+  realw duxdxl, duxdyl, duxdzl, duydxl, duydyl, duydzl, duzdxl, duzdyl, duzdzl, jacobianl;
+  if (irr >= 0) {
+    duxdxl = m.xix * t1x + m.etax * t2x + m.gammax * t3x;
+    duxdyl = m.xiy * t1x + m.etay * t2x + m.gammay * t3x;
+    duxdzl = m.xiz * t1x + m.etaz * t2x + m.gammaz * t3x;
+    duydxl = m.xix * t1y + m.etax * t2y + m.gammax * t3y;
+    duydyl = m.xiy * t1y + m.etay * t2y + m.gammay * t3y;
+    duydzl = m.xiz * t1y + m.etaz * t2y + m.gammaz * t3y;
+    duzdxl = m.xix * t1z + m.etax * t2z + m.gammax * t3z;
+    duzdyl = m.xiy * t1z + m.etay * t2z + m.gammay * t3z;
+    duzdzl = m.xiz * t1z + m.etaz * t2z + m.gammaz * t3z;
+    jacobianl = jacobian_of(m);
+  } else {
+    duxdxl = a.xix_regular * t1x; duxdyl = a.xix_regular * t2x; duxdzl = a.xix_regular * t3x;
+    duydxl = a.xix_regular * t1y; duydyl = a.xix_regular * t2y; duydzl = a.xix_regular * t3y;
+    duzdxl = a.xix_regular * t1z; duzdyl = a.xix_regular * t2z; duzdzl = a.xix_regular * t3z;
+    jacobianl = a.jacobian_regular;
+  }
+
+  // strain for attenuation / storage
+  realw e_xx = 0.f, e_yy = 0.f, e_xy = 0.f, e_xz = 0.f, e_yz = 0.f, e_tr = 0.f;
+  if (ATT) {
+    realw a1x = 0.f, a2x = 0.f, a3x = 0.f, a1y = 0.f, a2y = 0.f, a3y = 0.f, a1z = 0.f, a2z = 0.f, a3z = 0.f;
+#pragma unroll
+    for (int l = 0; l < NGLLX; ++l) {
+      const realw h1 = s_hp[l * NGLLX + I], h2 = s_hp[l * NGLLX + J], h3 = s_hp[l * NGLLX + K];
+      const int o1 = K * NGLL2 + J * NGLLX + l, o2 = K * NGLL2 + l * NGLLX + I, o3 = l * NGLL2 + J * NGLLX + I;
+      a1x += s_ax[o1] * h1; a1y += s_ay[o1] * h1; a1z += s_az[o1] * h1;
+      a2x += s_ax[o2] * h2; a2y += s_ay[o2] * h2; a2z += s_az[o2] * h2;
+      a3x += s_ax[o3] * h3; a3y += s_ay[o3] * h3; a3z += s_az[o3] * h3;
+    }
+    realw dxx, dxy, dxz, dyx, dyy, dyz, dzx, dzy, dzz;
+    if (irr >= 0) {
+      dxx = m.xix * a1x + m.etax * a2x + m.gammax * a3x; dxy = m.xiy * a1x + m.etay * a2x + m.gammay * a3x;
+      dxz = m.xiz * a1x + m.etaz * a2x + m.gammaz * a3x; dyx = m.xix * a1y + m.etax * a2y + m.gammax * a3y;
+      dyy = m.xiy * a1y + m.etay * a2y + m.gammay * a3y; dyz = m.xiz * a1y + m.etaz * a2y + m.gammaz * a3y;
+      dzx = m.xix * a1z + m.etax * a2z + m.gammax * a3z; dzy = m.xiy * a1z + m.etay * a2z + m.gammay * a3z;
+      dzz = m.xiz * a1z + m.etaz * a2z + m.gammaz * a3z;
+    } else {
+      dxx = a.xix_regular * a1x; dxy = a.xix_regular * a2x; dxz = a.xix_regular * a3x;
+      dyx = a.xix_regular * a1y; dyy = a.xix_regular * a2y; dyz = a.xix_regular * a3y;
+      dzx = a.xix_regular * a1z; dzy = a.xix_regular * a2z; dzz = a.xix_regular * a3z;
+    }
+    e_tr = dxx + dyy + dzz;
+    const realw templ = 0.33333333333333333333f * e_tr;
+    e_xx = dxx - templ; e_yy = dyy - templ;
+    e_xy = 0.5f * (dxy + dyx); e_xz = 0.5f * (dzx + dxz); e_yz = 0.5f * (dzy + dyz);
+  } else if (STRAIN) {
+    e_tr = duxdxl + duydyl + duzdzl;
+    const realw templ = 0.33333333333333333333f * e_tr;
+    e_xx = duxdxl - templ; e_yy = duydyl - templ;
+    e_xy = 0.5f * (duxdyl + duydxl); e_xz = 0.5f * (duzdxl + duxdzl); e_yz = 0.5f * (duzdyl + duydzl);
+  }
+
+  // isotropic stress
+  const realw lambdalplus2mul = kappal + 1.33333333333333333333f * mul;
+  const realw lambdal = lambdalplus2mul - 2.0f * mul;
+  realw sigma_xx = lambdalplus2mul * duxdxl + lambdal * (duydyl + duzdzl);
+  realw sigma_yy = lambdalplus2mul * duydyl + lambdal * (duxdxl + duzdzl);
+  realw sigma_zz = lambdalplus2mul * duzdzl + lambdal * (duxdxl + duydyl);
+  realw sigma_xy = mul * (duxdyl + duydxl);
+  realw sigma_xz = mul * (duzdxl + duxdzl);
+  realw sigma_yz = mul * (duzdyl + duydzl);
+
+  realw Rxx[N_SLS], Ryy[N_SLS], Rxy[N_SLS], Rxz[N_SLS], Ryz[N_SLS], Rtr[N_SLS];
+  const size_t roff = (size_t)ispec * N_SLS * NGLL3_PADDED + t;
+  if (ATT) {
+    realw sxx = 0.f, syy = 0.f, sxy = 0.f, sxz = 0.f, syz = 0.f, str = 0.f;
+#pragma unroll
+    for (int s = 0; s < N_SLS; ++s) {
+      Rtr[s] = a.R_trace[roff + s * NGLL3_PADDED]; str += Rtr[s];
+      Rxx[s] = a.R_xx[roff + s * NGLL3_PADDED]; sxx += Rxx[s];
+      Ryy[s] = a.R_yy[roff + s * NGLL3_PADDED]; syy += Ryy[s];
+      Rxy[s] = a.R_xy[roff + s * NGLL3_PADDED]; sxy += Rxy[s];
+      Rxz[s] = a.R_xz[roff + s * NGLL3_PADDED]; sxz += Rxz[s];
+      Ryz[s] = a.R_yz[roff + s * NGLL3_PADDED]; syz += Ryz[s];
+    }
+    sigma_xx = sigma_xx - sxx - str;
+    sigma_yy = sigma_yy - syy - str;
+    sigma_zz = sigma_zz + sxx + syy - str;
+    sigma_xy = sigma_xy - sxy;
+    sigma_xz = sigma_xz - sxz;
+    sigma_yz = sigma_yz - syz;
+  }
+
+  // weak form: three cut planes, reusing the displacement tiles
+  realw f1x, f1y, f1z, f2x, f2y, f2z, f3x, f3y, f3z;
+  if (irr >= 0) {
+    f1x = jacobianl * (sigma_xx * m.xix + sigma_xy * m.xiy + sigma_xz * m.xiz);
+    f1y = jacobianl * (sigma_xy * m.xix + sigma_yy * m.xiy + sigma_yz * m.xiz);
+    f1z = jacobianl * (sigma_xz * m.xix + sigma_yz * m.xiy + sigma_zz * m.xiz);
+    f2x = jacobianl * (sigma_xx * m.etax + sigma_xy * m.etay + sigma_xz * m.etaz);
+    f2y = jacobianl * (sigma_xy * m.etax + sigma_yy * m.etay + sigma_yz * m.etaz);
+    f2z = jacobianl * (sigma_xz * m.etax + sigma_yz * m.etay + sigma_zz * m.etaz);
+    f3x = jacobianl * (sigma_xx * m.gammax + sigma_xy * m.gammay + sigma_xz * m.gammaz);
+    f3y = jacobianl * (sigma_xy * m.gammax + sigma_yy * m.gammay + sigma_yz * m.gammaz);
+    f3z = jacobianl * (sigma_xz * m.gammax + sigma_yz * m.gammay + sigma_zz * m.gammaz);
+  } else {
+    const realw f = jacobianl * a.xix_regular;
+    f1x = f * sigma_xx; f1y = f * sigma_xy; f1z = f * sigma_xz;
+    f2x = f * sigma_xy; f2y = f * sigma_yy; f2z = f * sigma_yz;
+    f3x = f * sigma_xz; f3y = f * sigma_yz; f3z = f * sigma_zz;
+  }
+
+  realw n1x = 0.f, n1y = 0.f, n1z = 0.f, n2x = 0.f, n2y = 0.f, n2z = 0.f, n3x = 0.f, n3y = 0.f, n3z = 0.f;
+  __syncthreads();
+  s_x[t] = f1x; s_y[t] = f1y; s_z[t] = f1z;
+  __syncthreads();
+#pragma unroll
+  for (int l = 0; l < NGLLX; ++l) {
+    const realw h = s_hw[I * NGLLX + l];
+    const int o = K * NGLL2 + J * NGLLX + l;
+    n1x += s_x[o] * h; n1y += s_y[o] * h; n1z += s_z[o] * h;
+  }
+  __syncthreads();
+  s_x[t] = f2x; s_y[t] = f2y; s_z[t] = f2z;
+  __syncthreads();
+#pragma unroll
+  for (int l = 0; l < NGLLX; ++l) {
+    const realw h = s_hw[J * NGLLX + l];
+    const int o = K * NGLL2 + l * NGLLX + I;
+    n2x += s_x[o] * h; n2y += s_y[o] * h; n2z += s_z[o] * h;
+  }
+  __syncthreads();
+  s_x[t] = f3x; s_y[t] = f3y; s_z[t] = f3z;
+  __syncthreads();
+#pragma unroll
+  for (int l = 0; l < NGLLX; ++l) {
+    const realw h = s_hw[K * NGLLX + l];
+    const int o = l * NGLL2 + J * NGLLX + I;
+    n3x += s_x[o] * h; n3y += s_y[o] * h; n3z += s_z[o] * h;
+  }
+
+  const realw fac1 = c_wgllwgll_yz[K * NGLLX + J], fac2 = c_wgllwgll_xz[K * NGLLX + I], fac3 = c_wgllwgll_xy[J * NGLLX + I];
+  const realw sum1 = -(fac1 * n1x + fac2 * n2x + fac3 * n3x);
+  const realw sum2 = -(fac1 * n1y + fac2 * n2y + fac3 * n3y);
+  const realw sum3 = -(fac1 * n1z + fac2 * n2z + fac3 * n3z);
+
+  if (active) {
+    realw* acc = a.accel + 3 * (size_t)iglob;
+    if (a.use_atomics) {
+      red_add(acc, sum1); red_add(acc + 1, sum2); red_add(acc + 2, sum3);
+    } else {
+      acc[0] += sum1; acc[1] += sum2; acc[2] += sum3;
+    }
+    if (ATT) {
+      // second-order Runge-Kutta update of the memory variables (compute_element_att_memory.f90:112-152)
+      const realw Sn_tr = a.eps_trace[off], Sn_xx = a.eps_xx[off], Sn_yy = a.eps_yy[off], Sn_xy = a.eps_xy[off],
+                  Sn_xz = a.eps_xz[off], Sn_yz = a.eps_yz[off];
+#pragma unroll
+      for (int s = 0; s < N_SLS; ++s) {
+        const realw al = c_alphaval[s], be = c_betaval[s], ga = c_gammaval[s];
+        realw fl = kappal * a.factor_common_kappa[roff + s * NGLL3_PADDED];
+        a.R_trace[roff + s * NGLL3_PADDED] = al * Rtr[s] + fl * (be * Sn_tr + ga * e_tr);
+        fl = mul * a.factor_common[roff + s * NGLL3_PADDED];
+        a.R_xx[roff + s * NGLL3_PADDED] = al * Rxx[s] + fl * (be * Sn_xx + ga * e_xx);
+        a.R_yy[roff + s * NGLL3_PADDED] = al * Ryy[s] + fl * (be * Sn_yy + ga * e_yy);
+        a.R_xy[roff + s * NGLL3_PADDED] = al * Rxy[s] + fl * (be * Sn_xy + ga * e_xy);
+        a.R_xz[roff + s * NGLL3_PADDED] = al * Rxz[s] + fl * (be * Sn_xz + ga * e_xz);
+        a.R_yz[roff + s * NGLL3_PADDED] = al * Ryz[s] + fl * (be * Sn_yz + ga * e_yz);
+      }
+    }
+    if (ATT || STRAIN) {
+      if (ATT) a.eps_trace[off] = e_tr;
+      a.eps_xx[off] = e_xx; a.eps_yy[off] = e_yy; a.eps_xy[off] = e_xy; a.eps_xz[off] = e_xz; a.eps_yz[off] = e_yz;
+    }
+  }
+}
+
+}  // namespace sb200

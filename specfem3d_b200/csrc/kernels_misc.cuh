@@ -1,0 +1,397 @@
+// kernels_misc.cuh -- time integration, boundary, source/receiver, halo and norm kernels
+// (SURVEY.md section 8 rows a5-a12).  Each kernel cites the reference kernel it replaces and the CPU routine whose
+// arithmetic it follows.
+#pragma once
+#include "kernels_common.cuh"
+
+namespace sb200 {
+
+// ---------------------------------------------------------------------------------------------------------------
+// Newmark predictor (replaces UpdateDispVeloc_kernel, src/gpu/kernels/UpdateDispVeloc_kernel.cu:30-60;
+// CPU: update_displ_elastic, update_displacement_scheme.f90:359-410).  Pure stream, 24 B per DOF: vectorised
+// float4 grid-stride loop; `n` is the flat length (3*NGLOB elastic, NGLOB acoustic).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_newmark_predictor(realw* __restrict__ displ, realw* __restrict__ veloc,
+                                                           realw* __restrict__ accel, long long n, realw deltat,
+                                                           realw deltatsqover2, realw deltatover2) {
+  const long long n4 = n >> 2;
+  float4* d4 = reinterpret_cast<float4*>(displ);
+  float4* v4 = reinterpret_cast<float4*>(veloc);
+  float4* a4 = reinterpret_cast<float4*>(accel);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 d = d4[i], v = v4[i];
+    const float4 a = a4[i];
+    d.x = d.x + deltat * v.x + deltatsqover2 * a.x; d.y = d.y + deltat * v.y + deltatsqover2 * a.y;
+    d.z = d.z + deltat * v.z + deltatsqover2 * a.z; d.w = d.w + deltat * v.w + deltatsqover2 * a.w;
+    v.x = v.x + deltatover2 * a.x; v.y = v.y + deltatover2 * a.y;
+    v.z = v.z + deltatover2 * a.z; v.w = v.w + deltatover2 * a.w;
+    d4[i] = d; v4[i] = v; a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // tail (n not a multiple of 4)
+  const long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const realw a = accel[i];
+    displ[i] = displ[i] + deltat * veloc[i] + deltatsqover2 * a;
+    veloc[i] = veloc[i] + deltatover2 * a;
+    accel[i] = 0.f;
+  }
+}
+
+// Corrector (replaces kernel_3_cuda_device, src/gpu/kernels/kernel_3_cuda_device.cu:30-58; CPU:
+// compute_forces_viscoelastic_calling_routine.F90:371-375 + update_veloc_elastic).  rmass3 is the library's own
+// interleaved copy of (rmassx,rmassy,rmassz) so the kernel is a flat stream: accel *= rmass3; veloc += dt/2 accel.
+__global__ void __launch_bounds__(256) k_newmark_corrector(realw* __restrict__ veloc, realw* __restrict__ accel,
+                                                           const realw* __restrict__ rmass3, long long n,
+                                                           realw deltatover2, int update_veloc) {
+  const long long n4 = n >> 2;
+  float4* v4 = reinterpret_cast<float4*>(veloc);
+  float4* a4 = reinterpret_cast<float4*>(accel);
+  const float4* r4 = reinterpret_cast<const float4*>(rmass3);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 a = a4[i];
+    const float4 r = __ldg(r4 + i);
+    a.x *= r.x; a.y *= r.y; a.z *= r.z; a.w *= r.w;
+    a4[i] = a;
+    if (update_veloc) {
+      float4 v = v4[i];
+      v.x += deltatover2 * a.x; v.y += deltatover2 * a.y; v.z += deltatover2 * a.z; v.w += deltatover2 * a.w;
+      v4[i] = v;
+    }
+  }
+  const long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const realw a = accel[i] * rmass3[i];
+    accel[i] = a;
+    if (update_veloc) veloc[i] += deltatover2 * a;
+  }
+}
+
+// veloc += dt/2 * accel only (kernel_3_veloc_cuda_device, used by kernel_3_b_cuda after the ocean-load correction)
+__global__ void __launch_bounds__(256) k_newmark_veloc_only(realw* __restrict__ veloc, const realw* __restrict__ accel,
+                                                            long long n, realw deltatover2) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    veloc[i] += deltatover2 * accel[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Stacey absorbing boundary, elastic (replaces compute_stacey_elastic_kernel, src/gpu/kernels/
+// compute_stacey_elastic_kernel.cu:30-105; CPU: compute_stacey_viscoelastic.F90:32-202).  One block of 32 threads
+// per face (25 active).  b_absorb_field != nullptr stores the traction (SAVE_FORWARD).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_stacey_elastic(const realw* __restrict__ veloc, realw* accel,
+                                                       const int* __restrict__ abs_ispec, const int* __restrict__ abs_ijk,
+                                                       const realw* __restrict__ abs_normal,
+                                                       const realw* __restrict__ abs_jac2Dw, const int* __restrict__ ibool,
+                                                       const realw* __restrict__ rho_vp, const realw* __restrict__ rho_vs,
+                                                       const int* __restrict__ ispec_is_elastic, int num_faces,
+                                                       realw* b_absorb_field) {
+  const int iface = blockIdx.x, igll = threadIdx.x;
+  if (iface >= num_faces || igll >= NGLL2) return;
+  const int ispec = abs_ispec[iface] - 1;
+  if (!ispec_is_elastic[ispec]) return;
+  const int* ijk = abs_ijk + 3 * (igll + NGLL2 * (size_t)iface);
+  const int p = (ijk[0] - 1) + NGLLX * (ijk[1] - 1) + NGLL2 * (ijk[2] - 1);
+  const size_t iglob = (size_t)ibool[(size_t)ispec * NGLL3_PADDED + p] - 1;
+  const realw vx = veloc[3 * iglob], vy = veloc[3 * iglob + 1], vz = veloc[3 * iglob + 2];
+  const realw* nrm = abs_normal + 3 * (igll + NGLL2 * (size_t)iface);
+  const realw nx = nrm[0], ny = nrm[1], nz = nrm[2];
+  const realw vn = vx * nx + vy * ny + vz * nz;
+  const realw rvp = rho_vp[(size_t)ispec * NGLL3 + p], rvs = rho_vs[(size_t)ispec * NGLL3 + p];
+  const realw tx = rvp * vn * nx + rvs * (vx - vn * nx);
+  const realw ty = rvp * vn * ny + rvs * (vy - vn * ny);
+  const realw tz = rvp * vn * nz + rvs * (vz - vn * nz);
+  const realw jw = abs_jac2Dw[igll + NGLL2 * (size_t)iface];
+  red_add(accel + 3 * iglob, -tx * jw);
+  red_add(accel + 3 * iglob + 1, -ty * jw);
+  red_add(accel + 3 * iglob + 2, -tz * jw);
+  if (b_absorb_field) {
+    realw* b = b_absorb_field + 3 * (igll + NGLL2 * (size_t)iface);
+    b[0] = tx * jw; b[1] = ty * jw; b[2] = tz * jw;
+  }
+}
+
+// Stacey, acoustic (replaces compute_stacey_acoustic_kernel; CPU: compute_stacey_acoustic.f90:30-110)
+__global__ void __launch_bounds__(32) k_stacey_acoustic(const realw* __restrict__ potential_dot, realw* potential_dot_dot,
+                                                        const int* __restrict__ abs_ispec, const int* __restrict__ abs_ijk,
+                                                        const realw* __restrict__ abs_jac2Dw, const int* __restrict__ ibool,
+                                                        const realw* __restrict__ rhostore /*[128]*/,
+                                                        const realw* __restrict__ kappastore /*[125]*/,
+                                                        const int* __restrict__ ispec_is_acoustic, int num_faces,
+                                                        realw* b_absorb_potential) {
+  const int iface = blockIdx.x, igll = threadIdx.x;
+  if (iface >= num_faces || igll >= NGLL2) return;
+  const int ispec = abs_ispec[iface] - 1;
+  if (!ispec_is_acoustic[ispec]) return;
+  const int* ijk = abs_ijk + 3 * (igll + NGLL2 * (size_t)iface);
+  const int p = (ijk[0] - 1) + NGLLX * (ijk[1] - 1) + NGLL2 * (ijk[2] - 1);
+  const size_t iglob = (size_t)ibool[(size_t)ispec * NGLL3_PADDED + p] - 1;
+  const realw rhol = rhostore[(size_t)ispec * NGLL3_PADDED + p];
+  const realw cpl = sqrtf(kappastore[(size_t)ispec * NGLL3 + p] / rhol);
+  const realw jw = abs_jac2Dw[igll + NGLL2 * (size_t)iface];
+  const realw absorbl = potential_dot[iglob] * jw / cpl / rhol;
+  red_add(potential_dot_dot + iglob, -absorbl);
+  if (b_absorb_potential) b_absorb_potential[igll + NGLL2 * (size_t)iface] = absorbl;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fluid-solid coupling (replaces compute_coupling_acoustic_el_kernel / compute_coupling_elastic_ac_kernel;
+// CPU: compute_coupling_acoustic_el.f90, compute_coupling_viscoelastic_ac.f90), forward simulation, no PML.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_coupling_ac_el(const realw* __restrict__ displ, realw* potential_dot_dot,
+                                                       int num_faces, const int* __restrict__ c_ispec,
+                                                       const int* __restrict__ c_ijk, const realw* __restrict__ c_normal,
+                                                       const realw* __restrict__ c_jac2Dw, const int* __restrict__ ibool) {
+  const int iface = blockIdx.x, igll = threadIdx.x;
+  if (iface >= num_faces || igll >= NGLL2) return;
+  const int ispec = c_ispec[iface] - 1;
+  const int* ijk = c_ijk + 3 * (igll + NGLL2 * (size_t)iface);
+  const int p = (ijk[0] - 1) + NGLLX * (ijk[1] - 1) + NGLL2 * (ijk[2] - 1);
+  const size_t iglob = (size_t)ibool[(size_t)ispec * NGLL3_PADDED + p] - 1;
+  const realw* n = c_normal + 3 * (igll + NGLL2 * (size_t)iface);
+  const realw displ_n = displ[3 * iglob] * n[0] + displ[3 * iglob + 1] * n[1] + displ[3 * iglob + 2] * n[2];
+  red_add(potential_dot_dot + iglob, c_jac2Dw[igll + NGLL2 * (size_t)iface] * displ_n);
+}
+
+__global__ void __launch_bounds__(32) k_coupling_el_ac(const realw* __restrict__ potential_dot_dot, realw* accel,
+                                                       int num_faces, const int* __restrict__ c_ispec,
+                                                       const int* __restrict__ c_ijk, const realw* __restrict__ c_normal,
+                                                       const realw* __restrict__ c_jac2Dw, const int* __restrict__ ibool) {
+  const int iface = blockIdx.x, igll = threadIdx.x;
+  if (iface >= num_faces || igll >= NGLL2) return;
+  const int ispec = c_ispec[iface] - 1;
+  const int* ijk = c_ijk + 3 * (igll + NGLL2 * (size_t)iface);
+  const int p = (ijk[0] - 1) + NGLLX * (ijk[1] - 1) + NGLL2 * (ijk[2] - 1);
+  const size_t iglob = (size_t)ibool[(size_t)ispec * NGLL3_PADDED + p] - 1;
+  const realw* n = c_normal + 3 * (igll + NGLL2 * (size_t)iface);
+  const realw pressure = -potential_dot_dot[iglob];
+  const realw jw = c_jac2Dw[igll + NGLL2 * (size_t)iface];
+  red_add(accel + 3 * iglob, jw * n[0] * pressure);
+  red_add(accel + 3 * iglob + 1, jw * n[1] * pressure);
+  red_add(accel + 3 * iglob + 2, jw * n[2] * pressure);
+}
+
+// acoustic free surface: zero the potential and its derivatives (replaces enforce_free_surface_cuda_kernel,
+// src/gpu/kernels/enforce_free_surface_cuda_kernel.cu:30-67)
+__global__ void __launch_bounds__(32) k_enforce_free_surface(realw* pot, realw* pot_dot, realw* pot_dot_dot, int num_faces,
+                                                             const int* __restrict__ fs_ispec, const int* __restrict__ fs_ijk,
+                                                             const int* __restrict__ ibool,
+                                                             const int* __restrict__ ispec_is_acoustic) {
+  const int iface = blockIdx.x, igll = threadIdx.x;
+  if (iface >= num_faces || igll >= NGLL2) return;
+  const int ispec = fs_ispec[iface] - 1;
+  if (!ispec_is_acoustic[ispec]) return;
+  const int* ijk = fs_ijk + 3 * (igll + NGLL2 * (size_t)iface);
+  const int p = (ijk[0] - 1) + NGLLX * (ijk[1] - 1) + NGLL2 * (ijk[2] - 1);
+  const size_t iglob = (size_t)ibool[(size_t)ispec * NGLL3_PADDED + p] - 1;
+  pot[iglob] = 0.f; pot_dot[iglob] = 0.f; pot_dot_dot[iglob] = 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// sources (replaces compute_add_sources_kernel / compute_add_sources_acoustic_kernel;
+// CPU: compute_add_sources_viscoelastic.F90:98-150, compute_add_sources_acoustic.f90:60-110).
+// sourcearrays keeps the Fortran layout (NSOURCES,3,5,5,5); stf was cast double->float on the host.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NGLL3_PADDED) k_add_sources_el(realw* accel, const int* __restrict__ ibool,
+                                                                  const realw* __restrict__ sourcearrays,
+                                                                  const realw* __restrict__ stf_pre_compute, int myrank,
+                                                                  const int* __restrict__ islice_selected_source,
+                                                                  const int* __restrict__ ispec_selected_source,
+                                                                  const int* __restrict__ ispec_is_elastic, int NSOURCES) {
+  const int isrc = blockIdx.x, p = threadIdx.x;
+  if (isrc >= NSOURCES || p >= NGLL3) return;
+  if (islice_selected_source[isrc] != myrank) return;
+  const int ispec = ispec_selected_source[isrc] - 1;
+  if (!ispec_is_elastic[ispec]) return;
+  const size_t iglob = (size_t)ibool[(size_t)ispec * NGLL3_PADDED + p] - 1;
+  const realw stf = stf_pre_compute[isrc];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) red_add(accel + 3 * iglob + c, sourcearrays[isrc + (size_t)NSOURCES * (c + 3 * p)] * stf);
+}
+
+__global__ void __launch_bounds__(NGLL3_PADDED) k_add_sources_ac(realw* potential_dot_dot, const int* __restrict__ ibool,
+                                                                  const realw* __restrict__ sourcearrays,
+                                                                  const realw* __restrict__ stf_pre_compute, int myrank,
+                                                                  const int* __restrict__ islice_selected_source,
+                                                                  const int* __restrict__ ispec_selected_source,
+                                                                  const int* __restrict__ ispec_is_acoustic,
+                                                                  const realw* __restrict__ kappastore /*[125]*/, int NSOURCES) {
+  const int isrc = blockIdx.x, p = threadIdx.x;
+  if (isrc >= NSOURCES || p >= NGLL3) return;
+  if (islice_selected_source[isrc] != myrank) return;
+  const int ispec = ispec_selected_source[isrc] - 1;
+  if (!ispec_is_acoustic[ispec]) return;
+  const size_t iglob = (size_t)ibool[(size_t)ispec * NGLL3_PADDED + p] - 1;
+  const realw stf = stf_pre_compute[isrc];
+  red_add(potential_dot_dot + iglob, -sourcearrays[isrc + (size_t)NSOURCES * (0 + 3 * p)] * stf / kappastore[(size_t)ispec * NGLL3 + p]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// seismograms (replaces compute_elastic_seismogram_kernel / compute_acoustic_seismogram_kernel;
+// CPU: compute_interpolated_dva.f90:28-95 + rotation compute_seismograms.f90:238-260).
+// One block of 128 threads per local receiver; warp-shuffle tree instead of the reference's shared-memory tree.
+// In a fluid element the vector field is grad(potential)/rho (compute_gradient_kernel.h).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ realw block_sum_128(realw v, realw* s_red /*[4]*/) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  const realw r = s_red[0] + s_red[1] + s_red[2] + s_red[3];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(NGLL3_PADDED) k_seismogram_vector(
+    int nrec_local, const realw* __restrict__ field, const realw* __restrict__ potential, const int* __restrict__ ibool,
+    const realw* __restrict__ hxir, const realw* __restrict__ hetar, const realw* __restrict__ hgammar,
+    realw* seismograms, const realw* __restrict__ nu_rec, const int* __restrict__ ispec_selected_rec_loc,
+    const int* __restrict__ ispec_is_elastic, const int* __restrict__ ispec_is_acoustic,
+    const realw* __restrict__ rhostore, const realw* __restrict__ metric, const int* __restrict__ irregular_element_number,
+    realw xix_regular, int seismo_current) {
+  const int irec = blockIdx.x;
+  if (irec >= nrec_local) return;
+  const int tx = threadIdx.x;
+  const bool active = tx < NGLL3;
+  const int t = active ? tx : NGLL3 - 1;
+  const int K = t / NGLL2, J = (t - K * NGLL2) / NGLLX, I = t - K * NGLL2 - J * NGLLX;
+  __shared__ realw s_chi[NGLL3_PADDED];
+  __shared__ realw s_red[4];
+  const int ispec = ispec_selected_rec_loc[irec] - 1;
+  const size_t off = (size_t)ispec * NGLL3_PADDED + t;
+  const size_t iglob = (size_t)ibool[off] - 1;
+  const realw hl = active ? hxir[I + NGLLX * irec] * hetar[J + NGLLX * irec] * hgammar[K + NGLLX * irec] : 0.f;
+  realw dx = 0.f, dy = 0.f, dz = 0.f;
+  if (ispec_is_elastic[ispec]) {
+    dx = hl * field[3 * iglob]; dy = hl * field[3 * iglob + 1]; dz = hl * field[3 * iglob + 2];
+  } else if (ispec_is_acoustic[ispec] && potential != nullptr) {
+    s_chi[t] = potential[iglob];
+    __syncthreads();
+    realw t1 = 0.f, t2 = 0.f, t3 = 0.f;
+#pragma unroll
+    for (int l = 0; l < NGLLX; ++l) {
+      t1 += s_chi[K * NGLL2 + J * NGLLX + l] * c_hprime_xx[l * NGLLX + I];
+      t2 += s_chi[K * NGLL2 + l * NGLLX + I] * c_hprime_xx[l * NGLLX + J];
+      t3 += s_chi[l * NGLL2 + J * NGLLX + I] * c_hprime_xx[l * NGLLX + K];
+    }
+    const realw rho_inv = 1.0f / rhostore[off];
+    const int irr = irregular_element_number[ispec] - 1;
+    realw gx, gy, gz;
+    if (irr >= 0) {
+      const realw* mp = metric + (size_t)irr * 9 * NGLL3_PADDED + t;
+      gx = mp[0] * t1 + mp[3 * NGLL3_PADDED] * t2 + mp[6 * NGLL3_PADDED] * t3;
+      gy = mp[NGLL3_PADDED] * t1 + mp[4 * NGLL3_PADDED] * t2 + mp[7 * NGLL3_PADDED] * t3;
+      gz = mp[2 * NGLL3_PADDED] * t1 + mp[5 * NGLL3_PADDED] * t2 + mp[8 * NGLL3_PADDED] * t3;
+    } else {
+      gx = xix_regular * t1; gy = xix_regular * t2; gz = xix_regular * t3;
+    }
+    dx = hl * gx * rho_inv; dy = hl * gy * rho_inv; dz = hl * gz * rho_inv;
+  }
+  dx = block_sum_128(dx, s_red);
+  dy = block_sum_128(dy, s_red);
+  dz = block_sum_128(dz, s_red);
+  if (tx < 3) {
+    const realw* nu = nu_rec + NDIM * NDIM * irec;  // nu(a,b) at [a + 3*b]
+    seismograms[tx + NDIM * (irec + (size_t)nrec_local * seismo_current)] = nu[tx] * dx + nu[tx + 3] * dy + nu[tx + 6] * dz;
+  }
+}
+
+// pressure seismogram: fluid element p = -potential_dot_dot (or potential with USE_TRICK_FOR_BETTER_PRESSURE);
+// solid element p = -kappa * div(u) is out of this round's scope (reference: compute_acoustic_seismogram_kernel.cu)
+__global__ void __launch_bounds__(NGLL3_PADDED) k_seismogram_pressure(
+    int nrec_local, const realw* __restrict__ potential, const int* __restrict__ ibool, const realw* __restrict__ hxir,
+    const realw* __restrict__ hetar, const realw* __restrict__ hgammar, realw* seismograms_p,
+    const int* __restrict__ ispec_selected_rec_loc, const int* __restrict__ ispec_is_acoustic, int seismo_current) {
+  const int irec = blockIdx.x;
+  if (irec >= nrec_local) return;
+  const int tx = threadIdx.x;
+  const bool active = tx < NGLL3;
+  const int t = active ? tx : NGLL3 - 1;
+  const int K = t / NGLL2, J = (t - K * NGLL2) / NGLLX, I = t - K * NGLL2 - J * NGLLX;
+  __shared__ realw s_red[4];
+  const int ispec = ispec_selected_rec_loc[irec] - 1;
+  realw v = 0.f;
+  if (ispec_is_acoustic[ispec] && active) {
+    const size_t iglob = (size_t)ibool[(size_t)ispec * NGLL3_PADDED + t] - 1;
+    v = -potential[iglob] * hxir[I + NGLLX * irec] * hetar[J + NGLLX * irec] * hgammar[K + NGLLX * irec];
+  }
+  v = block_sum_128(v, s_red);
+  if (tx == 0) seismograms_p[irec + (size_t)nrec_local * seismo_current] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// halo pack / unpack (replaces prepare_boundary_accel_on_device / assemble_boundary_accel_on_device and the
+// potential twins; CPU: assemble_MPI_vector.f90:243-384).  Buffer layout is the Fortran one:
+// buffer(NCOMP, max_nibool, num_interfaces).  One thread per (interface, point): 2-D grid.
+// ---------------------------------------------------------------------------------------------------------------
+template <int NCOMP>
+__global__ void __launch_bounds__(256) k_halo_pack(const realw* __restrict__ field, realw* __restrict__ buffer,
+                                                   int num_interfaces, int max_nibool, const int* __restrict__ nibool,
+                                                   const int* __restrict__ ibool_interfaces) {
+  const int ipoin = blockIdx.x * blockDim.x + threadIdx.x;
+  const int iface = blockIdx.y;
+  if (iface >= num_interfaces || ipoin >= nibool[iface]) return;
+  const size_t slot = ipoin + (size_t)max_nibool * iface;
+  const size_t iglob = (size_t)ibool_interfaces[slot] - 1;
+#pragma unroll
+  for (int c = 0; c < NCOMP; ++c) buffer[NCOMP * slot + c] = field[NCOMP * iglob + c];
+}
+
+template <int NCOMP>
+__global__ void __launch_bounds__(256) k_halo_unpack_add(realw* field, const realw* __restrict__ buffer, int num_interfaces,
+                                                         int max_nibool, const int* __restrict__ nibool,
+                                                         const int* __restrict__ ibool_interfaces) {
+  const int ipoin = blockIdx.x * blockDim.x + threadIdx.x;
+  const int iface = blockIdx.y;
+  if (iface >= num_interfaces || ipoin >= nibool[iface]) return;
+  const size_t slot = ipoin + (size_t)max_nibool * iface;
+  const size_t iglob = (size_t)ibool_interfaces[slot] - 1;
+#pragma unroll
+  for (int c = 0; c < NCOMP; ++c) red_add(field + NCOMP * iglob + c, buffer[NCOMP * slot + c]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// norms for check_stability (replaces get_maximum_vector_kernel / get_maximum_field_kernel,
+// src/gpu/kernels/get_maximum_vector_kernel.cu): per-block maxima, final max on the host.
+// vector: max over points of (ux^2+uy^2+uz^2) (the wrapper takes the sqrt); scalar: max |x|.
+// ---------------------------------------------------------------------------------------------------------------
+template <bool VECTOR>
+__global__ void __launch_bounds__(256) k_max_norm(const realw* __restrict__ f, long long npoints, realw* __restrict__ partial) {
+  realw m = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npoints; i += stride) {
+    realw v;
+    if (VECTOR) {
+      const realw x = f[3 * i], y = f[3 * i + 1], z = f[3 * i + 2];
+      v = x * x + y * y + z * z;
+    } else {
+      v = fabsf(f[i]);
+    }
+    m = fmaxf(m, v);
+  }
+  __shared__ realw s[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_down_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    realw r = s[0];
+    for (int w = 1; w < 8; ++w) r = fmaxf(r, s[w]);
+    partial[blockIdx.x] = r;
+  }
+}
+
+// (sls, 125, nspec) host layout  <->  [nspec][sls][128] device planes, and [nspec][125] <-> [nspec][128]
+__global__ void k_relayout_sls_to_host(const realw* __restrict__ dev, realw* __restrict__ host_layout, long long nspec) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over nspec*125*N_SLS
+  if (i >= nspec * NGLL3 * N_SLS) return;
+  const int s = (int)(i % N_SLS);
+  const long long r = i / N_SLS;
+  const int p = (int)(r % NGLL3);
+  const long long e = r / NGLL3;
+  host_layout[i] = dev[(e * N_SLS + s) * NGLL3_PADDED + p];
+}
+
+}  // namespace sb200

@@ -1,0 +1,152 @@
+"""Host-side plumbing of the halo exchange when every rank is its own process (torchrun, one rank per GPU).
+
+Two paths, selected by ``mode``:
+
+``host``  bit-compatible with the reference: the library packs into pinned host buffers, this module plays the role of
+          the Fortran ``isend_cr`` / ``irecv_cr`` / ``wait_req`` calls (src/specfem3D/assemble_MPI_vector.f90:700-749)
+          with ``torch.distributed`` (gloo, CPU tensors), the library unpacks.
+``p2p``   NVLink: at start-up the ranks exchange the CUDA-IPC handles of their receive slabs and the interface
+          geometry (hard part H3: neighbour ranks are not part of the reference ABI), then the library's pack kernel
+          stores directly into the neighbour GPU and nothing travels through the host any more.
+
+``torch.distributed`` is plumbing only (rendezvous + tiny metadata); no tensor of the hot path goes through it in
+``p2p`` mode.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List
+
+import numpy as np
+
+
+def assemble_scalar_distributed(db, arr: np.ndarray, group) -> None:
+    """assemble_MPI_scalar_blocking (src/specfem3D/assemble_MPI_scalar.f90:30-120) over torch.distributed."""
+    import torch
+    import torch.distributed as dist
+
+    sends, recvs, reqs = [], [], []
+    for n in range(db.num_interfaces_ext_mesh):
+        ids = db.ibool_interfaces_ext_mesh[n, : db.nibool_interfaces_ext_mesh[n]] - 1
+        s = torch.from_numpy(np.ascontiguousarray(arr[ids]))
+        r = torch.empty_like(s)
+        nb = int(db.my_neighbors_ext_mesh[n])
+        reqs.append(dist.isend(s, nb, group=group))
+        reqs.append(dist.irecv(r, nb, group=group))
+        sends.append(s)
+        recvs.append((ids, r))
+    for q in reqs:
+        q.wait()
+    for ids, r in recvs:
+        arr[ids] += r.numpy()
+
+
+class DistributedExchange:
+    """The exchange object used by :class:`specfem3d_b200.time_loop.DeviceRun` when it drives a single rank."""
+
+    def __init__(self, rank_obj, group, mode: str = "p2p"):
+        import torch.distributed as dist
+
+        self.r, self.group, self.mode = rank_obj, group, mode
+        self.world = dist.get_world_size()
+        if mode == "p2p":
+            self._connect()
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def _connect(self):
+        import torch
+        import torch.distributed as dist
+
+        r, db, L = self.r, self.r.db, self.r.lib
+        nif = db.num_interfaces_ext_mesh
+        handle = (ctypes.c_char * 64)()
+        words = ctypes.c_int(0)
+        L.cdll.specfem_b200_halo_p2p_local_info_(ctypes.byref(r.Mesh_pointer), handle, ctypes.byref(words))
+        dev = ctypes.c_int(0)
+        slab = ctypes.c_void_p(0)
+        L.cdll.specfem_b200_halo_p2p_local_pointer_(ctypes.byref(r.Mesh_pointer), ctypes.byref(slab), ctypes.byref(dev))
+        me = {"rank": r.rank, "handle": bytes(handle.raw), "device": int(dev.value), "nif": nif,
+              "max_nibool": int(db.max_nibool_interfaces_ext_mesh),
+              "neighbors": [int(v) for v in db.my_neighbors_ext_mesh[:nif]]}
+        allinfo = [None] * self.world
+        dist.all_gather_object(allinfo, me, group=self.group)
+        by_rank = {d["rank"]: d for d in allinfo}
+        handles = (ctypes.c_char * (64 * nif))()
+        geom = np.zeros(3 * nif, np.int32)
+        nbr = np.zeros(nif, np.int32)
+        nbdev = np.zeros(nif, np.int32)
+        same = np.zeros(nif, np.int32)
+        ptrs = (ctypes.c_void_p * nif)()
+        for n in range(nif):
+            d = by_rank[int(db.my_neighbors_ext_mesh[n])]
+            handles[64 * n: 64 * (n + 1)] = d["handle"]
+            geom[3 * n: 3 * n + 3] = (d["neighbors"].index(r.rank), d["nif"], d["max_nibool"])
+            nbr[n], nbdev[n] = d["rank"], d["device"]
+        L.cdll.specfem_b200_halo_p2p_connect_(ctypes.byref(r.Mesh_pointer), ctypes.byref(ctypes.c_int(nif)),
+                                               nbr.ctypes.data_as(ctypes.c_void_p), nbdev.ctypes.data_as(ctypes.c_void_p),
+                                               handles, geom.ctypes.data_as(ctypes.c_void_p),
+                                               same.ctypes.data_as(ctypes.c_void_p), ptrs)
+        dist.barrier(group=self.group)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def exchange(self, kind: str):
+        if self.mode == "p2p":
+            return  # the payload went GPU -> GPU inside the pack kernel
+        import torch
+        import torch.distributed as dist
+
+        r, db = self.r, self.r.db
+        send = r.buffer_send_vector if kind == "vector" else r.buffer_send_scalar
+        recv = r.buffer_recv_vector if kind == "vector" else r.buffer_recv_scalar
+        reqs, keep = [], []
+        for n in range(db.num_interfaces_ext_mesh):
+            cnt = int(db.nibool_interfaces_ext_mesh[n])
+            s = torch.from_numpy(send[n, :cnt])
+            t = torch.from_numpy(recv[n, :cnt])
+            nb = int(db.my_neighbors_ext_mesh[n])
+            reqs.append(dist.isend(s, nb, group=self.group))
+            reqs.append(dist.irecv(t, nb, group=self.group))
+            keep.append((s, t))
+        for q in reqs:
+            q.wait()
+
+
+def connect_p2p_in_process(ranks: List) -> None:
+    """All handles live in this process (tests, single-process multi-GPU): connect the slabs with plain pointers."""
+    info = {}
+    for r in ranks:
+        L = r.lib
+        handle = (ctypes.c_char * 64)()
+        words = ctypes.c_int(0)
+        L.cdll.specfem_b200_halo_p2p_local_info_(ctypes.byref(r.Mesh_pointer), handle, ctypes.byref(words))
+        dev = ctypes.c_int(0)
+        slab = ctypes.c_void_p(0)
+        L.cdll.specfem_b200_halo_p2p_local_pointer_(ctypes.byref(r.Mesh_pointer), ctypes.byref(slab), ctypes.byref(dev))
+        info[r.rank] = (slab.value, int(dev.value))
+    by_rank = {r.rank: r for r in ranks}
+    for r in ranks:
+        db, L = r.db, r.lib
+        nif = db.num_interfaces_ext_mesh
+        geom = np.zeros(3 * nif, np.int32)
+        nbr = np.zeros(nif, np.int32)
+        nbdev = np.zeros(nif, np.int32)
+        same = np.ones(nif, np.int32)
+        ptrs = (ctypes.c_void_p * nif)()
+        handles = (ctypes.c_char * (64 * nif))()
+        for n in range(nif):
+            nb = by_rank[int(db.my_neighbors_ext_mesh[n])]
+            m = [int(v) for v in nb.db.my_neighbors_ext_mesh[: nb.db.num_interfaces_ext_mesh]].index(r.rank)
+            geom[3 * n: 3 * n + 3] = (m, nb.db.num_interfaces_ext_mesh, nb.db.max_nibool_interfaces_ext_mesh)
+            nbr[n] = nb.rank
+            ptrs[n], nbdev[n] = info[nb.rank]
+        L.cdll.specfem_b200_halo_p2p_connect_(ctypes.byref(r.Mesh_pointer), ctypes.byref(ctypes.c_int(nif)),
+                                               nbr.ctypes.data_as(ctypes.c_void_p), nbdev.ctypes.data_as(ctypes.c_void_p),
+                                               handles, geom.ctypes.data_as(ctypes.c_void_p),
+                                               same.ctypes.data_as(ctypes.c_void_p), ptrs)
+
+
+class NoExchange:
+    """In-process p2p mode: nothing to do on the host."""
+
+    def exchange(self, kind: str):
+        return

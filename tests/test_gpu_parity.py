@@ -1,0 +1,231 @@
+"""GPU parity tests: every hot-path kernel and the whole time loop, called through the C ABI exactly like the Fortran
+solver would, against the CPU oracle on the same inputs.
+
+Tolerances.  Index/byte work is compared bit-exactly; float fields within the tolerance BASELINE.json states for
+the path: seismograms relative L2 <= 1e-4 over the run.  Single kernels are held to a much tighter bound
+(a few float32 ulps of the field maximum) because only summation order and FMA contraction differ.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from specfem3d_b200.configs import HALFSPACE, cfg1, halfspace_scaled
+from specfem3d_b200.meshfem import BoxSpec, Material
+from specfem3d_b200.simulation import make_simulation
+from specfem3d_b200.sources_receivers import CMTSource, Station
+
+pytestmark = pytest.mark.gpu
+
+
+def smooth_fields(sim, amp=1.0, seed=0):
+    """Deterministic smooth wavefields (no denormals): displ/veloc/accel as sines of the coordinates."""
+    out = []
+    for db in sim.dbs:
+        x, y, z = (db.xstore / 5000.0, db.ystore / 5000.0, db.zstore / 5000.0)
+        f = {}
+        if db.nspec_elastic:
+            f["displ"] = amp * np.stack([np.sin(x + 0.3 * y) + 0.1, np.cos(0.7 * y - z), np.sin(0.5 * z + x * y * 0.1)], -1).astype(np.float32)
+            f["veloc"] = amp * np.stack([np.cos(0.9 * x - z), np.sin(y + 0.2 * x), np.cos(0.4 * z - y)], -1).astype(np.float32)
+            f["accel"] = np.zeros_like(f["displ"])
+        if db.nspec_acoustic:
+            f["pot"] = (amp * np.sin(x - 0.4 * y + 0.2 * z)).astype(np.float32)
+            f["pot_dot"] = (amp * np.cos(0.8 * x + z)).astype(np.float32)
+            f["pot_dot_dot"] = np.zeros_like(f["pot"])
+        out.append(f)
+    return out
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def small_sim(deform=0.15, regular=False, nproc=(1, 1), nstep=60, nex=(6, 6, 4), stacey=True, source=True):
+    if regular:
+        spec = BoxSpec(nex[0], nex[1], nex[2], xmax=1000.0 * nex[0], ymax=1000.0 * nex[1], zmin=-1000.0 * nex[2],
+                       nproc_xi=nproc[0], nproc_eta=nproc[1], materials=(HALFSPACE,), stacey=stacey)
+    else:
+        spec = BoxSpec(nex[0], nex[1], nex[2], xmax=1100.0 * nex[0], ymax=900.0 * nex[1], zmin=-1000.0 * nex[2],
+                       nproc_xi=nproc[0], nproc_eta=nproc[1], materials=(HALFSPACE,), deform=deform, stacey=stacey)
+    src = [CMTSource(0.52 * spec.xmax, 0.47 * spec.ymax, 0.55 * spec.zmin, (1e23, -2e23, 0.5e23, 0.3e23, -0.7e23, 0.2e23),
+                     hdur=0.4)] if source else []
+    sts = [Station("A", "XX", 0.21 * spec.xmax, 0.33 * spec.ymax, 0.0), Station("B", "XX", 0.77 * spec.xmax, 0.62 * spec.ymax, 0.0),
+           Station("C", "XX", 0.40 * spec.xmax, 0.81 * spec.ymax, 0.4 * spec.zmin)]
+    return make_simulation(spec, DT=0.012, NSTEP=nstep, sources=src, stations=sts)
+
+
+# -------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", [1, 0])
+@pytest.mark.parametrize("regular", [False, True])
+def test_elastic_force_kernel_matches_oracle(device_lib, variant, regular):
+    """a1: one call of compute_forces_viscoelastic_cuda (both phases) vs oracle_compute_forces_viscoelastic."""
+    from oracle.solver import OracleRun
+    from specfem3d_b200.time_loop import DeviceRun
+
+    os.environ["SPECFEM_B200_FORCE_KERNEL"] = str(variant)
+    sim = small_sim(regular=regular, source=False)
+    sim.initial_fields = smooth_fields(sim)
+    run = DeviceRun(sim)
+    r = run.ranks[0]
+    db = r.db
+    for iphase in (1, 2):
+        r.lib.compute_forces_viscoelastic_cuda(r.Mesh_pointer, iphase, float(sim.deltat), db.nspec_outer_elastic,
+                                               db.nspec_inner_elastic, 0, 0, 1)
+    _, _, accel = r.fields_el()
+    o = OracleRun(sim)
+    p = o.parts[0]
+    p.forces_elastic(1)
+    p.forces_elastic(2)
+    assert np.abs(p.accel).max() > 0
+    assert relerr(accel, p.accel) < 2e-5, relerr(accel, p.accel)
+    run.cleanup()
+    os.environ.pop("SPECFEM_B200_FORCE_KERNEL")
+
+
+def test_newmark_stacey_sources_norm_kernels(device_lib):
+    """a6-a9, a12: predictor, Stacey, source, corrector and the max-norm, each compared right after the call."""
+    from oracle.solver import OracleRun, P, c_float, c_i64, lib as olib
+    from specfem3d_b200.time_loop import DeviceRun
+
+    sim = small_sim()
+    sim.initial_fields = smooth_fields(sim)
+    for f in sim.initial_fields:
+        f["accel"] = (0.5 * f["veloc"] + 0.25).astype(np.float32)
+    run = DeviceRun(sim)
+    r = run.ranks[0]
+    db, L, M = r.db, r.lib, r.Mesh_pointer
+    o = OracleRun(sim)
+    p = o.parts[0]
+    dt, dt2, dtsq2 = float(sim.deltat), float(sim.deltatover2), float(sim.deltatsqover2)
+    # predictor: bit-exact up to FMA contraction
+    L.update_displacement_cuda(M, dt, dt2, dtsq2, 1)
+    olib().oracle_update_displ_elastic(c_i64(db.NGLOB_AB), P(p.displ), P(p.veloc), P(p.accel), c_float(dt), c_float(dt2), c_float(dtsq2))
+    d, v, a = r.fields_el()
+    assert relerr(d, p.displ) < 3e-7 and relerr(v, p.veloc) < 3e-7 and np.all(a == 0)
+    # max norm
+    n = ctypes.c_float(0)
+    L.get_norm_elastic_from_device(n, M, 1)
+    assert abs(n.value - o.max_norm_displ()) <= 1e-6 * o.max_norm_displ()
+    # Stacey + source into accel
+    L.compute_stacey_viscoelastic_cuda(M, 1, np.zeros(1, np.float32), 1)
+    p.stacey_elastic()
+    L.compute_add_sources_el_cuda(M, sim.stf_pre_compute(40), sim.sources.NSOURCES)
+    p.add_sources_elastic(40)
+    _, _, a = r.fields_el()
+    assert np.abs(p.accel).max() > 0 and relerr(a, p.accel) < 1e-6
+    # corrector
+    L.kernel_3_a_cuda(M, dt2, dt2, 0, 1)
+    olib().oracle_multiply_accel_update_veloc(c_i64(db.NGLOB_AB), P(p.veloc), P(p.accel), P(db.rmassx), P(db.rmassy), P(db.rmassz), c_float(dt2))
+    _, v, a = r.fields_el()
+    assert relerr(a, p.accel) < 1e-6 and relerr(v, p.veloc) < 1e-6
+    run.cleanup()
+
+
+@pytest.mark.parametrize("nproc", [(1, 1), (2, 2)])
+def test_time_loop_seismograms_match_oracle(device_lib, nproc):
+    """Whole forward run through the ABI (Newmark, forces, Stacey, CMT source, halo exchange, seismograms) vs the
+    oracle's CPU time loop: relative L2 of every displacement trace <= 1e-4 (BASELINE.json tolerance)."""
+    from oracle.solver import OracleRun
+    from specfem3d_b200.time_loop import DeviceRun
+
+    sim = small_sim(nproc=nproc, nstep=300, nex=(8, 8, 4))
+    sim.SAVE_SEISMOGRAMS_VELOCITY = True
+    run = DeviceRun(sim).run()
+    o = OracleRun(sim).run()
+    sd, sv = run.gather_seismograms("d"), run.gather_seismograms("v")
+    assert np.abs(o.seis_d).max() > 0
+    for irec in range(sim.receivers.nrec):
+        for c in range(3):
+            assert rel_l2(sd[irec, :, c], o.seis_d[irec, :, c]) <= 1e-4
+            assert rel_l2(sv[irec, :, c], o.seis_v[irec, :, c]) <= 1e-4
+    assert abs(run.max_norm_displ() - o.max_norm_displ()) <= 1e-4 * o.max_norm_displ()
+    assert run.kernel_launches() > 300 * 3
+    run.cleanup()
+
+
+def test_partitioned_run_equals_single_rank_run(device_lib):
+    """Halo pack / exchange / unpack: 4 ranks must give the same seismograms as 1 rank (same mesh, same physics)."""
+    from specfem3d_b200.time_loop import DeviceRun
+
+    s1 = small_sim(nproc=(1, 1), nstep=150, nex=(8, 8, 4))
+    s4 = small_sim(nproc=(2, 2), nstep=150, nex=(8, 8, 4))
+    a = DeviceRun(s1).run()
+    b = DeviceRun(s4).run()
+    sa, sb = a.gather_seismograms("d"), b.gather_seismograms("d")
+    assert np.abs(sa).max() > 0
+    assert rel_l2(sb, sa) <= 2e-5
+    a.cleanup(); b.cleanup()
+
+
+def test_cfg1_against_REF_SEIS_golden(device_lib):
+    """Config 1 on the GPU against the reference's own golden seismograms (first 600 of 5000 steps), 4 ranks."""
+    from specfem3d_b200.time_loop import DeviceRun
+
+    nstep = 600
+    sim = cfg1(2, 2, nstep)
+    run = DeviceRun(sim).run()
+    sd = run.gather_seismograms("d")
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "halfspace_ref_seis.npz"))
+    for i, st in enumerate(("X20", "X30", "X40", "X50")):
+        for c, ch in enumerate("XYZ"):
+            ref = gold[f"{st}_{ch}"][:nstep]
+            assert rel_l2(sd[i, :nstep, c], ref) <= 1e-4, (st, ch)
+    ref500 = dict(zip(gold["maxnorm_step"].tolist(), gold["maxnorm_value"].tolist()))[500]
+    run.cleanup()
+    sim2 = cfg1(2, 2, 500)
+    run2 = DeviceRun(sim2).run()
+    assert abs(run2.max_norm_displ() - ref500) / ref500 < 1e-5
+    run2.cleanup()
+
+
+def test_full_size_properties_cfg2(device_lib):
+    """BASELINE config 2 size (128x128x64 = 1,048,576 elements): size-independent properties of the force kernel:
+    K(0) = 0, K(rigid translation) = 0 (to rounding), linearity K(2u) = 2K(u), and determinism of the element list."""
+    from specfem3d_b200.time_loop import DeviceRun
+
+    sim = halfspace_scaled(128, 128, 64, NSTEP=2, stations=False)
+    db = sim.dbs[0]
+    assert db.NSPEC_AB == 1048576
+    run = DeviceRun(sim)
+    r = run.ranks[0]
+    L, M = r.lib, r.Mesh_pointer
+    n = db.NGLOB_AB
+
+    def K(displ):
+        L.transfer_fields_el_to_device(3 * n, displ, np.zeros_like(displ), np.zeros_like(displ), M)
+        L.compute_forces_viscoelastic_cuda(M, 2, float(sim.deltat), db.nspec_outer_elastic, db.nspec_inner_elastic, 0, 0, 1)
+        return r.fields_el()[2]
+
+    u = smooth_fields(sim)[0]["displ"]
+    assert np.all(K(np.zeros_like(u)) == 0)
+    k1 = K(u)
+    scale = np.abs(k1).max()
+    assert scale > 0
+    kt = K(np.ones_like(u) * np.float32(3.0))
+    assert np.abs(kt).max() < 1e-4 * scale * 100  # constants are annihilated up to float32 cancellation
+    k2 = K((2.0 * u).astype(np.float32))
+    assert relerr(k2, 2.0 * k1) < 1e-5
+    run.cleanup()
+
+
+def test_p2p_halo_matches_host_staged_halo(device_lib):
+    """a11: the fused pack + peer-store + flag kernel and the wait + unpack kernel (NVLink path; here the four
+    ranks share one GPU, so the 'peer' stores are plain device stores) against the reference-compatible host path."""
+    from specfem3d_b200.time_loop import DeviceRun
+
+    s_host = small_sim(nproc=(2, 2), nstep=120, nex=(8, 8, 4))
+    s_p2p = small_sim(nproc=(2, 2), nstep=120, nex=(8, 8, 4))
+    a = DeviceRun(s_host, halo="host").run()
+    b = DeviceRun(s_p2p, halo="p2p").run()
+    sa, sb = a.gather_seismograms("d"), b.gather_seismograms("d")
+    assert np.abs(sa).max() > 0
+    assert rel_l2(sb, sa) <= 2e-5
+    assert abs(a.max_norm_displ() - b.max_norm_displ()) <= 1e-5 * a.max_norm_displ()
+    a.cleanup(); b.cleanup()

@@ -1,0 +1,66 @@
+"""Pins the CPU oracle against the reference's own golden vectors.
+
+Config 1 (default DATA/Par_file example, homogeneous halfspace, CMT source, Stacey, 4 stations): the oracle's
+displacement seismograms must reproduce EXAMPLES/applications/homogeneous_halfspace/REF_SEIS (fixture
+tests/golden/halfspace_ref_seis.npz made by tests/golden/make_golden.py) and the "Max norm displacement" lines of
+REF_SEIS/output_solver.txt.  BASELINE.json tolerance: relative L2 misfit <= 1e-4.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from specfem3d_b200.configs import cfg1
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "halfspace_ref_seis.npz")
+NSTEP = 600  # P and S have reached X50 and X40, P has reached all stations (t = 20 s after origin)
+
+
+@pytest.fixture(scope="module")
+def oracle_run():
+    from oracle.solver import OracleRun, set_num_threads
+
+    set_num_threads(os.cpu_count() or 1)
+    sim = cfg1(2, 2, NSTEP)  # 4 ranks like the reference run
+    run = OracleRun(sim)
+    norms = {}
+    for it in range(1, NSTEP + 1):
+        run.step()
+        if it in (5, 500):
+            norms[it] = run.max_norm_displ()
+    return sim, run, norms
+
+
+def test_source_and_receiver_location_match_reference_log(oracle_run):
+    sim, _, _ = oracle_run
+    # output_solver.txt: source at xi=eta=gamma=1 of its element; receivers in slice 0, elements 5173/5176/5179/5182
+    assert np.allclose(sim.sources.local[0], (1.0, 1.0, 1.0), atol=1e-9)
+    assert list(sim.receivers.islice_selected_rec) == [0, 0, 0, 0]
+    assert list(sim.receivers.ispec_selected_rec) == [5173, 5176, 5179, 5182]
+    assert abs(sim.receivers.local[0][0] - (-0.78573757580241610)) < 2e-6
+    assert abs(sim.sources.t0 - 10.0) < 1e-12  # traces start at -10.0000000
+
+
+def test_seismograms_match_REF_SEIS(oracle_run):
+    sim, run, _ = oracle_run
+    gold = np.load(GOLD)
+    t = sim.time_axis()
+    assert np.allclose(t[:NSTEP], gold["time"][:NSTEP], atol=2e-5)
+    worst = 0.0
+    for i, st in enumerate(("X20", "X30", "X40", "X50")):
+        for c, ch in enumerate("XYZ"):
+            ref = gold[f"{st}_{ch}"][:NSTEP].astype(np.float64)
+            syn = run.seis_d[i, :NSTEP, c].astype(np.float64)
+            # the 2016 reference run used FIX_UNDERFLOW_PROBLEM (traces start at 1e-24): irrelevant at these amplitudes
+            err = np.linalg.norm(syn - ref) / np.linalg.norm(ref)
+            worst = max(worst, err)
+            assert err <= 1e-4, f"{st}.BX{ch}: relative L2 {err:.3e}"
+    print(f"worst relative L2 vs REF_SEIS over {NSTEP} steps: {worst:.3e}")
+
+
+def test_max_norm_matches_reference_log(oracle_run):
+    _, _, norms = oracle_run
+    gold = np.load(GOLD)
+    ref = dict(zip(gold["maxnorm_step"].tolist(), gold["maxnorm_value"].tolist()))
+    assert abs(norms[5] - ref[5]) / ref[5] < 1e-5      # 2.24574184
+    assert abs(norms[500] - ref[500]) / ref[500] < 1e-5  # 828559.312
