@@ -60,9 +60,27 @@ class DeviceLibrary:
         if name.startswith("_") or name in ("cdll", "symbols", "path"):
             raise AttributeError(name)
         if name not in self.symbols:
-            fn = getattr(self.cdll, name + "_")
-            fn.restype = None
-            return fn
+            # extension entry points (not in the reference contract): same by-reference convention for ctypes scalars
+            raw = getattr(self.cdll, name + "_")
+            raw.restype = None
+
+            def ext_call(*args: Any):
+                boxed = []
+                for a in args:
+                    if isinstance(a, np.ndarray):
+                        boxed.append(a.ctypes.data_as(ctypes.c_void_p))
+                    elif isinstance(a, ctypes._SimpleCData):
+                        boxed.append(ctypes.byref(a))
+                    elif isinstance(a, (bytes, ctypes.Array)) or a is None:
+                        boxed.append(a)
+                    elif isinstance(a, int):
+                        boxed.append(ctypes.byref(ctypes.c_int(a)))
+                    else:
+                        raise TypeError(f"{name}: cannot pass {type(a)} to an extension entry point")
+                return raw(*boxed)
+
+            ext_call.__name__ = name
+            return ext_call
         fn = getattr(self.cdll, name + "_")
         fn.restype = None
         decls = self.symbols[name]["args"]
