@@ -57,7 +57,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -161,7 +161,8 @@ def run_device(args):
     lib = abi.load()
 
     nex = tuple(int(v) for v in args.nex.split("x"))
-    nstep_total = args.warmup + args.steps + 2
+    # warm-up + timed region 1 (value) + timed region 3 (e2e) record one seismogram sample per step; region 2 does not
+    nstep_total = args.warmup + 2 * args.steps + 4
     spec, DT, gll, db, loc, sources, receivers, _ = build_workload(world, rank, nex, nstep_total)
 
     # ---- mass-matrix assembly across ranks (assemble_MPI_scalar_blocking) ---------------------------------------------
@@ -385,7 +386,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nex", default="128x128x64", help="elements per GPU (config 2 = 128x128x64)")

@@ -67,7 +67,11 @@ class OraclePartition:
     """Wavefields and static arrays of one rank."""
 
     def __init__(self, sim, db, att=None, pml=None):
-        self.sim, self.db, self.att, self.pml = sim, db, att, pml
+        self.sim, self.db, self.pml = sim, db, pml
+        # the memory variables / stored strains are state: work on private copies so that the Simulation object
+        # still describes the initial condition for whoever runs it next (the device run of the same test)
+        self.att = None if att is None else {k: (v.copy() if isinstance(v, np.ndarray) and k.startswith(("R_", "epsilondev_")) else v)
+                                             for k, v in att.items()}
         n = db.NGLOB_AB
         if db.nspec_elastic:
             self.displ = np.zeros((n, 3), np.float32)
@@ -293,6 +297,17 @@ class OracleRun:
                     o = np.zeros(3, np.float32)
                     L.oracle_interpolate_seismogram(c_int(ispec), P(p.db.ibool), P(fld), P(hx), P(hy), P(hz), P(nu), P(o))
                     out[irec, k] = o
+                if sim.SAVE_SEISMOGRAMS_PRESSURE:
+                    db, g = p.db, sim.gll
+                    o = np.zeros(1, np.float32)
+                    a = p.att
+                    L.oracle_interpolate_pressure_elastic(
+                        c_int(ispec), P(db.ibool), P(db.irregular_element_number), P(db.xixstore), P(db.xiystore),
+                        P(db.xizstore), P(db.etaxstore), P(db.etaystore), P(db.etazstore), P(db.gammaxstore),
+                        P(db.gammaystore), P(db.gammazstore), c_float(db.xix_regular),
+                        P(db.kappastore if a is None else a["kappastore"]), P(db.mustore if a is None else a["mustore"]),
+                        P(g.hprime_xx.ravel(order="F").copy()), P(p.displ), P(hx), P(hy), P(hz), P(o))
+                    self.seis_p[irec, k] = o[0]
             else:
                 o = np.zeros(1, np.float32)
                 L.oracle_interpolate_pressure(c_int(ispec), P(p.db.ibool), P(p.pot_dot_dot), P(hx), P(hy), P(hz), P(o))

@@ -628,6 +628,66 @@ void oracle_interpolate_pressure(int ispec1, const int* ibool, const realw* pote
   *out = (realw)(-d);
 }
 
+
+/* pressure seismogram in a solid element: p = -trace(sigma)/3 at every GLL point, then interpolated
+ * (compute_interpolated_dva_viscoelast, src/specfem3D/compute_interpolated_dva.f90:104-215, with the strain taken from
+ * compute_element_strain, compute_element_strain.F90:28-171: deviatoric strain + trace/3, recombined).  Isotropic. */
+void oracle_interpolate_pressure_elastic(int ispec1, const int* ibool, const int* irregular_element_number,
+                                         const realw* xix, const realw* xiy, const realw* xiz, const realw* etax,
+                                         const realw* etay, const realw* etaz, const realw* gammax, const realw* gammay,
+                                         const realw* gammaz, realw xix_regular, const realw* kappastore,
+                                         const realw* mustore, const realw* hprime_xx, const realw* displ,
+                                         const double* hxir, const double* hetar, const double* hgammar, realw* out) {
+  const int ispec = ispec1 - 1;
+  const realw ONE_THIRD = (realw)(1.0 / 3.0), FOUR_THIRDS = (realw)(4.0 / 3.0);
+  const int irr = irregular_element_number[ispec];
+  realw u[3][NGLL3];
+  for (int p = 0; p < NGLL3; ++p) {
+    const size_t g = (size_t)(ibool[(size_t)ispec * NGLL3 + p] - 1) * 3;
+    u[0][p] = displ[g]; u[1][p] = displ[g + 1]; u[2][p] = displ[g + 2];
+  }
+  double pd = 0;
+  for (int k = 0; k < 5; ++k)
+    for (int j = 0; j < 5; ++j)
+      for (int i = 0; i < 5; ++i) {
+        realw t1[3] = {0, 0, 0}, t2[3] = {0, 0, 0}, t3[3] = {0, 0, 0};
+        for (int l = 0; l < 5; ++l) {
+          const realw hp1 = hprime_xx[i + 5 * l], hp2 = hprime_xx[j + 5 * l], hp3 = hprime_xx[k + 5 * l];
+          for (int c = 0; c < 3; ++c) {
+            t1[c] = t1[c] + u[c][l + 5 * j + 25 * k] * hp1;
+            t2[c] = t2[c] + u[c][i + 5 * l + 25 * k] * hp2;
+            t3[c] = t3[c] + u[c][i + 5 * j + 25 * l] * hp3;
+          }
+        }
+        realw dxx, dyy, dzz;
+        const int p = i + 5 * j + 25 * k;
+        if (irr != 0) {
+          const size_t o = (size_t)(irr - 1) * NGLL3 + p;
+          dxx = xix[o] * t1[0] + etax[o] * t2[0] + gammax[o] * t3[0];
+          dyy = xiy[o] * t1[1] + etay[o] * t2[1] + gammay[o] * t3[1];
+          dzz = xiz[o] * t1[2] + etaz[o] * t2[2] + gammaz[o] * t3[2];
+        } else {
+          dxx = xix_regular * t1[0]; dyy = xix_regular * t2[1]; dzz = xix_regular * t3[2];
+        }
+        /* compute_element_strain: templ = ONE_THIRD * (dxx + dyy + dzz); eps_trace_over_3 = templ; dev = d - templ */
+        const realw templ = ONE_THIRD * (dxx + dyy + dzz);
+        const realw e1 = dxx - templ, e2 = dyy - templ;
+        /* compute_interpolated_dva_viscoelast: recombination */
+        const realw duxdxl = e1 + templ, duydyl = e2 + templ;
+        const realw duzdzl = (realw)3.0 * templ - duxdxl - duydyl;
+        const size_t q = (size_t)ispec * NGLL3 + p;
+        const realw kappal = kappastore[q], mul = mustore[q];
+        const realw lambdalplus2mul = kappal + FOUR_THIRDS * mul;
+        const realw lambdal = lambdalplus2mul - (realw)2.0 * mul;
+        const realw sxx = lambdalplus2mul * duxdxl + lambdal * (duydyl + duzdzl);
+        const realw syy = lambdalplus2mul * duydyl + lambdal * (duxdxl + duzdzl);
+        const realw szz = lambdalplus2mul * duzdzl + lambdal * (duxdxl + duydyl);
+        const realw pressure = -(sxx + syy + szz) / (realw)3.0;
+        pd += (double)pressure * (hxir[i] * hetar[j] * hgammar[k]);
+      }
+  *out = (realw)pd;
+}
+
 /* check_stability: max over points of sqrt(ux^2+uy^2+uz^2), src/specfem3D/check_stability.f90:85-115 */
 realw oracle_max_norm_displ(int64_t nglob, const realw* displ) {
   realw m = 0.f;

@@ -1,0 +1,178 @@
+"""Host-side attenuation set-up (N_SLS = 3 standard linear solids): what ``xgenerate_databases`` writes to
+``attenuation.bin`` and what ``prepare_attenuation`` turns it into before the time loop.
+
+Restated from (no code copied):
+
+* src/shared/get_attenuation_model.f90:184-462   get_attenuation_model: per GLL point ``factor_common``,
+  ``scale_factor`` (shear) and ``factor_common_kappa``, ``scale_factor_kappa`` (bulk) from Q_mu / Q_kappa
+* :464-498  get_attenuation_memory_values  (alphaval, betaval, gammaval: 4th-order expansion of exp(-dt/tau))
+* :500-538  get_attenuation_constants, :702-752 get_attenuation_periods (THETA table), :754-789 tau_sigma
+  (log-spaced relaxation frequencies), :791-830 f_c_source (log centre of the band)
+* :838-1220 tau_eps by a Nelder-Mead fit of tan(delta)(f) to 1/Q over 100 log-spaced frequencies
+  (attenuation_invert_by_simplex / attenuation_eval / attenuation_maxwell)
+* src/specfem3D/prepare_attenuation.f90:28-241   scaling of mustore / kappastore by the scale factors, zeroed
+  memory variables and strains.
+
+The simplex itself is scipy's Nelder-Mead started from the same initial guess ``tau_s (1 + 2/Q)`` with the same
+objective; the optimum is not pinned bit-for-bit to the Fortran fminsearch (no golden vector exists for it), which
+does not matter for kernel parity: the device library and the oracle consume the very same arrays.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List
+
+import numpy as np
+
+from .gll import N_SLS, NGLL3
+
+ATTENUATION_COMP_MAXIMUM = 9000.0  # setup/constants.h.in
+_THETA = (0.00, 0.75, 1.75, 2.25, 2.85)
+
+
+def attenuation_periods(min_resolved_period: float):
+    """get_attenuation_periods: band = [T_min, T_min * 10**THETA(N_SLS)] with a 1 % margin (get_attenuation_constants)."""
+    tmin = float(np.float32(0.99) * np.float32(min_resolved_period))
+    return tmin, tmin * 10.0 ** _THETA[N_SLS - 1]
+
+
+def tau_sigma_of(min_period: float, max_period: float) -> np.ndarray:
+    f1, f2 = 1.0 / max_period, 1.0 / min_period
+    e1, e2 = math.log10(f1), math.log10(f2)
+    d = (e2 - e1) / (N_SLS - 1.0)
+    return np.array([1.0 / (3.14159265358979 * 2.0 * 10.0 ** (e1 + i * d)) for i in range(N_SLS)])
+
+
+def f_c_source_of(min_period: float, max_period: float) -> float:
+    return 10.0 ** (0.5 * (math.log10(1.0 / max_period) + math.log10(1.0 / min_period)))
+
+
+def _maxwell(f_log: np.ndarray, tau_s: np.ndarray, tau_eps: np.ndarray):
+    w = 2.0 * 3.14159265358979 * 10.0 ** f_log[:, None]
+    denom = 1.0 + w ** 2 * tau_s[None, :] ** 2
+    A = ((1.0 + w ** 2 * tau_eps[None, :] * tau_s[None, :]) / denom).sum(1)
+    B = (w * (tau_eps[None, :] - tau_s[None, :]) / denom).sum(1)
+    return A, B
+
+
+_TAU_EPS_CACHE: Dict[tuple, np.ndarray] = {}
+
+
+def tau_eps_of(Q: float, tau_s: np.ndarray, min_period: float, max_period: float) -> np.ndarray:
+    """attenuation_invert_by_simplex: minimise sum_f |tan_delta(f) - 1/Q| / (1/Q) over tau_eps."""
+    from scipy.optimize import minimize
+
+    key = (round(Q, 6), tuple(np.round(tau_s, 15)), min_period, max_period)
+    if key in _TAU_EPS_CACHE:
+        return _TAU_EPS_CACHE[key]
+    nf = 100
+    e1, e2 = math.log10(1.0 / max_period), math.log10(1.0 / min_period)
+    f_log = e1 + np.arange(nf) * (e2 - e1) / (nf - 1.0)
+    iQ = 1.0 / Q
+
+    def cost(x):
+        A, B = _maxwell(f_log, tau_s, x)
+        return float(np.sqrt(((B / A - iQ) ** 2) / iQ ** 2).sum())
+
+    x0 = tau_s + tau_s * 2.0 / Q
+    res = minimize(cost, x0, method="Nelder-Mead", options={"xatol": 1e-12, "fatol": 1e-10, "maxiter": 20000,
+                                                             "maxfev": 40000, "adaptive": False})
+    _TAU_EPS_CACHE[key] = res.x
+    return res.x
+
+
+def scale_factor_of(f_c_source: float, tau_eps: np.ndarray, tau_s: np.ndarray, Q: float, f0_ref: float) -> float:
+    """get_attenuation_scale_factor (:634-700)."""
+    factor_mu0 = 1.0 + 2.0 * math.log(f_c_source / f0_ref) / (math.pi * Q)
+    x1 = x2 = 1.0
+    for i in range(N_SLS):
+        ak = tau_eps[i] / tau_s[i] - 1.0
+        x1 += ak / N_SLS
+        x2 += ak / (1.0 + 1.0 / (2.0 * math.pi * f_c_source * tau_s[i]) ** 2) / N_SLS
+    sf = (x1 / x2) * factor_mu0
+    if not (0.5 <= sf <= 1.5):
+        raise ValueError(f"unreliable attenuation scale factor {sf} (Q={Q}, f_c={f_c_source}, f0={f0_ref})")
+    return sf
+
+
+def memory_values(tau_s32: np.ndarray, deltat: np.float32):
+    """get_attenuation_memory_values in single precision, term by term like the Fortran expression."""
+    f = np.float32
+    dt = f(deltat)
+    ti = (f(-1.0) / tau_s32).astype(np.float32)
+    alpha = f(1.0) + dt * ti + dt ** 2 * ti ** 2 / f(2.0) + dt ** 3 * ti ** 3 / f(6.0) + dt ** 4 * ti ** 4 / f(24.0)
+    beta = dt / f(2.0) + dt ** 2 * ti / f(3.0) + dt ** 3 * ti ** 2 / f(8.0) + dt ** 4 * ti ** 3 / f(24.0)
+    gamma = dt / f(2.0) + dt ** 2 * ti / f(6.0) + dt ** 3 * ti ** 2 / f(24.0)
+    return alpha.astype(np.float32), beta.astype(np.float32), gamma.astype(np.float32)
+
+
+def min_resolved_period_of(sim) -> float:
+    """check_mesh_resolution's estimate (src/shared/check_mesh_resolution.f90:245-271): per element
+    ``pmax = (elemsize_max / (NGLLX-1)) / vel_min * NPTS_PER_WAVELENGTH`` with NPTS_PER_WAVELENGTH = 5
+    (setup/constants.h.in:301), maximum over elements.  For the harness' box meshes the element size is the
+    largest edge of the undeformed cell (deformed test meshes differ by a few per cent, which only shifts the band)."""
+    spec = sim.spec
+    h = max((spec.xmax - spec.xmin) / spec.nex_xi, (spec.ymax - spec.ymin) / spec.nex_eta,
+            (spec.zmax - spec.zmin) / spec.ner)
+    vmin = min(m.vs if m.domain == 2 else m.vp for m in spec.materials)
+    return (h / 4.0) / vmin * 5.0
+
+
+def prepare_attenuation(sim, f0_reference: float = 0.0) -> List[dict]:
+    """Per-rank dict of the arrays handed to ``prepare_fields_elastic_device`` when ATTENUATION is on."""
+    tmin, tmax = attenuation_periods(min_resolved_period_of(sim))
+    tau_s = tau_sigma_of(tmin, tmax)
+    fc = f_c_source_of(tmin, tmax)
+    f0 = f0_reference if f0_reference > 0 else fc
+    tau_s32 = tau_s.astype(np.float32)
+    tauinv = (np.float32(1.0) / tau_s32).astype(np.float32)
+    alphaval, betaval, gammaval = memory_values(tau_s32, sim.deltat)
+    out = []
+    for db in sim.dbs:
+        if db is None:
+            out.append(None)
+            continue
+        nspec = db.NSPEC_AB
+        fcom = np.ones((nspec, NGLL3, N_SLS), np.float32)
+        fcomk = np.ones((nspec, NGLL3, N_SLS), np.float32)
+        sf = np.ones((nspec, NGLL3), np.float32)
+        sfk = np.ones((nspec, NGLL3), np.float32)
+        pairs = {}
+        for e in range(nspec):
+            if not db.ispec_is_elastic[e]:
+                continue
+            qmu, qk = float(db.qmu[e]), float(db.qkappa[e])
+            if qmu <= 1e-5:
+                continue
+            qmu = min(max(qmu, 1.0), ATTENUATION_COMP_MAXIMUM)
+            if qk <= 1e-5:
+                qk = ATTENUATION_COMP_MAXIMUM
+            qk = min(max(qk, 1.0), ATTENUATION_COMP_MAXIMUM)
+            key = (qmu, qk)
+            if key not in pairs:
+                te = tau_eps_of(qmu, tau_s, tmin, tmax)
+                tek = tau_eps_of(qk, tau_s, tmin, tmax)
+                beta = te / tau_s
+                omsb = beta.sum()
+                beta = beta - 1.0
+                betak = tek / tau_s
+                omsbk = betak.sum()
+                betak = betak - 1.0
+                # factor_common(:) = (2 * beta(:) * tauinv(:)) / one_minus_sum_beta  with tauinv in single precision
+                fc_mu = ((2.0 * beta * tauinv.astype(np.float64)) / omsb).astype(np.float32)
+                fc_k = ((betak * tauinv.astype(np.float64)) / omsbk).astype(np.float32)
+                pairs[key] = (fc_mu, fc_k, np.float32(scale_factor_of(fc, te, tau_s, qmu, f0)),
+                              np.float32(scale_factor_of(fc, tek, tau_s, qk, f0)))
+            a, b, c, d = pairs[key]
+            fcom[e], fcomk[e], sf[e], sfk[e] = a, b, c, d
+        att = {
+            "mustore": (db.mustore.reshape(nspec, NGLL3) * sf).astype(np.float32).reshape(db.mustore.shape),
+            "kappastore": (db.kappastore.reshape(nspec, NGLL3) * sfk).astype(np.float32).reshape(db.kappastore.shape),
+            "factor_common": fcom, "factor_common_kappa": fcomk, "alphaval": alphaval, "betaval": betaval,
+            "gammaval": gammaval, "tau_sigma": tau_s32, "f_c_source": fc,
+        }
+        for k in ("xx", "yy", "xy", "xz", "yz", "trace"):
+            att["epsilondev_" + k] = np.zeros((nspec, NGLL3), np.float32)
+            att["R_" + k] = np.zeros((nspec, NGLL3, N_SLS), np.float32)
+        out.append(att)
+    return out

@@ -162,8 +162,14 @@ struct DeviceMesh {
   realw* h_norm_partial = nullptr;
   int norm_blocks = 0;
 
+  // grouped element storage of the TMA force kernels (kernels_elastic_grp.cuh), built lazily at the first launch
+  struct GroupStore* grp_elastic = nullptr;
+  std::vector<int> h_irregular_element_number;   // host copies needed to build it
+  std::vector<int> h_phase_ispec_elastic;        // [2][num_phase_ispec_elastic]
+  std::vector<int> h_is_CPML;                    // empty when no PML
+
   // options
-  int force_kernel_variant = 0;  // 0 = default
+  int force_kernel_variant = 0;  // 0 = default (grp), 1 = pt, 2 = col
   long long kernel_launches = 0;
 };
 

@@ -298,12 +298,16 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_seismogram_vector(
   }
 }
 
-// pressure seismogram: fluid element p = -potential_dot_dot (or potential with USE_TRICK_FOR_BETTER_PRESSURE);
-// solid element p = -kappa * div(u) is out of this round's scope (reference: compute_acoustic_seismogram_kernel.cu)
+// pressure seismogram (replaces compute_acoustic_seismogram_kernel.cu:30-250; CPU: compute_interpolated_dva.f90:104-215):
+// fluid element p = -potential_dot_dot (or -potential with USE_TRICK_FOR_BETTER_PRESSURE);
+// solid element p = -trace(sigma)/3 with the isotropic stress of the displacement gradient at every GLL point.
 __global__ void __launch_bounds__(NGLL3_PADDED) k_seismogram_pressure(
-    int nrec_local, const realw* __restrict__ potential, const int* __restrict__ ibool, const realw* __restrict__ hxir,
-    const realw* __restrict__ hetar, const realw* __restrict__ hgammar, realw* seismograms_p,
-    const int* __restrict__ ispec_selected_rec_loc, const int* __restrict__ ispec_is_acoustic, int seismo_current) {
+    int nrec_local, const realw* __restrict__ potential, const realw* __restrict__ displ, const int* __restrict__ ibool,
+    const realw* __restrict__ hxir, const realw* __restrict__ hetar, const realw* __restrict__ hgammar, realw* seismograms_p,
+    const int* __restrict__ ispec_selected_rec_loc, const int* __restrict__ ispec_is_acoustic,
+    const int* __restrict__ ispec_is_elastic, const realw* __restrict__ kappav, const realw* __restrict__ muv,
+    const realw* __restrict__ metric, const int* __restrict__ irregular_element_number, realw xix_regular,
+    int seismo_current) {
   const int irec = blockIdx.x;
   if (irec >= nrec_local) return;
   const int tx = threadIdx.x;
@@ -311,11 +315,47 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_seismogram_pressure(
   const int t = active ? tx : NGLL3 - 1;
   const int K = t / NGLL2, J = (t - K * NGLL2) / NGLLX, I = t - K * NGLL2 - J * NGLLX;
   __shared__ realw s_red[4];
+  __shared__ realw s_u[3][NGLL3_PADDED];
   const int ispec = ispec_selected_rec_loc[irec] - 1;
+  const realw hl = hxir[I + NGLLX * irec] * hetar[J + NGLLX * irec] * hgammar[K + NGLLX * irec];
   realw v = 0.f;
-  if (ispec_is_acoustic[ispec] && active) {
+  if (ispec_is_acoustic[ispec]) {
+    if (active && potential) {
+      const size_t iglob = (size_t)ibool[(size_t)ispec * NGLL3_PADDED + t] - 1;
+      v = -potential[iglob] * hl;
+    }
+  } else if (ispec_is_elastic[ispec] && displ) {  // uniform per block
     const size_t iglob = (size_t)ibool[(size_t)ispec * NGLL3_PADDED + t] - 1;
-    v = -potential[iglob] * hxir[I + NGLLX * irec] * hetar[J + NGLLX * irec] * hgammar[K + NGLLX * irec];
+    s_u[0][t] = displ[3 * iglob]; s_u[1][t] = displ[3 * iglob + 1]; s_u[2][t] = displ[3 * iglob + 2];
+    __syncthreads();
+    realw t1[3] = {0.f, 0.f, 0.f}, t2[3] = {0.f, 0.f, 0.f}, t3[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int l = 0; l < NGLLX; ++l) {
+      const realw h1 = c_hprime_xx[l * NGLLX + I], h2 = c_hprime_xx[l * NGLLX + J], h3 = c_hprime_xx[l * NGLLX + K];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        t1[c] += s_u[c][K * NGLL2 + J * NGLLX + l] * h1;
+        t2[c] += s_u[c][K * NGLL2 + l * NGLLX + I] * h2;
+        t3[c] += s_u[c][l * NGLL2 + J * NGLLX + I] * h3;
+      }
+    }
+    realw dxx, dyy, dzz;
+    const int irr = irregular_element_number[ispec] - 1;
+    if (irr >= 0) {
+      const realw* mp = metric + (size_t)irr * 9 * NGLL3_PADDED + t;
+      dxx = mp[0] * t1[0] + mp[3 * NGLL3_PADDED] * t2[0] + mp[6 * NGLL3_PADDED] * t3[0];
+      dyy = mp[NGLL3_PADDED] * t1[1] + mp[4 * NGLL3_PADDED] * t2[1] + mp[7 * NGLL3_PADDED] * t3[1];
+      dzz = mp[2 * NGLL3_PADDED] * t1[2] + mp[5 * NGLL3_PADDED] * t2[2] + mp[8 * NGLL3_PADDED] * t3[2];
+    } else {
+      dxx = xix_regular * t1[0]; dyy = xix_regular * t2[1]; dzz = xix_regular * t3[2];
+    }
+    const realw kappal = kappav[(size_t)ispec * NGLL3_PADDED + t], mul = muv[(size_t)ispec * NGLL3_PADDED + t];
+    const realw lambdalplus2mul = kappal + 1.33333333333333333333f * mul;
+    const realw lambdal = lambdalplus2mul - 2.0f * mul;
+    const realw sxx = lambdalplus2mul * dxx + lambdal * (dyy + dzz);
+    const realw syy = lambdalplus2mul * dyy + lambdal * (dxx + dzz);
+    const realw szz = lambdalplus2mul * dzz + lambdal * (dxx + dyy);
+    if (active) v = -hl * ((sxx + syy + szz) / 3.0f);
   }
   v = block_sum_128(v, s_red);
   if (tx == 0) seismograms_p[irec + (size_t)nrec_local * seismo_current] = v;

@@ -11,6 +11,7 @@
 #include "kernels_common.cuh"
 #include "kernels_elastic.cuh"
 #include "kernels_elastic_col.cuh"
+#include "kernels_elastic_grp.cuh"
 #include "kernels_misc.cuh"
 #include "pml.cuh"
 #include "halo_p2p.cuh"
@@ -189,6 +190,7 @@ extern "C" void SB200_FC(prepare_constants_device)(
 
   const size_t nspec = mp->NSPEC_AB;
   mp->d_irregular_element_number = dev_copy(h_irregular_element_number, nspec);
+  mp->h_irregular_element_number.assign(h_irregular_element_number, h_irregular_element_number + nspec);
   mp->d_ibool = dev_copy_padded<int>(h_ibool, nspec, 1);
 
   // metric record per irregular element: 9 planes of 128 floats (one contiguous 4.5 KB slab)
@@ -331,6 +333,7 @@ extern "C" void SB200_FC(prepare_fields_elastic_device)(
   }
   mp->num_phase_ispec_elastic = *num_phase_ispec_elastic;
   mp->d_phase_ispec_inner_elastic = dev_copy(phase_ispec_inner_elastic, 2 * (size_t)mp->num_phase_ispec_elastic);
+  mp->h_phase_ispec_elastic.assign(phase_ispec_inner_elastic, phase_ispec_inner_elastic + 2 * (size_t)mp->num_phase_ispec_elastic);
 
   if (mp->stacey_absorbing_conditions && mp->num_abs_boundary_faces > 0) {
     mp->d_rho_vp = dev_copy(rho_vp, NGLL3 * nspec);
@@ -449,6 +452,7 @@ extern "C" void SB200_FC(prepare_cleanup_device)(long* Mesh_pointer, int* ACOUST
   CUDA_CHECK(cudaDeviceSynchronize());
   p2p_destroy(mp);
   pml_destroy(mp);
+  group_store_free(mp->grp_elastic);
   void* dptrs[] = {mp->d_ibool, mp->d_irregular_element_number, mp->d_metric, mp->d_kappav, mp->d_muv, mp->d_rhostore,
                    mp->d_rho_vp, mp->d_rho_vs, mp->d_kappastore_unpadded, mp->d_ispec_is_inner, mp->d_ispec_is_elastic,
                    mp->d_ispec_is_acoustic, mp->d_phase_ispec_inner_elastic, mp->d_phase_ispec_inner_acoustic,
@@ -648,15 +652,43 @@ static void launch_elastic(DeviceMesh* mp, int nb, const int* phase_list, int fi
 
   const bool att = mp->attenuation != 0;
   const bool strain = mp->compute_and_store_strain != 0;
-  if (mp->force_kernel_variant == 1 || att || strain) {
-    // plain one-thread-per-point path; also the only one that handles attenuation / strain storage so far
+  if (mp->force_kernel_variant == 2 && !att && !strain) {
+    launch_elastic_col(mp, a);
+  } else {
+    // plain one-thread-per-point path; the only one that handles attenuation / strain storage so far
     if (att) k_elastic_forces_pt<true, true><<<nb, NGLL3_PADDED, 0, mp->compute_stream>>>(a);
     else if (strain) k_elastic_forces_pt<false, true><<<nb, NGLL3_PADDED, 0, mp->compute_stream>>>(a);
     else k_elastic_forces_pt<false, false><<<nb, NGLL3_PADDED, 0, mp->compute_stream>>>(a);
-  } else {
-    launch_elastic_col(mp, a);
   }
   KERNEL_CHECK(mp, "elastic forces");
+}
+
+// grouped storage for the TMA kernel: segment 0/1 = outer/inner phase lists (atomics mode) or one segment per colour
+static void ensure_elastic_groups(DeviceMesh* mp, int nspec_outer, int nspec_inner) {
+  if (mp->grp_elastic) return;
+  std::vector<std::vector<int>> segs;
+  auto keep = [&](int ispec) { return mp->h_is_CPML.empty() || mp->h_is_CPML[ispec] == 0; };
+  if (mp->use_mesh_coloring_gpu) {
+    const int ncol = mp->num_colors_outer_elastic + mp->num_colors_inner_elastic;
+    int offset = 0;
+    for (int ic = 0; ic < ncol; ++ic) {
+      std::vector<int> seg;
+      for (int e = 0; e < mp->h_num_elem_colors_elastic[ic]; ++e)
+        if (keep(offset + e)) seg.push_back(offset + e);
+      offset += mp->h_num_elem_colors_elastic[ic];
+      segs.push_back(seg);
+    }
+  } else {
+    const int counts[2] = {nspec_outer, nspec_inner};
+    for (int ph = 0; ph < 2; ++ph) {
+      std::vector<int> seg;
+      const int* list = mp->h_phase_ispec_elastic.data() + (size_t)mp->num_phase_ispec_elastic * ph;
+      for (int e = 0; e < counts[ph]; ++e)
+        if (keep(list[e] - 1)) seg.push_back(list[e] - 1);
+      segs.push_back(seg);
+    }
+  }
+  mp->grp_elastic = group_store_build(mp, segs, mp->h_irregular_element_number, mp->d_irregular_element_number, mp->d_kappav, mp->d_muv);
 }
 
 extern "C" void SB200_FC(compute_forces_viscoelastic_cuda)(long* Mesh_pointer, int* iphase, realw* deltat,
@@ -668,7 +700,21 @@ extern "C" void SB200_FC(compute_forces_viscoelastic_cuda)(long* Mesh_pointer, i
   if ((*ATTENUATION != 0) != (mp->attenuation != 0)) exit_on_error("compute_forces_viscoelastic_cuda: ATTENUATION differs from prepare_fields_elastic_device");
   (void)COMPUTE_AND_STORE_STRAIN;
   const int num_elements = (*iphase == 1) ? *nspec_outer_elastic : *nspec_inner_elastic;
-  if (num_elements > 0) {
+  const bool grp = mp->force_kernel_variant == 0 && !mp->attenuation && !mp->compute_and_store_strain;
+  if (num_elements > 0 && grp) {
+    ensure_elastic_groups(mp, *nspec_outer_elastic, *nspec_inner_elastic);
+    if (mp->use_mesh_coloring_gpu) {
+      const int c0 = (*iphase == 1) ? 0 : mp->num_colors_outer_elastic;
+      const int c1 = (*iphase == 1) ? mp->num_colors_outer_elastic : mp->num_colors_outer_elastic + mp->num_colors_inner_elastic;
+      for (int ic = c0; ic < c1; ++ic) {
+        launch_elastic_grp(mp, mp->grp_elastic, ic, /*use_atomics=*/0);
+        KERNEL_CHECK(mp, "k_elastic_forces_grp(colour)");
+      }
+    } else {
+      launch_elastic_grp(mp, mp->grp_elastic, *iphase - 1, /*use_atomics=*/1);
+      KERNEL_CHECK(mp, "k_elastic_forces_grp");
+    }
+  } else if (num_elements > 0) {
     if (mp->use_mesh_coloring_gpu) {
       // colours are contiguous element ranges: outer colours first, then inner (compute_forces_viscoelastic_cuda.cu:1139-1229)
       int nb_colors, istart, offset;
@@ -844,10 +890,14 @@ extern "C" void SB200_FC(compute_add_sources_el_cuda)(long* Mesh_pointer, double
 
 extern "C" void SB200_FC(compute_add_sources_ac_cuda)(long* Mesh_pointer, int* NSOURCESf, double* h_stf_pre_compute,
                                                       int* run_number_of_the_source) {
-  (void)run_number_of_the_source;
   DeviceMesh* mp = get_mesh(Mesh_pointer);
   if (mp->nsources_local == 0) return;
-  const realw* d_stf = upload_stf(mp, h_stf_pre_compute, *NSOURCESf);
+  // NB_RUNS_ACOUSTIC_GPU == 1: a source belongs to run 0 or contributes nothing (get_stf_for_gpu,
+  // compute_add_sources_acoustic_cuda.cu:40-58)
+  std::vector<double> stf(h_stf_pre_compute, h_stf_pre_compute + *NSOURCESf);
+  for (int i = 0; i < *NSOURCESf; ++i)
+    if (run_number_of_the_source[i] != 0) stf[i] = 0.0;
+  const realw* d_stf = upload_stf(mp, stf.data(), *NSOURCESf);
   k_add_sources_ac<<<mp->nsources, NGLL3_PADDED, 0, mp->compute_stream>>>(
       mp->d_potential_dot_dot, mp->d_ibool, mp->d_sourcearrays, d_stf, mp->myrank, mp->d_islice_selected_source,
       mp->d_ispec_selected_source, mp->d_ispec_is_acoustic, mp->d_kappastore_unpadded, mp->nsources);
@@ -1010,11 +1060,11 @@ extern "C" void SB200_FC(compute_seismograms_cuda)(long* Mesh_pointer_f, realw* 
     KERNEL_CHECK(mp, "k_seismogram_vector");
   }
   if (mp->save_seismograms_p) {
-    if (!mp->d_potential_dot_dot) exit_on_error("pressure seismograms in purely elastic runs are not implemented by this library");
     const realw* pot = *USE_TRICK_FOR_BETTER_PRESSURE ? mp->d_potential : mp->d_potential_dot_dot;
     k_seismogram_pressure<<<mp->nrec_local, NGLL3_PADDED, 0, mp->compute_stream>>>(
-        mp->nrec_local, pot, mp->d_ibool, mp->d_hxir, mp->d_hetar, mp->d_hgammar, mp->d_seismograms_p,
-        mp->d_ispec_selected_rec_loc, mp->d_ispec_is_acoustic, seismo_current);
+        mp->nrec_local, pot, mp->d_displ, mp->d_ibool, mp->d_hxir, mp->d_hetar, mp->d_hgammar, mp->d_seismograms_p,
+        mp->d_ispec_selected_rec_loc, mp->d_ispec_is_acoustic, mp->d_ispec_is_elastic, mp->d_kappav, mp->d_muv, mp->d_metric,
+        mp->d_irregular_element_number, mp->xix_regular, seismo_current);
     KERNEL_CHECK(mp, "k_seismogram_pressure");
   }
   if (seismo_current == nlength - 1 || *itf == *it_endf) {

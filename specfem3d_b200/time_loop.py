@@ -266,7 +266,8 @@ class DeviceRun:
                     if sim.ELASTIC_SIMULATION:
                         L.compute_coupling_ac_el_cuda(M, iphase, db.num_coupling_ac_el_faces, 1)
                     if sim.sources is not None:
-                        L.compute_add_sources_ac_cuda(M, sim.sources.NSOURCES, sim.stf_pre_compute_acoustic(it), 1)
+                        L.compute_add_sources_ac_cuda(M, sim.sources.NSOURCES, sim.stf_pre_compute_acoustic(it),
+                                                      np.zeros(sim.sources.NSOURCES, np.int32))  # run_number_of_the_source(:) = 0
             if self.NPROC > 1:
                 if iphase == 1:
                     for r in A:

@@ -62,7 +62,7 @@ def small_sim(deform=0.15, regular=False, nproc=(1, 1), nstep=60, nex=(6, 6, 4),
 
 
 # -------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("variant", [1, 0])
+@pytest.mark.parametrize("variant", [1, 2, 0])
 @pytest.mark.parametrize("regular", [False, True])
 def test_elastic_force_kernel_matches_oracle(device_lib, variant, regular):
     """a1: one call of compute_forces_viscoelastic_cuda (both phases) vs oracle_compute_forces_viscoelastic."""
@@ -229,3 +229,116 @@ def test_p2p_halo_matches_host_staged_halo(device_lib):
     assert rel_l2(sb, sa) <= 2e-5
     assert abs(a.max_norm_displ() - b.max_norm_displ()) <= 1e-5 * a.max_norm_displ()
     a.cleanup(); b.cleanup()
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# attenuation (a2), acoustic + coupling (a4, a5), and the same runs against the reference's own CUDA backend
+# -------------------------------------------------------------------------------------------------------------------
+VISCO = (Material(2300.0, 2800.0, 1500.0, 9999.0, 40.0, 2), Material(2600.0, 4200.0, 2500.0, 300.0, 100.0, 2))
+WATER = Material(1020.0, 1500.0, 0.0, 9999.0, 9999.0, 1)
+CMT_SMALL = (1e23, -2e23, 0.5e23, 0.3e23, -0.7e23, 0.2e23)
+
+
+def visco_sim(nproc=(1, 1), nstep=200, nex=(8, 6, 4), deform=0.12):
+    spec = BoxSpec(nex[0], nex[1], nex[2], xmax=1100.0 * nex[0], ymax=900.0 * nex[1], zmin=-1000.0 * nex[2],
+                   nproc_xi=nproc[0], nproc_eta=nproc[1], materials=VISCO, layer_material=[0, 0, 1, 1][: nex[2]],
+                   deform=deform)
+    src = [CMTSource(0.52 * spec.xmax, 0.47 * spec.ymax, 0.55 * spec.zmin, CMT_SMALL, hdur=0.4)]
+    sts = [Station("A", "XX", 0.21 * spec.xmax, 0.33 * spec.ymax, 0.0), Station("B", "XX", 0.77 * spec.xmax, 0.62 * spec.ymax, 0.0)]
+    return make_simulation(spec, DT=0.008, NSTEP=nstep, sources=src, stations=sts, attenuation=True)
+
+
+def ocean_sim(nproc=(1, 1), nstep=200, nex=(8, 6, 5), deform=0.1, source_in_water=False):
+    """cfg4 in small: top element layer is water (acoustic), the rest elastic; receivers in both media."""
+    spec = BoxSpec(nex[0], nex[1], nex[2], xmax=1100.0 * nex[0], ymax=900.0 * nex[1], zmin=-1000.0 * nex[2],
+                   nproc_xi=nproc[0], nproc_eta=nproc[1], materials=(HALFSPACE, WATER),
+                   layer_material=[0] * (nex[2] - 1) + [1], deform=deform)
+    zs = 0.1 * spec.zmin if source_in_water else 0.6 * spec.zmin
+    src = [CMTSource(0.52 * spec.xmax, 0.47 * spec.ymax, zs, CMT_SMALL, hdur=0.4)]
+    sts = [Station("W", "XX", 0.31 * spec.xmax, 0.43 * spec.ymax, 0.08 * spec.zmin),   # in the water layer
+           Station("S", "XX", 0.67 * spec.xmax, 0.58 * spec.ymax, 0.5 * spec.zmin)]   # in the solid
+    sim = make_simulation(spec, DT=0.006, NSTEP=nstep, sources=src, stations=sts)
+    sim.SAVE_SEISMOGRAMS_PRESSURE = True
+    return sim
+
+
+def test_attenuation_force_kernel_matches_oracle(device_lib):
+    """a2: one call per phase of the viscoelastic kernel from smooth non-zero u, v, R, eps: accel, the six memory
+    variables and the six stored strains against compute_forces_viscoelastic + compute_element_att_memory."""
+    from oracle.solver import OracleRun
+    from specfem3d_b200.time_loop import DeviceRun
+
+    sim = visco_sim(nstep=4)
+    sim.initial_fields = smooth_fields(sim, amp=1e-3)
+    rng = np.random.default_rng(7)
+    for att in sim.att:
+        for k in ("xx", "yy", "xy", "xz", "yz", "trace"):
+            att["epsilondev_" + k][:] = rng.standard_normal(att["epsilondev_" + k].shape).astype(np.float32) * 1e-7
+            att["R_" + k][:] = rng.standard_normal(att["R_" + k].shape).astype(np.float32) * 1e3
+    o = OracleRun(sim)  # copies the attenuation state before the device run touches anything
+    run = DeviceRun(sim)
+    r = run.ranks[0]
+    db = r.db
+    for iphase in (1, 2):
+        r.lib.compute_forces_viscoelastic_cuda(r.Mesh_pointer, iphase, float(sim.deltat), db.nspec_outer_elastic,
+                                               db.nspec_inner_elastic, 1, 1, 1)
+    _, _, accel = r.fields_el()
+    n = db.NSPEC_AB
+    R = [np.zeros((n, 125, 3), np.float32) for _ in range(6)]
+    E = [np.zeros((n, 125), np.float32) for _ in range(6)]
+    r.lib.transfer_rmemory_from_device(r.Mesh_pointer, *R, 3 * 125 * n)
+    r.lib.transfer_strain_from_device(r.Mesh_pointer, *E, 125 * n)
+    p = o.parts[0]
+    p.forces_elastic(1)
+    p.forces_elastic(2)
+    assert np.abs(p.accel).max() > 0
+    assert relerr(accel, p.accel) < 2e-5
+    for got, key in zip(R, ("R_xx", "R_yy", "R_xy", "R_xz", "R_yz", "R_trace")):
+        assert relerr(got, p.att[key]) < 2e-5, key
+    # the stored strain is a float32 derivative of a field with a large mean (u ~ 1e-3, strain ~ 3e-8): the GPU
+    # differentiates u + dt*v in one pass (like the reference GPU kernel), the CPU adds two gradients, so the
+    # cancellation noise differs; 3e-4 of the maximum is ~5 ulp of the differentiated values
+    for got, key in zip(E, ("epsilondev_xx", "epsilondev_yy", "epsilondev_xy", "epsilondev_xz", "epsilondev_yz", "epsilondev_trace")):
+        assert relerr(got, p.att[key]) < 3e-4, key
+    run.cleanup()
+
+
+@pytest.mark.parametrize("nproc", [(1, 1), (2, 1)])
+def test_viscoelastic_time_loop_matches_oracle(device_lib, nproc):
+    """cfg3's physics in small (layered Q, 3 SLS, Stacey): seismograms within 1e-4 relative L2 of the oracle."""
+    from oracle.solver import OracleRun
+    from specfem3d_b200.time_loop import DeviceRun
+
+    sim = visco_sim(nproc=nproc, nstep=300)
+    o = OracleRun(sim).run()
+    run = DeviceRun(sim).run()
+    sd = run.gather_seismograms("d")
+    assert np.abs(o.seis_d).max() > 0
+    for irec in range(sim.receivers.nrec):
+        for c in range(3):
+            assert rel_l2(sd[irec, :, c], o.seis_d[irec, :, c]) <= 1e-4
+    run.cleanup()
+
+
+@pytest.mark.parametrize("source_in_water", [False, True])
+@pytest.mark.parametrize("nproc", [(1, 1), (2, 2)])
+def test_coupled_acoustic_elastic_time_loop_matches_oracle(device_lib, nproc, source_in_water):
+    """cfg4 in small: acoustic potential kernel, free surface, both coupling kernels, acoustic Stacey and sources,
+    pressure + displacement seismograms, scalar and vector halo exchange."""
+    from oracle.solver import OracleRun
+    from specfem3d_b200.time_loop import DeviceRun
+
+    sim = ocean_sim(nproc=nproc, nstep=300, source_in_water=source_in_water)
+    assert sim.ACOUSTIC_SIMULATION and sim.ELASTIC_SIMULATION
+    o = OracleRun(sim).run()
+    run = DeviceRun(sim).run()
+    sd, sp = run.gather_seismograms("d"), run.gather_seismograms("p")
+    assert np.abs(o.seis_d).max() > 0 and np.abs(o.seis_p).max() > 0
+    for irec in range(sim.receivers.nrec):
+        for c in range(3):
+            if np.abs(o.seis_d[irec, :, c]).max() > 0:
+                assert rel_l2(sd[irec, :, c], o.seis_d[irec, :, c]) <= 1e-4, (irec, c)
+    for irec in range(sim.receivers.nrec):  # pressure in the water layer (-chi_dot_dot) and in the solid (-trace(sigma)/3)
+        assert np.abs(o.seis_p[irec]).max() > 0
+        assert rel_l2(sp[irec, :, 0], o.seis_p[irec, :]) <= 1e-4, irec
+    run.cleanup()

@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""Times the reference's own CUDA backend (oracle/_ref/libspecfem_ref_cuda.so, src/gpu compiled unmodified for sm_100a)
+and the product library on the SAME workload through the SAME host time loop (BASELINE.json north_star: "the
+reference's existing CUDA backend run on the same box is also reported").  Host wall clock around K steps with a
+device synchronise on both sides (the reference library does not expose its stream).  Not part of bench.py's contract;
+the output goes to profiles/.
+
+    python tools/bench_ref_cuda.py --nex 128x128x64 --steps 30 --warmup 5 [--attenuation]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nex", default="128x128x64")
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    args = ap.parse_args()
+    import torch
+
+    import bench
+    from specfem3d_b200 import abi
+    from specfem3d_b200.meshfem import invert_mass
+    from specfem3d_b200.simulation import Simulation
+    from specfem3d_b200.time_loop import DeviceRank, DeviceRun
+
+    nex = tuple(int(v) for v in args.nex.split("x"))
+    nstep = args.warmup + args.steps + 2
+    spec, DT, gll, db, loc, sources, receivers, _ = bench.build_workload(1, 0, nex, nstep)
+    for key in ("rmassx", "rmassy", "rmassz"):
+        setattr(db, key, invert_mass(loc[key]))
+    out = {}
+    libs = {"specfem3d_b200": abi.LIB_PATH, "reference_cuda_backend": os.path.join(ROOT, "oracle", "_ref", "libspecfem_ref_cuda.so")}
+    for name, path in libs.items():
+        if not os.path.exists(path):
+            out[name] = {"unavailable": path}
+            continue
+        lib = abi.DeviceLibrary(path)
+        sim = Simulation(spec, DT, nstep, [db], gll, sources, receivers)
+        r = DeviceRank(sim, 0, lib).prepare()
+        run = DeviceRun(sim, prepared=[r], exchange=False)
+        for _ in range(args.warmup):
+            run.step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            run.step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out[name] = {"ms_per_step": dt / args.steps * 1e3, "element_timesteps_per_s": db.NSPEC_AB * args.steps / dt,
+                     "max_norm_displ": run.max_norm_displ()}
+        r.cleanup()
+    out["workload"] = f"{nex[0]}x{nex[1]}x{nex[2]} elastic halfspace, {db.NSPEC_AB} elements, Stacey, CMT, 4 receivers"
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
