@@ -29,7 +29,6 @@ namespace sb200 {
 #define GRP_ROW 128                     // words per [k][array] row
 #define GRP_NARR_IRR 11
 #define GRP_NARR_REG 2
-#define GRP_STAGES 8                    // parameter ring depth (k-plane chunks)
 #define GRP_CHUNK_WORDS (GRP_NARR_IRR * GRP_ROW)   // 1408 words = 5632 B
 #define GRP_IB_WORDS (5 * GRP_ROW)      // ibool of one group: 640 ints
 #define GRP_U_ELEM 377                  // element stride of the dense tiles: 375 + 2, == 25 (mod 32)
@@ -37,9 +36,9 @@ namespace sb200 {
 #define GRP_CONSUMERS 128
 #define GRP_THREADS 160
 #define GRP_OFF_PARAMS (((3 * GRP_U_WORDS * 4) + 127) / 128 * 128)
-#define GRP_OFF_IBOOL (GRP_OFF_PARAMS + GRP_STAGES * GRP_CHUNK_WORDS * 4)
-#define GRP_OFF_BARS (GRP_OFF_IBOOL + 2 * GRP_IB_WORDS * 4)
-#define GRP_SMEM_BYTES (GRP_OFF_BARS + (2 * GRP_STAGES + 4) * 8)
+#define GRP_OFF_IBOOL(ST) (GRP_OFF_PARAMS + (ST) * GRP_CHUNK_WORDS * 4)
+#define GRP_OFF_BARS(ST) (GRP_OFF_IBOOL(ST) + 2 * GRP_IB_WORDS * 4)
+#define GRP_SMEM_BYTES(ST) (GRP_OFF_BARS(ST) + (2 * (ST) + 4) * 8)
 #define GRP_KIND_LANE 125               // ibool row 0, lane 125 carries the group kind (1 = irregular)
 
 // ---- mbarrier / bulk-copy primitives (PTX ISA 8.x, sm_90+) ---------------------------------------------------------
@@ -53,10 +52,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// bounded wait: a broken pipeline must trap (launch failure reported to the host), never hang the GPU
+// bounded wait: a broken pipeline must trap (launch failure reported to the host), never hang the GPU.
+// Consumers: the data is almost always there already, poll tightly.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
-  long long t0 = 0;
   for (unsigned spin = 0;; ++spin) {
     asm volatile(
         "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
@@ -64,14 +63,42 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (ok) return;
-    if (spin == 64) t0 = clock64();
-    if (spin > 64 && clock64() - t0 > 4000000000LL) __trap();  // ~2 s
+    if (spin > (1u << 22)) __trap();
+  }
+}
+// Producer: it is ahead of the math most of the time; a spinning lane would steal issue slots from the consumer warps
+// of its SM sub-partition (ncu, r01: 34 % of all issued instructions were the producers' polling loops).  Suspend in
+// hardware for up to ~4 us per try, then back off with nanosleep.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (unsigned spin = 0;; ++spin) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(4000u)
+        : "memory");
+    if (ok) return;
+    __nanosleep(256);
+    if (spin > (1u << 20)) __trap();
   }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+// streamed-once data (element parameters): evict-first in L2 so that the re-used wavefield lines (displ, accel of the
+// neighbouring element layers) stay resident
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+      "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+      : "memory");
 }
 __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
@@ -86,14 +113,17 @@ struct GrpArgs {
   int use_atomics;
 };
 
-__global__ void __launch_bounds__(GRP_THREADS, 3) k_elastic_forces_grp(const GrpArgs a) {
+// GRP_STAGES: parameter ring depth in k-plane chunks (power of two); MINB: resident CTAs per SM the registers are capped for
+// PREFETCH: 0 = none, 1 = gather the next batch into registers during stage 2, 2 = pull its lines into L1 (prefetch.global.L1)
+template <int PREFETCH, int GRP_STAGES, int MINB>
+__global__ void __launch_bounds__(GRP_THREADS, MINB) k_elastic_forces_grp(const GrpArgs a) {
   extern __shared__ __align__(128) unsigned char grp_smem[];
   realw* const s_u = reinterpret_cast<realw*>(grp_smem);
   realw* const s_f1 = s_u + GRP_U_WORDS;
   realw* const s_f2 = s_f1 + GRP_U_WORDS;
   realw* const s_p = reinterpret_cast<realw*>(grp_smem + GRP_OFF_PARAMS);
-  int* const s_ib = reinterpret_cast<int*>(grp_smem + GRP_OFF_IBOOL);
-  const uint32_t bars = smem_u32(grp_smem + GRP_OFF_BARS);
+  int* const s_ib = reinterpret_cast<int*>(grp_smem + GRP_OFF_IBOOL(GRP_STAGES));
+  const uint32_t bars = smem_u32(grp_smem + GRP_OFF_BARS(GRP_STAGES));
   // barrier slots: fullP[0..7], emptyP[8..15], fullI[16..17], emptyI[18..19]
   auto fullP = [&](int s) { return bars + 8u * s; };
   auto emptyP = [&](int s) { return bars + 8u * (GRP_STAGES + s); };
@@ -121,7 +151,7 @@ __global__ void __launch_bounds__(GRP_THREADS, 3) k_elastic_forces_grp(const Grp
       int n = 0;
       for (int g = a.first_group + blockIdx.x; g < a.end_group; g += gridDim.x, ++n) {
         const int sI = n & 1;
-        mbar_wait(emptyI(sI), ((n >> 1) & 1) ^ 1);
+        mbar_wait_sleep(emptyI(sI), ((n >> 1) & 1) ^ 1);
         mbar_expect_tx(fullI(sI), GRP_IB_WORDS * 4);
         bulk_g2s(smem_u32(s_ib + sI * GRP_IB_WORDS), a.ibool + (size_t)g * GRP_IB_WORDS, GRP_IB_WORDS * 4, fullI(sI));
         const int kind = __ldg(a.ibool + (size_t)g * GRP_IB_WORDS + GRP_KIND_LANE);
@@ -131,7 +161,7 @@ __global__ void __launch_bounds__(GRP_THREADS, 3) k_elastic_forces_grp(const Grp
 #pragma unroll 1
         for (int k = 0; k < 5; ++k) {
           const int q = n * 5 + k, sP = q & (GRP_STAGES - 1);
-          mbar_wait(emptyP(sP), ((q / GRP_STAGES) & 1) ^ 1);
+          mbar_wait_sleep(emptyP(sP), ((q / GRP_STAGES) & 1) ^ 1);
           mbar_expect_tx(fullP(sP), bytes);
           bulk_g2s(smem_u32(s_p + sP * GRP_CHUNK_WORDS), src + (size_t)k * narr * GRP_ROW, bytes, fullP(sP));
         }
@@ -167,21 +197,17 @@ __global__ void __launch_bounds__(GRP_THREADS, 3) k_elastic_forces_grp(const Grp
   const int row_i = j * NGLLX;  // start of my i-row inside a plane
   const int own = j * NGLLX + i;
 
-  int n = 0;
-  for (int g = a.first_group + blockIdx.x; g < a.end_group; g += gridDim.x, ++n) {
-    // ---- indices of this batch, displacement gather, tile store ----
+  // fetch the indices of batch n from the ibool ring and gather its displacements (registers only)
+  auto fetch = [&](int n, int (&ig)[5], int& kind, bool& valid, realw (&ux)[5], realw (&uy)[5], realw (&uz)[5]) {
     const int sI = n & 1;
     mbar_wait(fullI(sI), (n >> 1) & 1);
     const int* ib = s_ib + sI * GRP_IB_WORDS;
-    int ig[5];
 #pragma unroll
     for (int k = 0; k < 5; ++k) ig[k] = ib[k * GRP_ROW + t] - 1;
-    const int kind = ib[GRP_KIND_LANE];
+    kind = ib[GRP_KIND_LANE];
     __syncwarp();
     if (lane == 0) mbar_arrive(emptyI(sI));
-    const bool valid = lane_ok && ig[0] >= 0;
-
-    realw ux[5], uy[5], uz[5];
+    valid = lane_ok && ig[0] >= 0;
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
       if (valid) {
@@ -191,12 +217,30 @@ __global__ void __launch_bounds__(GRP_THREADS, 3) k_elastic_forces_grp(const Grp
         ux[k] = 0.f; uy[k] = 0.f; uz[k] = 0.f;
       }
     }
+  };
+  auto store_tile = [&](const realw (&ux)[5], const realw (&uy)[5], const realw (&uz)[5]) {
     if (lane_ok) {
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
         const int o = k * NGLL2 + own;
         my_u[o] = ux[k]; my_u[NGLL3 + o] = uy[k]; my_u[2 * NGLL3 + o] = uz[k];
       }
+    }
+  };
+
+  int ig[5], kind = 0;
+  bool valid = false;
+  realw ux[5], uy[5], uz[5];
+  const int g0 = a.first_group + blockIdx.x;
+  if (PREFETCH == 1 && g0 < a.end_group) {
+    fetch(0, ig, kind, valid, ux, uy, uz);
+    store_tile(ux, uy, uz);
+  }
+  int n = 0;
+  for (int g = g0; g < a.end_group; g += gridDim.x, ++n) {
+    if (PREFETCH != 1) {
+      fetch(n, ig, kind, valid, ux, uy, uz);
+      store_tile(ux, uy, uz);
     }
     consumer_bar_sync();
 
@@ -309,6 +353,26 @@ __global__ void __launch_bounds__(GRP_THREADS, 3) k_elastic_forces_grp(const Grp
     }
     consumer_bar_sync();
 
+    // ---- gather of the NEXT batch, issued now so that its latency hides behind the second stage ----
+    int ig_n[5], kind_n = 0;
+    bool valid_n = false;
+    realw nx[5], ny[5], nz[5];
+    const bool has_next = PREFETCH == 1 && (g + (int)gridDim.x < a.end_group);
+    if (has_next) fetch(n + 1, ig_n, kind_n, valid_n, nx, ny, nz);
+    if (PREFETCH == 2 && g + (int)gridDim.x < a.end_group) {
+      // peek at the next batch's indices (the ring slot is released by the real fetch at the top of the loop)
+      const int sN = (n + 1) & 1;
+      mbar_wait(fullI(sN), ((n + 1) >> 1) & 1);
+      const int* ibn = s_ib + sN * GRP_IB_WORDS;
+      if (lane_ok) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const int gi = ibn[k * GRP_ROW + t] - 1;
+          if (gi >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.displ + 3 * (size_t)gi));
+        }
+      }
+    }
+
     // ---- second stage: i- and j-direction weak-form contractions, assembly ----
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
@@ -336,6 +400,16 @@ __global__ void __launch_bounds__(GRP_THREADS, 3) k_elastic_forces_grp(const Grp
     }
     // no barrier needed here: the next batch writes s_u (last read before the barrier above) and touches
     // s_f1/s_f2 only after its own first barrier, by which time every thread has finished the reads above
+    if (has_next) {
+      store_tile(nx, ny, nz);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        ig[k] = ig_n[k];
+        ux[k] = nx[k]; uy[k] = ny[k]; uz[k] = nz[k];
+      }
+      kind = kind_n;
+      valid = valid_n;
+    }
   }
 }
 
@@ -456,12 +530,22 @@ inline GroupStore* group_store_build(DeviceMesh* mp, const std::vector<std::vect
   return gs;
 }
 
-inline void launch_elastic_grp(DeviceMesh* mp, const GroupStore* gs, int segment, int use_atomics) {
+template <int PREFETCH, int STAGES, int MINB>
+inline void launch_elastic_grp_t(DeviceMesh* mp, const GrpArgs& a, int ng) {
   static bool configured[64] = {false};
   if (!configured[mp->device & 63]) {
-    CUDA_CHECK(cudaFuncSetAttribute(k_elastic_forces_grp, cudaFuncAttributeMaxDynamicSharedMemorySize, GRP_SMEM_BYTES));
+    CUDA_CHECK(cudaFuncSetAttribute(k_elastic_forces_grp<PREFETCH, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    GRP_SMEM_BYTES(STAGES)));
     configured[mp->device & 63] = true;
   }
+  int grid = 148 * MINB;  // persistent: MINB resident CTAs per SM
+  if (ng < grid) grid = ng;
+  k_elastic_forces_grp<PREFETCH, STAGES, MINB><<<grid, GRP_THREADS, GRP_SMEM_BYTES(STAGES), mp->compute_stream>>>(a);
+}
+
+bool launch_elastic_po_variant(DeviceMesh* mp, const GrpArgs& a, int ng);  // kernels_elastic_po.cuh
+
+inline void launch_elastic_grp(DeviceMesh* mp, const GroupStore* gs, int segment, int use_atomics) {
   GrpArgs a;
   a.first_group = gs->seg_first[segment];
   a.end_group = gs->seg_end[segment];
@@ -475,9 +559,15 @@ inline void launch_elastic_grp(DeviceMesh* mp, const GroupStore* gs, int segment
   a.xix_regular = mp->xix_regular;
   a.jacobian_regular = mp->jacobian_regular;
   a.use_atomics = use_atomics;
-  int grid = 148 * 3;  // persistent: 3 resident CTAs per SM
-  if (ng < grid) grid = ng;
-  k_elastic_forces_grp<<<grid, GRP_THREADS, GRP_SMEM_BYTES, mp->compute_stream>>>(a);
+  if (launch_elastic_po_variant(mp, a, ng)) return;
+  switch (mp->force_kernel_variant) {  // A/B variants (tools/bench_force_variants.py)
+    case 3: launch_elastic_grp_t<1, 8, 3>(mp, a, ng); break;
+    case 4: launch_elastic_grp_t<0, 4, 4>(mp, a, ng); break;
+    case 5: launch_elastic_grp_t<2, 4, 4>(mp, a, ng); break;
+    case 6: launch_elastic_grp_t<2, 8, 3>(mp, a, ng); break;
+    case 9: launch_elastic_grp_t<0, 8, 3>(mp, a, ng); break;
+    default: launch_elastic_grp_t<0, 4, 4>(mp, a, ng); break;
+  }
 }
 
 }  // namespace sb200

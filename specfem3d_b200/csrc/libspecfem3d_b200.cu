@@ -12,6 +12,7 @@
 #include "kernels_elastic.cuh"
 #include "kernels_elastic_col.cuh"
 #include "kernels_elastic_grp.cuh"
+#include "kernels_elastic_po.cuh"
 #include "kernels_misc.cuh"
 #include "pml.cuh"
 #include "halo_p2p.cuh"
@@ -700,7 +701,7 @@ extern "C" void SB200_FC(compute_forces_viscoelastic_cuda)(long* Mesh_pointer, i
   if ((*ATTENUATION != 0) != (mp->attenuation != 0)) exit_on_error("compute_forces_viscoelastic_cuda: ATTENUATION differs from prepare_fields_elastic_device");
   (void)COMPUTE_AND_STORE_STRAIN;
   const int num_elements = (*iphase == 1) ? *nspec_outer_elastic : *nspec_inner_elastic;
-  const bool grp = mp->force_kernel_variant == 0 && !mp->attenuation && !mp->compute_and_store_strain;
+  const bool grp = (mp->force_kernel_variant == 0 || mp->force_kernel_variant >= 3) && !mp->attenuation && !mp->compute_and_store_strain;
   if (num_elements > 0 && grp) {
     ensure_elastic_groups(mp, *nspec_outer_elastic, *nspec_inner_elastic);
     if (mp->use_mesh_coloring_gpu) {
