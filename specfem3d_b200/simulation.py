@@ -53,11 +53,11 @@ class Simulation:
 
     @property
     def ELASTIC_SIMULATION(self) -> bool:
-        return any(db.nspec_elastic > 0 for db in self.dbs)
+        return any(db.nspec_elastic > 0 for db in self.dbs if db is not None)
 
     @property
     def ACOUSTIC_SIMULATION(self) -> bool:
-        return any(db.nspec_acoustic > 0 for db in self.dbs)
+        return any(db.nspec_acoustic > 0 for db in self.dbs if db is not None)
 
     @property
     def nlength_seismogram(self) -> int:

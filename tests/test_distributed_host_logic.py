@@ -64,3 +64,18 @@ def test_gloo_world2_mass_assembly_and_exchange(tmp_path):
         got = np.load(tmp_path / f"rmassx_{r}.npy")
         assert np.array_equal(got, loc[r])  # same additions in the same order: bit-exact
         assert np.load(tmp_path / f"ok_{r}.npy")[0]
+
+
+def test_single_rank_view_of_a_partitioned_simulation():
+    """bench.py under torchrun builds only its own rank's database (the other slots stay None): the Simulation
+    properties the time loop reads must work on that view."""
+    import bench
+
+    spec, DT, gll, db, loc, sources, receivers, _ = bench.build_workload(2, 1, (4, 4, 2), 10)
+    from specfem3d_b200.simulation import Simulation
+
+    dbs = [None] * spec.nproc
+    dbs[1] = db
+    sim = Simulation(spec, DT, 10, dbs, gll, sources, receivers)
+    assert sim.ELASTIC_SIMULATION and not sim.ACOUSTIC_SIMULATION
+    assert sim.nlength_seismogram == 10
