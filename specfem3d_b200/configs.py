@@ -72,3 +72,15 @@ def cfg2(NSTEP: int = 1000, regular: bool = False) -> Simulation:
 
 def cfg5(nproc_xi: int, nproc_eta: int, NSTEP: int = 100) -> Simulation:
     return halfspace_scaled(256, 256, 128, nproc_xi, nproc_eta, NSTEP=NSTEP)
+
+
+def cpml_example(NSTEP: int = 2400, nproc_xi: int = 1, nproc_eta: int = 1) -> Simulation:
+    """The reference's own elastic C-PML example (EXAMPLES/applications/CPML_examples/
+    homogeneous_halfspace_HEX8_elastic_absorbing_CPML_5sides): the cfg1 box, C-PML 3 elements thick on the four sides
+    and the bottom, no Stacey, point force (1,-2,-1) x 1e10 with a 0.128 Hz Ricker wavelet at (67000, 67000, -30 km),
+    f0_FOR_PML 0.05555, DT 0.11, NSTEP 2400 (DATA/Par_file, DATA/FORCESOLUTION, REF_SEIS/output_solver.txt)."""
+    spec = BoxSpec(36, 36, 16, nproc_xi=nproc_xi, nproc_eta=nproc_eta, materials=(HALFSPACE,), stacey=False,
+                   pml_thickness=3, f0_for_pml=0.05555)
+    src = ForceSource(x=67000.0, y=67000.0, z=-30000.0, factor=1.0e10, comp=(1.0, -2.0, -1.0), hdur=0.128)
+    return make_simulation(spec, DT=0.11, NSTEP=NSTEP, sources=[src], stations=STATIONS_DEFAULT,
+                           SAVE_SEISMOGRAMS_VELOCITY=True, SAVE_SEISMOGRAMS_ACCELERATION=True)

@@ -139,4 +139,169 @@ void mg_scatter_coords(int64_t nspec, const int32_t* ibool, const double* loc, f
   for (int64_t o = 0; o < nspec * 125; ++o) glob[ibool[o] - 1] = (float)loc[o];
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// C-PML damping profiles (restates src/generate_databases/pml_set_local_dampingcoeff.f90:300-1840 in CUSTOM_REAL =
+// float arithmetic; the profile itself in double like pml_damping_profile_l :1946-1985).
+//   regions: 1 X, 2 Y, 3 Z, 4 XY, 5 XZ, 6 YZ, 7 XYZ  (setup/constants.h.in:240-246)
+//   glob[]  : x_origin,y_origin,z_origin, xoriginleft,xoriginright, yoriginback,yoriginfront, zoriginbottom,
+//             CPML_width_x,_y,_z, vp_max_all, ALPHA_MAX_x,_y,_z, min_distance_between_CPML_parameter   (16 floats)
+//   out     : K/d/alpha per axis, each [nspec_cpml][125]
+// Pass 1 fills the raw profiles, pass 2 separates alpha/beta values that come closer than
+// min_distance_between_CPML_parameter in edge and corner regions (:1446-1835).
+// Returns 0, or a negative code for the reference's `stop` conditions.
+static inline bool axis_on(int region, int axis) {  // axis 0 x, 1 y, 2 z
+  static const int on[8][3] = {{0,0,0},{1,0,0},{0,1,0},{0,0,1},{1,1,0},{1,0,1},{0,1,1},{1,1,1}};
+  return on[region][axis] != 0;
+}
+
+int mg_pml_damping(int64_t nspec_cpml, const int32_t* CPML_to_spec, const int32_t* CPML_regions, const int32_t* ibool,
+                   const float* xstore, const float* ystore, const float* zstore, const float* glob,
+                   float* K_x, float* K_y, float* K_z, float* d_x, float* d_y, float* d_z,
+                   float* a_x, float* a_y, float* a_z) {
+  const float origin[3] = {glob[0], glob[1], glob[2]};
+  const float org_lo[3] = {glob[3], glob[5], glob[7]};   // xoriginleft, yoriginback, zoriginbottom
+  const float org_hi[3] = {glob[4], glob[6], 0.f};       // xoriginright, yoriginfront, (no top PML)
+  const float width[3] = {glob[8], glob[9], glob[10]};
+  const float vp = glob[11];
+  const float amax[3] = {glob[12], glob[13], glob[14]};
+  const float mind = glob[15];
+  const float c2 = mind * 2.f, c4 = mind * 4.f;
+  const double NPOWER = 1.0, Rcoef = 0.001;
+  float* K[3] = {K_x, K_y, K_z};
+  float* D[3] = {d_x, d_y, d_z};
+  float* A[3] = {a_x, a_y, a_z};
+  const float* X[3] = {xstore, ystore, zstore};
+  int err = 0;
+
+  for (int64_t e = 0; e < nspec_cpml; ++e) {
+    const int64_t ispec = CPML_to_spec[e] - 1;
+    const int region = CPML_regions[e];
+    for (int p = 0; p < 125; ++p) {
+      const int64_t ig = ibool[ispec * 125 + p] - 1;
+      for (int ax = 0; ax < 3; ++ax) {
+        float Kv = 1.f, dv = 0.f, av = 0.f;
+        if (axis_on(region, ax)) {
+          const float c = X[ax][ig];
+          float abscissa;
+          if (c - origin[ax] > 0.f) {
+            if (ax == 2) { err = -1; continue; }  // top C-PML (PML_INSTEAD_OF_FREE_SURFACE) is not generated by this harness
+            abscissa = c - org_hi[ax];
+          } else if (c - origin[ax] < 0.f) {
+            abscissa = org_lo[ax] - c;
+          } else {
+            err = -2;
+            continue;
+          }
+          const float dist = abscissa / width[ax];
+          if (dist > 1.f) err = -3;
+          Kv = 1.f + (1.f - 1.f) * dist;
+          dv = -(float)(((NPOWER + 1.0) * (double)vp * std::log(Rcoef) / (2.0 * (double)width[ax])) *
+                        std::pow((double)dist, 1.2 * NPOWER));
+          av = amax[ax] * (1.f - dist);
+          if (Kv < 1.f || dv < 0.f) { Kv = 1.f; dv = 0.f; }
+          if (av < 0.f) err = -4;
+        }
+        K[ax][e * 125 + p] = Kv; D[ax][e * 125 + p] = dv; A[ax][e * 125 + p] = av;
+      }
+    }
+  }
+  if (err) return err;
+
+  auto sep2 = [&](float& a, float& b) { if (a >= b) a = b + c2; else b = a + c2; };             // :1989-2002
+  auto sep1 = [&](float& a, const float b) { if (a >= b) a = b + c2; else a = b + c4; };        // :2008-2023
+  auto near = [&](float a, float b) { return std::fabs(a - b) < mind; };
+
+  for (int64_t e = 0; e < nspec_cpml; ++e) {
+    const int region = CPML_regions[e];
+    if (region < 4) continue;
+    for (int p = 0; p < 125; ++p) {
+      const int64_t o = e * 125 + p;
+      if (region < 7) {
+        const int u = (region == 6) ? 1 : 0, v = (region == 4) ? 1 : 2;  // XY: (0,1), XZ: (0,2), YZ: (1,2)
+        float au = A[u][o], av = A[v][o];
+        const float Ku = K[u][o], Kv = K[v][o];
+        if (near(au, av)) sep2(au, av);
+        float bu = au + D[u][o] / Ku, bv = av + D[v][o] / Kv;
+        if (near(bu, av)) sep1(bu, av);
+        if (near(bv, au)) sep1(bv, au);
+        if (near(au, av) || near(bu, av) || near(bv, au)) return -5;
+        D[u][o] = (bu - au) * Ku; A[u][o] = au;
+        D[v][o] = (bv - av) * Kv; A[v][o] = av;
+      } else {
+        float al[3] = {A[0][o], A[1][o], A[2][o]};
+        // pairwise separation of the three alphas, third value moved out of the way (:1612-1714)
+        auto pair = [&](float& a, float& b, float& c) {
+          if (!near(a, b)) return;
+          if (a > b) a = b + c2; else b = a + c2;
+          const float mx = std::fmax(a, b), mn = std::fmin(a, b);
+          if (c > mx) {
+            if (near(c, mx)) c = mx + c2;
+          } else if (c < mn) {
+            if (near(c, mn)) {
+              if (a > b) { a = c + c4; b = c + c2; } else { b = c + c4; a = c + c2; }
+            }
+          } else {
+            if (a > b) { a = b + c4; c = b + c2; } else { b = a + c4; c = a + c2; }
+          }
+        };
+        pair(al[0], al[1], al[2]);
+        pair(al[0], al[2], al[1]);
+        pair(al[1], al[2], al[0]);
+        if (near(al[0], al[1]) || near(al[1], al[2]) || near(al[0], al[2])) return -6;
+        float be[3];
+        for (int ax = 0; ax < 3; ++ax) {
+          const float pa = al[(ax + 1) % 3], qa = al[(ax + 2) % 3];
+          float b = al[ax] + D[ax][o] / K[ax][o];
+          const float mx = std::fmax(pa, qa), mn = std::fmin(pa, qa);
+          if (b > mx) {
+            if (near(b, mx)) b = mx + c2;
+          } else if (b < mn) {
+            if (near(b, mn)) b = mx + c2;
+          } else {
+            if (near(b, mx)) b = mx + c2;
+            if (near(b, mn)) {
+              b = mn + c2;
+              if (near(b, mx)) b = mx + c2;
+            }
+          }
+          if (near(b, pa) || near(b, qa)) return -7;
+          be[ax] = b;
+        }
+        for (int ax = 0; ax < 3; ++ax) {
+          D[ax][o] = (be[ax] - al[ax]) * K[ax][o];
+          A[ax][o] = al[ax];
+        }
+      }
+    }
+  }
+  return 0;
+}
+
+// Elastic mass matrix with C-PML (define_mass_matrices_pml_elastic, src/shared/define_mass_matrices.f90:528-769):
+// regular elements first in element order, then the C-PML elements in CPML_to_spec order with the factor
+// K_x K_y K_z + (d_x K_y K_z + d_y K_x K_z + d_z K_x K_y) dt/2 (inactive axes carry K = 1, d = 0, which reproduces every
+// region's own formula), double products, float accumulation.
+void mg_mass_matrix_pml(int64_t nspec, const int32_t* ibool, const float* jacobian, const float* rho, const double* w3,
+                        const int32_t* is_elastic, const int32_t* is_CPML, int64_t nspec_cpml, const int32_t* CPML_to_spec,
+                        const float* K_x, const float* K_y, const float* K_z, const float* d_x, const float* d_y,
+                        const float* d_z, float deltat, float* rmass) {
+  for (int64_t e = 0; e < nspec; ++e) {
+    if (is_CPML[e] || !is_elastic[e]) continue;
+    for (int p = 0; p < 125; ++p) {
+      const int64_t o = e * 125 + p;
+      rmass[ibool[o] - 1] += (float)((double)jacobian[o] * w3[p] * (double)rho[o]);
+    }
+  }
+  for (int64_t c = 0; c < nspec_cpml; ++c) {
+    const int64_t e = CPML_to_spec[c] - 1;
+    if (!is_CPML[e] || !is_elastic[e]) continue;
+    for (int p = 0; p < 125; ++p) {
+      const int64_t o = e * 125 + p, q = c * 125 + p;
+      const double kx = K_x[q], ky = K_y[q], kz = K_z[q], dx = d_x[q], dy = d_y[q], dz = d_z[q];
+      const double f = kx * ky * kz + (dx * ky * kz + dy * kx * kz + dz * kx * ky) * (double)deltat / 2.0;
+      rmass[ibool[o] - 1] += (float)((double)jacobian[o] * w3[p] * (double)rho[o] * f);
+    }
+  }
+}
+
 }  // extern "C"

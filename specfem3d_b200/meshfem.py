@@ -96,6 +96,7 @@ class BoxSpec:
     stacey_instead_of_free_surface: bool = False
     # C-PML shell thickness in elements on xmin/xmax/ymin/ymax/bottom (0 = none)
     pml_thickness: int = 0
+    f0_for_pml: float = 0.05555  # f0_FOR_PML of the Par_file (dominant frequency the C-PML is tuned for)
 
     @property
     def nproc(self) -> int:
@@ -450,7 +451,7 @@ def build_partition(spec: BoxSpec, myrank: int, gll: Optional[GLL] = None, with_
                 np.concatenate(nrm), np.concatenate(jw))
 
     abs_faces = []
-    if spec.stacey:
+    if spec.stacey or spec.pml_thickness > 0:  # with C-PML the outer faces carry the Dirichlet condition instead
         abs_faces = [1, 2, 3, 4, 5] + ([6] if spec.stacey_instead_of_free_surface else [])
     (db.num_abs_boundary_faces, db.abs_boundary_ispec, db.abs_boundary_ijk, db.abs_boundary_normal,
      db.abs_boundary_jacobian2Dw) = face_set(abs_faces)
@@ -554,8 +555,13 @@ def build_partition(spec: BoxSpec, myrank: int, gll: Optional[GLL] = None, with_
     # --- C-PML flags (shell of given thickness on the five absorbing sides) ------------------------------------------
     t = spec.pml_thickness
     if t > 0:
-        pml = (eix < t) | (eix >= spec.nex_xi - t) | (eiy < t) | (eiy >= spec.nex_eta - t) | (eiz < t)
-        db.is_CPML = pml.astype(np.int32)
+        from .pml import region_code
+
+        fx = (eix < t) | (eix >= spec.nex_xi - t)
+        fy = (eiy < t) | (eiy >= spec.nex_eta - t)
+        fz = eiz < t
+        db.is_CPML = (fx | fy | fz).astype(np.int32)
+        db.extra["CPML_regions_of_spec"] = region_code(fx, fy, fz)
     else:
         db.is_CPML = np.zeros(nspec, dtype=np.int32)
     return db
@@ -573,9 +579,14 @@ def local_mass_matrices(spec: BoxSpec, db: Database, DT: float, gll: Optional[GL
     flat_ibool = db.ibool.reshape(-1, 125)
 
     if db.nspec_elastic:
-        rmass = np.zeros(nglob, dtype=np.float32)
-        mg.mg_mass_matrix(db.NSPEC_AB, _p(db.ibool), _p(db.jacobian_full), _p(db.rhostore), _p(w3),
-                          _p(db.ispec_is_elastic), 0, _p(rmass))
+        if "pml" in db.extra:
+            from .pml import mass_matrix_pml_elastic
+
+            rmass = mass_matrix_pml_elastic(db, DT, gll)
+        else:
+            rmass = np.zeros(nglob, dtype=np.float32)
+            mg.mg_mass_matrix(db.NSPEC_AB, _p(db.ibool), _p(db.jacobian_full), _p(db.rhostore), _p(w3),
+                              _p(db.ispec_is_elastic), 0, _p(rmass))
         rx = np.zeros(nglob, dtype=np.float32)
         ry = np.zeros(nglob, dtype=np.float32)
         rz = np.zeros(nglob, dtype=np.float32)
@@ -655,6 +666,12 @@ def build_all(spec: BoxSpec, DT: float, gll: Optional[GLL] = None) -> List[Datab
     """All partitions in one process with assembled + inverted mass matrices (used by tests and N=1 runs)."""
     gll = gll or GLL()
     dbs = [build_partition(spec, r, gll) for r in range(spec.nproc)]
+    if spec.pml_thickness > 0:
+        from .pml import set_local_dampingcoeff
+
+        if any(db.nspec_acoustic for db in dbs):
+            raise NotImplementedError("harness: C-PML is generated for elastic boxes only")
+        set_local_dampingcoeff(spec, dbs, spec.f0_for_pml)
     loc = [local_mass_matrices(spec, db, DT, gll) for db in dbs]
     for key in ("rmassx", "rmassy", "rmassz", "rmass_acoustic"):
         if all(key in l for l in loc):

@@ -67,3 +67,48 @@ def test_max_norm_matches_reference_log(oracle_run):
     assert abs(norms[5] - ref[5]) / ref[5] < 1e-5      # 2.24574184
     # single-precision summation order differs (4 ranks x OpenMP vs 4 MPI ranks): 1.1e-5 observed; bar = BASELINE's 1e-4
     assert abs(norms[500] - ref[500]) / ref[500] < 1e-4  # 828559.312
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# C-PML: the reference's own elastic C-PML example
+# EXAMPLES/applications/CPML_examples/homogeneous_halfspace_HEX8_elastic_absorbing_CPML_5sides, fixture
+# tests/golden/cpml_ref_seis.npz.  The mesh there comes from CUBIT (same 36x36x16 box, other element numbering); the
+# harness regenerates the box and the C-PML flags, damping profiles, mass matrix and convolution coefficients
+# (specfem3d_b200/pml.py), so this pins the host preparation and the oracle's C-PML solver together.
+# Default: the first CPML_NSTEP samples (direct P and S at all four stations plus ~30 s in which the side and bottom
+# layers are absorbing them); SPECFEM_B200_FULL_GOLDEN=1 runs all 2400 steps (5.6e-6 .. 1.0e-5 relative L2 measured).
+CPML_GOLD = os.path.join(os.path.dirname(__file__), "golden", "cpml_ref_seis.npz")
+CPML_NSTEP = 2400 if os.environ.get("SPECFEM_B200_FULL_GOLDEN") else 560
+
+
+def test_cpml_example_against_REF_SEIS():
+    from oracle.solver import OracleRun, set_num_threads
+    from specfem3d_b200.configs import cpml_example
+
+    set_num_threads(os.cpu_count() or 1)
+    sim = cpml_example(CPML_NSTEP)
+    P = sim.pml[0]
+    # REF_SEIS/output_solver.txt: 9036 C-PML elements, layer thickness 11166.6670 / 11166.6670 / 11250.0000 m, t0 = 9.375
+    assert P["NSPEC_CPML"] == 9036
+    assert np.allclose(P["CPML_width"], (11166.667, 11166.667, 11250.0), rtol=1e-7)
+    assert abs(sim.sources.t0 - 9.375) < 1e-12
+    gold = np.load(CPML_GOLD)
+    ref_norm = dict(zip(gold["maxnorm_step"].tolist(), gold["maxnorm_value"].tolist()))
+    run = OracleRun(sim)
+    norms = {}
+    for it in range(1, CPML_NSTEP + 1):
+        if it in (5, 100, 500):  # check_stability samples at the top of the step
+            norms[it] = run.max_norm_displ()
+        run.step()
+    assert np.allclose(sim.time_axis()[:CPML_NSTEP], gold["time"][:CPML_NSTEP], atol=2e-5)
+    worst = 0.0
+    for i, st in enumerate(("X20", "X30", "X40", "X50")):
+        for c, ch in enumerate("XYZ"):
+            ref = gold[f"{st}_{ch}"][:CPML_NSTEP].astype(np.float64)
+            syn = run.seis_d[i, :CPML_NSTEP, c].astype(np.float64)
+            err = np.linalg.norm(syn - ref) / np.linalg.norm(ref)
+            worst = max(worst, err)
+            assert err <= 1e-4, f"C-PML example {st}.MX{ch}: relative L2 {err:.3e}"
+    print(f"C-PML example: worst relative L2 vs REF_SEIS over {CPML_NSTEP} steps: {worst:.3e}")
+    for it, v in norms.items():
+        assert abs(v - ref_norm[it]) / ref_norm[it] < 1e-4, (it, v, ref_norm[it])
