@@ -735,7 +735,7 @@ extern "C" void SB200_FC(compute_forces_viscoelastic_cuda)(long* Mesh_pointer, i
       launch_elastic(mp, num_elements, list, 0, *deltat, /*use_atomics=*/1);
     }
   }
-  if (mp->pml_conditions && mp->NSPEC_CPML > 0) pml_compute_forces(mp, *iphase, num_elements, *deltat);
+  if (mp->pml_conditions && mp->NSPEC_CPML > 0) pml_compute_forces(mp, *iphase, *nspec_outer_elastic, *nspec_inner_elastic);
 }
 
 // =================================================================================================================

@@ -26,6 +26,8 @@ def factories():
         "viscoelastic": lambda: T.visco_sim(nstep=300),
         "ocean_source_in_solid": lambda: T.ocean_sim(nstep=300, source_in_water=False),
         "ocean_source_in_water": lambda: T.ocean_sim(nstep=300, source_in_water=True),
+        "cpml_irregular": lambda: T.pml_sim(nstep=300),
+        "cpml_regular": lambda: T.pml_sim(nstep=300, regular=True),
     }
 
 

@@ -342,3 +342,80 @@ def test_coupled_acoustic_elastic_time_loop_matches_oracle(device_lib, nproc, so
         assert np.abs(o.seis_p[irec]).max() > 0
         assert rel_l2(sp[irec, :, 0], o.seis_p[irec, :]) <= 1e-4, irec
     run.cleanup()
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# C-PML
+# -------------------------------------------------------------------------------------------------------------------
+def pml_sim(nproc=(1, 1), nstep=300, nex=(10, 10, 6), deform=0.1, regular=False):
+    """Small elastic box with a 2-element C-PML shell on the four sides and the bottom, no Stacey; the deformation
+    makes all nine metric terms non-trivial inside the layer too."""
+    from specfem3d_b200.sources_receivers import ForceSource
+
+    if regular:
+        spec = BoxSpec(nex[0], nex[1], nex[2], xmax=1000.0 * nex[0], ymax=1000.0 * nex[1], zmin=-1000.0 * nex[2],
+                       nproc_xi=nproc[0], nproc_eta=nproc[1], materials=(HALFSPACE,), stacey=False, pml_thickness=2,
+                       f0_for_pml=1.0)
+    else:
+        spec = BoxSpec(nex[0], nex[1], nex[2], xmax=1100.0 * nex[0], ymax=900.0 * nex[1], zmin=-1000.0 * nex[2],
+                       nproc_xi=nproc[0], nproc_eta=nproc[1], materials=(HALFSPACE,), deform=deform, stacey=False,
+                       pml_thickness=2, f0_for_pml=1.0)
+    src = [ForceSource(0.52 * spec.xmax, 0.47 * spec.ymax, 0.45 * spec.zmin, factor=1e10, comp=(1.0, -2.0, -1.0), hdur=1.5)]
+    sts = [Station("A", "XX", 0.31 * spec.xmax, 0.33 * spec.ymax, 0.0), Station("B", "XX", 0.67 * spec.xmax, 0.62 * spec.ymax, 0.0),
+           Station("C", "XX", 0.08 * spec.xmax, 0.5 * spec.ymax, 0.5 * spec.zmin)]  # C sits inside the C-PML layer
+    return make_simulation(spec, DT=0.012, NSTEP=nstep, sources=src, stations=sts)
+
+
+@pytest.mark.parametrize("case", ["irregular", "regular", "partitioned"])
+def test_cpml_time_loop_matches_oracle(device_lib, case):
+    """Forward run with C-PML elements through the ABI (PML_displ snapshots in update_displacement_cuda, the C-PML
+    force kernel, the Dirichlet condition, transfer_pml_displ_from_device) against the oracle's CPU C-PML solver."""
+    from oracle.solver import OracleRun
+    from specfem3d_b200.time_loop import DeviceRun
+
+    sim = pml_sim(nproc=(2, 2) if case == "partitioned" else (1, 1), regular=(case == "regular"))
+    assert sum(p["NSPEC_CPML"] for p in sim.pml) == 10 * 10 * 6 - 6 * 6 * 4
+    run = DeviceRun(sim).run()
+    o = OracleRun(sim).run()
+    sd = run.gather_seismograms("d")
+    assert np.abs(o.seis_d).max() > 0
+    for irec in range(sim.receivers.nrec):
+        for c in range(3):
+            assert rel_l2(sd[irec, :, c], o.seis_d[irec, :, c]) <= 1e-4, (irec, c)
+    for r, p in zip(run.ranks, o.parts):
+        assert rel_l2(r.fields_el()[0], p.displ) <= 1e-4
+        n = p.pml["NSPEC_CPML"]
+        if n:
+            old, new = np.zeros((n, 125, 3), np.float32), np.zeros((n, 125, 3), np.float32)
+            r.lib.transfer_pml_displ_from_device(3 * 125 * n, old, new, r.Mesh_pointer)
+            assert rel_l2(new, p.pml_state["new"]) <= 1e-4 and rel_l2(old, p.pml_state["old"]) <= 1e-4
+            # host -> device -> host round trip of the PML_displ layout conversion is exact
+            r.lib.transfer_pml_displ_to_device(3 * 125 * n, old, new, r.Mesh_pointer)
+            old2, new2 = np.zeros_like(old), np.zeros_like(new)
+            r.lib.transfer_pml_displ_from_device(3 * 125 * n, old2, new2, r.Mesh_pointer)
+            assert np.array_equal(old, old2) and np.array_equal(new, new2)
+    run.cleanup()
+
+
+def test_cpml_example_against_REF_SEIS_golden(device_lib):
+    """The reference's own elastic C-PML example on the GPU, all 2400 steps, against its REF_SEIS traces, plus the
+    property an absorbing layer exists for: the wavefield has left the box at the end of the run."""
+    from specfem3d_b200.configs import cpml_example
+    from specfem3d_b200.time_loop import DeviceRun
+
+    nstep = 2400
+    sim = cpml_example(nstep)
+    run = DeviceRun(sim)
+    peak = 0.0
+    for it in range(1, nstep + 1):
+        run.step()
+        if it % 100 == 0:
+            peak = max(peak, run.max_norm_displ())
+    sd = run.gather_seismograms("d")
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "cpml_ref_seis.npz"))
+    for i, st in enumerate(("X20", "X30", "X40", "X50")):
+        for c, ch in enumerate("XYZ"):
+            assert rel_l2(sd[i, :, c], gold[f"{st}_{ch}"]) <= 1e-4, (st, ch)
+    final = run.max_norm_displ()
+    assert final < 1e-3 * peak, (final, peak)  # REF_SEIS/output_solver.txt: 3.3e-4 m at step 100, 4e-10 m at step 2000
+    run.cleanup()

@@ -2,7 +2,7 @@
 oracle/_ref/libspecfem_ref_cuda.so by oracle/build_ref_cuda.sh).  Both libraries export the same Fortran-callable
 ABI, so the same host time loop drives them with byte-identical inputs.  This pins the product (and, transitively,
 the CPU oracle the other tests use) to the reference's real kernels for the physics where no Fortran build is
-possible in this image: attenuation, acoustic/elastic coupling, Stacey, sources, seismograms.
+possible in this image: attenuation, acoustic/elastic coupling, Stacey, C-PML, sources, seismograms.
 
 The reference library is the CHECKER here, never the thing shipped; it is built in the development container (where
 /root/reference exists) and travels to the GPU box as a prebuilt .so.  It runs in a helper process
@@ -28,7 +28,7 @@ def rel_l2(a, b):
 
 
 @pytest.mark.parametrize("name", ["elastic_irregular", "elastic_regular", "viscoelastic", "ocean_source_in_solid",
-                                  "ocean_source_in_water"])
+                                  "ocean_source_in_water", "cpml_irregular", "cpml_regular"])
 def test_against_reference_cuda_backend(device_lib, name, tmp_path):
     if not os.path.exists(REF_LIB):
         pytest.skip("oracle/_ref/libspecfem_ref_cuda.so not built (run oracle/build_ref_cuda.sh where /root/reference exists)")
