@@ -44,10 +44,13 @@ def forces_elastic_pml(p, iphase: int):
     if nel == 0 or pm["NSPEC_CPML"] == 0:
         return
     ph = np.ascontiguousarray(db.phase_ispec_inner_elastic[iphase - 1])
+    # with attenuation the moduli in memory are the unrelaxed ones (prepare_attenuation.f90 scales mustore/kappastore in place)
+    kappa = db.kappastore if p.att is None else p.att["kappastore"]
+    mu = db.mustore if p.att is None else p.att["mustore"]
     lib().oracle_compute_forces_viscoelastic_pml(
         c_int(nel), P(ph), P(db.ibool), P(db.irregular_element_number), P(db.xixstore), P(db.xiystore), P(db.xizstore),
         P(db.etaxstore), P(db.etaystore), P(db.etazstore), P(db.gammaxstore), P(db.gammaystore), P(db.gammazstore),
-        P(db.jacobianstore), c_float(db.xix_regular), c_float(db.jacobian_regular), P(db.kappastore), P(db.mustore),
+        P(db.jacobianstore), c_float(db.xix_regular), c_float(db.jacobian_regular), P(kappa), P(mu),
         P(db.rhostore), P(g.hprime_xx.ravel(order="F").copy()), P(g.hprimewgll_xx.ravel(order="F").copy()),
         P(g.wgllwgll_xy.ravel(order="F").copy()), P(g.wgllwgll_xz.ravel(order="F").copy()),
         P(g.wgllwgll_yz.ravel(order="F").copy()), P(np.ascontiguousarray(pm["wgll_cube"])), P(p.displ), P(p.veloc), P(p.accel),

@@ -544,6 +544,7 @@ inline void launch_elastic_grp_t(DeviceMesh* mp, const GrpArgs& a, int ng) {
 }
 
 bool launch_elastic_po_variant(DeviceMesh* mp, const GrpArgs& a, int ng);  // kernels_elastic_po.cuh
+bool launch_elastic_pk_variant(DeviceMesh* mp, const GrpArgs& a, int ng);  // kernels_elastic_pk.cuh
 
 inline void launch_elastic_grp(DeviceMesh* mp, const GroupStore* gs, int segment, int use_atomics) {
   GrpArgs a;
@@ -559,6 +560,7 @@ inline void launch_elastic_grp(DeviceMesh* mp, const GroupStore* gs, int segment
   a.xix_regular = mp->xix_regular;
   a.jacobian_regular = mp->jacobian_regular;
   a.use_atomics = use_atomics;
+  if (launch_elastic_pk_variant(mp, a, ng)) return;
   if (launch_elastic_po_variant(mp, a, ng)) return;
   switch (mp->force_kernel_variant) {  // A/B variants (tools/bench_force_variants.py)
     case 3: launch_elastic_grp_t<1, 8, 3>(mp, a, ng); break;

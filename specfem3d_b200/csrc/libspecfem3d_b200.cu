@@ -13,6 +13,7 @@
 #include "kernels_elastic_col.cuh"
 #include "kernels_elastic_grp.cuh"
 #include "kernels_elastic_po.cuh"
+#include "kernels_elastic_pk.cuh"
 #include "kernels_misc.cuh"
 #include "pml.cuh"
 #include "halo_p2p.cuh"

@@ -28,6 +28,7 @@ def factories():
         "ocean_source_in_water": lambda: T.ocean_sim(nstep=300, source_in_water=True),
         "cpml_irregular": lambda: T.pml_sim(nstep=300),
         "cpml_regular": lambda: T.pml_sim(nstep=300, regular=True),
+        "cfg3_small": lambda: T.cfg3_small(nstep=300),
     }
 
 

@@ -62,7 +62,7 @@ def small_sim(deform=0.15, regular=False, nproc=(1, 1), nstep=60, nex=(6, 6, 4),
 
 
 # -------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("variant", [1, 2, 4, 10, 0])
+@pytest.mark.parametrize("variant", [1, 2, 4, 10, 12, 15, 16, 17, 18, 30, 0])
 @pytest.mark.parametrize("regular", [False, True])
 def test_elastic_force_kernel_matches_oracle(device_lib, variant, regular):
     """a1: one call of compute_forces_viscoelastic_cuda (both phases) vs oracle_compute_forces_viscoelastic."""
@@ -418,4 +418,31 @@ def test_cpml_example_against_REF_SEIS_golden(device_lib):
             assert rel_l2(sd[i, :, c], gold[f"{st}_{ch}"]) <= 1e-4, (st, ch)
     final = run.max_norm_displ()
     assert final < 1e-3 * peak, (final, peak)  # REF_SEIS/output_solver.txt: 3.3e-4 m at step 100, 4e-10 m at step 2000
+    run.cleanup()
+
+
+def cfg3_small(nproc=(1, 1), nstep=300):
+    """BASELINE config 3 in small: layered viscoelastic model (3 SLS) inside a C-PML shell."""
+    spec = BoxSpec(10, 10, 6, xmax=1100.0 * 10, ymax=900.0 * 10, zmin=-1000.0 * 6, nproc_xi=nproc[0], nproc_eta=nproc[1],
+                   materials=VISCO, layer_material=[0, 0, 0, 1, 1, 1], deform=0.1, stacey=False, pml_thickness=2, f0_for_pml=1.0)
+    src = [CMTSource(0.52 * spec.xmax, 0.47 * spec.ymax, 0.45 * spec.zmin, CMT_SMALL, hdur=0.4)]
+    sts = [Station("A", "XX", 0.31 * spec.xmax, 0.33 * spec.ymax, 0.0), Station("B", "XX", 0.67 * spec.xmax, 0.62 * spec.ymax, 0.0)]
+    return make_simulation(spec, DT=0.008, NSTEP=nstep, sources=src, stations=sts, attenuation=True)
+
+
+@pytest.mark.parametrize("nproc", [(1, 1), (2, 1)])
+def test_cfg3_attenuation_with_cpml_matches_oracle(device_lib, nproc):
+    from oracle.solver import OracleRun
+    from specfem3d_b200.time_loop import DeviceRun
+
+    sim = cfg3_small(nproc=nproc)
+    run = DeviceRun(sim).run()
+    o = OracleRun(sim).run()
+    sd = run.gather_seismograms("d")
+    assert np.abs(o.seis_d).max() > 0
+    for irec in range(sim.receivers.nrec):
+        for c in range(3):
+            assert rel_l2(sd[irec, :, c], o.seis_d[irec, :, c]) <= 1e-4, (irec, c)
+    for r, p in zip(run.ranks, o.parts):
+        assert rel_l2(r.fields_el()[0], p.displ) <= 1e-4
     run.cleanup()
