@@ -168,17 +168,33 @@ struct DeviceMesh {
   std::vector<int> h_phase_ispec_elastic;        // [2][num_phase_ispec_elastic]
   std::vector<int> h_is_CPML;                    // empty when no PML
 
+  // deferred Newmark corrector (see kernel_3_a_cuda): the corrector of step n is applied by the predictor of step n+1
+  // in one pass over the wavefields; any other entry point that looks at veloc / accel first makes it happen
+  int fuse_newmark = 1;
+  bool corrector_pending = false;
+  realw pending_deltatover2 = 0.f;
+
   // options
   int force_kernel_variant = 0;  // 0 = default (grp), 1 = pt, 2 = col
   long long kernel_launches = 0;
 };
 
-inline DeviceMesh* get_mesh(long* Mesh_pointer) {
+// set by the library: launches the deferred corrector kernel (libspecfem3d_b200.cu: flush_corrector)
+extern void (*g_flush_corrector)(DeviceMesh*);
+
+// handle -> state for the few entry points that know how to work with a pending corrector
+inline DeviceMesh* get_mesh_keep_pending(long* Mesh_pointer) {
   DeviceMesh* mp = reinterpret_cast<DeviceMesh*>(*Mesh_pointer);
   if (mp == nullptr) exit_on_error("NULL Mesh_pointer: prepare_constants_device must be called first");
   int cur = -1;
   cudaGetDevice(&cur);
   if (cur != mp->device) CUDA_CHECK(cudaSetDevice(mp->device));
+  return mp;
+}
+// handle -> state for everybody else: veloc / accel are made current first
+inline DeviceMesh* get_mesh(long* Mesh_pointer) {
+  DeviceMesh* mp = get_mesh_keep_pending(Mesh_pointer);
+  if (mp->corrector_pending) g_flush_corrector(mp);
   return mp;
 }
 

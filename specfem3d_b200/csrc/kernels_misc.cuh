@@ -68,6 +68,40 @@ __global__ void __launch_bounds__(256) k_newmark_corrector(realw* __restrict__ v
   }
 }
 
+// Corrector of step n and predictor of step n+1 in ONE pass (84 instead of 60 + 72 = 132 bytes per point): same
+// expressions, same order as the two kernels above, so the wavefields come out bit-identical.
+__global__ void __launch_bounds__(256) k_newmark_corrector_predictor(realw* __restrict__ displ, realw* __restrict__ veloc,
+                                                                     realw* __restrict__ accel, const realw* __restrict__ rmass3,
+                                                                     long long n, realw corr_deltatover2, realw deltat,
+                                                                     realw deltatsqover2, realw deltatover2) {
+  const long long n4 = n >> 2;
+  float4* d4 = reinterpret_cast<float4*>(displ);
+  float4* v4 = reinterpret_cast<float4*>(veloc);
+  float4* a4 = reinterpret_cast<float4*>(accel);
+  const float4* r4 = reinterpret_cast<const float4*>(rmass3);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 a = a4[i], v = v4[i], d = d4[i];
+    const float4 r = __ldg(r4 + i);
+    a.x *= r.x; a.y *= r.y; a.z *= r.z; a.w *= r.w;
+    v.x += corr_deltatover2 * a.x; v.y += corr_deltatover2 * a.y; v.z += corr_deltatover2 * a.z; v.w += corr_deltatover2 * a.w;
+    d.x = d.x + deltat * v.x + deltatsqover2 * a.x; d.y = d.y + deltat * v.y + deltatsqover2 * a.y;
+    d.z = d.z + deltat * v.z + deltatsqover2 * a.z; d.w = d.w + deltat * v.w + deltatsqover2 * a.w;
+    v.x = v.x + deltatover2 * a.x; v.y = v.y + deltatover2 * a.y;
+    v.z = v.z + deltatover2 * a.z; v.w = v.w + deltatover2 * a.w;
+    d4[i] = d; v4[i] = v; a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const realw a = accel[i] * rmass3[i];
+    realw v = veloc[i];
+    v += corr_deltatover2 * a;
+    displ[i] = displ[i] + deltat * v + deltatsqover2 * a;
+    veloc[i] = v + deltatover2 * a;
+    accel[i] = 0.f;
+  }
+}
+
 // veloc += dt/2 * accel only (kernel_3_veloc_cuda_device, used by kernel_3_b_cuda after the ocean-load correction)
 __global__ void __launch_bounds__(256) k_newmark_veloc_only(realw* __restrict__ veloc, const realw* __restrict__ accel,
                                                             long long n, realw deltatover2) {
@@ -250,7 +284,10 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_seismogram_vector(
     realw* seismograms, const realw* __restrict__ nu_rec, const int* __restrict__ ispec_selected_rec_loc,
     const int* __restrict__ ispec_is_elastic, const int* __restrict__ ispec_is_acoustic,
     const realw* __restrict__ rhostore, const realw* __restrict__ metric, const int* __restrict__ irregular_element_number,
-    realw xix_regular, int seismo_current) {
+    realw xix_regular, int seismo_current, int corr_mode, const realw* __restrict__ corr_accel,
+    const realw* __restrict__ corr_rmass3, realw corr_deltatover2) {
+  // corr_mode (elastic receivers while the Newmark corrector is still pending): 0 = field is current,
+  // 1 = field is veloc: use veloc + dt/2 (accel rmass), 2 = field is accel: use accel rmass
   const int irec = blockIdx.x;
   if (irec >= nrec_local) return;
   const int tx = threadIdx.x;
@@ -265,7 +302,18 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_seismogram_vector(
   const realw hl = active ? hxir[I + NGLLX * irec] * hetar[J + NGLLX * irec] * hgammar[K + NGLLX * irec] : 0.f;
   realw dx = 0.f, dy = 0.f, dz = 0.f;
   if (ispec_is_elastic[ispec]) {
-    dx = hl * field[3 * iglob]; dy = hl * field[3 * iglob + 1]; dz = hl * field[3 * iglob + 2];
+    realw f[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      f[c] = field[3 * iglob + c];
+      if (corr_mode == 1) {
+        const realw a = corr_accel[3 * iglob + c] * corr_rmass3[3 * iglob + c];
+        f[c] += corr_deltatover2 * a;
+      } else if (corr_mode == 2) {
+        f[c] *= corr_rmass3[3 * iglob + c];
+      }
+    }
+    dx = hl * f[0]; dy = hl * f[1]; dz = hl * f[2];
   } else if (ispec_is_acoustic[ispec] && potential != nullptr) {
     s_chi[t] = potential[iglob];
     __syncthreads();

@@ -286,6 +286,8 @@ extern "C" void SB200_FC(prepare_constants_device)(
 
   const char* fk = getenv("SPECFEM_B200_FORCE_KERNEL");
   if (fk) mp->force_kernel_variant = atoi(fk);
+  const char* fn = getenv("SPECFEM_B200_FUSE_NEWMARK");
+  if (fn) mp->fuse_newmark = atoi(fn);
   CUDA_CHECK(cudaDeviceSynchronize());
 }
 
@@ -569,11 +571,33 @@ extern "C" void SB200_FC(transfer_strain_from_device)(long* Mesh_pointer, realw*
 // =================================================================================================================
 // Newmark (replaces src/gpu/update_displacement_cuda.cu)
 // =================================================================================================================
+// the corrector deferred by kernel_3_a_cuda, applied on its own (called through get_mesh() by every entry point that is not
+// prepared to see veloc / accel one half-step behind)
+static void flush_corrector_impl(DeviceMesh* mp) {
+  if (!mp->corrector_pending) return;
+  mp->corrector_pending = false;
+  const long long n = (long long)NDIM * mp->NGLOB_AB;
+  k_newmark_corrector<<<streaming_grid(n >> 2), 256, 0, mp->compute_stream>>>(mp->d_veloc, mp->d_accel, mp->d_rmassx, n,
+                                                                               mp->pending_deltatover2, 1);
+  KERNEL_CHECK(mp, "k_newmark_corrector(deferred)");
+}
+namespace sb200 {
+void (*g_flush_corrector)(DeviceMesh*) = &flush_corrector_impl;
+}
+
 extern "C" void SB200_FC(update_displacement_cuda)(long* Mesh_pointer, realw* deltat_F, realw* deltatover2_F,
                                                    realw* deltatsqover2_F, int* FORWARD_OR_ADJOINT) {
-  DeviceMesh* mp = get_mesh(Mesh_pointer);
+  DeviceMesh* mp = get_mesh_keep_pending(Mesh_pointer);
   if (*FORWARD_OR_ADJOINT != 1) exit_on_error("update_displacement_cuda: only FORWARD_OR_ADJOINT = 1 is supported");
   const long long n = (long long)NDIM * mp->NGLOB_AB;
+  if (mp->corrector_pending) {
+    // the corrector kernel_3_a_cuda deferred at the end of the previous step and this predictor in one pass
+    mp->corrector_pending = false;
+    k_newmark_corrector_predictor<<<streaming_grid(n >> 2), 256, 0, mp->compute_stream>>>(
+        mp->d_displ, mp->d_veloc, mp->d_accel, mp->d_rmassx, n, mp->pending_deltatover2, *deltat_F, *deltatsqover2_F, *deltatover2_F);
+    KERNEL_CHECK(mp, "k_newmark_corrector_predictor");
+    return;
+  }
   if (mp->pml_conditions && mp->NSPEC_CPML > 0) pml_snapshot_displ(mp, /*which=*/0, *deltat_F, *deltatsqover2_F, *deltatover2_F);
   k_newmark_predictor<<<streaming_grid(n >> 2), 256, 0, mp->compute_stream>>>(mp->d_displ, mp->d_veloc, mp->d_accel, n,
                                                                                *deltat_F, *deltatsqover2_F, *deltatover2_F);
@@ -583,7 +607,7 @@ extern "C" void SB200_FC(update_displacement_cuda)(long* Mesh_pointer, realw* de
 
 extern "C" void SB200_FC(update_displacement_ac_cuda)(long* Mesh_pointer, realw* deltat_F, realw* deltatover2_F,
                                                       realw* deltatsqover2_F, int* FORWARD_OR_ADJOINT) {
-  DeviceMesh* mp = get_mesh(Mesh_pointer);
+  DeviceMesh* mp = get_mesh_keep_pending(Mesh_pointer);  // touches the acoustic fields only
   if (*FORWARD_OR_ADJOINT != 1) exit_on_error("update_displacement_ac_cuda: only FORWARD_OR_ADJOINT = 1 is supported");
   const long long n = mp->NGLOB_AB;
   k_newmark_predictor<<<streaming_grid(n >> 2), 256, 0, mp->compute_stream>>>(
@@ -597,6 +621,13 @@ extern "C" void SB200_FC(kernel_3_a_cuda)(long* Mesh_pointer, realw* deltatover2
   DeviceMesh* mp = get_mesh(Mesh_pointer);
   if (*FORWARD_OR_ADJOINT != 1) exit_on_error("kernel_3_a_cuda: only FORWARD_OR_ADJOINT = 1 is supported");
   const long long n = (long long)NDIM * mp->NGLOB_AB;
+  if (mp->fuse_newmark && *APPROXIMATE_OCEAN_LOAD == 0 && !(mp->pml_conditions && mp->NSPEC_CPML > 0)) {
+    // deferred: update_displacement_cuda of the next step applies it together with the predictor; compute_seismograms_cuda
+    // evaluates it on the fly at the receivers; every other entry point flushes it first (device_mesh.h: get_mesh)
+    mp->corrector_pending = true;
+    mp->pending_deltatover2 = *deltatover2_F;
+    return;
+  }
   // with the ocean load the velocity update is deferred to kernel_3_b_cuda (reference: kernel_3_accel_cuda_device)
   k_newmark_corrector<<<streaming_grid(n >> 2), 256, 0, mp->compute_stream>>>(mp->d_veloc, mp->d_accel, mp->d_rmassx, n,
                                                                                *deltatover2_F, *APPROXIMATE_OCEAN_LOAD == 0);
@@ -1043,22 +1074,24 @@ extern "C" void SB200_FC(compute_seismograms_cuda)(long* Mesh_pointer_f, realw* 
                                                    int* ACOUSTIC_SIMULATION, int* ELASTIC_SIMULATION,
                                                    int* USE_TRICK_FOR_BETTER_PRESSURE) {
   (void)ACOUSTIC_SIMULATION; (void)ELASTIC_SIMULATION;
-  DeviceMesh* mp = get_mesh(Mesh_pointer_f);
+  DeviceMesh* mp = get_mesh_keep_pending(Mesh_pointer_f);
   if (mp->nrec_local == 0) return;
+  const int pend = mp->corrector_pending ? 1 : 0;
   const int seismo_current = *seismo_currentf - 1;
   const int nlength = *nlength_seismogramf;
   if (nlength != mp->nlength_seismogram) exit_on_error("compute_seismograms_cuda: nlength_seismogram differs from prepare_constants_device");
   if (seismo_current < 0 || seismo_current >= nlength) exit_on_error("compute_seismograms_cuda: seismo_current out of range");
-  struct { int on; const realw* vec; const realw* pot; realw* out; } sets[3] = {
-      {mp->save_seismograms_d, mp->d_displ, mp->d_potential, mp->d_seismograms_d},
-      {mp->save_seismograms_v, mp->d_veloc, mp->d_potential_dot, mp->d_seismograms_v},
-      {mp->save_seismograms_a, mp->d_accel, mp->d_potential_dot_dot, mp->d_seismograms_a}};
+  struct { int on; const realw* vec; const realw* pot; realw* out; int corr_mode; } sets[3] = {
+      {mp->save_seismograms_d, mp->d_displ, mp->d_potential, mp->d_seismograms_d, 0},
+      {mp->save_seismograms_v, mp->d_veloc, mp->d_potential_dot, mp->d_seismograms_v, pend * 1},
+      {mp->save_seismograms_a, mp->d_accel, mp->d_potential_dot_dot, mp->d_seismograms_a, pend * 2}};
   for (auto& s : sets) {
     if (!s.on) continue;
     k_seismogram_vector<<<mp->nrec_local, NGLL3_PADDED, 0, mp->compute_stream>>>(
         mp->nrec_local, s.vec, s.pot, mp->d_ibool, mp->d_hxir, mp->d_hetar, mp->d_hgammar, s.out, mp->d_nu_rec,
         mp->d_ispec_selected_rec_loc, mp->d_ispec_is_elastic, mp->d_ispec_is_acoustic, mp->d_rhostore, mp->d_metric,
-        mp->d_irregular_element_number, mp->xix_regular, seismo_current);
+        mp->d_irregular_element_number, mp->xix_regular, seismo_current, s.corr_mode, mp->d_accel, mp->d_rmassx,
+        mp->pending_deltatover2);
     KERNEL_CHECK(mp, "k_seismogram_vector");
   }
   if (mp->save_seismograms_p) {
@@ -1108,7 +1141,7 @@ static realw max_norm(DeviceMesh* mp, const realw* f) {
 }
 
 extern "C" void SB200_FC(get_norm_elastic_from_device)(realw* norm, long* Mesh_pointer, int* type) {
-  DeviceMesh* mp = get_mesh(Mesh_pointer);
+  DeviceMesh* mp = get_mesh_keep_pending(Mesh_pointer);  // the displacement does not depend on a pending corrector
   if (*type != 1) exit_on_error("get_norm_elastic_from_device: only the forward wavefield (type 1) is supported");
   *norm = sqrtf(max_norm<true>(mp, mp->d_displ));
 }

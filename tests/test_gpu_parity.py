@@ -181,7 +181,8 @@ def test_cfg1_against_REF_SEIS_golden(device_lib):
     run.cleanup()
     sim2 = cfg1(2, 2, 500)
     run2 = DeviceRun(sim2).run()
-    assert abs(run2.max_norm_displ() - ref500) / ref500 < 1e-5
+    # atomics order is not reproducible run to run: 0.9e-5 .. 1.3e-5 observed (the CPU oracle sits at 1.1e-5); bar = BASELINE 1e-4
+    assert abs(run2.max_norm_displ() - ref500) / ref500 < 1e-4
     run2.cleanup()
 
 
@@ -446,3 +447,59 @@ def test_cfg3_attenuation_with_cpml_matches_oracle(device_lib, nproc):
     for r, p in zip(run.ranks, o.parts):
         assert rel_l2(r.fields_el()[0], p.displ) <= 1e-4
     run.cleanup()
+
+
+def test_deferred_corrector(device_lib):
+    """kernel_3_a_cuda defers the Newmark corrector so that update_displacement_cuda of the next step applies it together
+    with the predictor in one pass, and compute_seismograms_cuda evaluates it on the fly at the receivers.
+    (a) the element-wise part is deterministic: corrector + seismogram sample + predictor on given fields must be
+        bit-identical to the unfused sequence;
+    (b) whole runs (atomics order differs run to run) agree to rounding, with one launch less per rank and step."""
+    from specfem3d_b200.time_loop import DeviceRank, DeviceRun
+
+    # ---- (a) ----
+    res = {}
+    for fuse in ("1", "0"):
+        os.environ["SPECFEM_B200_FUSE_NEWMARK"] = fuse
+        sim = small_sim(nstep=4, nex=(6, 6, 4))
+        sim.SAVE_SEISMOGRAMS_VELOCITY = sim.SAVE_SEISMOGRAMS_ACCELERATION = True
+        f = smooth_fields(sim)[0]
+        f["accel"] = (0.37 * f["veloc"] + 0.11 * f["displ"]).astype(np.float32)
+        sim.initial_fields = [f]
+        r = DeviceRank(sim, 0, device_lib).prepare()
+        L, M = r.lib, r.Mesh_pointer
+        dt, dt2, dtsq2 = float(sim.deltat), float(sim.deltatover2), float(sim.deltatsqover2)
+        L.kernel_3_a_cuda(M, dt2, dt2, 0, 1)
+        L.compute_seismograms_cuda(M, r.seismograms_d, r.seismograms_v, r.seismograms_a, r.seismograms_p, 1,
+                                   sim.nlength_seismogram, 1, 1, 0, 1, 0)  # it == it_end: flushes the buffers to the host
+        seis = [r.seismograms_d.copy(), r.seismograms_v.copy(), r.seismograms_a.copy()]
+        L.update_displacement_cuda(M, dt, dt2, dtsq2, 1)
+        fields = r.fields_el()
+        L.kernel_3_a_cuda(M, dt2, dt2, 0, 1)
+        fields2 = r.fields_el()  # transfer_fields_el_from_device flushes a pending corrector
+        res[fuse] = (seis, fields, fields2, r.kernel_launches())
+        r.cleanup()
+    for a, b in zip(res["1"][0], res["0"][0]):
+        assert np.abs(b).max() > 0 and np.array_equal(a, b)
+    for k in (1, 2):
+        for n, (a, b) in enumerate(zip(res["1"][k], res["0"][k])):
+            assert np.array_equal(a, b)
+            assert np.abs(b).max() > 0 or n == 2  # accel is zero after the predictor (no force computation in between)
+    assert res["1"][3] == res["0"][3] - 1
+
+    # ---- (b) ----
+    out = {}
+    for fuse in ("1", "0"):
+        os.environ["SPECFEM_B200_FUSE_NEWMARK"] = fuse
+        sim = small_sim(nproc=(2, 1), nstep=120, nex=(8, 8, 4))
+        sim.SAVE_SEISMOGRAMS_VELOCITY = sim.SAVE_SEISMOGRAMS_ACCELERATION = True
+        run = DeviceRun(sim).run()
+        out[fuse] = ([run.gather_seismograms(w) for w in "dva"], [r.fields_el() for r in run.ranks], run.kernel_launches())
+        run.cleanup()
+    os.environ.pop("SPECFEM_B200_FUSE_NEWMARK")
+    for a, b in zip(out["1"][0], out["0"][0]):
+        assert np.abs(b).max() > 0 and rel_l2(a, b) <= 2e-5
+    for fa, fb in zip(out["1"][1], out["0"][1]):
+        for a, b in zip(fa, fb):
+            assert rel_l2(a, b) <= 1e-4  # accel carries the run-to-run noise of the atomics order (3.6e-5 observed)
+    assert out["1"][2] < out["0"][2]
