@@ -97,6 +97,9 @@ class BoxSpec:
     # C-PML shell thickness in elements on xmin/xmax/ymin/ymax/bottom (0 = none)
     pml_thickness: int = 0
     f0_for_pml: float = 0.05555  # f0_FOR_PML of the Par_file (dominant frequency the C-PML is tuned for)
+    # USE_MESH_COLORING_GPU: elements are permuted into colour order (outer colours, then inner; elastic before acoustic)
+    # and the force kernels run colour by colour without atomics (setup_color_perm.f90 semantics)
+    mesh_coloring: bool = False
 
     @property
     def nproc(self) -> int:
@@ -564,7 +567,65 @@ def build_partition(spec: BoxSpec, myrank: int, gll: Optional[GLL] = None, with_
         db.extra["CPML_regions_of_spec"] = region_code(fx, fy, fz)
     else:
         db.is_CPML = np.zeros(nspec, dtype=np.int32)
+    if spec.mesh_coloring:
+        _apply_mesh_coloring(spec, db)
     return db
+
+
+def _apply_mesh_coloring(spec: BoxSpec, db: Database) -> None:
+    """USE_MESH_COLORING_GPU for a structured slab: what setup_color_perm (src/specfem3D/setup_color_perm.f90) leaves
+    behind -- elements permuted so that every domain is ordered [outer colour 1.. | inner colour 1..], elastic elements
+    first, and ``num_elem_colors_*`` holding the colour sizes.  Elements of one colour share no GLL point, so the device
+    can accumulate without atomics.  The colouring itself is the parity 8-colouring of the structured grid, not the
+    Droux algorithm of get_perm_color.f90 (the device contract only needs validity; colour parity with the reference's
+    permutation is unpinned by the reference's tests)."""
+    nspec = db.NSPEC_AB
+    eix, eiy, eiz = db.extra["eijk"]
+    colour = (eix - db.ix0) % 2 + 2 * ((eiy - db.iy0) % 2) + 4 * (eiz % 2)
+    inner = db.ispec_is_inner.astype(bool)
+    perm_parts, counts = [], {}
+    for dom, mask in (("elastic", db.ispec_is_elastic.astype(bool)), ("acoustic", db.ispec_is_acoustic.astype(bool))):
+        n_out, n_in = [], []
+        for phase_inner, acc in ((False, n_out), (True, n_in)):
+            for col in range(8):
+                idx = np.nonzero(mask & (inner == phase_inner) & (colour == col))[0]
+                if len(idx):
+                    perm_parts.append(idx)
+                    acc.append(len(idx))
+        counts[dom] = (n_out, n_in)
+    perm = np.concatenate(perm_parts)  # new position -> old element
+    assert len(perm) == nspec
+    inv = np.empty(nspec, np.int64)
+    inv[perm] = np.arange(nspec)
+
+    for name in ("ibool", "irregular_element_number", "kappastore", "mustore", "rhostore", "rho_vp", "rho_vs", "qkappa", "qmu",
+                 "jacobian_full", "ispec_is_elastic", "ispec_is_acoustic", "ispec_is_inner", "is_CPML"):
+        a = getattr(db, name)
+        if a is not None:
+            setattr(db, name, np.ascontiguousarray(a[perm]))
+    db.extra["eijk"] = tuple(a[perm] for a in db.extra["eijk"])
+    db.extra["corners"] = np.ascontiguousarray(db.extra["corners"][perm])
+    if "CPML_regions_of_spec" in db.extra:
+        db.extra["CPML_regions_of_spec"] = db.extra["CPML_regions_of_spec"][perm]
+    for name, cnt in (("abs_boundary_ispec", db.num_abs_boundary_faces), ("free_surface_ispec", db.num_free_surface_faces),
+                      ("coupling_ac_el_ispec", db.num_coupling_ac_el_faces)):
+        a = getattr(db, name)
+        if a is not None and cnt > 0:
+            setattr(db, name, (inv[a[:cnt] - 1] + 1).astype(np.int32))
+    # phase lists in the new numbering: contiguous ranges, outer first
+    first = 0
+    for dom in ("elastic", "acoustic"):
+        n_out, n_in = sum(counts[dom][0]), sum(counts[dom][1])
+        nph = max(n_out, n_in, 1)
+        ph = np.zeros((2, nph), np.int32)
+        ph[0, :n_out] = np.arange(first + 1, first + n_out + 1)
+        ph[1, :n_in] = np.arange(first + n_out + 1, first + n_out + n_in + 1)
+        setattr(db, f"phase_ispec_inner_{dom}", ph)
+        setattr(db, f"num_phase_ispec_{dom}", nph)
+        first += n_out + n_in
+        db.extra[f"num_colors_outer_{dom}"] = len(counts[dom][0])
+        db.extra[f"num_colors_inner_{dom}"] = len(counts[dom][1])
+        db.extra[f"num_elem_colors_{dom}"] = np.array(counts[dom][0] + counts[dom][1] + [0], np.int32)
 
 
 # ----------------------------------------------------------------------------------------------------------------

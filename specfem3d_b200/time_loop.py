@@ -105,8 +105,8 @@ class DeviceRank:
             db.ibool_interfaces_ext_mesh, H["hprime_xx"], H["hprimewgll_xx"], H["wgllwgll_xy"], H["wgllwgll_xz"],
             H["wgllwgll_yz"], int(sim.spec.stacey), db.abs_boundary_ispec, db.abs_boundary_ijk, db.abs_boundary_normal,
             db.abs_boundary_jacobian2Dw, db.num_abs_boundary_faces, db.ispec_is_inner, NSOURCES, nsources_local,
-            H["sourcearrays"], H["islice_src"], H["ispec_src"], H["ispec_rec"], nrec, self.nrec_local, 1, 0,
-            db.nspec_acoustic, db.nspec_elastic, db.ispec_is_acoustic, db.ispec_is_elastic, self.rank, 0, H["hxir"],
+            H["sourcearrays"], H["islice_src"], H["ispec_src"], H["ispec_rec"], nrec, self.nrec_local, 1,
+            int(sim.spec.mesh_coloring), db.nspec_acoustic, db.nspec_elastic, db.ispec_is_acoustic, db.ispec_is_elastic, self.rank, 0, H["hxir"],
             H["hetar"], H["hgammar"], H["nu_rec"], H["nu_source"], H["islice_rec"], sim.nlength_seismogram,
             int(sim.SAVE_SEISMOGRAMS_DISPLACEMENT), int(sim.SAVE_SEISMOGRAMS_VELOCITY),
             int(sim.SAVE_SEISMOGRAMS_ACCELERATION), int(sim.SAVE_SEISMOGRAMS_PRESSURE), 1, 0, 0,
@@ -114,12 +114,17 @@ class DeviceRank:
 
         dummy = np.zeros(1, np.float32)
         idummy = np.zeros(1, np.int32)
+        col = {}
+        for dom in ("elastic", "acoustic"):  # setup_color_perm.f90: colour counts per domain (retained by the library)
+            H["num_elem_colors_" + dom] = db.extra.get("num_elem_colors_" + dom, idummy)
+            col[dom] = (int(db.extra.get("num_colors_outer_" + dom, 0)), int(db.extra.get("num_colors_inner_" + dom, 0)),
+                        H["num_elem_colors_" + dom])
         if self.ACOUSTIC:
             L.prepare_fields_acoustic_device(
                 self.Mesh_pointer, db.rmass_acoustic, db.rhostore, db.kappastore, db.num_phase_ispec_acoustic,
                 db.phase_ispec_inner_acoustic, 0, db.num_free_surface_faces, db.free_surface_ispec, db.free_surface_ijk,
                 0, dummy, int(sim.ELASTIC_SIMULATION), db.num_coupling_ac_el_faces, db.coupling_ac_el_ispec,
-                db.coupling_ac_el_ijk, db.coupling_ac_el_normal, db.coupling_ac_el_jacobian2Dw, 0, 0, idummy)
+                db.coupling_ac_el_ijk, db.coupling_ac_el_normal, db.coupling_ac_el_jacobian2Dw, *col["acoustic"])
         if self.ELASTIC:
             att = sim.att[self.rank] if sim.att is not None else None
             nspec = db.NSPEC_AB
@@ -144,7 +149,7 @@ class DeviceRank:
                 db.num_phase_ispec_elastic, db.phase_ispec_inner_elastic, dummy, 0, strain, eps[0], eps[1], eps[2],
                 eps[3], eps[4], int(att is not None), R_size, R[0], R[1], R[2], R[3], R[4], fc, R[5], eps[5], fck, al,
                 be, ga, 0, dummy, 0, dummy, db.free_surface_ispec, db.free_surface_ijk, db.num_free_surface_faces,
-                int(sim.ACOUSTIC_SIMULATION), 0, 0, idummy, 0, *([dummy] * 21))
+                int(sim.ACOUSTIC_SIMULATION), *col["elastic"], 0, *([dummy] * 21))
             if sim.PML_CONDITIONS and sim.pml is not None:
                 from .pml import prepare_fields_elastic_pml
 
