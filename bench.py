@@ -309,7 +309,7 @@ def run_device(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(out))
+        emit(json.dumps(out))
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -372,7 +372,7 @@ def run_reference(args):
     value = nspec * args.steps / el
     sample = (f"each step = one full time step of a {nex[0]}x{nex[1]}x{nex[2]} ({nspec}-element) halfspace mesh of the same kind "
               f"(element-timesteps/s is size-independent on the CPU); oracle port, {cores} OpenMP threads")
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -383,7 +383,39 @@ def run_reference(args):
     }))
 
 
+class QuietStdout:
+    """The contract is ONE JSON line on stdout.  Libraries chat on fd 1 (NCCL prints its version banner there), so the
+    run happens with fd 1 pointing at stderr and the JSON line goes to the saved descriptor."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line: str):
+        sys.stdout.flush()
+        os.write(self.saved, (line + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
+OUT = None
+
+
+def emit(line: str):
+    if OUT is not None:
+        OUT.emit(line)
+    else:
+        print(line, flush=True)
+
+
 def main():
+    global OUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
@@ -396,10 +428,13 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_device(args)
+    with QuietStdout() as q:
+        OUT = q
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_device(args)
+    OUT = None
 
 
 if __name__ == "__main__":
