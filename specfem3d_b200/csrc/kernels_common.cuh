@@ -35,4 +35,14 @@ __device__ __forceinline__ realw jacobian_of(const Metric& m) {
                  m.xiz * (m.etax * m.gammay - m.etay * m.gammax));
 }
 
+// same with the reciprocal from the SFU (rcp.approx.ftz: max 1 ulp): used by the default force kernel, where the ~10
+// instructions of the IEEE division per GLL point are visible in the issue-bound pointwise phase
+__device__ __forceinline__ realw jacobian_of_approx(const Metric& m) {
+  const realw det = m.xix * (m.etay * m.gammaz - m.etaz * m.gammay) - m.xiy * (m.etax * m.gammaz - m.etaz * m.gammax) +
+                    m.xiz * (m.etax * m.gammay - m.etay * m.gammax);
+  realw r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(det));
+  return r;
+}
+
 }  // namespace sb200
