@@ -86,4 +86,122 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_acoustic_forces_pt(const Acous
   }
 }
 
+// ---- persistent, software-pipelined variant (default) -----------------------------------------------------------------
+// The one-element-per-CTA kernel above reaches 0.48 of the HBM roofline (profiles/r01g_secondary_kernels.md): a CTA lives
+// for two dependent global latencies (ibool -> potential gather) plus the math and moves only 6.3 KB, so Little's law
+// caps the bytes in flight per SM.  Here a CTA walks over elements (stride = grid) and keeps the NEXT element's
+// potential values and its ten parameter words in registers while it works on the current one, and the index word of
+// the element after that: three elements deep, no extra shared memory traffic, two barriers per element as before
+// (the shared tiles are double-buffered by element parity, so no third barrier is needed).
+struct AcousticElem {
+  int ispec, irr;
+  size_t iglob;
+  realw chi, rho;
+  Metric m;
+};
+
+__global__ void __launch_bounds__(NGLL3_PADDED) k_acoustic_forces_pf(const AcousticArgs a) {
+  const int tx = threadIdx.x;
+  const bool active = tx < NGLL3;
+  const int t = active ? tx : NGLL3 - 1;
+  const int K = t / NGLL2, J = (t - K * NGLL2) / NGLLX, I = t - K * NGLL2 - J * NGLLX;
+  __shared__ realw s_chi[2][NGLL3_PADDED], s_t1[2][NGLL3_PADDED], s_t2[2][NGLL3_PADDED], s_t3[2][NGLL3_PADDED];
+  __shared__ realw s_hp[NGLL2], s_hw[NGLL2];
+  if (tx < NGLL2) {
+    s_hp[tx] = c_hprime_xx[tx];
+    s_hw[tx] = c_hprimewgll_xx[tx];
+  }
+  const realw fac1 = c_wgllwgll_yz[K * NGLLX + J], fac2 = c_wgllwgll_xz[K * NGLLX + I], fac3 = c_wgllwgll_xy[J * NGLLX + I];
+  const int stride = gridDim.x;
+  auto element_of = [&](int e) { return a.phase_ispec ? __ldg(a.phase_ispec + e) - 1 : a.first_ispec + e; };
+  // stage 1 of the pipeline: element id and this thread's global point
+  auto index_stage = [&](int e, AcousticElem& E) {
+    E.ispec = element_of(e);
+    E.irr = __ldg(a.irregular_element_number + E.ispec) - 1;
+    E.iglob = (size_t)ld_stream(a.ibool + (size_t)E.ispec * NGLL3_PADDED + t) - 1;
+  };
+  // stage 2: the gathered potential and the parameters (streamed once: evict-first loads)
+  auto data_stage = [&](AcousticElem& E) {
+    const size_t off = (size_t)E.ispec * NGLL3_PADDED + t;
+    E.chi = a.potential[E.iglob];
+    E.rho = ld_stream(a.rhostore + off);
+    if (E.irr >= 0) {
+      const realw* mp = a.metric + (size_t)E.irr * 9 * NGLL3_PADDED + t;
+      E.m.xix = ld_stream(mp); E.m.xiy = ld_stream(mp + NGLL3_PADDED); E.m.xiz = ld_stream(mp + 2 * NGLL3_PADDED);
+      E.m.etax = ld_stream(mp + 3 * NGLL3_PADDED); E.m.etay = ld_stream(mp + 4 * NGLL3_PADDED); E.m.etaz = ld_stream(mp + 5 * NGLL3_PADDED);
+      E.m.gammax = ld_stream(mp + 6 * NGLL3_PADDED); E.m.gammay = ld_stream(mp + 7 * NGLL3_PADDED); E.m.gammaz = ld_stream(mp + 8 * NGLL3_PADDED);
+    }
+  };
+
+  int e = blockIdx.x;
+  if (e >= a.nb_elements) return;
+  AcousticElem cur, nxt, nn;
+  index_stage(e, cur);
+  data_stage(cur);
+  const bool has1 = e + stride < a.nb_elements;
+  if (has1) index_stage(e + stride, nxt);
+  int par = 0;
+  for (; e < a.nb_elements; e += stride, par ^= 1) {
+    const bool has_next = e + stride < a.nb_elements, has_nn = e + 2 * stride < a.nb_elements;
+    if (has_next) data_stage(nxt);
+    if (has_nn) index_stage(e + 2 * stride, nn);
+
+    s_chi[par][t] = cur.chi;
+    __syncthreads();
+    realw t1 = 0.f, t2 = 0.f, t3 = 0.f;
+#pragma unroll
+    for (int l = 0; l < NGLLX; ++l) {
+      t1 += s_chi[par][K * NGLL2 + J * NGLLX + l] * s_hp[l * NGLLX + I];
+      t2 += s_chi[par][K * NGLL2 + l * NGLLX + I] * s_hp[l * NGLLX + J];
+      t3 += s_chi[par][l * NGLL2 + J * NGLLX + I] * s_hp[l * NGLLX + K];
+    }
+    const realw rho_invl = 1.0f / cur.rho;
+    realw f1, f2, f3;
+    if (cur.irr >= 0) {
+      const Metric& m = cur.m;
+      const realw jacobianl = jacobian_of(m);
+      const realw dx = m.xix * t1 + m.etax * t2 + m.gammax * t3;
+      const realw dy = m.xiy * t1 + m.etay * t2 + m.gammay * t3;
+      const realw dz = m.xiz * t1 + m.etaz * t2 + m.gammaz * t3;
+      f1 = rho_invl * jacobianl * (m.xix * dx + m.xiy * dy + m.xiz * dz);
+      f2 = rho_invl * jacobianl * (m.etax * dx + m.etay * dy + m.etaz * dz);
+      f3 = rho_invl * jacobianl * (m.gammax * dx + m.gammay * dy + m.gammaz * dz);
+    } else {
+      const realw f = rho_invl * a.jacobian_regular * a.xix_regular * a.xix_regular;
+      f1 = f * t1; f2 = f * t2; f3 = f * t3;
+    }
+    s_t1[par][t] = f1; s_t2[par][t] = f2; s_t3[par][t] = f3;
+    __syncthreads();
+    realw n1 = 0.f, n2 = 0.f, n3 = 0.f;
+#pragma unroll
+    for (int l = 0; l < NGLLX; ++l) {
+      n1 += s_t1[par][K * NGLL2 + J * NGLLX + l] * s_hw[I * NGLLX + l];
+      n2 += s_t2[par][K * NGLL2 + l * NGLLX + I] * s_hw[J * NGLLX + l];
+      n3 += s_t3[par][l * NGLL2 + J * NGLLX + I] * s_hw[K * NGLLX + l];
+    }
+    const realw sum = -(fac1 * n1 + fac2 * n2 + fac3 * n3);
+    if (active) {
+      if (a.use_atomics) red_add(a.potential_dot_dot + cur.iglob, sum);
+      else a.potential_dot_dot[cur.iglob] += sum;
+    }
+    cur = nxt;
+    nxt = nn;
+  }
+}
+
+inline void launch_acoustic(DeviceMesh* mp, const AcousticArgs& a) {
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("SPECFEM_B200_ACOUSTIC_KERNEL");
+    variant = e ? atoi(e) : 0;
+  }
+  if (variant == 1) {
+    k_acoustic_forces_pt<<<a.nb_elements, NGLL3_PADDED, 0, mp->compute_stream>>>(a);
+  } else {
+    const int resident = 148 * 7;  // 71 registers x 128 threads: 7 CTAs per SM stay resident
+    const int grid = a.nb_elements < resident ? a.nb_elements : resident;
+    k_acoustic_forces_pf<<<grid, NGLL3_PADDED, 0, mp->compute_stream>>>(a);
+  }
+}
+
 }  // namespace sb200

@@ -803,8 +803,8 @@ extern "C" void SB200_FC(compute_forces_acoustic_cuda)(long* Mesh_pointer, int* 
       a.nb_elements = mp->h_num_elem_colors_acoustic[icolor];
       a.phase_ispec = nullptr; a.first_ispec = offset; a.use_atomics = 0;
       if (a.nb_elements > 0) {
-        k_acoustic_forces_pt<<<a.nb_elements, NGLL3_PADDED, 0, mp->compute_stream>>>(a);
-        KERNEL_CHECK(mp, "k_acoustic_forces_pt(colour)");
+        launch_acoustic(mp, a);
+        KERNEL_CHECK(mp, "acoustic forces (colour)");
       }
       offset += a.nb_elements;
     }
@@ -812,8 +812,8 @@ extern "C" void SB200_FC(compute_forces_acoustic_cuda)(long* Mesh_pointer, int* 
     a.nb_elements = num_elements;
     a.phase_ispec = mp->d_phase_ispec_inner_acoustic + (size_t)mp->num_phase_ispec_acoustic * (*iphase - 1);
     a.first_ispec = 0; a.use_atomics = 1;
-    k_acoustic_forces_pt<<<num_elements, NGLL3_PADDED, 0, mp->compute_stream>>>(a);
-    KERNEL_CHECK(mp, "k_acoustic_forces_pt");
+    launch_acoustic(mp, a);
+    KERNEL_CHECK(mp, "acoustic forces");
   }
 }
 

@@ -304,4 +304,36 @@ void mg_mass_matrix_pml(int64_t nspec, const int32_t* ibool, const float* jacobi
   }
 }
 
+// Greedy first-fit mesh colouring of one domain (get_color_faster, src/generate_databases/get_perm_color.f90:100-419,
+// with the shipped defaults USE_DROUX_OPTIMIZATION = BALANCE_COLORS_SIMPLE_ALGO = .false., setup/constants.h.in:336-340):
+// outer elements first, then inner ones; for each new colour sweep the still uncoloured elements in element order and
+// take every element none of whose 8 corner points has been touched by this colour yet.
+// color[e] = 1-based colour (0 for elements outside the domain); returns the colour counts through nb[0] (outer), nb[1] (inner).
+void mg_greedy_color(int64_t nspec, int64_t nglob, const int32_t* ibool, const int32_t* is_outer, const int32_t* in_domain,
+                     int32_t* color, int32_t* nb) {
+  static const int corner[8] = {0, 4, 24, 20, 100, 104, 124, 120};  // (1,1,1) (N,1,1) (N,N,1) (1,N,1) (1,1,N) ...
+  std::vector<int32_t> mask(nglob, 0);  // colour that touched the point last
+  for (int64_t e = 0; e < nspec; ++e) color[e] = 0;
+  int icolor = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    int64_t todo = 0;
+    for (int64_t e = 0; e < nspec; ++e)
+      if (in_domain[e] && ((is_outer[e] != 0) == (pass == 0))) ++todo;
+    const int first = icolor;
+    while (todo > 0) {
+      ++icolor;
+      for (int64_t e = 0; e < nspec; ++e) {
+        if (!in_domain[e] || ((is_outer[e] != 0) != (pass == 0)) || color[e] != 0) continue;
+        bool conflict = false;
+        for (int c = 0; c < 8; ++c) conflict = conflict || mask[ibool[e * 125 + corner[c]] - 1] == icolor;
+        if (conflict) continue;
+        color[e] = icolor;
+        --todo;
+        for (int c = 0; c < 8; ++c) mask[ibool[e * 125 + corner[c]] - 1] = icolor;
+      }
+    }
+    nb[pass] = icolor - first;
+  }
+}
+
 }  // extern "C"

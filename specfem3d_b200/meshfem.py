@@ -576,23 +576,28 @@ def _apply_mesh_coloring(spec: BoxSpec, db: Database) -> None:
     """USE_MESH_COLORING_GPU for a structured slab: what setup_color_perm (src/specfem3D/setup_color_perm.f90) leaves
     behind -- elements permuted so that every domain is ordered [outer colour 1.. | inner colour 1..], elastic elements
     first, and ``num_elem_colors_*`` holding the colour sizes.  Elements of one colour share no GLL point, so the device
-    can accumulate without atomics.  The colouring itself is the parity 8-colouring of the structured grid, not the
-    Droux algorithm of get_perm_color.f90 (the device contract only needs validity; colour parity with the reference's
-    permutation is unpinned by the reference's tests)."""
+    can accumulate without atomics.  The colouring is the reference's greedy first-fit (get_color_faster with the shipped
+    defaults, csrc/meshgen.cpp: mg_greedy_color), the ordering get_final_perm + setup_permutation: elastic outer colours,
+    elastic inner colours, acoustic outer, acoustic inner.  (No reference-generated colour file exists in the tree to compare
+    with: the restatement is exact by construction, its parity with a Fortran run is unpinned.)"""
+    import ctypes
+
+    mg = _meshgen()
+    mg.mg_greedy_color.restype = None
+    mg.mg_greedy_color.argtypes = [ctypes.c_int64, ctypes.c_int64] + [ctypes.c_void_p] * 5
     nspec = db.NSPEC_AB
-    eix, eiy, eiz = db.extra["eijk"]
-    colour = (eix - db.ix0) % 2 + 2 * ((eiy - db.iy0) % 2) + 4 * (eiz % 2)
-    inner = db.ispec_is_inner.astype(bool)
+    is_outer = np.ascontiguousarray(1 - db.ispec_is_inner, dtype=np.int32)
     perm_parts, counts = [], {}
-    for dom, mask in (("elastic", db.ispec_is_elastic.astype(bool)), ("acoustic", db.ispec_is_acoustic.astype(bool))):
-        n_out, n_in = [], []
-        for phase_inner, acc in ((False, n_out), (True, n_in)):
-            for col in range(8):
-                idx = np.nonzero(mask & (inner == phase_inner) & (colour == col))[0]
-                if len(idx):
-                    perm_parts.append(idx)
-                    acc.append(len(idx))
-        counts[dom] = (n_out, n_in)
+    for dom, mask in (("elastic", db.ispec_is_elastic), ("acoustic", db.ispec_is_acoustic)):
+        colour = np.zeros(nspec, np.int32)
+        nb = np.zeros(2, np.int32)
+        mg.mg_greedy_color(nspec, db.NGLOB_AB, _p(db.ibool), _p(is_outer), _p(np.ascontiguousarray(mask, dtype=np.int32)),
+                           _p(colour), _p(nb))
+        sizes = [int((colour == c).sum()) for c in range(1, int(nb.sum()) + 1)]
+        for c in range(1, int(nb.sum()) + 1):  # get_final_perm: colour by colour, element order kept inside a colour
+            perm_parts.append(np.nonzero(colour == c)[0])
+        counts[dom] = (sizes[: int(nb[0])], sizes[int(nb[0]):])
+        db.extra["colour_of_old_ispec_" + dom] = colour
     perm = np.concatenate(perm_parts)  # new position -> old element
     assert len(perm) == nspec
     inv = np.empty(nspec, np.int64)

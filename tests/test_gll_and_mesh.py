@@ -90,3 +90,52 @@ def test_mass_matrix_total():
     db = build_all(spec, 0.01)[0]
     total = (1.0 / db.rmassx.astype(np.float64)).sum()
     assert abs(total - 2300.0 * 900.0 ** 3) / (2300.0 * 900.0 ** 3) < 1e-5
+
+
+def test_mesh_coloring_permutation_follows_the_reference_rules():
+    """USE_MESH_COLORING_GPU (harness: meshfem._apply_mesh_coloring + csrc/meshgen.cpp: mg_greedy_color): greedy first-fit
+    colours by shared corner points (get_perm_color.f90:100-419), elements ordered elastic-outer | elastic-inner |
+    acoustic-outer | acoustic-inner colour by colour (get_final_perm, setup_permutation), phase lists contiguous."""
+    import numpy as np
+
+    from oracle.solver import OracleRun
+    from specfem3d_b200.configs import HALFSPACE
+    from specfem3d_b200.meshfem import BoxSpec, Material
+    from specfem3d_b200.simulation import make_simulation
+    from specfem3d_b200.sources_receivers import CMTSource, Station
+
+    water = Material(1020.0, 1500.0, 0.0, 9999.0, 9999.0, 1)
+
+    def make(coloring):
+        spec = BoxSpec(6, 4, 5, xmax=6600.0, ymax=3600.0, zmin=-5000.0, nproc_xi=2, nproc_eta=1, materials=(HALFSPACE, water),
+                       layer_material=[0, 0, 0, 0, 1], deform=0.1, mesh_coloring=coloring)
+        src = [CMTSource(0.52 * spec.xmax, 0.47 * spec.ymax, 0.6 * spec.zmin, (1e23, -2e23, 0.5e23, 0.3e23, -0.7e23, 0.2e23), hdur=0.4)]
+        sts = [Station("S", "XX", 0.67 * spec.xmax, 0.58 * spec.ymax, 0.5 * spec.zmin)]
+        return make_simulation(spec, DT=0.006, NSTEP=80, sources=src, stations=sts)
+
+    sim = make(True)
+    for db in sim.dbs:
+        ib = db.ibool.reshape(db.NSPEC_AB, 125)
+        off = 0
+        for dom, flag in (("elastic", db.ispec_is_elastic), ("acoustic", db.ispec_is_acoustic)):
+            sizes = db.extra["num_elem_colors_" + dom][:-1]
+            n_out, n_in = db.extra["num_colors_outer_" + dom], db.extra["num_colors_inner_" + dom]
+            assert len(sizes) == n_out + n_in and sum(sizes) == int(flag.sum())
+            for ic, n in enumerate(sizes):
+                rng = slice(off, off + n)
+                assert flag[rng].all()                                        # the domain's elements are contiguous
+                assert (db.ispec_is_inner[rng] == (0 if ic < n_out else 1)).all()  # outer colours first
+                pts = ib[rng].ravel()
+                assert len(np.unique(pts)) == len(pts)                        # no GLL point shared inside a colour
+                off += n
+            ph = getattr(db, "phase_ispec_inner_" + dom)
+            n_o, n_i = sum(sizes[:n_out]), sum(sizes[n_out:])
+            first = off - n_o - n_i
+            assert list(ph[0, :n_o]) == list(range(first + 1, first + n_o + 1))
+            assert list(ph[1, :n_i]) == list(range(first + n_o + 1, first + n_o + n_i + 1))
+        # greedy first-fit property: an element of colour c > 1 touches an element of every earlier colour of its set
+        col = db.extra["colour_of_old_ispec_elastic"]
+        assert col.max() <= 16
+    a, b = OracleRun(sim).run(), OracleRun(make(False)).run()
+    assert np.abs(b.seis_d).max() > 0
+    assert np.linalg.norm(a.seis_d - b.seis_d) <= 1e-5 * np.linalg.norm(b.seis_d)  # same physics, permuted storage
