@@ -33,7 +33,37 @@ struct ElasticArgs {
   realw *R_xx, *R_yy, *R_xy, *R_xz, *R_yz, *R_trace;                    // [NSPEC][N_SLS][128]
   const realw *factor_common, *factor_common_kappa;                      // [NSPEC][N_SLS][128]
   realw *eps_xx, *eps_yy, *eps_xy, *eps_xz, *eps_yz, *eps_trace;         // [NSPEC][128]
+  int att_prefetch;            // 0 = none, 1 = prefetch the element's attenuation planes into L2, 2 = into L1
 };
+
+// ncu on the attenuation kernel (profiles/r01g_secondary_kernels.md): 73 % of every issue slot's latency is a long
+// scoreboard on the ~50 dependent loads of memory variables, factors and stored strains, DRAM only 50 % busy.  All of an
+// element's attenuation data are 120 contiguous 128-byte lines: one prefetch per thread at kernel entry starts them all at
+// once, so the later loads find them in cache instead of paying a DRAM round trip each.
+template <int LEVEL>
+__device__ __forceinline__ void prefetch_line(const void* p) {
+  if (LEVEL == 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+  else asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ void prefetch_attenuation_planes(const ElasticArgs& a, int ispec, int tx) {
+  const realw* p = nullptr;
+  if (tx < 72) {  // six memory-variable arrays, 12 lines each
+    const int arr = tx / 12, line = tx - 12 * arr;
+    const realw* base = arr == 0 ? a.R_xx : arr == 1 ? a.R_yy : arr == 2 ? a.R_xy : arr == 3 ? a.R_xz : arr == 4 ? a.R_yz : a.R_trace;
+    p = base + (size_t)ispec * N_SLS * NGLL3_PADDED + line * 32;
+  } else if (tx < 96) {  // the two factor arrays
+    const int arr = (tx - 72) / 12, line = (tx - 72) - 12 * arr;
+    p = (arr == 0 ? a.factor_common : a.factor_common_kappa) + (size_t)ispec * N_SLS * NGLL3_PADDED + line * 32;
+  } else if (tx < 120) {  // six stored strains, 4 lines each
+    const int arr = (tx - 96) / 4, line = (tx - 96) - 4 * arr;
+    const realw* base = arr == 0 ? a.eps_xx : arr == 1 ? a.eps_yy : arr == 2 ? a.eps_xy : arr == 3 ? a.eps_xz : arr == 4 ? a.eps_yz : a.eps_trace;
+    p = base + (size_t)ispec * NGLL3_PADDED + line * 32;
+  }
+  if (p) {
+    if (a.att_prefetch == 1) prefetch_line<1>(p);
+    else prefetch_line<2>(p);
+  }
+}
 
 // One thread per GLL point.  ATT: attenuation (implies strain storage).  STRAIN: store epsilondev without attenuation.
 template <bool ATT, bool STRAIN>
@@ -51,6 +81,7 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_elastic_forces_pt(const Elasti
 
   const int ispec = a.phase_ispec ? a.phase_ispec[bx] - 1 : a.first_ispec + bx;
   if (a.is_CPML && a.is_CPML[ispec]) return;  // PML elements are handled by the PML kernel
+  if (ATT && a.att_prefetch) prefetch_attenuation_planes(a, ispec, tx);
   const int irr = a.irregular_element_number[ispec] - 1;
   const size_t off = (size_t)ispec * NGLL3_PADDED + t;
   const int iglob = a.ibool[off] - 1;

@@ -682,6 +682,12 @@ static void launch_elastic(DeviceMesh* mp, int nb, const int* phase_list, int fi
   a.factor_common = mp->d_factor_common; a.factor_common_kappa = mp->d_factor_common_kappa;
   a.eps_xx = mp->d_epsilondev_xx; a.eps_yy = mp->d_epsilondev_yy; a.eps_xy = mp->d_epsilondev_xy;
   a.eps_xz = mp->d_epsilondev_xz; a.eps_yz = mp->d_epsilondev_yz; a.eps_trace = mp->d_epsilondev_trace;
+  static int att_prefetch = -1;
+  if (att_prefetch < 0) {
+    const char* e = getenv("SPECFEM_B200_ATT_PREFETCH");
+    att_prefetch = e ? atoi(e) : 2;
+  }
+  a.att_prefetch = att_prefetch;
 
   const bool att = mp->attenuation != 0;
   const bool strain = mp->compute_and_store_strain != 0;
