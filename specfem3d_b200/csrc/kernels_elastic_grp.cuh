@@ -69,6 +69,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // Producer: it is ahead of the math most of the time; a spinning lane would steal issue slots from the consumer warps
 // of its SM sub-partition (ncu, r01: 34 % of all issued instructions were the producers' polling loops).  Suspend in
 // hardware for up to ~4 us per try, then back off with nanosleep.
+// back-off of the producer lane between two polls (SPECFEM_B200_PRODUCER_SLEEP, set in prepare_constants_device)
+__constant__ unsigned c_producer_sleep_ns = 256;
 __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
   for (unsigned spin = 0;; ++spin) {
@@ -78,7 +80,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity), "r"(4000u)
         : "memory");
     if (ok) return;
-    __nanosleep(256);
+    __nanosleep(c_producer_sleep_ns);
     if (spin > (1u << 20)) __trap();
   }
 }

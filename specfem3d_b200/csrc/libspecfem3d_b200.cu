@@ -288,6 +288,10 @@ extern "C" void SB200_FC(prepare_constants_device)(
   if (fk) mp->force_kernel_variant = atoi(fk);
   const char* fn = getenv("SPECFEM_B200_FUSE_NEWMARK");
   if (fn) mp->fuse_newmark = atoi(fn);
+  if (const char* ps = getenv("SPECFEM_B200_PRODUCER_SLEEP")) {
+    const unsigned v = (unsigned)atoi(ps);
+    CUDA_CHECK(cudaMemcpyToSymbol(c_producer_sleep_ns, &v, sizeof(v)));
+  }
   CUDA_CHECK(cudaDeviceSynchronize());
 }
 
