@@ -682,6 +682,8 @@ def local_mass_matrices(spec: BoxSpec, db: Database, DT: float, gll: Optional[GL
             out["rmassx"], out["rmassy"], out["rmassz"] = rmass + rx, rmass + ry, rmass + rz
         else:
             out["rmassx"], out["rmassy"], out["rmassz"] = rmass.copy(), rmass.copy(), rmass.copy()
+        # the separate records of the database file (save_arrays_solver.F90:196-233): rmass and the Stacey terms alone
+        out["_parts_elastic"] = (rmass, rx, ry, rz)
 
     if db.nspec_acoustic:
         rma = np.zeros(nglob, dtype=np.float32)
@@ -700,7 +702,10 @@ def local_mass_matrices(spec: BoxSpec, db: Database, DT: float, gll: Optional[GL
                 sl = dto2 / db.rho_vp.reshape(-1, 125)[isp, p]
                 ig = flat_ibool[isp, p] - 1
                 rz[ig] += db.abs_boundary_jacobian2Dw[f] * sl
+            out["_parts_acoustic"] = (rma, rz)
             rma = rma + rz
+        else:
+            out["_parts_acoustic"] = (rma, np.zeros(nglob, dtype=np.float32))
         out["rmass_acoustic"] = rma
     return out
 
