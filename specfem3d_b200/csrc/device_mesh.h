@@ -102,7 +102,7 @@ struct DeviceMesh {
   int* h_num_elem_colors_acoustic = nullptr;
 
   // wavefields
-  realw *d_displ = nullptr, *d_veloc = nullptr, *d_accel = nullptr;                                       // [NGLOB][3]
+  realw *d_displ = nullptr, *d_veloc = nullptr, *d_accel = nullptr;                                       // component planes [3][NGLOB] (kernels_common.cuh: vidx)
   realw *d_potential = nullptr, *d_potential_dot = nullptr, *d_potential_dot_dot = nullptr;               // [NGLOB]
   realw *d_rmassx = nullptr, *d_rmassy = nullptr, *d_rmassz = nullptr, *d_rmass_acoustic = nullptr;       // [NGLOB]
   realw* d_rmass_ocean_load = nullptr;

@@ -77,14 +77,14 @@ __global__ void __launch_bounds__(256) k_halo_pack_put(const realw* __restrict__
                                                        realw* const* __restrict__ remote_data, unsigned* const* __restrict__ remote_flag,
                                                        const size_t* __restrict__ remote_parity_stride,
                                                        const int* __restrict__ remote_flag_parity_stride, unsigned* block_counter,
-                                                       unsigned step, int parity) {
+                                                       unsigned step, int parity, size_t nglob) {
   const int iface = blockIdx.y;
   const int ipoin = blockIdx.x * blockDim.x + threadIdx.x;
   if (ipoin < nibool[iface]) {
     const size_t iglob = (size_t)ibool_interfaces[ipoin + (size_t)max_nibool * iface] - 1;
     realw* dst = remote_data[iface] + (size_t)parity * remote_parity_stride[iface] + (size_t)NCOMP * ipoin;
 #pragma unroll
-    for (int c = 0; c < NCOMP; ++c) dst[c] = field[NCOMP * iglob + c];
+    for (int c = 0; c < NCOMP; ++c) dst[c] = field[vidxn<NCOMP>(iglob, c, nglob)];
   }
   __threadfence_system();
   __syncthreads();
@@ -103,7 +103,7 @@ template <int NCOMP>
 __global__ void __launch_bounds__(256) k_halo_wait_unpack(realw* field, const realw* __restrict__ slab_data /*this parity*/,
                                                           const unsigned* flags /*this parity*/, int max_nibool,
                                                           const int* __restrict__ nibool, const int* __restrict__ ibool_interfaces,
-                                                          unsigned step, int* error_flag) {
+                                                          unsigned step, int* error_flag, size_t nglob) {
   const int iface = blockIdx.y;
   __shared__ int ok;
   if (threadIdx.x == 0) {
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) k_halo_wait_unpack(realw* field, const re
   for (int c = 0; c < NCOMP; ++c) {
     // the slab was written by a peer GPU: bypass L1 (ld.volatile goes to L2 / the system)
     const realw v = __ldcv(slab_data + NCOMP * slot + c);
-    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(field + NCOMP * iglob + c), "f"(v) : "memory");
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(field + vidxn<NCOMP>(iglob, c, nglob)), "f"(v) : "memory");
   }
 }
 
@@ -171,12 +171,12 @@ inline void p2p_pack_put(DeviceMesh* mp, int k, const realw* field) {
     k_halo_pack_put<3><<<grid, 256, 0, mp->compute_stream>>>(field, p->max_nibool, mp->d_nibool_interfaces_ext_mesh,
                                                              mp->d_ibool_interfaces_ext_mesh, K.d_remote_data, K.d_remote_flag,
                                                              K.d_remote_parity_stride, K.d_remote_flag_parity_stride,
-                                                             p->d_block_counter + (size_t)k * p->nif, K.step, parity);
+                                                             p->d_block_counter + (size_t)k * p->nif, K.step, parity, (size_t)mp->NGLOB_AB);
   else
     k_halo_pack_put<1><<<grid, 256, 0, mp->compute_stream>>>(field, p->max_nibool, mp->d_nibool_interfaces_ext_mesh,
                                                              mp->d_ibool_interfaces_ext_mesh, K.d_remote_data, K.d_remote_flag,
                                                              K.d_remote_parity_stride, K.d_remote_flag_parity_stride,
-                                                             p->d_block_counter + (size_t)k * p->nif, K.step, parity);
+                                                             p->d_block_counter + (size_t)k * p->nif, K.step, parity, (size_t)mp->NGLOB_AB);
   KERNEL_CHECK(mp, "k_halo_pack_put");
 }
 
@@ -189,10 +189,10 @@ inline void p2p_wait_unpack(DeviceMesh* mp, int k, realw* field) {
   const unsigned* flags = reinterpret_cast<const unsigned*>(p->slab) + K.flag_off + (size_t)parity * p->nif;
   if (k == 0)
     k_halo_wait_unpack<3><<<grid, 256, 0, mp->compute_stream>>>(field, data, flags, p->max_nibool, mp->d_nibool_interfaces_ext_mesh,
-                                                                mp->d_ibool_interfaces_ext_mesh, K.step, p2p_error_flag(mp));
+                                                                mp->d_ibool_interfaces_ext_mesh, K.step, p2p_error_flag(mp), (size_t)mp->NGLOB_AB);
   else
     k_halo_wait_unpack<1><<<grid, 256, 0, mp->compute_stream>>>(field, data, flags, p->max_nibool, mp->d_nibool_interfaces_ext_mesh,
-                                                                mp->d_ibool_interfaces_ext_mesh, K.step, p2p_error_flag(mp));
+                                                                mp->d_ibool_interfaces_ext_mesh, K.step, p2p_error_flag(mp), (size_t)mp->NGLOB_AB);
   KERNEL_CHECK(mp, "k_halo_wait_unpack");
 }
 

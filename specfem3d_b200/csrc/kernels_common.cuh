@@ -24,6 +24,25 @@ __device__ __forceinline__ void red_add(realw* addr, realw v) {
 __device__ __forceinline__ realw ld_stream(const realw* p) { return __ldcs(p); }
 __device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }
 
+// Vector wavefields (displ, veloc, accel, the interleaved inverse mass) are stored as three component planes [3][NGLOB]:
+// the 32 lanes of a gather / RED instruction then touch ~128 contiguous bytes per component instead of 384 (12-byte
+// stride), i.e. a third of the L1 wavefronts and L2 atomic operations of the [NGLOB][3] layout the host uses
+// (profiles/r01f_force_ablation.md: gather + RED cost 0.55 of the force kernel's 2.3 ms).  The Fortran (3,NGLOB) arrays
+// are transposed in the transfer_* entry points.  SB200_SOA = 0 restores the interleaved layout.
+#ifndef SB200_SOA
+#define SB200_SOA 1
+#endif
+__host__ __device__ __forceinline__ size_t vidx(size_t ig, int c, size_t nglob) {
+  return SB200_SOA ? (size_t)c * nglob + ig : 3 * ig + (size_t)c;
+}
+// first component of point ig, and the distance between the components of one point
+__host__ __device__ __forceinline__ size_t vbase(long long ig) { return SB200_SOA ? (size_t)ig : 3 * (size_t)ig; }
+__host__ __device__ __forceinline__ size_t vstride(size_t nglob) { return SB200_SOA ? nglob : (size_t)1; }
+template <int NCOMP>
+__host__ __device__ __forceinline__ size_t vidxn(size_t ig, int c, size_t nglob) {
+  return NCOMP == 1 ? ig : vidx(ig, c, nglob);
+}
+
 struct Metric {
   realw xix, xiy, xiz, etax, etay, etaz, gammax, gammay, gammaz;
 };

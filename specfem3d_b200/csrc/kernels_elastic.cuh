@@ -29,6 +29,7 @@ struct ElasticArgs {
   const int* is_CPML;          // nullptr when no PML
   realw deltat;
   int use_atomics;             // 0 for coloured launches
+  size_t nglob;                // component-plane stride of the vector wavefields (kernels_common.cuh: vidx)
   // attenuation
   realw *R_xx, *R_yy, *R_xy, *R_xz, *R_yz, *R_trace;                    // [NSPEC][N_SLS][128]
   const realw *factor_common, *factor_common_kappa;                      // [NSPEC][N_SLS][128]
@@ -68,6 +69,7 @@ __device__ __forceinline__ void prefetch_attenuation_planes(const ElasticArgs& a
 // One thread per GLL point.  ATT: attenuation (implies strain storage).  STRAIN: store epsilondev without attenuation.
 template <bool ATT, bool STRAIN>
 __global__ void __launch_bounds__(NGLL3_PADDED) k_elastic_forces_pt(const ElasticArgs a) {
+  const size_t cs = vstride(a.nglob);  // distance between the components of one point (kernels_common.cuh)
   const int bx = blockIdx.x;
   if (bx >= a.nb_elements) return;
   const int tx = threadIdx.x;
@@ -87,12 +89,13 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_elastic_forces_pt(const Elasti
   const int iglob = a.ibool[off] - 1;
 
   {
-    const realw ux = a.displ[3 * (size_t)iglob], uy = a.displ[3 * (size_t)iglob + 1], uz = a.displ[3 * (size_t)iglob + 2];
+    const size_t vb = vbase(iglob);
+    const realw ux = a.displ[vb], uy = a.displ[vb + cs], uz = a.displ[vb + 2 * cs];
     s_x[t] = ux; s_y[t] = uy; s_z[t] = uz;
     if (ATT) {
-      s_ax[t] = ux + a.deltat * a.veloc[3 * (size_t)iglob];
-      s_ay[t] = uy + a.deltat * a.veloc[3 * (size_t)iglob + 1];
-      s_az[t] = uz + a.deltat * a.veloc[3 * (size_t)iglob + 2];
+      s_ax[t] = ux + a.deltat * a.veloc[vb];
+      s_ay[t] = uy + a.deltat * a.veloc[vb + cs];
+      s_az[t] = uz + a.deltat * a.veloc[vb + 2 * cs];
     }
   }
   if (tx < NGLL2) {
@@ -258,11 +261,11 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_elastic_forces_pt(const Elasti
   const realw sum3 = -(fac1 * n1z + fac2 * n2z + fac3 * n3z);
 
   if (active) {
-    realw* acc = a.accel + 3 * (size_t)iglob;
+    realw* acc = a.accel + vbase(iglob);
     if (a.use_atomics) {
-      red_add(acc, sum1); red_add(acc + 1, sum2); red_add(acc + 2, sum3);
+      red_add(acc, sum1); red_add(acc + cs, sum2); red_add(acc + 2 * cs, sum3);
     } else {
-      acc[0] += sum1; acc[1] += sum2; acc[2] += sum3;
+      acc[0] += sum1; acc[cs] += sum2; acc[2 * cs] += sum3;
     }
     if (ATT) {
       // second-order Runge-Kutta update of the memory variables (compute_element_att_memory.f90:112-152)

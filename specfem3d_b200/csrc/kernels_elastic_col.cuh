@@ -34,6 +34,7 @@ __device__ __forceinline__ void load_line5(const realw* p, realw v[5]) {
 }
 
 __global__ void __launch_bounds__(NGLL3_PADDED, 4) k_elastic_forces_col(const ElasticArgs a) {
+  const size_t cs = vstride(a.nglob);  // distance between the components of one point (kernels_common.cuh)
   extern __shared__ float4 smem_raw[];
   realw* const s_u = reinterpret_cast<realw*>(smem_raw);   // [el][comp][k][j][8]  (i contiguous)
   realw* const s_ut = s_u + COL_ELEMS * COL_ELEM;          // [el][comp][k][i][8]  (j contiguous)
@@ -94,8 +95,8 @@ __global__ void __launch_bounds__(NGLL3_PADDED, 4) k_elastic_forces_col(const El
       for (int k = 0; k < 5; ++k) ig[k] = ib[k * NGLL2] - 1;
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        const realw* d = a.displ + 3 * (size_t)ig[k];
-        ux[k] = d[0]; uy[k] = d[1]; uz[k] = d[2];
+        const realw* d = a.displ + vbase(ig[k]);
+        ux[k] = d[0]; uy[k] = d[cs]; uz[k] = d[2 * cs];
       }
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
@@ -217,11 +218,11 @@ __global__ void __launch_bounds__(NGLL3_PADDED, 4) k_elastic_forces_col(const El
           const realw n2 = q[0] * hw_j[0] + q[1] * hw_j[1] + q[2] * hw_j[2] + q[3] * hw_j[3] + q[4] * hw_j[4];
           out[cc] = -(fac1[k] * n1 + fac2[k] * n2 + fac3 * acc[cc][k]);
         }
-        realw* dst = a.accel + 3 * (size_t)ig[k];
+        realw* dst = a.accel + vbase(ig[k]);
         if (a.use_atomics) {
-          red_add(dst, out[0]); red_add(dst + 1, out[1]); red_add(dst + 2, out[2]);
+          red_add(dst, out[0]); red_add(dst + cs, out[1]); red_add(dst + 2 * cs, out[2]);
         } else {
-          dst[0] += out[0]; dst[1] += out[1]; dst[2] += out[2];
+          dst[0] += out[0]; dst[cs] += out[1]; dst[2 * cs] += out[2];
         }
       }
     }

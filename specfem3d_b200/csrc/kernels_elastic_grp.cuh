@@ -113,12 +113,14 @@ struct GrpArgs {
   realw* accel;
   realw xix_regular, jacobian_regular;
   int use_atomics;
+  size_t nglob;
 };
 
 // GRP_STAGES: parameter ring depth in k-plane chunks (power of two); MINB: resident CTAs per SM the registers are capped for
 // PREFETCH: 0 = none, 1 = gather the next batch into registers during stage 2, 2 = pull its lines into L1 (prefetch.global.L1)
 template <int PREFETCH, int GRP_STAGES, int MINB>
 __global__ void __launch_bounds__(GRP_THREADS, MINB) k_elastic_forces_grp(const GrpArgs a) {
+  const size_t cs = vstride(a.nglob);  // distance between the components of one point (kernels_common.cuh)
   extern __shared__ __align__(128) unsigned char grp_smem[];
   realw* const s_u = reinterpret_cast<realw*>(grp_smem);
   realw* const s_f1 = s_u + GRP_U_WORDS;
@@ -213,8 +215,8 @@ __global__ void __launch_bounds__(GRP_THREADS, MINB) k_elastic_forces_grp(const 
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
       if (valid) {
-        const realw* d = a.displ + 3 * (size_t)ig[k];
-        ux[k] = d[0]; uy[k] = d[1]; uz[k] = d[2];
+        const realw* d = a.displ + vbase(ig[k]);
+        ux[k] = d[0]; uy[k] = d[cs]; uz[k] = d[2 * cs];
       } else {
         ux[k] = 0.f; uy[k] = 0.f; uz[k] = 0.f;
       }
@@ -370,7 +372,7 @@ __global__ void __launch_bounds__(GRP_THREADS, MINB) k_elastic_forces_grp(const 
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
           const int gi = ibn[k * GRP_ROW + t] - 1;
-          if (gi >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.displ + 3 * (size_t)gi));
+          if (gi >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.displ + vbase(gi)));
         }
       }
     }
@@ -392,11 +394,11 @@ __global__ void __launch_bounds__(GRP_THREADS, MINB) k_elastic_forces_grp(const 
         out[cc] = -(fac1[k] * n1 + fac2[k] * n2 + fac3 * acc[cc][k]);
       }
       if (valid) {
-        realw* dst = a.accel + 3 * (size_t)ig[k];
+        realw* dst = a.accel + vbase(ig[k]);
         if (a.use_atomics) {
-          red_add(dst, out[0]); red_add(dst + 1, out[1]); red_add(dst + 2, out[2]);
+          red_add(dst, out[0]); red_add(dst + cs, out[1]); red_add(dst + 2 * cs, out[2]);
         } else {
-          dst[0] += out[0]; dst[1] += out[1]; dst[2] += out[2];
+          dst[0] += out[0]; dst[cs] += out[1]; dst[2 * cs] += out[2];
         }
       }
     }
@@ -562,6 +564,7 @@ inline void launch_elastic_grp(DeviceMesh* mp, const GroupStore* gs, int segment
   a.xix_regular = mp->xix_regular;
   a.jacobian_regular = mp->jacobian_regular;
   a.use_atomics = use_atomics;
+  a.nglob = (size_t)mp->NGLOB_AB;
   if (launch_elastic_pk_variant(mp, a, ng)) return;
   if (launch_elastic_po_variant(mp, a, ng)) return;
   switch (mp->force_kernel_variant) {  // A/B variants (tools/bench_force_variants.py)

@@ -145,6 +145,7 @@ __device__ __forceinline__ void pk_plane_contract(const V* v, V* dst, const V* w
 
 template <int STAGES, int MINB>
 __global__ void __launch_bounds__(GRP_THREADS, MINB) k_elastic_forces_pk(const GrpArgs a) {
+  const size_t cs = vstride(a.nglob);  // distance between the components of one point (kernels_common.cuh)
   extern __shared__ __align__(128) unsigned char pk_smem[];
   realw* const s_U = reinterpret_cast<realw*>(pk_smem);
   realw* const s_T1 = s_U + PK_TILE_WORDS;  // T1, then F1, then N1
@@ -250,8 +251,8 @@ __global__ void __launch_bounds__(GRP_THREADS, MINB) k_elastic_forces_pk(const G
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
       if (valid) {
-        const realw* d = a.displ + 3 * (size_t)ig[k];
-        u[0][k] = d[0]; u[1][k] = d[1]; u[2][k] = d[2];
+        const realw* d = a.displ + vbase(ig[k]);
+        u[0][k] = d[0]; u[1][k] = d[cs]; u[2][k] = d[2 * cs];
       } else {
         u[0][k] = 0.f; u[1][k] = 0.f; u[2][k] = 0.f;
       }
@@ -430,7 +431,7 @@ __global__ void __launch_bounds__(GRP_THREADS, MINB) k_elastic_forces_pk(const G
         out[4] = -(T11[cc * 125 + t] + T21[cc * 125 + t] + fac3 * acc[cc][4]);
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
-          realw* dst = a.accel + 3 * (size_t)ig[k] + cc;
+          realw* dst = a.accel + vbase(ig[k]) + cc * cs;
           if (a.use_atomics) red_add(dst, out[k]);
           else *dst += out[k];
         }

@@ -48,6 +48,7 @@ namespace sb200 {
 //   bit 0 = no RED.ADD to accel, bit 1 = no displacement gather, bit 2 = no parameter stream (ring never filled / waited)
 template <int STAGES, int MINB, int ABL = 0, bool TILE3 = false>
 __global__ void __launch_bounds__(GRP_THREADS, MINB) k_elastic_forces_po(const GrpArgs a) {
+  const size_t cs = vstride(a.nglob);  // distance between the components of one point (kernels_common.cuh)
   extern __shared__ __align__(128) unsigned char po_smem[];
   realw* const s_A = reinterpret_cast<realw*>(po_smem);  // U
   realw* const s_B = s_A + PO_TILE_WORDS;                // T1
@@ -141,8 +142,8 @@ __global__ void __launch_bounds__(GRP_THREADS, MINB) k_elastic_forces_po(const G
       if (valid && (ABL & 2)) {
         ux[k] = 1e-9f * (realw)ig[k]; uy[k] = 2e-9f * (realw)ig[k]; uz[k] = -1e-9f * (realw)ig[k];
       } else if (valid) {
-        const realw* d = a.displ + 3 * (size_t)ig[k];
-        ux[k] = d[0]; uy[k] = d[1]; uz[k] = d[2];
+        const realw* d = a.displ + vbase(ig[k]);
+        ux[k] = d[0]; uy[k] = d[cs]; uz[k] = d[2 * cs];
       } else {
         ux[k] = 0.f; uy[k] = 0.f; uz[k] = 0.f;
       }
@@ -318,13 +319,13 @@ __global__ void __launch_bounds__(GRP_THREADS, MINB) k_elastic_forces_po(const G
         realw out[3];
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) out[cc] = -(s_N[(cc * 5 + k) * 125 + t] + fac3 * acc[cc][k]);
-        realw* dst = a.accel + 3 * (size_t)ig[k];
+        realw* dst = a.accel + vbase(ig[k]);
         if (ABL & 1) {
           if (out[0] == 1.2345e33f) dst[0] = out[1] + out[2];  // keeps the arithmetic alive, never stores
         } else if (a.use_atomics) {
-          red_add(dst, out[0]); red_add(dst + 1, out[1]); red_add(dst + 2, out[2]);
+          red_add(dst, out[0]); red_add(dst + cs, out[1]); red_add(dst + 2 * cs, out[2]);
         } else {
-          dst[0] += out[0]; dst[1] += out[1]; dst[2] += out[2];
+          dst[0] += out[0]; dst[cs] += out[1]; dst[2 * cs] += out[2];
         }
       }
     }
@@ -341,6 +342,7 @@ __global__ void __launch_bounds__(GRP_THREADS, MINB) k_elastic_forces_po(const G
 // and the index slab is single-buffered (it is consumed in P0 and re-filled while the other phases run).
 template <int STAGES, int MINB>
 __global__ void __launch_bounds__(GRP_THREADS, MINB) k_elastic_forces_po2(const GrpArgs a) {
+  const size_t cs = vstride(a.nglob);  // distance between the components of one point (kernels_common.cuh)
   constexpr int ABL = 0;
   extern __shared__ __align__(128) unsigned char po_smem[];
   realw* const s_A = reinterpret_cast<realw*>(po_smem);  // U, T1, F1, N
@@ -434,8 +436,8 @@ __global__ void __launch_bounds__(GRP_THREADS, MINB) k_elastic_forces_po2(const 
       if (valid && (ABL & 2)) {
         ux[k] = 1e-9f * (realw)ig[k]; uy[k] = 2e-9f * (realw)ig[k]; uz[k] = -1e-9f * (realw)ig[k];
       } else if (valid) {
-        const realw* d = a.displ + 3 * (size_t)ig[k];
-        ux[k] = d[0]; uy[k] = d[1]; uz[k] = d[2];
+        const realw* d = a.displ + vbase(ig[k]);
+        ux[k] = d[0]; uy[k] = d[cs]; uz[k] = d[2 * cs];
       } else {
         ux[k] = 0.f; uy[k] = 0.f; uz[k] = 0.f;
       }
@@ -614,13 +616,13 @@ __global__ void __launch_bounds__(GRP_THREADS, MINB) k_elastic_forces_po2(const 
         realw out[3];
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) out[cc] = -(s_N[(cc * 5 + k) * 125 + t] + fac3 * acc[cc][k]);
-        realw* dst = a.accel + 3 * (size_t)ig[k];
+        realw* dst = a.accel + vbase(ig[k]);
         if (ABL & 1) {
           if (out[0] == 1.2345e33f) dst[0] = out[1] + out[2];  // keeps the arithmetic alive, never stores
         } else if (a.use_atomics) {
-          red_add(dst, out[0]); red_add(dst + 1, out[1]); red_add(dst + 2, out[2]);
+          red_add(dst, out[0]); red_add(dst + cs, out[1]); red_add(dst + 2 * cs, out[2]);
         } else {
-          dst[0] += out[0]; dst[1] += out[1]; dst[2] += out[2];
+          dst[0] += out[0]; dst[cs] += out[1]; dst[2 * cs] += out[2];
         }
       }
     }
@@ -631,6 +633,7 @@ __global__ void __launch_bounds__(GRP_THREADS, MINB) k_elastic_forces_po2(const 
 // ---- same kernel with the displacement gather issued one batch ahead through cp.async --------------------------------
 template <int STAGES, int MINB>
 __global__ void __launch_bounds__(GRP_THREADS, MINB) k_elastic_forces_po_async(const GrpArgs a) {
+  const size_t cs = vstride(a.nglob);  // distance between the components of one point (kernels_common.cuh)
   extern __shared__ __align__(128) unsigned char po_smem[];
   realw* const s_A = reinterpret_cast<realw*>(po_smem);  // U (filled asynchronously one batch ahead)
   realw* const s_B = s_A + PO_TILE_WORDS;                // T1, then F1 (same word, same thread)
@@ -721,10 +724,10 @@ __global__ void __launch_bounds__(GRP_THREADS, MINB) k_elastic_forces_po_async(c
     if (valid) {
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        const realw* d = a.displ + 3 * (size_t)ig[k];
+        const realw* d = a.displ + vbase(ig[k]);
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc)
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(s_A + (cc * 5 + k) * 125 + t)), "l"(d + cc)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(s_A + (cc * 5 + k) * 125 + t)), "l"(d + cc * cs)
                        : "memory");
       }
     }
@@ -915,11 +918,11 @@ __global__ void __launch_bounds__(GRP_THREADS, MINB) k_elastic_forces_po_async(c
         realw out[3];
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) out[cc] = -(s_D[(cc * 5 + k) * 125 + t] + fac3 * acc[cc][k]);
-        realw* dst = a.accel + 3 * (size_t)ig[k];
+        realw* dst = a.accel + vbase(ig[k]);
         if (a.use_atomics) {
-          red_add(dst, out[0]); red_add(dst + 1, out[1]); red_add(dst + 2, out[2]);
+          red_add(dst, out[0]); red_add(dst + cs, out[1]); red_add(dst + 2 * cs, out[2]);
         } else {
-          dst[0] += out[0]; dst[1] += out[1]; dst[2] += out[2];
+          dst[0] += out[0]; dst[cs] += out[1]; dst[2 * cs] += out[2];
         }
       }
     }

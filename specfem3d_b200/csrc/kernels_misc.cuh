@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(32) k_stacey_elastic(const realw* __restrict__
                                                        const realw* __restrict__ abs_jac2Dw, const int* __restrict__ ibool,
                                                        const realw* __restrict__ rho_vp, const realw* __restrict__ rho_vs,
                                                        const int* __restrict__ ispec_is_elastic, int num_faces,
-                                                       realw* b_absorb_field) {
+                                                       realw* b_absorb_field, size_t nglob) {
   const int iface = blockIdx.x, igll = threadIdx.x;
   if (iface >= num_faces || igll >= NGLL2) return;
   const int ispec = abs_ispec[iface] - 1;
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(32) k_stacey_elastic(const realw* __restrict__
   const int* ijk = abs_ijk + 3 * (igll + NGLL2 * (size_t)iface);
   const int p = (ijk[0] - 1) + NGLLX * (ijk[1] - 1) + NGLL2 * (ijk[2] - 1);
   const size_t iglob = (size_t)ibool[(size_t)ispec * NGLL3_PADDED + p] - 1;
-  const realw vx = veloc[3 * iglob], vy = veloc[3 * iglob + 1], vz = veloc[3 * iglob + 2];
+  const realw vx = veloc[vidx(iglob, 0, nglob)], vy = veloc[vidx(iglob, 1, nglob)], vz = veloc[vidx(iglob, 2, nglob)];
   const realw* nrm = abs_normal + 3 * (igll + NGLL2 * (size_t)iface);
   const realw nx = nrm[0], ny = nrm[1], nz = nrm[2];
   const realw vn = vx * nx + vy * ny + vz * nz;
@@ -138,9 +138,9 @@ __global__ void __launch_bounds__(32) k_stacey_elastic(const realw* __restrict__
   const realw ty = rvp * vn * ny + rvs * (vy - vn * ny);
   const realw tz = rvp * vn * nz + rvs * (vz - vn * nz);
   const realw jw = abs_jac2Dw[igll + NGLL2 * (size_t)iface];
-  red_add(accel + 3 * iglob, -tx * jw);
-  red_add(accel + 3 * iglob + 1, -ty * jw);
-  red_add(accel + 3 * iglob + 2, -tz * jw);
+  red_add(accel + vidx(iglob, 0, nglob), -tx * jw);
+  red_add(accel + vidx(iglob, 1, nglob), -ty * jw);
+  red_add(accel + vidx(iglob, 2, nglob), -tz * jw);
   if (b_absorb_field) {
     realw* b = b_absorb_field + 3 * (igll + NGLL2 * (size_t)iface);
     b[0] = tx * jw; b[1] = ty * jw; b[2] = tz * jw;
@@ -177,7 +177,8 @@ __global__ void __launch_bounds__(32) k_stacey_acoustic(const realw* __restrict_
 __global__ void __launch_bounds__(32) k_coupling_ac_el(const realw* __restrict__ displ, realw* potential_dot_dot,
                                                        int num_faces, const int* __restrict__ c_ispec,
                                                        const int* __restrict__ c_ijk, const realw* __restrict__ c_normal,
-                                                       const realw* __restrict__ c_jac2Dw, const int* __restrict__ ibool) {
+                                                       const realw* __restrict__ c_jac2Dw, const int* __restrict__ ibool,
+                                                       size_t nglob) {
   const int iface = blockIdx.x, igll = threadIdx.x;
   if (iface >= num_faces || igll >= NGLL2) return;
   const int ispec = c_ispec[iface] - 1;
@@ -185,14 +186,15 @@ __global__ void __launch_bounds__(32) k_coupling_ac_el(const realw* __restrict__
   const int p = (ijk[0] - 1) + NGLLX * (ijk[1] - 1) + NGLL2 * (ijk[2] - 1);
   const size_t iglob = (size_t)ibool[(size_t)ispec * NGLL3_PADDED + p] - 1;
   const realw* n = c_normal + 3 * (igll + NGLL2 * (size_t)iface);
-  const realw displ_n = displ[3 * iglob] * n[0] + displ[3 * iglob + 1] * n[1] + displ[3 * iglob + 2] * n[2];
+  const realw displ_n = displ[vidx(iglob, 0, nglob)] * n[0] + displ[vidx(iglob, 1, nglob)] * n[1] + displ[vidx(iglob, 2, nglob)] * n[2];
   red_add(potential_dot_dot + iglob, c_jac2Dw[igll + NGLL2 * (size_t)iface] * displ_n);
 }
 
 __global__ void __launch_bounds__(32) k_coupling_el_ac(const realw* __restrict__ potential_dot_dot, realw* accel,
                                                        int num_faces, const int* __restrict__ c_ispec,
                                                        const int* __restrict__ c_ijk, const realw* __restrict__ c_normal,
-                                                       const realw* __restrict__ c_jac2Dw, const int* __restrict__ ibool) {
+                                                       const realw* __restrict__ c_jac2Dw, const int* __restrict__ ibool,
+                                                       size_t nglob) {
   const int iface = blockIdx.x, igll = threadIdx.x;
   if (iface >= num_faces || igll >= NGLL2) return;
   const int ispec = c_ispec[iface] - 1;
@@ -202,9 +204,9 @@ __global__ void __launch_bounds__(32) k_coupling_el_ac(const realw* __restrict__
   const realw* n = c_normal + 3 * (igll + NGLL2 * (size_t)iface);
   const realw pressure = -potential_dot_dot[iglob];
   const realw jw = c_jac2Dw[igll + NGLL2 * (size_t)iface];
-  red_add(accel + 3 * iglob, jw * n[0] * pressure);
-  red_add(accel + 3 * iglob + 1, jw * n[1] * pressure);
-  red_add(accel + 3 * iglob + 2, jw * n[2] * pressure);
+  red_add(accel + vidx(iglob, 0, nglob), jw * n[0] * pressure);
+  red_add(accel + vidx(iglob, 1, nglob), jw * n[1] * pressure);
+  red_add(accel + vidx(iglob, 2, nglob), jw * n[2] * pressure);
 }
 
 // acoustic free surface: zero the potential and its derivatives (replaces enforce_free_surface_cuda_kernel,
@@ -233,7 +235,8 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_add_sources_el(realw* accel, c
                                                                   const realw* __restrict__ stf_pre_compute, int myrank,
                                                                   const int* __restrict__ islice_selected_source,
                                                                   const int* __restrict__ ispec_selected_source,
-                                                                  const int* __restrict__ ispec_is_elastic, int NSOURCES) {
+                                                                  const int* __restrict__ ispec_is_elastic, int NSOURCES,
+                                                                  size_t nglob) {
   const int isrc = blockIdx.x, p = threadIdx.x;
   if (isrc >= NSOURCES || p >= NGLL3) return;
   if (islice_selected_source[isrc] != myrank) return;
@@ -242,7 +245,7 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_add_sources_el(realw* accel, c
   const size_t iglob = (size_t)ibool[(size_t)ispec * NGLL3_PADDED + p] - 1;
   const realw stf = stf_pre_compute[isrc];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) red_add(accel + 3 * iglob + c, sourcearrays[isrc + (size_t)NSOURCES * (c + 3 * p)] * stf);
+  for (int c = 0; c < 3; ++c) red_add(accel + vidx(iglob, c, nglob), sourcearrays[isrc + (size_t)NSOURCES * (c + 3 * p)] * stf);
 }
 
 __global__ void __launch_bounds__(NGLL3_PADDED) k_add_sources_ac(realw* potential_dot_dot, const int* __restrict__ ibool,
@@ -285,7 +288,7 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_seismogram_vector(
     const int* __restrict__ ispec_is_elastic, const int* __restrict__ ispec_is_acoustic,
     const realw* __restrict__ rhostore, const realw* __restrict__ metric, const int* __restrict__ irregular_element_number,
     realw xix_regular, int seismo_current, int corr_mode, const realw* __restrict__ corr_accel,
-    const realw* __restrict__ corr_rmass3, realw corr_deltatover2) {
+    const realw* __restrict__ corr_rmass3, realw corr_deltatover2, size_t nglob) {
   // corr_mode (elastic receivers while the Newmark corrector is still pending): 0 = field is current,
   // 1 = field is veloc: use veloc + dt/2 (accel rmass), 2 = field is accel: use accel rmass
   const int irec = blockIdx.x;
@@ -305,12 +308,12 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_seismogram_vector(
     realw f[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      f[c] = field[3 * iglob + c];
+      f[c] = field[vidx(iglob, c, nglob)];
       if (corr_mode == 1) {
-        const realw a = corr_accel[3 * iglob + c] * corr_rmass3[3 * iglob + c];
+        const realw a = corr_accel[vidx(iglob, c, nglob)] * corr_rmass3[vidx(iglob, c, nglob)];
         f[c] += corr_deltatover2 * a;
       } else if (corr_mode == 2) {
-        f[c] *= corr_rmass3[3 * iglob + c];
+        f[c] *= corr_rmass3[vidx(iglob, c, nglob)];
       }
     }
     dx = hl * f[0]; dy = hl * f[1]; dz = hl * f[2];
@@ -355,7 +358,7 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_seismogram_pressure(
     const int* __restrict__ ispec_selected_rec_loc, const int* __restrict__ ispec_is_acoustic,
     const int* __restrict__ ispec_is_elastic, const realw* __restrict__ kappav, const realw* __restrict__ muv,
     const realw* __restrict__ metric, const int* __restrict__ irregular_element_number, realw xix_regular,
-    int seismo_current) {
+    int seismo_current, size_t nglob) {
   const int irec = blockIdx.x;
   if (irec >= nrec_local) return;
   const int tx = threadIdx.x;
@@ -374,7 +377,7 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_seismogram_pressure(
     }
   } else if (ispec_is_elastic[ispec] && displ) {  // uniform per block
     const size_t iglob = (size_t)ibool[(size_t)ispec * NGLL3_PADDED + t] - 1;
-    s_u[0][t] = displ[3 * iglob]; s_u[1][t] = displ[3 * iglob + 1]; s_u[2][t] = displ[3 * iglob + 2];
+    s_u[0][t] = displ[vidx(iglob, 0, nglob)]; s_u[1][t] = displ[vidx(iglob, 1, nglob)]; s_u[2][t] = displ[vidx(iglob, 2, nglob)];
     __syncthreads();
     realw t1[3] = {0.f, 0.f, 0.f}, t2[3] = {0.f, 0.f, 0.f}, t3[3] = {0.f, 0.f, 0.f};
 #pragma unroll
@@ -417,27 +420,27 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_seismogram_pressure(
 template <int NCOMP>
 __global__ void __launch_bounds__(256) k_halo_pack(const realw* __restrict__ field, realw* __restrict__ buffer,
                                                    int num_interfaces, int max_nibool, const int* __restrict__ nibool,
-                                                   const int* __restrict__ ibool_interfaces) {
+                                                   const int* __restrict__ ibool_interfaces, size_t nglob) {
   const int ipoin = blockIdx.x * blockDim.x + threadIdx.x;
   const int iface = blockIdx.y;
   if (iface >= num_interfaces || ipoin >= nibool[iface]) return;
   const size_t slot = ipoin + (size_t)max_nibool * iface;
   const size_t iglob = (size_t)ibool_interfaces[slot] - 1;
 #pragma unroll
-  for (int c = 0; c < NCOMP; ++c) buffer[NCOMP * slot + c] = field[NCOMP * iglob + c];
+  for (int c = 0; c < NCOMP; ++c) buffer[NCOMP * slot + c] = field[vidxn<NCOMP>(iglob, c, nglob)];
 }
 
 template <int NCOMP>
 __global__ void __launch_bounds__(256) k_halo_unpack_add(realw* field, const realw* __restrict__ buffer, int num_interfaces,
                                                          int max_nibool, const int* __restrict__ nibool,
-                                                         const int* __restrict__ ibool_interfaces) {
+                                                         const int* __restrict__ ibool_interfaces, size_t nglob) {
   const int ipoin = blockIdx.x * blockDim.x + threadIdx.x;
   const int iface = blockIdx.y;
   if (iface >= num_interfaces || ipoin >= nibool[iface]) return;
   const size_t slot = ipoin + (size_t)max_nibool * iface;
   const size_t iglob = (size_t)ibool_interfaces[slot] - 1;
 #pragma unroll
-  for (int c = 0; c < NCOMP; ++c) red_add(field + NCOMP * iglob + c, buffer[NCOMP * slot + c]);
+  for (int c = 0; c < NCOMP; ++c) red_add(field + vidxn<NCOMP>(iglob, c, nglob), buffer[NCOMP * slot + c]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -445,6 +448,19 @@ __global__ void __launch_bounds__(256) k_halo_unpack_add(realw* field, const rea
 // src/gpu/kernels/get_maximum_vector_kernel.cu): per-block maxima, final max on the host.
 // vector: max over points of (ux^2+uy^2+uz^2) (the wrapper takes the sqrt); scalar: max |x|.
 // ---------------------------------------------------------------------------------------------------------------
+// host layout (NDIM,NGLOB) <-> the library's vector-wavefield layout (kernels_common.cuh: vidx); transfer_* entry points only
+template <bool TO_LIBRARY>
+__global__ void __launch_bounds__(256) k_vector_layout(realw* __restrict__ dst, const realw* __restrict__ src, size_t nglob) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nglob; i += stride) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (TO_LIBRARY) dst[vidx(i, c, nglob)] = src[3 * i + c];
+      else dst[3 * i + c] = src[vidx(i, c, nglob)];
+    }
+  }
+}
+
 template <bool VECTOR>
 __global__ void __launch_bounds__(256) k_max_norm(const realw* __restrict__ f, long long npoints, realw* __restrict__ partial) {
   realw m = 0.f;
@@ -452,7 +468,7 @@ __global__ void __launch_bounds__(256) k_max_norm(const realw* __restrict__ f, l
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npoints; i += stride) {
     realw v;
     if (VECTOR) {
-      const realw x = f[3 * i], y = f[3 * i + 1], z = f[3 * i + 2];
+      const realw x = f[vidx(i, 0, npoints)], y = f[vidx(i, 1, npoints)], z = f[vidx(i, 2, npoints)];
       v = x * x + y * y + z * z;
     } else {
       v = fabsf(f[i]);

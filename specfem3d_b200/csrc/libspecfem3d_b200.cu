@@ -329,15 +329,16 @@ extern "C" void SB200_FC(prepare_fields_elastic_device)(
     mp->d_send_accel_buffer = dev_alloc_zero<realw>(mp->size_mpi_buffer);
   }
 
-  // interleave the three inverse mass matrices -> [NGLOB][3] so the corrector is a flat stream
+  // the three inverse mass matrices in the layout of the wavefields (kernels_common.cuh: vidx) so the corrector is a
+  // flat stream
   {
     std::vector<realw> r3(NDIM * nglob);
     for (size_t i = 0; i < nglob; ++i) {
-      r3[3 * i] = rmassx[i];
-      r3[3 * i + 1] = rmassy[i];
-      r3[3 * i + 2] = rmassz[i];
+      r3[vidx(i, 0, nglob)] = rmassx[i];
+      r3[vidx(i, 1, nglob)] = rmassy[i];
+      r3[vidx(i, 2, nglob)] = rmassz[i];
     }
-    mp->d_rmassx = dev_copy(r3.data(), r3.size());  // d_rmassx holds the interleaved copy
+    mp->d_rmassx = dev_copy(r3.data(), r3.size());  // d_rmassx holds all three
   }
   mp->num_phase_ispec_elastic = *num_phase_ispec_elastic;
   mp->d_phase_ispec_inner_elastic = dev_copy(phase_ispec_inner_elastic, 2 * (size_t)mp->num_phase_ispec_elastic);
@@ -504,31 +505,55 @@ static void d2h(DeviceMesh* mp, realw* h, const realw* d, size_t n) {
   CUDA_CHECK(cudaStreamSynchronize(mp->compute_stream));
 }
 
+// vector wavefields: the Fortran (NDIM,NGLOB) array <-> the library's component planes (kernels_common.cuh: vidx), through
+// a temporary device buffer and one transposing kernel (these entry points are outside the time loop)
+static void h2d_vec(DeviceMesh* mp, realw* d, const realw* h, int size) {
+  if (!d) exit_on_error("transfer to a device field that was never allocated (prepare_fields_* not called?)");
+  if ((size_t)size != (size_t)NDIM * mp->NGLOB_AB) exit_on_error("transfer of a vector wavefield: size is not NDIM * NGLOB_AB");
+  if (!SB200_SOA) { h2d(mp, d, h, size); return; }
+  realw* tmp = dev_alloc<realw>(size);
+  h2d(mp, tmp, h, size);
+  k_vector_layout<true><<<streaming_grid(mp->NGLOB_AB), 256, 0, mp->compute_stream>>>(d, tmp, (size_t)mp->NGLOB_AB);
+  KERNEL_CHECK(mp, "k_vector_layout(to planes)");
+  CUDA_CHECK(cudaStreamSynchronize(mp->compute_stream));
+  dev_free(tmp);
+}
+static void d2h_vec(DeviceMesh* mp, realw* h, const realw* d, int size) {
+  if (!d) exit_on_error("transfer from a device field that was never allocated (prepare_fields_* not called?)");
+  if ((size_t)size != (size_t)NDIM * mp->NGLOB_AB) exit_on_error("transfer of a vector wavefield: size is not NDIM * NGLOB_AB");
+  if (!SB200_SOA) { d2h(mp, h, d, size); return; }
+  realw* tmp = dev_alloc<realw>(size);
+  k_vector_layout<false><<<streaming_grid(mp->NGLOB_AB), 256, 0, mp->compute_stream>>>(tmp, d, (size_t)mp->NGLOB_AB);
+  KERNEL_CHECK(mp, "k_vector_layout(from planes)");
+  d2h(mp, h, tmp, size);
+  dev_free(tmp);
+}
+
 extern "C" void SB200_FC(transfer_fields_el_to_device)(int* size, realw* displ, realw* veloc, realw* accel, long* Mesh_pointer) {
   DeviceMesh* mp = get_mesh(Mesh_pointer);
-  h2d(mp, mp->d_displ, displ, *size); h2d(mp, mp->d_veloc, veloc, *size); h2d(mp, mp->d_accel, accel, *size);
+  h2d_vec(mp, mp->d_displ, displ, *size); h2d_vec(mp, mp->d_veloc, veloc, *size); h2d_vec(mp, mp->d_accel, accel, *size);
 }
 extern "C" void SB200_FC(transfer_fields_el_from_device)(int* size, realw* displ, realw* veloc, realw* accel, long* Mesh_pointer) {
   DeviceMesh* mp = get_mesh(Mesh_pointer);
-  d2h(mp, displ, mp->d_displ, *size); d2h(mp, veloc, mp->d_veloc, *size); d2h(mp, accel, mp->d_accel, *size);
+  d2h_vec(mp, displ, mp->d_displ, *size); d2h_vec(mp, veloc, mp->d_veloc, *size); d2h_vec(mp, accel, mp->d_accel, *size);
 }
 extern "C" void SB200_FC(transfer_displ_to_device)(int* size, realw* displ, long* Mesh_pointer) {
-  DeviceMesh* mp = get_mesh(Mesh_pointer); h2d(mp, mp->d_displ, displ, *size);
+  DeviceMesh* mp = get_mesh(Mesh_pointer); h2d_vec(mp, mp->d_displ, displ, *size);
 }
 extern "C" void SB200_FC(transfer_displ_from_device)(int* size, realw* displ, long* Mesh_pointer) {
-  DeviceMesh* mp = get_mesh(Mesh_pointer); d2h(mp, displ, mp->d_displ, *size);
+  DeviceMesh* mp = get_mesh(Mesh_pointer); d2h_vec(mp, displ, mp->d_displ, *size);
 }
 extern "C" void SB200_FC(transfer_veloc_to_device)(int* size, realw* veloc, long* Mesh_pointer) {
-  DeviceMesh* mp = get_mesh(Mesh_pointer); h2d(mp, mp->d_veloc, veloc, *size);
+  DeviceMesh* mp = get_mesh(Mesh_pointer); h2d_vec(mp, mp->d_veloc, veloc, *size);
 }
 extern "C" void SB200_FC(transfer_veloc_from_device)(int* size, realw* veloc, long* Mesh_pointer) {
-  DeviceMesh* mp = get_mesh(Mesh_pointer); d2h(mp, veloc, mp->d_veloc, *size);
+  DeviceMesh* mp = get_mesh(Mesh_pointer); d2h_vec(mp, veloc, mp->d_veloc, *size);
 }
 extern "C" void SB200_FC(transfer_accel_to_device)(int* size, realw* accel, long* Mesh_pointer) {
-  DeviceMesh* mp = get_mesh(Mesh_pointer); h2d(mp, mp->d_accel, accel, *size);
+  DeviceMesh* mp = get_mesh(Mesh_pointer); h2d_vec(mp, mp->d_accel, accel, *size);
 }
 extern "C" void SB200_FC(transfer_accel_from_device)(int* size, realw* accel, long* Mesh_pointer) {
-  DeviceMesh* mp = get_mesh(Mesh_pointer); d2h(mp, accel, mp->d_accel, *size);
+  DeviceMesh* mp = get_mesh(Mesh_pointer); d2h_vec(mp, accel, mp->d_accel, *size);
 }
 extern "C" void SB200_FC(transfer_fields_ac_to_device)(int* size, field* p, field* pd, field* pdd, long* Mesh_pointer) {
   DeviceMesh* mp = get_mesh(Mesh_pointer);
@@ -681,6 +706,7 @@ static void launch_elastic(DeviceMesh* mp, int nb, const int* phase_list, int fi
   a.is_CPML = (mp->pml_conditions && mp->NSPEC_CPML > 0) ? mp->d_is_CPML : nullptr;
   a.deltat = deltat;
   a.use_atomics = use_atomics;
+  a.nglob = (size_t)mp->NGLOB_AB;
   a.R_xx = mp->d_R_xx; a.R_yy = mp->d_R_yy; a.R_xy = mp->d_R_xy; a.R_xz = mp->d_R_xz; a.R_yz = mp->d_R_yz;
   a.R_trace = mp->d_R_trace;
   a.factor_common = mp->d_factor_common; a.factor_common_kappa = mp->d_factor_common_kappa;
@@ -850,7 +876,7 @@ extern "C" void SB200_FC(compute_stacey_viscoelastic_cuda)(long* Mesh_pointer, i
   k_stacey_elastic<<<mp->num_abs_boundary_faces, 32, 0, mp->compute_stream>>>(
       mp->d_veloc, mp->d_accel, mp->d_abs_boundary_ispec, mp->d_abs_boundary_ijk, mp->d_abs_boundary_normal,
       mp->d_abs_boundary_jacobian2Dw, mp->d_ibool, mp->d_rho_vp, mp->d_rho_vs, mp->d_ispec_is_elastic,
-      mp->num_abs_boundary_faces, d_b);
+      mp->num_abs_boundary_faces, d_b, (size_t)mp->NGLOB_AB);
   KERNEL_CHECK(mp, "k_stacey_elastic");
   if (d_b) {  // SAVE_FORWARD: hand the absorbed tractions back for the Fortran side to write (blocking, like the reference)
     CUDA_CHECK(cudaMemcpyAsync(b_absorb_field, d_b, mp->b_reclen_field, cudaMemcpyDeviceToHost, mp->compute_stream));
@@ -887,7 +913,7 @@ extern "C" void SB200_FC(compute_coupling_ac_el_cuda)(long* Mesh_pointer, int* i
   if (nf == 0) return;
   k_coupling_ac_el<<<nf, 32, 0, mp->compute_stream>>>(mp->d_displ, mp->d_potential_dot_dot, nf, mp->d_coupling_ac_el_ispec,
                                                       mp->d_coupling_ac_el_ijk, mp->d_coupling_ac_el_normal,
-                                                      mp->d_coupling_ac_el_jacobian2Dw, mp->d_ibool);
+                                                      mp->d_coupling_ac_el_jacobian2Dw, mp->d_ibool, (size_t)mp->NGLOB_AB);
   KERNEL_CHECK(mp, "k_coupling_ac_el");
 }
 
@@ -900,7 +926,7 @@ extern "C" void SB200_FC(compute_coupling_el_ac_cuda)(long* Mesh_pointer, int* i
   if (nf == 0) return;
   k_coupling_el_ac<<<nf, 32, 0, mp->compute_stream>>>(mp->d_potential_dot_dot, mp->d_accel, nf, mp->d_coupling_ac_el_ispec,
                                                       mp->d_coupling_ac_el_ijk, mp->d_coupling_ac_el_normal,
-                                                      mp->d_coupling_ac_el_jacobian2Dw, mp->d_ibool);
+                                                      mp->d_coupling_ac_el_jacobian2Dw, mp->d_ibool, (size_t)mp->NGLOB_AB);
   KERNEL_CHECK(mp, "k_coupling_el_ac");
 }
 
@@ -927,7 +953,7 @@ extern "C" void SB200_FC(compute_add_sources_el_cuda)(long* Mesh_pointer, double
   const realw* d_stf = upload_stf(mp, h_stf_pre_compute, *h_NSOURCES);
   k_add_sources_el<<<mp->nsources, NGLL3_PADDED, 0, mp->compute_stream>>>(
       mp->d_accel, mp->d_ibool, mp->d_sourcearrays, d_stf, mp->myrank, mp->d_islice_selected_source,
-      mp->d_ispec_selected_source, mp->d_ispec_is_elastic, mp->nsources);
+      mp->d_ispec_selected_source, mp->d_ispec_is_elastic, mp->nsources, (size_t)mp->NGLOB_AB);
   KERNEL_CHECK(mp, "k_add_sources_el");
 }
 
@@ -962,7 +988,7 @@ extern "C" void SB200_FC(transfer_boun_accel_from_device)(long* Mesh_pointer, re
   if (mp->size_mpi_buffer <= 0) return;
   k_halo_pack<3><<<halo_grid(mp), 256, 0, mp->compute_stream>>>(mp->d_accel, mp->d_send_accel_buffer, mp->num_interfaces_ext_mesh,
                                                                 mp->max_nibool_interfaces_ext_mesh,
-                                                                mp->d_nibool_interfaces_ext_mesh, mp->d_ibool_interfaces_ext_mesh);
+                                                                mp->d_nibool_interfaces_ext_mesh, mp->d_ibool_interfaces_ext_mesh, (size_t)mp->NGLOB_AB);
   KERNEL_CHECK(mp, "k_halo_pack<3>");
   CUDA_CHECK(cudaMemcpyAsync(send_accel_buffer, mp->d_send_accel_buffer, mp->size_mpi_buffer * sizeof(realw),
                              cudaMemcpyDeviceToHost, mp->compute_stream));
@@ -979,7 +1005,7 @@ extern "C" void SB200_FC(transfer_boundary_from_device_a)(long* Mesh_pointer, co
   }
   k_halo_pack<3><<<halo_grid(mp), 256, 0, mp->compute_stream>>>(mp->d_accel, mp->d_send_accel_buffer, mp->num_interfaces_ext_mesh,
                                                                 mp->max_nibool_interfaces_ext_mesh,
-                                                                mp->d_nibool_interfaces_ext_mesh, mp->d_ibool_interfaces_ext_mesh);
+                                                                mp->d_nibool_interfaces_ext_mesh, mp->d_ibool_interfaces_ext_mesh, (size_t)mp->NGLOB_AB);
   KERNEL_CHECK(mp, "k_halo_pack<3>");
   // no host block here (the reference synchronises compute_stream): the copy stream waits on an event instead, so
   // the inner-element kernel can be enqueued immediately behind the pack kernel
@@ -1032,7 +1058,7 @@ extern "C" void SB200_FC(transfer_asmbl_accel_to_device)(long* Mesh_pointer, rea
                                                                       mp->num_interfaces_ext_mesh,
                                                                       mp->max_nibool_interfaces_ext_mesh,
                                                                       mp->d_nibool_interfaces_ext_mesh,
-                                                                      mp->d_ibool_interfaces_ext_mesh);
+                                                                      mp->d_ibool_interfaces_ext_mesh, (size_t)mp->NGLOB_AB);
   KERNEL_CHECK(mp, "k_halo_unpack_add<3>");
 }
 
@@ -1047,7 +1073,7 @@ extern "C" void SB200_FC(transfer_boun_pot_from_device)(long* Mesh_pointer, fiel
   }
   k_halo_pack<1><<<halo_grid(mp), 256, 0, mp->compute_stream>>>(mp->d_potential_dot_dot, mp->d_send_potential_buffer,
                                                                 mp->num_interfaces_ext_mesh, mp->max_nibool_interfaces_ext_mesh,
-                                                                mp->d_nibool_interfaces_ext_mesh, mp->d_ibool_interfaces_ext_mesh);
+                                                                mp->d_nibool_interfaces_ext_mesh, mp->d_ibool_interfaces_ext_mesh, (size_t)mp->NGLOB_AB);
   KERNEL_CHECK(mp, "k_halo_pack<1>");
   CUDA_CHECK(cudaMemcpyAsync(send_potential_dot_dot_buffer, mp->d_send_potential_buffer,
                              mp->size_mpi_buffer_potential * sizeof(realw), cudaMemcpyDeviceToHost, mp->compute_stream));
@@ -1069,7 +1095,7 @@ extern "C" void SB200_FC(transfer_asmbl_pot_to_device)(long* Mesh_pointer, field
                                                                       mp->num_interfaces_ext_mesh,
                                                                       mp->max_nibool_interfaces_ext_mesh,
                                                                       mp->d_nibool_interfaces_ext_mesh,
-                                                                      mp->d_ibool_interfaces_ext_mesh);
+                                                                      mp->d_ibool_interfaces_ext_mesh, (size_t)mp->NGLOB_AB);
   KERNEL_CHECK(mp, "k_halo_unpack_add<1>");
   // the host buffer may be reused by the caller as soon as we return (pageable memcpy semantics)
   CUDA_CHECK(cudaStreamSynchronize(mp->compute_stream));
@@ -1101,7 +1127,7 @@ extern "C" void SB200_FC(compute_seismograms_cuda)(long* Mesh_pointer_f, realw* 
         mp->nrec_local, s.vec, s.pot, mp->d_ibool, mp->d_hxir, mp->d_hetar, mp->d_hgammar, s.out, mp->d_nu_rec,
         mp->d_ispec_selected_rec_loc, mp->d_ispec_is_elastic, mp->d_ispec_is_acoustic, mp->d_rhostore, mp->d_metric,
         mp->d_irregular_element_number, mp->xix_regular, seismo_current, s.corr_mode, mp->d_accel, mp->d_rmassx,
-        mp->pending_deltatover2);
+        mp->pending_deltatover2, (size_t)mp->NGLOB_AB);
     KERNEL_CHECK(mp, "k_seismogram_vector");
   }
   if (mp->save_seismograms_p) {
@@ -1109,7 +1135,7 @@ extern "C" void SB200_FC(compute_seismograms_cuda)(long* Mesh_pointer_f, realw* 
     k_seismogram_pressure<<<mp->nrec_local, NGLL3_PADDED, 0, mp->compute_stream>>>(
         mp->nrec_local, pot, mp->d_displ, mp->d_ibool, mp->d_hxir, mp->d_hetar, mp->d_hgammar, mp->d_seismograms_p,
         mp->d_ispec_selected_rec_loc, mp->d_ispec_is_acoustic, mp->d_ispec_is_elastic, mp->d_kappav, mp->d_muv, mp->d_metric,
-        mp->d_irregular_element_number, mp->xix_regular, seismo_current);
+        mp->d_irregular_element_number, mp->xix_regular, seismo_current, (size_t)mp->NGLOB_AB);
     KERNEL_CHECK(mp, "k_seismogram_pressure");
   }
   if (seismo_current == nlength - 1 || *itf == *it_endf) {

@@ -67,6 +67,7 @@ struct PmlArgs {
   const realw *kappav, *muv, *rhostore;
   const realw *displ, *veloc;
   realw* accel;
+  size_t nglob;  // component-plane stride of displ / veloc / accel (kernels_common.cuh: vidx)
   const realw *displ_old, *displ_new;
   realw* rmem;
   const realw* coef;
@@ -97,8 +98,8 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_pml_elastic_forces(const PmlAr
   realw uu[3], vv[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    uu[c] = a.displ[3 * (size_t)iglob + c];
-    vv[c] = a.veloc[3 * (size_t)iglob + c];
+    uu[c] = a.displ[vidx(iglob, c, a.nglob)];
+    vv[c] = a.veloc[vidx(iglob, c, a.nglob)];
     s_f[c][t] = uu[c];
     s_f[3 + c][t] = a.displ_old[po + c * NGLL3_PADDED];
     s_f[6 + c][t] = a.displ_new[po + c * NGLL3_PADDED];
@@ -284,7 +285,7 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_pml_elastic_forces(const PmlAr
         n2 += s_f[3 * s + 1][K * NGLL2 + l * NGLLX + I] * s_hw[J * NGLLX + l];
         n3 += s_f[3 * s + 2][l * NGLL2 + J * NGLLX + I] * s_hw[K * NGLLX + l];
       }
-      red_add(a.accel + 3 * (size_t)iglob + s, -(fac1 * n1 + fac2 * n2 + fac3 * n3 + acc_pml[s]));
+      red_add(a.accel + vidx(iglob, s, a.nglob), -(fac1 * n1 + fac2 * n2 + fac3 * n3 + acc_pml[s]));
     }
   }
 }
@@ -293,14 +294,14 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_pml_elastic_forces(const PmlAr
 // (update_displ_elastic_PML, update_displacement_scheme.f90:417-455)
 __global__ void __launch_bounds__(NGLL3_PADDED) k_pml_snapshot(const realw* displ, const realw* veloc, const realw* accel,
                                                                 realw* pml_displ, int nspec_cpml, const int* CPML_to_spec,
-                                                                const int* ibool, realw c1, realw c2) {
+                                                                const int* ibool, realw c1, realw c2, size_t nglob) {
   const int e = blockIdx.x, t = threadIdx.x;
   if (e >= nspec_cpml || t >= NGLL3) return;
   const int ispec = CPML_to_spec[e] - 1;
-  const size_t g = 3 * (size_t)(ibool[(size_t)ispec * NGLL3_PADDED + t] - 1);
+  const size_t g = vbase(ibool[(size_t)ispec * NGLL3_PADDED + t] - 1), cs = vstride(nglob);
 #pragma unroll
   for (int c = 0; c < 3; ++c)
-    pml_displ[((size_t)e * 3 + c) * NGLL3_PADDED + t] = displ[g + c] + c1 * veloc[g + c] + c2 * accel[g + c];
+    pml_displ[((size_t)e * 3 + c) * NGLL3_PADDED + t] = displ[g + c * cs] + c1 * veloc[g + c * cs] + c2 * accel[g + c * cs];
 }
 
 // Dirichlet condition on the outer faces of the layer (pml_impose_boundary_condition_elastic,
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_pml_snapshot(const realw* disp
 __global__ void k_pml_impose_boundary(realw* accel, realw* veloc, realw* displ, realw* displ_old, realw* displ_new,
                                       const int* abs_boundary_ispec, const int* abs_boundary_ijk, int num_faces,
                                       const int* ibool, const int* ispec_is_elastic, const int* is_CPML,
-                                      const int* spec_to_CPML) {
+                                      const int* spec_to_CPML, size_t nglob) {
   const int f = blockIdx.x, q = threadIdx.x;
   if (f >= num_faces || q >= NGLL2) return;
   const int ispec = abs_boundary_ispec[f] - 1;
@@ -316,10 +317,10 @@ __global__ void k_pml_impose_boundary(realw* accel, realw* veloc, realw* displ, 
   const int e = spec_to_CPML[ispec] - 1;
   const int* ijk = abs_boundary_ijk + ((size_t)f * NGLL2 + q) * 3;
   const int p = (ijk[0] - 1) + NGLLX * (ijk[1] - 1) + NGLL2 * (ijk[2] - 1);
-  const size_t g = 3 * (size_t)(ibool[(size_t)ispec * NGLL3_PADDED + p] - 1);
+  const size_t g = vbase(ibool[(size_t)ispec * NGLL3_PADDED + p] - 1), cs = vstride(nglob);
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    accel[g + c] = 0.f; veloc[g + c] = 0.f; displ[g + c] = 0.f;
+    accel[g + c * cs] = 0.f; veloc[g + c * cs] = 0.f; displ[g + c * cs] = 0.f;
     displ_old[((size_t)e * 3 + c) * NGLL3_PADDED + p] = 0.f;
     displ_new[((size_t)e * 3 + c) * NGLL3_PADDED + p] = 0.f;
   }
@@ -342,7 +343,7 @@ inline void pml_snapshot_displ(DeviceMesh* mp, int which, realw /*deltat*/, real
   const realw theta = 0.125f;
   k_pml_snapshot<<<P->nspec_cpml, NGLL3_PADDED, 0, mp->compute_stream>>>(
       mp->d_displ, mp->d_veloc, mp->d_accel, which == 0 ? P->d_displ_old : P->d_displ_new, P->nspec_cpml, P->d_CPML_to_spec,
-      mp->d_ibool, deltatover2 * (1.0f - 2.0f * theta), deltatsqover2 * (1.0f - theta));
+      mp->d_ibool, deltatover2 * (1.0f - 2.0f * theta), deltatsqover2 * (1.0f - theta), (size_t)mp->NGLOB_AB);
   KERNEL_CHECK(mp, "k_pml_snapshot");
 }
 
@@ -379,7 +380,7 @@ inline void pml_compute_forces(DeviceMesh* mp, int iphase, int nspec_outer, int 
   a.xix_regular = mp->xix_regular;
   a.jacobian_regular = mp->jacobian_regular;
   a.kappav = mp->d_kappav; a.muv = mp->d_muv; a.rhostore = mp->d_rhostore;
-  a.displ = mp->d_displ; a.veloc = mp->d_veloc; a.accel = mp->d_accel;
+  a.displ = mp->d_displ; a.veloc = mp->d_veloc; a.accel = mp->d_accel; a.nglob = (size_t)mp->NGLOB_AB;
   a.displ_old = P->d_displ_old; a.displ_new = P->d_displ_new;
   a.rmem = P->d_rmem; a.coef = P->d_coef; a.wgll_cube = P->d_wgll_cube;
   a.store_strain = mp->compute_and_store_strain;
@@ -442,7 +443,7 @@ extern "C" void SB200_FC(pml_impose_boundary_condition_elastic_cuda)(long* Mesh_
   if (!mp->pml_conditions || !P || P->nspec_cpml == 0 || mp->num_abs_boundary_faces == 0) return;
   k_pml_impose_boundary<<<mp->num_abs_boundary_faces, 32, 0, mp->compute_stream>>>(
       mp->d_accel, mp->d_veloc, mp->d_displ, P->d_displ_old, P->d_displ_new, mp->d_abs_boundary_ispec, mp->d_abs_boundary_ijk,
-      mp->num_abs_boundary_faces, mp->d_ibool, mp->d_ispec_is_elastic, mp->d_is_CPML, P->d_spec_to_CPML);
+      mp->num_abs_boundary_faces, mp->d_ibool, mp->d_ispec_is_elastic, mp->d_is_CPML, P->d_spec_to_CPML, (size_t)mp->NGLOB_AB);
   KERNEL_CHECK(mp, "k_pml_impose_boundary");
 }
 
