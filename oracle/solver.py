@@ -91,6 +91,7 @@ class OraclePartition:
         ph = np.ascontiguousarray(db.phase_ispec_inner_elastic[iphase - 1])
         a = self.att
         att = 1 if sim.ATTENUATION else 0
+        st = getattr(self, "strain", None)  # kernel runs without attenuation (oracle/adjoint.py): stored strains
         is_cpml = db.is_CPML if sim.PML_CONDITIONS else None
         lib().oracle_compute_forces_viscoelastic(
             c_int(nel), P(ph), P(db.ibool), P(db.irregular_element_number), P(db.xixstore), P(db.xiystore),
@@ -100,11 +101,14 @@ class OraclePartition:
             P(g.hprime_xx.ravel(order="F").copy()), P(g.hprimewgll_xx.ravel(order="F").copy()),
             P(g.wgllwgll_xy.ravel(order="F").copy()), P(g.wgllwgll_xz.ravel(order="F").copy()),
             P(g.wgllwgll_yz.ravel(order="F").copy()), P(self.displ), P(self.veloc), P(self.accel), P(is_cpml),
-            c_float(sim.deltat), c_int(att), c_int(att),
+            c_float(sim.deltat), c_int(att), c_int(1 if (att or st is not None) else 0),
             *( [P(a[k]) for k in ("R_xx", "R_yy", "R_xy", "R_xz", "R_yz", "R_trace", "epsilondev_xx", "epsilondev_yy",
                                   "epsilondev_xy", "epsilondev_xz", "epsilondev_yz", "epsilondev_trace",
                                   "factor_common", "factor_common_kappa", "alphaval", "betaval", "gammaval")]
-               if a is not None else [None] * 17))
+               if a is not None else
+               ([None] * 6 + [P(st[k]) for k in ("epsilondev_xx", "epsilondev_yy", "epsilondev_xy", "epsilondev_xz",
+                                                 "epsilondev_yz")] + [None] * 6 if st is not None else [None] * 17)),
+            P(st["epsilon_trace_over_3"]) if st is not None else None)
         if sim.PML_CONDITIONS and self.pml is not None:
             from . import pml_oracle
 

@@ -145,7 +145,7 @@ static inline void contract3w(const realw M[5][5], const realw* B1, const realw*
  * attenuation : != 0 -> R_*, epsilondev_*, factor_common(_kappa), alphaval/betaval/gammaval are used;
  *               strain of u + deltat*v is formed the CPU way (gradient of u plus gradient of deltat*v, :396-412).
  * compute_and_store_strain without attenuation also stores epsilondev_* (:540-552,945-959) when the pointers are
- * non-NULL.
+ * non-NULL; epsilon_trace_over_3 (kernel runs, :546,560) likewise.
  * ------------------------------------------------------------------------------------------------------------- */
 void oracle_compute_forces_viscoelastic(
     int num_elements, const int* phase_ispec, const int* ibool, const int* irregular_element_number,
@@ -157,7 +157,7 @@ void oracle_compute_forces_viscoelastic(
     int compute_and_store_strain, realw* R_xx, realw* R_yy, realw* R_xy, realw* R_xz, realw* R_yz, realw* R_trace,
     realw* epsilondev_xx, realw* epsilondev_yy, realw* epsilondev_xy, realw* epsilondev_xz, realw* epsilondev_yz,
     realw* epsilondev_trace, const realw* factor_common, const realw* factor_common_kappa, const realw* alphaval,
-    const realw* betaval, const realw* gammaval) {
+    const realw* betaval, const realw* gammaval, realw* epsilon_trace_over_3 /* NULL unless SIMULATION_TYPE == 3 (:546,560) */) {
   realw HP[5][5], HW[5][5]; /* HP[a][l] = hprime_xx(a,l) ; HW[a][l] = hprimewgll_xx(l,a) */
   for (int a = 0; a < 5; ++a)
     for (int l = 0; l < 5; ++l) {
@@ -377,6 +377,7 @@ void oracle_compute_forces_viscoelastic(
     if (compute_and_store_strain && epsilondev_xx) {
       for (int p = 0; p < NGLL3; ++p) {
         if (attenuation) epsilondev_trace[eo + p] = e_tr[p];
+        if (epsilon_trace_over_3) epsilon_trace_over_3[eo + p] = ONE_THIRD * e_tr[p];
         epsilondev_xx[eo + p] = e_xx[p];
         epsilondev_yy[eo + p] = e_yy[p];
         epsilondev_xy[eo + p] = e_xy[p];

@@ -59,7 +59,7 @@ def build_meshgen(force: bool = False) -> str:
 
 def build_cuda(force: bool = False, verbose: bool = False) -> str:
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
-    deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(
+    deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.inc")) + glob.glob(
         os.path.join(ROOT, "include", "*.h"))
     if not force and _newer(LIB_PATH, deps):
         return LIB_PATH

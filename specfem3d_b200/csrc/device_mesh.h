@@ -149,6 +149,19 @@ struct DeviceMesh {
   realw *d_send_accel_buffer = nullptr, *h_send_accel_buffer = nullptr, *h_recv_accel_buffer = nullptr;
   realw *d_send_potential_buffer = nullptr;
 
+  // kernel (SIMULATION_TYPE == 3) runs: backward / reconstructed wavefield, its stored strains, sensitivity kernels
+  // and adjoint sources (adjoint.cuh)
+  realw *d_b_displ = nullptr, *d_b_veloc = nullptr, *d_b_accel = nullptr;  // component planes like d_displ
+  realw *d_b_epsilondev_xx = nullptr, *d_b_epsilondev_yy = nullptr, *d_b_epsilondev_xy = nullptr,
+        *d_b_epsilondev_xz = nullptr, *d_b_epsilondev_yz = nullptr;                              // [NSPEC][128]
+  realw *d_epsilon_trace_over_3 = nullptr, *d_b_epsilon_trace_over_3 = nullptr;                  // [NSPEC][128]
+  realw *d_rho_kl = nullptr, *d_mu_kl = nullptr, *d_kappa_kl = nullptr;                          // [NSPEC][128]
+  realw *d_hess_el_kl = nullptr, *d_hess_rho_el_kl = nullptr, *d_hess_kappa_el_kl = nullptr, *d_hess_mu_el_kl = nullptr;
+  int anisotropic_kl = 0, approximate_hess_kl = 0;
+  int nadj_rec_local = 0, ntstep_between_read_adjsrc = 0;
+  realw* d_source_adjoint = nullptr;  // Fortran (NDIM, nadj_rec_local, NTSTEP_BETWEEN_READ_ADJSRC)
+  realw* d_b_send_accel_buffer = nullptr;
+
   // peer-to-peer halo over NVLink (extension, see halo_p2p.cuh)
   struct P2P* p2p = nullptr;
 

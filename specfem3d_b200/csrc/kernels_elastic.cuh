@@ -34,6 +34,7 @@ struct ElasticArgs {
   realw *R_xx, *R_yy, *R_xy, *R_xz, *R_yz, *R_trace;                    // [NSPEC][N_SLS][128]
   const realw *factor_common, *factor_common_kappa;                      // [NSPEC][N_SLS][128]
   realw *eps_xx, *eps_yy, *eps_xy, *eps_xz, *eps_yz, *eps_trace;         // [NSPEC][128]
+  realw* eps_trace_over_3 = nullptr;  // [NSPEC][128], kernel runs only (SIMULATION_TYPE == 3, Kernel_2_noatt_iso_impl :890-893)
   int att_prefetch;            // 0 = none, 1 = prefetch the element's attenuation planes into L2, 2 = into L1
 };
 
@@ -286,6 +287,7 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_elastic_forces_pt(const Elasti
     }
     if (ATT || STRAIN) {
       if (ATT) a.eps_trace[off] = e_tr;
+      if (!ATT && a.eps_trace_over_3) a.eps_trace_over_3[off] = 0.33333333333333333333f * e_tr;
       a.eps_xx[off] = e_xx; a.eps_yy[off] = e_yy; a.eps_xy[off] = e_xy; a.eps_xz[off] = e_xz; a.eps_yz[off] = e_yz;
     }
   }

@@ -15,6 +15,7 @@
 #include "kernels_elastic_po.cuh"
 #include "kernels_elastic_pk.cuh"
 #include "kernels_misc.cuh"
+#include "adjoint.cuh"
 #include "pml.cuh"
 #include "halo_p2p.cuh"
 
@@ -158,8 +159,9 @@ extern "C" void SB200_FC(prepare_constants_device)(
   if (*h_NGLLX != NGLLX)
     exit_on_error("NGLLX of the solver differs from the NGLLX = 5 this library is built for (setup/constants.h)");
   if (*h_NB_RUNS_ACOUSTIC_GPU != 1) exit_on_error("NB_RUNS_ACOUSTIC_GPU must be 1 (batched acoustic runs are out of scope)");
-  if (*SIMULATION_TYPE != 1)
-    exit_on_error("SIMULATION_TYPE must be 1: adjoint / kernel simulations are outside the forward hot path of this library");
+  if (*SIMULATION_TYPE != 1 && *SIMULATION_TYPE != 3)
+    exit_on_error("SIMULATION_TYPE must be 1 (forward) or 3 (kernel run: adjoint + reconstructed forward wavefield); "
+                  "the pure adjoint run (2) is not implemented by this library");
   if (*FAULT_SIMULATION != 0) exit_on_error("FAULT_SIMULATION is out of scope of this library");
 
   DeviceMesh* mp = new DeviceMesh();
@@ -172,6 +174,7 @@ extern "C" void SB200_FC(prepare_constants_device)(
   mp->NGLOB_AB = *NGLOB_AB;
   mp->NSPEC_IRREGULAR = *NSPEC_IRREGULAR;
   mp->simulation_type = *SIMULATION_TYPE;
+  if (mp->simulation_type == 3) mp->fuse_newmark = 0;  // two wavefields per step: the corrector is applied where it is called
   mp->save_forward = *SAVE_FORWARD;
   mp->stacey_absorbing_conditions = *STACEY_ABSORBING_CONDITIONS;
   mp->pml_conditions = *PML_CONDITIONS;
@@ -347,7 +350,7 @@ extern "C" void SB200_FC(prepare_fields_elastic_device)(
   if (mp->stacey_absorbing_conditions && mp->num_abs_boundary_faces > 0) {
     mp->d_rho_vp = dev_copy(rho_vp, NGLL3 * nspec);
     mp->d_rho_vs = dev_copy(rho_vs, NGLL3 * nspec);
-    if (mp->simulation_type == 1 && mp->save_forward) {
+    if (mp->simulation_type == 3 || (mp->simulation_type == 1 && mp->save_forward)) {
       mp->b_reclen_field = *b_reclen_field;
       mp->d_b_absorb_field = dev_alloc_zero<realw>(mp->b_reclen_field / sizeof(realw));
     }
@@ -477,7 +480,12 @@ extern "C" void SB200_FC(prepare_cleanup_device)(long* Mesh_pointer, int* ACOUST
                    mp->d_ispec_selected_rec, mp->d_ispec_selected_rec_loc, mp->d_hxir, mp->d_hetar, mp->d_hgammar,
                    mp->d_nu_rec, mp->d_seismograms_d, mp->d_seismograms_v, mp->d_seismograms_a, mp->d_seismograms_p,
                    mp->d_nibool_interfaces_ext_mesh, mp->d_ibool_interfaces_ext_mesh, mp->d_send_accel_buffer,
-                   mp->d_send_potential_buffer, mp->d_norm_partial, mp->d_is_CPML};
+                   mp->d_send_potential_buffer, mp->d_norm_partial, mp->d_is_CPML,
+                   mp->d_b_displ, mp->d_b_veloc, mp->d_b_accel, mp->d_b_epsilondev_xx, mp->d_b_epsilondev_yy,
+                   mp->d_b_epsilondev_xy, mp->d_b_epsilondev_xz, mp->d_b_epsilondev_yz, mp->d_epsilon_trace_over_3,
+                   mp->d_b_epsilon_trace_over_3, mp->d_rho_kl, mp->d_mu_kl, mp->d_kappa_kl, mp->d_hess_el_kl,
+                   mp->d_hess_rho_el_kl, mp->d_hess_kappa_el_kl, mp->d_hess_mu_el_kl, mp->d_source_adjoint,
+                   mp->d_b_send_accel_buffer};
   for (void* p : dptrs) dev_free(p);
   if (mp->h_send_accel_buffer) cudaFreeHost(mp->h_send_accel_buffer);
   if (mp->h_recv_accel_buffer) cudaFreeHost(mp->h_recv_accel_buffer);
@@ -602,6 +610,13 @@ extern "C" void SB200_FC(transfer_strain_from_device)(long* Mesh_pointer, realw*
 // =================================================================================================================
 // the corrector deferred by kernel_3_a_cuda, applied on its own (called through get_mesh() by every entry point that is not
 // prepared to see veloc / accel one half-step behind)
+static void require_backward_fields(DeviceMesh* mp, const char* who) {
+  if (mp->simulation_type != 3 || !mp->d_b_displ) {
+    char msg[256];
+    snprintf(msg, sizeof(msg), "%s: FORWARD_OR_ADJOINT 0 / 3 needs SIMULATION_TYPE == 3 and prepare_fields_elastic_adj_dev", who);
+    exit_on_error(msg);
+  }
+}
 static void flush_corrector_impl(DeviceMesh* mp) {
   if (!mp->corrector_pending) return;
   mp->corrector_pending = false;
@@ -617,8 +632,15 @@ void (*g_flush_corrector)(DeviceMesh*) = &flush_corrector_impl;
 extern "C" void SB200_FC(update_displacement_cuda)(long* Mesh_pointer, realw* deltat_F, realw* deltatover2_F,
                                                    realw* deltatsqover2_F, int* FORWARD_OR_ADJOINT) {
   DeviceMesh* mp = get_mesh_keep_pending(Mesh_pointer);
-  if (*FORWARD_OR_ADJOINT != 1) exit_on_error("update_displacement_cuda: only FORWARD_OR_ADJOINT = 1 is supported");
+  if (*FORWARD_OR_ADJOINT != 1 && *FORWARD_OR_ADJOINT != 3) exit_on_error("update_displacement_cuda: FORWARD_OR_ADJOINT must be 1 or 3");
   const long long n = (long long)NDIM * mp->NGLOB_AB;
+  if (*FORWARD_OR_ADJOINT == 3) {  // backward / reconstructed wavefield: the caller passes b_deltat, b_deltatover2, ...
+    require_backward_fields(mp, "update_displacement_cuda");
+    k_newmark_predictor<<<streaming_grid(n >> 2), 256, 0, mp->compute_stream>>>(mp->d_b_displ, mp->d_b_veloc, mp->d_b_accel, n,
+                                                                                 *deltat_F, *deltatsqover2_F, *deltatover2_F);
+    KERNEL_CHECK(mp, "k_newmark_predictor(backward)");
+    return;
+  }
   if (mp->corrector_pending) {
     // the corrector kernel_3_a_cuda deferred at the end of the previous step and this predictor in one pass
     mp->corrector_pending = false;
@@ -646,10 +668,16 @@ extern "C" void SB200_FC(update_displacement_ac_cuda)(long* Mesh_pointer, realw*
 
 extern "C" void SB200_FC(kernel_3_a_cuda)(long* Mesh_pointer, realw* deltatover2_F, realw* b_deltatover2_F,
                                           int* APPROXIMATE_OCEAN_LOAD, int* FORWARD_OR_ADJOINT) {
-  (void)b_deltatover2_F;
   DeviceMesh* mp = get_mesh(Mesh_pointer);
-  if (*FORWARD_OR_ADJOINT != 1) exit_on_error("kernel_3_a_cuda: only FORWARD_OR_ADJOINT = 1 is supported");
+  if (*FORWARD_OR_ADJOINT != 1 && *FORWARD_OR_ADJOINT != 3) exit_on_error("kernel_3_a_cuda: FORWARD_OR_ADJOINT must be 1 or 3");
   const long long n = (long long)NDIM * mp->NGLOB_AB;
+  if (*FORWARD_OR_ADJOINT == 3) {
+    require_backward_fields(mp, "kernel_3_a_cuda");
+    k_newmark_corrector<<<streaming_grid(n >> 2), 256, 0, mp->compute_stream>>>(mp->d_b_veloc, mp->d_b_accel, mp->d_rmassx, n,
+                                                                                 *b_deltatover2_F, *APPROXIMATE_OCEAN_LOAD == 0);
+    KERNEL_CHECK(mp, "k_newmark_corrector(backward)");
+    return;
+  }
   if (mp->fuse_newmark && *APPROXIMATE_OCEAN_LOAD == 0 && !(mp->pml_conditions && mp->NSPEC_CPML > 0)) {
     // deferred: update_displacement_cuda of the next step applies it together with the predictor; compute_seismograms_cuda
     // evaluates it on the fly at the receivers; every other entry point flushes it first (device_mesh.h: get_mesh)
@@ -665,10 +693,15 @@ extern "C" void SB200_FC(kernel_3_a_cuda)(long* Mesh_pointer, realw* deltatover2
 
 extern "C" void SB200_FC(kernel_3_b_cuda)(long* Mesh_pointer, realw* deltatover2_F, realw* b_deltatover2_F,
                                           int* FORWARD_OR_ADJOINT) {
-  (void)b_deltatover2_F;
   DeviceMesh* mp = get_mesh(Mesh_pointer);
-  if (*FORWARD_OR_ADJOINT != 1) exit_on_error("kernel_3_b_cuda: only FORWARD_OR_ADJOINT = 1 is supported");
+  if (*FORWARD_OR_ADJOINT != 1 && *FORWARD_OR_ADJOINT != 3) exit_on_error("kernel_3_b_cuda: FORWARD_OR_ADJOINT must be 1 or 3");
   const long long n = (long long)NDIM * mp->NGLOB_AB;
+  if (*FORWARD_OR_ADJOINT == 3) {
+    require_backward_fields(mp, "kernel_3_b_cuda");
+    k_newmark_veloc_only<<<streaming_grid(n), 256, 0, mp->compute_stream>>>(mp->d_b_veloc, mp->d_b_accel, n, *b_deltatover2_F);
+    KERNEL_CHECK(mp, "k_newmark_veloc_only(backward)");
+    return;
+  }
   k_newmark_veloc_only<<<streaming_grid(n), 256, 0, mp->compute_stream>>>(mp->d_veloc, mp->d_accel, n, *deltatover2_F);
   KERNEL_CHECK(mp, "k_newmark_veloc_only");
 }
@@ -687,7 +720,8 @@ extern "C" void SB200_FC(kernel_3_acoustic_cuda)(long* Mesh_pointer, realw* delt
 // =================================================================================================================
 // elastic forces (replaces src/gpu/compute_forces_viscoelastic_cuda.cu:1114-1278)
 // =================================================================================================================
-static void launch_elastic(DeviceMesh* mp, int nb, const int* phase_list, int first_ispec, realw deltat, int use_atomics) {
+static void launch_elastic(DeviceMesh* mp, int nb, const int* phase_list, int first_ispec, realw deltat, int use_atomics,
+                           bool backward = false) {
   if (nb <= 0) return;
   ElasticArgs a;
   a.nb_elements = nb;
@@ -712,6 +746,13 @@ static void launch_elastic(DeviceMesh* mp, int nb, const int* phase_list, int fi
   a.factor_common = mp->d_factor_common; a.factor_common_kappa = mp->d_factor_common_kappa;
   a.eps_xx = mp->d_epsilondev_xx; a.eps_yy = mp->d_epsilondev_yy; a.eps_xy = mp->d_epsilondev_xy;
   a.eps_xz = mp->d_epsilondev_xz; a.eps_yz = mp->d_epsilondev_yz; a.eps_trace = mp->d_epsilondev_trace;
+  a.eps_trace_over_3 = mp->d_epsilon_trace_over_3;
+  if (backward) {  // reconstructed forward wavefield of a kernel run (no attenuation there: prepare_fields_elastic_adj_dev)
+    a.displ = mp->d_b_displ; a.veloc = mp->d_b_veloc; a.accel = mp->d_b_accel;
+    a.eps_xx = mp->d_b_epsilondev_xx; a.eps_yy = mp->d_b_epsilondev_yy; a.eps_xy = mp->d_b_epsilondev_xy;
+    a.eps_xz = mp->d_b_epsilondev_xz; a.eps_yz = mp->d_b_epsilondev_yz; a.eps_trace = nullptr;
+    a.eps_trace_over_3 = mp->d_b_epsilon_trace_over_3;
+  }
   static int att_prefetch = -1;
   if (att_prefetch < 0) {
     const char* e = getenv("SPECFEM_B200_ATT_PREFETCH");
@@ -765,10 +806,40 @@ extern "C" void SB200_FC(compute_forces_viscoelastic_cuda)(long* Mesh_pointer, i
                                                            int* COMPUTE_AND_STORE_STRAIN, int* ATTENUATION,
                                                            int* FORWARD_OR_ADJOINT_f) {
   DeviceMesh* mp = get_mesh(Mesh_pointer);
-  if (*FORWARD_OR_ADJOINT_f != 1) exit_on_error("compute_forces_viscoelastic_cuda: only FORWARD_OR_ADJOINT = 1 is supported");
+  const int foa = *FORWARD_OR_ADJOINT_f;
+  if (foa != 0 && foa != 1 && foa != 3) exit_on_error("compute_forces_viscoelastic_cuda: FORWARD_OR_ADJOINT must be 0, 1 or 3");
   if ((*ATTENUATION != 0) != (mp->attenuation != 0)) exit_on_error("compute_forces_viscoelastic_cuda: ATTENUATION differs from prepare_fields_elastic_device");
   (void)COMPUTE_AND_STORE_STRAIN;
   const int num_elements = (*iphase == 1) ? *nspec_outer_elastic : *nspec_inner_elastic;
+  if (foa != 1 || mp->simulation_type == 3) {
+    // kernel run (compute_forces_viscoelastic_cuda.cu:1131-1278): 0 = adjoint wavefield, then the reconstructed forward
+    // wavefield with the caller's deltat; 3 = the reconstructed one only (b_deltat).  Both store their strains for
+    // compute_kernels_elastic_cuda, so the one-thread-per-point kernel is used (the plane-owner kernel stores no strain).
+    if (foa != 1) require_backward_fields(mp, "compute_forces_viscoelastic_cuda");
+    if (mp->pml_conditions && mp->NSPEC_CPML > 0) exit_on_error("compute_forces_viscoelastic_cuda: C-PML in a kernel run is not implemented");
+    for (int pass = 0; pass < 2 && num_elements > 0; ++pass) {
+      const bool backward = pass == 1;
+      if (backward ? foa == 1 : foa == 3) continue;
+      if (mp->use_mesh_coloring_gpu) {
+        int nb_colors, istart, offset;
+        if (*iphase == 1) { nb_colors = mp->num_colors_outer_elastic; istart = 0; offset = 0; }
+        else {
+          nb_colors = mp->num_colors_outer_elastic + mp->num_colors_inner_elastic;
+          istart = mp->num_colors_outer_elastic;
+          offset = *nspec_outer_elastic;
+        }
+        for (int icolor = istart; icolor < nb_colors; ++icolor) {
+          const int nb = mp->h_num_elem_colors_elastic[icolor];
+          launch_elastic(mp, nb, nullptr, offset, *deltat, /*use_atomics=*/0, backward);
+          offset += nb;
+        }
+      } else {
+        const int* list = mp->d_phase_ispec_inner_elastic + (size_t)mp->num_phase_ispec_elastic * (*iphase - 1);
+        launch_elastic(mp, num_elements, list, 0, *deltat, /*use_atomics=*/1, backward);
+      }
+    }
+    return;
+  }
   const bool grp = (mp->force_kernel_variant == 0 || mp->force_kernel_variant >= 3) && !mp->attenuation && !mp->compute_and_store_strain;
   if (num_elements > 0 && grp) {
     ensure_elastic_groups(mp, *nspec_outer_elastic, *nspec_inner_elastic);
@@ -870,9 +941,23 @@ extern "C" void SB200_FC(acoustic_enforce_free_surf_cuda)(long* Mesh_pointer, in
 extern "C" void SB200_FC(compute_stacey_viscoelastic_cuda)(long* Mesh_pointer, int* iphasef, realw* b_absorb_field,
                                                            int* FORWARD_OR_ADJOINT_f) {
   DeviceMesh* mp = get_mesh(Mesh_pointer);
-  if (*FORWARD_OR_ADJOINT_f != 1) exit_on_error("compute_stacey_viscoelastic_cuda: only FORWARD_OR_ADJOINT = 1 is supported");
+  const int foa = *FORWARD_OR_ADJOINT_f;
+  if (foa != 0 && foa != 1 && foa != 3) exit_on_error("compute_stacey_viscoelastic_cuda: FORWARD_OR_ADJOINT must be 0, 1 or 3");
   if (*iphasef != 1 || mp->num_abs_boundary_faces == 0) return;  // only in the first pass
-  realw* d_b = (mp->save_forward && mp->d_b_absorb_field) ? mp->d_b_absorb_field : nullptr;
+  if (foa != 1) {
+    // kernel run: the tractions the forward run absorbed at this time level are put back into the reconstructed
+    // wavefield (compute_stacey_viscoelastic_cuda.cu:78-80,136-152; CPU compute_stacey_viscoelastic_backward)
+    require_backward_fields(mp, "compute_stacey_viscoelastic_cuda");
+    if (!mp->d_b_absorb_field) exit_on_error("compute_stacey_viscoelastic_cuda: b_absorb_field was not prepared");
+    CUDA_CHECK(cudaMemcpyAsync(mp->d_b_absorb_field, b_absorb_field, mp->b_reclen_field, cudaMemcpyHostToDevice, mp->compute_stream));
+    CUDA_CHECK(cudaStreamSynchronize(mp->compute_stream));  // pageable host buffer: the caller may reuse it on return
+    k_stacey_elastic_replay<<<mp->num_abs_boundary_faces, 32, 0, mp->compute_stream>>>(
+        mp->d_b_accel, mp->d_abs_boundary_ispec, mp->d_abs_boundary_ijk, mp->d_ibool, mp->d_ispec_is_elastic,
+        mp->num_abs_boundary_faces, mp->d_b_absorb_field, (size_t)mp->NGLOB_AB);
+    KERNEL_CHECK(mp, "k_stacey_elastic_replay");
+    if (foa == 3) return;
+  }
+  realw* d_b = (mp->simulation_type == 1 && mp->save_forward && mp->d_b_absorb_field) ? mp->d_b_absorb_field : nullptr;
   k_stacey_elastic<<<mp->num_abs_boundary_faces, 32, 0, mp->compute_stream>>>(
       mp->d_veloc, mp->d_accel, mp->d_abs_boundary_ispec, mp->d_abs_boundary_ijk, mp->d_abs_boundary_normal,
       mp->d_abs_boundary_jacobian2Dw, mp->d_ibool, mp->d_rho_vp, mp->d_rho_vs, mp->d_ispec_is_elastic,
@@ -984,8 +1069,19 @@ static dim3 halo_grid(const DeviceMesh* mp) {
 extern "C" void SB200_FC(transfer_boun_accel_from_device)(long* Mesh_pointer, realw* send_accel_buffer,
                                                           const int* FORWARD_OR_ADJOINT) {
   DeviceMesh* mp = get_mesh(Mesh_pointer);
-  if (*FORWARD_OR_ADJOINT != 1) exit_on_error("transfer_boun_accel_from_device: only FORWARD_OR_ADJOINT = 1 is supported");
+  if (*FORWARD_OR_ADJOINT != 1 && *FORWARD_OR_ADJOINT != 3) exit_on_error("transfer_boun_accel_from_device: FORWARD_OR_ADJOINT must be 1 or 3");
   if (mp->size_mpi_buffer <= 0) return;
+  if (*FORWARD_OR_ADJOINT == 3) {  // b_accel through its own staging buffer: the forward copy may still be in flight
+    require_backward_fields(mp, "transfer_boun_accel_from_device");
+    k_halo_pack<3><<<halo_grid(mp), 256, 0, mp->compute_stream>>>(mp->d_b_accel, mp->d_b_send_accel_buffer, mp->num_interfaces_ext_mesh,
+                                                                  mp->max_nibool_interfaces_ext_mesh, mp->d_nibool_interfaces_ext_mesh,
+                                                                  mp->d_ibool_interfaces_ext_mesh, (size_t)mp->NGLOB_AB);
+    KERNEL_CHECK(mp, "k_halo_pack<3>(backward)");
+    CUDA_CHECK(cudaMemcpyAsync(send_accel_buffer, mp->d_b_send_accel_buffer, mp->size_mpi_buffer * sizeof(realw),
+                               cudaMemcpyDeviceToHost, mp->compute_stream));
+    CUDA_CHECK(cudaStreamSynchronize(mp->compute_stream));
+    return;
+  }
   k_halo_pack<3><<<halo_grid(mp), 256, 0, mp->compute_stream>>>(mp->d_accel, mp->d_send_accel_buffer, mp->num_interfaces_ext_mesh,
                                                                 mp->max_nibool_interfaces_ext_mesh,
                                                                 mp->d_nibool_interfaces_ext_mesh, mp->d_ibool_interfaces_ext_mesh, (size_t)mp->NGLOB_AB);
@@ -1042,11 +1138,23 @@ extern "C" void SB200_FC(transfer_asmbl_accel_to_device)(long* Mesh_pointer, rea
                                                          const int* nibool_interfaces_ext_mesh,
                                                          const int* ibool_interfaces_ext_mesh,
                                                          const int* FORWARD_OR_ADJOINT) {
-  (void)buffer_recv_vector_ext_mesh; (void)num_interfaces_ext_mesh; (void)max_nibool_interfaces_ext_mesh;
+  (void)num_interfaces_ext_mesh; (void)max_nibool_interfaces_ext_mesh;
   (void)nibool_interfaces_ext_mesh; (void)ibool_interfaces_ext_mesh;
   DeviceMesh* mp = get_mesh(Mesh_pointer);
-  if (*FORWARD_OR_ADJOINT != 1) exit_on_error("transfer_asmbl_accel_to_device: only FORWARD_OR_ADJOINT = 1 is supported");
+  if (*FORWARD_OR_ADJOINT != 1 && *FORWARD_OR_ADJOINT != 3) exit_on_error("transfer_asmbl_accel_to_device: FORWARD_OR_ADJOINT must be 1 or 3");
   if (mp->size_mpi_buffer <= 0) return;
+  if (*FORWARD_OR_ADJOINT == 3) {  // assemble_MPI_vector_cuda.cu:224-255: the received b_ buffer is copied here, then summed
+    require_backward_fields(mp, "transfer_asmbl_accel_to_device");
+    CUDA_CHECK(cudaMemcpyAsync(mp->d_b_send_accel_buffer, buffer_recv_vector_ext_mesh, mp->size_mpi_buffer * sizeof(realw),
+                               cudaMemcpyHostToDevice, mp->compute_stream));
+    CUDA_CHECK(cudaStreamSynchronize(mp->compute_stream));
+    k_halo_unpack_add<3><<<halo_grid(mp), 256, 0, mp->compute_stream>>>(mp->d_b_accel, mp->d_b_send_accel_buffer,
+                                                                        mp->num_interfaces_ext_mesh, mp->max_nibool_interfaces_ext_mesh,
+                                                                        mp->d_nibool_interfaces_ext_mesh,
+                                                                        mp->d_ibool_interfaces_ext_mesh, (size_t)mp->NGLOB_AB);
+    KERNEL_CHECK(mp, "k_halo_unpack_add<3>(backward)");
+    return;
+  }
   if (p2p_active(mp)) {
     p2p_wait_unpack(mp, 0, mp->d_accel);
     return;
@@ -1117,10 +1225,12 @@ extern "C" void SB200_FC(compute_seismograms_cuda)(long* Mesh_pointer_f, realw* 
   const int nlength = *nlength_seismogramf;
   if (nlength != mp->nlength_seismogram) exit_on_error("compute_seismograms_cuda: nlength_seismogram differs from prepare_constants_device");
   if (seismo_current < 0 || seismo_current >= nlength) exit_on_error("compute_seismograms_cuda: seismo_current out of range");
+  // kernel runs record the reconstructed forward wavefield (write_seismograms_cuda.cu:100-118)
+  const bool b3 = mp->simulation_type == 3 && mp->d_b_displ != nullptr;
   struct { int on; const realw* vec; const realw* pot; realw* out; int corr_mode; } sets[3] = {
-      {mp->save_seismograms_d, mp->d_displ, mp->d_potential, mp->d_seismograms_d, 0},
-      {mp->save_seismograms_v, mp->d_veloc, mp->d_potential_dot, mp->d_seismograms_v, pend * 1},
-      {mp->save_seismograms_a, mp->d_accel, mp->d_potential_dot_dot, mp->d_seismograms_a, pend * 2}};
+      {mp->save_seismograms_d, b3 ? mp->d_b_displ : mp->d_displ, mp->d_potential, mp->d_seismograms_d, 0},
+      {mp->save_seismograms_v, b3 ? mp->d_b_veloc : mp->d_veloc, mp->d_potential_dot, mp->d_seismograms_v, pend * 1},
+      {mp->save_seismograms_a, b3 ? mp->d_b_accel : mp->d_accel, mp->d_potential_dot_dot, mp->d_seismograms_a, pend * 2}};
   for (auto& s : sets) {
     if (!s.on) continue;
     k_seismogram_vector<<<mp->nrec_local, NGLL3_PADDED, 0, mp->compute_stream>>>(
@@ -1178,8 +1288,9 @@ static realw max_norm(DeviceMesh* mp, const realw* f) {
 
 extern "C" void SB200_FC(get_norm_elastic_from_device)(realw* norm, long* Mesh_pointer, int* type) {
   DeviceMesh* mp = get_mesh_keep_pending(Mesh_pointer);  // the displacement does not depend on a pending corrector
-  if (*type != 1) exit_on_error("get_norm_elastic_from_device: only the forward wavefield (type 1) is supported");
-  *norm = sqrtf(max_norm<true>(mp, mp->d_displ));
+  if (*type != 1 && *type != 3) exit_on_error("get_norm_elastic_from_device: type must be 1 (displ) or 3 (b_displ)");
+  if (*type == 3) require_backward_fields(mp, "get_norm_elastic_from_device");
+  *norm = sqrtf(max_norm<true>(mp, *type == 1 ? mp->d_displ : mp->d_b_displ));
 }
 
 extern "C" void SB200_FC(get_norm_acoustic_from_device)(realw* norm, long* Mesh_pointer, int* sim_type) {
@@ -1187,6 +1298,8 @@ extern "C" void SB200_FC(get_norm_acoustic_from_device)(realw* norm, long* Mesh_
   if (*sim_type != 1) exit_on_error("get_norm_acoustic_from_device: only the forward wavefield (type 1) is supported");
   *norm = max_norm<false>(mp, mp->d_potential_dot_dot);
 }
+
+#include "adjoint.inc"
 
 // =================================================================================================================
 // extensions

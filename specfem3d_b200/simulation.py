@@ -38,6 +38,9 @@ class Simulation:
     att: Optional[list] = None  # per-partition attenuation arrays (see attenuation.py)
     pml: Optional[list] = None  # per-partition C-PML arrays (see pml.py)
     initial_fields: Optional[list] = None  # per-partition dict(displ=, veloc=, accel=, pot=...) or None = zero
+    SIMULATION_TYPE: int = 1     # 1 forward, 3 kernel run (adjoint + reconstructed forward wavefield), kernel_run.py
+    SAVE_FORWARD: bool = False   # forward run keeps the absorbed Stacey tractions of every step and the last frame
+    APPROXIMATE_HESS_KL: bool = False
 
     @property
     def deltat(self) -> np.float32:

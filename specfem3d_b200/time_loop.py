@@ -64,6 +64,10 @@ class DeviceRank:
         self.buffer_recv_vector = np.zeros((max(ni, 1), mx, 3), np.float32)
         self.buffer_send_scalar = np.zeros((max(ni, 1), mx), np.float32)
         self.buffer_recv_scalar = np.zeros((max(ni, 1), mx), np.float32)
+        self.b_buffer_send_vector = np.zeros((max(ni, 1), mx, 3), np.float32)
+        self.b_buffer_recv_vector = np.zeros((max(ni, 1), mx, 3), np.float32)
+        self.absorb_history: List[np.ndarray] = []  # SAVE_FORWARD: what proc*_absorb_field.bin would hold
+        self.b_absorb_field = np.zeros((1, 25, 3), np.float32)
 
     # --------------------------------------------------------------------------------------------------------------
     def prepare(self):
@@ -105,8 +109,9 @@ class DeviceRank:
             db.ibool_interfaces_ext_mesh, H["hprime_xx"], H["hprimewgll_xx"], H["wgllwgll_xy"], H["wgllwgll_xz"],
             H["wgllwgll_yz"], int(sim.spec.stacey), db.abs_boundary_ispec, db.abs_boundary_ijk, db.abs_boundary_normal,
             db.abs_boundary_jacobian2Dw, db.num_abs_boundary_faces, db.ispec_is_inner, NSOURCES, nsources_local,
-            H["sourcearrays"], H["islice_src"], H["ispec_src"], H["ispec_rec"], nrec, self.nrec_local, 1,
-            int(sim.spec.mesh_coloring), db.nspec_acoustic, db.nspec_elastic, db.ispec_is_acoustic, db.ispec_is_elastic, self.rank, 0, H["hxir"],
+            H["sourcearrays"], H["islice_src"], H["ispec_src"], H["ispec_rec"], nrec, self.nrec_local, int(sim.SIMULATION_TYPE),
+            int(sim.spec.mesh_coloring), db.nspec_acoustic, db.nspec_elastic, db.ispec_is_acoustic, db.ispec_is_elastic, self.rank,
+            int(sim.SAVE_FORWARD), H["hxir"],
             H["hetar"], H["hgammar"], H["nu_rec"], H["nu_source"], H["islice_rec"], sim.nlength_seismogram,
             int(sim.SAVE_SEISMOGRAMS_DISPLACEMENT), int(sim.SAVE_SEISMOGRAMS_VELOCITY),
             int(sim.SAVE_SEISMOGRAMS_ACCELERATION), int(sim.SAVE_SEISMOGRAMS_PRESSURE), 1, 0, 0,
@@ -143,10 +148,16 @@ class DeviceRank:
                 fc = fck = dummy
                 al = be = ga = np.zeros(N_SLS, np.float32)
                 R_size = 1
-            strain = 1 if att is not None else 0
+            # COMPUTE_AND_STORE_STRAIN = ATTENUATION .or. SIMULATION_TYPE == 3 (read_mesh_databases.F90)
+            strain = 1 if (att is not None or sim.SIMULATION_TYPE == 3) else 0
+            if strain and att is None:
+                eps = [np.zeros((nspec, 5, 5, 5), np.float32) for _ in range(6)]
+            # b_absorb_field(NDIM,NGLLSQUARE,num_abs_boundary_faces): one record of proc*_absorb_field.bin
+            self.b_reclen_field = 4 * 3 * 25 * db.num_abs_boundary_faces
+            self.b_absorb_field = np.zeros((max(db.num_abs_boundary_faces, 1), 25, 3), np.float32)
             L.prepare_fields_elastic_device(
                 self.Mesh_pointer, db.rmassx, db.rmassy, db.rmassz, db.rho_vp, db.rho_vs, kappa, mu,
-                db.num_phase_ispec_elastic, db.phase_ispec_inner_elastic, dummy, 0, strain, eps[0], eps[1], eps[2],
+                db.num_phase_ispec_elastic, db.phase_ispec_inner_elastic, self.b_absorb_field, self.b_reclen_field, strain, eps[0], eps[1], eps[2],
                 eps[3], eps[4], int(att is not None), R_size, R[0], R[1], R[2], R[3], R[4], fc, R[5], eps[5], fck, al,
                 be, ga, 0, dummy, 0, dummy, db.free_surface_ispec, db.free_surface_ijk, db.num_free_surface_faces,
                 int(sim.ACOUSTIC_SIMULATION), *col["elastic"], 0, *([dummy] * 21))
@@ -154,6 +165,14 @@ class DeviceRank:
                 from .pml import prepare_fields_elastic_pml
 
                 prepare_fields_elastic_pml(self)
+            if sim.SIMULATION_TYPE == 3:  # prepare_gpu.f90:232-262
+                z = np.zeros((nspec, 5, 5, 5), np.float32)
+                L.prepare_fields_elastic_adj_dev(
+                    self.Mesh_pointer, 3 * db.NGLOB_AB, z, z, z, z, z, z, z, R_size, *([dummy] * 7),
+                    np.zeros(N_SLS, np.float32), np.zeros(N_SLS, np.float32), np.zeros(N_SLS, np.float32), 0,
+                    int(sim.APPROXIMATE_HESS_KL))
+                L.prepare_sim2_or_3_const_device(self.Mesh_pointer, self.nrec_local, sim.NSTEP, H["hxir"], H["hetar"],
+                                                 H["hgammar"], nrec, H["islice_rec"], H["ispec_rec"])
         # initial wavefields (prepare_gpu.f90:296-306)
         n = db.NGLOB_AB
         init = sim.initial_fields[self.rank] if sim.initial_fields is not None else {}
@@ -205,6 +224,8 @@ class InProcessExchange:
                 cnt = int(db.nibool_interfaces_ext_mesh[n])
                 if kind == "vector":
                     nb.buffer_recv_vector[m, :cnt] = r.buffer_send_vector[n, :cnt]
+                elif kind == "b_vector":
+                    nb.b_buffer_recv_vector[m, :cnt] = r.b_buffer_send_vector[n, :cnt]
                 else:
                     nb.buffer_recv_scalar[m, :cnt] = r.buffer_send_scalar[n, :cnt]
 
@@ -296,7 +317,9 @@ class DeviceRun:
                 L.compute_forces_viscoelastic_cuda(M, iphase, dt, db.nspec_outer_elastic, db.nspec_inner_elastic, att, att, 1)
                 if iphase == 1:
                     if sim.spec.stacey:
-                        L.compute_stacey_viscoelastic_cuda(M, iphase, np.zeros(1, np.float32), 1)
+                        L.compute_stacey_viscoelastic_cuda(M, iphase, r.b_absorb_field, 1)
+                        if sim.SAVE_FORWARD:  # write_abs(IOABS, b_absorb_field, b_reclen_field, it)
+                            r.absorb_history.append(r.b_absorb_field.copy())
                     if sim.ACOUSTIC_SIMULATION and db.num_coupling_ac_el_faces > 0:
                         L.compute_coupling_el_ac_cuda(M, iphase, db.num_coupling_ac_el_faces, 1)
                     if sim.sources is not None:

@@ -29,11 +29,42 @@ def factories():
         "cpml_irregular": lambda: T.pml_sim(nstep=300),
         "cpml_regular": lambda: T.pml_sim(nstep=300, regular=True),
         "cfg3_small": lambda: T.cfg3_small(nstep=300),
+        "kernel_run": lambda: kernel_run_case(),
     }
+
+
+class kernel_run_case:
+    """Forward run with SAVE_FORWARD, then the SIMULATION_TYPE = 3 run (tests/test_oracle_kernel_run.py: kernel_sim)."""
+    NSTEP = 120
+    SAVE_SEISMOGRAMS_PRESSURE = False
+
+
+def run_kernel_case(lib):
+    import test_oracle_kernel_run as K
+    from specfem3d_b200.kernel_run import KernelRun, run_forward_and_save
+
+    n = kernel_run_case.NSTEP
+    fwd, prod = run_forward_and_save(K.kernel_sim((1, 1), n), lib=lib)
+    seis = fwd.gather_seismograms("d")
+    # the adjoint source must be the same bytes for both libraries: an analytic wavelet per receiver and component
+    t = np.arange(n, dtype=np.float64) * 0.012
+    nrec = seis.shape[0]
+    adj = np.zeros((nrec, n, 3), np.float32)
+    for irec in range(nrec):
+        for c in range(3):
+            adj[irec, :, c] = 1e15 * np.sin(2 * np.pi * (1.5 + 0.4 * c) * t + 0.7 * irec) * np.exp(-((t - 0.7) / 0.3) ** 2)
+    k = KernelRun(K.kernel_sim((1, 1), n, sim_type=3), prod, adj, lib=lib).run()
+    rho, mu, kappa = k.kernels()[0]
+    out = {"d_forward": seis, "b_d": k.gather_seismograms("d"), "displ": k.ranks[0].fields_el()[0],
+           "rho_kl": rho.copy(), "mu_kl": mu.copy(), "kappa_kl": kappa.copy()}
+    return k, out
 
 
 def run(sim, lib):
     from specfem3d_b200.time_loop import DeviceRun
+
+    if isinstance(sim, kernel_run_case):
+        return run_kernel_case(lib)
 
     run = DeviceRun(sim, lib=lib).run()
     out = {"d": run.gather_seismograms("d")}

@@ -1,0 +1,131 @@
+"""GPU parity of kernel runs (SIMULATION_TYPE == 3) through the C ABI: reconstructed forward
+wavefield, adjoint sources, Stacey replay, b_accel halo and the sensitivity kernels rho_kl / mu_kl / kappa_kl against the
+CPU oracle (oracle/adjoint.py), plus the properties that need no oracle (the reconstruction retraces the forward run; a
+partitioned run equals the single-rank run).
+
+Tolerances: the reconstructed seismograms are compared with the forward ones to 5e-4 relative L2 (float32 round-off of
+NSTEP steps forward and NSTEP back); whole-run kernels to KERNEL_RTOL = 5e-3 (see tests/test_oracle_kernel_run.py: the
+summation order alone moves them by a few 1e-4); the two-step test that isolates the kernel arithmetic to 2e-5.
+"""
+import numpy as np
+import pytest
+
+from test_oracle_kernel_run import KERNEL_RTOL, adjoint_source, kernel_sim, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def device_kernel_run(device_lib, nproc, nstep, adj=None, hess=False):
+    from specfem3d_b200.kernel_run import KernelRun, run_forward_and_save
+
+    fwd, prod = run_forward_and_save(kernel_sim(nproc, nstep), lib=device_lib)
+    seis_fwd = fwd.gather_seismograms("d")
+    fwd.cleanup()
+    if adj is None:
+        adj = adjoint_source(seis_fwd)
+    sim3 = kernel_sim(nproc, nstep, sim_type=3)
+    sim3.APPROXIMATE_HESS_KL = hess
+    k = KernelRun(sim3, prod, adj, lib=device_lib).run()
+    return seis_fwd, prod, k
+
+
+@pytest.mark.parametrize("nproc", [(1, 1), (2, 2)])
+def test_kernel_run_matches_oracle(device_lib, nproc):
+    from oracle.adjoint import OracleForwardRun, OracleKernelRun
+
+    nstep = 120
+    ofwd = OracleForwardRun(kernel_sim(nproc, nstep)).run()
+    adj = adjoint_source(ofwd.seis_d)
+    ok = OracleKernelRun(kernel_sim(nproc, nstep, sim_type=3), ofwd.record, adj).run()
+    seis_fwd, prod, k = device_kernel_run(device_lib, nproc, nstep, adj)
+    # SAVE_FORWARD products: absorbed tractions of every step and the last frame
+    for r in range(len(prod.absorb)):
+        a, b = np.stack(prod.absorb[r]), np.stack(ofwd.record.absorb[r])
+        assert a.shape == b.shape and rel_l2(a, b) <= 1e-4
+        assert rel_l2(prod.last[r]["displ"], ofwd.record.last[r]["displ"]) <= 1e-4
+    # reconstructed wavefield: sample j of the kernel run = forward displacement after step NSTEP - j
+    sk = k.gather_seismograms("d")
+    assert np.abs(seis_fwd).max() > 0
+    assert rel_l2(sk[:, 1:], seis_fwd[:, ::-1][:, 1:]) <= 5e-4
+    assert rel_l2(sk[:, 1:], ok.seis_d[:, 1:]) <= 5e-4
+    # adjoint wavefield at the end of the run and the kernels
+    for r, (rho, mu, kappa) in enumerate(k.kernels()):
+        n = rho.shape[0]
+        assert rel_l2(k.ranks[r].fields_el()[0], ok.parts[r].displ) <= 1e-4
+        for mine, ref in ((rho, ok.rho_kl[r]), (mu, ok.mu_kl[r]), (kappa, ok.kappa_kl[r])):
+            assert np.abs(ref).max() > 0
+            assert rel_l2(mine.reshape(n, 125), ref) <= KERNEL_RTOL
+    k.cleanup()
+
+
+def test_kernel_arithmetic_two_steps(device_lib):
+    """Two steps from smooth, O(1) wavefields and no sources: the strains both force launches store and the three kernel
+    integrands are compared point by point before any round-off can pile up."""
+    from oracle.adjoint import ForwardRecord, OracleKernelRun
+    from specfem3d_b200.kernel_run import ForwardProducts, KernelRun
+    from test_gpu_parity import smooth_fields
+
+    def sim3():
+        s = kernel_sim((1, 1), 2, sim_type=3)
+        s.sources = None
+        s.initial_fields = smooth_fields(s, amp=1.0)
+        return s
+
+    s = sim3()
+    nfaces = s.dbs[0].num_abs_boundary_faces
+    rng = np.random.default_rng(5)
+    absorb = [(1e9 * rng.standard_normal((nfaces, 25, 3))).astype(np.float32) for _ in range(2)]
+    last = {k: (0.7 * v[:, ::-1]).copy() for k, v in smooth_fields(s, amp=1.0)[0].items()}
+    adj = (1e15 * rng.standard_normal((s.receivers.nrec, 2, 3))).astype(np.float32)
+    rec = ForwardRecord(1)
+    rec.absorb[0], rec.last[0] = absorb, last
+    o = OracleKernelRun(sim3(), rec, adj)
+    for p, f in zip(o.parts, s.initial_fields):
+        for key, v in f.items():
+            getattr(p, key)[...] = v
+    o.run()
+    k = KernelRun(sim3(), ForwardProducts([absorb], [last]), adj, lib=device_lib).run()
+    rho, mu, kappa = k.kernels()[0]
+    n = rho.shape[0]
+    for mine, ref in ((rho, o.rho_kl[0]), (mu, o.mu_kl[0]), (kappa, o.kappa_kl[0])):
+        assert np.abs(ref).max() > 0
+        assert np.abs(mine.reshape(n, 125) - ref).max() <= 2e-5 * np.abs(ref).max()
+    bd, bv, ba = k.b_fields(0)
+    assert rel_l2(bd, o.bparts[0].displ) <= 1e-5 and rel_l2(ba, o.bparts[0].accel) <= 2e-5
+    assert rel_l2(k.ranks[0].fields_el()[2], o.parts[0].accel) <= 2e-5
+    k.cleanup()
+
+
+def test_partitioned_kernel_run_equals_single_rank(device_lib):
+    """b_accel halo (transfer_boun_accel_from_device / transfer_asmbl_accel_to_device with FORWARD_OR_ADJOINT = 3)."""
+    seis1, _, k1 = device_kernel_run(device_lib, (1, 1), 100)
+    adj = adjoint_source(seis1)
+    _, _, k4 = device_kernel_run(device_lib, (2, 2), 100, adj)
+    assert rel_l2(k4.gather_seismograms("d"), k1.gather_seismograms("d")) <= 5e-4
+
+    def keyed(run):
+        out = {}
+        for r, (rho, mu, kappa) in zip(run.ranks, run.kernels()):
+            db = r.db
+            ib = db.ibool.reshape(db.NSPEC_AB, 125) - 1
+            for e in range(db.NSPEC_AB):
+                key = tuple(round(float(c[ib[e, 0]]), 1) for c in (db.xstore, db.ystore, db.zstore))
+                out[key] = np.stack([rho[e].ravel(), mu[e].ravel(), kappa[e].ravel()])
+        return out
+
+    a, b = keyed(k1), keyed(k4)
+    assert a.keys() == b.keys()
+    keys = sorted(a)
+    for c in range(3):
+        assert rel_l2(np.stack([b[q][c] for q in keys]), np.stack([a[q][c] for q in keys])) <= KERNEL_RTOL
+    k1.cleanup(); k4.cleanup()
+
+
+def test_approximate_hessian_kernels(device_lib):
+    """compute_kernels_hess_cuda: hess_rho_kl = dt * sum |b_veloc|^2 etc. are non-negative; hess_kl pairs accel with b_accel."""
+    _, _, k = device_kernel_run(device_lib, (1, 1), 60, hess=True)
+    hess, hess_rho, hess_kappa, hess_mu = k.hess_kernels()[0]
+    for a in (hess_rho, hess_kappa, hess_mu):
+        assert a.min() >= 0 and a.max() > 0
+    assert np.isfinite(hess).all() and np.abs(hess).max() > 0
+    k.cleanup()

@@ -28,7 +28,7 @@ def rel_l2(a, b):
 
 
 @pytest.mark.parametrize("name", ["elastic_irregular", "elastic_regular", "viscoelastic", "ocean_source_in_solid",
-                                  "ocean_source_in_water", "cpml_irregular", "cpml_regular", "cfg3_small"])
+                                  "ocean_source_in_water", "cpml_irregular", "cpml_regular", "cfg3_small", "kernel_run"])
 def test_against_reference_cuda_backend(device_lib, name, tmp_path):
     if not os.path.exists(REF_LIB):
         pytest.skip("oracle/_ref/libspecfem_ref_cuda.so not built (run oracle/build_ref_cuda.sh where /root/reference exists)")
@@ -50,7 +50,11 @@ def test_against_reference_cuda_backend(device_lib, name, tmp_path):
     for key in ref.files:
         a, b = mine[key], ref[key]
         assert np.abs(b).max() > 0, key
-        if key in ("d", "p"):  # seismograms: every trace within the BASELINE tolerance
+        if key in ("b_d", "rho_kl", "mu_kl", "kappa_kl"):
+            # kernel run: reconstructed seismograms and kernels carry the round-off of NSTEP steps forward and NSTEP back
+            # (tests/test_oracle_kernel_run.py: KERNEL_RTOL)
+            assert rel_l2(a, b) <= (5e-4 if key == "b_d" else 5e-3), key
+        elif key in ("d", "p", "d_forward"):  # seismograms: every trace within the BASELINE tolerance
             for irec in range(b.shape[0]):
                 for c in range(b.shape[2]):
                     if np.abs(b[irec, :, c]).max() > 0:

@@ -1,0 +1,86 @@
+"""CPU checks of the kernel-run (SIMULATION_TYPE == 3) oracle, oracle/adjoint.py: the reconstructed forward wavefield must
+retrace the forward run (a property of the Newmark scheme with the absorbed Stacey tractions replayed), partitioned and
+single-rank kernel runs must agree, and the kernels must be bilinear in (adjoint source, forward source)."""
+import numpy as np
+import pytest
+
+from specfem3d_b200.configs import HALFSPACE
+from specfem3d_b200.meshfem import BoxSpec
+from specfem3d_b200.simulation import make_simulation
+from specfem3d_b200.sources_receivers import CMTSource, Station
+
+
+def kernel_sim(nproc=(1, 1), nstep=120, nex=(6, 6, 4), sim_type=1, scale=1.0):
+    spec = BoxSpec(nex[0], nex[1], nex[2], xmax=1100.0 * nex[0], ymax=900.0 * nex[1], zmin=-1000.0 * nex[2],
+                   nproc_xi=nproc[0], nproc_eta=nproc[1], materials=(HALFSPACE,), deform=0.12, stacey=True)
+    m = tuple(scale * v for v in (1e23, -2e23, 0.5e23, 0.3e23, -0.7e23, 0.2e23))
+    src = [CMTSource(0.52 * spec.xmax, 0.47 * spec.ymax, 0.55 * spec.zmin, m, hdur=0.25)]
+    sts = [Station("A", "XX", 0.21 * spec.xmax, 0.33 * spec.ymax, 0.0), Station("B", "XX", 0.77 * spec.xmax, 0.62 * spec.ymax, 0.0),
+           Station("C", "XX", 0.40 * spec.xmax, 0.81 * spec.ymax, 0.4 * spec.zmin)]
+    sim = make_simulation(spec, DT=0.012, NSTEP=nstep, sources=src, stations=sts)
+    sim.SIMULATION_TYPE = sim_type
+    sim.SAVE_FORWARD = sim_type == 1
+    return sim
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def adjoint_source(seis_d, scale=1.0):
+    """Waveform adjoint source: the recorded displacement itself, scaled to forces that move the mesh by O(1) so that no
+    product in the kernels comes near the float32 underflow range."""
+    return (scale * 1e15 / np.abs(seis_d).max()) * seis_d
+
+
+def oracle_kernels(nproc, nstep=120, adj_scale=1.0, src_scale=1.0):
+    from oracle.adjoint import OracleForwardRun, OracleKernelRun
+
+    fwd = OracleForwardRun(kernel_sim(nproc, nstep, scale=src_scale)).run()
+    adj = adjoint_source(fwd.seis_d, adj_scale)
+    k = OracleKernelRun(kernel_sim(nproc, nstep, sim_type=3, scale=src_scale), fwd.record, adj).run()
+    return fwd, k
+
+
+def test_reconstructed_wavefield_retraces_forward_run():
+    fwd, k = oracle_kernels((1, 1))
+    assert np.abs(fwd.seis_d).max() > 0
+    # sample j of the kernel run holds b_displ after step j+1 = forward displacement after step NSTEP-j
+    assert rel_l2(k.seis_d[:, 1:], fwd.seis_d[:, ::-1][:, 1:]) < 2e-4
+    # back at the start the reconstructed wavefield is (almost) at rest again
+    assert np.abs(k.bparts[0].displ).max() < 1e-3 * np.abs(fwd.seis_d).max()
+    for a in (k.rho_kl[0], k.mu_kl[0], k.kappa_kl[0]):
+        assert np.isfinite(a).all() and np.abs(a).max() > 0
+
+
+def test_partitioned_kernel_run_equals_single_rank():
+    _, k1 = oracle_kernels((1, 1), nstep=80)
+    _, k4 = oracle_kernels((2, 2), nstep=80)
+    s1, s4 = kernel_sim((1, 1)), kernel_sim((2, 2))
+    # compare element by element through the structured position of each element's first corner
+    def keyed(sim, arrs):
+        out = {}
+        for db, a in zip(sim.dbs, arrs):
+            ib = db.ibool.reshape(db.NSPEC_AB, 125) - 1
+            for e in range(db.NSPEC_AB):
+                key = (round(float(db.xstore[ib[e, 0]]), 1), round(float(db.ystore[ib[e, 0]]), 1), round(float(db.zstore[ib[e, 0]]), 1))
+                out[key] = a[e]
+        return out
+    for name in ("rho_kl", "mu_kl", "kappa_kl"):
+        a, b = keyed(s1, getattr(k1, name)), keyed(s4, getattr(k4, name))
+        assert a.keys() == b.keys()
+        keys = sorted(a)
+        assert rel_l2(np.stack([b[q] for q in keys]), np.stack([a[q] for q in keys])) < 5e-3
+
+
+# Tolerance of whole-run kernel comparisons: the reconstructed wavefield carries the float32 round-off of NSTEP forward and
+# NSTEP backward steps (the OpenMP / atomic summation order alone moves the kernels by a few 1e-4 from run to run).
+KERNEL_RTOL = 5e-3
+
+
+def test_kernels_are_bilinear():
+    _, k1 = oracle_kernels((1, 1), nstep=100)
+    _, k2 = oracle_kernels((1, 1), nstep=100, adj_scale=2.0)
+    for name in ("rho_kl", "mu_kl", "kappa_kl"):
+        assert rel_l2(getattr(k2, name)[0], 2.0 * getattr(k1, name)[0]) < KERNEL_RTOL
