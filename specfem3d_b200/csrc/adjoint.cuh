@@ -86,4 +86,197 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_kernels_elastic(const KernelAr
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Kernel runs, FORWARD_OR_ADJOINT == 0: internal forces of the adjoint AND the reconstructed forward wavefield in one
+// launch.  The element's parameters (ibool, nine inverse-metric planes, kappa, mu: 6 of the 8.3 KB a force launch moves
+// per element) are read once for both wavefields, and because both strains are then in registers at the same GLL
+// point the mu / kappa kernels (and the approximate-Hessian strain terms) are accumulated on the spot: the twelve
+// epsilondev / epsilon_trace_over_3 arrays of the reference (Kernel_2_noatt_iso_impl :880-905 stores them,
+// compute_kernels_cudakernel reads them back) never exist in HBM.  ~12.6 KB per element and step instead of ~33 KB.
+// compute_kernels_elastic_cuda then only adds the rho kernel.  Arithmetic per wavefield = k_elastic_forces_pt<false,true>.
+// ---------------------------------------------------------------------------------------------------------------
+struct KlPairArgs {
+  int nb_elements;
+  const int* phase_ispec;
+  int first_ispec;
+  const int* ibool;
+  const int* irregular_element_number;
+  const realw* metric;
+  realw xix_regular, jacobian_regular;
+  const realw *kappav, *muv;
+  const realw* displ[2];  // 0 = adjoint wavefield (displ), 1 = reconstructed forward wavefield (b_displ)
+  realw* accel[2];
+  realw *mu_kl, *kappa_kl, *hess_mu_kl, *hess_kappa_kl;  // hess_* may be nullptr
+  realw deltat;
+  int use_atomics;
+  size_t nglob;
+};
+
+__global__ void __launch_bounds__(NGLL3_PADDED) k_elastic_forces_kl_pair(const KlPairArgs a) {
+  const size_t cs = vstride(a.nglob);
+  const int bx = blockIdx.x;
+  if (bx >= a.nb_elements) return;
+  const int tx = threadIdx.x;
+  const bool active = tx < NGLL3;
+  const int t = active ? tx : NGLL3 - 1;
+  const int K = t / NGLL2, J = (t - K * NGLL2) / NGLLX, I = t - K * NGLL2 - J * NGLLX;
+
+  __shared__ realw s_x[NGLL3_PADDED], s_y[NGLL3_PADDED], s_z[NGLL3_PADDED];
+  __shared__ realw s_hp[NGLL2], s_hw[NGLL2];
+
+  const int ispec = a.phase_ispec ? a.phase_ispec[bx] - 1 : a.first_ispec + bx;
+  const int irr = a.irregular_element_number[ispec] - 1;
+  const size_t off = (size_t)ispec * NGLL3_PADDED + t;
+  const int iglob = a.ibool[off] - 1;
+  const size_t vb = vbase(iglob);
+  if (tx < NGLL2) {
+    s_hp[tx] = c_hprime_xx[tx];
+    s_hw[tx] = c_hprimewgll_xx[tx];
+  }
+  const realw kappal = a.kappav[off], mul = a.muv[off];
+  Metric m;
+  realw jacobianl = a.jacobian_regular;
+  if (irr >= 0) {
+    const realw* mp = a.metric + (size_t)irr * 9 * NGLL3_PADDED + t;
+    m.xix = mp[0]; m.xiy = mp[NGLL3_PADDED]; m.xiz = mp[2 * NGLL3_PADDED];
+    m.etax = mp[3 * NGLL3_PADDED]; m.etay = mp[4 * NGLL3_PADDED]; m.etaz = mp[5 * NGLL3_PADDED];
+    m.gammax = mp[6 * NGLL3_PADDED]; m.gammay = mp[7 * NGLL3_PADDED]; m.gammaz = mp[8 * NGLL3_PADDED];
+    jacobianl = jacobian_of(m);
+  }
+  const realw fac1 = c_wgllwgll_yz[K * NGLLX + J], fac2 = c_wgllwgll_xz[K * NGLLX + I], fac3 = c_wgllwgll_xy[J * NGLLX + I];
+  const realw lambdalplus2mul = kappal + 1.33333333333333333333f * mul;
+  const realw lambdal = lambdalplus2mul - 2.0f * mul;
+
+  realw e_xx[2], e_yy[2], e_xy[2], e_xz[2], e_yz[2], e_tr3[2];
+#pragma unroll
+  for (int w = 0; w < 2; ++w) {
+    const realw* d = a.displ[w] + vb;
+    const realw ux = d[0], uy = d[cs], uz = d[2 * cs];
+    __syncthreads();  // the previous wavefield's last contraction has read the tiles
+    s_x[t] = ux; s_y[t] = uy; s_z[t] = uz;
+    __syncthreads();
+    realw t1x = 0.f, t2x = 0.f, t3x = 0.f, t1y = 0.f, t2y = 0.f, t3y = 0.f, t1z = 0.f, t2z = 0.f, t3z = 0.f;
+#pragma unroll
+    for (int l = 0; l < NGLLX; ++l) {
+      const realw h1 = s_hp[l * NGLLX + I], h2 = s_hp[l * NGLLX + J], h3 = s_hp[l * NGLLX + K];
+      const int o1 = K * NGLL2 + J * NGLLX + l, o2 = K * NGLL2 + l * NGLLX + I, o3 = l * NGLL2 + J * NGLLX + I;
+      t1x += s_x[o1] * h1; t1y += s_y[o1] * h1; t1z += s_z[o1] * h1;
+      t2x += s_x[o2] * h2; t2y += s_y[o2] * h2; t2z += s_z[o2] * h2;
+      t3x += s_x[o3] * h3; t3y += s_y[o3] * h3; t3z += s_z[o3] * h3;
+    }
+    realw duxdxl, duxdyl, duxdzl, duydxl, duydyl, duydzl, duzdxl, duzdyl, duzdzl;
+    if (irr >= 0) {
+      duxdxl = m.xix * t1x + m.etax * t2x + m.gammax * t3x;
+      duxdyl = m.xiy * t1x + m.etay * t2x + m.gammay * t3x;
+      duxdzl = m.xiz * t1x + m.etaz * t2x + m.gammaz * t3x;
+      duydxl = m.xix * t1y + m.etax * t2y + m.gammax * t3y;
+      duydyl = m.xiy * t1y + m.etay * t2y + m.gammay * t3y;
+      duydzl = m.xiz * t1y + m.etaz * t2y + m.gammaz * t3y;
+      duzdxl = m.xix * t1z + m.etax * t2z + m.gammax * t3z;
+      duzdyl = m.xiy * t1z + m.etay * t2z + m.gammay * t3z;
+      duzdzl = m.xiz * t1z + m.etaz * t2z + m.gammaz * t3z;
+    } else {
+      duxdxl = a.xix_regular * t1x; duxdyl = a.xix_regular * t2x; duxdzl = a.xix_regular * t3x;
+      duydxl = a.xix_regular * t1y; duydyl = a.xix_regular * t2y; duydzl = a.xix_regular * t3y;
+      duzdxl = a.xix_regular * t1z; duzdyl = a.xix_regular * t2z; duzdzl = a.xix_regular * t3z;
+    }
+    {
+      const realw templ = 0.33333333333333333333f * (duxdxl + duydyl + duzdzl);
+      e_tr3[w] = templ;
+      e_xx[w] = duxdxl - templ; e_yy[w] = duydyl - templ;
+      e_xy[w] = 0.5f * (duxdyl + duydxl); e_xz[w] = 0.5f * (duzdxl + duxdzl); e_yz[w] = 0.5f * (duzdyl + duydzl);
+    }
+    const realw sigma_xx = lambdalplus2mul * duxdxl + lambdal * (duydyl + duzdzl);
+    const realw sigma_yy = lambdalplus2mul * duydyl + lambdal * (duxdxl + duzdzl);
+    const realw sigma_zz = lambdalplus2mul * duzdzl + lambdal * (duxdxl + duydyl);
+    const realw sigma_xy = mul * (duxdyl + duydxl);
+    const realw sigma_xz = mul * (duzdxl + duxdzl);
+    const realw sigma_yz = mul * (duzdyl + duydzl);
+    realw f1x, f1y, f1z, f2x, f2y, f2z, f3x, f3y, f3z;
+    if (irr >= 0) {
+      f1x = jacobianl * (sigma_xx * m.xix + sigma_xy * m.xiy + sigma_xz * m.xiz);
+      f1y = jacobianl * (sigma_xy * m.xix + sigma_yy * m.xiy + sigma_yz * m.xiz);
+      f1z = jacobianl * (sigma_xz * m.xix + sigma_yz * m.xiy + sigma_zz * m.xiz);
+      f2x = jacobianl * (sigma_xx * m.etax + sigma_xy * m.etay + sigma_xz * m.etaz);
+      f2y = jacobianl * (sigma_xy * m.etax + sigma_yy * m.etay + sigma_yz * m.etaz);
+      f2z = jacobianl * (sigma_xz * m.etax + sigma_yz * m.etay + sigma_zz * m.etaz);
+      f3x = jacobianl * (sigma_xx * m.gammax + sigma_xy * m.gammay + sigma_xz * m.gammaz);
+      f3y = jacobianl * (sigma_xy * m.gammax + sigma_yy * m.gammay + sigma_yz * m.gammaz);
+      f3z = jacobianl * (sigma_xz * m.gammax + sigma_yz * m.gammay + sigma_zz * m.gammaz);
+    } else {
+      const realw f = jacobianl * a.xix_regular;
+      f1x = f * sigma_xx; f1y = f * sigma_xy; f1z = f * sigma_xz;
+      f2x = f * sigma_xy; f2y = f * sigma_yy; f2z = f * sigma_yz;
+      f3x = f * sigma_xz; f3y = f * sigma_yz; f3z = f * sigma_zz;
+    }
+    realw n1x = 0.f, n1y = 0.f, n1z = 0.f, n2x = 0.f, n2y = 0.f, n2z = 0.f, n3x = 0.f, n3y = 0.f, n3z = 0.f;
+    __syncthreads();
+    s_x[t] = f1x; s_y[t] = f1y; s_z[t] = f1z;
+    __syncthreads();
+#pragma unroll
+    for (int l = 0; l < NGLLX; ++l) {
+      const realw h = s_hw[I * NGLLX + l];
+      const int o = K * NGLL2 + J * NGLLX + l;
+      n1x += s_x[o] * h; n1y += s_y[o] * h; n1z += s_z[o] * h;
+    }
+    __syncthreads();
+    s_x[t] = f2x; s_y[t] = f2y; s_z[t] = f2z;
+    __syncthreads();
+#pragma unroll
+    for (int l = 0; l < NGLLX; ++l) {
+      const realw h = s_hw[J * NGLLX + l];
+      const int o = K * NGLL2 + l * NGLLX + I;
+      n2x += s_x[o] * h; n2y += s_y[o] * h; n2z += s_z[o] * h;
+    }
+    __syncthreads();
+    s_x[t] = f3x; s_y[t] = f3y; s_z[t] = f3z;
+    __syncthreads();
+#pragma unroll
+    for (int l = 0; l < NGLLX; ++l) {
+      const realw h = s_hw[K * NGLLX + l];
+      const int o = l * NGLL2 + J * NGLLX + I;
+      n3x += s_x[o] * h; n3y += s_y[o] * h; n3z += s_z[o] * h;
+    }
+    if (active) {
+      const realw sum1 = -(fac1 * n1x + fac2 * n2x + fac3 * n3x);
+      const realw sum2 = -(fac1 * n1y + fac2 * n2y + fac3 * n3y);
+      const realw sum3 = -(fac1 * n1z + fac2 * n2z + fac3 * n3z);
+      realw* acc = a.accel[w] + vb;
+      if (a.use_atomics) {
+        red_add(acc, sum1); red_add(acc + cs, sum2); red_add(acc + 2 * cs, sum3);
+      } else {
+        acc[0] += sum1; acc[cs] += sum2; acc[2 * cs] += sum3;
+      }
+    }
+  }
+  if (active) {
+    a.mu_kl[off] += a.deltat * (e_xx[0] * e_xx[1] + e_yy[0] * e_yy[1] + (e_xx[0] + e_yy[0]) * (e_xx[1] + e_yy[1]) +
+                                2 * (e_xy[0] * e_xy[1] + e_xz[0] * e_xz[1] + e_yz[0] * e_yz[1]));
+    a.kappa_kl[off] += a.deltat * (9 * e_tr3[0] * e_tr3[1]);
+    if (a.hess_mu_kl) {
+      a.hess_mu_kl[off] += a.deltat * (e_xx[1] * e_xx[1] + e_yy[1] * e_yy[1] + (e_xx[1] + e_yy[1]) * (e_xx[1] + e_yy[1]) +
+                                       2 * (e_xy[1] * e_xy[1] + e_xz[1] * e_xz[1] + e_yz[1] * e_yz[1]));
+      a.hess_kappa_kl[off] += a.deltat * (9 * e_tr3[1] * e_tr3[1]);
+    }
+  }
+}
+
+// what is left for compute_kernels_elastic_cuda / compute_kernels_hess_cuda after the pair launch: the terms that need
+// the wavefields after the mass-matrix multiplication
+template <bool HESS>
+__global__ void __launch_bounds__(NGLL3_PADDED) k_kernels_elastic_pointwise(const KernelArgs a) {
+  const int ispec = blockIdx.x, t = threadIdx.x;
+  if (ispec >= a.nspec || t >= NGLL3 || !a.ispec_is_elastic[ispec]) return;
+  const size_t off = (size_t)ispec * NGLL3_PADDED + t;
+  const size_t iglob = (size_t)a.ibool[off] - 1;
+  const size_t g0 = vidx(iglob, 0, a.nglob), g1 = vidx(iglob, 1, a.nglob), g2 = vidx(iglob, 2, a.nglob);
+  if (!HESS) {
+    a.rho_kl[off] += a.deltat * (a.accel[g0] * a.b_displ[g0] + a.accel[g1] * a.b_displ[g1] + a.accel[g2] * a.b_displ[g2]);
+  } else {
+    a.hess_kl[off] += a.deltat * (a.accel[g0] * a.b_accel[g0] + a.accel[g1] * a.b_accel[g1] + a.accel[g2] * a.b_accel[g2]);
+    const realw vx = a.b_veloc[g0], vy = a.b_veloc[g1], vz = a.b_veloc[g2];
+    a.hess_rho_kl[off] += a.deltat * (vx * vx + vy * vy + vz * vz);
+  }
+}
+
 }  // namespace sb200

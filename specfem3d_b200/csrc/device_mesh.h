@@ -161,6 +161,12 @@ struct DeviceMesh {
   int nadj_rec_local = 0, ntstep_between_read_adjsrc = 0;
   realw* d_source_adjoint = nullptr;  // Fortran (NDIM, nadj_rec_local, NTSTEP_BETWEEN_READ_ADJSRC)
   realw* d_b_send_accel_buffer = nullptr;
+  realw* h_absorb_registered = nullptr;  // caller's b_absorb_field record buffer, page-locked on first use (Stacey replay)
+  // FORWARD_OR_ADJOINT == 0 force launches use the two-wavefield kernel that accumulates mu_kl / kappa_kl itself
+  // (adjoint.cuh: k_elastic_forces_kl_pair); SPECFEM_B200_KL_FUSED=0 restores the stored-strain path of the reference
+  int kl_fused = 1;
+  int kl_pair_launches = 0, kl_single_launches = 0;  // since the last compute_kernels_elastic_cuda
+  bool kl_pair_done = false;                           // what the last compute_kernels_elastic_cuda found
 
   // peer-to-peer halo over NVLink (extension, see halo_p2p.cuh)
   struct P2P* p2p = nullptr;

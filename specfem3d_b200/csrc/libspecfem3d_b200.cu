@@ -174,6 +174,7 @@ extern "C" void SB200_FC(prepare_constants_device)(
   mp->NGLOB_AB = *NGLOB_AB;
   mp->NSPEC_IRREGULAR = *NSPEC_IRREGULAR;
   mp->simulation_type = *SIMULATION_TYPE;
+  if (const char* e = getenv("SPECFEM_B200_KL_FUSED")) mp->kl_fused = atoi(e);
   if (mp->simulation_type == 3) mp->fuse_newmark = 0;  // two wavefields per step: the corrector is applied where it is called
   mp->save_forward = *SAVE_FORWARD;
   mp->stacey_absorbing_conditions = *STACEY_ABSORBING_CONDITIONS;
@@ -487,6 +488,7 @@ extern "C" void SB200_FC(prepare_cleanup_device)(long* Mesh_pointer, int* ACOUST
                    mp->d_hess_rho_el_kl, mp->d_hess_kappa_el_kl, mp->d_hess_mu_el_kl, mp->d_source_adjoint,
                    mp->d_b_send_accel_buffer};
   for (void* p : dptrs) dev_free(p);
+  if (mp->h_absorb_registered) cudaHostUnregister(mp->h_absorb_registered);
   if (mp->h_send_accel_buffer) cudaFreeHost(mp->h_send_accel_buffer);
   if (mp->h_recv_accel_buffer) cudaFreeHost(mp->h_recv_accel_buffer);
   if (mp->h_stf_pinned) cudaFreeHost(mp->h_stf_pinned);
@@ -817,6 +819,43 @@ extern "C" void SB200_FC(compute_forces_viscoelastic_cuda)(long* Mesh_pointer, i
     // compute_kernels_elastic_cuda, so the one-thread-per-point kernel is used (the plane-owner kernel stores no strain).
     if (foa != 1) require_backward_fields(mp, "compute_forces_viscoelastic_cuda");
     if (mp->pml_conditions && mp->NSPEC_CPML > 0) exit_on_error("compute_forces_viscoelastic_cuda: C-PML in a kernel run is not implemented");
+    if (foa == 0 && mp->kl_fused && !mp->attenuation && num_elements > 0) {
+      // both wavefields in one launch, mu / kappa (and the Hessian strain terms) accumulated on the spot (adjoint.cuh)
+      KlPairArgs a;
+      a.ibool = mp->d_ibool; a.irregular_element_number = mp->d_irregular_element_number; a.metric = mp->d_metric;
+      a.xix_regular = mp->xix_regular; a.jacobian_regular = mp->jacobian_regular;
+      a.kappav = mp->d_kappav; a.muv = mp->d_muv;
+      a.displ[0] = mp->d_displ; a.displ[1] = mp->d_b_displ; a.accel[0] = mp->d_accel; a.accel[1] = mp->d_b_accel;
+      a.mu_kl = mp->d_mu_kl; a.kappa_kl = mp->d_kappa_kl;
+      a.hess_mu_kl = mp->approximate_hess_kl ? mp->d_hess_mu_el_kl : nullptr;
+      a.hess_kappa_kl = mp->approximate_hess_kl ? mp->d_hess_kappa_el_kl : nullptr;
+      a.deltat = *deltat;
+      a.nglob = (size_t)mp->NGLOB_AB;
+      if (mp->use_mesh_coloring_gpu) {
+        const int c0 = (*iphase == 1) ? 0 : mp->num_colors_outer_elastic;
+        const int c1 = (*iphase == 1) ? mp->num_colors_outer_elastic : mp->num_colors_outer_elastic + mp->num_colors_inner_elastic;
+        int offset = 0;
+        for (int ic = 0; ic < c0; ++ic) offset += mp->h_num_elem_colors_elastic[ic];
+        for (int ic = c0; ic < c1; ++ic) {
+          a.nb_elements = mp->h_num_elem_colors_elastic[ic];
+          a.phase_ispec = nullptr; a.first_ispec = offset; a.use_atomics = 0;
+          if (a.nb_elements > 0) {
+            k_elastic_forces_kl_pair<<<a.nb_elements, NGLL3_PADDED, 0, mp->compute_stream>>>(a);
+            KERNEL_CHECK(mp, "k_elastic_forces_kl_pair(colour)");
+          }
+          offset += a.nb_elements;
+        }
+      } else {
+        a.nb_elements = num_elements;
+        a.phase_ispec = mp->d_phase_ispec_inner_elastic + (size_t)mp->num_phase_ispec_elastic * (*iphase - 1);
+        a.first_ispec = 0; a.use_atomics = 1;
+        k_elastic_forces_kl_pair<<<a.nb_elements, NGLL3_PADDED, 0, mp->compute_stream>>>(a);
+        KERNEL_CHECK(mp, "k_elastic_forces_kl_pair");
+      }
+      mp->kl_pair_launches++;
+      return;
+    }
+    if (num_elements > 0) mp->kl_single_launches++;
     for (int pass = 0; pass < 2 && num_elements > 0; ++pass) {
       const bool backward = pass == 1;
       if (backward ? foa == 1 : foa == 3) continue;
@@ -949,8 +988,16 @@ extern "C" void SB200_FC(compute_stacey_viscoelastic_cuda)(long* Mesh_pointer, i
     // wavefield (compute_stacey_viscoelastic_cuda.cu:78-80,136-152; CPU compute_stacey_viscoelastic_backward)
     require_backward_fields(mp, "compute_stacey_viscoelastic_cuda");
     if (!mp->d_b_absorb_field) exit_on_error("compute_stacey_viscoelastic_cuda: b_absorb_field was not prepared");
+    // the caller hands over the same record buffer every step: page-lock it once so the copy is one DMA transfer instead
+    // of a staged pageable copy (14.7 MB per step on the 1M-element mesh); falls back to the pageable copy if refused
+    if (mp->h_absorb_registered != b_absorb_field) {
+      if (mp->h_absorb_registered) cudaHostUnregister(mp->h_absorb_registered);
+      mp->h_absorb_registered = nullptr;
+      if (cudaHostRegister(b_absorb_field, mp->b_reclen_field, cudaHostRegisterDefault) == cudaSuccess) mp->h_absorb_registered = b_absorb_field;
+      else (void)cudaGetLastError();
+    }
     CUDA_CHECK(cudaMemcpyAsync(mp->d_b_absorb_field, b_absorb_field, mp->b_reclen_field, cudaMemcpyHostToDevice, mp->compute_stream));
-    CUDA_CHECK(cudaStreamSynchronize(mp->compute_stream));  // pageable host buffer: the caller may reuse it on return
+    CUDA_CHECK(cudaStreamSynchronize(mp->compute_stream));  // the caller may overwrite the buffer as soon as we return
     k_stacey_elastic_replay<<<mp->num_abs_boundary_faces, 32, 0, mp->compute_stream>>>(
         mp->d_b_accel, mp->d_abs_boundary_ispec, mp->d_abs_boundary_ijk, mp->d_ibool, mp->d_ispec_is_elastic,
         mp->num_abs_boundary_faces, mp->d_b_absorb_field, (size_t)mp->NGLOB_AB);

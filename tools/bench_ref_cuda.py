@@ -22,6 +22,9 @@ def main():
     ap.add_argument("--nex", default="128x128x64")
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--kernel-run", action="store_true",
+                    help="time a SIMULATION_TYPE = 3 run (adjoint + reconstructed wavefield + kernels) instead of a forward run")
+    ap.add_argument("--skip-reference", action="store_true", help="time the product library only")
     args = ap.parse_args()
     import torch
 
@@ -36,6 +39,8 @@ def main():
     spec, DT, gll, db, loc, sources, receivers, _ = bench.build_workload(1, 0, nex, nstep)
     for key in ("rmassx", "rmassy", "rmassz"):
         setattr(db, key, invert_mass(loc[key]))
+    if args.kernel_run:
+        return kernel_run_bench(args, spec, DT, gll, db, sources, receivers, nstep)
     out = {}
     libs = {"specfem3d_b200": abi.LIB_PATH, "reference_cuda_backend": os.path.join(ROOT, "oracle", "_ref", "libspecfem_ref_cuda.so")}
     for name, path in libs.items():
@@ -58,6 +63,54 @@ def main():
                      "max_norm_displ": run.max_norm_displ()}
         r.cleanup()
     out["workload"] = f"{nex[0]}x{nex[1]}x{nex[2]} elastic halfspace, {db.NSPEC_AB} elements, Stacey, CMT, 4 receivers"
+    print(json.dumps(out))
+
+
+def kernel_run_bench(args, spec, DT, gll, db, sources, receivers, nstep):
+    """Forward run with SAVE_FORWARD once (product library), then the same kernel run through both libraries."""
+    import numpy as np
+    import torch
+
+    from specfem3d_b200 import abi
+    from specfem3d_b200.kernel_run import KernelRun, run_forward_and_save
+    from specfem3d_b200.simulation import Simulation
+
+    def sim(sim_type):
+        s = Simulation(spec, DT, nstep, [db], gll, sources, receivers)
+        s.SIMULATION_TYPE, s.SAVE_FORWARD = sim_type, sim_type == 1
+        return s
+
+    fwd, prod = run_forward_and_save(sim(1), lib=abi.load())
+    fwd.cleanup()
+    t = np.arange(nstep) * DT
+    adj = np.zeros((receivers.nrec, nstep, 3), np.float32)
+    adj[:] = (1e15 * np.cos(2 * np.pi * 0.3 * t))[None, :, None]
+    out = {}
+    libs = {"specfem3d_b200": abi.LIB_PATH, "reference_cuda_backend": os.path.join(ROOT, "oracle", "_ref", "libspecfem_ref_cuda.so")}
+    for name, path in libs.items():
+        if args.skip_reference and name != "specfem3d_b200":
+            continue
+        if not os.path.exists(path):
+            out[name] = {"unavailable": path}
+            continue
+        print("kernel run with", name, file=sys.stderr, flush=True)
+        k = KernelRun(sim(3), prod, adj, lib=abi.DeviceLibrary(path))
+        for _ in range(args.warmup):
+            k.step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            k.step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        rho, mu, kappa = k.kernels()[0]
+        out[name] = {"ms_per_step": dt / args.steps * 1e3, "element_timesteps_per_s": db.NSPEC_AB * args.steps / dt,
+                     "kl_l2": [float(np.linalg.norm(a.astype(np.float64))) for a in (rho, mu, kappa)]}
+        if name == "specfem3d_b200":
+            k.cleanup()  # the reference library resets the device when it initialises: nothing of ours may be alive then
+    out["workload"] = (f"kernel run (SIMULATION_TYPE 3), {db.NSPEC_AB} elastic elements, Stacey replay "
+                       f"({db.num_abs_boundary_faces} faces, host record per step), CMT, {receivers.nrec} adjoint sources; "
+                       "one step = adjoint + reconstructed wavefield + rho/mu/kappa kernels")
     print(json.dumps(out))
 
 
