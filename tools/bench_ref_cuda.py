@@ -75,9 +75,17 @@ def kernel_run_bench(args, spec, DT, gll, db, sources, receivers, nstep):
     from specfem3d_b200.kernel_run import KernelRun, run_forward_and_save
     from specfem3d_b200.simulation import Simulation
 
+    # the CMT source has not ramped up within the few timed steps: start the forward run from a smooth O(1e-3 m) wavefield
+    # so that the Stacey record, the reconstructed wavefield and the kernels are not identically zero
+    x, y, z = db.xstore / 5000.0, db.ystore / 5000.0, db.zstore / 5000.0
+    u0 = 1e-3 * np.stack([np.sin(x + 0.3 * y) + 0.1, np.cos(0.7 * y - z), np.sin(0.5 * z + x * y * 0.1)], -1).astype(np.float32)
+    init = [dict(displ=u0, veloc=np.zeros_like(u0), accel=np.zeros_like(u0))]
+
     def sim(sim_type):
         s = Simulation(spec, DT, nstep, [db], gll, sources, receivers)
         s.SIMULATION_TYPE, s.SAVE_FORWARD = sim_type, sim_type == 1
+        if sim_type == 1:
+            s.initial_fields = init
         return s
 
     fwd, prod = run_forward_and_save(sim(1), lib=abi.load())
