@@ -61,6 +61,7 @@ struct KernelArgs {
   realw deltat;
   int nspec;
   size_t nglob;
+  const realw* rmass3 = nullptr;  // != nullptr: the Newmark corrector of accel is still pending, apply the mass matrix here
 };
 
 template <bool HESS>
@@ -271,7 +272,9 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_kernels_elastic_pointwise(cons
   const size_t iglob = (size_t)a.ibool[off] - 1;
   const size_t g0 = vidx(iglob, 0, a.nglob), g1 = vidx(iglob, 1, a.nglob), g2 = vidx(iglob, 2, a.nglob);
   if (!HESS) {
-    a.rho_kl[off] += a.deltat * (a.accel[g0] * a.b_displ[g0] + a.accel[g1] * a.b_displ[g1] + a.accel[g2] * a.b_displ[g2]);
+    realw ax = a.accel[g0], ay = a.accel[g1], az = a.accel[g2];
+    if (a.rmass3) { ax *= a.rmass3[g0]; ay *= a.rmass3[g1]; az *= a.rmass3[g2]; }
+    a.rho_kl[off] += a.deltat * (ax * a.b_displ[g0] + ay * a.b_displ[g1] + az * a.b_displ[g2]);
   } else {
     a.hess_kl[off] += a.deltat * (a.accel[g0] * a.b_accel[g0] + a.accel[g1] * a.b_accel[g1] + a.accel[g2] * a.b_accel[g2]);
     const realw vx = a.b_veloc[g0], vy = a.b_veloc[g1], vz = a.b_veloc[g2];

@@ -192,6 +192,8 @@ struct DeviceMesh {
   int fuse_newmark = 1;
   bool corrector_pending = false;
   realw pending_deltatover2 = 0.f;
+  bool b_corrector_pending = false;  // same for the reconstructed wavefield of a kernel run (kernel_3_a_cuda with FORWARD_OR_ADJOINT = 3)
+  realw pending_b_deltatover2 = 0.f;
 
   // options
   int force_kernel_variant = 0;  // 0 = default (grp), 1 = pt, 2 = col
@@ -213,7 +215,7 @@ inline DeviceMesh* get_mesh_keep_pending(long* Mesh_pointer) {
 // handle -> state for everybody else: veloc / accel are made current first
 inline DeviceMesh* get_mesh(long* Mesh_pointer) {
   DeviceMesh* mp = get_mesh_keep_pending(Mesh_pointer);
-  if (mp->corrector_pending) g_flush_corrector(mp);
+  if (mp->corrector_pending || mp->b_corrector_pending) g_flush_corrector(mp);
   return mp;
 }
 

@@ -175,7 +175,6 @@ extern "C" void SB200_FC(prepare_constants_device)(
   mp->NSPEC_IRREGULAR = *NSPEC_IRREGULAR;
   mp->simulation_type = *SIMULATION_TYPE;
   if (const char* e = getenv("SPECFEM_B200_KL_FUSED")) mp->kl_fused = atoi(e);
-  if (mp->simulation_type == 3) mp->fuse_newmark = 0;  // two wavefields per step: the corrector is applied where it is called
   mp->save_forward = *SAVE_FORWARD;
   mp->stacey_absorbing_conditions = *STACEY_ABSORBING_CONDITIONS;
   mp->pml_conditions = *PML_CONDITIONS;
@@ -620,12 +619,19 @@ static void require_backward_fields(DeviceMesh* mp, const char* who) {
   }
 }
 static void flush_corrector_impl(DeviceMesh* mp) {
-  if (!mp->corrector_pending) return;
-  mp->corrector_pending = false;
   const long long n = (long long)NDIM * mp->NGLOB_AB;
-  k_newmark_corrector<<<streaming_grid(n >> 2), 256, 0, mp->compute_stream>>>(mp->d_veloc, mp->d_accel, mp->d_rmassx, n,
-                                                                               mp->pending_deltatover2, 1);
-  KERNEL_CHECK(mp, "k_newmark_corrector(deferred)");
+  if (mp->corrector_pending) {
+    mp->corrector_pending = false;
+    k_newmark_corrector<<<streaming_grid(n >> 2), 256, 0, mp->compute_stream>>>(mp->d_veloc, mp->d_accel, mp->d_rmassx, n,
+                                                                                 mp->pending_deltatover2, 1);
+    KERNEL_CHECK(mp, "k_newmark_corrector(deferred)");
+  }
+  if (mp->b_corrector_pending) {
+    mp->b_corrector_pending = false;
+    k_newmark_corrector<<<streaming_grid(n >> 2), 256, 0, mp->compute_stream>>>(mp->d_b_veloc, mp->d_b_accel, mp->d_rmassx, n,
+                                                                                 mp->pending_b_deltatover2, 1);
+    KERNEL_CHECK(mp, "k_newmark_corrector(deferred, backward)");
+  }
 }
 namespace sb200 {
 void (*g_flush_corrector)(DeviceMesh*) = &flush_corrector_impl;
@@ -638,6 +644,14 @@ extern "C" void SB200_FC(update_displacement_cuda)(long* Mesh_pointer, realw* de
   const long long n = (long long)NDIM * mp->NGLOB_AB;
   if (*FORWARD_OR_ADJOINT == 3) {  // backward / reconstructed wavefield: the caller passes b_deltat, b_deltatover2, ...
     require_backward_fields(mp, "update_displacement_cuda");
+    if (mp->b_corrector_pending) {  // deferred corrector of the previous step and this predictor in one pass
+      mp->b_corrector_pending = false;
+      k_newmark_corrector_predictor<<<streaming_grid(n >> 2), 256, 0, mp->compute_stream>>>(
+          mp->d_b_displ, mp->d_b_veloc, mp->d_b_accel, mp->d_rmassx, n, mp->pending_b_deltatover2, *deltat_F, *deltatsqover2_F,
+          *deltatover2_F);
+      KERNEL_CHECK(mp, "k_newmark_corrector_predictor(backward)");
+      return;
+    }
     k_newmark_predictor<<<streaming_grid(n >> 2), 256, 0, mp->compute_stream>>>(mp->d_b_displ, mp->d_b_veloc, mp->d_b_accel, n,
                                                                                  *deltat_F, *deltatsqover2_F, *deltatover2_F);
     KERNEL_CHECK(mp, "k_newmark_predictor(backward)");
@@ -670,16 +684,25 @@ extern "C" void SB200_FC(update_displacement_ac_cuda)(long* Mesh_pointer, realw*
 
 extern "C" void SB200_FC(kernel_3_a_cuda)(long* Mesh_pointer, realw* deltatover2_F, realw* b_deltatover2_F,
                                           int* APPROXIMATE_OCEAN_LOAD, int* FORWARD_OR_ADJOINT) {
-  DeviceMesh* mp = get_mesh(Mesh_pointer);
+  // a kernel run calls this twice per step (1, then 3): the second call must not flush what the first one deferred
+  DeviceMesh* mp = get_mesh_keep_pending(Mesh_pointer);
   if (*FORWARD_OR_ADJOINT != 1 && *FORWARD_OR_ADJOINT != 3) exit_on_error("kernel_3_a_cuda: FORWARD_OR_ADJOINT must be 1 or 3");
   const long long n = (long long)NDIM * mp->NGLOB_AB;
+  const bool defer = mp->fuse_newmark && *APPROXIMATE_OCEAN_LOAD == 0 && !(mp->pml_conditions && mp->NSPEC_CPML > 0);
   if (*FORWARD_OR_ADJOINT == 3) {
     require_backward_fields(mp, "kernel_3_a_cuda");
+    if (mp->b_corrector_pending) flush_corrector_impl(mp);  // two correctors without a predictor in between: apply the first
+    if (defer) {
+      mp->b_corrector_pending = true;
+      mp->pending_b_deltatover2 = *b_deltatover2_F;
+      return;
+    }
     k_newmark_corrector<<<streaming_grid(n >> 2), 256, 0, mp->compute_stream>>>(mp->d_b_veloc, mp->d_b_accel, mp->d_rmassx, n,
                                                                                  *b_deltatover2_F, *APPROXIMATE_OCEAN_LOAD == 0);
     KERNEL_CHECK(mp, "k_newmark_corrector(backward)");
     return;
   }
+  if (mp->corrector_pending) flush_corrector_impl(mp);
   if (mp->fuse_newmark && *APPROXIMATE_OCEAN_LOAD == 0 && !(mp->pml_conditions && mp->NSPEC_CPML > 0)) {
     // deferred: update_displacement_cuda of the next step applies it together with the predictor; compute_seismograms_cuda
     // evaluates it on the fly at the receivers; every other entry point flushes it first (device_mesh.h: get_mesh)
@@ -1267,13 +1290,14 @@ extern "C" void SB200_FC(compute_seismograms_cuda)(long* Mesh_pointer_f, realw* 
   (void)ACOUSTIC_SIMULATION; (void)ELASTIC_SIMULATION;
   DeviceMesh* mp = get_mesh_keep_pending(Mesh_pointer_f);
   if (mp->nrec_local == 0) return;
-  const int pend = mp->corrector_pending ? 1 : 0;
+  // kernel runs record the reconstructed forward wavefield (write_seismograms_cuda.cu:100-118)
+  const bool b3 = mp->simulation_type == 3 && mp->d_b_displ != nullptr;
+  if (b3 && mp->b_corrector_pending && (mp->save_seismograms_v || mp->save_seismograms_a)) flush_corrector_impl(mp);
+  const int pend = (!b3 && mp->corrector_pending) ? 1 : 0;
   const int seismo_current = *seismo_currentf - 1;
   const int nlength = *nlength_seismogramf;
   if (nlength != mp->nlength_seismogram) exit_on_error("compute_seismograms_cuda: nlength_seismogram differs from prepare_constants_device");
   if (seismo_current < 0 || seismo_current >= nlength) exit_on_error("compute_seismograms_cuda: seismo_current out of range");
-  // kernel runs record the reconstructed forward wavefield (write_seismograms_cuda.cu:100-118)
-  const bool b3 = mp->simulation_type == 3 && mp->d_b_displ != nullptr;
   struct { int on; const realw* vec; const realw* pot; realw* out; int corr_mode; } sets[3] = {
       {mp->save_seismograms_d, b3 ? mp->d_b_displ : mp->d_displ, mp->d_potential, mp->d_seismograms_d, 0},
       {mp->save_seismograms_v, b3 ? mp->d_b_veloc : mp->d_veloc, mp->d_potential_dot, mp->d_seismograms_v, pend * 1},
