@@ -170,6 +170,36 @@ def prepare_attenuation(sim, f0_reference: float = 0.0) -> List[dict]:
             "kappastore": (db.kappastore.reshape(nspec, NGLL3) * sfk).astype(np.float32).reshape(db.kappastore.shape),
             "factor_common": fcom, "factor_common_kappa": fcomk, "alphaval": alphaval, "betaval": betaval,
             "gammaval": gammaval, "tau_sigma": tau_s32, "f_c_source": fc,
+            "scale_factor": sf, "scale_factor_kappa": sfk,  # what proc*_attenuation.bin holds next to factor_common*
+        }
+        for k in ("xx", "yy", "xy", "xz", "yz", "trace"):
+            att["epsilondev_" + k] = np.zeros((nspec, NGLL3), np.float32)
+            att["R_" + k] = np.zeros((nspec, NGLL3, N_SLS), np.float32)
+        out.append(att)
+    return out
+
+
+def attenuation_from_database_arrays(sim, arrays: List[dict]) -> List[dict]:
+    """prepare_attenuation (src/specfem3D/prepare_attenuation.f90:60-241) for arrays READ from ``proc*_attenuation.bin``
+    (``databases.read_attenuation_bin``): scale mu / kappa with the stored scale factors (:140-160), Runge-Kutta constants
+    from tau_sigma of the resolved period band, zero memory variables and strains."""
+    tmin, tmax = attenuation_periods(min_resolved_period_of(sim))
+    tau_s = tau_sigma_of(tmin, tmax)
+    tau_s32 = tau_s.astype(np.float32)
+    alphaval, betaval, gammaval = memory_values(tau_s32, sim.deltat)
+    out = []
+    for db, a in zip(sim.dbs, arrays):
+        nspec = db.NSPEC_AB
+        el = np.asarray(db.ispec_is_elastic, bool)[:, None]
+        sf = np.where(el, a["scale_factor"].reshape(nspec, NGLL3), np.float32(1)).astype(np.float32)
+        sfk = np.where(el, a["scale_factor_kappa"].reshape(nspec, NGLL3), np.float32(1)).astype(np.float32)
+        att = {
+            "mustore": (db.mustore.reshape(nspec, NGLL3) * sf).astype(np.float32).reshape(db.mustore.shape),
+            "kappastore": (db.kappastore.reshape(nspec, NGLL3) * sfk).astype(np.float32).reshape(db.kappastore.shape),
+            "factor_common": np.ascontiguousarray(a["factor_common"], np.float32).reshape(nspec, NGLL3, N_SLS),
+            "factor_common_kappa": np.ascontiguousarray(a["factor_common_kappa"], np.float32).reshape(nspec, NGLL3, N_SLS),
+            "alphaval": alphaval, "betaval": betaval, "gammaval": gammaval, "tau_sigma": tau_s32,
+            "f_c_source": f_c_source_of(tmin, tmax), "scale_factor": sf, "scale_factor_kappa": sfk,
         }
         for k in ("xx", "yy", "xy", "xz", "yz", "trace"):
             att["epsilondev_" + k] = np.zeros((nspec, NGLL3), np.float32)

@@ -122,3 +122,40 @@ def test_run_from_reread_databases_equals_run_from_memory(tmp_path):
     r1, r2 = OracleRun(sim).run(), OracleRun(sim2).run()
     assert np.abs(r1.seis_d).max() > 0
     assert np.linalg.norm(r2.seis_d - r1.seis_d) <= 1e-4 * np.linalg.norm(r1.seis_d)  # 2e-5: source and receivers re-located from float32 coordinates
+
+
+def test_attenuation_bin_round_trip_and_run(tmp_path):
+    """proc%06d_attenuation.bin (five Fortran records, get_attenuation_model.f90:434-451): exact round trip, the reader's
+    element-count check, and prepare_attenuation redone from the re-read arrays gives the arrays the run was built with."""
+    from specfem3d_b200.databases import read_attenuation_bin, simulation_from_databases, write_attenuation_bin
+    from specfem3d_b200.simulation import make_simulation
+    from specfem3d_b200.sources_receivers import CMTSource, Station
+
+    mats = (Material(2300.0, 2800.0, 1500.0, 9999.0, 40.0, 2), Material(2600.0, 4200.0, 2500.0, 300.0, 100.0, 2))
+    spec = BoxSpec(6, 4, 4, xmax=6600.0, ymax=3600.0, zmin=-4000.0, nproc_xi=2, materials=mats, layer_material=[0, 0, 1, 1], deform=0.1)
+    src = [CMTSource(0.52 * spec.xmax, 0.47 * spec.ymax, 0.55 * spec.zmin, (1e23, -2e23, 0.5e23, 0.3e23, -0.7e23, 0.2e23), hdur=0.4)]
+    sts = [Station("A", "XX", 0.21 * spec.xmax, 0.33 * spec.ymax, 0.0)]
+    DT, NSTEP = 0.008, 10
+    sim = make_simulation(spec, DT=DT, NSTEP=NSTEP, sources=src, stations=sts, attenuation=True)
+    flags = DatabaseFlags()
+    dbs, arrays = [], []
+    for db, att in zip(sim.dbs, sim.att):
+        mesh = str(tmp_path / f"proc{db.myrank:06d}_external_mesh.bin")
+        write_external_mesh(mesh, db, spec, flags, mass_records(spec, db, DT, sim.gll))
+        dbs.append(read_external_mesh(mesh, flags, db.myrank, spec.nproc))
+        path = str(tmp_path / f"proc{db.myrank:06d}_attenuation.bin")
+        write_attenuation_bin(path, att)
+        recs = records(path)
+        assert len(recs) == 5 and struct.unpack("<i", recs[0])[0] == db.NSPEC_AB
+        assert [len(r) for r in recs[1:]] == [db.NSPEC_AB * 125 * 3 * 4, db.NSPEC_AB * 125 * 4] * 2
+        back = read_attenuation_bin(path, db.NSPEC_AB)
+        for k in ("factor_common", "scale_factor", "factor_common_kappa", "scale_factor_kappa"):
+            assert np.array_equal(back[k], att[k]), k
+        with pytest.raises(ValueError):
+            read_attenuation_bin(path, db.NSPEC_AB + 1)
+        arrays.append(back)
+    sim2 = simulation_from_databases(dbs, spec, DT, NSTEP, sources=src, stations=sts, attenuation_arrays=arrays)
+    assert sim2.ATTENUATION
+    for a, b in zip(sim.att, sim2.att):
+        for k in ("mustore", "kappastore", "factor_common", "factor_common_kappa", "alphaval", "betaval", "gammaval"):
+            assert np.array_equal(np.asarray(a[k]).ravel(), np.asarray(b[k]).ravel()), k
