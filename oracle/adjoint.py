@@ -33,7 +33,35 @@ class ForwardRecord:
 
     def __init__(self, nranks: int):
         self.absorb: List[List[np.ndarray]] = [[] for _ in range(nranks)]  # [rank][it-1] -> (nfaces, 25, 3)
+        self.absorb_potential: List[List[np.ndarray]] = [[] for _ in range(nranks)]  # [rank][it-1] -> (nfaces, 25)
         self.last: List[Optional[dict]] = [None] * nranks
+
+
+def _face_points(db, f):
+    """(ispec, local point ids p = i + 5 j + 25 k, global point ids) of the 25 GLL points of absorbing face f."""
+    ispec = int(db.abs_boundary_ispec[f]) - 1
+    ijk = np.asarray(db.abs_boundary_ijk[f]).reshape(25, 3).astype(np.int64) - 1
+    pt = ijk[:, 0] + 5 * ijk[:, 1] + 25 * ijk[:, 2]
+    return ispec, pt, db.ibool.reshape(db.NSPEC_AB, 125)[ispec, pt] - 1
+
+
+def absorbed_flux_acoustic(p: OraclePartition) -> np.ndarray:
+    """b_absorb_potential(igll,iface) = potential_dot * jacobianw / cpl / rhol of compute_stacey_acoustic_forward with
+    SAVE_FORWARD (compute_stacey_acoustic.f90:80-105)."""
+    db = p.db
+    if not p.sim.spec.stacey or db.num_abs_boundary_faces == 0:
+        return np.zeros((0, 25), np.float32)
+    b = np.zeros((db.num_abs_boundary_faces, 25), np.float32)
+    rho, kappa = db.rhostore.reshape(db.NSPEC_AB, 125), db.kappastore.reshape(db.NSPEC_AB, 125)
+    for f in range(db.num_abs_boundary_faces):
+        ispec, pt, ig = _face_points(db, f)
+        if not db.ispec_is_acoustic[ispec]:
+            continue
+        rhol = rho[ispec, pt]
+        cpl = np.sqrt(kappa[ispec, pt] / rhol).astype(np.float32)
+        jw = np.asarray(db.abs_boundary_jacobian2Dw[f], np.float32).reshape(25)
+        b[f] = (p.pot_dot[ig] * jw / cpl / rhol).astype(np.float32)
+    return b
 
 
 def absorbed_tractions(p: OraclePartition) -> np.ndarray:
@@ -69,18 +97,28 @@ class OracleForwardRun(OracleRun):
             self._wrap(p, i)
 
     def _wrap(self, p, i):
-        orig = p.stacey_elastic
+        orig, orig_ac = p.stacey_elastic, p.stacey_acoustic
 
         def record_then_apply():
             self.record.absorb[i].append(absorbed_tractions(p))
             orig()
 
+        def record_then_apply_ac():
+            self.record.absorb_potential[i].append(absorbed_flux_acoustic(p))
+            orig_ac()
+
         p.stacey_elastic = record_then_apply
+        p.stacey_acoustic = record_then_apply_ac
 
     def run(self, nstep=None, progress=False):
         super().run(nstep, progress)
         for i, p in enumerate(self.parts):
-            self.record.last[i] = dict(displ=p.displ.copy(), veloc=p.veloc.copy(), accel=p.accel.copy())
+            last = {}
+            if p.db.nspec_elastic:
+                last.update(displ=p.displ.copy(), veloc=p.veloc.copy(), accel=p.accel.copy())
+            if p.db.nspec_acoustic:
+                last.update(pot=p.pot.copy(), pot_dot=p.pot_dot.copy(), pot_dot_dot=p.pot_dot_dot.copy())
+            self.record.last[i] = last
         return self
 
 
@@ -201,6 +239,135 @@ class OracleKernelRun:
             o = np.zeros(3, np.float32)
             L.oracle_interpolate_seismogram(c_int(ispec), P(pb.db.ibool), P(pb.displ), P(hx), P(hy), P(hz), P(nu), P(o))
             self.seis_d[irec, k] = o
+
+    def run(self, nstep: Optional[int] = None):
+        for _ in range(self.sim.NSTEP if nstep is None else nstep):
+            self.step()
+        return self
+
+
+def gradient_over_rho(db, gll, field: np.ndarray) -> np.ndarray:
+    """compute_gradient_in_acoustic (src/specfem3D/compute_gradient_in_acoustic.f90): (1/rho) grad(field) at every GLL point
+    of every element, (NSPEC, 125, 3), single precision."""
+    n = db.NSPEC_AB
+    u = field[db.ibool.reshape(n, 125) - 1].reshape(n, 5, 5, 5)  # [e, k, j, i]
+    hp = gll.hprime_xx.astype(np.float32)                       # hprime_xx(i, l)
+    t1 = np.einsum("ekjl,il->ekji", u, hp).astype(np.float32)
+    t2 = np.einsum("eklj,il->ekij", u, hp).astype(np.float32)   # sum_l u(i,l,k) hprime_xx(j,l)
+    t3 = np.einsum("eljk,il->eijk", u, hp).astype(np.float32)   # sum_l u(i,j,l) hprime_xx(k,l)
+    rho_inv = (np.float32(1) / db.rhostore.reshape(n, 5, 5, 5)).astype(np.float32)
+    out = np.zeros((n, 5, 5, 5, 3), np.float32)
+    irr = np.asarray(db.irregular_element_number) - 1
+    for e in range(n):
+        if irr[e] >= 0:
+            m = {k: getattr(db, k + "store")[irr[e]] for k in ("xix", "xiy", "xiz", "etax", "etay", "etaz", "gammax", "gammay", "gammaz")}
+            out[e, ..., 0] = (t1[e] * m["xix"] + t2[e] * m["etax"] + t3[e] * m["gammax"]) * rho_inv[e]
+            out[e, ..., 1] = (t1[e] * m["xiy"] + t2[e] * m["etay"] + t3[e] * m["gammay"]) * rho_inv[e]
+            out[e, ..., 2] = (t1[e] * m["xiz"] + t2[e] * m["etaz"] + t3[e] * m["gammaz"]) * rho_inv[e]
+        else:
+            x = np.float32(db.xix_regular)
+            out[e, ..., 0], out[e, ..., 1], out[e, ..., 2] = t1[e] * x * rho_inv[e], t2[e] * x * rho_inv[e], t3[e] * x * rho_inv[e]
+    return out.reshape(n, 125, 3)
+
+
+class OracleAcousticKernelRun:
+    """SIMULATION_TYPE == 3 for purely acoustic meshes on the CPU: compute_forces_acoustic_forward_calling for the adjoint
+    potentials, compute_forces_acoustic_backward_calling for the reconstructed ones (compute_forces_acoustic_calling_routine.f90
+    :28-330, 336-590), compute_kernels_ac (compute_kernels.f90:258-331).  ``adj``: (nrec, NSTEP, 3), first component used."""
+
+    def __init__(self, sim, record: ForwardRecord, adj: np.ndarray):
+        assert sim.ACOUSTIC_SIMULATION and not sim.ELASTIC_SIMULATION
+        self.sim, self.record, self.adj = sim, record, np.asarray(adj, np.float32)
+        self.parts = [OraclePartition(sim, db) for db in sim.dbs]
+        self.bparts = [OraclePartition(sim, db) for db in sim.dbs]
+        self.rho_ac_kl = [np.zeros((db.NSPEC_AB, 125), np.float32) for db in sim.dbs]
+        self.kappa_ac_kl = [np.zeros((db.NSPEC_AB, 125), np.float32) for db in sim.dbs]
+        self.seis_p = np.zeros((sim.receivers.nrec, sim.nlength_seismogram), np.float32)
+        self.it = 0
+
+    def _add_adjoint_sources(self, it: int):
+        sim, rec = self.sim, self.sim.receivers
+        if it >= sim.NSTEP:
+            return
+        for irec in range(rec.nrec):
+            p = self.parts[rec.islice_selected_rec[irec]]
+            ispec = int(rec.ispec_selected_rec[irec]) - 1
+            if not p.db.ispec_is_acoustic[ispec]:
+                continue
+            hx, hy, hz = (np.asarray(a[irec], np.float32) for a in (rec.hxir_store, rec.hetar_store, rec.hgammar_store))
+            lag = ((hx[None, None, :] * hy[None, :, None]).astype(np.float32) * hz[:, None, None]).astype(np.float32).reshape(125)
+            ig = p.db.ibool.reshape(p.db.NSPEC_AB, 125)[ispec] - 1
+            np.add.at(p.pot_dot_dot, ig, (self.adj[irec, sim.NSTEP - it, 0] * lag).astype(np.float32))
+
+    def _stacey_replay(self, pb: OraclePartition, rank: int, it: int):
+        db = pb.db
+        if not self.sim.spec.stacey or db.num_abs_boundary_faces == 0:
+            return
+        b = self.record.absorb_potential[rank][self.sim.NSTEP - it]
+        for f in range(db.num_abs_boundary_faces):
+            ispec, _, ig = _face_points(db, f)
+            if db.ispec_is_acoustic[ispec]:
+                np.subtract.at(pb.pot_dot_dot, ig, b[f])
+
+    def _solve(self, parts, dt2, extra):
+        L = lib()
+        for p in parts:
+            p.enforce_free_surface()
+        for r, p in enumerate(parts):
+            p.forces_acoustic(1)
+            extra(r, p)
+        for p in parts:
+            p.forces_acoustic(2)
+        _assemble(parts, "pot_dot_dot", 1)
+        for p in parts:
+            L.oracle_multiply_update_potential(c_i64(p.db.NGLOB_AB), P(p.pot_dot), P(p.pot_dot_dot), P(p.db.rmass_acoustic), c_float(dt2))
+            p.enforce_free_surface()
+
+    def step(self):
+        sim, L = self.sim, lib()
+        self.it += 1
+        it = self.it
+        dt, dt2, dtsq2 = sim.deltat, sim.deltatover2, sim.deltatsqover2
+        bdt = np.float32(-dt)
+        bdt2, bdtsq2 = np.float32(bdt / np.float32(2)), np.float32(bdt * bdt / np.float32(2))
+        for p, pb in zip(self.parts, self.bparts):
+            n = c_i64(p.db.NGLOB_AB)
+            L.oracle_update_displ_acoustic(n, P(p.pot), P(p.pot_dot), P(p.pot_dot_dot), c_float(dt), c_float(dt2), c_float(dtsq2))
+            L.oracle_update_displ_acoustic(n, P(pb.pot), P(pb.pot_dot), P(pb.pot_dot_dot), c_float(bdt), c_float(bdt2), c_float(bdtsq2))
+        added = []
+
+        def adjoint_extra(r, p):
+            p.stacey_acoustic()
+            if not added:  # all receivers at once, after the first partition's outer elements like the per-rank Fortran loop
+                added.append(1)
+                self._add_adjoint_sources(it)
+
+        def backward_extra(r, pb):
+            self._stacey_replay(pb, r, it)
+            pb.add_sources_acoustic(sim.NSTEP - it + 1)
+
+        self._solve(self.parts, dt2, adjoint_extra)
+        self._solve(self.bparts, bdt2, backward_extra)
+        if it == 1:
+            for r, pb in enumerate(self.bparts):
+                for k, v in self.record.last[r].items():
+                    getattr(pb, k)[...] = v
+        rec = sim.receivers
+        for irec in range(rec.nrec):
+            pb = self.bparts[rec.islice_selected_rec[irec]]
+            hx, hy, hz = (np.ascontiguousarray(a[irec]) for a in (rec.hxir_store, rec.hetar_store, rec.hgammar_store))
+            o = np.zeros(1, np.float32)
+            L.oracle_interpolate_pressure(c_int(int(rec.ispec_selected_rec[irec])), P(pb.db.ibool), P(pb.pot_dot_dot), P(hx), P(hy), P(hz), P(o))
+            self.seis_p[irec, it - 1] = o[0]
+        for r, (p, pb) in enumerate(zip(self.parts, self.bparts)):
+            db = p.db
+            ib = db.ibool.reshape(db.NSPEC_AB, 125) - 1
+            ac = np.asarray(db.ispec_is_acoustic, bool)
+            rho = db.rhostore.reshape(db.NSPEC_AB, 125, 1)
+            accel_elm = rho * gradient_over_rho(db, sim.gll, p.pot)
+            b_displ_elm = rho * gradient_over_rho(db, sim.gll, pb.pot)
+            self.rho_ac_kl[r][ac] += dt * (accel_elm * b_displ_elm).sum(-1, dtype=np.float32)[ac]
+            self.kappa_ac_kl[r][ac] += dt * (p.pot[ib] * pb.pot_dot_dot[ib])[ac]
 
     def run(self, nstep: Optional[int] = None):
         for _ in range(self.sim.NSTEP if nstep is None else nstep):

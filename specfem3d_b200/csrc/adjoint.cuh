@@ -282,4 +282,102 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_kernels_elastic_pointwise(cons
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// acoustic domains of a kernel run
+// ---------------------------------------------------------------------------------------------------------------
+// b_potential_dot_dot -= flux the forward run absorbed at this time level (compute_stacey_acoustic_kernel with
+// SIMULATION_TYPE 3; CPU compute_stacey_acoustic_backward, compute_stacey_acoustic.f90)
+__global__ void __launch_bounds__(32) k_stacey_acoustic_replay(realw* b_potential_dot_dot, const int* __restrict__ abs_ispec,
+                                                               const int* __restrict__ abs_ijk, const int* __restrict__ ibool,
+                                                               const int* __restrict__ ispec_is_acoustic, int num_faces,
+                                                               const realw* __restrict__ b_absorb_potential) {
+  const int iface = blockIdx.x, igll = threadIdx.x;
+  if (iface >= num_faces || igll >= NGLL2) return;
+  const int ispec = abs_ispec[iface] - 1;
+  if (!ispec_is_acoustic[ispec]) return;
+  const int* ijk = abs_ijk + 3 * (igll + NGLL2 * (size_t)iface);
+  const int p = (ijk[0] - 1) + NGLLX * (ijk[1] - 1) + NGLL2 * (ijk[2] - 1);
+  const size_t iglob = (size_t)ibool[(size_t)ispec * NGLL3_PADDED + p] - 1;
+  red_add(b_potential_dot_dot + iglob, -b_absorb_potential[igll + NGLL2 * (size_t)iface]);
+}
+
+// potential_dot_dot(ibool(i,j,k, ispec_rec)) += source_adjoint(1, irec_local, it_index) * hxi(i) heta(j) hgamma(k): first
+// component only, no 1/kappa (add_sources_ac_SIM_TYPE_2_OR_3_kernel; CPU compute_add_sources_acoustic.f90:200-240)
+__global__ void __launch_bounds__(NGLL3_PADDED) k_add_adjoint_sources_ac(realw* potential_dot_dot, int it_index,
+                                                                          const realw* __restrict__ source_adjoint,
+                                                                          const realw* __restrict__ hxir,
+                                                                          const realw* __restrict__ hetar,
+                                                                          const realw* __restrict__ hgammar,
+                                                                          const int* __restrict__ ibool,
+                                                                          const int* __restrict__ ispec_is_acoustic,
+                                                                          const int* __restrict__ ispec_selected_rec_loc,
+                                                                          int nadj_rec_local) {
+  const int irec = blockIdx.x, p = threadIdx.x;
+  if (irec >= nadj_rec_local || p >= NGLL3) return;
+  const int ispec = ispec_selected_rec_loc[irec] - 1;
+  if (!ispec_is_acoustic[ispec]) return;
+  const int i = p % NGLLX, j = (p / NGLLX) % NGLLX, k = p / NGLL2;
+  const size_t iglob = (size_t)ibool[(size_t)ispec * NGLL3_PADDED + p] - 1;
+  const realw sa = source_adjoint[3 * (irec + (size_t)nadj_rec_local * it_index)];
+  red_add(potential_dot_dot + iglob, sa * hxir[i + NGLLX * irec] * hetar[j + NGLLX * irec] * hgammar[k + NGLLX * irec]);
+}
+
+// rho_ac_kl += dt * (rho grad(phi^dagger)/rho) . (rho grad(b_phi)/rho) ; kappa_ac_kl += dt * phi^dagger * b_phi_dot_dot
+// (compute_kernels_acoustic_kernel + compute_gradient_kernel.h; CPU compute_kernels_ac, compute_kernels.f90:258-331)
+struct AcousticKernelArgs {
+  const int *ispec_is_acoustic, *ibool, *irregular_element_number;
+  const realw *metric, *rhostore;
+  realw xix_regular;
+  const realw *potential, *b_potential, *b_potential_dot_dot;
+  realw *rho_ac_kl, *kappa_ac_kl;
+  realw deltat;
+  int nspec;
+};
+
+__global__ void __launch_bounds__(NGLL3_PADDED) k_kernels_acoustic(const AcousticKernelArgs a) {
+  const int ispec = blockIdx.x, tx = threadIdx.x;
+  if (ispec >= a.nspec || !a.ispec_is_acoustic[ispec]) return;  // uniform per block
+  const bool active = tx < NGLL3;
+  const int t = active ? tx : NGLL3 - 1;
+  const int K = t / NGLL2, J = (t - K * NGLL2) / NGLLX, I = t - K * NGLL2 - J * NGLLX;
+  __shared__ realw s_b[NGLL3_PADDED], s_a[NGLL3_PADDED], s_hp[NGLL2];
+  const size_t off = (size_t)ispec * NGLL3_PADDED + t;
+  const size_t iglob = (size_t)a.ibool[off] - 1;
+  const realw pot = a.potential[iglob];
+  s_b[t] = a.b_potential[iglob];
+  s_a[t] = pot;
+  if (tx < NGLL2) s_hp[tx] = c_hprime_xx[tx];
+  __syncthreads();
+  if (!active) return;
+  realw b1 = 0.f, b2 = 0.f, b3 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+  for (int l = 0; l < NGLLX; ++l) {
+    const realw h1 = s_hp[l * NGLLX + I], h2 = s_hp[l * NGLLX + J], h3 = s_hp[l * NGLLX + K];
+    const int o1 = K * NGLL2 + J * NGLLX + l, o2 = K * NGLL2 + l * NGLLX + I, o3 = l * NGLL2 + J * NGLLX + I;
+    b1 += s_b[o1] * h1; b2 += s_b[o2] * h2; b3 += s_b[o3] * h3;
+    a1 += s_a[o1] * h1; a2 += s_a[o2] * h2; a3 += s_a[o3] * h3;
+  }
+  const realw rhol = a.rhostore[off];
+  const realw rho_invl = 1.0f / rhol;
+  realw bx, by, bz, ax, ay, az;
+  const int irr = a.irregular_element_number[ispec] - 1;
+  if (irr >= 0) {
+    const realw* mp = a.metric + (size_t)irr * 9 * NGLL3_PADDED + t;
+    const realw xix = mp[0], xiy = mp[NGLL3_PADDED], xiz = mp[2 * NGLL3_PADDED];
+    const realw etax = mp[3 * NGLL3_PADDED], etay = mp[4 * NGLL3_PADDED], etaz = mp[5 * NGLL3_PADDED];
+    const realw gammax = mp[6 * NGLL3_PADDED], gammay = mp[7 * NGLL3_PADDED], gammaz = mp[8 * NGLL3_PADDED];
+    bx = (b1 * xix + b2 * etax + b3 * gammax) * rho_invl; by = (b1 * xiy + b2 * etay + b3 * gammay) * rho_invl;
+    bz = (b1 * xiz + b2 * etaz + b3 * gammaz) * rho_invl;
+    ax = (a1 * xix + a2 * etax + a3 * gammax) * rho_invl; ay = (a1 * xiy + a2 * etay + a3 * gammay) * rho_invl;
+    az = (a1 * xiz + a2 * etaz + a3 * gammaz) * rho_invl;
+  } else {
+    bx = b1 * a.xix_regular * rho_invl; by = b2 * a.xix_regular * rho_invl; bz = b3 * a.xix_regular * rho_invl;
+    ax = a1 * a.xix_regular * rho_invl; ay = a2 * a.xix_regular * rho_invl; az = a3 * a.xix_regular * rho_invl;
+  }
+  ax *= rhol; ay *= rhol; az *= rhol;
+  bx *= rhol; by *= rhol; bz *= rhol;
+  a.rho_ac_kl[off] += a.deltat * (ax * bx + ay * by + az * bz);
+  a.kappa_ac_kl[off] += a.deltat * (pot * a.b_potential_dot_dot[iglob]);
+}
+
 }  // namespace sb200

@@ -161,6 +161,9 @@ struct DeviceMesh {
   int nadj_rec_local = 0, ntstep_between_read_adjsrc = 0;
   realw* d_source_adjoint = nullptr;  // Fortran (NDIM, nadj_rec_local, NTSTEP_BETWEEN_READ_ADJSRC)
   realw* d_b_send_accel_buffer = nullptr;
+  realw *d_b_potential = nullptr, *d_b_potential_dot = nullptr, *d_b_potential_dot_dot = nullptr;  // [NGLOB]
+  realw *d_rho_ac_kl = nullptr, *d_kappa_ac_kl = nullptr;                                          // [NSPEC][128]
+  realw* d_b_send_potential_buffer = nullptr;
   realw* h_absorb_registered = nullptr;  // caller's b_absorb_field record buffer, page-locked on first use (Stacey replay)
   // FORWARD_OR_ADJOINT == 0 force launches use the two-wavefield kernel that accumulates mu_kl / kappa_kl itself
   // (adjoint.cuh: k_elastic_forces_kl_pair); SPECFEM_B200_KL_FUSED=0 restores the stored-strain path of the reference

@@ -178,7 +178,9 @@ __global__ void __launch_bounds__(32) k_coupling_ac_el(const realw* __restrict__
                                                        int num_faces, const int* __restrict__ c_ispec,
                                                        const int* __restrict__ c_ijk, const realw* __restrict__ c_normal,
                                                        const realw* __restrict__ c_jac2Dw, const int* __restrict__ ibool,
-                                                       size_t nglob) {
+                                                       size_t nglob, realw sign = 1.f) {
+  // sign = -1: adjoint wavefield of a kernel run, where `displ` is the adjoint acceleration
+  // (partial_t^2 s^dagger = -1/rho grad phi^dagger, compute_coupling_cuda.cu:71-82)
   const int iface = blockIdx.x, igll = threadIdx.x;
   if (iface >= num_faces || igll >= NGLL2) return;
   const int ispec = c_ispec[iface] - 1;
@@ -186,7 +188,7 @@ __global__ void __launch_bounds__(32) k_coupling_ac_el(const realw* __restrict__
   const int p = (ijk[0] - 1) + NGLLX * (ijk[1] - 1) + NGLL2 * (ijk[2] - 1);
   const size_t iglob = (size_t)ibool[(size_t)ispec * NGLL3_PADDED + p] - 1;
   const realw* n = c_normal + 3 * (igll + NGLL2 * (size_t)iface);
-  const realw displ_n = displ[vidx(iglob, 0, nglob)] * n[0] + displ[vidx(iglob, 1, nglob)] * n[1] + displ[vidx(iglob, 2, nglob)] * n[2];
+  const realw displ_n = sign * (displ[vidx(iglob, 0, nglob)] * n[0] + displ[vidx(iglob, 1, nglob)] * n[1] + displ[vidx(iglob, 2, nglob)] * n[2]);
   red_add(potential_dot_dot + iglob, c_jac2Dw[igll + NGLL2 * (size_t)iface] * displ_n);
 }
 
@@ -194,7 +196,9 @@ __global__ void __launch_bounds__(32) k_coupling_el_ac(const realw* __restrict__
                                                        int num_faces, const int* __restrict__ c_ispec,
                                                        const int* __restrict__ c_ijk, const realw* __restrict__ c_normal,
                                                        const realw* __restrict__ c_jac2Dw, const int* __restrict__ ibool,
-                                                       size_t nglob) {
+                                                       size_t nglob, realw sign = 1.f) {
+  // sign = -1: adjoint wavefield of a kernel run, `potential_dot_dot` is then the adjoint potential itself
+  // (pressure^dagger = potential^dagger, compute_coupling_cuda.cu:170-177)
   const int iface = blockIdx.x, igll = threadIdx.x;
   if (iface >= num_faces || igll >= NGLL2) return;
   const int ispec = c_ispec[iface] - 1;
@@ -202,7 +206,7 @@ __global__ void __launch_bounds__(32) k_coupling_el_ac(const realw* __restrict__
   const int p = (ijk[0] - 1) + NGLLX * (ijk[1] - 1) + NGLL2 * (ijk[2] - 1);
   const size_t iglob = (size_t)ibool[(size_t)ispec * NGLL3_PADDED + p] - 1;
   const realw* n = c_normal + 3 * (igll + NGLL2 * (size_t)iface);
-  const realw pressure = -potential_dot_dot[iglob];
+  const realw pressure = sign * -potential_dot_dot[iglob];
   const realw jw = c_jac2Dw[igll + NGLL2 * (size_t)iface];
   red_add(accel + vidx(iglob, 0, nglob), jw * n[0] * pressure);
   red_add(accel + vidx(iglob, 1, nglob), jw * n[1] * pressure);

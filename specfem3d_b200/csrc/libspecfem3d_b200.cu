@@ -431,7 +431,8 @@ extern "C" void SB200_FC(prepare_fields_acoustic_device)(
       mp->d_free_surface_ijk = dev_copy(free_surface_ijk, 3 * NGLL2 * (size_t)mp->num_free_surface_faces);
     }
   }
-  if (mp->stacey_absorbing_conditions && mp->num_abs_boundary_faces > 0 && mp->simulation_type == 1 && mp->save_forward) {
+  if (mp->stacey_absorbing_conditions && mp->num_abs_boundary_faces > 0 &&
+      (mp->simulation_type == 3 || (mp->simulation_type == 1 && mp->save_forward))) {
     mp->b_reclen_potential = *b_reclen_potential;
     mp->d_b_absorb_potential = dev_alloc_zero<realw>(mp->b_reclen_potential / sizeof(realw));
   }
@@ -485,7 +486,8 @@ extern "C" void SB200_FC(prepare_cleanup_device)(long* Mesh_pointer, int* ACOUST
                    mp->d_b_epsilondev_xy, mp->d_b_epsilondev_xz, mp->d_b_epsilondev_yz, mp->d_epsilon_trace_over_3,
                    mp->d_b_epsilon_trace_over_3, mp->d_rho_kl, mp->d_mu_kl, mp->d_kappa_kl, mp->d_hess_el_kl,
                    mp->d_hess_rho_el_kl, mp->d_hess_kappa_el_kl, mp->d_hess_mu_el_kl, mp->d_source_adjoint,
-                   mp->d_b_send_accel_buffer};
+                   mp->d_b_send_accel_buffer, mp->d_b_potential, mp->d_b_potential_dot, mp->d_b_potential_dot_dot,
+                   mp->d_rho_ac_kl, mp->d_kappa_ac_kl, mp->d_b_send_potential_buffer};
   for (void* p : dptrs) dev_free(p);
   if (mp->h_absorb_registered) cudaHostUnregister(mp->h_absorb_registered);
   if (mp->h_send_accel_buffer) cudaFreeHost(mp->h_send_accel_buffer);
@@ -618,6 +620,13 @@ static void require_backward_fields(DeviceMesh* mp, const char* who) {
     exit_on_error(msg);
   }
 }
+static void require_backward_potentials(DeviceMesh* mp, const char* who) {
+  if (mp->simulation_type != 3 || !mp->d_b_potential) {
+    char msg[256];
+    snprintf(msg, sizeof(msg), "%s: FORWARD_OR_ADJOINT 0 / 3 needs SIMULATION_TYPE == 3 and prepare_fields_acoustic_adj_dev", who);
+    exit_on_error(msg);
+  }
+}
 static void flush_corrector_impl(DeviceMesh* mp) {
   const long long n = (long long)NDIM * mp->NGLOB_AB;
   if (mp->corrector_pending) {
@@ -675,8 +684,15 @@ extern "C" void SB200_FC(update_displacement_cuda)(long* Mesh_pointer, realw* de
 extern "C" void SB200_FC(update_displacement_ac_cuda)(long* Mesh_pointer, realw* deltat_F, realw* deltatover2_F,
                                                       realw* deltatsqover2_F, int* FORWARD_OR_ADJOINT) {
   DeviceMesh* mp = get_mesh_keep_pending(Mesh_pointer);  // touches the acoustic fields only
-  if (*FORWARD_OR_ADJOINT != 1) exit_on_error("update_displacement_ac_cuda: only FORWARD_OR_ADJOINT = 1 is supported");
+  if (*FORWARD_OR_ADJOINT != 1 && *FORWARD_OR_ADJOINT != 3) exit_on_error("update_displacement_ac_cuda: FORWARD_OR_ADJOINT must be 1 or 3");
   const long long n = mp->NGLOB_AB;
+  if (*FORWARD_OR_ADJOINT == 3) {  // reconstructed potentials: the caller passes b_deltat, b_deltatover2, b_deltatsqover2
+    require_backward_potentials(mp, "update_displacement_ac_cuda");
+    k_newmark_predictor<<<streaming_grid(n >> 2), 256, 0, mp->compute_stream>>>(
+        mp->d_b_potential, mp->d_b_potential_dot, mp->d_b_potential_dot_dot, n, *deltat_F, *deltatsqover2_F, *deltatover2_F);
+    KERNEL_CHECK(mp, "k_newmark_predictor(acoustic, backward)");
+    return;
+  }
   k_newmark_predictor<<<streaming_grid(n >> 2), 256, 0, mp->compute_stream>>>(
       mp->d_potential, mp->d_potential_dot, mp->d_potential_dot_dot, n, *deltat_F, *deltatsqover2_F, *deltatover2_F);
   KERNEL_CHECK(mp, "k_newmark_predictor(acoustic)");
@@ -733,10 +749,17 @@ extern "C" void SB200_FC(kernel_3_b_cuda)(long* Mesh_pointer, realw* deltatover2
 
 extern "C" void SB200_FC(kernel_3_acoustic_cuda)(long* Mesh_pointer, realw* deltatover2_F, realw* b_deltatover2_F,
                                                  int* FORWARD_OR_ADJOINT_f) {
-  (void)b_deltatover2_F;
   DeviceMesh* mp = get_mesh(Mesh_pointer);
-  if (*FORWARD_OR_ADJOINT_f != 1) exit_on_error("kernel_3_acoustic_cuda: only FORWARD_OR_ADJOINT = 1 is supported");
+  const int foa3 = *FORWARD_OR_ADJOINT_f;
+  if (foa3 != 0 && foa3 != 1 && foa3 != 3) exit_on_error("kernel_3_acoustic_cuda: FORWARD_OR_ADJOINT must be 0, 1 or 3");
   const long long n = mp->NGLOB_AB;
+  if (foa3 != 1) {  // 0 = both (update_displacement_cuda.cu:479-520)
+    require_backward_potentials(mp, "kernel_3_acoustic_cuda");
+    k_newmark_corrector<<<streaming_grid(n >> 2), 256, 0, mp->compute_stream>>>(mp->d_b_potential_dot, mp->d_b_potential_dot_dot,
+                                                                                 mp->d_rmass_acoustic, n, *b_deltatover2_F, 1);
+    KERNEL_CHECK(mp, "k_newmark_corrector(acoustic, backward)");
+    if (foa3 == 3) return;
+  }
   k_newmark_corrector<<<streaming_grid(n >> 2), 256, 0, mp->compute_stream>>>(mp->d_potential_dot, mp->d_potential_dot_dot,
                                                                                mp->d_rmass_acoustic, n, *deltatover2_F, 1);
   KERNEL_CHECK(mp, "k_newmark_corrector(acoustic)");
@@ -945,9 +968,13 @@ extern "C" void SB200_FC(compute_forces_viscoelastic_cuda)(long* Mesh_pointer, i
 extern "C" void SB200_FC(compute_forces_acoustic_cuda)(long* Mesh_pointer, int* iphase, int* nspec_outer_acoustic,
                                                        int* nspec_inner_acoustic, int* FORWARD_OR_ADJOINT_f) {
   DeviceMesh* mp = get_mesh(Mesh_pointer);
-  if (*FORWARD_OR_ADJOINT_f != 1) exit_on_error("compute_forces_acoustic_cuda: only FORWARD_OR_ADJOINT = 1 is supported");
+  const int foa = *FORWARD_OR_ADJOINT_f;
+  if (foa != 0 && foa != 1 && foa != 3) exit_on_error("compute_forces_acoustic_cuda: FORWARD_OR_ADJOINT must be 0, 1 or 3");
   const int num_elements = (*iphase == 1) ? *nspec_outer_acoustic : *nspec_inner_acoustic;
   if (num_elements <= 0) return;
+  if (foa != 1) require_backward_potentials(mp, "compute_forces_acoustic_cuda");
+  for (int pass = 0; pass < 2; ++pass) {  // 0: (adjoint) potentials, 1: reconstructed forward potentials
+  if (pass == 0 ? foa == 3 : foa == 1) continue;
   AcousticArgs a;
   a.ibool = mp->d_ibool;
   a.irregular_element_number = mp->d_irregular_element_number;
@@ -955,8 +982,8 @@ extern "C" void SB200_FC(compute_forces_acoustic_cuda)(long* Mesh_pointer, int* 
   a.xix_regular = mp->xix_regular;
   a.jacobian_regular = mp->jacobian_regular;
   a.rhostore = mp->d_rhostore;
-  a.potential = mp->d_potential;
-  a.potential_dot_dot = mp->d_potential_dot_dot;
+  a.potential = pass == 0 ? mp->d_potential : mp->d_b_potential;
+  a.potential_dot_dot = pass == 0 ? mp->d_potential_dot_dot : mp->d_b_potential_dot_dot;
   a.is_CPML = nullptr;
   if (mp->use_mesh_coloring_gpu) {
     int nb_colors, istart, offset;
@@ -984,17 +1011,28 @@ extern "C" void SB200_FC(compute_forces_acoustic_cuda)(long* Mesh_pointer, int* 
     launch_acoustic(mp, a);
     KERNEL_CHECK(mp, "acoustic forces");
   }
+  }
 }
 
 extern "C" void SB200_FC(acoustic_enforce_free_surf_cuda)(long* Mesh_pointer, int* ABSORB_INSTEAD_OF_FREE_SURFACE,
                                                           int* FORWARD_OR_ADJOINT) {
   DeviceMesh* mp = get_mesh(Mesh_pointer);
-  if (*FORWARD_OR_ADJOINT != 1) exit_on_error("acoustic_enforce_free_surf_cuda: only FORWARD_OR_ADJOINT = 1 is supported");
+  const int foa = *FORWARD_OR_ADJOINT;
+  if (foa != 0 && foa != 1 && foa != 3) exit_on_error("acoustic_enforce_free_surf_cuda: FORWARD_OR_ADJOINT must be 0, 1 or 3");
   if (*ABSORB_INSTEAD_OF_FREE_SURFACE != 0 || mp->num_free_surface_faces == 0) return;
-  k_enforce_free_surface<<<mp->num_free_surface_faces, 32, 0, mp->compute_stream>>>(
-      mp->d_potential, mp->d_potential_dot, mp->d_potential_dot_dot, mp->num_free_surface_faces, mp->d_free_surface_ispec,
-      mp->d_free_surface_ijk, mp->d_ibool, mp->d_ispec_is_acoustic);
-  KERNEL_CHECK(mp, "k_enforce_free_surface");
+  if (foa != 3) {
+    k_enforce_free_surface<<<mp->num_free_surface_faces, 32, 0, mp->compute_stream>>>(
+        mp->d_potential, mp->d_potential_dot, mp->d_potential_dot_dot, mp->num_free_surface_faces, mp->d_free_surface_ispec,
+        mp->d_free_surface_ijk, mp->d_ibool, mp->d_ispec_is_acoustic);
+    KERNEL_CHECK(mp, "k_enforce_free_surface");
+  }
+  if (foa != 1) {
+    require_backward_potentials(mp, "acoustic_enforce_free_surf_cuda");
+    k_enforce_free_surface<<<mp->num_free_surface_faces, 32, 0, mp->compute_stream>>>(
+        mp->d_b_potential, mp->d_b_potential_dot, mp->d_b_potential_dot_dot, mp->num_free_surface_faces,
+        mp->d_free_surface_ispec, mp->d_free_surface_ijk, mp->d_ibool, mp->d_ispec_is_acoustic);
+    KERNEL_CHECK(mp, "k_enforce_free_surface(backward)");
+  }
 }
 
 // =================================================================================================================
@@ -1042,9 +1080,22 @@ extern "C" void SB200_FC(compute_stacey_viscoelastic_cuda)(long* Mesh_pointer, i
 extern "C" void SB200_FC(compute_stacey_acoustic_cuda)(long* Mesh_pointer, int* iphasef, realw* h_b_absorb_potential,
                                                        int* FORWARD_OR_ADJOINT_f) {
   DeviceMesh* mp = get_mesh(Mesh_pointer);
-  if (*FORWARD_OR_ADJOINT_f != 1) exit_on_error("compute_stacey_acoustic_cuda: only FORWARD_OR_ADJOINT = 1 is supported");
+  const int foa = *FORWARD_OR_ADJOINT_f;
+  if (foa != 0 && foa != 1 && foa != 3) exit_on_error("compute_stacey_acoustic_cuda: FORWARD_OR_ADJOINT must be 0, 1 or 3");
   if (*iphasef != 1 || mp->num_abs_boundary_faces == 0) return;
-  realw* d_b = (mp->save_forward && mp->d_b_absorb_potential) ? mp->d_b_absorb_potential : nullptr;
+  if (foa != 1) {  // kernel run: put the absorbed flux of this time level back (compute_stacey_acoustic_cuda.cu:75-80,150-170)
+    require_backward_potentials(mp, "compute_stacey_acoustic_cuda");
+    if (!mp->d_b_absorb_potential) exit_on_error("compute_stacey_acoustic_cuda: b_absorb_potential was not prepared");
+    CUDA_CHECK(cudaMemcpyAsync(mp->d_b_absorb_potential, h_b_absorb_potential, mp->b_reclen_potential, cudaMemcpyHostToDevice,
+                               mp->compute_stream));
+    CUDA_CHECK(cudaStreamSynchronize(mp->compute_stream));
+    k_stacey_acoustic_replay<<<mp->num_abs_boundary_faces, 32, 0, mp->compute_stream>>>(
+        mp->d_b_potential_dot_dot, mp->d_abs_boundary_ispec, mp->d_abs_boundary_ijk, mp->d_ibool, mp->d_ispec_is_acoustic,
+        mp->num_abs_boundary_faces, mp->d_b_absorb_potential);
+    KERNEL_CHECK(mp, "k_stacey_acoustic_replay");
+    if (foa == 3) return;
+  }
+  realw* d_b = (mp->simulation_type == 1 && mp->save_forward && mp->d_b_absorb_potential) ? mp->d_b_absorb_potential : nullptr;
   k_stacey_acoustic<<<mp->num_abs_boundary_faces, 32, 0, mp->compute_stream>>>(
       mp->d_potential_dot, mp->d_potential_dot_dot, mp->d_abs_boundary_ispec, mp->d_abs_boundary_ijk,
       mp->d_abs_boundary_jacobian2Dw, mp->d_ibool, mp->d_rhostore, mp->d_kappastore_unpadded, mp->d_ispec_is_acoustic,
@@ -1061,27 +1112,47 @@ extern "C" void SB200_FC(compute_stacey_acoustic_cuda)(long* Mesh_pointer, int* 
 // =================================================================================================================
 extern "C" void SB200_FC(compute_coupling_ac_el_cuda)(long* Mesh_pointer, int* iphasef, int* num_coupling_ac_el_facesf,
                                                       int* FORWARD_OR_ADJOINT) {
-  DeviceMesh* mp = get_mesh(Mesh_pointer);
-  if (*FORWARD_OR_ADJOINT != 1) exit_on_error("compute_coupling_ac_el_cuda: only FORWARD_OR_ADJOINT = 1 is supported");
+  DeviceMesh* mp = get_mesh(Mesh_pointer);  // flushes a pending corrector: the adjoint branch reads accel
+  if (*FORWARD_OR_ADJOINT != 1 && *FORWARD_OR_ADJOINT != 3) exit_on_error("compute_coupling_ac_el_cuda: FORWARD_OR_ADJOINT must be 1 or 3");
   if (*iphasef != 1) return;
   const int nf = *num_coupling_ac_el_facesf;
   if (nf == 0) return;
-  k_coupling_ac_el<<<nf, 32, 0, mp->compute_stream>>>(mp->d_displ, mp->d_potential_dot_dot, nf, mp->d_coupling_ac_el_ispec,
+  const realw* vec = mp->d_displ;
+  realw* pdd = mp->d_potential_dot_dot;
+  realw sign = 1.f;
+  if (*FORWARD_OR_ADJOINT == 3) {
+    require_backward_fields(mp, "compute_coupling_ac_el_cuda");
+    require_backward_potentials(mp, "compute_coupling_ac_el_cuda");
+    vec = mp->d_b_displ; pdd = mp->d_b_potential_dot_dot;
+  } else if (mp->simulation_type != 1) {  // adjoint wavefield: minus the adjoint acceleration (compute_coupling_cuda.cu:71-82)
+    vec = mp->d_accel; sign = -1.f;
+  }
+  k_coupling_ac_el<<<nf, 32, 0, mp->compute_stream>>>(vec, pdd, nf, mp->d_coupling_ac_el_ispec,
                                                       mp->d_coupling_ac_el_ijk, mp->d_coupling_ac_el_normal,
-                                                      mp->d_coupling_ac_el_jacobian2Dw, mp->d_ibool, (size_t)mp->NGLOB_AB);
+                                                      mp->d_coupling_ac_el_jacobian2Dw, mp->d_ibool, (size_t)mp->NGLOB_AB, sign);
   KERNEL_CHECK(mp, "k_coupling_ac_el");
 }
 
 extern "C" void SB200_FC(compute_coupling_el_ac_cuda)(long* Mesh_pointer, int* iphasef, int* num_coupling_ac_el_facesf,
                                                       int* FORWARD_OR_ADJOINT) {
   DeviceMesh* mp = get_mesh(Mesh_pointer);
-  if (*FORWARD_OR_ADJOINT != 1) exit_on_error("compute_coupling_el_ac_cuda: only FORWARD_OR_ADJOINT = 1 is supported");
+  if (*FORWARD_OR_ADJOINT != 1 && *FORWARD_OR_ADJOINT != 3) exit_on_error("compute_coupling_el_ac_cuda: FORWARD_OR_ADJOINT must be 1 or 3");
   if (*iphasef != 1) return;
   const int nf = *num_coupling_ac_el_facesf;
   if (nf == 0) return;
-  k_coupling_el_ac<<<nf, 32, 0, mp->compute_stream>>>(mp->d_potential_dot_dot, mp->d_accel, nf, mp->d_coupling_ac_el_ispec,
+  const realw* pot = mp->d_potential_dot_dot;
+  realw* acc = mp->d_accel;
+  realw sign = 1.f;
+  if (*FORWARD_OR_ADJOINT == 3) {
+    require_backward_fields(mp, "compute_coupling_el_ac_cuda");
+    require_backward_potentials(mp, "compute_coupling_el_ac_cuda");
+    pot = mp->d_b_potential_dot_dot; acc = mp->d_b_accel;
+  } else if (mp->simulation_type != 1) {  // adjoint wavefield: pressure^dagger = potential^dagger (compute_coupling_cuda.cu:170-177)
+    pot = mp->d_potential; sign = -1.f;
+  }
+  k_coupling_el_ac<<<nf, 32, 0, mp->compute_stream>>>(pot, acc, nf, mp->d_coupling_ac_el_ispec,
                                                       mp->d_coupling_ac_el_ijk, mp->d_coupling_ac_el_normal,
-                                                      mp->d_coupling_ac_el_jacobian2Dw, mp->d_ibool, (size_t)mp->NGLOB_AB);
+                                                      mp->d_coupling_ac_el_jacobian2Dw, mp->d_ibool, (size_t)mp->NGLOB_AB, sign);
   KERNEL_CHECK(mp, "k_coupling_el_ac");
 }
 
@@ -1243,8 +1314,20 @@ extern "C" void SB200_FC(transfer_asmbl_accel_to_device)(long* Mesh_pointer, rea
 extern "C" void SB200_FC(transfer_boun_pot_from_device)(long* Mesh_pointer, field* send_potential_dot_dot_buffer,
                                                         const int* FORWARD_OR_ADJOINT) {
   DeviceMesh* mp = get_mesh(Mesh_pointer);
-  if (*FORWARD_OR_ADJOINT != 1) exit_on_error("transfer_boun_pot_from_device: only FORWARD_OR_ADJOINT = 1 is supported");
+  if (*FORWARD_OR_ADJOINT != 1 && *FORWARD_OR_ADJOINT != 3) exit_on_error("transfer_boun_pot_from_device: FORWARD_OR_ADJOINT must be 1 or 3");
   if (mp->size_mpi_buffer_potential <= 0) return;
+  if (*FORWARD_OR_ADJOINT == 3) {
+    require_backward_potentials(mp, "transfer_boun_pot_from_device");
+    k_halo_pack<1><<<halo_grid(mp), 256, 0, mp->compute_stream>>>(mp->d_b_potential_dot_dot, mp->d_b_send_potential_buffer,
+                                                                  mp->num_interfaces_ext_mesh, mp->max_nibool_interfaces_ext_mesh,
+                                                                  mp->d_nibool_interfaces_ext_mesh, mp->d_ibool_interfaces_ext_mesh,
+                                                                  (size_t)mp->NGLOB_AB);
+    KERNEL_CHECK(mp, "k_halo_pack<1>(backward)");
+    CUDA_CHECK(cudaMemcpyAsync(send_potential_dot_dot_buffer, mp->d_b_send_potential_buffer,
+                               mp->size_mpi_buffer_potential * sizeof(realw), cudaMemcpyDeviceToHost, mp->compute_stream));
+    CUDA_CHECK(cudaStreamSynchronize(mp->compute_stream));
+    return;
+  }
   if (p2p_active(mp)) {
     p2p_pack_put(mp, 1, mp->d_potential_dot_dot);
     return;
@@ -1261,8 +1344,20 @@ extern "C" void SB200_FC(transfer_boun_pot_from_device)(long* Mesh_pointer, fiel
 extern "C" void SB200_FC(transfer_asmbl_pot_to_device)(long* Mesh_pointer, field* buffer_recv_scalar_ext_mesh,
                                                        const int* FORWARD_OR_ADJOINT) {
   DeviceMesh* mp = get_mesh(Mesh_pointer);
-  if (*FORWARD_OR_ADJOINT != 1) exit_on_error("transfer_asmbl_pot_to_device: only FORWARD_OR_ADJOINT = 1 is supported");
+  if (*FORWARD_OR_ADJOINT != 1 && *FORWARD_OR_ADJOINT != 3) exit_on_error("transfer_asmbl_pot_to_device: FORWARD_OR_ADJOINT must be 1 or 3");
   if (mp->size_mpi_buffer_potential <= 0) return;
+  if (*FORWARD_OR_ADJOINT == 3) {
+    require_backward_potentials(mp, "transfer_asmbl_pot_to_device");
+    CUDA_CHECK(cudaMemcpyAsync(mp->d_b_send_potential_buffer, buffer_recv_scalar_ext_mesh,
+                               mp->size_mpi_buffer_potential * sizeof(realw), cudaMemcpyHostToDevice, mp->compute_stream));
+    k_halo_unpack_add<1><<<halo_grid(mp), 256, 0, mp->compute_stream>>>(mp->d_b_potential_dot_dot, mp->d_b_send_potential_buffer,
+                                                                        mp->num_interfaces_ext_mesh, mp->max_nibool_interfaces_ext_mesh,
+                                                                        mp->d_nibool_interfaces_ext_mesh,
+                                                                        mp->d_ibool_interfaces_ext_mesh, (size_t)mp->NGLOB_AB);
+    KERNEL_CHECK(mp, "k_halo_unpack_add<1>(backward)");
+    CUDA_CHECK(cudaStreamSynchronize(mp->compute_stream));
+    return;
+  }
   if (p2p_active(mp)) {
     p2p_wait_unpack(mp, 1, mp->d_potential_dot_dot);
     return;
@@ -1292,6 +1387,7 @@ extern "C" void SB200_FC(compute_seismograms_cuda)(long* Mesh_pointer_f, realw* 
   if (mp->nrec_local == 0) return;
   // kernel runs record the reconstructed forward wavefield (write_seismograms_cuda.cu:100-118)
   const bool b3 = mp->simulation_type == 3 && mp->d_b_displ != nullptr;
+  const bool b3p = mp->simulation_type == 3 && mp->d_b_potential != nullptr;
   if (b3 && mp->b_corrector_pending && (mp->save_seismograms_v || mp->save_seismograms_a)) flush_corrector_impl(mp);
   const int pend = (!b3 && mp->corrector_pending) ? 1 : 0;
   const int seismo_current = *seismo_currentf - 1;
@@ -1299,9 +1395,9 @@ extern "C" void SB200_FC(compute_seismograms_cuda)(long* Mesh_pointer_f, realw* 
   if (nlength != mp->nlength_seismogram) exit_on_error("compute_seismograms_cuda: nlength_seismogram differs from prepare_constants_device");
   if (seismo_current < 0 || seismo_current >= nlength) exit_on_error("compute_seismograms_cuda: seismo_current out of range");
   struct { int on; const realw* vec; const realw* pot; realw* out; int corr_mode; } sets[3] = {
-      {mp->save_seismograms_d, b3 ? mp->d_b_displ : mp->d_displ, mp->d_potential, mp->d_seismograms_d, 0},
-      {mp->save_seismograms_v, b3 ? mp->d_b_veloc : mp->d_veloc, mp->d_potential_dot, mp->d_seismograms_v, pend * 1},
-      {mp->save_seismograms_a, b3 ? mp->d_b_accel : mp->d_accel, mp->d_potential_dot_dot, mp->d_seismograms_a, pend * 2}};
+      {mp->save_seismograms_d, b3 ? mp->d_b_displ : mp->d_displ, b3p ? mp->d_b_potential : mp->d_potential, mp->d_seismograms_d, 0},
+      {mp->save_seismograms_v, b3 ? mp->d_b_veloc : mp->d_veloc, b3p ? mp->d_b_potential_dot : mp->d_potential_dot, mp->d_seismograms_v, pend * 1},
+      {mp->save_seismograms_a, b3 ? mp->d_b_accel : mp->d_accel, b3p ? mp->d_b_potential_dot_dot : mp->d_potential_dot_dot, mp->d_seismograms_a, pend * 2}};
   for (auto& s : sets) {
     if (!s.on) continue;
     k_seismogram_vector<<<mp->nrec_local, NGLL3_PADDED, 0, mp->compute_stream>>>(
@@ -1312,9 +1408,10 @@ extern "C" void SB200_FC(compute_seismograms_cuda)(long* Mesh_pointer_f, realw* 
     KERNEL_CHECK(mp, "k_seismogram_vector");
   }
   if (mp->save_seismograms_p) {
-    const realw* pot = *USE_TRICK_FOR_BETTER_PRESSURE ? mp->d_potential : mp->d_potential_dot_dot;
+    const realw* pot = b3p ? (*USE_TRICK_FOR_BETTER_PRESSURE ? mp->d_b_potential : mp->d_b_potential_dot_dot)
+                           : (*USE_TRICK_FOR_BETTER_PRESSURE ? mp->d_potential : mp->d_potential_dot_dot);
     k_seismogram_pressure<<<mp->nrec_local, NGLL3_PADDED, 0, mp->compute_stream>>>(
-        mp->nrec_local, pot, mp->d_displ, mp->d_ibool, mp->d_hxir, mp->d_hetar, mp->d_hgammar, mp->d_seismograms_p,
+        mp->nrec_local, pot, b3 ? mp->d_b_displ : mp->d_displ, mp->d_ibool, mp->d_hxir, mp->d_hetar, mp->d_hgammar, mp->d_seismograms_p,
         mp->d_ispec_selected_rec_loc, mp->d_ispec_is_acoustic, mp->d_ispec_is_elastic, mp->d_kappav, mp->d_muv, mp->d_metric,
         mp->d_irregular_element_number, mp->xix_regular, seismo_current, (size_t)mp->NGLOB_AB);
     KERNEL_CHECK(mp, "k_seismogram_pressure");
@@ -1366,8 +1463,9 @@ extern "C" void SB200_FC(get_norm_elastic_from_device)(realw* norm, long* Mesh_p
 
 extern "C" void SB200_FC(get_norm_acoustic_from_device)(realw* norm, long* Mesh_pointer, int* sim_type) {
   DeviceMesh* mp = get_mesh(Mesh_pointer);
-  if (*sim_type != 1) exit_on_error("get_norm_acoustic_from_device: only the forward wavefield (type 1) is supported");
-  *norm = max_norm<false>(mp, mp->d_potential_dot_dot);
+  if (*sim_type != 1 && *sim_type != 3) exit_on_error("get_norm_acoustic_from_device: type must be 1 or 3");
+  if (*sim_type == 3) require_backward_potentials(mp, "get_norm_acoustic_from_device");
+  *norm = max_norm<false>(mp, *sim_type == 1 ? mp->d_potential_dot_dot : mp->d_b_potential_dot_dot);
 }
 
 #include "adjoint.inc"

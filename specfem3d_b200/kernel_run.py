@@ -8,10 +8,11 @@ sensitivity kernels rho_kl / mu_kl / kappa_kl.  Re
 * compute_add_sources_viscoelastic_GPU                src/specfem3D/compute_add_sources_viscoelastic.F90:469-726
 * compute_stacey_viscoelastic_GPU                     src/specfem3D/compute_stacey_viscoelastic.F90:420-480
 * read_forward_arrays / save_forward_arrays           src/specfem3D/read_forward_arrays.f90, save_forward_arrays.f90
-* compute_kernels_el (GPU branch)                     src/specfem3D/compute_kernels.f90:60-200
+* compute_forces_acoustic_GPU_calling                 src/specfem3D/compute_forces_acoustic_calling_routine.f90:597-748
+* compute_kernels_el / _ac (GPU branches)             src/specfem3D/compute_kernels.f90:60-340
 * it_transfer_from_GPU                                src/specfem3D/iterate_time.F90:381-445
 
-Elastic domains, no attenuation, no C-PML (the library aborts on the others).  What the Fortran solver keeps in files
+Elastic, acoustic and coupled domains; no attenuation, no C-PML (the library aborts on those).  What the Fortran solver keeps in files
 between the two runs (``proc*_absorb_field.bin``, ``proc*_save_forward_arrays.bin``, ``SEM/*.adj``) is kept in memory in
 a :class:`ForwardProducts` object.
 """
@@ -27,9 +28,10 @@ from .time_loop import DeviceRank, DeviceRun
 
 @dataclass
 class ForwardProducts:
-    """Per rank: absorbed Stacey tractions of every step ([it-1] -> (nfaces, 25, 3)) and the last frame."""
+    """Per rank: absorbed Stacey tractions / fluxes of every step ([it-1] -> (nfaces, 25, 3) / (nfaces, 25)) and the last frame."""
     absorb: List[List[np.ndarray]] = field(default_factory=list)
     last: List[dict] = field(default_factory=list)
+    absorb_potential: List[List[np.ndarray]] = field(default_factory=list)
 
 
 def run_forward_and_save(sim, lib=None, halo: str = "host"):
@@ -39,21 +41,27 @@ def run_forward_and_save(sim, lib=None, halo: str = "host"):
     prod = ForwardProducts()
     for r in run.ranks:
         prod.absorb.append(list(r.absorb_history))
-        d, v, a = r.fields_el()  # it_transfer_from_GPU + save_forward_arrays
-        prod.last.append(dict(displ=d, veloc=v, accel=a))
+        prod.absorb_potential.append(list(r.absorb_potential_history))
+        last = {}
+        if r.ELASTIC:  # it_transfer_from_GPU + save_forward_arrays
+            last["displ"], last["veloc"], last["accel"] = r.fields_el()
+        if r.ACOUSTIC:
+            last["pot"], last["pot_dot"], last["pot_dot_dot"] = r.fields_ac()
+        prod.last.append(last)
     return run, prod
 
 
 class KernelRun(DeviceRun):
     """iterate_time with SIMULATION_TYPE == 3.  ``adj``: (nrec, NSTEP, 3) adjoint source time series in forward time
-    order and mesh x / y / z components (the content of the ``NET.STA.BX?.adj`` files after the rotation by nu_rec)."""
+    order and mesh x / y / z components (the content of the ``NET.STA.BX?.adj`` files after the rotation by nu_rec);
+    receivers in the fluid use the first component only (compute_add_sources_acoustic.f90:233)."""
 
     def __init__(self, sim, products: ForwardProducts, adj: np.ndarray, lib=None, halo: str = "host"):
         assert sim.SIMULATION_TYPE == 3 and not sim.SAVE_FORWARD
-        if sim.ACOUSTIC_SIMULATION or sim.ATTENUATION or sim.PML_CONDITIONS:
-            raise NotImplementedError("kernel runs: elastic domains without attenuation / C-PML only")
+        if sim.ATTENUATION or sim.PML_CONDITIONS:
+            raise NotImplementedError("kernel runs: no attenuation / C-PML")
         if halo != "host":
-            raise NotImplementedError("kernel runs exchange b_accel through the host-staged halo")
+            raise NotImplementedError("kernel runs exchange the b_ fields through the host-staged halo")
         super().__init__(sim, lib=lib, halo=halo)
         self.products = products
         adj = np.asarray(adj, np.float32)
@@ -64,27 +72,76 @@ class KernelRun(DeviceRun):
             r.source_adjoint = np.ascontiguousarray(np.transpose(adj[loc], (1, 0, 2))) if len(loc) else np.zeros((sim.NSTEP, 1, 3), np.float32)
             n = r.db.NSPEC_AB
             r.rho_kl, r.mu_kl, r.kappa_kl = (np.zeros((n, 5, 5, 5), np.float32) for _ in range(3))
+            r.rho_ac_kl, r.kappa_ac_kl = (np.zeros((n, 5, 5, 5), np.float32) for _ in range(2))
+        # prepare_timerun.F90:425-430: b_deltat = - real(DT), b_deltatover2 = b_deltat/2, b_deltatsqover2 = b_deltat**2/2
+        bdt = np.float32(-sim.deltat)
+        self.dts = (float(sim.deltat), float(sim.deltatover2), float(sim.deltatsqover2))
+        self.b_dts = (float(bdt), float(np.float32(bdt / np.float32(2))), float(np.float32(bdt * bdt / np.float32(2))))
 
     # --------------------------------------------------------------------------------------------------------------
     def step(self):
         sim = self.sim
         self.it += 1
         it = self.it
-        NSTEP = sim.NSTEP
-        dt, dt2, dtsq2 = float(sim.deltat), float(sim.deltatover2), float(sim.deltatsqover2)
-        # prepare_timerun.F90:425-430: b_deltat = - real(DT), b_deltatover2 = b_deltat/2, b_deltatsqover2 = b_deltat**2/2
-        bdt = np.float32(-sim.deltat)
-        b_dt, b_dt2, b_dtsq2 = float(bdt), float(np.float32(bdt / np.float32(2))), float(np.float32(bdt * bdt / np.float32(2)))
-        E = self.ranks
+        dt, dt2, dtsq2 = self.dts
+        b_dt, b_dt2, b_dtsq2 = self.b_dts
+        for r in self.ranks:  # update_displ_Newmark, then update_displ_Newmark_backward
+            if r.ACOUSTIC:
+                r.lib.update_displacement_ac_cuda(r.Mesh_pointer, dt, dt2, dtsq2, 1)
+            if r.ELASTIC:
+                r.lib.update_displacement_cuda(r.Mesh_pointer, dt, dt2, dtsq2, 1)
+        for r in self.ranks:
+            if r.ACOUSTIC:
+                r.lib.update_displacement_ac_cuda(r.Mesh_pointer, b_dt, b_dt2, b_dtsq2, 3)
+            if r.ELASTIC:
+                r.lib.update_displacement_cuda(r.Mesh_pointer, b_dt, b_dt2, b_dtsq2, 3)
+        if sim.ELASTIC_SIMULATION and sim.ACOUSTIC_SIMULATION:
+            # coupled: the combined routines are not used (compute_forces_viscoelastic_calling_routine.F90:61-67); adjoint
+            # wavefield elastic first, then acoustic; reconstructed wavefield acoustic first, then elastic.  (In this
+            # branch the Fortran GPU path reaches compute_add_sources_el_s3_cuda twice per step -- from
+            # compute_add_sources_viscoelastic_GPU and from ..._backward_GPU; the CPU path adds the source once, which is
+            # what is restated here.)
+            self._elastic(it, (1,))
+            self._acoustic(it, (1,))
+            self._acoustic(it, (3,))
+            self._elastic(it, (3,))
+        else:
+            if sim.ACOUSTIC_SIMULATION:
+                self._acoustic(it, (0,))
+            if sim.ELASTIC_SIMULATION:
+                self._elastic(it, (0,))
+        if it == 1:  # read_forward_arrays: the last frame of the forward run replaces the b_ fields after the first step
+            for ir, r in enumerate(self.ranks):
+                f, n = self.products.last[ir], r.db.NGLOB_AB
+                if r.ACOUSTIC:
+                    r.lib.transfer_b_fields_ac_to_device(n, f["pot"], f["pot_dot"], f["pot_dot_dot"], r.Mesh_pointer)
+                if r.ELASTIC:
+                    r.lib.transfer_b_fields_to_device(3 * n, f["displ"], f["veloc"], f["accel"], r.Mesh_pointer)
+        if sim.receivers is not None and (it - 1) % sim.NTSTEP_BETWEEN_OUTPUT_SAMPLE == 0:
+            self._seismograms(it)
+        for r in self.ranks:  # compute_kernels
+            if r.ACOUSTIC:
+                r.lib.compute_kernels_acoustic_cuda(r.Mesh_pointer, dt)
+            if r.ELASTIC:
+                r.lib.compute_kernels_elastic_cuda(r.Mesh_pointer, dt)
+                if sim.APPROXIMATE_HESS_KL:
+                    r.lib.compute_kernels_hess_cuda(r.Mesh_pointer, dt, 1, 0)
+
+    def _elastic(self, it: int, foas):
+        """foas = (0,): compute_forces_viscoelastic_GPU_calling (both wavefields); (1,) / (3,): the separate routines."""
+        sim, NSTEP = self.sim, self.sim.NSTEP
+        dt, dt2, _ = self.dts
+        b_dt, b_dt2, _ = self.b_dts
+        E = [r for r in self.ranks if r.ELASTIC]
         multi = self.NPROC > 1
-        for r in E:
-            r.lib.update_displacement_cuda(r.Mesh_pointer, dt, dt2, dtsq2, 1)
-            r.lib.update_displacement_cuda(r.Mesh_pointer, b_dt, b_dt2, b_dtsq2, 3)
+        both, fwd, bwd = foas == (0,), foas != (3,), foas != (1,)
+        foa = foas[0]
         for iphase in (1, 2):
             for r in E:
-                db, L, M = r.db, r.lib, r.Mesh_pointer
-                L.compute_forces_viscoelastic_cuda(M, iphase, dt, db.nspec_outer_elastic, db.nspec_inner_elastic, 1, 0, 0)
-            if multi and iphase == 2:
+                db = r.db
+                r.lib.compute_forces_viscoelastic_cuda(r.Mesh_pointer, iphase, b_dt if foa == 3 else dt, db.nspec_outer_elastic,
+                                                       db.nspec_inner_elastic, 1, 0, foa)
+            if multi and iphase == 2 and fwd:
                 for r in E:
                     r.lib.sync_copy_from_device(r.Mesh_pointer, iphase, r.buffer_send_vector)
                 self.exchange.exchange("vector")
@@ -92,41 +149,102 @@ class KernelRun(DeviceRun):
                     r.lib.transfer_boundary_to_device_a(r.Mesh_pointer, r.buffer_recv_vector, r.db.num_interfaces_ext_mesh,
                                                         r.db.max_nibool_interfaces_ext_mesh)
             if iphase == 1:
-                for ir, r in enumerate(E):
+                for ir, r in enumerate(self.ranks):
+                    if not r.ELASTIC:
+                        continue
                     db, L, M = r.db, r.lib, r.Mesh_pointer
                     if sim.spec.stacey:
-                        if db.num_abs_boundary_faces > 0:  # read_abs(IOABS, b_absorb_field, b_reclen_field, NSTEP-it+1)
+                        if bwd and db.num_abs_boundary_faces > 0:  # read_abs(IOABS, b_absorb_field, b_reclen_field, NSTEP-it+1)
                             r.b_absorb_field[...] = self.products.absorb[ir][NSTEP - it]
-                        L.compute_stacey_viscoelastic_cuda(M, iphase, r.b_absorb_field, 0)
-                    if r.nrec_local > 0 and it < NSTEP:
+                        L.compute_stacey_viscoelastic_cuda(M, iphase, r.b_absorb_field, foa)
+                    if sim.ACOUSTIC_SIMULATION and db.num_coupling_ac_el_faces > 0:
+                        L.compute_coupling_el_ac_cuda(M, iphase, db.num_coupling_ac_el_faces, foa)
+                    if fwd and r.nrec_local > 0 and it < NSTEP:
                         L.add_sources_el_sim_type_2_or_3(M, r.source_adjoint, sim.receivers.nrec, r.nrec_local, NSTEP, it)
-                    if sim.sources is not None:
+                    if bwd and sim.sources is not None:
                         L.compute_add_sources_el_s3_cuda(M, sim.stf_pre_compute(NSTEP - it + 1), sim.sources.NSOURCES)
                     if multi:
-                        L.transfer_boundary_from_device_a(M, db.nspec_outer_elastic)
-                        L.transfer_boun_accel_from_device(M, r.b_buffer_send_vector, 3)
-                if multi:
+                        if fwd:
+                            L.transfer_boundary_from_device_a(M, db.nspec_outer_elastic)
+                        if bwd:
+                            L.transfer_boun_accel_from_device(M, r.b_buffer_send_vector, 3)
+                if multi and bwd:
                     self.exchange.exchange("b_vector")
             elif multi:
                 for r in E:
                     db = r.db
                     args = (db.num_interfaces_ext_mesh, db.max_nibool_interfaces_ext_mesh, db.nibool_interfaces_ext_mesh,
                             db.ibool_interfaces_ext_mesh)
-                    r.lib.transfer_asmbl_accel_to_device(r.Mesh_pointer, r.buffer_recv_vector, *args, 1)
-                    r.lib.transfer_asmbl_accel_to_device(r.Mesh_pointer, r.b_buffer_recv_vector, *args, 3)
+                    if fwd:
+                        r.lib.transfer_asmbl_accel_to_device(r.Mesh_pointer, r.buffer_recv_vector, *args, 1)
+                    if bwd:
+                        r.lib.transfer_asmbl_accel_to_device(r.Mesh_pointer, r.b_buffer_recv_vector, *args, 3)
         for r in E:
-            r.lib.kernel_3_a_cuda(r.Mesh_pointer, dt2, b_dt2, 0, 1)
-            r.lib.kernel_3_a_cuda(r.Mesh_pointer, dt2, b_dt2, 0, 3)
-        if it == 1:  # read_forward_arrays: the last frame of the forward run replaces the b_ fields after the first step
-            for ir, r in enumerate(E):
-                f = self.products.last[ir]
-                r.lib.transfer_b_fields_to_device(3 * r.db.NGLOB_AB, f["displ"], f["veloc"], f["accel"], r.Mesh_pointer)
-        if sim.receivers is not None and (it - 1) % sim.NTSTEP_BETWEEN_OUTPUT_SAMPLE == 0:
-            self._seismograms(it)
-        for r in E:  # compute_kernels
-            r.lib.compute_kernels_elastic_cuda(r.Mesh_pointer, dt)
-            if sim.APPROXIMATE_HESS_KL:
-                r.lib.compute_kernels_hess_cuda(r.Mesh_pointer, dt, 1, 0)
+            if fwd:
+                r.lib.kernel_3_a_cuda(r.Mesh_pointer, dt2, b_dt2, 0, 1)
+            if bwd:
+                r.lib.kernel_3_a_cuda(r.Mesh_pointer, dt2, b_dt2, 0, 3)
+        del both
+
+    def _acoustic(self, it: int, foas):
+        """foas = (0,): compute_forces_acoustic_GPU_calling (compute_forces_acoustic_calling_routine.f90:597-748);
+        (1,) / (3,): compute_forces_acoustic_forward_calling / _backward_calling of a coupled run."""
+        sim, NSTEP = self.sim, self.sim.NSTEP
+        _, dt2, _ = self.dts
+        _, b_dt2, _ = self.b_dts
+        A = [r for r in self.ranks if r.ACOUSTIC]
+        multi = self.NPROC > 1
+        fwd, bwd = foas != (3,), foas != (1,)
+        foa = foas[0]
+        sifs = int(sim.spec.stacey_instead_of_free_surface)
+        for r in A:
+            if fwd:
+                r.lib.acoustic_enforce_free_surf_cuda(r.Mesh_pointer, sifs, 1)
+            if bwd:
+                r.lib.acoustic_enforce_free_surf_cuda(r.Mesh_pointer, sifs, 3)
+        for iphase in (1, 2):
+            for ir, r in enumerate(self.ranks):
+                if not r.ACOUSTIC:
+                    continue
+                db, L, M = r.db, r.lib, r.Mesh_pointer
+                L.compute_forces_acoustic_cuda(M, iphase, db.nspec_outer_acoustic, db.nspec_inner_acoustic, foa)
+                if iphase == 1:
+                    if sim.spec.stacey:
+                        if bwd and db.num_abs_boundary_faces > 0:
+                            r.b_absorb_potential[...] = self.products.absorb_potential[ir][NSTEP - it]
+                        L.compute_stacey_acoustic_cuda(M, iphase, r.b_absorb_potential, foa)
+                    if sim.ELASTIC_SIMULATION:
+                        if fwd:
+                            L.compute_coupling_ac_el_cuda(M, iphase, db.num_coupling_ac_el_faces, 1)
+                        if bwd:
+                            L.compute_coupling_ac_el_cuda(M, iphase, db.num_coupling_ac_el_faces, 3)
+                    if fwd and r.nrec_local > 0 and it < NSTEP:
+                        L.add_sources_ac_sim_2_or_3_cuda(M, r.source_adjoint, sim.receivers.nrec, r.nrec_local, NSTEP, it)
+                    if bwd and sim.sources is not None:
+                        L.compute_add_sources_ac_s3_cuda(M, sim.sources.NSOURCES, sim.stf_pre_compute_acoustic(NSTEP - it + 1),
+                                                         np.zeros(sim.sources.NSOURCES, np.int32))
+            if multi:
+                if iphase == 1:
+                    if fwd:
+                        for r in A:
+                            r.lib.transfer_boun_pot_from_device(r.Mesh_pointer, r.buffer_send_scalar, 1)
+                        self.exchange.exchange("scalar")
+                    if bwd:
+                        for r in A:
+                            r.lib.transfer_boun_pot_from_device(r.Mesh_pointer, r.b_buffer_send_scalar, 3)
+                        self.exchange.exchange("b_scalar")
+                else:
+                    for r in A:
+                        if fwd:
+                            r.lib.transfer_asmbl_pot_to_device(r.Mesh_pointer, r.buffer_recv_scalar, 1)
+                        if bwd:
+                            r.lib.transfer_asmbl_pot_to_device(r.Mesh_pointer, r.b_buffer_recv_scalar, 3)
+        for r in A:
+            r.lib.kernel_3_acoustic_cuda(r.Mesh_pointer, dt2, b_dt2, foa)
+            if fwd:
+                r.lib.acoustic_enforce_free_surf_cuda(r.Mesh_pointer, sifs, 1)
+            if bwd:
+                r.lib.acoustic_enforce_free_surf_cuda(r.Mesh_pointer, sifs, 3)
 
     # --------------------------------------------------------------------------------------------------------------
     def b_fields(self, rank: int):
@@ -136,14 +254,31 @@ class KernelRun(DeviceRun):
         r.lib.transfer_b_fields_from_device(3 * n, d, v, a, r.Mesh_pointer)
         return d, v, a
 
+    def b_fields_ac(self, rank: int):
+        r = self.ranks[rank]
+        n = r.db.NGLOB_AB
+        p, pd, pdd = (np.zeros(n, np.float32) for _ in range(3))
+        r.lib.transfer_b_fields_ac_from_device(n, p, pd, pdd, r.Mesh_pointer)
+        return p, pd, pdd
+
     def kernels(self):
         """it_transfer_from_GPU: [(rho_kl, mu_kl, kappa_kl)] per rank, each (NSPEC, 5, 5, 5) raw interaction integrals
         (the sign / material scaling of save_adjoint_kernels is host post-processing)."""
         out = []
         dummy = np.zeros(1, np.float32)
         for r in self.ranks:
-            r.lib.transfer_kernels_el_to_host(r.Mesh_pointer, r.rho_kl, r.mu_kl, r.kappa_kl, dummy, r.db.NSPEC_AB)
+            if r.ELASTIC:
+                r.lib.transfer_kernels_el_to_host(r.Mesh_pointer, r.rho_kl, r.mu_kl, r.kappa_kl, dummy, r.db.NSPEC_AB)
             out.append((r.rho_kl, r.mu_kl, r.kappa_kl))
+        return out
+
+    def kernels_ac(self):
+        """[(rho_ac_kl, kappa_ac_kl)] per rank."""
+        out = []
+        for r in self.ranks:
+            if r.ACOUSTIC:
+                r.lib.transfer_kernels_ac_to_host(r.Mesh_pointer, r.rho_ac_kl, r.kappa_ac_kl, r.db.NSPEC_AB)
+            out.append((r.rho_ac_kl, r.kappa_ac_kl))
         return out
 
     def hess_kernels(self):

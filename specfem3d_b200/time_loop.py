@@ -67,6 +67,10 @@ class DeviceRank:
         self.b_buffer_send_vector = np.zeros((max(ni, 1), mx, 3), np.float32)
         self.b_buffer_recv_vector = np.zeros((max(ni, 1), mx, 3), np.float32)
         self.absorb_history: List[np.ndarray] = []  # SAVE_FORWARD: what proc*_absorb_field.bin would hold
+        self.absorb_potential_history: List[np.ndarray] = []  # ... and proc*_absorb_potential.bin
+        self.b_absorb_potential = np.zeros((1, 25), np.float32)
+        self.b_buffer_send_scalar = np.zeros((max(ni, 1), mx), np.float32)
+        self.b_buffer_recv_scalar = np.zeros((max(ni, 1), mx), np.float32)
         self.b_absorb_field = np.zeros((1, 25, 3), np.float32)
 
     # --------------------------------------------------------------------------------------------------------------
@@ -125,11 +129,17 @@ class DeviceRank:
             col[dom] = (int(db.extra.get("num_colors_outer_" + dom, 0)), int(db.extra.get("num_colors_inner_" + dom, 0)),
                         H["num_elem_colors_" + dom])
         if self.ACOUSTIC:
+            # b_absorb_potential(NGLLSQUARE,num_abs_boundary_faces): one record of proc*_absorb_potential.bin
+            self.b_reclen_potential = 4 * 25 * db.num_abs_boundary_faces
+            self.b_absorb_potential = np.zeros((max(db.num_abs_boundary_faces, 1), 25), np.float32)
             L.prepare_fields_acoustic_device(
                 self.Mesh_pointer, db.rmass_acoustic, db.rhostore, db.kappastore, db.num_phase_ispec_acoustic,
                 db.phase_ispec_inner_acoustic, 0, db.num_free_surface_faces, db.free_surface_ispec, db.free_surface_ijk,
-                0, dummy, int(sim.ELASTIC_SIMULATION), db.num_coupling_ac_el_faces, db.coupling_ac_el_ispec,
-                db.coupling_ac_el_ijk, db.coupling_ac_el_normal, db.coupling_ac_el_jacobian2Dw, *col["acoustic"])
+                self.b_reclen_potential, self.b_absorb_potential, int(sim.ELASTIC_SIMULATION), db.num_coupling_ac_el_faces,
+                db.coupling_ac_el_ispec, db.coupling_ac_el_ijk, db.coupling_ac_el_normal, db.coupling_ac_el_jacobian2Dw,
+                *col["acoustic"])
+            if sim.SIMULATION_TYPE == 3:
+                L.prepare_fields_acoustic_adj_dev(self.Mesh_pointer, 0)
         if self.ELASTIC:
             att = sim.att[self.rank] if sim.att is not None else None
             nspec = db.NSPEC_AB
@@ -171,8 +181,9 @@ class DeviceRank:
                     self.Mesh_pointer, 3 * db.NGLOB_AB, z, z, z, z, z, z, z, R_size, *([dummy] * 7),
                     np.zeros(N_SLS, np.float32), np.zeros(N_SLS, np.float32), np.zeros(N_SLS, np.float32), 0,
                     int(sim.APPROXIMATE_HESS_KL))
-                L.prepare_sim2_or_3_const_device(self.Mesh_pointer, self.nrec_local, sim.NSTEP, H["hxir"], H["hetar"],
-                                                 H["hgammar"], nrec, H["islice_rec"], H["ispec_rec"])
+        if sim.SIMULATION_TYPE == 3:  # prepare_gpu.f90:264-270
+            L.prepare_sim2_or_3_const_device(self.Mesh_pointer, self.nrec_local, sim.NSTEP, H["hxir"], H["hetar"],
+                                             H["hgammar"], nrec, H["islice_rec"], H["ispec_rec"])
         # initial wavefields (prepare_gpu.f90:296-306)
         n = db.NGLOB_AB
         init = sim.initial_fields[self.rank] if sim.initial_fields is not None else {}
@@ -226,6 +237,8 @@ class InProcessExchange:
                     nb.buffer_recv_vector[m, :cnt] = r.buffer_send_vector[n, :cnt]
                 elif kind == "b_vector":
                     nb.b_buffer_recv_vector[m, :cnt] = r.b_buffer_send_vector[n, :cnt]
+                elif kind == "b_scalar":
+                    nb.b_buffer_recv_scalar[m, :cnt] = r.b_buffer_send_scalar[n, :cnt]
                 else:
                     nb.buffer_recv_scalar[m, :cnt] = r.buffer_send_scalar[n, :cnt]
 
@@ -288,7 +301,9 @@ class DeviceRun:
                 L.compute_forces_acoustic_cuda(M, iphase, db.nspec_outer_acoustic, db.nspec_inner_acoustic, 1)
                 if iphase == 1:
                     if sim.spec.stacey:
-                        L.compute_stacey_acoustic_cuda(M, iphase, np.zeros(1, np.float32), 1)
+                        L.compute_stacey_acoustic_cuda(M, iphase, r.b_absorb_potential, 1)
+                        if sim.SAVE_FORWARD:  # write_abs(IOABS_AC, b_absorb_potential, b_reclen_potential, it)
+                            r.absorb_potential_history.append(r.b_absorb_potential.copy())
                     if sim.ELASTIC_SIMULATION:
                         L.compute_coupling_ac_el_cuda(M, iphase, db.num_coupling_ac_el_faces, 1)
                     if sim.sources is not None:

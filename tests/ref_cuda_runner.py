@@ -30,6 +30,8 @@ def factories():
         "cpml_regular": lambda: T.pml_sim(nstep=300, regular=True),
         "cfg3_small": lambda: T.cfg3_small(nstep=300),
         "kernel_run": lambda: kernel_run_case(),
+        "kernel_run_acoustic": lambda: kernel_run_case("acoustic"),
+        "kernel_run_coupled": lambda: kernel_run_case("coupled"),
     }
 
 
@@ -38,33 +40,62 @@ class kernel_run_case:
     NSTEP = 120
     SAVE_SEISMOGRAMS_PRESSURE = False
 
+    def __init__(self, kind="elastic"):
+        self.kind = kind
 
-def run_kernel_case(lib):
+
+def coupled_kernel_sim(nstep, sim_type):
+    """Water layer over an elastic halfspace (test_gpu_parity.ocean_sim), receivers in both media."""
+    import test_gpu_parity as T
+
+    sim = T.ocean_sim(nstep=nstep, source_in_water=True)  # both media must carry signal, or their kernels are round-off
+    sim.SAVE_SEISMOGRAMS_PRESSURE = False
+    sim.SIMULATION_TYPE, sim.SAVE_FORWARD = sim_type, sim_type == 1
+    return sim
+
+
+def run_kernel_case(lib, kind="elastic", adj_path=None):
+    """``adj_path``: .npy with the adjoint sources; written if it does not exist yet (the first library to run derives them
+    from its own forward seismograms, the second one must use the same bytes)."""
     import test_oracle_kernel_run as K
     from specfem3d_b200.kernel_run import KernelRun, run_forward_and_save
 
-    n = kernel_run_case.NSTEP
-    fwd, prod = run_forward_and_save(K.kernel_sim((1, 1), n), lib=lib)
-    seis = fwd.gather_seismograms("d")
-    # the adjoint source must be the same bytes for both libraries: an analytic wavelet per receiver and component
-    t = np.arange(n, dtype=np.float64) * 0.012
-    nrec = seis.shape[0]
-    adj = np.zeros((nrec, n, 3), np.float32)
-    for irec in range(nrec):
-        for c in range(3):
-            adj[irec, :, c] = 1e15 * np.sin(2 * np.pi * (1.5 + 0.4 * c) * t + 0.7 * irec) * np.exp(-((t - 0.7) / 0.3) ** 2)
-    k = KernelRun(K.kernel_sim((1, 1), n, sim_type=3), prod, adj, lib=lib).run()
-    rho, mu, kappa = k.kernels()[0]
-    out = {"d_forward": seis, "b_d": k.gather_seismograms("d"), "displ": k.ranks[0].fields_el()[0],
-           "rho_kl": rho.copy(), "mu_kl": mu.copy(), "kappa_kl": kappa.copy()}
+    n = 300 if kind == "coupled" else kernel_run_case.NSTEP  # coupled: time for the wave to cross the interface and reach both receivers
+    make = {"elastic": lambda st: K.kernel_sim((1, 1), n, sim_type=st), "acoustic": lambda st: K.acoustic_kernel_sim((1, 1), n, sim_type=st),
+            "coupled": lambda st: coupled_kernel_sim(n, st)}[kind]
+    which = "p" if kind == "acoustic" else "d"
+    sim1 = make(1)
+    fwd, prod = run_forward_and_save(sim1, lib=lib)
+    seis = fwd.gather_seismograms(which)
+    if adj_path is not None and os.path.exists(adj_path):
+        adj = np.load(adj_path)
+    else:
+        # waveform adjoint sources: the recorded traces, scaled so that the adjoint wavefield is O(1) in either medium
+        rec = sim1.receivers
+        adj = np.zeros(seis.shape, np.float32)
+        for irec in range(rec.nrec):
+            db = sim1.dbs[rec.islice_selected_rec[irec]]
+            in_fluid = bool(db.ispec_is_acoustic[rec.ispec_selected_rec[irec] - 1])
+            adj[irec] = ((1e3 if in_fluid else 1e15) / np.abs(seis[irec]).max()) * seis[irec]
+        if adj_path is not None:
+            np.save(adj_path, adj)
+    k = KernelRun(make(3), prod, adj, lib=lib).run()
+    out = {"d_forward": seis, "b_d": k.gather_seismograms(which)}
+    r = k.ranks[0]
+    if r.ELASTIC:
+        rho, mu, kappa = k.kernels()[0]
+        out.update(displ=r.fields_el()[0], rho_kl=rho.copy(), mu_kl=mu.copy(), kappa_kl=kappa.copy())
+    if r.ACOUSTIC:
+        rho_ac, kappa_ac = k.kernels_ac()[0]
+        out.update(pot=r.fields_ac()[0], rho_ac_kl=rho_ac.copy(), kappa_ac_kl=kappa_ac.copy())
     return k, out
 
 
-def run(sim, lib):
+def run(sim, lib, adj_path=None):
     from specfem3d_b200.time_loop import DeviceRun
 
     if isinstance(sim, kernel_run_case):
-        return run_kernel_case(lib)
+        return run_kernel_case(lib, sim.kind, adj_path)
 
     run = DeviceRun(sim, lib=lib).run()
     out = {"d": run.gather_seismograms("d")}
@@ -84,7 +115,7 @@ if __name__ == "__main__":
     name, path = sys.argv[1], sys.argv[2]
     sim = factories()[name]()
     lib = abi.DeviceLibrary(os.path.join(ROOT, "oracle", "_ref", "libspecfem_ref_cuda.so"))
-    _, out = run(sim, lib)
+    _, out = run(sim, lib, sys.argv[3] if len(sys.argv) > 3 else None)
     np.savez(path, **out)
     sys.stdout.flush()
     os._exit(0)  # skip the reference's cleanup (device reset) and any interpreter teardown after it

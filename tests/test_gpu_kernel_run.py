@@ -143,3 +143,82 @@ def test_approximate_hessian_kernels(device_lib, monkeypatch):
     for i, (a, b) in enumerate(zip(res[0], res[1])):
         # hess_kl = dt * sum accel . b_accel is a sum of terms of both signs that nearly cancel: looser bound
         assert rel_l2(a, b) <= (4 * KERNEL_RTOL if i == 0 else KERNEL_RTOL), i
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# acoustic domains
+# -------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nproc", [(1, 1), (2, 2)])
+def test_acoustic_kernel_run_matches_oracle(device_lib, nproc):
+    """Purely acoustic mesh: reconstructed potentials (Stacey flux replay, source at NSTEP - it, b_ halo), adjoint sources in
+    the fluid, rho_ac_kl / kappa_ac_kl against oracle/adjoint.py: OracleAcousticKernelRun."""
+    from oracle.adjoint import OracleAcousticKernelRun, OracleForwardRun
+    from specfem3d_b200.kernel_run import KernelRun, run_forward_and_save
+    from test_oracle_kernel_run import PRESSURE_RTOL, acoustic_adjoint_source, acoustic_kernel_sim
+
+    nstep = 120
+    ofwd = OracleForwardRun(acoustic_kernel_sim(nproc, nstep)).run()
+    adj = acoustic_adjoint_source(ofwd.seis_p)
+    ok = OracleAcousticKernelRun(acoustic_kernel_sim(nproc, nstep, sim_type=3), ofwd.record, adj).run()
+    fwd, prod = run_forward_and_save(acoustic_kernel_sim(nproc, nstep), lib=device_lib)
+    seis_fwd = fwd.gather_seismograms("p")[..., 0]
+    fwd.cleanup()
+    for r in range(len(prod.absorb_potential)):
+        a, b = np.stack(prod.absorb_potential[r]), np.stack(ofwd.record.absorb_potential[r])
+        assert a.shape == b.shape and rel_l2(a, b) <= 1e-4
+        assert rel_l2(prod.last[r]["pot"], ofwd.record.last[r]["pot"]) <= 1e-4
+    k = KernelRun(acoustic_kernel_sim(nproc, nstep, sim_type=3), prod, adj, lib=device_lib).run()
+    sk = k.gather_seismograms("p")[..., 0]
+    assert np.abs(seis_fwd).max() > 0
+    assert rel_l2(sk[:, 1:], seis_fwd[:, ::-1][:, 1:]) <= PRESSURE_RTOL
+    assert rel_l2(sk[:, 1:], ok.seis_p[:, 1:]) <= PRESSURE_RTOL
+    kernels = k.kernels_ac()
+    for r in range(len(kernels)):
+        assert rel_l2(k.ranks[r].fields_ac()[0], ok.parts[r].pot) <= 1e-4      # adjoint potential at the end of the run
+    # kernels over the whole mesh (a rank far from the interaction region holds only round-off)
+    for i, ref in enumerate((ok.rho_ac_kl, ok.kappa_ac_kl)):
+        mine = np.concatenate([kr[i].reshape(-1, 125) for kr in kernels])
+        ref = np.concatenate(ref)
+        assert np.abs(ref).max() > 0
+        assert rel_l2(mine, ref) <= 2 * KERNEL_RTOL, i
+    k.cleanup()
+
+
+def test_acoustic_kernel_arithmetic_two_steps(device_lib):
+    """Two steps from smooth O(1) potentials and no sources: flux replay, adjoint source in the fluid and the two acoustic
+    kernel integrands point by point (no round-off piled up yet)."""
+    from oracle.adjoint import ForwardRecord, OracleAcousticKernelRun
+    from specfem3d_b200.kernel_run import ForwardProducts, KernelRun
+    from test_gpu_parity import smooth_fields
+    from test_oracle_kernel_run import acoustic_kernel_sim
+
+    def sim3():
+        s = acoustic_kernel_sim((1, 1), 2, sim_type=3)
+        s.sources = None
+        s.initial_fields = smooth_fields(s, amp=1.0)
+        return s
+
+    s = sim3()
+    nfaces = s.dbs[0].num_abs_boundary_faces
+    rng = np.random.default_rng(7)
+    absorb = [(1e3 * rng.standard_normal((nfaces, 25))).astype(np.float32) for _ in range(2)]
+    last = {key: (0.6 * v[::-1]).copy() for key, v in smooth_fields(s, amp=1.0)[0].items()}
+    adj = (1e3 * rng.standard_normal((s.receivers.nrec, 2, 3))).astype(np.float32)
+    rec = ForwardRecord(1)
+    rec.absorb_potential[0], rec.last[0] = absorb, last
+    o = OracleAcousticKernelRun(sim3(), rec, adj)
+    for p, f in zip(o.parts, s.initial_fields):
+        for key, v in f.items():
+            getattr(p, key)[...] = v
+    o.run()
+    prod = ForwardProducts(absorb=[[]], last=[last], absorb_potential=[absorb])
+    k = KernelRun(sim3(), prod, adj, lib=device_lib).run()
+    rho_ac, kappa_ac = k.kernels_ac()[0]
+    n = rho_ac.shape[0]
+    for mine, ref in ((rho_ac, o.rho_ac_kl[0]), (kappa_ac, o.kappa_ac_kl[0])):
+        assert np.abs(ref).max() > 0
+        assert np.abs(mine.reshape(n, 125) - ref).max() <= 2e-5 * np.abs(ref).max()
+    bp, _, bpdd = k.b_fields_ac(0)
+    assert rel_l2(bp, o.bparts[0].pot) <= 1e-5 and rel_l2(bpdd, o.bparts[0].pot_dot_dot) <= 2e-5
+    assert rel_l2(k.ranks[0].fields_ac()[2], o.parts[0].pot_dot_dot) <= 2e-5
+    k.cleanup()

@@ -28,7 +28,8 @@ def rel_l2(a, b):
 
 
 @pytest.mark.parametrize("name", ["elastic_irregular", "elastic_regular", "viscoelastic", "ocean_source_in_solid",
-                                  "ocean_source_in_water", "cpml_irregular", "cpml_regular", "cfg3_small", "kernel_run"])
+                                  "ocean_source_in_water", "cpml_irregular", "cpml_regular", "cfg3_small", "kernel_run", "kernel_run_acoustic",
+                                  "kernel_run_coupled"])
 def test_against_reference_cuda_backend(device_lib, name, tmp_path):
     if not os.path.exists(REF_LIB):
         pytest.skip("oracle/_ref/libspecfem_ref_cuda.so not built (run oracle/build_ref_cuda.sh where /root/reference exists)")
@@ -40,24 +41,36 @@ def test_against_reference_cuda_backend(device_lib, name, tmp_path):
     # initialises the flags of features whose prepare_* routine is not called (gravity, noise, ...); under the Fortran
     # driver those bytes come from fresh zero pages, inside a Python process they are recycled heap garbage
     env = dict(os.environ, MALLOC_PERTURB_="255")
-    res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_cuda_runner.py"), name, out],
+    # kernel runs: the product library runs first and leaves its adjoint sources for the reference run to pick up
+    adj_path = str(tmp_path / "adj.npy")
+    sim = R.factories()[name]()
+    run, mine = R.run(sim, device_lib, adj_path)
+    run.cleanup()
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_cuda_runner.py"), name, out, adj_path],
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=env)
     assert res.returncode == 0 and os.path.exists(out), res.stdout[-3000:]
     ref = np.load(out)
-    sim = R.factories()[name]()
-    run, mine = R.run(sim, device_lib)
-    run.cleanup()
+    # tolerance per key; everything is evaluated before asserting so that a failure reports the whole picture
+    errs, bad = {}, []
     for key in ref.files:
         a, b = mine[key], ref[key]
         assert np.abs(b).max() > 0, key
-        if key in ("b_d", "rho_kl", "mu_kl", "kappa_kl"):
-            # kernel run: reconstructed seismograms and kernels carry the round-off of NSTEP steps forward and NSTEP back
-            # (tests/test_oracle_kernel_run.py: KERNEL_RTOL)
-            assert rel_l2(a, b) <= (5e-4 if key == "b_d" else 5e-3), key
+        if key in ("rho_kl", "mu_kl", "kappa_kl", "rho_ac_kl", "kappa_ac_kl"):
+            # whole-run kernels carry the round-off of NSTEP steps forward and NSTEP back, each library its own
+            # (tests/test_oracle_kernel_run.py: KERNEL_RTOL); the acoustic ones differentiate the reconstructed potential once
+            # more.  The arithmetic itself is pinned point-wise in tests/test_gpu_kernel_run.py (two-step tests).
+            tol = 5e-3 if name == "kernel_run" else 1e-2
+            errs[key] = rel_l2(a, b)
+        elif key == "b_d":  # reconstructed seismograms (pressure in the acoustic case: second time derivative, 5e-3)
+            tol = 5e-3 if name == "kernel_run_acoustic" else 5e-4
+            errs[key] = rel_l2(a, b)
         elif key in ("d", "p", "d_forward"):  # seismograms: every trace within the BASELINE tolerance
-            for irec in range(b.shape[0]):
-                for c in range(b.shape[2]):
-                    if np.abs(b[irec, :, c]).max() > 0:
-                        assert rel_l2(a[irec, :, c], b[irec, :, c]) <= 1e-4, (key, irec, c)
+            tol = 1e-4
+            errs[key] = max(rel_l2(a[irec, :, c], b[irec, :, c]) for irec in range(b.shape[0]) for c in range(b.shape[2])
+                            if np.abs(b[irec, :, c]).max() > 0)
         else:  # final wavefield over the whole mesh
-            assert rel_l2(a, b) <= 1e-4, key
+            tol = 1e-4
+            errs[key] = rel_l2(a, b)
+        if not errs[key] <= tol:
+            bad.append((key, errs[key], tol))
+    assert not bad, (bad, errs)
