@@ -222,3 +222,34 @@ def test_acoustic_kernel_arithmetic_two_steps(device_lib):
     assert rel_l2(bp, o.bparts[0].pot) <= 1e-5 and rel_l2(bpdd, o.bparts[0].pot_dot_dot) <= 2e-5
     assert rel_l2(k.ranks[0].fields_ac()[2], o.parts[0].pot_dot_dot) <= 2e-5
     k.cleanup()
+
+
+@pytest.mark.parametrize("fused", [1, 0])
+def test_kernel_run_with_mesh_coloring(device_lib, fused, monkeypatch):
+    """USE_MESH_COLORING_GPU in a kernel run: colour-by-colour launches of the two-wavefield kernel (and of the per-wavefield
+    kernel) without atomics give the kernels of the atomic run.  Elements are permuted by the colouring, so the comparison
+    goes through the position of each element's first corner."""
+    from specfem3d_b200.kernel_run import KernelRun, run_forward_and_save
+
+    monkeypatch.setenv("SPECFEM_B200_KL_FUSED", str(fused))
+    nstep = 100
+    seis, _, k0 = device_kernel_run(device_lib, (1, 1), nstep)
+    adj = adjoint_source(seis)
+    fwd, prod = run_forward_and_save(kernel_sim((1, 1), nstep, coloring=True), lib=device_lib)
+    assert rel_l2(fwd.gather_seismograms("d"), seis) <= 2e-5
+    fwd.cleanup()
+    kc = KernelRun(kernel_sim((1, 1), nstep, sim_type=3, coloring=True), prod, adj, lib=device_lib).run()
+
+    def keyed(run):
+        db = run.ranks[0].db
+        ib = db.ibool.reshape(db.NSPEC_AB, 125) - 1
+        rho, mu, kappa = run.kernels()[0]
+        return {tuple(round(float(c[ib[e, 0]]), 1) for c in (db.xstore, db.ystore, db.zstore)):
+                np.stack([rho[e].ravel(), mu[e].ravel(), kappa[e].ravel()]) for e in range(db.NSPEC_AB)}
+
+    a, b = keyed(k0), keyed(kc)
+    assert a.keys() == b.keys()
+    keys = sorted(a)
+    for c in range(3):
+        assert rel_l2(np.stack([b[q][c] for q in keys]), np.stack([a[q][c] for q in keys])) <= KERNEL_RTOL
+    k0.cleanup(); kc.cleanup()

@@ -10,9 +10,9 @@ from specfem3d_b200.simulation import make_simulation
 from specfem3d_b200.sources_receivers import CMTSource, Station
 
 
-def kernel_sim(nproc=(1, 1), nstep=120, nex=(6, 6, 4), sim_type=1, scale=1.0):
+def kernel_sim(nproc=(1, 1), nstep=120, nex=(6, 6, 4), sim_type=1, scale=1.0, coloring=False):
     spec = BoxSpec(nex[0], nex[1], nex[2], xmax=1100.0 * nex[0], ymax=900.0 * nex[1], zmin=-1000.0 * nex[2],
-                   nproc_xi=nproc[0], nproc_eta=nproc[1], materials=(HALFSPACE,), deform=0.12, stacey=True)
+                   nproc_xi=nproc[0], nproc_eta=nproc[1], materials=(HALFSPACE,), deform=0.12, stacey=True, mesh_coloring=coloring)
     m = tuple(scale * v for v in (1e23, -2e23, 0.5e23, 0.3e23, -0.7e23, 0.2e23))
     src = [CMTSource(0.52 * spec.xmax, 0.47 * spec.ymax, 0.55 * spec.zmin, m, hdur=0.25)]
     sts = [Station("A", "XX", 0.21 * spec.xmax, 0.33 * spec.ymax, 0.0), Station("B", "XX", 0.77 * spec.xmax, 0.62 * spec.ymax, 0.0),
