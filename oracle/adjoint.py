@@ -373,3 +373,112 @@ class OracleAcousticKernelRun:
         for _ in range(self.sim.NSTEP if nstep is None else nstep):
             self.step()
         return self
+
+
+class OracleCoupledKernelRun:
+    """SIMULATION_TYPE == 3 for fluid-solid meshes on the CPU (iterate_time.F90:243-262): adjoint wavefield elastic first, then
+    acoustic (compute_forces_viscoelastic_calling, compute_forces_acoustic_forward_calling with the adjoint definitions
+    pressure^dagger = potential^dagger and d2/dt2 s^dagger = -grad(phi^dagger)/rho,
+    compute_forces_viscoelastic_calling_routine.F90:186-218, compute_forces_acoustic_calling_routine.f90:128-155);
+    reconstructed wavefield acoustic first, then elastic (the *_backward_calling routines).  Kernels of both media."""
+
+    def __init__(self, sim, record: ForwardRecord, adj: np.ndarray):
+        assert sim.ACOUSTIC_SIMULATION and sim.ELASTIC_SIMULATION
+        self.sim, self.record, self.adj = sim, record, np.asarray(adj, np.float32)
+        self.el = OracleKernelRun.__new__(OracleKernelRun)          # helpers of the two single-medium classes, shared state
+        self.ac = OracleAcousticKernelRun.__new__(OracleAcousticKernelRun)
+        self.parts = [OraclePartition(sim, db) for db in sim.dbs]
+        self.bparts = [OraclePartition(sim, db) for db in sim.dbs]
+        for p in self.parts + self.bparts:
+            p.strain = {k: np.zeros((p.db.NSPEC_AB, 5, 5, 5), np.float32) for k in STRAIN_KEYS}
+        z = lambda: [np.zeros((db.NSPEC_AB, 125), np.float32) for db in sim.dbs]
+        self.rho_kl, self.mu_kl, self.kappa_kl, self.rho_ac_kl, self.kappa_ac_kl = z(), z(), z(), z(), z()
+        for h in (self.el, self.ac):
+            h.sim, h.record, h.adj, h.parts, h.bparts = sim, record, self.adj, self.parts, self.bparts
+        self.el.rho_kl, self.el.mu_kl, self.el.kappa_kl = self.rho_kl, self.mu_kl, self.kappa_kl
+        self.ac.rho_ac_kl, self.ac.kappa_ac_kl = self.rho_ac_kl, self.kappa_ac_kl
+        self.it = 0
+
+    @staticmethod
+    def _with(p, name, value, call):
+        keep = getattr(p, name)
+        setattr(p, name, np.ascontiguousarray(value, np.float32))
+        call()
+        setattr(p, name, keep)
+
+    def step(self):
+        sim, L = self.sim, lib()
+        self.it += 1
+        it = self.it
+        dt, dt2, dtsq2 = sim.deltat, sim.deltatover2, sim.deltatsqover2
+        bdt = np.float32(-dt)
+        bdt2, bdtsq2 = np.float32(bdt / np.float32(2)), np.float32(bdt * bdt / np.float32(2))
+        for parts, (a, b, c) in ((self.parts, (dt, dt2, dtsq2)), (self.bparts, (bdt, bdt2, bdtsq2))):
+            for p in parts:
+                n = c_i64(p.db.NGLOB_AB)
+                L.oracle_update_displ_acoustic(n, P(p.pot), P(p.pot_dot), P(p.pot_dot_dot), c_float(a), c_float(b), c_float(c))
+                L.oracle_update_displ_elastic(n, P(p.displ), P(p.veloc), P(p.accel), c_float(a), c_float(b), c_float(c))
+
+        def elastic(parts, half, extra):
+            for r, p in enumerate(parts):
+                p.forces_elastic(1)
+                extra(r, p)
+            for p in parts:
+                p.forces_elastic(2)
+            _assemble(parts, "accel", 3)
+            for p in parts:
+                db = p.db
+                L.oracle_multiply_accel_update_veloc(c_i64(db.NGLOB_AB), P(p.veloc), P(p.accel), P(db.rmassx), P(db.rmassy),
+                                                     P(db.rmassz), c_float(half))
+
+        src_done = []
+
+        def el_adjoint(r, p):
+            p.stacey_elastic()
+            self._with(p, "pot_dot_dot", -p.pot, p.coupling_el_ac)      # pressure^dagger = potential^dagger
+            if not src_done:
+                src_done.append(1)
+                self.el._add_adjoint_sources(it)
+
+        ac_done = []
+
+        def ac_adjoint(r, p):
+            p.stacey_acoustic()
+            self._with(p, "displ", -p.accel, p.coupling_ac_el)         # minus the adjoint acceleration
+            if not ac_done:
+                ac_done.append(1)
+                self.ac._add_adjoint_sources(it)
+
+        def ac_backward(r, pb):
+            self.ac._stacey_replay(pb, r, it)
+            pb.coupling_ac_el()
+            pb.add_sources_acoustic(sim.NSTEP - it + 1)
+
+        def el_backward(r, pb):
+            self.el._stacey_replay(pb, r, it)
+            pb.coupling_el_ac()
+            pb.add_sources_elastic(sim.NSTEP - it + 1)
+
+        elastic(self.parts, dt2, el_adjoint)
+        self.ac._solve(self.parts, dt2, ac_adjoint)
+        self.ac._solve(self.bparts, bdt2, ac_backward)
+        elastic(self.bparts, bdt2, el_backward)
+        if it == 1:
+            for r, pb in enumerate(self.bparts):
+                for k, v in self.record.last[r].items():
+                    getattr(pb, k)[...] = v
+        self.el._kernels()
+        for r, (p, pb) in enumerate(zip(self.parts, self.bparts)):
+            db = p.db
+            ib = db.ibool.reshape(db.NSPEC_AB, 125) - 1
+            ac = np.asarray(db.ispec_is_acoustic, bool)
+            rho = db.rhostore.reshape(db.NSPEC_AB, 125, 1)
+            accel_elm = rho * gradient_over_rho(db, sim.gll, p.pot)
+            b_displ_elm = rho * gradient_over_rho(db, sim.gll, pb.pot)
+            self.rho_ac_kl[r][ac] += dt * (accel_elm * b_displ_elm).sum(-1, dtype=np.float32)[ac]
+            self.kappa_ac_kl[r][ac] += dt * (p.pot[ib] * pb.pot_dot_dot[ib])[ac]
+
+    def run(self, nstep: Optional[int] = None):
+        for _ in range(self.sim.NSTEP if nstep is None else nstep):
+            self.step()
+        return self

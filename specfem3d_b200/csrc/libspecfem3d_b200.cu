@@ -1038,6 +1038,17 @@ extern "C" void SB200_FC(acoustic_enforce_free_surf_cuda)(long* Mesh_pointer, in
 // =================================================================================================================
 // Stacey (replaces src/gpu/compute_stacey_viscoelastic_cuda.cu:39-220, compute_stacey_acoustic_cuda.cu:39-200)
 // =================================================================================================================
+// The caller hands over the same b_absorb_field record buffer every step (SAVE_FORWARD: device -> host, kernel runs: host ->
+// device; 14.7 MB per step on the 1M-element mesh): page-lock it once so the copy is one DMA transfer instead of a staged
+// pageable copy; falls back to the pageable copy if the registration is refused.
+static void pin_absorb_record(DeviceMesh* mp, realw* b_absorb_field) {
+  if (mp->h_absorb_registered == b_absorb_field) return;
+  if (mp->h_absorb_registered) cudaHostUnregister(mp->h_absorb_registered);
+  mp->h_absorb_registered = nullptr;
+  if (cudaHostRegister(b_absorb_field, mp->b_reclen_field, cudaHostRegisterDefault) == cudaSuccess) mp->h_absorb_registered = b_absorb_field;
+  else (void)cudaGetLastError();
+}
+
 extern "C" void SB200_FC(compute_stacey_viscoelastic_cuda)(long* Mesh_pointer, int* iphasef, realw* b_absorb_field,
                                                            int* FORWARD_OR_ADJOINT_f) {
   DeviceMesh* mp = get_mesh(Mesh_pointer);
@@ -1049,14 +1060,7 @@ extern "C" void SB200_FC(compute_stacey_viscoelastic_cuda)(long* Mesh_pointer, i
     // wavefield (compute_stacey_viscoelastic_cuda.cu:78-80,136-152; CPU compute_stacey_viscoelastic_backward)
     require_backward_fields(mp, "compute_stacey_viscoelastic_cuda");
     if (!mp->d_b_absorb_field) exit_on_error("compute_stacey_viscoelastic_cuda: b_absorb_field was not prepared");
-    // the caller hands over the same record buffer every step: page-lock it once so the copy is one DMA transfer instead
-    // of a staged pageable copy (14.7 MB per step on the 1M-element mesh); falls back to the pageable copy if refused
-    if (mp->h_absorb_registered != b_absorb_field) {
-      if (mp->h_absorb_registered) cudaHostUnregister(mp->h_absorb_registered);
-      mp->h_absorb_registered = nullptr;
-      if (cudaHostRegister(b_absorb_field, mp->b_reclen_field, cudaHostRegisterDefault) == cudaSuccess) mp->h_absorb_registered = b_absorb_field;
-      else (void)cudaGetLastError();
-    }
+    pin_absorb_record(mp, b_absorb_field);
     CUDA_CHECK(cudaMemcpyAsync(mp->d_b_absorb_field, b_absorb_field, mp->b_reclen_field, cudaMemcpyHostToDevice, mp->compute_stream));
     CUDA_CHECK(cudaStreamSynchronize(mp->compute_stream));  // the caller may overwrite the buffer as soon as we return
     k_stacey_elastic_replay<<<mp->num_abs_boundary_faces, 32, 0, mp->compute_stream>>>(
@@ -1072,6 +1076,7 @@ extern "C" void SB200_FC(compute_stacey_viscoelastic_cuda)(long* Mesh_pointer, i
       mp->num_abs_boundary_faces, d_b, (size_t)mp->NGLOB_AB);
   KERNEL_CHECK(mp, "k_stacey_elastic");
   if (d_b) {  // SAVE_FORWARD: hand the absorbed tractions back for the Fortran side to write (blocking, like the reference)
+    pin_absorb_record(mp, b_absorb_field);
     CUDA_CHECK(cudaMemcpyAsync(b_absorb_field, d_b, mp->b_reclen_field, cudaMemcpyDeviceToHost, mp->compute_stream));
     CUDA_CHECK(cudaStreamSynchronize(mp->compute_stream));
   }

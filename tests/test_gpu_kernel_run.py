@@ -253,3 +253,31 @@ def test_kernel_run_with_mesh_coloring(device_lib, fused, monkeypatch):
     for c in range(3):
         assert rel_l2(np.stack([b[q][c] for q in keys]), np.stack([a[q][c] for q in keys])) <= KERNEL_RTOL
     k0.cleanup(); kc.cleanup()
+
+
+def test_coupled_kernel_run_matches_oracle(device_lib):
+    """Fluid-solid kernel run (adjoint wavefield elastic -> acoustic with the adjoint coupling definitions, reconstructed
+    wavefield acoustic -> elastic) against oracle/adjoint.py: OracleCoupledKernelRun, all five kernels."""
+    from oracle.adjoint import OracleCoupledKernelRun, OracleForwardRun
+    from specfem3d_b200.kernel_run import KernelRun, run_forward_and_save
+    from test_oracle_kernel_run import coupled_adjoint_source, coupled_kernel_sim
+
+    n = 300  # time for the wave to cross the interface: before that the kernels of the far medium are round-off
+    fwd, prod = run_forward_and_save(coupled_kernel_sim(n, 1), lib=device_lib)
+    seis = fwd.gather_seismograms("d")
+    fwd.cleanup()
+    sim1 = coupled_kernel_sim(n, 1)
+    adj = coupled_adjoint_source(sim1, seis)
+    ofwd = OracleForwardRun(sim1).run()
+    ok = OracleCoupledKernelRun(coupled_kernel_sim(n, 3), ofwd.record, adj).run()
+    k = KernelRun(coupled_kernel_sim(n, 3), prod, adj, lib=device_lib).run()
+    assert rel_l2(k.ranks[0].fields_el()[0], ok.parts[0].displ) <= 1e-4
+    assert rel_l2(k.ranks[0].fields_ac()[0], ok.parts[0].pot) <= 1e-4
+    rho, mu, kappa = k.kernels()[0]
+    rho_ac, kappa_ac = k.kernels_ac()[0]
+    nspec = rho.shape[0]
+    for name, mine in (("rho_kl", rho), ("mu_kl", mu), ("kappa_kl", kappa), ("rho_ac_kl", rho_ac), ("kappa_ac_kl", kappa_ac)):
+        ref = getattr(ok, name)[0]
+        assert np.abs(ref).max() > 0, name
+        assert rel_l2(mine.reshape(nspec, 125), ref) <= 2 * KERNEL_RTOL, name
+    k.cleanup()
