@@ -132,6 +132,27 @@ class OraclePartition:
             c_int(s.NSOURCES), c_int(db.myrank), P(s.islice_selected_source), P(s.ispec_selected_source),
             P(db.ispec_is_elastic), P(s.sourcearrays), P(stf), P(db.ibool), P(self.accel))
 
+    def multiply_ocean_load_update_veloc(self, deltatover2):
+        """APPROXIMATE_OCEAN_LOAD branch of compute_forces_viscoelastic_calling (…calling_routine.F90:368-424): accel * rmass,
+        compute_coupling_ocean (compute_coupling_viscoelastic_ac.f90:171-251; the first face that touches a point supplies
+        its normal), then the velocity update (update_veloc_elastic).  Single precision throughout."""
+        db, f32 = self.db, np.float32
+        rm = np.stack([db.rmassx, db.rmassy, db.rmassz], -1).astype(f32)
+        self.accel *= rm
+        ib = db.ibool.reshape(db.NSPEC_AB, 125)
+        seen = np.zeros(db.NGLOB_AB, bool)
+        for f in range(db.num_free_surface_faces):
+            ispec = int(db.free_surface_ispec[f]) - 1
+            ijk = np.asarray(db.free_surface_ijk[f]).reshape(25, 3).astype(np.int64) - 1
+            ig = ib[ispec, ijk[:, 0] + 5 * ijk[:, 1] + 25 * ijk[:, 2]] - 1
+            new = ~seen[ig]
+            seen[ig] = True
+            ig, n = ig[new], np.asarray(db.free_surface_normal[f], f32).reshape(25, 3)[new]
+            a = self.accel[ig]
+            fn = (a[:, 0] * n[:, 0] / rm[ig, 0] + a[:, 1] * n[:, 1] / rm[ig, 1] + a[:, 2] * n[:, 2] / rm[ig, 2]).astype(f32)
+            self.accel[ig] = (a + (db.rmass_ocean_load[ig, None] - rm[ig]) * fn[:, None] * n).astype(f32)
+        self.veloc += f32(deltatover2) * self.accel
+
     # -- acoustic --------------------------------------------------------------------------------------------------
     def forces_acoustic(self, iphase: int):
         sim, db, g = self.sim, self.db, self.sim.gll
@@ -283,6 +304,9 @@ class OracleRun:
                     from . import pml_oracle
 
                     pml_oracle.impose_boundary_condition(p)
+                if sim.APPROXIMATE_OCEAN_LOAD:
+                    p.multiply_ocean_load_update_veloc(dt2)
+                    continue
                 L.oracle_multiply_accel_update_veloc(c_i64(p.db.NGLOB_AB), P(p.veloc), P(p.accel), P(p.db.rmassx),
                                                      P(p.db.rmassy), P(p.db.rmassz), c_float(dt2))
         # --- seismograms ------------------------------------------------------------------------------------------

@@ -105,7 +105,12 @@ struct DeviceMesh {
   realw *d_displ = nullptr, *d_veloc = nullptr, *d_accel = nullptr;                                       // component planes [3][NGLOB] (kernels_common.cuh: vidx)
   realw *d_potential = nullptr, *d_potential_dot = nullptr, *d_potential_dot_dot = nullptr;               // [NGLOB]
   realw *d_rmassx = nullptr, *d_rmassy = nullptr, *d_rmassz = nullptr, *d_rmass_acoustic = nullptr;       // [NGLOB]
-  realw* d_rmass_ocean_load = nullptr;
+  realw* d_rmass_ocean_load = nullptr;  // [NGLOB], inverted like the others
+  // APPROXIMATE_OCEAN_LOAD: the free-surface points of elastic faces, each once, in the face order of the CPU loop (the first
+  // face that touches a point supplies its normal: compute_coupling_ocean, compute_coupling_viscoelastic_ac.f90:207-247)
+  int num_ocean_points = 0;
+  int* d_ocean_iglob = nullptr;      // [num_ocean_points], 0-based
+  realw* d_ocean_normal = nullptr;   // [num_ocean_points][3]
 
   // attenuation (planes of 128 per element and SLS)
   realw *d_R_xx = nullptr, *d_R_yy = nullptr, *d_R_xy = nullptr, *d_R_xz = nullptr, *d_R_yz = nullptr,

@@ -213,6 +213,27 @@ __global__ void __launch_bounds__(32) k_coupling_el_ac(const realw* __restrict__
   red_add(accel + vidx(iglob, 2, nglob), jw * n[2] * pressure);
 }
 
+// APPROXIMATE_OCEAN_LOAD (replaces compute_coupling_ocean_cuda_kernel; CPU compute_coupling_ocean,
+// compute_coupling_viscoelastic_ac.f90:171-251): the normal force at a free-surface point feels the mass of the water column.
+// The reference marks visited points with atomicExch on an NGLOB-sized array it clears every step; here the unique points
+// (first face in face order wins, like the CPU loop) are listed once at preparation: one thread per point, no atomics.
+__global__ void __launch_bounds__(128) k_coupling_ocean(realw* accel, const realw* __restrict__ rmass3,
+                                                        const realw* __restrict__ rmass_ocean_load, int npoints,
+                                                        const int* __restrict__ ocean_iglob,
+                                                        const realw* __restrict__ ocean_normal, size_t nglob) {
+  const int ip = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= npoints) return;
+  const size_t iglob = (size_t)ocean_iglob[ip];
+  const realw nx = ocean_normal[3 * ip], ny = ocean_normal[3 * ip + 1], nz = ocean_normal[3 * ip + 2];
+  const size_t g0 = vidx(iglob, 0, nglob), g1 = vidx(iglob, 1, nglob), g2 = vidx(iglob, 2, nglob);
+  const realw rx = rmass3[g0], ry = rmass3[g1], rz = rmass3[g2], ro = rmass_ocean_load[iglob];
+  const realw ax = accel[g0], ay = accel[g1], az = accel[g2];
+  const realw force_normal_comp = ax * nx / rx + ay * ny / ry + az * nz / rz;
+  accel[g0] = ax + (ro - rx) * force_normal_comp * nx;
+  accel[g1] = ay + (ro - ry) * force_normal_comp * ny;
+  accel[g2] = az + (ro - rz) * force_normal_comp * nz;
+}
+
 // acoustic free surface: zero the potential and its derivatives (replaces enforce_free_surface_cuda_kernel,
 // src/gpu/kernels/enforce_free_surface_cuda_kernel.cu:30-67)
 __global__ void __launch_bounds__(32) k_enforce_free_surface(realw* pot, realw* pot_dot, realw* pot_dot_dot, int num_faces,

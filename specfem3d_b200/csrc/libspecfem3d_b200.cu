@@ -317,7 +317,6 @@ extern "C" void SB200_FC(prepare_fields_elastic_device)(
     realw* c66store) {
   DeviceMesh* mp = get_mesh(Mesh_pointer);
   if (*ANISOTROPY) exit_on_error("ANISOTROPY is not part of this round's hot path (isotropic elastic / viscoelastic only)");
-  if (*APPROXIMATE_OCEAN_LOAD) exit_on_error("APPROXIMATE_OCEAN_LOAD is not implemented by this library yet");
   if (*NOISE_TOMOGRAPHY) exit_on_error("NOISE_TOMOGRAPHY is out of scope of this library");
   const size_t nglob = mp->NGLOB_AB, nspec = mp->NSPEC_AB;
 
@@ -394,8 +393,33 @@ extern "C" void SB200_FC(prepare_fields_elastic_device)(
     mp->num_colors_inner_elastic = *num_colors_inner_elastic;
     mp->h_num_elem_colors_elastic = num_elem_colors_elastic;  // retained by pointer, like the reference
   }
-  (void)rmass_ocean_load; (void)free_surface_normal; (void)free_surface_ispec; (void)free_surface_ijk;
-  (void)num_free_surface_faces; (void)ACOUSTIC_SIMULATION;
+  (void)ACOUSTIC_SIMULATION;
+  mp->approximate_ocean_load = *APPROXIMATE_OCEAN_LOAD;
+  if (mp->approximate_ocean_load) {
+    mp->d_rmass_ocean_load = dev_copy(rmass_ocean_load, nglob);
+    // unique free-surface points in the order of the CPU loop (faces, then GLL points; every face, like the reference)
+    std::vector<int> h_ibool((size_t)nspec * NGLL3_PADDED);
+    CUDA_CHECK(cudaMemcpy(h_ibool.data(), mp->d_ibool, h_ibool.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<char> seen(nglob, 0);
+    std::vector<int> pts;
+    std::vector<realw> nrm;
+    for (int f = 0; f < *num_free_surface_faces; ++f) {
+      const int ispec = free_surface_ispec[f] - 1;
+      for (int g = 0; g < NGLL2; ++g) {
+        const int* ijk = free_surface_ijk + 3 * (g + NGLL2 * (size_t)f);
+        const int p = (ijk[0] - 1) + NGLLX * (ijk[1] - 1) + NGLL2 * (ijk[2] - 1);
+        const int iglob = h_ibool[(size_t)ispec * NGLL3_PADDED + p] - 1;
+        if (seen[iglob]) continue;
+        seen[iglob] = 1;
+        pts.push_back(iglob);
+        const realw* n = free_surface_normal + 3 * (g + NGLL2 * (size_t)f);
+        nrm.insert(nrm.end(), n, n + 3);
+      }
+    }
+    mp->num_ocean_points = (int)pts.size();
+    mp->d_ocean_iglob = dev_copy(pts.data(), pts.size());
+    mp->d_ocean_normal = dev_copy(nrm.data(), nrm.size());
+  }
   (void)c11store; (void)c12store; (void)c13store; (void)c14store; (void)c15store; (void)c16store; (void)c22store;
   (void)c23store; (void)c24store; (void)c25store; (void)c26store; (void)c33store; (void)c34store; (void)c35store;
   (void)c36store; (void)c44store; (void)c45store; (void)c46store; (void)c55store; (void)c56store; (void)c66store;
@@ -486,6 +510,7 @@ extern "C" void SB200_FC(prepare_cleanup_device)(long* Mesh_pointer, int* ACOUST
                    mp->d_b_epsilondev_xy, mp->d_b_epsilondev_xz, mp->d_b_epsilondev_yz, mp->d_epsilon_trace_over_3,
                    mp->d_b_epsilon_trace_over_3, mp->d_rho_kl, mp->d_mu_kl, mp->d_kappa_kl, mp->d_hess_el_kl,
                    mp->d_hess_rho_el_kl, mp->d_hess_kappa_el_kl, mp->d_hess_mu_el_kl, mp->d_source_adjoint,
+                   mp->d_rmass_ocean_load, mp->d_ocean_iglob, mp->d_ocean_normal,
                    mp->d_b_send_accel_buffer, mp->d_b_potential, mp->d_b_potential_dot, mp->d_b_potential_dot_dot,
                    mp->d_rho_ac_kl, mp->d_kappa_ac_kl, mp->d_b_send_potential_buffer};
   for (void* p : dptrs) dev_free(p);
@@ -1159,6 +1184,20 @@ extern "C" void SB200_FC(compute_coupling_el_ac_cuda)(long* Mesh_pointer, int* i
                                                       mp->d_coupling_ac_el_ijk, mp->d_coupling_ac_el_normal,
                                                       mp->d_coupling_ac_el_jacobian2Dw, mp->d_ibool, (size_t)mp->NGLOB_AB, sign);
   KERNEL_CHECK(mp, "k_coupling_el_ac");
+}
+
+// APPROXIMATE_OCEAN_LOAD (replaces compute_coupling_cuda.cu: COMPUTE_COUPLING_OCEAN_CUDA): between kernel_3_a_cuda, which then
+// only multiplies by the mass matrix, and kernel_3_b_cuda, which updates the velocity
+extern "C" void SB200_FC(compute_coupling_ocean_cuda)(long* Mesh_pointer, int* FORWARD_OR_ADJOINT) {
+  DeviceMesh* mp = get_mesh(Mesh_pointer);
+  if (*FORWARD_OR_ADJOINT != 1 && *FORWARD_OR_ADJOINT != 3) exit_on_error("compute_coupling_ocean_cuda: FORWARD_OR_ADJOINT must be 1 or 3");
+  if (!mp->approximate_ocean_load) exit_on_error("compute_coupling_ocean_cuda called without APPROXIMATE_OCEAN_LOAD in prepare_fields_elastic_device");
+  if (*FORWARD_OR_ADJOINT == 3) require_backward_fields(mp, "compute_coupling_ocean_cuda");
+  if (mp->num_ocean_points == 0) return;
+  k_coupling_ocean<<<(mp->num_ocean_points + 127) / 128, 128, 0, mp->compute_stream>>>(
+      *FORWARD_OR_ADJOINT == 1 ? mp->d_accel : mp->d_b_accel, mp->d_rmassx, mp->d_rmass_ocean_load, mp->num_ocean_points,
+      mp->d_ocean_iglob, mp->d_ocean_normal, (size_t)mp->NGLOB_AB);
+  KERNEL_CHECK(mp, "k_coupling_ocean");
 }
 
 // =================================================================================================================

@@ -100,6 +100,9 @@ class BoxSpec:
     # USE_MESH_COLORING_GPU: elements are permuted into colour order (outer colours, then inner; elastic before acoustic)
     # and the force kernels run colour by colour without atomics (setup_color_perm.f90 semantics)
     mesh_coloring: bool = False
+    # APPROXIMATE_OCEAN_LOAD: the water column above an elastic free surface that lies below sea level (zmax < 0; no
+    # topography file: elevation = z of the surface point, define_mass_matrices.f90:323-336) loads the normal motion
+    approximate_ocean_load: bool = False
 
     @property
     def nproc(self) -> int:
@@ -190,6 +193,7 @@ class Database:
     rmassy: np.ndarray = None
     rmassz: np.ndarray = None
     rmass_acoustic: np.ndarray = None
+    rmass_ocean_load: np.ndarray = None  # APPROXIMATE_OCEAN_LOAD only
     # C-PML
     is_CPML: np.ndarray = None
     extra: dict = field(default_factory=dict)
@@ -684,6 +688,21 @@ def local_mass_matrices(spec: BoxSpec, db: Database, DT: float, gll: Optional[GL
             out["rmassx"], out["rmassy"], out["rmassz"] = rmass.copy(), rmass.copy(), rmass.copy()
         # the separate records of the database file (save_arrays_solver.F90:196-233): rmass and the Stacey terms alone
         out["_parts_elastic"] = (rmass, rx, ry, rz)
+        if spec.approximate_ocean_load:
+            # define_mass_matrices_ocean_load (define_mass_matrices.f90:262-347) + create_mass_matrices_ocean_load :178
+            RHO_APPROXIMATE_OCEAN_LOAD, MINIMUM_THICKNESS_3D_OCEANS = np.float32(1020.0), 10.0
+            ro = np.zeros(nglob, dtype=np.float32)
+            for f in range(db.num_free_surface_faces):
+                isp = db.free_surface_ispec[f] - 1
+                if not db.ispec_is_elastic[isp]:
+                    continue
+                ijk = db.free_surface_ijk[f] - 1
+                ig = flat_ibool[isp, ijk[:, 0] + 5 * ijk[:, 1] + 25 * ijk[:, 2]] - 1
+                elevation = db.zstore[ig].astype(np.float64)
+                height = np.where(elevation >= -MINIMUM_THICKNESS_3D_OCEANS, 0.0, np.abs(elevation))
+                weight = db.free_surface_jacobian2Dw[f].astype(np.float64) * float(RHO_APPROXIMATE_OCEAN_LOAD) * height
+                ro[ig] += weight.astype(np.float32)
+            out["rmass_ocean_load"] = ro + rmass
 
     if db.nspec_acoustic:
         rma = np.zeros(nglob, dtype=np.float32)
@@ -744,7 +763,7 @@ def build_all(spec: BoxSpec, DT: float, gll: Optional[GLL] = None) -> List[Datab
             raise NotImplementedError("harness: C-PML is generated for elastic boxes only")
         set_local_dampingcoeff(spec, dbs, spec.f0_for_pml)
     loc = [local_mass_matrices(spec, db, DT, gll) for db in dbs]
-    for key in ("rmassx", "rmassy", "rmassz", "rmass_acoustic"):
+    for key in ("rmassx", "rmassy", "rmassz", "rmass_acoustic", "rmass_ocean_load"):
         if all(key in l for l in loc):
             arrs = [l[key] for l in loc]
             if spec.nproc > 1:

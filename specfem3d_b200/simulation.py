@@ -55,6 +55,10 @@ class Simulation:
         return np.float32(self.deltat * self.deltat / np.float32(2.0))
 
     @property
+    def APPROXIMATE_OCEAN_LOAD(self) -> bool:
+        return bool(getattr(self.spec, "approximate_ocean_load", False))
+
+    @property
     def ELASTIC_SIMULATION(self) -> bool:
         return any(db.nspec_elastic > 0 for db in self.dbs if db is not None)
 

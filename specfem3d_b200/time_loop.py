@@ -169,7 +169,9 @@ class DeviceRank:
                 self.Mesh_pointer, db.rmassx, db.rmassy, db.rmassz, db.rho_vp, db.rho_vs, kappa, mu,
                 db.num_phase_ispec_elastic, db.phase_ispec_inner_elastic, self.b_absorb_field, self.b_reclen_field, strain, eps[0], eps[1], eps[2],
                 eps[3], eps[4], int(att is not None), R_size, R[0], R[1], R[2], R[3], R[4], fc, R[5], eps[5], fck, al,
-                be, ga, 0, dummy, 0, dummy, db.free_surface_ispec, db.free_surface_ijk, db.num_free_surface_faces,
+                be, ga, int(sim.APPROXIMATE_OCEAN_LOAD), db.rmass_ocean_load if sim.APPROXIMATE_OCEAN_LOAD else dummy, 0,
+                _f(db.free_surface_normal) if sim.APPROXIMATE_OCEAN_LOAD else dummy, db.free_surface_ispec, db.free_surface_ijk,
+                db.num_free_surface_faces,
                 int(sim.ACOUSTIC_SIMULATION), *col["elastic"], 0, *([dummy] * 21))
             if sim.PML_CONDITIONS and sim.pml is not None:
                 from .pml import prepare_fields_elastic_pml
@@ -357,7 +359,11 @@ class DeviceRun:
         for r in E:
             if sim.PML_CONDITIONS and sim.pml is not None:
                 r.lib.pml_impose_boundary_condition_elastic_cuda(r.Mesh_pointer)
-            r.lib.kernel_3_a_cuda(r.Mesh_pointer, dt2, dt2, 0, 1)
+            ocean = int(sim.APPROXIMATE_OCEAN_LOAD)
+            r.lib.kernel_3_a_cuda(r.Mesh_pointer, dt2, dt2, ocean, 1)
+            if ocean:  # compute_forces_viscoelastic_calling_routine.F90:380-424
+                r.lib.compute_coupling_ocean_cuda(r.Mesh_pointer, 1)
+                r.lib.kernel_3_b_cuda(r.Mesh_pointer, dt2, dt2, 1)
 
     def _seismograms(self, it: int):
         sim = self.sim

@@ -159,3 +159,28 @@ def test_attenuation_bin_round_trip_and_run(tmp_path):
     for a, b in zip(sim.att, sim2.att):
         for k in ("mustore", "kappastore", "factor_common", "factor_common_kappa", "alphaval", "betaval", "gammaval"):
             assert np.array_equal(np.asarray(a[k]).ravel(), np.asarray(b[k]).ravel()), k
+
+
+def test_ocean_load_record_round_trip(tmp_path):
+    """APPROXIMATE_OCEAN_LOAD: rmass_ocean_load sits between rmass and rho_vp (save_arrays_solver.F90:160-168); the solver
+    assembles and inverts it like the other mass matrices (prepare_timerun.F90:340-348)."""
+    from specfem3d_b200.databases import simulation_from_databases
+    from specfem3d_b200.simulation import make_simulation
+
+    spec = BoxSpec(6, 4, 4, xmax=6600.0, ymax=3600.0, zmin=-7000.0, zmax=-3000.0, nproc_xi=2, materials=(HALFSPACE,), deform=0.1,
+                   approximate_ocean_load=True)
+    DT = 0.012
+    sim = make_simulation(spec, DT=DT, NSTEP=5)
+    flags = DatabaseFlags(APPROXIMATE_OCEAN_LOAD=True)
+    dry = DatabaseFlags()
+    back = []
+    for db in sim.dbs:
+        path = str(tmp_path / f"proc{db.myrank:06d}_external_mesh.bin")
+        n_wet = write_external_mesh(path, db, spec, flags, mass_records(spec, db, DT, sim.gll))
+        back.append(read_external_mesh(path, flags, db.myrank, spec.nproc))
+        n_dry = write_external_mesh(str(tmp_path / "dry.bin"), db, spec, dry, mass_records(spec, db, DT, sim.gll))
+        assert n_wet == n_dry + 1
+    sim2 = simulation_from_databases(back, spec, DT, 5)
+    for a, b in zip(sim.dbs, sim2.dbs):
+        assert np.array_equal(a.rmass_ocean_load, b.rmass_ocean_load)
+        assert (a.rmass_ocean_load < 0.5 * a.rmassz).any()  # inverse masses: heavier where the water column sits
