@@ -282,6 +282,8 @@ class OracleAcousticKernelRun:
         self.bparts = [OraclePartition(sim, db) for db in sim.dbs]
         self.rho_ac_kl = [np.zeros((db.NSPEC_AB, 125), np.float32) for db in sim.dbs]
         self.kappa_ac_kl = [np.zeros((db.NSPEC_AB, 125), np.float32) for db in sim.dbs]
+        self.hess_ac_kl, self.hess_rho_ac_kl, self.hess_kappa_ac_kl = ([np.zeros((db.NSPEC_AB, 125), np.float32) for db in sim.dbs]
+                                                                      for _ in range(3))
         self.seis_p = np.zeros((sim.receivers.nrec, sim.nlength_seismogram), np.float32)
         self.it = 0
 
@@ -368,6 +370,13 @@ class OracleAcousticKernelRun:
             b_displ_elm = rho * gradient_over_rho(db, sim.gll, pb.pot)
             self.rho_ac_kl[r][ac] += dt * (accel_elm * b_displ_elm).sum(-1, dtype=np.float32)[ac]
             self.kappa_ac_kl[r][ac] += dt * (p.pot[ib] * pb.pot_dot_dot[ib])[ac]
+            if sim.APPROXIMATE_HESS_KL:  # compute_kernels_hess_ac (compute_kernels.f90:620-700; GPU compute_kernels_hess_ac_cudakernel)
+                ga = gradient_over_rho(db, sim.gll, p.pot_dot_dot)
+                gb = gradient_over_rho(db, sim.gll, pb.pot_dot_dot)
+                gv = gradient_over_rho(db, sim.gll, pb.pot_dot)
+                self.hess_ac_kl[r][ac] += dt * (ga * gb).sum(-1, dtype=np.float32)[ac]
+                self.hess_rho_ac_kl[r][ac] += (dt * rho[..., 0] * (gv * gv).sum(-1, dtype=np.float32))[ac]
+                self.hess_kappa_ac_kl[r][ac] += (dt / db.kappastore.reshape(db.NSPEC_AB, 125) * (pb.pot_dot[ib] * pb.pot_dot[ib]))[ac]
 
     def run(self, nstep: Optional[int] = None):
         for _ in range(self.sim.NSTEP if nstep is None else nstep):

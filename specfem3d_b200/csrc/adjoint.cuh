@@ -332,7 +332,60 @@ struct AcousticKernelArgs {
   realw *rho_ac_kl, *kappa_ac_kl;
   realw deltat;
   int nspec;
+  // approximate Hessian (compute_kernels_hess_ac_cudakernel)
+  const realw *potential_dot_dot, *b_potential_dot, *kappastore /* [NSPEC][125] */;
+  realw *hess_ac_kl, *hess_rho_ac_kl, *hess_kappa_ac_kl;
 };
+
+// (1/rho) grad of the scalar field held in the tile s (compute_gradient_kernel.h), at GLL point t = (I, J, K)
+__device__ __forceinline__ void gradient_over_rho(const realw* s, const realw* s_hp, int I, int J, int K, const realw* mp /*or nullptr*/,
+                                                  realw xix_regular, realw rho_invl, realw& gx, realw& gy, realw& gz) {
+  realw t1 = 0.f, t2 = 0.f, t3 = 0.f;
+#pragma unroll
+  for (int l = 0; l < NGLLX; ++l) {
+    t1 += s[K * NGLL2 + J * NGLLX + l] * s_hp[l * NGLLX + I];
+    t2 += s[K * NGLL2 + l * NGLLX + I] * s_hp[l * NGLLX + J];
+    t3 += s[l * NGLL2 + J * NGLLX + I] * s_hp[l * NGLLX + K];
+  }
+  if (mp) {
+    gx = (t1 * mp[0] + t2 * mp[3 * NGLL3_PADDED] + t3 * mp[6 * NGLL3_PADDED]) * rho_invl;
+    gy = (t1 * mp[NGLL3_PADDED] + t2 * mp[4 * NGLL3_PADDED] + t3 * mp[7 * NGLL3_PADDED]) * rho_invl;
+    gz = (t1 * mp[2 * NGLL3_PADDED] + t2 * mp[5 * NGLL3_PADDED] + t3 * mp[8 * NGLL3_PADDED]) * rho_invl;
+  } else {
+    gx = t1 * xix_regular * rho_invl; gy = t2 * xix_regular * rho_invl; gz = t3 * xix_regular * rho_invl;
+  }
+}
+
+// hess_ac_kl += dt grad(phi_dd)/rho . grad(b_phi_dd)/rho ; hess_rho_ac_kl += dt rho |grad(b_phi_d)/rho|^2 ;
+// hess_kappa_ac_kl += dt / kappa * b_phi_d^2   (compute_kernels_hess_ac_cudakernel)
+__global__ void __launch_bounds__(NGLL3_PADDED) k_kernels_hess_acoustic(const AcousticKernelArgs a) {
+  const int ispec = blockIdx.x, tx = threadIdx.x;
+  if (ispec >= a.nspec || !a.ispec_is_acoustic[ispec]) return;  // uniform per block
+  const bool active = tx < NGLL3;
+  const int t = active ? tx : NGLL3 - 1;
+  const int K = t / NGLL2, J = (t - K * NGLL2) / NGLLX, I = t - K * NGLL2 - J * NGLLX;
+  __shared__ realw s_a[NGLL3_PADDED], s_ba[NGLL3_PADDED], s_bv[NGLL3_PADDED], s_hp[NGLL2];
+  const size_t off = (size_t)ispec * NGLL3_PADDED + t;
+  const size_t iglob = (size_t)a.ibool[off] - 1;
+  const realw bvel = a.b_potential_dot[iglob];
+  s_a[t] = a.potential_dot_dot[iglob];
+  s_ba[t] = a.b_potential_dot_dot[iglob];
+  s_bv[t] = bvel;
+  if (tx < NGLL2) s_hp[tx] = c_hprime_xx[tx];
+  __syncthreads();
+  if (!active) return;
+  const realw rhol = a.rhostore[off];
+  const realw rho_invl = 1.0f / rhol;
+  const int irr = a.irregular_element_number[ispec] - 1;
+  const realw* mp = irr >= 0 ? a.metric + (size_t)irr * 9 * NGLL3_PADDED + t : nullptr;
+  realw ax, ay, az, bx, by, bz, vx, vy, vz;
+  gradient_over_rho(s_a, s_hp, I, J, K, mp, a.xix_regular, rho_invl, ax, ay, az);
+  gradient_over_rho(s_ba, s_hp, I, J, K, mp, a.xix_regular, rho_invl, bx, by, bz);
+  gradient_over_rho(s_bv, s_hp, I, J, K, mp, a.xix_regular, rho_invl, vx, vy, vz);
+  a.hess_ac_kl[off] += a.deltat * (ax * bx + ay * by + az * bz);
+  a.hess_rho_ac_kl[off] += a.deltat * rhol * (vx * vx + vy * vy + vz * vz);
+  a.hess_kappa_ac_kl[off] += a.deltat / a.kappastore[(size_t)ispec * NGLL3 + t] * (bvel * bvel);
+}
 
 __global__ void __launch_bounds__(NGLL3_PADDED) k_kernels_acoustic(const AcousticKernelArgs a) {
   const int ispec = blockIdx.x, tx = threadIdx.x;

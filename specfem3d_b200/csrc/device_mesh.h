@@ -168,6 +168,8 @@ struct DeviceMesh {
   realw* d_b_send_accel_buffer = nullptr;
   realw *d_b_potential = nullptr, *d_b_potential_dot = nullptr, *d_b_potential_dot_dot = nullptr;  // [NGLOB]
   realw *d_rho_ac_kl = nullptr, *d_kappa_ac_kl = nullptr;                                          // [NSPEC][128]
+  realw *d_hess_ac_kl = nullptr, *d_hess_rho_ac_kl = nullptr, *d_hess_kappa_ac_kl = nullptr;       // [NSPEC][128]
+  int approximate_hess_ac_kl = 0;
   realw* d_b_send_potential_buffer = nullptr;
   realw* h_absorb_registered = nullptr;  // caller's b_absorb_field record buffer, page-locked on first use (Stacey replay)
   // FORWARD_OR_ADJOINT == 0 force launches use the two-wavefield kernel that accumulates mu_kl / kappa_kl itself

@@ -512,7 +512,8 @@ extern "C" void SB200_FC(prepare_cleanup_device)(long* Mesh_pointer, int* ACOUST
                    mp->d_hess_rho_el_kl, mp->d_hess_kappa_el_kl, mp->d_hess_mu_el_kl, mp->d_source_adjoint,
                    mp->d_rmass_ocean_load, mp->d_ocean_iglob, mp->d_ocean_normal,
                    mp->d_b_send_accel_buffer, mp->d_b_potential, mp->d_b_potential_dot, mp->d_b_potential_dot_dot,
-                   mp->d_rho_ac_kl, mp->d_kappa_ac_kl, mp->d_b_send_potential_buffer};
+                   mp->d_rho_ac_kl, mp->d_kappa_ac_kl, mp->d_b_send_potential_buffer, mp->d_hess_ac_kl, mp->d_hess_rho_ac_kl,
+                   mp->d_hess_kappa_ac_kl};
   for (void* p : dptrs) dev_free(p);
   if (mp->h_absorb_registered) cudaHostUnregister(mp->h_absorb_registered);
   if (mp->h_send_accel_buffer) cudaFreeHost(mp->h_send_accel_buffer);

@@ -119,13 +119,13 @@ class KernelRun(DeviceRun):
                     r.lib.transfer_b_fields_to_device(3 * n, f["displ"], f["veloc"], f["accel"], r.Mesh_pointer)
         if sim.receivers is not None and (it - 1) % sim.NTSTEP_BETWEEN_OUTPUT_SAMPLE == 0:
             self._seismograms(it)
-        for r in self.ranks:  # compute_kernels
-            if r.ACOUSTIC:
-                r.lib.compute_kernels_acoustic_cuda(r.Mesh_pointer, dt)
+        for r in self.ranks:  # compute_kernels (compute_kernels.f90:60-75, 540-560)
             if r.ELASTIC:
                 r.lib.compute_kernels_elastic_cuda(r.Mesh_pointer, dt)
-                if sim.APPROXIMATE_HESS_KL:
-                    r.lib.compute_kernels_hess_cuda(r.Mesh_pointer, dt, 1, 0)
+            if r.ACOUSTIC:
+                r.lib.compute_kernels_acoustic_cuda(r.Mesh_pointer, dt)
+            if sim.APPROXIMATE_HESS_KL:
+                r.lib.compute_kernels_hess_cuda(r.Mesh_pointer, dt, int(r.ELASTIC), int(r.ACOUSTIC))
 
     def _elastic(self, it: int, foas):
         """foas = (0,): compute_forces_viscoelastic_GPU_calling (both wavefields); (1,) / (3,): the separate routines."""
@@ -279,6 +279,16 @@ class KernelRun(DeviceRun):
             if r.ACOUSTIC:
                 r.lib.transfer_kernels_ac_to_host(r.Mesh_pointer, r.rho_ac_kl, r.kappa_ac_kl, r.db.NSPEC_AB)
             out.append((r.rho_ac_kl, r.kappa_ac_kl))
+        return out
+
+    def hess_kernels_ac(self):
+        """[(hess_ac_kl, hess_rho_ac_kl, hess_kappa_ac_kl)] per rank."""
+        out = []
+        for r in self.ranks:
+            n = r.db.NSPEC_AB
+            h = [np.zeros((n, 5, 5, 5), np.float32) for _ in range(3)]
+            r.lib.transfer_kernels_hess_ac_tohost(r.Mesh_pointer, *h, n)
+            out.append(tuple(h))
         return out
 
     def hess_kernels(self):

@@ -139,7 +139,7 @@ class DeviceRank:
                 db.coupling_ac_el_ispec, db.coupling_ac_el_ijk, db.coupling_ac_el_normal, db.coupling_ac_el_jacobian2Dw,
                 *col["acoustic"])
             if sim.SIMULATION_TYPE == 3:
-                L.prepare_fields_acoustic_adj_dev(self.Mesh_pointer, 0)
+                L.prepare_fields_acoustic_adj_dev(self.Mesh_pointer, int(sim.APPROXIMATE_HESS_KL))
         if self.ELASTIC:
             att = sim.att[self.rank] if sim.att is not None else None
             nspec = db.NSPEC_AB

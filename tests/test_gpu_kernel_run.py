@@ -281,3 +281,29 @@ def test_coupled_kernel_run_matches_oracle(device_lib):
         assert np.abs(ref).max() > 0, name
         assert rel_l2(mine.reshape(nspec, 125), ref) <= 2 * KERNEL_RTOL, name
     k.cleanup()
+
+
+def test_acoustic_hessian_kernels_match_oracle(device_lib):
+    """APPROXIMATE_HESS_KL in the fluid (compute_kernels_hess_cuda with ACOUSTIC_SIMULATION, transfer_kernels_hess_ac_tohost)."""
+    from oracle.adjoint import OracleAcousticKernelRun, OracleForwardRun
+    from specfem3d_b200.kernel_run import KernelRun, run_forward_and_save
+    from test_oracle_kernel_run import acoustic_adjoint_source, acoustic_kernel_sim
+
+    def sim(st):
+        s = acoustic_kernel_sim((1, 1), 100, sim_type=st)
+        s.APPROXIMATE_HESS_KL = st == 3
+        return s
+
+    ofwd = OracleForwardRun(sim(1)).run()
+    adj = acoustic_adjoint_source(ofwd.seis_p)
+    ok = OracleAcousticKernelRun(sim(3), ofwd.record, adj).run()
+    fwd, prod = run_forward_and_save(sim(1), lib=device_lib)
+    fwd.cleanup()
+    k = KernelRun(sim(3), prod, adj, lib=device_lib).run()
+    mine = k.hess_kernels_ac()[0]
+    n = mine[0].shape[0]
+    for i, ref in enumerate((ok.hess_ac_kl[0], ok.hess_rho_ac_kl[0], ok.hess_kappa_ac_kl[0])):
+        assert np.abs(ref).max() > 0, i
+        # the reconstructed potential_dot / _dot_dot are first / second time derivatives of a field known to ~1e-4
+        assert rel_l2(mine[i].reshape(n, 125), ref) <= 4 * KERNEL_RTOL, i
+    k.cleanup()
