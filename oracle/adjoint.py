@@ -187,6 +187,27 @@ class OracleKernelRun:
             self.rho_kl[r][el] += dt * rho[el]
             self.mu_kl[r][el] += dt * mu[el]
             self.kappa_kl[r][el] += dt * ka[el]
+            if getattr(self.sim, "ANISOTROPIC_KL", False):
+                # compute_strain_product (compute_kernels.f90:700-760): full strains in Voigt order xx, yy, zz, yz, xz, xy
+                def voigt(s):
+                    t3 = s["epsilon_trace_over_3"]
+                    xx, yy = s["epsilondev_xx"] + t3, s["epsilondev_yy"] + t3
+                    return [xx, yy, -(xx + yy) + np.float32(3) * t3, s["epsilondev_yz"], s["epsilondev_xz"], s["epsilondev_xy"]]
+                ev, bv = voigt(e), voigt(b)
+                if not hasattr(self, "cijkl_kl"):
+                    self.cijkl_kl = [np.zeros((d.NSPEC_AB, 125, 21), np.float32) for d in self.sim.dbs]
+                p21 = 0
+                for i in range(6):
+                    for j in range(i, 6):
+                        prod = ev[i] * bv[j]
+                        if j > i:
+                            prod = prod + ev[j] * bv[i]
+                            if j > 2 and i < 3:
+                                prod = prod * np.float32(2)
+                        if i > 2:
+                            prod = prod * np.float32(4)
+                        self.cijkl_kl[r][el, :, p21] += (dt * prod)[el]
+                        p21 += 1
 
     # ----------------------------------------------------------------------------------------------------------------
     def step(self):

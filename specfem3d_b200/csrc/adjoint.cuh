@@ -51,7 +51,36 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_add_adjoint_sources_el(realw* 
 // rho_kl, mu_kl, kappa_kl += deltat * (interaction of the adjoint and the reconstructed forward wavefield)
 // (replaces compute_kernels_cudakernel, kernels/compute_kernels_cudakernel.cu:108-165; CPU compute_kernels_el,
 // compute_kernels.f90:123-190).  HESS: the approximate-Hessian pre-conditioner terms of compute_kernels_hess_el_cudakernel.
+// ANISOTROPIC_KL: the 21 products eps_i b_eps_j of the two full strain tensors in Voigt order (xx, yy, zz, yz, xz, xy), with
+// the symmetry factors of compute_strain_product (compute_kernels.f90:700-760; GPU compute_kernels_ani_cudakernel :80-100);
+// accumulated into planes cijkl_kl[ispec][21][128]
+__device__ __forceinline__ void accumulate_cijkl(realw* cijkl_elem /* + t */, realw deltat, realw exx, realw eyy, realw exy, realw exz,
+                                                 realw eyz, realw etr3, realw bxx, realw byy, realw bxy, realw bxz, realw byz,
+                                                 realw btr3) {
+  realw eps[6], b_eps[6];
+  eps[0] = exx + etr3; eps[1] = eyy + etr3; eps[2] = -(eps[0] + eps[1]) + 3 * etr3;
+  eps[3] = eyz; eps[4] = exz; eps[5] = exy;
+  b_eps[0] = bxx + btr3; b_eps[1] = byy + btr3; b_eps[2] = -(b_eps[0] + b_eps[1]) + 3 * btr3;
+  b_eps[3] = byz; b_eps[4] = bxz; b_eps[5] = bxy;
+  int p = 0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+#pragma unroll
+    for (int j = i; j < 6; ++j) {
+      realw prod = eps[i] * b_eps[j];
+      if (j > i) {
+        prod = prod + eps[j] * b_eps[i];
+        if (j > 2 && i < 3) prod = prod * 2;
+      }
+      if (i > 2) prod = prod * 4;
+      cijkl_elem[(size_t)p * NGLL3_PADDED] += deltat * prod;
+      ++p;
+    }
+  }
+}
+
 struct KernelArgs {
+  realw* cijkl_kl = nullptr;  // != nullptr: ANISOTROPIC_KL, replaces mu_kl / kappa_kl
   const int *ispec_is_elastic, *ibool;
   const realw *accel, *b_displ, *b_accel, *b_veloc;
   const realw *eps_xx, *eps_yy, *eps_xy, *eps_xz, *eps_yz, *eps_tr3;
@@ -76,8 +105,13 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_kernels_elastic(const KernelAr
   if (!HESS) {
     const realw exx = a.eps_xx[off], eyy = a.eps_yy[off], exy = a.eps_xy[off], exz = a.eps_xz[off], eyz = a.eps_yz[off];
     a.rho_kl[off] += a.deltat * (a.accel[g0] * a.b_displ[g0] + a.accel[g1] * a.b_displ[g1] + a.accel[g2] * a.b_displ[g2]);
-    a.mu_kl[off] += a.deltat * (exx * bxx + eyy * byy + (exx + eyy) * (bxx + byy) + 2 * (exy * bxy + exz * bxz + eyz * byz));
-    a.kappa_kl[off] += a.deltat * (9 * a.eps_tr3[off] * btr);
+    if (a.cijkl_kl) {
+      accumulate_cijkl(a.cijkl_kl + (size_t)ispec * 21 * NGLL3_PADDED + t, a.deltat, exx, eyy, exy, exz, eyz, a.eps_tr3[off], bxx, byy,
+                       bxy, bxz, byz, btr);
+    } else {
+      a.mu_kl[off] += a.deltat * (exx * bxx + eyy * byy + (exx + eyy) * (bxx + byy) + 2 * (exy * bxy + exz * bxz + eyz * byz));
+      a.kappa_kl[off] += a.deltat * (9 * a.eps_tr3[off] * btr);
+    }
   } else {
     a.hess_kl[off] += a.deltat * (a.accel[g0] * a.b_accel[g0] + a.accel[g1] * a.b_accel[g1] + a.accel[g2] * a.b_accel[g2]);
     const realw vx = a.b_veloc[g0], vy = a.b_veloc[g1], vz = a.b_veloc[g2];
@@ -108,6 +142,7 @@ struct KlPairArgs {
   const realw* displ[2];  // 0 = adjoint wavefield (displ), 1 = reconstructed forward wavefield (b_displ)
   realw* accel[2];
   realw *mu_kl, *kappa_kl, *hess_mu_kl, *hess_kappa_kl;  // hess_* may be nullptr
+  realw* cijkl_kl;                                       // != nullptr: ANISOTROPIC_KL, replaces mu_kl / kappa_kl
   realw deltat;
   int use_atomics;
   size_t nglob;
@@ -251,9 +286,14 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_elastic_forces_kl_pair(const K
     }
   }
   if (active) {
-    a.mu_kl[off] += a.deltat * (e_xx[0] * e_xx[1] + e_yy[0] * e_yy[1] + (e_xx[0] + e_yy[0]) * (e_xx[1] + e_yy[1]) +
-                                2 * (e_xy[0] * e_xy[1] + e_xz[0] * e_xz[1] + e_yz[0] * e_yz[1]));
-    a.kappa_kl[off] += a.deltat * (9 * e_tr3[0] * e_tr3[1]);
+    if (a.cijkl_kl) {
+      accumulate_cijkl(a.cijkl_kl + (size_t)ispec * 21 * NGLL3_PADDED + t, a.deltat, e_xx[0], e_yy[0], e_xy[0], e_xz[0], e_yz[0],
+                       e_tr3[0], e_xx[1], e_yy[1], e_xy[1], e_xz[1], e_yz[1], e_tr3[1]);
+    } else {
+      a.mu_kl[off] += a.deltat * (e_xx[0] * e_xx[1] + e_yy[0] * e_yy[1] + (e_xx[0] + e_yy[0]) * (e_xx[1] + e_yy[1]) +
+                                  2 * (e_xy[0] * e_xy[1] + e_xz[0] * e_xz[1] + e_yz[0] * e_yz[1]));
+      a.kappa_kl[off] += a.deltat * (9 * e_tr3[0] * e_tr3[1]);
+    }
     if (a.hess_mu_kl) {
       a.hess_mu_kl[off] += a.deltat * (e_xx[1] * e_xx[1] + e_yy[1] * e_yy[1] + (e_xx[1] + e_yy[1]) * (e_xx[1] + e_yy[1]) +
                                        2 * (e_xy[1] * e_xy[1] + e_xz[1] * e_xz[1] + e_yz[1] * e_yz[1]));

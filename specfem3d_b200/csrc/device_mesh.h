@@ -161,6 +161,7 @@ struct DeviceMesh {
         *d_b_epsilondev_xz = nullptr, *d_b_epsilondev_yz = nullptr;                              // [NSPEC][128]
   realw *d_epsilon_trace_over_3 = nullptr, *d_b_epsilon_trace_over_3 = nullptr;                  // [NSPEC][128]
   realw *d_rho_kl = nullptr, *d_mu_kl = nullptr, *d_kappa_kl = nullptr;                          // [NSPEC][128]
+  realw* d_cijkl_kl = nullptr;                                                                   // [NSPEC][21][128], ANISOTROPIC_KL
   realw *d_hess_el_kl = nullptr, *d_hess_rho_el_kl = nullptr, *d_hess_kappa_el_kl = nullptr, *d_hess_mu_el_kl = nullptr;
   int anisotropic_kl = 0, approximate_hess_kl = 0;
   int nadj_rec_local = 0, ntstep_between_read_adjsrc = 0;

@@ -509,7 +509,7 @@ extern "C" void SB200_FC(prepare_cleanup_device)(long* Mesh_pointer, int* ACOUST
                    mp->d_b_displ, mp->d_b_veloc, mp->d_b_accel, mp->d_b_epsilondev_xx, mp->d_b_epsilondev_yy,
                    mp->d_b_epsilondev_xy, mp->d_b_epsilondev_xz, mp->d_b_epsilondev_yz, mp->d_epsilon_trace_over_3,
                    mp->d_b_epsilon_trace_over_3, mp->d_rho_kl, mp->d_mu_kl, mp->d_kappa_kl, mp->d_hess_el_kl,
-                   mp->d_hess_rho_el_kl, mp->d_hess_kappa_el_kl, mp->d_hess_mu_el_kl, mp->d_source_adjoint,
+                   mp->d_hess_rho_el_kl, mp->d_hess_kappa_el_kl, mp->d_hess_mu_el_kl, mp->d_source_adjoint, mp->d_cijkl_kl,
                    mp->d_rmass_ocean_load, mp->d_ocean_iglob, mp->d_ocean_normal,
                    mp->d_b_send_accel_buffer, mp->d_b_potential, mp->d_b_potential_dot, mp->d_b_potential_dot_dot,
                    mp->d_rho_ac_kl, mp->d_kappa_ac_kl, mp->d_b_send_potential_buffer, mp->d_hess_ac_kl, mp->d_hess_rho_ac_kl,
@@ -898,7 +898,7 @@ extern "C" void SB200_FC(compute_forces_viscoelastic_cuda)(long* Mesh_pointer, i
       a.xix_regular = mp->xix_regular; a.jacobian_regular = mp->jacobian_regular;
       a.kappav = mp->d_kappav; a.muv = mp->d_muv;
       a.displ[0] = mp->d_displ; a.displ[1] = mp->d_b_displ; a.accel[0] = mp->d_accel; a.accel[1] = mp->d_b_accel;
-      a.mu_kl = mp->d_mu_kl; a.kappa_kl = mp->d_kappa_kl;
+      a.mu_kl = mp->d_mu_kl; a.kappa_kl = mp->d_kappa_kl; a.cijkl_kl = mp->d_cijkl_kl;
       a.hess_mu_kl = mp->approximate_hess_kl ? mp->d_hess_mu_el_kl : nullptr;
       a.hess_kappa_kl = mp->approximate_hess_kl ? mp->d_hess_kappa_el_kl : nullptr;
       a.deltat = *deltat;

@@ -73,6 +73,7 @@ class KernelRun(DeviceRun):
             n = r.db.NSPEC_AB
             r.rho_kl, r.mu_kl, r.kappa_kl = (np.zeros((n, 5, 5, 5), np.float32) for _ in range(3))
             r.rho_ac_kl, r.kappa_ac_kl = (np.zeros((n, 5, 5, 5), np.float32) for _ in range(2))
+            r.cijkl_kl = np.zeros((n, 5, 5, 5, 21), np.float32) if sim.ANISOTROPIC_KL else np.zeros(1, np.float32)
         # prepare_timerun.F90:425-430: b_deltat = - real(DT), b_deltatover2 = b_deltat/2, b_deltatsqover2 = b_deltat**2/2
         bdt = np.float32(-sim.deltat)
         self.dts = (float(sim.deltat), float(sim.deltatover2), float(sim.deltatsqover2))
@@ -265,11 +266,10 @@ class KernelRun(DeviceRun):
         """it_transfer_from_GPU: [(rho_kl, mu_kl, kappa_kl)] per rank, each (NSPEC, 5, 5, 5) raw interaction integrals
         (the sign / material scaling of save_adjoint_kernels is host post-processing)."""
         out = []
-        dummy = np.zeros(1, np.float32)
         for r in self.ranks:
             if r.ELASTIC:
-                r.lib.transfer_kernels_el_to_host(r.Mesh_pointer, r.rho_kl, r.mu_kl, r.kappa_kl, dummy, r.db.NSPEC_AB)
-            out.append((r.rho_kl, r.mu_kl, r.kappa_kl))
+                r.lib.transfer_kernels_el_to_host(r.Mesh_pointer, r.rho_kl, r.mu_kl, r.kappa_kl, r.cijkl_kl, r.db.NSPEC_AB)
+            out.append((r.rho_kl, r.cijkl_kl) if self.sim.ANISOTROPIC_KL else (r.rho_kl, r.mu_kl, r.kappa_kl))
         return out
 
     def kernels_ac(self):

@@ -41,6 +41,7 @@ class Simulation:
     SIMULATION_TYPE: int = 1     # 1 forward, 3 kernel run (adjoint + reconstructed forward wavefield), kernel_run.py
     SAVE_FORWARD: bool = False   # forward run keeps the absorbed Stacey tractions of every step and the last frame
     APPROXIMATE_HESS_KL: bool = False
+    ANISOTROPIC_KL: bool = False  # cijkl_kl (21 per point) instead of mu_kl / kappa_kl
 
     @property
     def deltat(self) -> np.float32:

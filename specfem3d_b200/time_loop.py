@@ -181,8 +181,8 @@ class DeviceRank:
                 z = np.zeros((nspec, 5, 5, 5), np.float32)
                 L.prepare_fields_elastic_adj_dev(
                     self.Mesh_pointer, 3 * db.NGLOB_AB, z, z, z, z, z, z, z, R_size, *([dummy] * 7),
-                    np.zeros(N_SLS, np.float32), np.zeros(N_SLS, np.float32), np.zeros(N_SLS, np.float32), 0,
-                    int(sim.APPROXIMATE_HESS_KL))
+                    np.zeros(N_SLS, np.float32), np.zeros(N_SLS, np.float32), np.zeros(N_SLS, np.float32),
+                    int(sim.ANISOTROPIC_KL), int(sim.APPROXIMATE_HESS_KL))
         if sim.SIMULATION_TYPE == 3:  # prepare_gpu.f90:264-270
             L.prepare_sim2_or_3_const_device(self.Mesh_pointer, self.nrec_local, sim.NSTEP, H["hxir"], H["hetar"],
                                              H["hgammar"], nrec, H["islice_rec"], H["ispec_rec"])

@@ -307,3 +307,36 @@ def test_acoustic_hessian_kernels_match_oracle(device_lib):
         # the reconstructed potential_dot / _dot_dot are first / second time derivatives of a field known to ~1e-4
         assert rel_l2(mine[i].reshape(n, 125), ref) <= 4 * KERNEL_RTOL, i
     k.cleanup()
+
+
+@pytest.mark.parametrize("fused", [1, 0])
+def test_anisotropic_kernels_match_oracle(device_lib, fused, monkeypatch):
+    """ANISOTROPIC_KL: the 21 cijkl kernels (compute_kernels_ani_cudakernel) from the two-wavefield launch and from the
+    stored-strain path against the oracle's restatement of compute_strain_product; rho_kl unchanged."""
+    from oracle.adjoint import OracleForwardRun, OracleKernelRun
+    from specfem3d_b200.kernel_run import KernelRun, run_forward_and_save
+
+    monkeypatch.setenv("SPECFEM_B200_KL_FUSED", str(fused))
+    nstep = 120
+
+    def sim3():
+        s = kernel_sim((1, 1), nstep, sim_type=3)
+        s.ANISOTROPIC_KL = True
+        return s
+
+    ofwd = OracleForwardRun(kernel_sim((1, 1), nstep)).run()
+    adj = adjoint_source(ofwd.seis_d)
+    ok = OracleKernelRun(sim3(), ofwd.record, adj).run()
+    fwd, prod = run_forward_and_save(kernel_sim((1, 1), nstep), lib=device_lib)
+    fwd.cleanup()
+    k = KernelRun(sim3(), prod, adj, lib=device_lib).run()
+    rho, cijkl = k.kernels()[0]
+    n = rho.shape[0]
+    assert rel_l2(rho.reshape(n, 125), ok.rho_kl[0]) <= KERNEL_RTOL
+    ref = ok.cijkl_kl[0]
+    mine = cijkl.reshape(n, 125, 21)
+    assert np.abs(ref).max() > 0
+    assert rel_l2(mine, ref) <= KERNEL_RTOL
+    for p21 in range(21):
+        assert rel_l2(mine[..., p21], ref[..., p21]) <= 4 * KERNEL_RTOL, p21
+    k.cleanup()

@@ -167,3 +167,23 @@ def test_coupled_kernel_run_oracle_reconstruction():
     for name in ("rho_kl", "mu_kl", "kappa_kl", "rho_ac_kl", "kappa_ac_kl"):
         a = getattr(k, name)[0]
         assert np.isfinite(a).all() and np.abs(a).max() > 0, name
+
+
+def test_anisotropic_kernels_contain_the_isotropic_ones():
+    """ANISOTROPIC_KL: summing the nine normal-strain products of cijkl_kl gives kappa_kl (9 tr/3 b_tr/3 = sum_ij eps_ii b_eps_jj),
+    which pins the Voigt ordering and the symmetry factors of the oracle's compute_strain_product restatement."""
+    from oracle.adjoint import OracleForwardRun, OracleKernelRun
+
+    fwd = OracleForwardRun(kernel_sim((1, 1), 60)).run()
+    s = kernel_sim((1, 1), 60, sim_type=3)
+    s.ANISOTROPIC_KL = True
+    k = OracleKernelRun(s, fwd.record, adjoint_source(fwd.seis_d)).run()
+    idx, p = {}, 0
+    for i in range(6):
+        for j in range(i, 6):
+            idx[(i, j)] = p
+            p += 1
+    c = k.cijkl_kl[0]
+    kappa = sum(c[..., idx[q]] for q in ((0, 0), (1, 1), (2, 2), (0, 1), (0, 2), (1, 2)))
+    assert rel_l2(kappa, k.kappa_kl[0]) < 1e-5
+    # shear part: 2 mu_kl-like combination of the deviatoric products is covered by the GPU comparison of all 21 planes
