@@ -336,4 +336,61 @@ void mg_greedy_color(int64_t nspec, int64_t nglob, const int32_t* ibool, const i
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Dual graph of the element mesh: elements that share at least `ncommonnodes` corner nodes are neighbours
+// (restates mesh2dual_ncommonnodes, src/decompose_mesh/part_decompose_mesh.F90:49-149, step by step so that xadj / adjncy
+// come out in the same order: neighbours are appended to BOTH elements of a pair in the order the node loop discovers them).
+// elmnts: [nspec][8] corner node ids (0-based); nsize: upper bound of elements around a node; sup_neighbor: upper bound of
+// neighbours per element.  Returns the number of edges entries (= xadj[nspec]) or -1 when sup_neighbor is too small.
+// ---------------------------------------------------------------------------------------------------------------
+int64_t mg_dual_graph(int64_t nspec, int64_t nnodes, int nsize, int sup_neighbor, const int32_t* elmnts, int ncommonnodes,
+                      int32_t* xadj /*[nspec+1]*/, int32_t* adjncy /*[sup_neighbor*nspec]*/, int32_t* max_neighbor) {
+  std::vector<int32_t> nnodes_elmnts(nnodes, 0), nodes_elmnts((size_t)nsize * nnodes, 0);
+  for (int64_t i = 0; i <= nspec; ++i) xadj[i] = 0;
+  for (int64_t i = 0; i < (int64_t)sup_neighbor * nspec; ++i) adjncy[i] = 0;
+  for (int64_t i = 0; i < 8 * nspec; ++i) {
+    const int32_t nd = elmnts[i];
+    if (nnodes_elmnts[nd] >= nsize) return -1;
+    nodes_elmnts[(size_t)nd * nsize + nnodes_elmnts[nd]] = (int32_t)(i / 8);
+    nnodes_elmnts[nd] += 1;
+  }
+  for (int64_t j = 0; j < nnodes; ++j) {
+    for (int k = 0; k < nnodes_elmnts[j]; ++k) {
+      for (int l = k + 1; l < nnodes_elmnts[j]; ++l) {
+        const int32_t elem_base = nodes_elmnts[k + j * nsize], elem_target = nodes_elmnts[l + j * nsize];
+        int connectivity = 0;
+        for (int n = 0; n < 8; ++n) {
+          const int32_t num_node = elmnts[8 * (int64_t)elem_base + n];
+          for (int m = 0; m < nnodes_elmnts[num_node]; ++m)
+            if (nodes_elmnts[m + (int64_t)num_node * nsize] == elem_target) connectivity += 1;
+        }
+        if (connectivity < ncommonnodes) continue;
+        bool is_neighbor = false;
+        // the reference scans one entry past the filled part (m = 0 .. xadj); that extra entry is a zero-initialised or
+        // not yet written slot and can only match element 0 spuriously when element 0 is the target and the slot is
+        // still zero -- reproduced as written
+        for (int m = 0; m <= xadj[elem_base] && m < sup_neighbor; ++m)
+          if (!is_neighbor && adjncy[(int64_t)elem_base * sup_neighbor + m] == elem_target) is_neighbor = true;
+        if (is_neighbor) continue;
+        if (xadj[elem_base] >= sup_neighbor || xadj[elem_target] >= sup_neighbor) return -1;
+        adjncy[(int64_t)elem_base * sup_neighbor + xadj[elem_base]] = elem_target;
+        xadj[elem_base] += 1;
+        adjncy[(int64_t)elem_target * sup_neighbor + xadj[elem_target]] = elem_base;
+        xadj[elem_target] += 1;
+      }
+    }
+  }
+  int32_t mx = 0;
+  for (int64_t i = 0; i < nspec; ++i) mx = xadj[i] > mx ? xadj[i] : mx;
+  *max_neighbor = mx;
+  int64_t nb_edges = 0;
+  for (int64_t i = 0; i < nspec; ++i) {  // compaction in place (reads are never behind the writes)
+    const int32_t k = xadj[i];
+    xadj[i] = (int32_t)nb_edges;
+    for (int32_t j = 0; j < k; ++j) adjncy[nb_edges++] = adjncy[i * sup_neighbor + j];
+  }
+  xadj[nspec] = (int32_t)nb_edges;
+  return nb_edges;
+}
+
 }  // extern "C"

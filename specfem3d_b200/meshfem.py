@@ -291,36 +291,70 @@ def _face_geometry(gll: GLL, corners_elem: np.ndarray, iface: int):
 
 
 # ----------------------------------------------------------------------------------------------------------------
-def build_partition(spec: BoxSpec, myrank: int, gll: Optional[GLL] = None, with_metrics: bool = True) -> Database:
-    """Create the database of one slab (no mass matrices yet, see :func:`finalize_mass_matrices`)."""
+def build_partition(spec: BoxSpec, myrank: int, gll: Optional[GLL] = None, with_metrics: bool = True,
+                    part: Optional[np.ndarray] = None) -> Database:
+    """Create the database of one rank (no mass matrices yet, see :func:`finalize_mass_matrices`).
+
+    Default: meshfem3D's NPROC_XI x NPROC_ETA slabs.  ``part`` (one rank id per element of the whole box, element id =
+    ix + NEX_XI * (iy + NEX_ETA * iz)): an arbitrary element partition as decompose_mesh writes it -- the rank keeps its
+    elements in ascending global order (part_decompose_mesh.F90: build_glob2loc_elmnts), points are numbered by first touch,
+    neighbours are listed by ascending rank (write_interfaces_database) and the points of an interface are ordered by their
+    coordinates on both sides (get_MPI.f90), here through their structured grid coordinates."""
     gll = gll or GLL()
     mg = _meshgen()
-    if spec.nex_xi % spec.nproc_xi or spec.nex_eta % spec.nproc_eta:
-        raise ValueError("NEX must be a multiple of NPROC in each direction (Mesh_Par_file rule)")
-    ipx, ipy = myrank % spec.nproc_xi, myrank // spec.nproc_xi
-    nx, ny, nz = spec.nex_xi // spec.nproc_xi, spec.nex_eta // spec.nproc_eta, spec.ner
-    ix0, iy0 = ipx * nx, ipy * ny
-    nspec = nx * ny * nz
-    db = Database(myrank=myrank, NPROC=spec.nproc, NSPEC_AB=nspec, nx=nx, ny=ny, nz=nz, ix0=ix0, iy0=iy0)
-
-    # --- ibool ------------------------------------------------------------------------------------------------
-    ibool = np.empty((nspec, 5, 5, 5), dtype=np.int32)
-    GX, GY, GZ = 4 * nx + 1, 4 * ny + 1, 4 * nz + 1
-    grid_local = np.empty(GX * GY * GZ, dtype=np.int64)
-    nglob = int(mg.mg_box_ibool(nx, ny, nz, _p(ibool), _p(grid_local)))
-    assert nglob == GX * GY * GZ
-    db.ibool, db.NGLOB_AB = ibool, nglob
-    lgx = grid_local % GX
-    lgy = (grid_local // GX) % GY
-    lgz = grid_local // (GX * GY)
     GXg, GYg = 4 * spec.nex_xi + 1, 4 * spec.nex_eta + 1
-    ggx, ggy = lgx + 4 * ix0, lgy + 4 * iy0
-    db.grid_of_glob = ggx + GXg * (ggy + GYg * lgz)
-    db.extra["lg"] = (lgx.astype(np.int32), lgy.astype(np.int32), lgz.astype(np.int32))
+    if part is None:
+        if spec.nex_xi % spec.nproc_xi or spec.nex_eta % spec.nproc_eta:
+            raise ValueError("NEX must be a multiple of NPROC in each direction (Mesh_Par_file rule)")
+        ipx, ipy = myrank % spec.nproc_xi, myrank // spec.nproc_xi
+        nx, ny, nz = spec.nex_xi // spec.nproc_xi, spec.nex_eta // spec.nproc_eta, spec.ner
+        ix0, iy0 = ipx * nx, ipy * ny
+        nspec = nx * ny * nz
+        db = Database(myrank=myrank, NPROC=spec.nproc, NSPEC_AB=nspec, nx=nx, ny=ny, nz=nz, ix0=ix0, iy0=iy0)
+
+        # --- ibool --------------------------------------------------------------------------------------------
+        ibool = np.empty((nspec, 5, 5, 5), dtype=np.int32)
+        GX, GY, GZ = 4 * nx + 1, 4 * ny + 1, 4 * nz + 1
+        grid_local = np.empty(GX * GY * GZ, dtype=np.int64)
+        nglob = int(mg.mg_box_ibool(nx, ny, nz, _p(ibool), _p(grid_local)))
+        assert nglob == GX * GY * GZ
+        db.ibool, db.NGLOB_AB = ibool, nglob
+        lgx = grid_local % GX
+        lgy = (grid_local // GX) % GY
+        lgz = grid_local // (GX * GY)
+        ggx, ggy = lgx + 4 * ix0, lgy + 4 * iy0
+        db.grid_of_glob = ggx + GXg * (ggy + GYg * lgz)
+        db.extra["lg"] = (lgx.astype(np.int32), lgy.astype(np.int32), lgz.astype(np.int32))
+        e = np.arange(nspec, dtype=np.int64)
+        eix, eiy, eiz = e % nx + ix0, (e // nx) % ny + iy0, e // (nx * ny)
+    else:
+        part = np.asarray(part)
+        if part.shape != (spec.nex_xi * spec.nex_eta * spec.ner,):
+            raise ValueError("part must hold one rank per element of the whole box")
+        ids = np.nonzero(part == myrank)[0].astype(np.int64)
+        nspec = len(ids)
+        if nspec == 0:
+            raise ValueError(f"rank {myrank} owns no element")
+        eix, eiy, eiz = ids % spec.nex_xi, (ids // spec.nex_xi) % spec.nex_eta, ids // (spec.nex_xi * spec.nex_eta)
+        db = Database(myrank=myrank, NPROC=int(part.max()) + 1, NSPEC_AB=nspec)
+        # --- ibool: first-touch numbering, i fastest, elements in ascending order --------------------------------
+        o = np.arange(5, dtype=np.int64)
+        gx = 4 * eix[:, None, None, None] + o[None, None, None, :]
+        gy = 4 * eiy[:, None, None, None] + o[None, None, :, None]
+        gz = 4 * eiz[:, None, None, None] + o[None, :, None, None]
+        gid = (gx + GXg * (gy + GYg * gz)).reshape(-1)
+        uniq, first, inverse = np.unique(gid, return_index=True, return_inverse=True)
+        order = np.argsort(first, kind="stable")
+        local_of_uniq = np.empty(len(uniq), dtype=np.int64)
+        local_of_uniq[order] = np.arange(len(uniq))
+        ibool = (local_of_uniq[inverse] + 1).astype(np.int32).reshape(nspec, 5, 5, 5)
+        nglob = len(uniq)
+        db.ibool, db.NGLOB_AB = ibool, nglob
+        db.grid_of_glob = uniq[order]
+        lgx, lgy, lgz = db.grid_of_glob % GXg, (db.grid_of_glob // GXg) % GYg, db.grid_of_glob // (GXg * GYg)
+        db.extra["lg"] = (lgx.astype(np.int32), lgy.astype(np.int32), lgz.astype(np.int32))
 
     # --- element corners ---------------------------------------------------------------------------------------
-    e = np.arange(nspec, dtype=np.int64)
-    eix, eiy, eiz = e % nx + ix0, (e // nx) % ny + iy0, e // (nx * ny)
     db.extra["eijk"] = (eix, eiy, eiz)
     cx, cy, cz = _corner_coords(
         spec,
@@ -498,9 +532,31 @@ def build_partition(spec: BoxSpec, myrank: int, gll: Optional[GLL] = None, with_
     # --- MPI interfaces ------------------------------------------------------------------------------------------
     lgx32, lgy32, lgz32 = db.extra["lg"]
     neigh = []  # (rank, mask)
-    W, E, S, N = ipx > 0, ipx < spec.nproc_xi - 1, ipy > 0, ipy < spec.nproc_eta - 1
-    rank_of = lambda a, b: b * spec.nproc_xi + a
-    on_w, on_e, on_s, on_n = lgx32 == 0, lgx32 == GX - 1, lgy32 == 0, lgy32 == GY - 1
+    if part is not None:
+        # every rank that owns one of the (up to eight) elements around a point shares that point
+        gx_, gy_, gz_ = lgx32.astype(np.int64), lgy32.astype(np.int64), lgz32.astype(np.int64)
+        shared = {}
+        for dx in (0, 1):
+            ex = gx_ // 4 - dx
+            okx = (ex >= 0) & (ex < spec.nex_xi) & ((dx == 0) | (gx_ % 4 == 0))
+            for dy in (0, 1):
+                ey = gy_ // 4 - dy
+                oky = (ey >= 0) & (ey < spec.nex_eta) & ((dy == 0) | (gy_ % 4 == 0))
+                for dz in (0, 1):
+                    ez = gz_ // 4 - dz
+                    ok = okx & oky & (ez >= 0) & (ez < spec.ner) & ((dz == 0) | (gz_ % 4 == 0))
+                    r_ = np.full(nglob, -1, dtype=np.int64)
+                    r_[ok] = part[ex[ok] + spec.nex_xi * (ey[ok] + spec.nex_eta * ez[ok])]
+                    for r in np.unique(r_[ok]):
+                        if r != myrank:
+                            shared[int(r)] = shared.get(int(r), np.zeros(nglob, bool)) | (r_ == r)
+        neigh = [(r, shared[r]) for r in sorted(shared)]
+        W = E = S = N = False
+        on_w = on_e = on_s = on_n = None
+    else:
+        W, E, S, N = ipx > 0, ipx < spec.nproc_xi - 1, ipy > 0, ipy < spec.nproc_eta - 1
+        rank_of = lambda a, b: b * spec.nproc_xi + a
+        on_w, on_e, on_s, on_n = lgx32 == 0, lgx32 == GX - 1, lgy32 == 0, lgy32 == GY - 1
     if W:
         neigh.append((rank_of(ipx - 1, ipy), on_w))
     if E:
@@ -752,10 +808,12 @@ def invert_mass(a: np.ndarray) -> np.ndarray:
     return (np.float32(1.0) / a).astype(np.float32)
 
 
-def build_all(spec: BoxSpec, DT: float, gll: Optional[GLL] = None) -> List[Database]:
-    """All partitions in one process with assembled + inverted mass matrices (used by tests and N=1 runs)."""
+def build_all(spec: BoxSpec, DT: float, gll: Optional[GLL] = None, part: Optional[np.ndarray] = None) -> List[Database]:
+    """All partitions in one process with assembled + inverted mass matrices (used by tests and N=1 runs).  ``part``: an
+    arbitrary element partition (see :func:`build_partition`) instead of the NPROC_XI x NPROC_ETA slabs."""
     gll = gll or GLL()
-    dbs = [build_partition(spec, r, gll) for r in range(spec.nproc)]
+    nproc = spec.nproc if part is None else int(np.asarray(part).max()) + 1
+    dbs = [build_partition(spec, r, gll, part=part) for r in range(nproc)]
     if spec.pml_thickness > 0:
         from .pml import set_local_dampingcoeff
 
@@ -766,7 +824,7 @@ def build_all(spec: BoxSpec, DT: float, gll: Optional[GLL] = None) -> List[Datab
     for key in ("rmassx", "rmassy", "rmassz", "rmass_acoustic", "rmass_ocean_load"):
         if all(key in l for l in loc):
             arrs = [l[key] for l in loc]
-            if spec.nproc > 1:
+            if len(dbs) > 1:
                 assemble_scalar_in_process(dbs, arrs)
             for db, a in zip(dbs, arrs):
                 setattr(db, key, invert_mass(a))

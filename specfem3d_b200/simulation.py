@@ -89,9 +89,11 @@ class Simulation:
 
 
 def make_simulation(spec: BoxSpec, DT: float, NSTEP: int, sources: Sequence = (), stations: Sequence[Station] = (),
-                    attenuation: bool = False, f0_attenuation: float = 0.0, **kw) -> Simulation:
+                    attenuation: bool = False, f0_attenuation: float = 0.0, part=None, **kw) -> Simulation:
+    """``part``: optional element partition (one rank per element of the box, see meshfem.build_partition / decompose.py)
+    instead of the NPROC_XI x NPROC_ETA slabs."""
     gll = GLL()
-    dbs = build_all(spec, DT, gll)
+    dbs = build_all(spec, DT, gll, part=part)
     acoustic_present = any(db.nspec_acoustic > 0 for db in dbs)
     src = setup_sources(spec, dbs, sources, DT, gll, acoustic_present) if len(sources) else None
     rec = setup_receivers(spec, dbs, stations, gll) if len(stations) else None

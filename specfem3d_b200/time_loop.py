@@ -259,7 +259,7 @@ class DeviceRun:
         else:
             ids = list(range(len(sim.dbs))) if ranks is None else ranks
             self.ranks = [DeviceRank(sim, r, lib).prepare() for r in ids]
-        self.NPROC = sim.spec.nproc
+        self.NPROC = len(sim.dbs)  # slabs: spec.nproc; arbitrary partitions (decompose.py): number of parts
         if exchange is not None:
             self.exchange = exchange or None
         elif halo == "p2p" and self.NPROC > 1:

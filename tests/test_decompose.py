@@ -1,0 +1,99 @@
+"""Element partitioning: dual graph of mesh2dual_ncommonnodes, element loads, and databases
+for ARBITRARY partition arrays (local first-touch numbering, interfaces by ascending neighbour rank with coordinate-ordered
+points, inner / outer elements).  SCOTCH itself cannot be built here, so part[] comes from a stand-in partitioner and from
+hand-made irregular partitions; bit parity of part[] with SCOTCH is unpinned (specfem3d_b200/decompose.py)."""
+import numpy as np
+import pytest
+
+from specfem3d_b200.configs import HALFSPACE
+from specfem3d_b200.decompose import corner_connectivity, dual_graph, element_loads, partition_graph_growing
+from specfem3d_b200.meshfem import BoxSpec, Material
+from specfem3d_b200.simulation import make_simulation
+from specfem3d_b200.sources_receivers import CMTSource, Station
+
+
+def box(nex=(6, 5, 4), **kw):
+    return BoxSpec(nex[0], nex[1], nex[2], xmax=1100.0 * nex[0], ymax=900.0 * nex[1], zmin=-1000.0 * nex[2],
+                   materials=kw.pop("materials", (HALFSPACE,)), deform=0.1, **kw)
+
+
+@pytest.mark.parametrize("ncommonnodes", [1, 2, 4])
+def test_dual_graph_is_the_ncommonnodes_neighbourhood(ncommonnodes):
+    spec = box()
+    nx, ny, nz = spec.nex_xi, spec.nex_eta, spec.ner
+    xadj, adjncy, max_neighbor = dual_graph(spec, ncommonnodes)
+    assert xadj[0] == 0 and xadj[-1] == len(adjncy) and max_neighbor == {1: 26, 2: 18, 4: 6}[ncommonnodes]
+    for e in range(nx * ny * nz):
+        ix, iy, iz = e % nx, (e // nx) % ny, e // (nx * ny)
+        ref = set()
+        for dz in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                for dx in (-1, 0, 1):
+                    shared = 8 >> (abs(dx) + abs(dy) + abs(dz))  # a face shares 4 corners, an edge 2, a corner 1
+                    jx, jy, jz = ix + dx, iy + dy, iz + dz
+                    if (dx, dy, dz) != (0, 0, 0) and shared >= ncommonnodes and 0 <= jx < nx and 0 <= jy < ny and 0 <= jz < nz:
+                        ref.add(jx + nx * (jy + ny * jz))
+        got = adjncy[xadj[e]:xadj[e + 1]]
+        assert len(got) == len(ref) and set(int(g) for g in got) == ref
+    # symmetric, and every pair listed in the order the node loop discovers it: the first neighbour of element 0 shares node 1
+    elm, _ = corner_connectivity(spec)
+    assert adjncy[xadj[0]] == 1 and set(elm[0]) & set(elm[1])
+
+
+def test_element_loads_follow_the_reference_constants():
+    water = Material(1020.0, 1500.0, 0.0, 9999.0, 9999.0, 1)
+    spec = box(materials=(HALFSPACE, water), layer_material=[0, 0, 0, 1])
+    loads = element_loads(spec)
+    assert set(loads[: 3 * 30]) == {41} and set(loads[3 * 30:]) == {10}
+    assert set(element_loads(spec, attenuation=True)[: 3 * 30]) == {59}
+
+
+def sim_for(part=None, nstep=100):
+    spec = box((6, 6, 4))
+    src = [CMTSource(0.52 * spec.xmax, 0.47 * spec.ymax, 0.55 * spec.zmin, (1e23, -2e23, 0.5e23, 0.3e23, -0.7e23, 0.2e23), hdur=0.3)]
+    sts = [Station("A", "XX", 0.21 * spec.xmax, 0.33 * spec.ymax, 0.0), Station("B", "XX", 0.7 * spec.xmax, 0.6 * spec.ymax, 0.0)]
+    return make_simulation(spec, DT=0.012, NSTEP=nstep, sources=src, stations=sts, part=part)
+
+
+def partitions():
+    spec = box((6, 6, 4))
+    xadj, adjncy, _ = dual_graph(spec, 1)
+    grown = partition_graph_growing(xadj, adjncy, element_loads(spec), 3)
+    n = 6 * 6 * 4
+    ix, iy, iz = np.arange(n) % 6, (np.arange(n) // 6) % 6, np.arange(n) // 36
+    ragged = ((ix + 2 * iy + iz) // 5) % 4  # diagonal bands with staircase boundaries: edge- and corner-only contacts
+    rng = np.random.default_rng(3)
+    ragged[rng.integers(0, n, 12)] = rng.integers(0, 4, 12)  # plus a few islands
+    return {"graph_growing_3": grown, "ragged_4": ragged.astype(np.int32)}
+
+
+@pytest.mark.parametrize("name", ["graph_growing_3", "ragged_4"])
+def test_arbitrary_partition_databases_and_run(name):
+    from oracle.solver import OracleRun
+
+    part = partitions()[name]
+    assert np.bincount(part).min() > 0
+    sim = sim_for(part)
+    assert sum(db.NSPEC_AB for db in sim.dbs) == len(part)
+    for db in sim.dbs:
+        nb_ranks = db.my_neighbors_ext_mesh[: db.num_interfaces_ext_mesh]
+        assert (np.diff(nb_ranks) > 0).all()  # ascending neighbour rank (write_interfaces_database)
+        # first-touch numbering: the first element's points are 1..125 in order
+        assert np.array_equal(db.ibool[0].ravel(), np.arange(1, 126))
+        for k in range(db.num_interfaces_ext_mesh):
+            nb = sim.dbs[int(nb_ranks[k])]
+            m = int(np.nonzero(nb.my_neighbors_ext_mesh[: nb.num_interfaces_ext_mesh] == db.myrank)[0][0])
+            cnt = int(db.nibool_interfaces_ext_mesh[k])
+            assert cnt == int(nb.nibool_interfaces_ext_mesh[m])
+            a = db.grid_of_glob[db.ibool_interfaces_ext_mesh[k, :cnt] - 1]
+            b = nb.grid_of_glob[nb.ibool_interfaces_ext_mesh[m, :cnt] - 1]
+            assert np.array_equal(a, b)  # same points in the same order on both sides
+        outer = np.zeros(db.NGLOB_AB, bool)
+        for k in range(db.num_interfaces_ext_mesh):
+            outer[db.ibool_interfaces_ext_mesh[k, : db.nibool_interfaces_ext_mesh[k]] - 1] = True
+        touches = outer[db.ibool.reshape(db.NSPEC_AB, 125) - 1].any(axis=1)
+        assert np.array_equal(touches, db.ispec_is_inner == 0)
+    one, many = OracleRun(sim_for()).run(), OracleRun(sim).run()
+    assert np.abs(one.seis_d).max() > 0
+    # summation order at the shared points differs (and the oracle's OpenMP scatter is not ordered): a few 1e-5 after 100 steps
+    assert np.linalg.norm(many.seis_d - one.seis_d) <= 1e-4 * np.linalg.norm(one.seis_d)
