@@ -90,14 +90,18 @@ class DistributedExchange:
 
     # ------------------------------------------------------------------------------------------------------------------
     def exchange(self, kind: str):
-        if self.mode == "p2p":
+        if self.mode == "p2p" and not kind.startswith("b_"):
             return  # the payload went GPU -> GPU inside the pack kernel
+        # (the b_ fields of a kernel run always travel through the host buffers: the library's FORWARD_OR_ADJOINT = 3 halo
+        # entry points are the host-staged ones)
         import torch
         import torch.distributed as dist
 
         r, db = self.r, self.r.db
-        send = r.buffer_send_vector if kind == "vector" else r.buffer_send_scalar
-        recv = r.buffer_recv_vector if kind == "vector" else r.buffer_recv_scalar
+        send = getattr(r, {"vector": "buffer_send_vector", "scalar": "buffer_send_scalar", "b_vector": "b_buffer_send_vector",
+                           "b_scalar": "b_buffer_send_scalar"}[kind])
+        recv = getattr(r, {"vector": "buffer_recv_vector", "scalar": "buffer_recv_scalar", "b_vector": "b_buffer_recv_vector",
+                           "b_scalar": "b_buffer_recv_scalar"}[kind])
         reqs, keep = [], []
         for n in range(db.num_interfaces_ext_mesh):
             cnt = int(db.nibool_interfaces_ext_mesh[n])

@@ -44,10 +44,18 @@ def _worker(rank, world, port, out_dir):
     r.buffer_recv_vector = np.zeros((ni, mx, 3), np.float32)
     r.buffer_send_scalar = np.zeros((ni, mx), np.float32)
     r.buffer_recv_scalar = np.zeros((ni, mx), np.float32)
+    # the b_ buffers of a kernel run (reconstructed wavefield) use the same plumbing
+    r.b_buffer_send_vector = np.full((ni, mx, 3), float(10 * (rank + 1)), np.float32)
+    r.b_buffer_recv_vector = np.zeros((ni, mx, 3), np.float32)
+    r.b_buffer_send_scalar = np.full((ni, mx), float(100 * (rank + 1)), np.float32)
+    r.b_buffer_recv_scalar = np.zeros((ni, mx), np.float32)
     ex = DistributedExchange(r, dist.group.WORLD, mode="host")
     ex.exchange("vector")
+    ex.exchange("b_vector")
+    ex.exchange("b_scalar")
     cnt = db.nibool_interfaces_ext_mesh[0]
-    ok = np.all(r.buffer_recv_vector[0, :cnt] == float(2 - rank))
+    ok = (np.all(r.buffer_recv_vector[0, :cnt] == float(2 - rank)) and np.all(r.b_buffer_recv_vector[0, :cnt] == float(10 * (2 - rank)))
+          and np.all(r.b_buffer_recv_scalar[0, :cnt] == float(100 * (2 - rank))))
     np.save(os.path.join(out_dir, f"ok_{rank}.npy"), np.array([ok]))
     dist.destroy_process_group()
 
