@@ -19,11 +19,11 @@ a :class:`ForwardProducts` object.
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import List, Optional
+from typing import List
 
 import numpy as np
 
-from .time_loop import DeviceRank, DeviceRun
+from .time_loop import DeviceRun
 
 
 @dataclass
@@ -135,7 +135,7 @@ class KernelRun(DeviceRun):
         b_dt, b_dt2, _ = self.b_dts
         E = [r for r in self.ranks if r.ELASTIC]
         multi = self.NPROC > 1
-        both, fwd, bwd = foas == (0,), foas != (3,), foas != (1,)
+        fwd, bwd = foas != (3,), foas != (1,)
         foa = foas[0]
         for iphase in (1, 2):
             for r in E:
@@ -185,7 +185,6 @@ class KernelRun(DeviceRun):
                 r.lib.kernel_3_a_cuda(r.Mesh_pointer, dt2, b_dt2, 0, 1)
             if bwd:
                 r.lib.kernel_3_a_cuda(r.Mesh_pointer, dt2, b_dt2, 0, 3)
-        del both
 
     def _acoustic(self, it: int, foas):
         """foas = (0,): compute_forces_acoustic_GPU_calling (compute_forces_acoustic_calling_routine.f90:597-748);
