@@ -88,3 +88,42 @@ def compare_with_reference(syn_dir: str, ref_dir: str) -> Dict[str, Dict[str, fl
         shift = int(np.argmax(cc) - (n - 1)) if len(cc) > 1 else 0
         out[name] = {"corr": corr, "rel_l2": err, "shift": shift}
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# adjoint sources of a kernel run
+# ------------------------------------------------------------------------------------------------------------------
+def write_adjoint_sources(sim, adj: np.ndarray, sem_dir: str) -> List[str]:
+    """``SEM/NET.STA.<band>{X,Y,Z}.adj``: two-column ASCII ``time value`` like the seismograms, NSTEP lines per file."""
+    os.makedirs(sem_dir, exist_ok=True)
+    rec, t = sim.receivers, sim.time_axis()
+    bic = band_instrument_code(sim.DT * sim.NTSTEP_BETWEEN_OUTPUT_SAMPLE)
+    paths = []
+    for irec in range(rec.nrec):
+        st = rec.stations[irec]
+        for c, ch in enumerate("XYZ"):
+            path = os.path.join(sem_dir, f"{st.network}.{st.name}.{bic}{ch}.adj")
+            with open(path, "w") as f:
+                for ti, vi in zip(t, adj[irec, :, c]):
+                    f.write(f"  {_fortran_real(ti):>12}     {_fortran_real(vi):>16}\n")
+            paths.append(path)
+    return paths
+
+
+def read_adjoint_sources(sim, sem_dir: str) -> np.ndarray:
+    """compute_arrays_adjoint_source (src/specfem3D/compute_arrays_source.f90:203-291) for one chunk
+    (NTSTEP_BETWEEN_READ_ADJSRC = NSTEP): the second column of the three component files of every receiver, NSTEP samples
+    each (shorter files are an error, like the reference's 'file too short' stop), as (nrec, NSTEP, 3) float32.  The
+    reference stores them as read, in mesh x / y / z (SUPPRESS_UTM_PROJECTION) -- no rotation is applied here either."""
+    rec = sim.receivers
+    bic = band_instrument_code(sim.DT * sim.NTSTEP_BETWEEN_OUTPUT_SAMPLE)
+    out = np.zeros((rec.nrec, sim.NSTEP, 3), np.float32)
+    for irec in range(rec.nrec):
+        st = rec.stations[irec]
+        for c, ch in enumerate("XYZ"):
+            path = os.path.join(sem_dir, f"{st.network}.{st.name}.{bic}{ch}.adj")
+            a = read_seismogram(path)
+            if a.shape[0] < sim.NSTEP:
+                raise ValueError(f"{path}: file too short ({a.shape[0]} lines), NSTEP = {sim.NSTEP}")
+            out[irec, :, c] = a[: sim.NSTEP, 1].astype(np.float32)
+    return out

@@ -38,3 +38,23 @@ def test_write_read_round_trip_and_reference_metrics(tmp_path):
     write_seismograms(sim, seis, str(tmp_path / "ref"), "d")
     m = compare_with_reference(str(tmp_path / "syn"), str(tmp_path / "ref"))
     assert len(m) == 12 and all(abs(v["corr"] - 1) < 1e-12 and v["rel_l2"] == 0 and v["shift"] == 0 for v in m.values())
+
+
+def test_adjoint_source_files_round_trip(tmp_path):
+    """SEM/*.adj the way compute_arrays_adjoint_source reads them: NSTEP lines per component file, second column."""
+    import numpy as np
+    import pytest
+
+    from specfem3d_b200.seismograms import read_adjoint_sources, write_adjoint_sources
+    from test_oracle_kernel_run import kernel_sim
+
+    sim = kernel_sim((1, 1), 30, sim_type=3)
+    rng = np.random.default_rng(1)
+    adj = (1e12 * rng.standard_normal((sim.receivers.nrec, sim.NSTEP, 3))).astype(np.float32)
+    paths = write_adjoint_sources(sim, adj, str(tmp_path / "SEM"))
+    assert len(paths) == 3 * sim.receivers.nrec and paths[0].endswith("XX.A.HXX.adj")  # DT = 0.012 s -> band code H
+    back = read_adjoint_sources(sim, str(tmp_path / "SEM"))
+    assert np.allclose(back, adj, rtol=2e-8 * 10, atol=0)  # nine significant digits in the file
+    sim.NSTEP = 31
+    with pytest.raises(ValueError):
+        read_adjoint_sources(sim, str(tmp_path / "SEM"))
