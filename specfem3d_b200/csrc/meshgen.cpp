@@ -393,4 +393,47 @@ int64_t mg_dual_graph(int64_t nspec, int64_t nnodes, int nsize, int sup_neighbor
   return nb_edges;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Interfaces between partitions as decompose_mesh tabulates them (restates build_interfaces,
+// src/decompose_mesh/part_decompose_mesh.F90:413-520, same loop order): for every pair of parts (i < j), in the order
+// (0,1), (0,2), ..., every dual-graph edge from an element of part i to an element of part j is one entry of seven integers
+// [el, el_adj, ncommon_nodes, node_1 .. node_4] (0-based ids; ncommon_nodes = 1 corner, 2 edge, 4 face).
+// tab_size[ninterfaces + 1]: prefix sums of the entry counts.  tab == nullptr: only count.  Returns the number of entries.
+// ---------------------------------------------------------------------------------------------------------------
+int64_t mg_build_interfaces(int64_t nspec, int nparts, const int32_t* part, const int32_t* elmnts, const int32_t* xadj,
+                            const int32_t* adjncy, int32_t* tab_size, int32_t* tab) {
+  int64_t num_interface = 0, total = 0;
+  tab_size[0] = 0;
+  for (int num_part = 0; num_part < nparts; ++num_part) {
+    for (int num_part_bis = num_part + 1; num_part_bis < nparts; ++num_part_bis) {
+      int64_t num_edge = 0;
+      for (int64_t el = 0; el < nspec; ++el) {
+        if (part[el] != num_part) continue;
+        for (int32_t e = xadj[el]; e < xadj[el + 1]; ++e) {
+          const int32_t adj = adjncy[e];
+          if (part[adj] != num_part_bis) continue;
+          if (tab) {
+            int32_t* t = tab + 7 * (total + num_edge);
+            t[0] = (int32_t)el;
+            t[1] = adj;
+            int ncommon = 0;
+            for (int a = 0; a < 8; ++a)
+              for (int b = 0; b < 8; ++b)
+                if (elmnts[8 * el + a] == elmnts[8 * (int64_t)adj + b]) {
+                  if (ncommon < 4) t[3 + ncommon] = elmnts[8 * el + a];
+                  ++ncommon;
+                }
+            t[2] = ncommon;
+          }
+          ++num_edge;
+        }
+      }
+      total += num_edge;
+      tab_size[num_interface + 1] = (int32_t)total;
+      ++num_interface;
+    }
+  }
+  return total;
+}
+
 }  // extern "C"

@@ -55,6 +55,23 @@ def dual_graph(spec: BoxSpec, ncommonnodes: int = 1):
     return xadj, adjncy[:n].copy(), int(mx.value)
 
 
+def build_interfaces(spec: BoxSpec, part: np.ndarray, nparts: int, ncommonnodes: int = 1):
+    """(tab_size_interfaces[ninterfaces + 1], tab_interfaces[n][7]) of build_interfaces (part_decompose_mesh.F90:413-520):
+    interface k belongs to the k-th pair (i < j) in the order (0,1), (0,2), ...; one row per dual-graph edge crossing from
+    part i to part j: [el, el_adj, ncommon_nodes (1 corner / 2 edge / 4 face), the shared corner nodes, zero padded]."""
+    elmnts, _ = corner_connectivity(spec)
+    xadj, adjncy, _ = dual_graph(spec, ncommonnodes)
+    part = np.ascontiguousarray(part, np.int32)
+    ninterfaces = nparts * (nparts - 1) // 2
+    tab_size = np.zeros(ninterfaces + 1, np.int32)
+    mg = _meshgen()
+    mg.mg_build_interfaces.restype = ctypes.c_int64
+    n = mg.mg_build_interfaces(ctypes.c_int64(len(part)), nparts, _p(part), _p(elmnts), _p(xadj), _p(adjncy), _p(tab_size), None)
+    tab = np.zeros((max(int(n), 1), 7), np.int32)
+    mg.mg_build_interfaces(ctypes.c_int64(len(part)), nparts, _p(part), _p(elmnts), _p(xadj), _p(adjncy), _p(tab_size), _p(tab))
+    return tab_size, tab[: int(n)]
+
+
 def element_loads(spec: BoxSpec, attenuation: bool = False) -> np.ndarray:
     """elmnts_load of acoustic_elastic_poro_load (one integer per element)."""
     layer_mat = np.zeros(spec.ner, dtype=np.int64) if spec.layer_material is None else np.asarray(spec.layer_material)

@@ -97,3 +97,45 @@ def test_arbitrary_partition_databases_and_run(name):
     assert np.abs(one.seis_d).max() > 0
     # summation order at the shared points differs (and the oracle's OpenMP scatter is not ordered): a few 1e-5 after 100 steps
     assert np.linalg.norm(many.seis_d - one.seis_d) <= 1e-4 * np.linalg.norm(one.seis_d)
+
+
+@pytest.mark.parametrize("name", ["graph_growing_3", "ragged_4"])
+def test_build_interfaces_tables(name):
+    """tab_size_interfaces / tab_interfaces of build_interfaces: pair order, one row per crossing dual-graph edge in element
+    order, contact type from the shared corner nodes, and agreement with the point interfaces of the solver databases (the
+    corner points of an interface are exactly the nodes listed for that pair)."""
+    from specfem3d_b200.decompose import build_interfaces
+
+    spec = box((6, 6, 4))
+    part = partitions()[name]
+    nparts = int(part.max()) + 1
+    tab_size, tab = build_interfaces(spec, part, nparts)
+    elm, _ = corner_connectivity(spec)
+    xadj, adjncy, _ = dual_graph(spec, 1)
+    pairs = [(i, j) for i in range(nparts) for j in range(i + 1, nparts)]
+    assert len(tab_size) == len(pairs) + 1 and tab_size[-1] == len(tab)
+    sim = sim_for(part, nstep=1)
+    GXg, GYg = 4 * spec.nex_xi + 1, 4 * spec.nex_eta + 1
+    for k, (i, j) in enumerate(pairs):
+        rows = tab[tab_size[k]: tab_size[k + 1]]
+        # brute force: every (el in i, neighbour in j) pair of the dual graph, in element order then adjacency order
+        ref = [(el, int(a)) for el in range(len(part)) if part[el] == i for a in adjncy[xadj[el]:xadj[el + 1]] if part[a] == j]
+        assert [(int(r[0]), int(r[1])) for r in rows] == ref
+        nodes = set()
+        for r in rows:
+            shared = sorted(set(elm[r[0]]) & set(elm[r[1]]))
+            assert r[2] == len(shared) and r[2] in (1, 2, 4) and sorted(int(v) for v in r[3:3 + r[2]]) == [int(v) for v in shared]
+            assert (r[3 + r[2]:] == 0).all()
+            nodes.update(int(v) for v in shared)
+        # the same contact seen from the solver databases: corner points of the (i, j) point interface
+        db = sim.dbs[i]
+        nb = list(db.my_neighbors_ext_mesh[: db.num_interfaces_ext_mesh])
+        if not rows.size:
+            assert j not in nb
+            continue
+        m = nb.index(j)
+        g = db.grid_of_glob[db.ibool_interfaces_ext_mesh[m, : db.nibool_interfaces_ext_mesh[m]] - 1]
+        gx, gy, gz = g % GXg, (g // GXg) % GYg, g // (GXg * GYg)
+        corner = (gx % 4 == 0) & (gy % 4 == 0) & (gz % 4 == 0)
+        node_ids = set(int(v) for v in (gx[corner] // 4 + (spec.nex_xi + 1) * (gy[corner] // 4 + (spec.nex_eta + 1) * (gz[corner] // 4))))
+        assert node_ids == nodes
