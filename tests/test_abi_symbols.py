@@ -52,3 +52,28 @@ def test_fortran_style_binding_checks_arguments():
     L = abi.load()
     with pytest.raises(TypeError):
         L.update_displacement_cuda(ctypes.c_long(0), 0.1)  # wrong arity is caught before touching the device
+
+
+def _run_snippet(code):
+    import subprocess
+    import sys
+
+    return subprocess.run([sys.executable, "-c", code], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+
+
+def test_out_of_scope_entry_points_fail_loudly(tmp_path):
+    """No silent no-ops and no CPU fallback: an entry point outside the implemented set prints its name and exits non-zero
+    (like exit_on_error in src/gpu/helper_functions.cu), and so does an implemented one called with a null handle."""
+    load = "import ctypes; L = ctypes.CDLL('specfem3d_b200/libspecfem3d_b200.so'); h = ctypes.c_long(0); i = ctypes.c_int(1)\n"
+    res = _run_snippet(load + "L.compute_strain_cuda_(ctypes.byref(h), ctypes.byref(i), ctypes.byref(i))\nprint('survived')")
+    assert res.returncode != 0 and "survived" not in res.stdout
+    assert "compute_strain_cuda" in res.stderr + res.stdout
+    f = "f = ctypes.c_float(0.1)\n"
+    res = _run_snippet(load + f + "L.update_displacement_cuda_(ctypes.byref(h), ctypes.byref(f), ctypes.byref(f), ctypes.byref(f), ctypes.byref(i))\nprint('survived')")
+    assert res.returncode != 0 and "survived" not in res.stdout
+    assert "Mesh_pointer" in res.stderr + res.stdout
+    table = json.load(open(os.path.join(ROOT, "specfem3d_b200", "abi_symbols.json")))
+    # kernel runs, ocean load: implemented this round
+    for n in ("prepare_fields_elastic_adj_dev", "compute_kernels_elastic_cuda", "compute_kernels_acoustic_cuda", "compute_coupling_ocean_cuda",
+              "transfer_kernels_el_to_host", "add_sources_el_sim_type_2_or_3", "transfer_b_fields_to_device"):
+        assert table[n]["implemented"], n
