@@ -5,7 +5,9 @@ can be restated without SCOTCH:
   ``mesh2dual_ncommonnodes`` (src/decompose_mesh/part_decompose_mesh.F90:49-149, ``ncommonnodes = 1`` as in
   decompose_mesh.F90:92) -- same algorithm, same neighbour order (csrc/meshgen.cpp: mg_dual_graph);
 * the integer element loads of ``acoustic_elastic_poro_load`` (:1162-1251: acoustic 10, elastic 41, viscoelastic 59);
-* a partition array ``part[]`` -- **not SCOTCH's**: SCOTCH 5.1.12b is vendored by the reference but needs its flex / bison
+* ``partition_rows``: PARTITIONING_TYPE = 4 of the reference (partition_rows.F90), restated exactly -- a partition array that
+  IS the reference's;
+* another partition array ``part[]`` -- **not SCOTCH's**: SCOTCH 5.1.12b is vendored by the reference but needs its flex / bison
   generated parser sources, which this image cannot produce, so ``partition_graph_growing`` is a plain deterministic
   load-balanced graph-growing partitioner standing in for ``scotchfgraphpart``.  Everything downstream of ``part[]``
   (meshfem.build_partition: local numbering, interfaces by ascending neighbour rank with coordinate-ordered points, inner /
@@ -78,6 +80,32 @@ def element_loads(spec: BoxSpec, attenuation: bool = False) -> np.ndarray:
     dom = np.array([m.domain for m in spec.materials], dtype=np.int64)[layer_mat]
     per_layer = np.where(dom == 1, ACOUSTIC_LOAD, VISCOELASTIC_LOAD if attenuation else ELASTIC_LOAD)
     return np.repeat(per_layer, spec.nex_xi * spec.nex_eta).astype(np.int32)
+
+
+def partition_rows(spec: BoxSpec, nparts: int) -> np.ndarray:
+    """PARTITIONING_TYPE = 4 (ROWS) of xdecompose_mesh, restated exactly (src/decompose_mesh/partition_rows.F90:30-100): the
+    centre of an element (mean x of its eight corner nodes, double precision) is placed in one of ``nparts`` equal slices of
+    the x-range of the nodes, ``part = floor(nparts * (xc - x_min) / range)`` clamped to [0, nparts - 1].  This one IS the
+    reference's partition array, unlike :func:`partition_graph_growing`."""
+    from .meshfem import _corner_coords
+
+    elmnts, _ = corner_connectivity(spec)
+    nx, ny = spec.nex_xi, spec.nex_eta
+    node = np.unique(elmnts)
+    cx_i, cy_i, cz_i = node % (nx + 1), (node // (nx + 1)) % (ny + 1), node // ((nx + 1) * (ny + 1))
+    x, _, _ = _corner_coords(spec, cx_i.astype(np.float64), cy_i.astype(np.float64), cz_i.astype(np.float64))
+    if nparts == 1:
+        return np.zeros(elmnts.shape[0], np.int32)
+    x_min, x_max = float(x.min()), float(x.max())
+    rng = x_max - x_min
+    if rng < 1e-16:
+        raise ValueError("Error zero range in x-direction")
+    centre = np.zeros(elmnts.shape[0])
+    for inode in range(8):  # the reference accumulates node by node in this order
+        centre = centre + x[elmnts[:, inode]]
+    centre = centre / 8
+    sliceid = np.floor(nparts * ((centre - x_min) / rng)).astype(np.int64)
+    return np.clip(sliceid, 0, nparts - 1).astype(np.int32)
 
 
 def partition_graph_growing(xadj: np.ndarray, adjncy: np.ndarray, loads: np.ndarray, nparts: int) -> np.ndarray:

@@ -139,3 +139,24 @@ def test_build_interfaces_tables(name):
         corner = (gx % 4 == 0) & (gy % 4 == 0) & (gz % 4 == 0)
         node_ids = set(int(v) for v in (gx[corner] // 4 + (spec.nex_xi + 1) * (gy[corner] // 4 + (spec.nex_eta + 1) * (gz[corner] // 4))))
         assert node_ids == nodes
+
+
+def test_partition_rows_is_the_reference_rows_partitioning():
+    """PARTITIONING_TYPE = 4: x-slices by element centre (partition_rows.F90).  On an undeformed box the slices are the
+    columns ix * nparts // nex; on the deformed box elements follow their centre; a run on the ROWS partition equals the
+    single-rank run."""
+    from oracle.solver import OracleRun
+    from specfem3d_b200.decompose import partition_rows
+
+    flat = BoxSpec(6, 6, 4, xmax=6600.0, ymax=5400.0, zmin=-4000.0, materials=(HALFSPACE,))
+    part = partition_rows(flat, 3)
+    ix = np.arange(6 * 6 * 4) % 6
+    assert np.array_equal(part, ix // 2)
+    assert np.array_equal(partition_rows(flat, 1), np.zeros(144, np.int32))
+    odd = partition_rows(flat, 4)  # 6 columns into 4 slices: floor(4 * (ix + 0.5) / 6)
+    assert np.array_equal(odd, np.floor(4 * (ix + 0.5) / 6).astype(np.int32))
+    spec = box((6, 6, 4))
+    part = partition_rows(spec, 3)
+    assert np.bincount(part).min() > 0
+    one, rows = OracleRun(sim_for()).run(), OracleRun(sim_for(part)).run()
+    assert np.linalg.norm(rows.seis_d - one.seis_d) <= 1e-4 * np.linalg.norm(one.seis_d)
