@@ -137,3 +137,137 @@ def partition_graph_growing(xadj: np.ndarray, adjncy: np.ndarray, loads: np.ndar
     if (part < 0).any():  # disconnected leftovers go to the last part
         part[part < 0] = nparts - 1
     return part
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# proc%06d_Database: what xdecompose_mesh hands to xgenerate_databases (write_mesh_databases.F90:37-150 and the write_*
+# routines of part_decompose_mesh.F90), Fortran unformatted sequential, one record per node / element / face / contact
+# ------------------------------------------------------------------------------------------------------------------
+def glob2loc(spec: BoxSpec, part: np.ndarray, nparts: int):
+    """(glob2loc_elmnts, glob2loc_nodes_nparts, glob2loc_nodes_parts, glob2loc_nodes) of build_glob2loc_elmnts /
+    build_glob2loc_nodes (part_decompose_mesh.F90:287-401): local element numbers in ascending global order per part; for every
+    node the parts that touch it in ascending part order with the node's local number there (ascending node order per part)."""
+    elmnts, nnodes = corner_connectivity(spec)
+    part = np.asarray(part, np.int64)
+    g2l_el = np.zeros(len(part), np.int32)
+    for ip in range(nparts):
+        ids = np.nonzero(part == ip)[0]
+        g2l_el[ids] = np.arange(len(ids), dtype=np.int32)
+    touch = np.zeros((nnodes, nparts), bool)
+    touch[elmnts.reshape(-1), np.repeat(part, 8)] = True
+    nparts_of_node = touch.sum(1)
+    g2l_nparts = np.concatenate([[0], np.cumsum(nparts_of_node)]).astype(np.int32)
+    node_ids, parts = np.nonzero(touch)  # row-major: ascending node, then ascending part
+    local = (np.cumsum(touch, axis=0) - 1)[node_ids, parts]
+    return g2l_el, g2l_nparts, parts.astype(np.int32), local.astype(np.int32)
+
+
+def _box_boundaries(spec: BoxSpec):
+    """ibelm_* and their four corner nodes (0-based) for the six sides in the reference's order xmin, xmax, ymin, ymax,
+    bottom, top; faces in ascending element order, nodes in the element's HEX8 order."""
+    elmnts, _ = corner_connectivity(spec)
+    nx, ny, nz = spec.nex_xi, spec.nex_eta, spec.ner
+    e = np.arange(nx * ny * nz)
+    ix, iy, iz = e % nx, (e // nx) % ny, e // (nx * ny)
+    corners_of_face = {1: (0, 3, 7, 4), 2: (1, 2, 6, 5), 3: (0, 1, 5, 4), 4: (3, 2, 6, 7), 5: (0, 1, 2, 3), 6: (4, 5, 6, 7)}
+    masks = {1: ix == 0, 2: ix == nx - 1, 3: iy == 0, 4: iy == ny - 1, 5: iz == 0, 6: iz == nz - 1}
+    return {f: (e[masks[f]], elmnts[masks[f]][:, corners_of_face[f]]) for f in range(1, 7)}
+
+
+def write_decomposed_database(path: str, spec: BoxSpec, part: np.ndarray, iproc: int, nparts: int) -> int:
+    """One rank's ``proc%06d_Database`` for the structured box (no C-PML, no moho, defined materials only).  Returns the number
+    of records."""
+    from .databases import _Writer
+
+    I4, F8 = np.int32, np.float64
+    from .meshfem import _corner_coords
+
+    elmnts, nnodes = corner_connectivity(spec)
+    part = np.asarray(part, np.int32)
+    g2l_el, g2l_np, g2l_parts, g2l_nodes = glob2loc(spec, part, nparts)
+    nx, ny = spec.nex_xi, spec.nex_eta
+    nid = np.arange(nnodes)
+    x, y, z = _corner_coords(spec, (nid % (nx + 1)).astype(F8), ((nid // (nx + 1)) % (ny + 1)).astype(F8), (nid // ((nx + 1) * (ny + 1))).astype(F8))
+
+    def local_node(node):  # the node's local number (0-based) in part iproc
+        seg = slice(g2l_np[node], g2l_np[node + 1])
+        k = np.nonzero(g2l_parts[seg] == iproc)[0][0]
+        return int(g2l_nodes[seg][k])
+
+    w = _Writer(path)
+    mine = np.nonzero(g2l_parts == iproc)[0]
+    node_of_entry = np.repeat(np.arange(nnodes), np.diff(g2l_np))
+    w.rec(I4(len(mine)))  # nnodes_loc
+    for k in mine:        # write_glob2loc_nodes_database: ascending global node
+        n = node_of_entry[k]
+        w.rec(I4(g2l_nodes[k] + 1), F8(x[n]), F8(y[n]), F8(z[n]))
+    # write_material_props_database: rho, vp, vs, Q_kappa, Q_mu, anisotropy flag, domain id, ten zeros (poroelastic slots)
+    w.rec(I4(len(spec.materials)), I4(0))
+    for m in spec.materials:
+        w.rec(np.array([m.rho, m.vp, m.vs, m.Qkappa, m.Qmu, 0.0, float(m.domain)] + [0.0] * 10, F8))
+    layer_mat = np.zeros(spec.ner, dtype=np.int64) if spec.layer_material is None else np.asarray(spec.layer_material)
+    els = np.nonzero(part == iproc)[0]
+    w.rec(I4(len(els)))   # nspec_local
+    for e in els:         # write_partition_database: local element, material id (1-based), flag, local nodes (1-based)
+        iz = e // (nx * ny)
+        w.rec(I4(g2l_el[e] + 1), I4(layer_mat[iz] + 1), I4(0), np.array([local_node(n) + 1 for n in elmnts[e]], I4))
+    bnd = _box_boundaries(spec)
+    for f in range(1, 7):  # write_boundaries_database: the six counts first ...
+        w.rec(I4(f), I4(int((part[bnd[f][0]] == iproc).sum())))
+    for f in range(1, 7):  # ... then the faces: local element, four local nodes
+        for e, nodes in zip(*bnd[f]):
+            if part[e] == iproc:
+                w.rec(I4(g2l_el[e] + 1), np.array([local_node(n) + 1 for n in nodes], I4))
+    w.rec(I4(0))          # write_cpml_database: nspec_cpml = 0
+    tab_size, tab = build_interfaces(spec, part, nparts)
+    pairs = [(i, j) for i in range(nparts) for j in range(i + 1, nparts)]
+    my = [(k, i, j) for k, (i, j) in enumerate(pairs) if tab_size[k] < tab_size[k + 1] and iproc in (i, j)]
+    sizes = [int(tab_size[k + 1] - tab_size[k]) for k, _, _ in my]
+    w.rec(I4(len(my)), I4(max(sizes) if sizes else 0))  # my_ninterface, max_interface_size
+    for (k, i, j), n in zip(my, sizes):  # write_interfaces_database
+        w.rec(I4(j if i == iproc else i), I4(n))
+        for row in tab[tab_size[k]: tab_size[k + 1]]:
+            el = row[0] if i == iproc else row[1]
+            nodes = [local_node(v) + 1 for v in row[3:3 + row[2]]] + [-1] * (4 - row[2])
+            w.rec(I4(g2l_el[el] + 1), I4(row[2]), np.array(nodes, I4))
+    w.close()
+    return w.nrec
+
+
+def read_decomposed_database(path: str):
+    """Reader of :func:`write_decomposed_database`'s file (the order xgenerate_databases reads it in,
+    src/generate_databases/read_partition_files.f90): dict with nodes (local id, xyz), materials, elements (local id, material,
+    flag, 8 local nodes), boundaries {1..6: (element, 4 nodes)}, interfaces [(neighbour, [(element, type, 4 nodes)])]."""
+    from .databases import _Reader
+    import struct
+
+    r = _Reader(path)
+    out = {}
+    nn = r.scalar(np.int32)
+    nodes = np.zeros((nn, 3))
+    for _ in range(nn):
+        b = r.raw()
+        (k,) = struct.unpack("<i", b[:4])
+        nodes[k - 1] = struct.unpack("<3d", b[4:])
+    out["nodes"] = nodes
+    ndef, nundef = np.frombuffer(r.raw(), np.int32)
+    out["materials"] = [np.frombuffer(r.raw(), np.float64).copy() for _ in range(ndef)]
+    assert nundef == 0
+    ne = r.scalar(np.int32)
+    el = np.zeros((ne, 11), np.int32)
+    for _ in range(ne):
+        row = np.frombuffer(r.raw(), np.int32)
+        el[row[0] - 1] = row
+    out["elements"] = el
+    counts = [tuple(np.frombuffer(r.raw(), np.int32)) for _ in range(6)]
+    out["boundaries"] = {int(f): [np.frombuffer(r.raw(), np.int32).copy() for _ in range(n)] for f, n in counts}
+    assert r.scalar(np.int32) == 0  # nspec_cpml
+    nif, mx = np.frombuffer(r.raw(), np.int32)
+    out["max_interface_size"] = int(mx)
+    out["interfaces"] = []
+    for _ in range(nif):
+        nb, n = np.frombuffer(r.raw(), np.int32)
+        out["interfaces"].append((int(nb), [np.frombuffer(r.raw(), np.int32).copy() for _ in range(n)]))
+    assert r.at_end()
+    r.close()
+    return out

@@ -160,3 +160,47 @@ def test_partition_rows_is_the_reference_rows_partitioning():
     assert np.bincount(part).min() > 0
     one, rows = OracleRun(sim_for()).run(), OracleRun(sim_for(part)).run()
     assert np.linalg.norm(rows.seis_d - one.seis_d) <= 1e-4 * np.linalg.norm(one.seis_d)
+
+
+@pytest.mark.parametrize("name", ["rows_3", "ragged_4"])
+def test_decomposed_database_files(tmp_path, name):
+    """proc%06d_Database of xdecompose_mesh for the box: record counts, local numbering (elements and nodes ascending in the
+    global order), boundary faces, and the contact list -- cross-checked against the solver databases built from the same
+    part[] (same elements in the same order with the same corner coordinates; every contact node lies on the point interface)."""
+    from specfem3d_b200.decompose import partition_rows, read_decomposed_database, write_decomposed_database
+
+    spec = box((6, 6, 4))
+    part = partition_rows(spec, 3) if name == "rows_3" else partitions()[name]
+    nparts = int(part.max()) + 1
+    sim = sim_for(part, nstep=1)
+    for iproc in range(nparts):
+        path = str(tmp_path / f"proc{iproc:06d}_Database")
+        nrec = write_decomposed_database(path, spec, part, iproc, nparts)
+        d = read_decomposed_database(path)
+        db = sim.dbs[iproc]
+        ne = len(d["elements"])
+        assert ne == db.NSPEC_AB == int((part == iproc).sum())
+        nfaces = sum(len(v) for v in d["boundaries"].values())
+        ncontacts = sum(len(c) for _, c in d["interfaces"])
+        assert nrec == 1 + len(d["nodes"]) + 1 + len(d["materials"]) + 1 + ne + 6 + nfaces + 1 + 1 + len(d["interfaces"]) + ncontacts
+        assert np.array_equal(d["elements"][:, 0], np.arange(1, ne + 1)) and (d["elements"][:, 1] == 1).all()
+        # same elements, same order, same corner coordinates as the solver database of this rank
+        corners = d["nodes"][d["elements"][:, 3:] - 1]  # (ne, 8, 3)
+        assert np.allclose(corners, db.extra["corners"], rtol=0, atol=1e-9)
+        # boundary faces: the solver database has the same number of absorbing + free-surface faces
+        assert sum(len(d["boundaries"][f]) for f in (1, 2, 3, 4, 5)) == db.num_abs_boundary_faces
+        assert len(d["boundaries"][6]) == db.num_free_surface_faces
+        for f in (1, 2):  # x-faces: all four nodes share the face's x
+            for row in d["boundaries"][f]:
+                assert np.ptp(d["nodes"][row[1:] - 1][:, 0]) < 0.3 * 1100.0  # deformed box: nearly planar
+        # contacts: neighbours ascending, every contact node is a point of the point interface with that neighbour
+        nbs = [nb for nb, _ in d["interfaces"]]
+        assert nbs == sorted(nbs) == [int(v) for v in db.my_neighbors_ext_mesh[: db.num_interfaces_ext_mesh]]
+        assert d["max_interface_size"] == max(len(c) for _, c in d["interfaces"])
+        xyz = np.stack([db.xstore, db.ystore, db.zstore], -1)
+        for m, (nb, contacts) in enumerate(d["interfaces"]):
+            pts = xyz[db.ibool_interfaces_ext_mesh[m, : db.nibool_interfaces_ext_mesh[m]] - 1]
+            for row in contacts:
+                assert row[1] in (1, 2, 4) and (row[2 + row[1]:] == -1).all()
+                for n in row[2:2 + row[1]]:
+                    assert np.abs(pts - d["nodes"][n - 1].astype(np.float32)).sum(1).min() < 1e-2
