@@ -271,3 +271,73 @@ def read_decomposed_database(path: str):
     assert r.at_end()
     r.close()
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# MESH/ directory: the ASCII mesh files xdecompose_mesh reads (read_mesh_files.F90:60-800); all ids 1-based in the files
+# ------------------------------------------------------------------------------------------------------------------
+_SURFACE_FILES = {1: "absorbing_surface_file_xmin", 2: "absorbing_surface_file_xmax", 3: "absorbing_surface_file_ymin",
+                  4: "absorbing_surface_file_ymax", 5: "absorbing_surface_file_bottom", 6: "free_or_absorbing_surface_file_zmax"}
+
+
+def write_mesh_files(directory: str, spec: BoxSpec) -> None:
+    """nodes_coords_file, mesh_file, materials_file, nummaterial_velocity_file and the six surface files of the box."""
+    import os
+
+    from .meshfem import _corner_coords
+
+    os.makedirs(directory, exist_ok=True)
+    elmnts, nnodes = corner_connectivity(spec)
+    nx, ny = spec.nex_xi, spec.nex_eta
+    nid = np.arange(nnodes)
+    x, y, z = _corner_coords(spec, (nid % (nx + 1)).astype(float), ((nid // (nx + 1)) % (ny + 1)).astype(float),
+                             (nid // ((nx + 1) * (ny + 1))).astype(float))
+    with open(os.path.join(directory, "nodes_coords_file"), "w") as f:
+        f.write(f"{nnodes}\n")
+        for i in range(nnodes):
+            f.write(f"{i + 1} {x[i]:.17g} {y[i]:.17g} {z[i]:.17g}\n")
+    with open(os.path.join(directory, "mesh_file"), "w") as f:
+        f.write(f"{len(elmnts)}\n")
+        for e, nodes in enumerate(elmnts):
+            f.write(f"{e + 1} " + " ".join(str(int(n) + 1) for n in nodes) + "\n")
+    layer_mat = np.zeros(spec.ner, dtype=np.int64) if spec.layer_material is None else np.asarray(spec.layer_material)
+    with open(os.path.join(directory, "materials_file"), "w") as f:
+        for e in range(len(elmnts)):
+            f.write(f"{e + 1} {int(layer_mat[e // (nx * ny)]) + 1}\n")
+    with open(os.path.join(directory, "nummaterial_velocity_file"), "w") as f:
+        for i, m in enumerate(spec.materials):  # domain_id material_id rho vp vs Q_kappa Q_mu anisotropy_flag
+            f.write(f"{m.domain} {i + 1} {m.rho:.9g} {m.vp:.9g} {m.vs:.9g} {m.Qkappa:.9g} {m.Qmu:.9g} 0\n")
+    for fid, (els, nodes) in _box_boundaries(spec).items():
+        with open(os.path.join(directory, _SURFACE_FILES[fid]), "w") as f:
+            f.write(f"{len(els)}\n")
+            for e, nd in zip(els, nodes):
+                f.write(f"{int(e) + 1} " + " ".join(str(int(n) + 1) for n in nd) + "\n")
+
+
+def read_mesh_files(directory: str):
+    """What read_mesh_files.F90 loads (0-based arrays): dict(nodes_coords[nnodes][3], elmnts[nspec][8], mat[nspec],
+    mat_prop[nmat][8], surfaces{1..6: (ibelm, nodes[n][4])})."""
+    import os
+
+    def table(name, skip=1):
+        with open(os.path.join(directory, name)) as f:
+            lines = f.read().split("\n")
+        return [ln.split() for ln in lines[skip:] if ln.strip()]
+
+    rows = table("nodes_coords_file")
+    coords = np.zeros((len(rows), 3))
+    for r in rows:
+        coords[int(r[0]) - 1] = [float(v) for v in r[1:4]]
+    rows = table("mesh_file")
+    elmnts = np.zeros((len(rows), 8), np.int32)
+    for r in rows:
+        elmnts[int(r[0]) - 1] = [int(v) - 1 for v in r[1:9]]
+    mat = np.zeros(len(elmnts), np.int32)
+    for r in table("materials_file", skip=0):
+        mat[int(r[0]) - 1] = int(r[1])
+    mat_prop = np.array([[float(v) for v in r] for r in table("nummaterial_velocity_file", skip=0)])
+    surfaces = {}
+    for fid, name in _SURFACE_FILES.items():
+        rows = table(name)
+        surfaces[fid] = (np.array([int(r[0]) - 1 for r in rows], np.int64), np.array([[int(v) - 1 for v in r[1:5]] for r in rows], np.int32))
+    return dict(nodes_coords=coords, elmnts=elmnts, mat=mat, mat_prop=mat_prop, surfaces=surfaces)

@@ -204,3 +204,26 @@ def test_decomposed_database_files(tmp_path, name):
                 assert row[1] in (1, 2, 4) and (row[2 + row[1]:] == -1).all()
                 for n in row[2:2 + row[1]]:
                     assert np.abs(pts - d["nodes"][n - 1].astype(np.float32)).sum(1).min() < 1e-2
+
+
+def test_mesh_files_round_trip(tmp_path):
+    """MESH/ files of the box (what xdecompose_mesh reads): round trip, 1-based ids in the files, and every surface face lies on
+    its side of the (undeformed) box."""
+    from specfem3d_b200.decompose import _box_boundaries, read_mesh_files, write_mesh_files
+
+    water = Material(1020.0, 1500.0, 0.0, 9999.0, 9999.0, 1)
+    spec = BoxSpec(5, 4, 3, xmax=5000.0, ymax=4000.0, zmin=-3000.0, materials=(HALFSPACE, water), layer_material=[0, 0, 1])
+    write_mesh_files(str(tmp_path), spec)
+    m = read_mesh_files(str(tmp_path))
+    elm, nnodes = corner_connectivity(spec)
+    assert m["nodes_coords"].shape == (nnodes, 3) and np.array_equal(m["elmnts"], elm)
+    assert open(tmp_path / "mesh_file").read().split("\n")[1].split()[:2] == ["1", "1"]  # 1-based element and node ids
+    assert set(m["mat"][:40]) == {1} and set(m["mat"][40:]) == {2}
+    assert m["mat_prop"].shape == (2, 8) and m["mat_prop"][1, 0] == 1 and m["mat_prop"][0, 0] == 2  # domain ids
+    ref = _box_boundaries(spec)
+    for fid, axis, val in ((1, 0, 0.0), (2, 0, 5000.0), (3, 1, 0.0), (4, 1, 4000.0), (5, 2, -3000.0), (6, 2, 0.0)):
+        els, nodes = m["surfaces"][fid]
+        assert np.array_equal(els, ref[fid][0]) and np.array_equal(nodes, ref[fid][1])
+        assert np.allclose(m["nodes_coords"][nodes][..., axis], val)
+        for e, nd in zip(els, nodes):
+            assert set(nd) <= set(elm[e])
