@@ -84,3 +84,18 @@ def cpml_example(NSTEP: int = 2400, nproc_xi: int = 1, nproc_eta: int = 1) -> Si
     src = ForceSource(x=67000.0, y=67000.0, z=-30000.0, factor=1.0e10, comp=(1.0, -2.0, -1.0), hdur=0.128)
     return make_simulation(spec, DT=0.11, NSTEP=NSTEP, sources=[src], stations=STATIONS_DEFAULT,
                            SAVE_SEISMOGRAMS_VELOCITY=True, SAVE_SEISMOGRAMS_ACCELERATION=True)
+
+
+def attenuation_benchmark(NSTEP: int = 1300) -> Simulation:
+    """The reference's viscoelastic benchmark (EXAMPLES/benchmarks/attenuation/viscoelastic): a 3 km cube of 80^3 regular
+    elements (37.5 m) centred at the origin (Zmin / Zmax = -1500 / +1500 in REF_SEIS/output_meshfem3D.txt), rho 2000,
+    vp 3297.849, vs 2222.536, Q_kappa 10, Q_mu 20, 3 standard linear solids with the automatic frequency band,
+    ATTENUATION_f0_REFERENCE 18 Hz, no absorbing boundaries, vertical point force with an 18 Hz Ricker wavelet at (10, 10, 10),
+    one receiver at (510, 510, 510) (USE_SOURCES_RECEIVERS_Z: the depth column is the z coordinate), DT 5e-4, NSTEP 1300
+    (DATA/Par_file, DATA/meshfem3D_files/Mesh_Par_file, DATA/FORCESOLUTION, DATA/STATIONS, REF_SEIS/output_solver.txt)."""
+    mat = Material(2000.0, 3297.849, 2222.536, 10.0, 20.0, 2)
+    spec = BoxSpec(80, 80, 80, xmin=-1500.0, xmax=1500.0, ymin=-1500.0, ymax=1500.0, zmin=-1500.0, zmax=1500.0, materials=(mat,),
+                   stacey=False)
+    src = ForceSource(x=10.0, y=10.0, z=10.0, factor=1.0, comp=(0.0, 0.0, 1.0), hdur=18.0)
+    return make_simulation(spec, DT=0.0005, NSTEP=NSTEP, sources=[src], stations=[Station("1", "CE", 510.0, 510.0, 510.0)],
+                           attenuation=True, f0_attenuation=18.0)

@@ -42,8 +42,25 @@ def cpml():
     print("wrote cpml_ref_seis.npz", len(out["time"]), "samples,", len(out["maxnorm_step"]), "max-norm lines")
 
 
+REF_ATT = "/root/reference/EXAMPLES/benchmarks/attenuation/viscoelastic/REF_SEIS"
+
+
+def attenuation():
+    """attenuation_ref_seis.npz: the three traces of the viscoelastic benchmark (CE.1.FX{X,Y,Z}.semd, 1300 samples) and the
+    max-norm lines of its output_solver.txt."""
+    out = {}
+    for ch in "XYZ":
+        d = np.loadtxt(os.path.join(REF_ATT, f"CE.1.FX{ch}.semd"))
+        out[f"1_{ch}"] = d[:, 1].astype(np.float32)
+        out["time"] = d[:, 0].astype(np.float64)
+    out["maxnorm_step"], out["maxnorm_value"] = maxnorms(os.path.join(REF_ATT, "output_solver.txt"))
+    np.savez_compressed(os.path.join(HERE, "attenuation_ref_seis.npz"), **out)
+    print("wrote attenuation_ref_seis.npz", len(out["time"]), "samples,", len(out["maxnorm_step"]), "max-norm lines")
+
+
 def main():
     cpml()
+    attenuation()
     out = {}
     for st in ("X20", "X30", "X40", "X50"):
         for ch in "XYZ":

@@ -112,3 +112,35 @@ def test_cpml_example_against_REF_SEIS():
     print(f"C-PML example: worst relative L2 vs REF_SEIS over {CPML_NSTEP} steps: {worst:.3e}")
     for it, v in norms.items():
         assert abs(v - ref_norm[it]) / ref_norm[it] < 1e-4, (it, v, ref_norm[it])
+
+
+ATT_GOLD = os.path.join(os.path.dirname(__file__), "golden", "attenuation_ref_seis.npz")
+
+
+@pytest.mark.skipif(not os.environ.get("SPECFEM_B200_FULL_GOLDEN"),
+                    reason="512,000 elements x 1300 steps with attenuation: ~40 min on 16 cores; set SPECFEM_B200_FULL_GOLDEN=1 "
+                           "(one-off result recorded in profiles/r01l_oracle_attenuation_benchmark.md)")
+def test_attenuation_benchmark_against_REF_SEIS():
+    """Pins the oracle's attenuation path (3 standard linear solids, memory-variable update, modulus shift to the reference
+    frequency) on the reference's own viscoelastic benchmark: EXAMPLES/benchmarks/attenuation/viscoelastic/REF_SEIS."""
+    from oracle.solver import OracleRun, set_num_threads
+    from specfem3d_b200.configs import attenuation_benchmark
+
+    set_num_threads(os.cpu_count() or 1)
+    gold = np.load(ATT_GOLD)
+    sim = attenuation_benchmark(1300)
+    assert abs(sim.sources.t0 + gold["time"][0]) < 1e-7  # t0 = 1.2 / f0
+    run = OracleRun(sim)
+    norms = {}
+    for it in range(1, 1301):
+        if it in (200, 400, 800):
+            norms[it] = run.max_norm_displ()
+        run.step()
+    ref_norm = dict(zip(gold["maxnorm_step"].tolist(), gold["maxnorm_value"].tolist()))
+    for it, v in norms.items():
+        assert abs(v - ref_norm[it]) / ref_norm[it] < 1e-3, (it, v, ref_norm[it])
+    for c, ch in enumerate("XYZ"):
+        ref = gold[f"1_{ch}"].astype(np.float64)
+        syn = run.seis_d[0, :, c].astype(np.float64)
+        err = np.linalg.norm(syn - ref) / np.linalg.norm(ref)
+        assert err <= 1e-4, f"attenuation benchmark CE.1.FX{ch}: relative L2 {err:.3e}"
