@@ -337,6 +337,16 @@ class OracleRun:
                         P(g.hprime_xx.ravel(order="F").copy()), P(p.displ), P(hx), P(hy), P(hz), P(o))
                     self.seis_p[irec, k] = o[0]
             else:
+                # fluid element: d / v / a are grad(potential, _dot, _dot_dot) / rho (compute_seismograms.f90:126-141)
+                db, g = p.db, sim.gll
+                for fld, out in ((p.pot, self.seis_d), (p.pot_dot, self.seis_v), (p.pot_dot_dot, self.seis_a)):
+                    o = np.zeros(3, np.float32)
+                    L.oracle_interpolate_acoustic_vector(
+                        c_int(ispec), P(db.ibool), P(db.irregular_element_number), P(db.xixstore), P(db.xiystore),
+                        P(db.xizstore), P(db.etaxstore), P(db.etaystore), P(db.etazstore), P(db.gammaxstore),
+                        P(db.gammaystore), P(db.gammazstore), c_float(db.xix_regular), P(db.rhostore),
+                        P(g.hprime_xx.ravel(order="F").copy()), P(fld), P(hx), P(hy), P(hz), P(nu), P(o))
+                    out[irec, k] = o
                 o = np.zeros(1, np.float32)
                 L.oracle_interpolate_pressure(c_int(ispec), P(p.db.ibool), P(p.pot_dot_dot), P(hx), P(hy), P(hz), P(o))
                 self.seis_p[irec, k] = o[0]

@@ -617,6 +617,56 @@ void oracle_interpolate_seismogram(int ispec1, const int* ibool, const realw* fi
   for (int a = 0; a < 3; ++a) out[a] = (realw)(nu[a + 3 * 0] * d[0] + nu[a + 3 * 1] * d[1] + nu[a + 3 * 2] * d[2]);
 }
 
+/* -------------------------------------------------------------------------------------------------------------
+ * Vector seismogram of a receiver in a FLUID element: the vector field is grad(scalar) / rho at every GLL point of the
+ * element (compute_gradient_in_acoustic_fast_Deville, src/specfem3D/compute_gradient_in_acoustic.f90:189-327: three
+ * single-precision 5x5 contractions with hprime_xx, metric terms, times 1/rho), interpolated with the Lagrange
+ * interpolants in double (compute_interpolated_dva_acoust, compute_interpolated_dva.f90:220-320) and rotated by nu_rec
+ * (compute_seismograms.f90:238-260).  scalar is potential, potential_dot or potential_dot_dot (-> d, v, a).
+ * ------------------------------------------------------------------------------------------------------------- */
+void oracle_interpolate_acoustic_vector(int ispec1, const int* ibool, const int* irregular_element_number,
+                                        const realw* xix, const realw* xiy, const realw* xiz, const realw* etax,
+                                        const realw* etay, const realw* etaz, const realw* gammax, const realw* gammay,
+                                        const realw* gammaz, realw xix_regular, const realw* rhostore,
+                                        const realw* hprime_xx /* F-order (i,l) */, const realw* scalar,
+                                        const double* hxir, const double* hetar, const double* hgammar,
+                                        const double* nu /* nu(a,b) F-order */, realw* out) {
+  const int ispec = ispec1 - 1;
+  const int irr = irregular_element_number[ispec];
+  realw chi[NGLL3];
+  for (int p = 0; p < NGLL3; ++p) chi[p] = scalar[ibool[(size_t)ispec * NGLL3 + p] - 1];
+  double d[3] = {0, 0, 0};
+  for (int k = 0; k < 5; ++k)
+    for (int j = 0; j < 5; ++j)
+      for (int i = 0; i < 5; ++i) {
+        /* mxm5_single / mxm5_3dmat_single: sums of five products, left to right */
+        realw t1 = 0, t2 = 0, t3 = 0;
+        for (int l = 0; l < 5; ++l) {
+          t1 = t1 + hprime_xx[i + 5 * l] * chi[l + 5 * j + 25 * k];
+          t2 = t2 + chi[i + 5 * l + 25 * k] * hprime_xx[j + 5 * l];
+          t3 = t3 + chi[i + 5 * j + 25 * l] * hprime_xx[k + 5 * l];
+        }
+        const int p = i + 5 * j + 25 * k;
+        const realw rho_invl = (realw)1.0 / rhostore[(size_t)ispec * NGLL3 + p];
+        realw v[3];
+        if (irr != 0) {
+          const size_t q = (size_t)(irr - 1) * NGLL3 + p;
+          v[0] = (t1 * xix[q] + t2 * etax[q] + t3 * gammax[q]) * rho_invl;
+          v[1] = (t1 * xiy[q] + t2 * etay[q] + t3 * gammay[q]) * rho_invl;
+          v[2] = (t1 * xiz[q] + t2 * etaz[q] + t3 * gammaz[q]) * rho_invl;
+        } else {
+          v[0] = t1 * xix_regular * rho_invl;
+          v[1] = t2 * xix_regular * rho_invl;
+          v[2] = t3 * xix_regular * rho_invl;
+        }
+        const double h = hxir[i] * hetar[j] * hgammar[k];
+        d[0] += h * (double)v[0];
+        d[1] += h * (double)v[1];
+        d[2] += h * (double)v[2];
+      }
+  for (int a = 0; a < 3; ++a) out[a] = (realw)(nu[a + 3 * 0] * d[0] + nu[a + 3 * 1] * d[1] + nu[a + 3 * 2] * d[2]);
+}
+
 /* pressure seismogram in fluid: p = - potential_dot_dot interpolated (compute_interpolated_dva_acoust / compute_seismograms.f90) */
 void oracle_interpolate_pressure(int ispec1, const int* ibool, const realw* potential_dot_dot, const double* hxir,
                                  const double* hetar, const double* hgammar, realw* out) {

@@ -8,14 +8,15 @@ Restated from (no code copied):
 * :464-498  get_attenuation_memory_values  (alphaval, betaval, gammaval: 4th-order expansion of exp(-dt/tau))
 * :500-538  get_attenuation_constants, :702-752 get_attenuation_periods (THETA table), :754-789 tau_sigma
   (log-spaced relaxation frequencies), :791-830 f_c_source (log centre of the band)
-* :838-1220 tau_eps by a Nelder-Mead fit of tan(delta)(f) to 1/Q over 100 log-spaced frequencies
-  (attenuation_invert_by_simplex / attenuation_eval / attenuation_maxwell)
+* :976-1216 tau_eps by a Nelder-Mead fit of tan(delta)(f) to 1/Q over 100 log-spaced frequencies
+  (attenuation_invert_by_simplex / attenuation_eval / attenuation_maxwell), :1222-1606 fminsearch, qsort_local
 * src/specfem3D/prepare_attenuation.f90:28-241   scaling of mustore / kappastore by the scale factors, zeroed
   memory variables and strains.
 
-The simplex itself is scipy's Nelder-Mead started from the same initial guess ``tau_s (1 + 2/Q)`` with the same
-objective; the optimum is not pinned bit-for-bit to the Fortran fminsearch (no golden vector exists for it), which
-does not matter for kernel parity: the device library and the oracle consume the very same arrays.
+The simplex is the reference's own ``fminsearch`` restated with its stopping rule (``fminsearch`` below) -- its loose
+absolute tolerance decides the result, so a generic Nelder-Mead gives a different attenuation model (round 1 used scipy's
+and missed the reference's benchmark seismograms by 5e-4).  Pinned on the tau_eps / scale factors the reference printed
+for its viscoelastic benchmark.
 """
 from __future__ import annotations
 
@@ -55,30 +56,124 @@ def _maxwell(f_log: np.ndarray, tau_s: np.ndarray, tau_eps: np.ndarray):
     return A, B
 
 
+def _attenuation_eval(x, f_log, tau_s, iQ: float) -> float:
+    """attenuation_eval / attenuation_maxwell (get_attenuation_model.f90:1100-1216): sum over the frequencies of
+    |tan_delta(f) - 1/Q| / (1/Q), accumulated in the Fortran loop order (doubles, PI = 3.14159265358979d0)."""
+    total = 0.0
+    iQ2 = iQ ** 2
+    for fl in f_log:
+        w = 2.0 * 3.14159265358979 * 10.0 ** fl
+        A = 0.0
+        B = 0.0
+        for ts, te in zip(tau_s, x):
+            denom = 1.0 + w ** 2 * ts ** 2
+            A = A + (1.0 + (w ** 2 * te * ts)) / denom
+            B = B + w * (te - ts) / denom
+        total = total + math.sqrt(((B / A - iQ) ** 2) / iQ2)
+    return total
+
+
+def _bubble_sort(fv):
+    """qsort_local (:1557-1606): bubble sort of fv, returns (sorted values, permutation); stable for ties."""
+    X = list(fv)
+    n = len(X)
+    place = list(range(n))
+    for j in range(1, n + 1):
+        for k in range(n - j):
+            if X[k + 1] < X[k]:
+                X[k], X[k + 1] = X[k + 1], X[k]
+                place[k], place[k + 1] = place[k + 1], place[k]
+    return X, place
+
+
+def fminsearch(funk, x0):
+    """The reference's own Nelder-Mead (get_attenuation_model.f90:1222-1473, "copied from Matlab fminsearch.m"):
+    initial simplex x0 and x0 with one coordinate stretched by 5 %, rho/chi/psi/sigma = 1/2/0.5/0.5, at most 200 n
+    iterations and function evaluations, and the ABSOLUTE stopping rule max|v_j - v_1| <= 1e-4 and max|f_j - f_1| <= 1e-4
+    (the single-precision literals 0.05, 0.00025 and 1.0e-4 promoted to double, as the Fortran does).  The loose absolute
+    tolerance is part of the reference's result: tau_eps stops well short of the true optimum, so a better optimiser
+    gives a *different* attenuation model.  Returns (x, f(x), iterations, function evaluations)."""
+    n = len(x0)
+    rho, chi, psi, sigma = 1.0, 2.0, 0.5, 0.5
+    maxiter = maxfun = 200 * n
+    tolx = tolf = float(np.float32(1.0e-4))
+    usual_delta, zero_term_delta = float(np.float32(0.05)), float(np.float32(0.00025))
+    v = [list(x0)]
+    fv = [funk(v[0])]
+    for j in range(n):
+        y = list(x0)
+        y[j] = (1.0 + usual_delta) * y[j] if y[j] != 0.0 else zero_term_delta
+        v.append(y)
+        fv.append(funk(y))
+    fv, place = _bubble_sort(fv)
+    v = [v[p] for p in place]
+    itercount, func_evals = 1, n + 1
+    while func_evals < maxfun and itercount < maxiter:
+        if (max(abs(v[j][i] - v[0][i]) for i in range(n) for j in range(1, n + 1)) <= tolx
+                and max(abs(fv[0] - fv[j]) for j in range(1, n + 1)) <= tolf):
+            break
+        xbar = [sum(v[j][i] for j in range(n)) / (n * 1.0) for i in range(n)]
+        xr = [(1 + rho) * xbar[i] - rho * v[n][i] for i in range(n)]
+        fxr = funk(xr)
+        func_evals += 1
+        shrink = False
+        if fxr < fv[0]:
+            xe = [(1 + rho * chi) * xbar[i] - rho * chi * v[n][i] for i in range(n)]
+            fxe = funk(xe)
+            func_evals += 1
+            v[n], fv[n] = (xe, fxe) if fxe < fxr else (xr, fxr)
+        elif fxr < fv[n - 1]:
+            v[n], fv[n] = xr, fxr
+        else:
+            if fxr < fv[n]:  # outside contraction
+                xc = [(1 + psi * rho) * xbar[i] - psi * rho * v[n][i] for i in range(n)]
+                fxc = funk(xc)
+                func_evals += 1
+                if fxc <= fxr:
+                    v[n], fv[n] = xc, fxc
+                else:
+                    shrink = True
+            else:  # inside contraction
+                xcc = [(1 - psi) * xbar[i] + psi * v[n][i] for i in range(n)]
+                fxcc = funk(xcc)
+                func_evals += 1
+                if fxcc < fv[n]:
+                    v[n], fv[n] = xcc, fxcc
+                else:
+                    shrink = True
+            if shrink:
+                for j in range(1, n + 1):
+                    v[j] = [v[0][i] + sigma * (v[j][i] - v[0][i]) for i in range(n)]
+                    fv[j] = funk(v[j])
+                func_evals += n
+        fv, place = _bubble_sort(fv)
+        v = [v[p] for p in place]
+        itercount += 1
+    return v[0], fv[0], itercount, func_evals
+
+
 _TAU_EPS_CACHE: Dict[tuple, np.ndarray] = {}
 
 
 def tau_eps_of(Q: float, tau_s: np.ndarray, min_period: float, max_period: float) -> np.ndarray:
-    """attenuation_invert_by_simplex: minimise sum_f |tan_delta(f) - 1/Q| / (1/Q) over tau_eps."""
-    from scipy.optimize import minimize
-
-    key = (round(Q, 6), tuple(np.round(tau_s, 15)), min_period, max_period)
+    """attenuation_invert_by_simplex (get_attenuation_model.f90:976-1058): fit of tau_eps to a constant Q over 100
+    log-spaced frequencies of the band, started at tau_s (1 + 2/Q), minimised by the reference's fminsearch above.
+    Pinned: the tau_eps / scale factors the reference printed for its viscoelastic benchmark (hard-wired in
+    EXAMPLES/benchmarks/attenuation/viscoelastic/analytical_solution_viscoelastic_3D_*.f90:131-150) are reproduced
+    to 1e-14 (tests/test_attenuation_constants.py).  Results are cached per Q like model_attenuation_storage
+    (:838-971; its index is int(10 Q), i.e. Q values closer than 0.1 share the first one's tau_eps)."""
+    key = (int(Q * 10.0), tuple(np.round(tau_s, 15)), min_period, max_period)
     if key in _TAU_EPS_CACHE:
         return _TAU_EPS_CACHE[key]
     nf = 100
     e1, e2 = math.log10(1.0 / max_period), math.log10(1.0 / min_period)
-    f_log = e1 + np.arange(nf) * (e2 - e1) / (nf - 1.0)
+    f_log = [e1 + ((i * 1.0) * (e2 - e1) / ((nf - 1) * 1.0)) for i in range(nf)]
+    ts = [float(t) for t in tau_s]
     iQ = 1.0 / Q
-
-    def cost(x):
-        A, B = _maxwell(f_log, tau_s, x)
-        return float(np.sqrt(((B / A - iQ) ** 2) / iQ ** 2).sum())
-
-    x0 = tau_s + tau_s * 2.0 / Q
-    res = minimize(cost, x0, method="Nelder-Mead", options={"xatol": 1e-12, "fatol": 1e-10, "maxiter": 20000,
-                                                             "maxfev": 40000, "adaptive": False})
-    _TAU_EPS_CACHE[key] = res.x
-    return res.x
+    x0 = [t + (t * 2.0 / Q) for t in ts]
+    x, _, _, _ = fminsearch(lambda x: _attenuation_eval(x, f_log, ts, iQ), x0)
+    _TAU_EPS_CACHE[key] = np.array(x)
+    return _TAU_EPS_CACHE[key]
 
 
 def scale_factor_of(f_c_source: float, tau_eps: np.ndarray, tau_s: np.ndarray, Q: float, f0_ref: float) -> float:

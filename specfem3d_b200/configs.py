@@ -99,3 +99,36 @@ def attenuation_benchmark(NSTEP: int = 1300) -> Simulation:
     src = ForceSource(x=10.0, y=10.0, z=10.0, factor=1.0, comp=(0.0, 0.0, 1.0), hdur=18.0)
     return make_simulation(spec, DT=0.0005, NSTEP=NSTEP, sources=[src], stations=[Station("1", "CE", 510.0, 510.0, 510.0)],
                            attenuation=True, f0_attenuation=18.0)
+
+
+WATER = Material(1028.0, 1480.0, 0.0, 9999.0, 9999.0, 1)
+ROCK = Material(3200.0, 7500.0, 4300.0, 9999.0, 9999.0, 2)
+
+# DATA/STATIONS of the water-layer example: name, x (longitude column), y (latitude column), burial depth in m
+_WATERLAYER_STATIONS = [
+    ("X10", 10767.86, 67000.0, 100.0), ("X20", 22732.14, 67000.0, 100.0), ("X30", 34696.43, 67000.0, 100.0),
+    ("X40", 46660.71, 67000.0, 100.0), ("X50", 58625.00, 67000.0, 100.0), ("X55", 67000.00, 67000.0, 100.0),
+    ("X60", 75375.00, 67000.0, 100.0), ("X70", 87339.29, 67000.0, 100.0), ("X80", 99303.57, 67000.0, 100.0),
+    ("X90", 111269.86, 67000.0, 100.0), ("X1", 0.0, 67000.0, 100.0), ("X2", 67000.0, 67000.0, 25000.0),
+    ("X3", 134000.0, 67000.0, 100.0), ("X4", 67000.0, 67000.0, 3500.0), ("X5", 67000.0, 67000.0, 3000.2),
+    ("X6", 67000.0, 67000.0, 3000.1), ("X7", 67000.0, 67000.0, 2999.9), ("X8", 67000.0, 67000.0, 2999.8),
+    ("Y1", 58625.0, 67000.0, 2999.9), ("Y2", 58625.0, 67000.0, 3000.1), ("Y3", 46660.71, 67000.0, 2999.9),
+    ("Y4", 46660.71, 67000.0, 3000.1),
+]
+
+
+def waterlayered_halfspace(NSTEP: int = 4500, nproc_xi: int = 1, nproc_eta: int = 1, stations=None) -> Simulation:
+    """The reference's coupled fluid-solid example (EXAMPLES/applications/waterlayered_halfspace, MESH-default): the
+    134 km x 134 km x 60 km box in 45 x 45 x 20 elements (2977.78 m x 2977.78 m x 3000 m), the top element layer water
+    (rho 1028, vp 1480), the rest rock (rho 3200, vp 7500, vs 4300; MESH-default/nummaterial_velocity_file), free surface
+    on top of the water, Stacey on the other five sides, an explosive moment tensor (1e23 dyne-cm on the diagonal,
+    half duration 2 s) IN the water at (66999.9, 67000, -1000), 22 stations of which 14 sit in the water layer and
+    X5 ... X8, Y1 ... Y4 straddle the sea floor; DT 0.005, NSTEP 4500 (DATA/Par_file, CMTSOLUTION, STATIONS;
+    REF_SEIS/output_solver.txt: 2025 acoustic + 38475 elastic elements, start time -6 s).  ``stations``: optional subset
+    of station names."""
+    spec = BoxSpec(45, 45, 20, nproc_xi=nproc_xi, nproc_eta=nproc_eta, materials=(ROCK, WATER),
+                   layer_material=[0] * 19 + [1])
+    src = CMTSource(x=66999.9, y=67000.0, z=-1000.0, moment_tensor=(1e23, 1e23, 1e23, 0.0, 0.0, 0.0), hdur=2.0)
+    sts = [Station(n, "DB", x, y, -d) for n, x, y, d in _WATERLAYER_STATIONS if stations is None or n in stations]
+    return make_simulation(spec, DT=0.005, NSTEP=NSTEP, sources=[src], stations=sts, SAVE_SEISMOGRAMS_VELOCITY=True,
+                           SAVE_SEISMOGRAMS_ACCELERATION=True)

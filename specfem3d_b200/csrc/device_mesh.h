@@ -71,6 +71,7 @@ inline bool very_slow_error_checking() {
 // ---------------------------------------------------------------------------------------------------------------
 struct DeviceMesh {
   int device = 0;
+  int num_sms = 148;  // multiProcessorCount of the device (persistent grids are sized from it)
   int myrank = 0;
   // sizes / flags
   int NSPEC_AB = 0, NGLOB_AB = 0, NSPEC_IRREGULAR = 0;
@@ -194,6 +195,9 @@ struct DeviceMesh {
 
   // grouped element storage of the TMA force kernels (kernels_elastic_grp.cuh), built lazily at the first launch
   struct GroupStore* grp_elastic = nullptr;
+  // library numbering of the global points (renumber.h): perm[host id] = device id, both 0-based; identity when disabled
+  std::vector<int> h_perm;
+  int* d_perm = nullptr;
   std::vector<int> h_irregular_element_number;   // host copies needed to build it
   std::vector<int> h_phase_ispec_elastic;        // [2][num_phase_ispec_elastic]
   std::vector<int> h_is_CPML;                    // empty when no PML

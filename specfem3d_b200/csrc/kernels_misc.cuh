@@ -475,14 +475,26 @@ __global__ void __launch_bounds__(256) k_halo_unpack_add(realw* field, const rea
 // ---------------------------------------------------------------------------------------------------------------
 // host layout (NDIM,NGLOB) <-> the library's vector-wavefield layout (kernels_common.cuh: vidx); transfer_* entry points only
 template <bool TO_LIBRARY>
-__global__ void __launch_bounds__(256) k_vector_layout(realw* __restrict__ dst, const realw* __restrict__ src, size_t nglob) {
+__global__ void __launch_bounds__(256) k_vector_layout(realw* __restrict__ dst, const realw* __restrict__ src,
+                                                       const int* __restrict__ perm, size_t nglob) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nglob; i += stride) {
+    const size_t q = (size_t)perm[i];  // host point i lives at library point q (renumber.h)
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      if (TO_LIBRARY) dst[vidx(i, c, nglob)] = src[3 * i + c];
-      else dst[3 * i + c] = src[vidx(i, c, nglob)];
+      if (TO_LIBRARY) dst[vidx(q, c, nglob)] = src[3 * i + c];
+      else dst[3 * i + c] = src[vidx(q, c, nglob)];
     }
+  }
+}
+template <bool TO_LIBRARY>
+__global__ void __launch_bounds__(256) k_scalar_layout(realw* __restrict__ dst, const realw* __restrict__ src,
+                                                       const int* __restrict__ perm, size_t nglob) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nglob; i += stride) {
+    const size_t q = (size_t)perm[i];
+    if (TO_LIBRARY) dst[q] = src[i];
+    else dst[i] = src[q];
   }
 }
 

@@ -10,10 +10,9 @@
 #include "kernels_acoustic.cuh"
 #include "kernels_common.cuh"
 #include "kernels_elastic.cuh"
-#include "kernels_elastic_col.cuh"
-#include "kernels_elastic_grp.cuh"
-#include "kernels_elastic_po.cuh"
-#include "kernels_elastic_pk.cuh"
+#include "group_store.cuh"
+#include "renumber.h"
+#include "kernels_elastic_row.cuh"
 #include "kernels_misc.cuh"
 #include "adjoint.cuh"
 #include "pml.cuh"
@@ -58,6 +57,7 @@ static void download_sls(DeviceMesh* mp, const realw* d, realw* h) {
   KERNEL_CHECK(mp, "k_relayout_sls_to_host");
   CUDA_CHECK(cudaMemcpyAsync(h, tmp, n * sizeof(realw), cudaMemcpyDeviceToHost, mp->compute_stream));
   CUDA_CHECK(cudaStreamSynchronize(mp->compute_stream));
+  p2p_check_error(mp);
   dev_free(tmp);
 }
 
@@ -68,6 +68,14 @@ static int streaming_grid(long long n4) {
   if (want > cap) want = cap;
   if (want < 1) want = 1;
   return (int)want;
+}
+
+// a host array indexed by global point, uploaded in the library numbering
+static realw* dev_copy_permuted(DeviceMesh* mp, const realw* h) {
+  const size_t nglob = mp->NGLOB_AB;
+  std::vector<realw> tmp(nglob);
+  for (size_t i = 0; i < nglob; ++i) tmp[mp->h_perm[i]] = h[i];
+  return dev_copy(tmp.data(), nglob);
 }
 
 }  // namespace sb200
@@ -169,6 +177,7 @@ extern "C" void SB200_FC(prepare_constants_device)(
   int cur = 0;
   CUDA_CHECK(cudaGetDevice(&cur));
   mp->device = cur;
+  CUDA_CHECK(cudaDeviceGetAttribute(&mp->num_sms, cudaDevAttrMultiProcessorCount, cur));
   mp->myrank = *h_myrank;
   mp->NSPEC_AB = *NSPEC_AB;
   mp->NGLOB_AB = *NGLOB_AB;
@@ -196,7 +205,25 @@ extern "C" void SB200_FC(prepare_constants_device)(
   const size_t nspec = mp->NSPEC_AB;
   mp->d_irregular_element_number = dev_copy(h_irregular_element_number, nspec);
   mp->h_irregular_element_number.assign(h_irregular_element_number, h_irregular_element_number + nspec);
-  mp->d_ibool = dev_copy_padded<int>(h_ibool, nspec, 1);
+  // the library's own point numbering (renumber.h); SPECFEM_B200_RENUMBER=0 keeps the host numbering
+  {
+    const char* e = getenv("SPECFEM_B200_RENUMBER");
+    const size_t nglob = mp->NGLOB_AB;
+    if (e && atoi(e) == 0) {
+      mp->h_perm.resize(nglob);
+      for (size_t p = 0; p < nglob; ++p) mp->h_perm[p] = (int)p;
+    } else {
+      mp->h_perm = compute_point_numbering(h_ibool, mp->NSPEC_AB, mp->NGLOB_AB, h_ispec_is_inner, ispec_is_elastic,
+                                           ispec_is_acoustic, h_irregular_element_number);
+    }
+    mp->d_perm = dev_copy(mp->h_perm.data(), nglob);
+    std::vector<int> ib(nspec * NGLL3);
+    for (size_t q = 0; q < ib.size(); ++q) {
+      if (h_ibool[q] < 1 || (size_t)h_ibool[q] > nglob) exit_on_error("prepare_constants_device: ibool entry outside 1..NGLOB_AB");
+      ib[q] = mp->h_perm[h_ibool[q] - 1] + 1;
+    }
+    mp->d_ibool = dev_copy_padded<int>(ib.data(), nspec, 1);
+  }
 
   // metric record per irregular element: 9 planes of 128 floats (one contiguous 4.5 KB slab)
   {
@@ -218,8 +245,18 @@ extern "C" void SB200_FC(prepare_constants_device)(
   mp->max_nibool_interfaces_ext_mesh = *max_nibool_interfaces_ext_mesh;
   if (mp->num_interfaces_ext_mesh > 0) {
     mp->d_nibool_interfaces_ext_mesh = dev_copy(h_nibool_interfaces_ext_mesh, mp->num_interfaces_ext_mesh);
-    mp->d_ibool_interfaces_ext_mesh =
-        dev_copy(h_ibool_interfaces_ext_mesh, (size_t)mp->num_interfaces_ext_mesh * mp->max_nibool_interfaces_ext_mesh);
+    {
+      // interface point lists in the library numbering; the slots behind nibool(i) are padding (zeros in the database)
+      const size_t mx = mp->max_nibool_interfaces_ext_mesh;
+      std::vector<int> ifc((size_t)mp->num_interfaces_ext_mesh * mx, 0);
+      for (int n = 0; n < mp->num_interfaces_ext_mesh; ++n)
+        for (int q = 0; q < h_nibool_interfaces_ext_mesh[n]; ++q) {
+          const int old = h_ibool_interfaces_ext_mesh[n * mx + q];
+          if (old < 1 || old > mp->NGLOB_AB) exit_on_error("prepare_constants_device: interface point outside 1..NGLOB_AB");
+          ifc[n * mx + q] = mp->h_perm[old - 1] + 1;
+        }
+      mp->d_ibool_interfaces_ext_mesh = dev_copy(ifc.data(), ifc.size());
+    }
     mp->h_nibool_interfaces.assign(h_nibool_interfaces_ext_mesh, h_nibool_interfaces_ext_mesh + mp->num_interfaces_ext_mesh);
   }
   mp->d_ispec_is_inner = dev_copy(h_ispec_is_inner, nspec);
@@ -336,9 +373,10 @@ extern "C" void SB200_FC(prepare_fields_elastic_device)(
   {
     std::vector<realw> r3(NDIM * nglob);
     for (size_t i = 0; i < nglob; ++i) {
-      r3[vidx(i, 0, nglob)] = rmassx[i];
-      r3[vidx(i, 1, nglob)] = rmassy[i];
-      r3[vidx(i, 2, nglob)] = rmassz[i];
+      const size_t q = mp->h_perm[i];
+      r3[vidx(q, 0, nglob)] = rmassx[i];
+      r3[vidx(q, 1, nglob)] = rmassy[i];
+      r3[vidx(q, 2, nglob)] = rmassz[i];
     }
     mp->d_rmassx = dev_copy(r3.data(), r3.size());  // d_rmassx holds all three
   }
@@ -396,7 +434,7 @@ extern "C" void SB200_FC(prepare_fields_elastic_device)(
   (void)ACOUSTIC_SIMULATION;
   mp->approximate_ocean_load = *APPROXIMATE_OCEAN_LOAD;
   if (mp->approximate_ocean_load) {
-    mp->d_rmass_ocean_load = dev_copy(rmass_ocean_load, nglob);
+    mp->d_rmass_ocean_load = dev_copy_permuted(mp, rmass_ocean_load);
     // unique free-surface points in the order of the CPU loop (faces, then GLL points; every face, like the reference)
     std::vector<int> h_ibool((size_t)nspec * NGLL3_PADDED);
     CUDA_CHECK(cudaMemcpy(h_ibool.data(), mp->d_ibool, h_ibool.size() * sizeof(int), cudaMemcpyDeviceToHost));
@@ -443,7 +481,7 @@ extern "C" void SB200_FC(prepare_fields_acoustic_device)(
   mp->d_potential_dot_dot = dev_alloc_zero<realw>(nglob);
   mp->size_mpi_buffer_potential = mp->num_interfaces_ext_mesh * mp->max_nibool_interfaces_ext_mesh;
   if (mp->size_mpi_buffer_potential > 0) mp->d_send_potential_buffer = dev_alloc_zero<realw>(mp->size_mpi_buffer_potential);
-  mp->d_rmass_acoustic = dev_copy(rmass_acoustic, nglob);
+  mp->d_rmass_acoustic = dev_copy_permuted(mp, rmass_acoustic);
   mp->d_rhostore = dev_copy_padded<realw>(rhostore, nspec, 1.f);
   mp->d_kappastore_unpadded = dev_copy(kappastore, NGLL3 * nspec);
   mp->num_phase_ispec_acoustic = *num_phase_ispec_acoustic;
@@ -487,7 +525,9 @@ extern "C" void SB200_FC(prepare_cleanup_device)(long* Mesh_pointer, int* ACOUST
   (void)ACOUSTIC_SIMULATION; (void)ELASTIC_SIMULATION; (void)NOISE_TOMOGRAPHY;
   DeviceMesh* mp = get_mesh(Mesh_pointer);
   CUDA_CHECK(cudaDeviceSynchronize());
+  p2p_check_error(mp);
   p2p_destroy(mp);
+  dev_free(mp->d_perm);
   pml_destroy(mp);
   group_store_free(mp->grp_elastic);
   void* dptrs[] = {mp->d_ibool, mp->d_irregular_element_number, mp->d_metric, mp->d_kappav, mp->d_muv, mp->d_rhostore,
@@ -540,6 +580,7 @@ static void d2h(DeviceMesh* mp, realw* h, const realw* d, size_t n) {
   if (!d) exit_on_error("transfer from a device field that was never allocated (prepare_fields_* not called?)");
   CUDA_CHECK(cudaMemcpyAsync(h, d, n * sizeof(realw), cudaMemcpyDeviceToHost, mp->compute_stream));
   CUDA_CHECK(cudaStreamSynchronize(mp->compute_stream));
+  p2p_check_error(mp);  // host-blocking point: a halo wait that timed out must abort, not hand back unassembled fields
 }
 
 // vector wavefields: the Fortran (NDIM,NGLOB) array <-> the library's component planes (kernels_common.cuh: vidx), through
@@ -547,21 +588,39 @@ static void d2h(DeviceMesh* mp, realw* h, const realw* d, size_t n) {
 static void h2d_vec(DeviceMesh* mp, realw* d, const realw* h, int size) {
   if (!d) exit_on_error("transfer to a device field that was never allocated (prepare_fields_* not called?)");
   if ((size_t)size != (size_t)NDIM * mp->NGLOB_AB) exit_on_error("transfer of a vector wavefield: size is not NDIM * NGLOB_AB");
-  if (!SB200_SOA) { h2d(mp, d, h, size); return; }
   realw* tmp = dev_alloc<realw>(size);
   h2d(mp, tmp, h, size);
-  k_vector_layout<true><<<streaming_grid(mp->NGLOB_AB), 256, 0, mp->compute_stream>>>(d, tmp, (size_t)mp->NGLOB_AB);
-  KERNEL_CHECK(mp, "k_vector_layout(to planes)");
+  k_vector_layout<true><<<streaming_grid(mp->NGLOB_AB), 256, 0, mp->compute_stream>>>(d, tmp, mp->d_perm, (size_t)mp->NGLOB_AB);
+  KERNEL_CHECK(mp, "k_vector_layout(to the library layout)");
   CUDA_CHECK(cudaStreamSynchronize(mp->compute_stream));
   dev_free(tmp);
 }
 static void d2h_vec(DeviceMesh* mp, realw* h, const realw* d, int size) {
   if (!d) exit_on_error("transfer from a device field that was never allocated (prepare_fields_* not called?)");
   if ((size_t)size != (size_t)NDIM * mp->NGLOB_AB) exit_on_error("transfer of a vector wavefield: size is not NDIM * NGLOB_AB");
-  if (!SB200_SOA) { d2h(mp, h, d, size); return; }
   realw* tmp = dev_alloc<realw>(size);
-  k_vector_layout<false><<<streaming_grid(mp->NGLOB_AB), 256, 0, mp->compute_stream>>>(tmp, d, (size_t)mp->NGLOB_AB);
-  KERNEL_CHECK(mp, "k_vector_layout(from planes)");
+  k_vector_layout<false><<<streaming_grid(mp->NGLOB_AB), 256, 0, mp->compute_stream>>>(tmp, d, mp->d_perm, (size_t)mp->NGLOB_AB);
+  KERNEL_CHECK(mp, "k_vector_layout(from the library layout)");
+  d2h(mp, h, tmp, size);
+  dev_free(tmp);
+}
+// scalar wavefields (potentials): host numbering <-> library numbering
+static void h2d_pot(DeviceMesh* mp, realw* d, const realw* h, int size) {
+  if (!d) exit_on_error("transfer to a device field that was never allocated (prepare_fields_* not called?)");
+  if (size != mp->NGLOB_AB) exit_on_error("transfer of a scalar wavefield: size is not NGLOB_AB");
+  realw* tmp = dev_alloc<realw>(size);
+  h2d(mp, tmp, h, size);
+  k_scalar_layout<true><<<streaming_grid(mp->NGLOB_AB), 256, 0, mp->compute_stream>>>(d, tmp, mp->d_perm, (size_t)mp->NGLOB_AB);
+  KERNEL_CHECK(mp, "k_scalar_layout(to the library numbering)");
+  CUDA_CHECK(cudaStreamSynchronize(mp->compute_stream));
+  dev_free(tmp);
+}
+static void d2h_pot(DeviceMesh* mp, realw* h, const realw* d, int size) {
+  if (!d) exit_on_error("transfer from a device field that was never allocated (prepare_fields_* not called?)");
+  if (size != mp->NGLOB_AB) exit_on_error("transfer of a scalar wavefield: size is not NGLOB_AB");
+  realw* tmp = dev_alloc<realw>(size);
+  k_scalar_layout<false><<<streaming_grid(mp->NGLOB_AB), 256, 0, mp->compute_stream>>>(tmp, d, mp->d_perm, (size_t)mp->NGLOB_AB);
+  KERNEL_CHECK(mp, "k_scalar_layout(from the library numbering)");
   d2h(mp, h, tmp, size);
   dev_free(tmp);
 }
@@ -594,20 +653,20 @@ extern "C" void SB200_FC(transfer_accel_from_device)(int* size, realw* accel, lo
 }
 extern "C" void SB200_FC(transfer_fields_ac_to_device)(int* size, field* p, field* pd, field* pdd, long* Mesh_pointer) {
   DeviceMesh* mp = get_mesh(Mesh_pointer);
-  h2d(mp, mp->d_potential, p, *size); h2d(mp, mp->d_potential_dot, pd, *size); h2d(mp, mp->d_potential_dot_dot, pdd, *size);
+  h2d_pot(mp, mp->d_potential, p, *size); h2d_pot(mp, mp->d_potential_dot, pd, *size); h2d_pot(mp, mp->d_potential_dot_dot, pdd, *size);
 }
 extern "C" void SB200_FC(transfer_fields_ac_from_device)(int* size, field* p, field* pd, field* pdd, long* Mesh_pointer) {
   DeviceMesh* mp = get_mesh(Mesh_pointer);
-  d2h(mp, p, mp->d_potential, *size); d2h(mp, pd, mp->d_potential_dot, *size); d2h(mp, pdd, mp->d_potential_dot_dot, *size);
+  d2h_pot(mp, p, mp->d_potential, *size); d2h_pot(mp, pd, mp->d_potential_dot, *size); d2h_pot(mp, pdd, mp->d_potential_dot_dot, *size);
 }
 extern "C" void SB200_FC(transfer_potential_ac_from_device)(int* size, field* p, long* Mesh_pointer) {
-  DeviceMesh* mp = get_mesh(Mesh_pointer); d2h(mp, p, mp->d_potential, *size);
+  DeviceMesh* mp = get_mesh(Mesh_pointer); d2h_pot(mp, p, mp->d_potential, *size);
 }
 extern "C" void SB200_FC(transfer_dot_dot_to_device)(int* size, field* pdd, long* Mesh_pointer) {
-  DeviceMesh* mp = get_mesh(Mesh_pointer); h2d(mp, mp->d_potential_dot_dot, pdd, *size);
+  DeviceMesh* mp = get_mesh(Mesh_pointer); h2d_pot(mp, mp->d_potential_dot_dot, pdd, *size);
 }
 extern "C" void SB200_FC(transfer_dot_dot_from_device)(int* size, field* pdd, long* Mesh_pointer) {
-  DeviceMesh* mp = get_mesh(Mesh_pointer); d2h(mp, pdd, mp->d_potential_dot_dot, *size);
+  DeviceMesh* mp = get_mesh(Mesh_pointer); d2h_pot(mp, pdd, mp->d_potential_dot_dot, *size);
 }
 
 extern "C" void SB200_FC(transfer_rmemory_from_device)(long* Mesh_pointer, realw* R_xx, realw* R_yy, realw* R_xy,
@@ -623,6 +682,7 @@ static void download_padded(DeviceMesh* mp, const realw* d, realw* h) {
   CUDA_CHECK(cudaMemcpy2DAsync(h, NGLL3 * sizeof(realw), d, NGLL3_PADDED * sizeof(realw), NGLL3 * sizeof(realw),
                                mp->NSPEC_AB, cudaMemcpyDeviceToHost, mp->compute_stream));
   CUDA_CHECK(cudaStreamSynchronize(mp->compute_stream));
+  p2p_check_error(mp);
 }
 extern "C" void SB200_FC(transfer_strain_from_device)(long* Mesh_pointer, realw* exx, realw* eyy, realw* exy, realw* exz,
                                                       realw* eyz, realw* etrace, int* size_epsilondev) {
@@ -836,14 +896,10 @@ static void launch_elastic(DeviceMesh* mp, int nb, const int* phase_list, int fi
 
   const bool att = mp->attenuation != 0;
   const bool strain = mp->compute_and_store_strain != 0;
-  if (mp->force_kernel_variant == 2 && !att && !strain) {
-    launch_elastic_col(mp, a);
-  } else {
-    // plain one-thread-per-point path; the only one that handles attenuation / strain storage so far
-    if (att) k_elastic_forces_pt<true, true><<<nb, NGLL3_PADDED, 0, mp->compute_stream>>>(a);
-    else if (strain) k_elastic_forces_pt<false, true><<<nb, NGLL3_PADDED, 0, mp->compute_stream>>>(a);
-    else k_elastic_forces_pt<false, false><<<nb, NGLL3_PADDED, 0, mp->compute_stream>>>(a);
-  }
+  // one-thread-per-point path: attenuation / strain storage, and SPECFEM_B200_FORCE_KERNEL=1 (A/B of the default kernel)
+  if (att) k_elastic_forces_pt<true, true><<<nb, NGLL3_PADDED, 0, mp->compute_stream>>>(a);
+  else if (strain) k_elastic_forces_pt<false, true><<<nb, NGLL3_PADDED, 0, mp->compute_stream>>>(a);
+  else k_elastic_forces_pt<false, false><<<nb, NGLL3_PADDED, 0, mp->compute_stream>>>(a);
   KERNEL_CHECK(mp, "elastic forces");
 }
 
@@ -872,7 +928,7 @@ static void ensure_elastic_groups(DeviceMesh* mp, int nspec_outer, int nspec_inn
       segs.push_back(seg);
     }
   }
-  mp->grp_elastic = group_store_build(mp, segs, mp->h_irregular_element_number, mp->d_irregular_element_number, mp->d_kappav, mp->d_muv);
+  mp->grp_elastic = group_store_build(mp, segs, mp->h_irregular_element_number, mp->d_irregular_element_number, mp->d_kappav, mp->d_muv, /*lane_map=*/1);
 }
 
 extern "C" void SB200_FC(compute_forces_viscoelastic_cuda)(long* Mesh_pointer, int* iphase, realw* deltat,
@@ -883,7 +939,10 @@ extern "C" void SB200_FC(compute_forces_viscoelastic_cuda)(long* Mesh_pointer, i
   const int foa = *FORWARD_OR_ADJOINT_f;
   if (foa != 0 && foa != 1 && foa != 3) exit_on_error("compute_forces_viscoelastic_cuda: FORWARD_OR_ADJOINT must be 0, 1 or 3");
   if ((*ATTENUATION != 0) != (mp->attenuation != 0)) exit_on_error("compute_forces_viscoelastic_cuda: ATTENUATION differs from prepare_fields_elastic_device");
-  (void)COMPUTE_AND_STORE_STRAIN;
+  // the kernel choice (strain-storing or not) was fixed by prepare_fields_elastic_device: a caller that asks for something
+  // else per call would be silently mis-served
+  if ((*COMPUTE_AND_STORE_STRAIN != 0) != (mp->compute_and_store_strain != 0))
+    exit_on_error("compute_forces_viscoelastic_cuda: COMPUTE_AND_STORE_STRAIN differs from prepare_fields_elastic_device");
   const int num_elements = (*iphase == 1) ? *nspec_outer_elastic : *nspec_inner_elastic;
   if (foa != 1 || mp->simulation_type == 3) {
     // kernel run (compute_forces_viscoelastic_cuda.cu:1131-1278): 0 = adjoint wavefield, then the reconstructed forward
@@ -951,7 +1010,7 @@ extern "C" void SB200_FC(compute_forces_viscoelastic_cuda)(long* Mesh_pointer, i
     }
     return;
   }
-  const bool grp = (mp->force_kernel_variant == 0 || mp->force_kernel_variant >= 3) && !mp->attenuation && !mp->compute_and_store_strain;
+  const bool grp = mp->force_kernel_variant == 0 && !mp->attenuation && !mp->compute_and_store_strain;
   if (num_elements > 0 && grp) {
     ensure_elastic_groups(mp, *nspec_outer_elastic, *nspec_inner_elastic);
     if (mp->use_mesh_coloring_gpu) {
@@ -1481,6 +1540,7 @@ extern "C" void SB200_FC(compute_seismograms_cuda)(long* Mesh_pointer_f, realw* 
       }
     }
     CUDA_CHECK(cudaStreamSynchronize(mp->compute_stream));
+    p2p_check_error(mp);  // the seismograms handed back must come from assembled wavefields
   }
 }
 

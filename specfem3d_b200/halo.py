@@ -20,6 +20,23 @@ from typing import List
 import numpy as np
 
 
+def check_p2p_domains(rank: int, domains, neighbor_domains: dict) -> None:
+    """The p2p path exchanges a field only between ranks that both launch its pack kernel.  The reference has EVERY rank
+    take part in assemble_MPI_* once ELASTIC_SIMULATION / ACOUSTIC_SIMULATION is set globally (a rank without elements of
+    the domain sends zeros); here a neighbour without the domain has no such field on its device and would never raise the
+    flag this rank waits for.  Such partitions (e.g. a purely acoustic part next to an elastic one) must use the
+    host-staged path; refuse them at connect time instead of timing out inside the time loop."""
+    for nb, dom in neighbor_domains.items():
+        for d in domains:
+            if d not in dom:
+                raise ValueError(f"p2p halo: rank {rank} exchanges its {d} field with rank {nb}, which owns no {d} elements; "
+                                 f"use the host-staged halo (halo='host') for this partition")
+
+
+def _domains_of(rank_obj):
+    return tuple(d for d, has in (("elastic", rank_obj.ELASTIC), ("acoustic", rank_obj.ACOUSTIC)) if has)
+
+
 def assemble_scalar_distributed(db, arr: np.ndarray, group) -> None:
     """assemble_MPI_scalar_blocking (src/specfem3D/assemble_MPI_scalar.f90:30-120) over torch.distributed."""
     import torch
@@ -67,10 +84,11 @@ class DistributedExchange:
         L.cdll.specfem_b200_halo_p2p_local_pointer_(ctypes.byref(r.Mesh_pointer), ctypes.byref(slab), ctypes.byref(dev))
         me = {"rank": r.rank, "handle": bytes(handle.raw), "device": int(dev.value), "nif": nif,
               "max_nibool": int(db.max_nibool_interfaces_ext_mesh),
-              "neighbors": [int(v) for v in db.my_neighbors_ext_mesh[:nif]]}
+              "neighbors": [int(v) for v in db.my_neighbors_ext_mesh[:nif]], "domains": _domains_of(r)}
         allinfo = [None] * self.world
         dist.all_gather_object(allinfo, me, group=self.group)
         by_rank = {d["rank"]: d for d in allinfo}
+        check_p2p_domains(r.rank, me["domains"], {nb: by_rank[nb]["domains"] for nb in me["neighbors"]})
         handles = (ctypes.c_char * (64 * nif))()
         geom = np.zeros(3 * nif, np.int32)
         nbr = np.zeros(nif, np.int32)
@@ -128,6 +146,9 @@ def connect_p2p_in_process(ranks: List) -> None:
         L.cdll.specfem_b200_halo_p2p_local_pointer_(ctypes.byref(r.Mesh_pointer), ctypes.byref(slab), ctypes.byref(dev))
         info[r.rank] = (slab.value, int(dev.value))
     by_rank = {r.rank: r for r in ranks}
+    for r in ranks:
+        check_p2p_domains(r.rank, _domains_of(r), {int(nb): _domains_of(by_rank[int(nb)])
+                                                   for nb in r.db.my_neighbors_ext_mesh[: r.db.num_interfaces_ext_mesh]})
     for r in ranks:
         db, L = r.db, r.lib
         nif = db.num_interfaces_ext_mesh

@@ -215,12 +215,14 @@ def setup_sources(spec: BoxSpec, dbs: List[Database], sources: Sequence, DT: flo
     tsh = tsh - tsh.min() if ns > 1 else np.zeros(1)
     is_cmt = isinstance(sources[0], CMTSource)
     local = []
+    in_fluid = []
     for n, s in enumerate(sources):
         rank, ispec, xi, eta, gam, _ = locate_point(spec, dbs, s.x, s.y, s.z)
         isl[n], isp[n] = rank, ispec
         local.append((xi, eta, gam))
+        in_fluid.append(bool(dbs[rank].ispec_is_acoustic[ispec - 1]))
         if is_cmt:
-            sa[..., n] = sourcearray_cmt(dbs[rank], gll, ispec, xi, eta, gam, s)
+            sa[..., n] = sourcearray_cmt(dbs[rank], gll, ispec, xi, eta, gam, s)  # fluid: simulation._acoustic_sourcearrays
             hdur[n] = max(s.hdur, 5.0 * DT)  # get_cmt.f90:369
         else:
             sa[..., n] = sourcearray_force(gll, xi, eta, gam, s)
@@ -228,8 +230,9 @@ def setup_sources(spec: BoxSpec, dbs: List[Database], sources: Sequence, DT: flo
     if is_cmt:
         hg = hdur / SOURCE_DECAY_MIMIC_TRIANGLE
         t0 = -2.0 * float(np.min(tsh - hdur))  # setup_sources_receivers.f90:491
-        if acoustic_present:
-            t0 = max(t0, -3.0 * float(np.min(tsh - hdur)))  # :494-520
+        for n in range(ns):  # sources located in a fluid element start earlier (:497-516)
+            if in_fluid[n]:
+                t0 = max(t0, -3.0 * float(tsh[n] - hdur[n]))
         kind = "cmt"
     else:
         hg = hdur / SOURCE_DECAY_MIMIC_TRIANGLE

@@ -1,0 +1,145 @@
+"""GPU runs of the reference's own examples, over their FULL length, against the reference's golden seismograms
+(tests/golden/*.npz, generated from /root/reference/EXAMPLES/**/REF_SEIS by tests/golden/make_golden.py), and parity with
+the CPU oracle at BASELINE config size.  Tolerance: relative L2 <= 1e-4 per trace (BASELINE.json north_star).
+
+Everything goes through the C ABI (specfem3d_b200/abi.py -> libspecfem3d_b200.so) exactly like the Fortran time loop.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def test_cfg1_all_5000_steps_against_REF_SEIS(device_lib):
+    """Config 1 (EXAMPLES/applications/homogeneous_halfspace), 4 ranks, all 5000 steps, all 12 traces and all ten
+    max-norm lines of REF_SEIS/output_solver.txt."""
+    from specfem3d_b200.configs import cfg1
+    from specfem3d_b200.time_loop import DeviceRun
+
+    gold = np.load(os.path.join(GOLD, "halfspace_ref_seis.npz"))
+    ref_norm = dict(zip(gold["maxnorm_step"].tolist(), gold["maxnorm_value"].tolist()))
+    sim = cfg1(2, 2, 5000)
+    run = DeviceRun(sim)
+    norms = {}
+    for it in range(1, 5001):
+        if it in ref_norm:  # check_stability reads the norm at the top of step it (iterate_time.F90:233)
+            norms[it] = run.max_norm_displ()
+        run.step()
+    sd = run.gather_seismograms("d")
+    run.cleanup()
+    errs = {}
+    for i, st in enumerate(("X20", "X30", "X40", "X50")):
+        for c, ch in enumerate("XYZ"):
+            errs[st + "." + ch] = rel_l2(sd[i, :, c], gold[f"{st}_{ch}"])
+    print("cfg1, 5000 steps on the GPU, relative L2 vs REF_SEIS:", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) <= 1e-4, errs
+    for it, v in norms.items():
+        if it >= 500:
+            assert abs(v - ref_norm[it]) / ref_norm[it] < 1e-4, (it, v, ref_norm[it])
+
+
+def test_waterlayered_halfspace_against_REF_SEIS(device_lib):
+    """Coupled fluid-solid example (EXAMPLES/applications/waterlayered_halfspace): acoustic forces, free surface, acoustic
+    Stacey, both coupling directions, pressure source in the water, vector seismograms of receivers in fluid elements.
+    All 4500 steps; the nine displacement and 22 velocity traces REF_SEIS holds (vertical component)."""
+    from specfem3d_b200.configs import waterlayered_halfspace
+    from specfem3d_b200.time_loop import DeviceRun
+
+    gold = np.load(os.path.join(GOLD, "waterlayer_ref_seis.npz"))
+    sim = waterlayered_halfspace(4500, nproc_xi=3, nproc_eta=3)
+    assert abs(sim.time_axis()[0] - gold["time"][0]) < 1e-6
+    run = DeviceRun(sim).run()
+    sd, sv = run.gather_seismograms("d"), run.gather_seismograms("v")
+    run.cleanup()
+    names = [s.name for s in sim.receivers.stations]
+    errs = {}
+    for key in gold.files:
+        if key[:2] not in ("d_", "v_"):
+            continue
+        syn = (sd if key[0] == "d" else sv)[names.index(key[2:]), :, 2]
+        errs[key] = rel_l2(syn, gold[key])
+    print("water-layer example, 4500 steps on the GPU, relative L2 vs REF_SEIS:", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) <= 1e-4, errs
+
+
+def test_attenuation_benchmark_against_REF_SEIS(device_lib):
+    """The reference's viscoelastic benchmark (EXAMPLES/benchmarks/attenuation/viscoelastic): 512,000 elements, 3 SLS,
+    1300 steps -- the attenuation force kernel, memory-variable update and the tau_eps / scale-factor constants."""
+    from specfem3d_b200.configs import attenuation_benchmark
+    from specfem3d_b200.time_loop import DeviceRun
+
+    gold = np.load(os.path.join(GOLD, "attenuation_ref_seis.npz"))
+    ref_norm = dict(zip(gold["maxnorm_step"].tolist(), gold["maxnorm_value"].tolist()))
+    sim = attenuation_benchmark(1300)
+    run = DeviceRun(sim)
+    norms = {}
+    for it in range(1, 1301):
+        if it in ref_norm:
+            norms[it] = run.max_norm_displ()
+        run.step()
+    sd = run.gather_seismograms("d")
+    run.cleanup()
+    for c, ch in enumerate("XYZ"):
+        err = rel_l2(sd[0, :, c], gold[f"1_{ch}"])
+        print(f"attenuation benchmark on the GPU, CE.1.FX{ch}: relative L2 vs REF_SEIS = {err:.3e}")
+        assert err <= 1e-4, (ch, err)
+    for it, v in norms.items():
+        if it >= 200:
+            assert abs(v - ref_norm[it]) / ref_norm[it] < 1e-4, (it, v, ref_norm[it])
+
+
+def test_config2_size_parity_with_oracle(device_lib):
+    """BASELINE config 2 (128 x 128 x 64 = 1,048,576 irregular elements): (i) one compute_forces_viscoelastic_cuda launch
+    over all elements on a smooth wavefield and (ii) three complete time steps with the source, against the CPU oracle on
+    the same mesh (0.5 s of CPU per step)."""
+    from oracle.solver import OracleRun, set_num_threads
+    from specfem3d_b200.configs import halfspace_scaled
+    from specfem3d_b200.time_loop import DeviceRun
+
+    set_num_threads(os.cpu_count() or 1)
+    sim = halfspace_scaled(128, 128, 64, NSTEP=3, stations=True)
+    db = sim.dbs[0]
+    assert db.NSPEC_AB == 1048576
+    x, y, z = (db.xstore / 5000.0, db.ystore / 5000.0, db.zstore / 5000.0)
+    u = np.stack([np.sin(x + 0.3 * y) + 0.1, np.cos(0.7 * y - z), np.sin(0.5 * z + x * y * 0.01)], -1).astype(np.float32)
+    zero = np.zeros_like(u)
+    run = DeviceRun(sim)
+    r = run.ranks[0]
+    L, M, n = r.lib, r.Mesh_pointer, db.NGLOB_AB
+    # (i) one launch of each phase
+    L.transfer_fields_el_to_device(3 * n, u, zero, zero, M)
+    for iphase in (1, 2):
+        L.compute_forces_viscoelastic_cuda(M, iphase, float(sim.deltat), db.nspec_outer_elastic, db.nspec_inner_elastic, 0, 0, 1)
+    acc_gpu = r.fields_el()[2]
+    o = OracleRun(sim)
+    p = o.parts[0]
+    p.displ[:] = u
+    p.accel[:] = 0
+    p.forces_elastic(1)
+    p.forces_elastic(2)
+    scale = np.abs(p.accel).max()
+    err = np.abs(acc_gpu - p.accel).max() / scale
+    print(f"config 2, one force launch over 1,048,576 elements: max |accel_gpu - accel_oracle| / max|accel| = {err:.3e}")
+    assert err <= 2e-5
+    # (ii) three full steps from rest
+    L.transfer_fields_el_to_device(3 * n, zero, zero, zero, M)
+    o2 = OracleRun(sim)
+    for _ in range(3):
+        run.step()
+        o2.step()
+    d_gpu, v_gpu, a_gpu = r.fields_el()
+    run.cleanup()
+    for name, g, c in (("displ", d_gpu, o2.parts[0].displ), ("veloc", v_gpu, o2.parts[0].veloc), ("accel", a_gpu, o2.parts[0].accel)):
+        e = rel_l2(g, c)
+        print(f"config 2, three full steps: {name} relative L2 vs oracle = {e:.3e}")
+        assert e <= 2e-5, (name, e)

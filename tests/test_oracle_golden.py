@@ -124,9 +124,9 @@ def test_attenuation_benchmark_against_REF_SEIS():
     """Pins the oracle's attenuation path (3 standard linear solids, memory-variable update, modulus shift to the reference
     frequency) on the reference's own viscoelastic benchmark: EXAMPLES/benchmarks/attenuation/viscoelastic/REF_SEIS.
 
-    Measured (profiles/r01l_oracle_attenuation_benchmark.md): traces 4.7e-4 ... 5.3e-4 relative L2, max norms 1.4e-5 (step 5)
-    growing to 3.2e-4 (step 1300).  That is ABOVE the 1e-4 the elastic and C-PML pins meet, so this test asserts the measured
-    level (1e-3) and the attenuation pin is recorded as PARTIAL in DESIGN.md section 6 until the tau_eps fit is matched."""
+    Round 1 (scipy Nelder-Mead for tau_eps) measured 4.7e-4 ... 5.3e-4; with the reference's own fminsearch restated
+    (specfem3d_b200/attenuation.py, pinned in tests/test_attenuation_constants.py) the bar is the north-star 1e-4.
+    Result of the full run: profiles/r02_oracle_attenuation_benchmark.md."""
     from oracle.solver import OracleRun, set_num_threads
     from specfem3d_b200.configs import attenuation_benchmark
 
@@ -142,9 +142,11 @@ def test_attenuation_benchmark_against_REF_SEIS():
         run.step()
     ref_norm = dict(zip(gold["maxnorm_step"].tolist(), gold["maxnorm_value"].tolist()))
     for it, v in norms.items():
-        assert abs(v - ref_norm[it]) / ref_norm[it] < 1e-3, (it, v, ref_norm[it])
+        print(f"max norm at step {it}: {v:.7e} vs {ref_norm[it]:.7e} ({abs(v - ref_norm[it]) / ref_norm[it]:.2e})")
+        assert abs(v - ref_norm[it]) / ref_norm[it] < 1e-4, (it, v, ref_norm[it])
     for c, ch in enumerate("XYZ"):
         ref = gold[f"1_{ch}"].astype(np.float64)
         syn = run.seis_d[0, :, c].astype(np.float64)
         err = np.linalg.norm(syn - ref) / np.linalg.norm(ref)
-        assert err <= 1e-3, f"attenuation benchmark CE.1.FX{ch}: relative L2 {err:.3e}"  # target 1e-4, see docstring
+        print(f"attenuation benchmark CE.1.FX{ch}: relative L2 {err:.3e}")
+        assert err <= 1e-4, f"attenuation benchmark CE.1.FX{ch}: relative L2 {err:.3e}"
