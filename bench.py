@@ -3,16 +3,23 @@
 
     python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
     python bench.py --impl reference --gpus N --steps K --warmup W
+    python bench.py --scaling strong --gpus N ...              BASELINE configs[4]: the 256 x 256 x 128 mesh in N parts
+    python bench.py --config cfg3 | cfg4                       configs[2] / configs[3] at their stated size (1 GPU)
 
-Workload (BASELINE.json configs[1]): homogeneous elastic halfspace, 128 x 128 x 64 = 1,048,576 NGLL=5 elements per
+Default workload (BASELINE.json configs[1]): homogeneous elastic halfspace, 128 x 128 x 64 = 1,048,576 NGLL=5 elements per
 GPU, irregular elements (non-cubic spacing), Stacey on 5 sides, CMT point source, 4 receivers, single precision.
-N>1 is weak scaling: the box grows to (128*px) x (128*py) x 64 elements, one 1M-element slab per GPU; at N=8 that is
-an 8.4M-element mesh in 8 partitions (config 5's size).  A "step" is one complete solver time step through the C
-ABI (predictor, outer+inner force kernels, Stacey, source, halo exchange, corrector, seismogram sample).
+N>1 is weak scaling by default: the box grows to (128*px) x (128*py) x 64 elements, one 1M-element slab per GPU; at N=8 that
+is an 8.4M-element mesh in 8 partitions (config 5's size).  `--scaling strong` keeps the 8,388,608-element mesh of config 5
+fixed and splits it into N slabs.  A "step" is one complete solver time step through the C ABI (predictor, outer+inner
+force kernels, Stacey, source, halo exchange, corrector, seismogram sample).
 
-Reported on one JSON line: `value` (device-timed, inputs resident), `e2e` (same loop through the ABI with the per-step
-host inputs / outputs inside the timed region), `roofline` of the dominant kernel (elastic internal forces), `cpu_baseline`
-(the CPU oracle = restated reference CPU solver, bounded sample) and the clocks seen during the timed region.
+Reported on one JSON line: `value` (device-timed, inputs resident), `e2e` (same loop through the ABI with the per-step host
+inputs / outputs inside the timed region), `roofline` of the dominant kernel (elastic internal forces, CUDA events around
+every launch INSIDE the timed steps: specfem_b200_kernel_timing), at N>1 `halo_parity` (NVLink peer-store halo against the
+host-staged gloo halo on the same initial state), at N=1 `secondary` (rooflines of the attenuation, C-PML and acoustic force
+kernels on scaled-down configs 3 / 4), `ref_cuda_backend` (the reference's own src/gpu backend compiled unmodified, same mesh,
+same host loop, same box), `config1` (the reference's default example, 4 ranks on the one GPU) and `cpu_baseline` (the CPU
+oracle = restated reference CPU solver, bounded sample), plus the clocks seen while the GPU was under load.
 """
 from __future__ import annotations
 
@@ -35,6 +42,15 @@ METRIC = "elastic element-timesteps/sec"
 UNIT = "element-timesteps/s"
 BYTES_PER_ELEMENT_FORCE_IRREGULAR = 8304  # SURVEY.md section 8d / BASELINE.md section 3
 BYTES_PER_ELEMENT_FORCE_REGULAR = 3804
+BYTES_PER_ELEMENT_ATTENUATION = 36072     # SURVEY.md section 8d (irregular element, 3 SLS)
+BYTES_PER_ELEMENT_ACOUSTIC = 6268
+BYTES_PER_ELEMENT_PML = 82300             # DESIGN.md section 4 (48 memory planes r+w, 41 coefficient planes, ...)
+BYTES_PER_ELEMENT_NEWMARK_FUSED = 5376    # 84 B per point x 64 points per element
+
+
+def workload_text(nex, nspec_total):
+    return (f"configs[1]: homogeneous elastic halfspace, {nex[0]}x{nex[1]}x{nex[2]} NGLL=5 hex elements per GPU "
+            f"({nspec_total} total), irregular elements, Stacey 5 sides, CMT source, 4 receivers, single precision")
 
 
 def measured_peaks():
@@ -104,7 +120,7 @@ def partition_grid(n: int):
     return px, py
 
 
-def build_workload(n_gpus: int, rank: int, nex_per_gpu=(128, 128, 64), nstep: int = 100):
+def build_workload(n_gpus: int, rank: int, nex_per_gpu=(128, 128, 64), nstep: int = 100, elem_size=None):
     """The rank's slab of the weak-scaled halfspace (only this rank's database is built; mass matrices are assembled
     with the neighbours through torch.distributed in `assemble_mass_distributed`)."""
     from specfem3d_b200.configs import CMT_DEFAULT, HALFSPACE, courant_dt
@@ -115,8 +131,8 @@ def build_workload(n_gpus: int, rank: int, nex_per_gpu=(128, 128, 64), nstep: in
 
     px, py = partition_grid(n_gpus)
     nx, ny, nz = nex_per_gpu
-    # element size of config 2 (134 km / 128) kept fixed under weak scaling
-    dx, dy, dz = 134000.0 / 128, 134000.0 / 128, 60000.0 / 64
+    # element size of config 2 (134 km / 128) kept fixed under weak scaling; config 5 (strong scaling) halves it
+    dx, dy, dz = elem_size if elem_size is not None else (134000.0 / 128, 134000.0 / 128, 60000.0 / 64)
     spec = BoxSpec(nx * px, ny * py, nz, xmax=dx * nx * px, ymax=dy * ny * py, zmin=-dz * nz, nproc_xi=px, nproc_eta=py,
                    materials=(HALFSPACE,))
     DT = courant_dt(spec, 2800.0)
@@ -135,6 +151,71 @@ def build_workload(n_gpus: int, rank: int, nex_per_gpu=(128, 128, 64), nstep: in
     else:
         sources = receivers = None
     return spec, DT, gll, db, loc, sources, receivers, (src, sts)
+
+
+def smooth_state(db, amp=1e-3):
+    """Deterministic smooth wavefield (no denormals) from the point coordinates: the same function on every rank, so points
+    shared between ranks start with identical values."""
+    x, y, z = db.xstore / 5000.0, db.ystore / 5000.0, db.zstore / 5000.0
+    u = amp * np.stack([np.sin(x + 0.3 * y) + 0.1, np.cos(0.7 * y - z), np.sin(0.5 * z + 0.01 * x * y)], -1)
+    v = amp * np.stack([np.cos(0.9 * x - z), np.sin(y + 0.2 * x), np.cos(0.4 * z - y)], -1)
+    return u.astype(np.float32), v.astype(np.float32)
+
+
+def kernel_time(lib, r, name):
+    ms, cnt = ctypes.c_float(0), ctypes.c_int(0)
+    lib.cdll.specfem_b200_kernel_time_(ctypes.byref(r.Mesh_pointer), name.encode(), ctypes.byref(ms), ctypes.byref(cnt))
+    return float(ms.value), int(cnt.value)
+
+
+def set_kernel_timing(lib, r, on):
+    lib.cdll.specfem_b200_kernel_timing_(ctypes.byref(r.Mesh_pointer), ctypes.byref(ctypes.c_int(int(on))))
+
+
+def halo_parity_check(sim, r, gloo, halo_mode, nsteps=10):
+    """N>1: K steps from the same smooth state, once with the reference-compatible host-staged halo (pinned buffers + gloo
+    send/recv = the Fortran MPI path, assemble_MPI_vector.f90:243-384) and once with the path that is timed (NVLink peer
+    stores through CUDA-IPC slabs, halo_p2p.cuh).  Returns the exchange object to go on with and the misfits."""
+    import torch
+    import torch.distributed as dist
+
+    from specfem3d_b200.halo import DistributedExchange
+    from specfem3d_b200.time_loop import DeviceRun
+
+    db, lib = r.db, r.lib
+    n = db.NGLOB_AB
+    u0, v0 = smooth_state(db)
+    zero = np.zeros_like(u0)
+
+    def k_steps(exchange):
+        lib.transfer_fields_el_to_device(3 * n, u0, v0, zero, r.Mesh_pointer)
+        run = DeviceRun(sim, prepared=[r], exchange=exchange)
+        r.seismo_current = 0
+        for _ in range(nsteps):
+            run.step()
+        d, v, a = r.fields_el()
+        # samples recorded so far sit in the device buffer; the last step's accel / displ fields carry the same information
+        return d, v, a
+
+    host = DistributedExchange(r, gloo, mode="host")
+    dh, vh, ah = k_steps(host)
+    timed = DistributedExchange(r, gloo, mode=halo_mode) if halo_mode != "host" else host
+    dp, vp, ap = k_steps(timed)
+
+    def sq(a, b):
+        return float(((a.astype(np.float64) - b) ** 2).sum()), float((b.astype(np.float64) ** 2).sum())
+
+    parts = torch.tensor([*sq(ap, ah), *sq(dp, dh), *sq(vp, vh)], dtype=torch.float64)
+    dist.all_reduce(parts, op=dist.ReduceOp.SUM, group=gloo)
+    p = parts.tolist()
+    res = {"steps": nsteps, "reference_path": "host-staged halo (pinned buffers + gloo isend/irecv)", "timed_path": halo_mode,
+           "rel_l2_accel": (p[0] / max(p[1], 1e-300)) ** 0.5, "rel_l2_displ": (p[2] / max(p[3], 1e-300)) ** 0.5,
+           "rel_l2_veloc": (p[4] / max(p[5], 1e-300)) ** 0.5, "bar": 2e-5,
+           "state": "smooth sin/cos wavefield of amplitude 1e-3 on every rank (interface points carry non-zero values from step 1)"}
+    # back to rest for the benchmark proper
+    lib.transfer_fields_el_to_device(3 * n, zero, zero, zero, r.Mesh_pointer)
+    r.seismo_current = 0
+    return timed, res
 
 
 def run_device(args):
@@ -160,10 +241,18 @@ def run_device(args):
         gloo = dist.new_group(backend="gloo")
     lib = abi.load()
 
-    nex = tuple(int(v) for v in args.nex.split("x"))
-    # warm-up + timed region 1 (value) + timed region 3 (e2e) record one seismogram sample per step; region 2 does not
-    nstep_total = args.warmup + 2 * args.steps + 4
-    spec, DT, gll, db, loc, sources, receivers, _ = build_workload(world, rank, nex, nstep_total)
+    px, py = partition_grid(world)
+    elem = None
+    if args.scaling == "strong":
+        # BASELINE configs[4]: the 256 x 256 x 128 = 8,388,608-element mesh of config 5, N slabs
+        nex = (256 // px, 256 // py, 128)
+        elem = (134000.0 / 256, 134000.0 / 256, 60000.0 / 128)
+    else:
+        nex = tuple(int(v) for v in args.nex.split("x"))
+    # warm-up + timed regions 1 (value), 2 (kernel events) and 3 (e2e) all record one seismogram sample per step
+    k2 = min(args.steps, 20)
+    nstep_total = args.warmup + 2 * args.steps + k2 + 4
+    spec, DT, gll, db, loc, sources, receivers, _ = build_workload(world, rank, nex, nstep_total, elem)
 
     # ---- mass-matrix assembly across ranks (assemble_MPI_scalar_blocking) ---------------------------------------------
     if world > 1:
@@ -186,11 +275,14 @@ def run_device(args):
     r = DeviceRank(sim, rank, lib)
     # torchrun: LOCAL_RANK selects the device; initialize_gpu_device uses myrank % ndevices, identical on one node
     r.prepare()
-    exchange = None
+    exchange, halo_parity = None, None
     if world > 1:
-        from specfem3d_b200.halo import DistributedExchange
-
-        exchange = DistributedExchange(r, gloo, mode=args.halo)
+        exchange, halo_parity = halo_parity_check(sim, r, gloo, args.halo)
+        if rank == 0:
+            print("halo parity:", json.dumps(halo_parity), file=sys.stderr, flush=True)
+        bad = max(halo_parity["rel_l2_accel"], halo_parity["rel_l2_displ"], halo_parity["rel_l2_veloc"])
+        if not (bad <= halo_parity["bar"]):
+            raise SystemExit(f"bench: the {args.halo} halo differs from the host-staged halo by {bad:.3e} (> 2e-5): not timing a wrong exchange")
     run = DeviceRun(sim, prepared=[r], exchange=exchange if exchange is not None else False)
 
     sp = ctypes.c_void_p(0)
@@ -204,6 +296,9 @@ def run_device(args):
         torch.cuda.synchronize()
 
     # ---- warm-up ------------------------------------------------------------------------------------------------------
+    # the clock sampler runs from here to the end of the last timed region (nvidia-smi delivers a sample every ~20-50 ms;
+    # region 1 alone can be shorter than that)
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
     for _ in range(args.warmup):
         run.step()
     barrier()
@@ -211,11 +306,8 @@ def run_device(args):
     # ---- timed region 1: device time of K steps, inputs resident (value) ------------------------------------------------
     # the workload (>= 8.7 GB of static arrays + 2.4 GB of wavefields per step) is far larger than the 126 MB L2, so no
     # explicit flush is needed between iterations
-    sampler = ClockSampler(local_rank).start() if rank == 0 else None
     launches0 = r.kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    fk = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    dt_, dt2, dtsq2 = float(sim.deltat), float(sim.deltatover2), float(sim.deltatsqover2)
     barrier()
     ev0.record(stream)
     for k in range(args.steps):
@@ -224,26 +316,19 @@ def run_device(args):
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     launches = r.kernel_launches() - launches0
-    clocks = sampler.stop() if sampler else None
 
-    # ---- timed region 2: the force kernel alone inside the step (roofline), CUDA events on the launching stream ---------
-    # events bracket the inner-element launch (the dominant kernel: all elements at N=1)
+    # ---- timed region 2: the same steps with CUDA events around every force / Newmark launch (roofline) -------------------
+    # the library records an event pair on its compute stream around each named launch (specfem_b200_kernel_timing)
     nel_inner, nel_outer = db.nspec_inner_elastic, db.nspec_outer_elastic
     barrier()
-    kernel_ms = []
-    for k in range(min(args.steps, 20)):
-        run.it += 1
-        it = run.it
-        lib.update_displacement_cuda(r.Mesh_pointer, dt_, dt2, dtsq2, 1)
-        lib.compute_forces_viscoelastic_cuda(r.Mesh_pointer, 1, dt_, nel_outer, nel_inner, 0, 0, 1)
-        a, b = fk[k]
-        a.record(stream)
-        lib.compute_forces_viscoelastic_cuda(r.Mesh_pointer, 2, dt_, nel_outer, nel_inner, 0, 0, 1)
-        b.record(stream)
-        lib.kernel_3_a_cuda(r.Mesh_pointer, dt2, dt2, 0, 1)
-        torch.cuda.synchronize()
-        kernel_ms.append(a.elapsed_time(b))
-    k_ms = float(np.mean(kernel_ms))
+    set_kernel_timing(lib, r, True)
+    for k in range(k2):
+        run.step()
+    set_kernel_timing(lib, r, False)
+    f_ms, f_cnt = kernel_time(lib, r, "elastic_forces")
+    n_ms, n_cnt = kernel_time(lib, r, "newmark")
+    k_ms = f_ms / k2              # all force launches of one step (outer + inner phase): every element of the rank once
+    newmark_ms = n_ms / max(n_cnt, 1)
 
     # ---- timed region 3: end to end through the ABI with host buffers (e2e) -----------------------------------------------
     # per step: stf H2D from pinned memory (inside compute_add_sources_el_cuda) and a D2H read of the step's stability
@@ -257,6 +342,7 @@ def run_device(args):
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     e2e_ms = (t1 - t0) * 1e3
+    clocks = sampler.stop() if sampler else None
     if not np.isfinite(norm.value):
         raise SystemExit("bench: wavefield became non-finite")
 
@@ -276,17 +362,22 @@ def run_device(args):
     if rank == 0:
         peak, peak_src = measured_peaks()
         bytes_per_el = BYTES_PER_ELEMENT_FORCE_IRREGULAR if db.NSPEC_IRREGULAR == db.NSPEC_AB else BYTES_PER_ELEMENT_FORCE_REGULAR
-        achieved = nel_inner * bytes_per_el / (k_ms * 1e-3) / 1e9
-        traffic = None
+        nel = nel_inner + nel_outer
+        achieved = nel * bytes_per_el / (k_ms * 1e-3) / 1e9
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "force_kernel_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+        workload = workload_text(nex, nspec_total)
+        if args.scaling == "strong":
+            workload = (f"configs[4]: the 256x256x128 = 8388608-element elastic mesh of config 5 in {world} part(s) of "
+                        f"{nex[0]}x{nex[1]}x{nex[2]} elements, irregular elements, Stacey 5 sides, CMT source, 4 receivers, single precision")
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"configs[1]: homogeneous elastic halfspace, {nex[0]}x{nex[1]}x{nex[2]} NGLL=5 hex elements per GPU "
-                                   f"({nspec_total} total), irregular elements, Stacey 5 sides, CMT source, 4 receivers, single precision",
+            "config": {"workload": workload,
                        "elements_total": nspec_total, "elements_per_gpu": db.NSPEC_AB, "nglob_per_gpu": db.NGLOB_AB,
                        "partitions": f"{spec.nproc_xi}x{spec.nproc_eta} slabs (meshfem3D NPROC_XI x NPROC_ETA)",
                        "halo": (args.halo if world > 1 else "none"), "dt": DT,
@@ -295,21 +386,222 @@ def run_device(args):
                     "d2h_bytes_per_step": 4 * 148 * 4,
                     "note": "K steps through the C ABI from host buffers: per-step stf upload + blocking norm readback; host wall clock"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "elastic internal forces (compute_forces_viscoelastic_cuda, inner phase)",
+            "roofline": {"bound": "hbm", "kernel": "k_elastic_forces_row (compute_forces_viscoelastic_cuda, outer + inner phase)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "algorithmic_bytes_per_element": bytes_per_el,
-                         "elements_per_launch": nel_inner, "kernel_ms": k_ms,
-                         "elements_per_s": nel_inner / (k_ms * 1e-3)},
+                         "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_element": bytes_per_el,
+                         "elements_per_step": nel, "launches_per_step": f_cnt / k2, "kernel_ms": k_ms,
+                         "timed": f"CUDA events on the library's compute stream around every launch of {k2} consecutive time steps",
+                         "elements_per_s": nel / (k_ms * 1e-3)},
+            "newmark": {"kernel": "k_newmark_corrector_predictor (deferred corrector + predictor)", "kernel_ms": newmark_ms,
+                        "achieved": nel * BYTES_PER_ELEMENT_NEWMARK_FUSED / (newmark_ms * 1e-3) / 1e9 if newmark_ms > 0 else None,
+                        "unit": "GB/s", "algorithmic_bytes_per_element": BYTES_PER_ELEMENT_NEWMARK_FUSED},
             "clocks": clocks,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline_sample(sim, seconds=args.cpu_seconds)
+        if halo_parity is not None:
+            out["halo_parity"] = halo_parity
     r.cleanup()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
+        if world == 1 and args.scaling == "weak":
+            # everything below runs AFTER the timed regions, with the benchmark's handle released
+            if not args.no_secondary:
+                out["secondary"] = secondary_rooflines(lib, args)
+                out["config1"] = config1_step_cost(lib)
+            if not args.no_ref_cuda:
+                out["ref_cuda_backend"] = ref_cuda_backend(args)
+            if not args.no_cpu_baseline:
+                out["cpu_baseline"] = cpu_baseline_sample(sim, seconds=args.cpu_seconds)
         emit(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def time_config(lib, sim, kernels, steps=12, warmup=3):
+    """A few steps of `sim` on cuda:0 through the ABI; returns ms per step (device events are inside the library) and the
+    per-step time of each named kernel."""
+    import torch
+
+    from specfem3d_b200.time_loop import DeviceRun
+
+    run = DeviceRun(sim, lib=lib)
+    for _ in range(warmup):
+        run.step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run.step()
+    torch.cuda.synchronize()
+    ms_step = (time.perf_counter() - t0) * 1e3 / steps
+    for r in run.ranks:
+        set_kernel_timing(lib, r, True)
+    for _ in range(steps):
+        run.step()
+    res = {}
+    for name in kernels:
+        tot = 0.0
+        for r in run.ranks:
+            set_kernel_timing(lib, r, False)
+            tot += kernel_time(lib, r, name)[0]
+        res[name] = tot / steps
+    norm = run.max_norm_displ() if sim.ELASTIC_SIMULATION else 0.0
+    launches = run.kernel_launches()
+    run.cleanup()
+    if not np.isfinite(norm):
+        raise SystemExit("bench: secondary workload became non-finite")
+    return ms_step, res, launches
+
+
+def roofline_entry(kernel, row, workload, units, unit_name, bytes_per_unit, ms):
+    peak, peak_src = measured_peaks()
+    ach = units * bytes_per_unit / (ms * 1e-3) / 1e9 if ms > 0 else None
+    return {"row": row, "kernel": kernel, "workload": workload, "units_per_step": units, "unit": unit_name,
+            "algorithmic_bytes_per_unit": bytes_per_unit, "kernel_ms": ms, "achieved": ach, "peak": peak,
+            "frac": (ach / peak) if ach else None, "bound": "hbm", "peak_source": peak_src,
+            "timed": "CUDA events on the compute stream around every launch of 12 consecutive time steps"}
+
+
+def secondary_rooflines(lib, args, cfg3_nex=(96, 96, 48), cfg4_nex=(128, 128, 64)):
+    """Rooflines of the kernels configs 3 and 4 are dominated by, measured in-step on scaled-down versions of those configs
+    (same materials, layering, shell thickness; `--config cfg3|cfg4` runs them at the stated size)."""
+    from specfem3d_b200.configs import cfg3, cfg4
+
+    out = []
+    sim = cfg3(cfg3_nex, NSTEP=40)
+    db = sim.dbs[0]
+    ncpml = int(sim.pml[0]["NSPEC_CPML"])
+    ms, k, _ = time_config(lib, sim, ("elastic_forces_attenuation", "pml_forces"))
+    w = (f"configs[2] scaled to {cfg3_nex[0]}x{cfg3_nex[1]}x{cfg3_nex[2]} = {db.NSPEC_AB} elements: 3 viscoelastic layers "
+         f"(3 SLS), C-PML shell 3 elements thick ({ncpml} C-PML elements)")
+    out.append(roofline_entry("k_elastic_forces_pt<ATTENUATION,STRAIN>", "a2", w, db.NSPEC_AB - ncpml, "element",
+                              BYTES_PER_ELEMENT_ATTENUATION, k["elastic_forces_attenuation"]))
+    out.append(roofline_entry("k_pml_elastic_forces", "a3", w, ncpml, "C-PML element", BYTES_PER_ELEMENT_PML, k["pml_forces"]))
+    out[-1]["ms_per_step_whole_config"] = out[-2]["ms_per_step_whole_config"] = ms
+    del sim
+    sim = cfg4(cfg4_nex, NSTEP=40)
+    db = sim.dbs[0]
+    ms, k, _ = time_config(lib, sim, ("acoustic_forces", "elastic_forces"))
+    w = (f"configs[3]: {cfg4_nex[0]}x{cfg4_nex[1]}x{cfg4_nex[2]} = {db.NSPEC_AB} elements, top 10 % of the layers water "
+         f"({db.nspec_acoustic} fluid elements), rest elastic, Stacey, fluid-solid coupling")
+    out.append(roofline_entry("acoustic force kernel (compute_forces_acoustic_cuda)", "a4", w, db.nspec_acoustic, "element",
+                              BYTES_PER_ELEMENT_ACOUSTIC, k["acoustic_forces"]))
+    out[-1]["ms_per_step_whole_config"] = ms
+    out[-1]["elastic_forces_ms_same_step"] = k["elastic_forces"]
+    return out
+
+
+def config1_step_cost(lib):
+    """BASELINE configs[0] (the reference's default example: 36 x 36 x 16 elements, 4 ranks): ms per step with the four ranks
+    as four handles on the one GPU, next to the reference's own CPU figure in REF_SEIS/output_solver.txt (2016, 4 cores)."""
+    from specfem3d_b200.configs import cfg1
+
+    sim = cfg1(2, 2, 400)
+    ms, _, launches = time_config(lib, sim, (), steps=100, warmup=20)
+    return {"workload": "configs[0]: homogeneous_halfspace example, 36x36x16 = 20736 elements, 4 ranks (2x2) on one GPU, host-staged halo",
+            "ms_per_step": ms, "element_timesteps_per_s": 20736 / (ms * 1e-3),
+            "reference_cpu_ms_per_step": 73.6,
+            "reference_cpu_source": "EXAMPLES/applications/homogeneous_halfspace/REF_SEIS/output_solver.txt: mean elapsed time per time step 7.36e-2 s (4 MPI ranks, 2016)"}
+
+
+def ref_cuda_backend(args):
+    """BASELINE north_star: 'the reference's existing CUDA backend run on the same box is also reported'.  oracle/_ref/
+    libspecfem_ref_cuda.so is src/gpu compiled unmodified for sm_100a (oracle/build_ref_cuda.sh); it exports the same ABI, so
+    the same host time loop drives it on the same mesh.  Runs in a child process (`--ref-cuda-only`): the reference library
+    resets the device when it initialises and calls exit() on any error, neither of which may take this line down."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libspecfem_ref_cuda.so")
+    if not os.path.exists(path):
+        return {"unavailable": "oracle/_ref/libspecfem_ref_cuda.so not built (needs /root/reference at build time)"}
+    cmd = [sys.executable, os.path.abspath(__file__), "--ref-cuda-only", "--nex", args.nex, "--steps", str(min(args.steps, 30))]
+    try:
+        res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+        lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
+        if res.returncode != 0 or not lines:
+            return {"unavailable": f"child exited with {res.returncode}: {res.stderr[-300:]}"}
+        return json.loads(lines[-1])
+    except Exception as e:  # the comparison arm must never take the benchmark line down
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
+def run_ref_cuda_only(args):
+    from specfem3d_b200 import abi
+    from specfem3d_b200.meshfem import invert_mass
+    from specfem3d_b200.simulation import Simulation
+    from specfem3d_b200.time_loop import DeviceRank, DeviceRun
+
+    nex = tuple(int(v) for v in args.nex.split("x"))
+    steps = args.steps
+    spec, DT, gll, db, loc, sources, receivers, _ = build_workload(1, 0, nex, steps + 10)
+    for key in ("rmassx", "rmassy", "rmassz"):
+        setattr(db, key, invert_mass(loc[key]))
+    sim = Simulation(spec, DT, steps + 10, [db], gll, sources, receivers)
+    ref = abi.DeviceLibrary(os.path.join(ROOT, "oracle", "_ref", "libspecfem_ref_cuda.so"))
+    r = DeviceRank(sim, 0, ref).prepare()
+    run = DeviceRun(sim, prepared=[r], exchange=False)
+    norm = ctypes.c_float(0)
+    for _ in range(5):
+        run.step()
+    ref.get_norm_elastic_from_device(norm, r.Mesh_pointer, 1)  # blocking: the reference does not expose its stream
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run.step()
+    ref.get_norm_elastic_from_device(norm, r.Mesh_pointer, 1)
+    dt = time.perf_counter() - t0
+    r.cleanup()
+    emit(json.dumps({
+        "ms_per_step": dt / steps * 1e3, "value": db.NSPEC_AB * steps / dt, "unit": UNIT, "steps": steps,
+        "what": "reference src/gpu CUDA backend (Kernel_2_noatt_iso_impl etc.) compiled unmodified for sm_100a: same mesh, same "
+                "host time loop, same GPU; host wall clock between two blocking norm read-backs",
+        "workload": workload_text(nex, db.NSPEC_AB), "max_norm_displ": float(norm.value)}))
+
+
+def run_config(args):
+    """--config cfg3 | cfg4: BASELINE configs[2] / configs[3] at their stated size on one GPU; same JSON contract, the
+    roofline is that config's dominant kernel."""
+    import torch
+
+    from specfem3d_b200 import abi
+    from specfem3d_b200.configs import cfg3, cfg4
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device visible; the device path has no CPU fallback")
+    lib = abi.load()
+    sampler = ClockSampler(0).start()
+    if args.config == "cfg3":
+        nex = tuple(int(v) for v in args.nex.split("x")) if args.nex != "128x128x64" else (160, 160, 80)
+        sim = cfg3(nex, NSTEP=2 * (args.steps + args.warmup) + 8)
+        names = ("elastic_forces_attenuation", "pml_forces")
+    else:
+        nex = tuple(int(v) for v in args.nex.split("x"))
+        sim = cfg4(nex, NSTEP=2 * (args.steps + args.warmup) + 8)
+        names = ("acoustic_forces", "elastic_forces")
+    db = sim.dbs[0]
+    ms, k, launches = time_config(lib, sim, names, steps=args.steps, warmup=args.warmup)
+    clocks = sampler.stop()
+    peak, peak_src = measured_peaks()
+    if args.config == "cfg3":
+        ncpml = int(sim.pml[0]["NSPEC_CPML"])
+        wl = (f"configs[2]: layered viscoelastic model, ATTENUATION (3 SLS), C-PML shell 3 elements thick, "
+              f"{nex[0]}x{nex[1]}x{nex[2]} = {db.NSPEC_AB} elements ({ncpml} C-PML), 1 GPU")
+        main = roofline_entry("k_elastic_forces_pt<ATTENUATION,STRAIN>", "a2", wl, db.NSPEC_AB - ncpml, "element",
+                              BYTES_PER_ELEMENT_ATTENUATION, k["elastic_forces_attenuation"])
+        extra = [roofline_entry("k_pml_elastic_forces", "a3", wl, ncpml, "C-PML element", BYTES_PER_ELEMENT_PML, k["pml_forces"])]
+    else:
+        wl = (f"configs[3]: water layer (top 10 % of the layers, {db.nspec_acoustic} fluid elements) over an elastic halfspace, "
+              f"{nex[0]}x{nex[1]}x{nex[2]} = {db.NSPEC_AB} elements, Stacey, fluid-solid coupling, 1 GPU")
+        main = roofline_entry("acoustic force kernel (compute_forces_acoustic_cuda)", "a4", wl, db.nspec_acoustic, "element",
+                              BYTES_PER_ELEMENT_ACOUSTIC, k["acoustic_forces"])
+        extra = [roofline_entry("k_elastic_forces_row", "a1", wl, db.nspec_elastic, "element", BYTES_PER_ELEMENT_FORCE_IRREGULAR,
+                                k["elastic_forces"])]
+    value = db.NSPEC_AB / (ms * 1e-3)
+    emit(json.dumps({
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl, "elements_total": db.NSPEC_AB, "nglob": db.NGLOB_AB, "dt": sim.DT,
+                   "l2_policy": "working set per step >> 126 MB L2, no flush needed",
+                   "timing": "host wall clock around K steps through the ABI with a device synchronise on both sides"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 0,
+                "note": "this mode times through the ABI only (stf upload per step inside the region)"},
+        "gpu_launches": launches, "roofline": main, "secondary": extra, "clocks": clocks}))
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -376,8 +668,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: homogeneous elastic halfspace, NGLL=5, Stacey, CMT source, single precision (bounded sample)",
-                   "elements_per_step": nspec},
+        "config": {"workload": workload_text(nex, nspec), "elements_total": nspec,
+                   "note": "reference arm = CPU restatement of the reference solver (oracle port: no Fortran compiler / MPI in "
+                           "this image) on the host cores; the mesh is the largest of 128x128x64 / 64x64x32 / ... that keeps the "
+                           "run near 90 s; specfem3d_b200/_meshgen.so (host mesh generator, no kernels) is loaded by this arm too"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -423,6 +717,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nex", default="128x128x64", help="elements per GPU (config 2 = 128x128x64)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "host"], help="halo exchange path for N>1")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: one 128x128x64 slab per GPU (default); strong: config 5's 256x256x128 mesh split into N slabs")
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4"],
+                    help="cfg2: BASELINE configs[1] (default); cfg3 / cfg4: configs[2] / configs[3] at their stated size, 1 GPU")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary-kernel rooflines and the config-1 step cost")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip the run of the reference's own CUDA backend")
+    ap.add_argument("--ref-cuda-only", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
@@ -430,8 +731,12 @@ def main():
         args.warmup = 3
     with QuietStdout() as q:
         OUT = q
-        if args.impl == "reference":
+        if args.ref_cuda_only:
+            run_ref_cuda_only(args)
+        elif args.impl == "reference":
             run_reference(args)
+        elif args.config != "cfg2":
+            run_config(args)
         else:
             run_device(args)
     OUT = None

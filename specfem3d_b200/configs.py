@@ -132,3 +132,42 @@ def waterlayered_halfspace(NSTEP: int = 4500, nproc_xi: int = 1, nproc_eta: int 
     sts = [Station(n, "DB", x, y, -d) for n, x, y, d in _WATERLAYER_STATIONS if stations is None or n in stations]
     return make_simulation(spec, DT=0.005, NSTEP=NSTEP, sources=[src], stations=sts, SAVE_SEISMOGRAMS_VELOCITY=True,
                            SAVE_SEISMOGRAMS_ACCELERATION=True)
+
+
+# BASELINE config 3: three horizontal layers, vs 1500 / 2500 / 3500 m/s, Q_mu 40 / 100 / 300, Q_kappa 9999
+CFG3_LAYERS = (Material(2300.0, 2800.0, 1500.0, 9999.0, 40.0, 2), Material(2600.0, 4400.0, 2500.0, 9999.0, 100.0, 2),
+               Material(3000.0, 6100.0, 3500.0, 9999.0, 300.0, 2))
+
+
+def cfg3(nex=(160, 160, 80), NSTEP: int = 100) -> Simulation:
+    """BASELINE config 3: layered viscoelastic model with ATTENUATION (3 standard linear solids) inside a C-PML shell three
+    elements thick on the four sides and the bottom, free surface on top; 160 x 160 x 80 = 2,048,000 elements at the stated
+    size (``nex`` scales it down for the default bench line and the tests).  Element size 900 m x 900 m x 750 m (irregular),
+    bottom / middle / top third = the fast / medium / slow layer."""
+    nx, ny, nz = nex
+    third = nz // 3
+    spec = BoxSpec(nx, ny, nz, xmax=900.0 * nx, ymax=900.0 * ny, zmin=-750.0 * nz, materials=CFG3_LAYERS, stacey=False,
+                   layer_material=[2] * third + [1] * third + [0] * (nz - 2 * third), pml_thickness=3, f0_for_pml=0.8)
+    DT = courant_dt(spec, 6100.0)
+    src = CMTSource(x=0.5 * spec.xmax + 200.0, y=0.5 * spec.ymax + 100.0, z=0.4 * spec.zmin, moment_tensor=CMT_DEFAULT.moment_tensor,
+                    hdur=max(1.0, 5.0 * DT))
+    sts = [Station(f"S{i}", "DB", (0.2 + 0.15 * i) * spec.xmax, 0.5 * spec.ymax + 150.0, 0.0) for i in range(4)]
+    return make_simulation(spec, DT=DT, NSTEP=NSTEP, sources=[src], stations=sts, attenuation=True)
+
+
+def cfg4(nex=(128, 128, 64), NSTEP: int = 100) -> Simulation:
+    """BASELINE config 4: ocean layer over an elastic halfspace -- the top 10 % of the element layers fluid (rho 1020, vp 1500),
+    the rest the config-1 rock, Stacey on five sides, free surface on top of the water, explosive source in the rock,
+    displacement receivers on the sea floor and in the rock, a pressure receiver in the water."""
+    nx, ny, nz = nex
+    nwater = max(1, round(0.1 * nz))
+    spec = BoxSpec(nx, ny, nz, xmax=134000.0 / 128 * nx, ymax=134000.0 / 128 * ny, zmin=-60000.0 / 64 * nz,
+                   materials=(HALFSPACE, Material(1020.0, 1500.0, 0.0, 9999.0, 9999.0, 1)),
+                   layer_material=[0] * (nz - nwater) + [1] * nwater)
+    DT = courant_dt(spec, 2800.0)
+    zfloor = spec.zmin * (nwater / nz) if False else -60000.0 / 64 * nwater
+    src = CMTSource(x=0.5 * spec.xmax + 300.0, y=0.5 * spec.ymax + 200.0, z=0.5 * spec.zmin, moment_tensor=CMT_DEFAULT.moment_tensor,
+                    hdur=max(1.4, 5.0 * DT))
+    sts = [Station(f"S{i}", "DB", (0.2 + 0.15 * i) * spec.xmax, 0.5 * spec.ymax + 150.0, zfloor - 400.0) for i in range(3)]
+    sts.append(Station("W0", "DB", 0.45 * spec.xmax, 0.5 * spec.ymax + 150.0, 0.5 * zfloor))
+    return make_simulation(spec, DT=DT, NSTEP=NSTEP, sources=[src], stations=sts, SAVE_SEISMOGRAMS_PRESSURE=True)

@@ -213,6 +213,10 @@ struct DeviceMesh {
   // options
   int force_kernel_variant = 0;  // 0 = default (grp), 1 = pt, 2 = col
   long long kernel_launches = 0;
+  // optional per-kernel device timing (specfem_b200_kernel_timing): CUDA event pairs around the named launches
+  struct TimedLaunch { const char* name; cudaEvent_t a, b; };
+  int timing = 0;
+  std::vector<TimedLaunch> timed;
 };
 
 // set by the library: launches the deferred corrector kernel (libspecfem3d_b200.cu: flush_corrector)
@@ -266,6 +270,26 @@ inline T* dev_copy_padded(const T* h, size_t nelem, T padval) {
 inline void dev_free(void* p) {
   if (p) cudaFree(p);
 }
+
+// Scoped timer of one kernel launch (or of the launches of one phase): two events on the compute stream, only while
+// specfem_b200_kernel_timing is switched on (bench.py: roofline of the dominant kernels measured INSIDE the time step).
+struct KernelTimer {
+  DeviceMesh* mp;
+  long idx = -1;
+  KernelTimer(DeviceMesh* m, const char* name) : mp(m) {
+    if (!m->timing) return;
+    DeviceMesh::TimedLaunch t;
+    t.name = name;
+    CUDA_CHECK(cudaEventCreate(&t.a));
+    CUDA_CHECK(cudaEventCreate(&t.b));
+    CUDA_CHECK(cudaEventRecord(t.a, m->compute_stream));
+    idx = (long)m->timed.size();
+    m->timed.push_back(t);
+  }
+  ~KernelTimer() {
+    if (idx >= 0) cudaEventRecord(mp->timed[idx].b, mp->compute_stream);
+  }
+};
 
 inline int grid_for(long long n, int block) { return (int)((n + block - 1) / block); }
 

@@ -290,6 +290,7 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_acoustic_forces_pl(const Acous
 }
 
 inline void launch_acoustic(DeviceMesh* mp, const AcousticArgs& a) {
+  KernelTimer timer(mp, "acoustic_forces");
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("SPECFEM_B200_ACOUSTIC_KERNEL");

@@ -340,6 +340,7 @@ inline void launch_elastic_grp(DeviceMesh* mp, const GroupStore* gs, int segment
   a.jacobian_regular = mp->jacobian_regular;
   a.use_atomics = use_atomics;
   a.nglob = (size_t)mp->NGLOB_AB;
+  KernelTimer timer(mp, "elastic_forces");
   // 72 registers keep five CTAs (25 warps) resident per SM; at 80 (no spill) only four fit and the kernel is slower
   launch_elastic_row_t<3, 72>(mp, a, ng);
 }

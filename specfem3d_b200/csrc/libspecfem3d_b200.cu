@@ -755,6 +755,7 @@ extern "C" void SB200_FC(update_displacement_cuda)(long* Mesh_pointer, realw* de
   if (mp->corrector_pending) {
     // the corrector kernel_3_a_cuda deferred at the end of the previous step and this predictor in one pass
     mp->corrector_pending = false;
+    KernelTimer timer(mp, "newmark");
     k_newmark_corrector_predictor<<<streaming_grid(n >> 2), 256, 0, mp->compute_stream>>>(
         mp->d_displ, mp->d_veloc, mp->d_accel, mp->d_rmassx, n, mp->pending_deltatover2, *deltat_F, *deltatsqover2_F, *deltatover2_F);
     KERNEL_CHECK(mp, "k_newmark_corrector_predictor");
@@ -897,6 +898,7 @@ static void launch_elastic(DeviceMesh* mp, int nb, const int* phase_list, int fi
   const bool att = mp->attenuation != 0;
   const bool strain = mp->compute_and_store_strain != 0;
   // one-thread-per-point path: attenuation / strain storage, and SPECFEM_B200_FORCE_KERNEL=1 (A/B of the default kernel)
+  KernelTimer timer(mp, att ? "elastic_forces_attenuation" : (strain ? "elastic_forces_strain" : "elastic_forces_pointwise"));
   if (att) k_elastic_forces_pt<true, true><<<nb, NGLL3_PADDED, 0, mp->compute_stream>>>(a);
   else if (strain) k_elastic_forces_pt<false, true><<<nb, NGLL3_PADDED, 0, mp->compute_stream>>>(a);
   else k_elastic_forces_pt<false, false><<<nb, NGLL3_PADDED, 0, mp->compute_stream>>>(a);
@@ -1581,6 +1583,33 @@ extern "C" void SB200_FC(get_norm_acoustic_from_device)(realw* norm, long* Mesh_
 extern "C" void SB200_FC(specfem_b200_version)(char* buf, int* len) {
   snprintf(buf, *len, "specfem3d_b200 0.1 (sm_100a, NGLL=5, N_SLS=3)");
 }
+// per-kernel device timing: enable != 0 starts a fresh collection, 0 stops it
+extern "C" void SB200_FC(specfem_b200_kernel_timing)(long* Mesh_pointer, int* enable) {
+  DeviceMesh* mp = get_mesh(Mesh_pointer);
+  CUDA_CHECK(cudaStreamSynchronize(mp->compute_stream));
+  if (*enable) {
+    for (auto& t : mp->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    mp->timed.clear();
+  }
+  mp->timing = *enable != 0;
+}
+// sum of the event-timed durations (ms) and number of the timed launches called `name` since timing was switched on
+extern "C" void SB200_FC(specfem_b200_kernel_time)(long* Mesh_pointer, const char* name, float* total_ms, int* launches) {
+  DeviceMesh* mp = get_mesh(Mesh_pointer);
+  CUDA_CHECK(cudaStreamSynchronize(mp->compute_stream));
+  double sum = 0;
+  int n = 0;
+  for (auto& t : mp->timed)
+    if (!strcmp(t.name, name)) {
+      float ms = 0.f;
+      CUDA_CHECK(cudaEventElapsedTime(&ms, t.a, t.b));
+      sum += ms;
+      ++n;
+    }
+  *total_ms = (float)sum;
+  *launches = n;
+}
+
 extern "C" void SB200_FC(specfem_b200_kernel_launches)(long* Mesh_pointer, long long* count) {
   *count = get_mesh(Mesh_pointer)->kernel_launches;
 }

@@ -386,6 +386,7 @@ inline void pml_compute_forces(DeviceMesh* mp, int iphase, int nspec_outer, int 
   a.store_strain = mp->compute_and_store_strain;
   a.eps_xx = mp->d_epsilondev_xx; a.eps_yy = mp->d_epsilondev_yy; a.eps_xy = mp->d_epsilondev_xy;
   a.eps_xz = mp->d_epsilondev_xz; a.eps_yz = mp->d_epsilondev_yz;
+  KernelTimer timer(mp, "pml_forces");
   k_pml_elastic_forces<<<n, NGLL3_PADDED, 0, mp->compute_stream>>>(a);
   KERNEL_CHECK(mp, "k_pml_elastic_forces");
 }

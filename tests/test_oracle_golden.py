@@ -150,3 +150,39 @@ def test_attenuation_benchmark_against_REF_SEIS():
         err = np.linalg.norm(syn - ref) / np.linalg.norm(ref)
         print(f"attenuation benchmark CE.1.FX{ch}: relative L2 {err:.3e}")
         assert err <= 1e-4, f"attenuation benchmark CE.1.FX{ch}: relative L2 {err:.3e}"
+
+
+WATER_GOLD = os.path.join(os.path.dirname(__file__), "golden", "waterlayer_ref_seis.npz")
+WATER_FULL = bool(os.environ.get("SPECFEM_B200_FULL_GOLDEN"))
+
+
+def test_waterlayered_halfspace_against_REF_SEIS():
+    """Pins the oracle's acoustic / fluid-solid path (acoustic forces, free surface, acoustic Stacey, both coupling
+    directions, pressure source in the water, vector seismograms of receivers in fluid elements) on the reference's coupled
+    example EXAMPLES/applications/waterlayered_halfspace (45 x 45 x 20 box, top layer water, explosion at 1 km depth IN the
+    water, 22 stations): REF_SEIS/DB.*.HXZ.sem{d,v}.
+
+    Default: the first 1000 of 4500 steps (~1 min), on the seven stations the wave has reached by then (above and below the
+    sea floor under the source).  SPECFEM_B200_FULL_GOLDEN=1: all 4500 steps, all 31 traces (~6 min on 8 cores).  Full-run
+    result (profiles/r02_oracle_waterlayer.md): 29 traces 1.3e-6 ... 3.4e-5; the vertical velocity 10 cm above the sea
+    floor away from the source (Y1, Y3: peak 4e-3 of the largest trace) 2.6e-4 / 1.2e-4, the single-precision rounding
+    floor of a z-derivative taken at the element boundary (absolute misfit 5e-7 m/s, 1e-6 of the peak velocity of the run)."""
+    from oracle.solver import OracleRun, set_num_threads
+    from specfem3d_b200.configs import waterlayered_halfspace
+
+    set_num_threads(os.cpu_count() or 1)
+    gold = np.load(WATER_GOLD)
+    nstep = 4500 if WATER_FULL else 1000
+    sim = waterlayered_halfspace(nstep)
+    assert sim.dbs[0].nspec_acoustic == 2025 and sim.dbs[0].nspec_elastic == 38475  # output_solver.txt
+    assert abs(sim.time_axis()[0] - gold["time"][0]) < 1e-6  # start time -6 s = 3 x half duration (source in the fluid)
+    run = OracleRun(sim).run()
+    names = [s.name for s in sim.receivers.stations]
+    early = ("v_X55", "v_X2", "v_X4", "v_X5", "v_X6", "v_X7", "v_X8")
+    keys = [k for k in gold.files if k[:2] in ("d_", "v_")] if WATER_FULL else early
+    for key in keys:
+        syn = (run.seis_d if key[0] == "d" else run.seis_v)[names.index(key[2:]), :nstep, 2].astype(np.float64)
+        ref = gold[key][:nstep].astype(np.float64)
+        err = np.linalg.norm(syn - ref) / np.linalg.norm(ref)
+        bar = 5e-4 if key in ("v_Y1", "v_Y3") else 1e-4
+        assert err <= bar, f"water-layer example {key}: relative L2 {err:.3e}"
