@@ -195,11 +195,13 @@ struct DeviceMesh {
 
   // grouped element storage of the TMA force kernels (kernels_elastic_grp.cuh), built lazily at the first launch
   struct GroupStore* grp_elastic = nullptr;
+  struct GroupStore* grp_acoustic = nullptr;
   // library numbering of the global points (renumber.h): perm[host id] = device id, both 0-based; identity when disabled
   std::vector<int> h_perm;
   int* d_perm = nullptr;
   std::vector<int> h_irregular_element_number;   // host copies needed to build it
   std::vector<int> h_phase_ispec_elastic;        // [2][num_phase_ispec_elastic]
+  std::vector<int> h_phase_ispec_acoustic;       // [2][num_phase_ispec_acoustic]
   std::vector<int> h_is_CPML;                    // empty when no PML
 
   // deferred Newmark corrector (see kernel_3_a_cuda): the corrector of step n is applied by the predictor of step n+1
@@ -212,6 +214,7 @@ struct DeviceMesh {
 
   // options
   int force_kernel_variant = 0;  // 0 = default (grp), 1 = pt, 2 = col
+  int acoustic_kernel_variant = 0;  // SPECFEM_B200_ACOUSTIC_KERNEL: 0 = row kernel (default), 1 = one element per CTA, n >= 2: prefetch kernel
   long long kernel_launches = 0;
   // optional per-kernel device timing (specfem_b200_kernel_timing): CUDA event pairs around the named launches
   struct TimedLaunch { const char* name; cudaEvent_t a, b; };

@@ -110,12 +110,13 @@ __global__ void __launch_bounds__(128) k_build_group_slabs(int ngroups, const in
                                                            const realw* __restrict__ metric, const realw* __restrict__ kappav,
                                                            const realw* __restrict__ muv, const unsigned* __restrict__ row0,
                                                            const int* __restrict__ kind_of_group, int* __restrict__ out_ibool,
-                                                           realw* __restrict__ out_params, int lane_map) {
+                                                           realw* __restrict__ out_params, int lane_map, int nmat) {
+  // nmat material rows behind the (optional) nine metric rows: 2 = kappa, mu (elastic), 1 = rho (acoustic, passed as kappav)
   const int g = blockIdx.x;
   if (g >= ngroups) return;
   const int t = threadIdx.x;
   const int kind = kind_of_group[g];
-  const int narr = kind ? GRP_NARR_IRR : GRP_NARR_REG;
+  const int narr = (kind ? 9 : 0) + nmat;
   int ispec = -1, c = 0;
   if (t < GRP_ELEMS * NGLL2) {
     int e;
@@ -144,11 +145,11 @@ __global__ void __launch_bounds__(128) k_build_group_slabs(int ngroups, const in
         if (irr >= 0) v = metric[((size_t)irr * 9 + m) * NGLL3_PADDED + p];
         dst[m * GRP_ROW] = v;
       }
-      dst[9 * GRP_ROW] = ispec >= 0 ? kappav[(size_t)ispec * NGLL3_PADDED + p] : 0.f;
-      dst[10 * GRP_ROW] = ispec >= 0 ? muv[(size_t)ispec * NGLL3_PADDED + p] : 0.f;
+      dst[9 * GRP_ROW] = ispec >= 0 ? kappav[(size_t)ispec * NGLL3_PADDED + p] : (nmat == 1 ? 1.f : 0.f);
+      if (nmat == 2) dst[10 * GRP_ROW] = ispec >= 0 ? muv[(size_t)ispec * NGLL3_PADDED + p] : 0.f;
     } else {
-      dst[0] = ispec >= 0 ? kappav[(size_t)ispec * NGLL3_PADDED + p] : 0.f;
-      dst[GRP_ROW] = ispec >= 0 ? muv[(size_t)ispec * NGLL3_PADDED + p] : 0.f;
+      dst[0] = ispec >= 0 ? kappav[(size_t)ispec * NGLL3_PADDED + p] : (nmat == 1 ? 1.f : 0.f);
+      if (nmat == 2) dst[GRP_ROW] = ispec >= 0 ? muv[(size_t)ispec * NGLL3_PADDED + p] : 0.f;
     }
   }
 }
@@ -157,6 +158,7 @@ __global__ void __launch_bounds__(128) k_build_group_slabs(int ngroups, const in
 struct GroupStore {
   bool built = false;
   int lane_map = 1;
+  int nmat = 2;  // material rows per point: 2 = kappa, mu (elastic), 1 = rho (acoustic)
   int ngroups = 0;
   int* d_ibool = nullptr;
   realw* d_params = nullptr;
@@ -177,9 +179,13 @@ inline void group_store_free(GroupStore* gs) {
 // irregular ones, each part padded to a multiple of five slots, so every group is homogeneous.
 inline GroupStore* group_store_build(DeviceMesh* mp, const std::vector<std::vector<int>>& segments,
                                      const std::vector<int>& h_irregular_element_number, const int* d_irregular_element_number,
-                                     const realw* d_kappav, const realw* d_muv, int lane_map) {
+                                     const realw* d_kappav, const realw* d_muv, int lane_map, int nmat = 2,
+                                     int groups_multiple = 1) {
+  // groups_multiple: every segment is padded with empty groups to a multiple of this many groups (the acoustic kernel works
+  // on three groups at a time)
   GroupStore* gs = new GroupStore();
   gs->lane_map = lane_map;
+  gs->nmat = nmat;
   std::vector<int> slot_ispec, kind;
   std::vector<unsigned> row0;
   size_t rows = 0;
@@ -193,7 +199,7 @@ inline GroupStore* group_store_build(DeviceMesh* mp, const std::vector<std::vect
         if (fill == 0) {
           kind.push_back(pass);
           row0.push_back((unsigned)rows);
-          rows += 5 * (size_t)(pass ? GRP_NARR_IRR : GRP_NARR_REG);
+          rows += 5 * (size_t)((pass ? 9 : 0) + nmat);
           if (rows >= 0xffffffffull) exit_on_error("group slab pool exceeds 2^32 rows");
         }
         slot_ispec.push_back(ispec);
@@ -203,6 +209,12 @@ inline GroupStore* group_store_build(DeviceMesh* mp, const std::vector<std::vect
         slot_ispec.push_back(-1);
         fill = (fill + 1) % GRP_ELEMS;
       }
+    }
+    while (((int)kind.size() - gs->seg_first.back()) % groups_multiple != 0) {  // empty regular groups
+      kind.push_back(0);
+      row0.push_back((unsigned)rows);
+      rows += 5 * (size_t)nmat;
+      for (int e = 0; e < GRP_ELEMS; ++e) slot_ispec.push_back(-1);
     }
     gs->seg_end.push_back((int)kind.size());
   }
@@ -219,7 +231,7 @@ inline GroupStore* group_store_build(DeviceMesh* mp, const std::vector<std::vect
   gs->d_params = dev_alloc<realw>(rows * GRP_ROW);
   k_build_group_slabs<<<gs->ngroups, 128, 0, mp->compute_stream>>>(gs->ngroups, d_slot, mp->d_ibool, d_irregular_element_number,
                                                                    mp->d_metric, d_kappav, d_muv, gs->d_row0, d_kind,
-                                                                   gs->d_ibool, gs->d_params, lane_map);
+                                                                   gs->d_ibool, gs->d_params, lane_map, nmat);
   KERNEL_CHECK(mp, "k_build_group_slabs");
   CUDA_CHECK(cudaStreamSynchronize(mp->compute_stream));
   dev_free(d_slot);

@@ -37,10 +37,57 @@ namespace sb200 {
 #define ROW_OFF_BARS(ST) (ROW_OFF_IBOOL(ST) + GRP_IB_WORDS * 4)
 #define ROW_SMEM_BYTES(ST) (ROW_OFF_BARS(ST) + (2 * (ST) + 2) * 8)
 
+// ---- the two plane-owner phases, shared by the elastic and the acoustic row kernels ------------------------------------------
+// A task owns one 5x5 plane (fixed field row r = comp*5 + k and element e) of the tiles: words task_base + 25 jj + ii.
+// P1: reads the plane of tile A once, writes t1 = d/dxi back in place and t2 = d/deta into tile B.
+__device__ __forceinline__ void row_plane_derivatives(realw* s_A, realw* s_B, int task_base) {
+  realw v[NGLL2];
+#pragma unroll
+  for (int w = 0; w < NGLL2; ++w) v[w] = s_A[task_base + (w / 5) * 25 + (w % 5)];
+#pragma unroll
+  for (int jj = 0; jj < 5; ++jj)
+#pragma unroll
+    for (int ii = 0; ii < 5; ++ii) {
+      realw s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int l = 0; l < 5; ++l) {
+        s1 += v[jj * 5 + l] * c_hprime_xx[l * 5 + ii];  // t1(ii,jj) = sum_l u(l,jj) hprime_xx(ii,l)
+        s2 += v[l * 5 + ii] * c_hprime_xx[l * 5 + jj];  // t2(ii,jj) = sum_l u(ii,l) hprime_xx(jj,l)
+      }
+      s_A[task_base + jj * 25 + ii] = s1;
+      s_B[task_base + jj * 25 + ii] = s2;
+    }
+}
+// P3: n(i,j) = w_yz(j,k) sum_l f1(l,j) h'w(l,i) + w_xz(i,k) sum_l f2(i,l) h'w(l,j), f1 / f2 from tiles A / B, n -> tile A
+__device__ __forceinline__ void row_plane_weak(realw* s_A, const realw* s_B, const realw* s_w, int task_base, int task_k) {
+  realw v1[NGLL2], v2[NGLL2], wyz[5], wxz[5];
+#pragma unroll
+  for (int w = 0; w < NGLL2; ++w) {
+    v1[w] = s_A[task_base + (w / 5) * 25 + (w % 5)];
+    v2[w] = s_B[task_base + (w / 5) * 25 + (w % 5)];
+  }
+#pragma unroll
+  for (int l = 0; l < 5; ++l) {
+    wyz[l] = s_w[task_k * 5 + l];
+    wxz[l] = s_w[NGLL2 + task_k * 5 + l];
+  }
+#pragma unroll
+  for (int jj = 0; jj < 5; ++jj)
+#pragma unroll
+    for (int ii = 0; ii < 5; ++ii) {
+      realw n1 = 0.f, n2 = 0.f;
+#pragma unroll
+      for (int l = 0; l < 5; ++l) {
+        n1 += v1[jj * 5 + l] * c_hprimewgll_xx[ii * 5 + l];  // sum_l f1(l,jj) hprimewgll_xx(l,ii)
+        n2 += v2[l * 5 + ii] * c_hprimewgll_xx[jj * 5 + l];  // sum_l f2(ii,l) hprimewgll_xx(l,jj)
+      }
+      s_A[task_base + jj * 25 + ii] = wyz[jj] * n1 + wxz[ii] * n2;
+    }
+}
+
 template <int STAGES, int MAXREG>
 __global__ void __launch_bounds__(GRP_THREADS) __maxnreg__(MAXREG) k_elastic_forces_row(const GrpArgs a) {
   constexpr int RS = ROW_STRIDE;  // words per (comp,k) tile row
-  constexpr int PJ = 25;          // word distance between the rows of one 5x5 plane
   const size_t cs = vstride(a.nglob);  // distance between the components of one point (kernels_common.cuh)
   extern __shared__ __align__(128) unsigned char row_smem[];
   realw* const s_A = reinterpret_cast<realw*>(row_smem);  // U -> T1 -> F1 -> N
@@ -139,24 +186,7 @@ __global__ void __launch_bounds__(GRP_THREADS) __maxnreg__(MAXREG) k_elastic_for
     consumer_bar_sync();  // B1
 
     // ---- P1: in-plane derivatives by the plane owners ----
-    if (plane_task) {
-      realw v[NGLL2];
-#pragma unroll
-      for (int w = 0; w < NGLL2; ++w) v[w] = s_A[task_base + (w / 5) * PJ + (w % 5)];
-#pragma unroll
-      for (int jj = 0; jj < 5; ++jj)
-#pragma unroll
-        for (int ii = 0; ii < 5; ++ii) {
-          realw s1 = 0.f, s2 = 0.f;
-#pragma unroll
-          for (int l = 0; l < 5; ++l) {
-            s1 += v[jj * 5 + l] * c_hprime_xx[l * 5 + ii];  // t1(ii,jj) = sum_l u(l,jj) hprime_xx(ii,l)
-            s2 += v[l * 5 + ii] * c_hprime_xx[l * 5 + jj];  // t2(ii,jj) = sum_l u(ii,l) hprime_xx(jj,l)
-          }
-          s_A[task_base + jj * PJ + ii] = s1;
-          s_B[task_base + jj * PJ + ii] = s2;
-        }
-    }
+    if (plane_task) row_plane_derivatives(s_A, s_B, task_base);
     // gamma-direction derivative from the registers of the column owner (overlaps with the plane owners' work)
     realw t3x[5], t3y[5], t3z[5];
 #pragma unroll
@@ -262,31 +292,7 @@ __global__ void __launch_bounds__(GRP_THREADS) __maxnreg__(MAXREG) k_elastic_for
     consumer_bar_sync();  // B3
 
     // ---- P3: in-plane weak-form contractions by the plane owners ----
-    if (plane_task) {
-      realw v1[NGLL2], v2[NGLL2], wyz[5], wxz[5];
-#pragma unroll
-      for (int w = 0; w < NGLL2; ++w) {
-        v1[w] = s_A[task_base + (w / 5) * PJ + (w % 5)];
-        v2[w] = s_B[task_base + (w / 5) * PJ + (w % 5)];
-      }
-#pragma unroll
-      for (int l = 0; l < 5; ++l) {
-        wyz[l] = s_w[task_k * 5 + l];
-        wxz[l] = s_w[NGLL2 + task_k * 5 + l];
-      }
-#pragma unroll
-      for (int jj = 0; jj < 5; ++jj)
-#pragma unroll
-        for (int ii = 0; ii < 5; ++ii) {
-          realw n1 = 0.f, n2 = 0.f;
-#pragma unroll
-          for (int l = 0; l < 5; ++l) {
-            n1 += v1[jj * 5 + l] * c_hprimewgll_xx[ii * 5 + l];  // sum_l f1(l,jj) hprimewgll_xx(l,ii)
-            n2 += v2[l * 5 + ii] * c_hprimewgll_xx[jj * 5 + l];  // sum_l f2(ii,l) hprimewgll_xx(l,jj)
-          }
-          s_A[task_base + jj * PJ + ii] = wyz[jj] * n1 + wxz[ii] * n2;
-        }
-    }
+    if (plane_task) row_plane_weak(s_A, s_B, s_w, task_base, task_k);
     consumer_bar_sync();  // B4
 
     // ---- P4: assembly ----

@@ -13,6 +13,7 @@
 #include "group_store.cuh"
 #include "renumber.h"
 #include "kernels_elastic_row.cuh"
+#include "kernels_acoustic_row.cuh"
 #include "kernels_misc.cuh"
 #include "adjoint.cuh"
 #include "pml.cuh"
@@ -326,6 +327,7 @@ extern "C" void SB200_FC(prepare_constants_device)(
 
   const char* fk = getenv("SPECFEM_B200_FORCE_KERNEL");
   if (fk) mp->force_kernel_variant = atoi(fk);
+  if (const char* ak = getenv("SPECFEM_B200_ACOUSTIC_KERNEL")) mp->acoustic_kernel_variant = atoi(ak);
   const char* fn = getenv("SPECFEM_B200_FUSE_NEWMARK");
   if (fn) mp->fuse_newmark = atoi(fn);
   if (const char* ps = getenv("SPECFEM_B200_PRODUCER_SLEEP")) {
@@ -486,6 +488,7 @@ extern "C" void SB200_FC(prepare_fields_acoustic_device)(
   mp->d_kappastore_unpadded = dev_copy(kappastore, NGLL3 * nspec);
   mp->num_phase_ispec_acoustic = *num_phase_ispec_acoustic;
   mp->d_phase_ispec_inner_acoustic = dev_copy(phase_ispec_inner_acoustic, 2 * (size_t)mp->num_phase_ispec_acoustic);
+  mp->h_phase_ispec_acoustic.assign(phase_ispec_inner_acoustic, phase_ispec_inner_acoustic + 2 * (size_t)mp->num_phase_ispec_acoustic);
   if (*NOISE_TOMOGRAPHY == 0) {
     mp->num_free_surface_faces = *num_free_surface_faces;
     if (mp->num_free_surface_faces > 0) {
@@ -530,6 +533,7 @@ extern "C" void SB200_FC(prepare_cleanup_device)(long* Mesh_pointer, int* ACOUST
   dev_free(mp->d_perm);
   pml_destroy(mp);
   group_store_free(mp->grp_elastic);
+  group_store_free(mp->grp_acoustic);
   void* dptrs[] = {mp->d_ibool, mp->d_irregular_element_number, mp->d_metric, mp->d_kappav, mp->d_muv, mp->d_rhostore,
                    mp->d_rho_vp, mp->d_rho_vs, mp->d_kappastore_unpadded, mp->d_ispec_is_inner, mp->d_ispec_is_elastic,
                    mp->d_ispec_is_acoustic, mp->d_phase_ispec_inner_elastic, mp->d_phase_ispec_inner_acoustic,
@@ -1052,6 +1056,33 @@ extern "C" void SB200_FC(compute_forces_viscoelastic_cuda)(long* Mesh_pointer, i
 // =================================================================================================================
 // acoustic forces (replaces src/gpu/compute_forces_acoustic_cuda.cu:238-398)
 // =================================================================================================================
+// grouped storage of the fluid elements for k_acoustic_forces_row: segment 0/1 = outer/inner phase lists (atomics mode) or one
+// segment per colour; every segment padded to a multiple of three groups
+static void ensure_acoustic_groups(DeviceMesh* mp, int nspec_outer, int nspec_inner) {
+  if (mp->grp_acoustic) return;
+  std::vector<std::vector<int>> segs;
+  if (mp->use_mesh_coloring_gpu) {
+    const int ncol = mp->num_colors_outer_acoustic + mp->num_colors_inner_acoustic;
+    int offset = mp->nspec_elastic;  // acoustic colours follow the elastic ones in the permuted element order
+    for (int ic = 0; ic < ncol; ++ic) {
+      std::vector<int> seg;
+      for (int e = 0; e < mp->h_num_elem_colors_acoustic[ic]; ++e) seg.push_back(offset + e);
+      offset += mp->h_num_elem_colors_acoustic[ic];
+      segs.push_back(seg);
+    }
+  } else {
+    const int counts[2] = {nspec_outer, nspec_inner};
+    for (int ph = 0; ph < 2; ++ph) {
+      std::vector<int> seg;
+      const int* list = mp->h_phase_ispec_acoustic.data() + (size_t)mp->num_phase_ispec_acoustic * ph;
+      for (int e = 0; e < counts[ph]; ++e) seg.push_back(list[e] - 1);
+      segs.push_back(seg);
+    }
+  }
+  mp->grp_acoustic = group_store_build(mp, segs, mp->h_irregular_element_number, mp->d_irregular_element_number, mp->d_rhostore,
+                                       nullptr, /*lane_map=*/1, /*nmat=*/1, /*groups_multiple=*/ACR_SUB);
+}
+
 extern "C" void SB200_FC(compute_forces_acoustic_cuda)(long* Mesh_pointer, int* iphase, int* nspec_outer_acoustic,
                                                        int* nspec_inner_acoustic, int* FORWARD_OR_ADJOINT_f) {
   DeviceMesh* mp = get_mesh(Mesh_pointer);
@@ -1060,8 +1091,26 @@ extern "C" void SB200_FC(compute_forces_acoustic_cuda)(long* Mesh_pointer, int* 
   const int num_elements = (*iphase == 1) ? *nspec_outer_acoustic : *nspec_inner_acoustic;
   if (num_elements <= 0) return;
   if (foa != 1) require_backward_potentials(mp, "compute_forces_acoustic_cuda");
+  const int acoustic_variant = mp->acoustic_kernel_variant;
   for (int pass = 0; pass < 2; ++pass) {  // 0: (adjoint) potentials, 1: reconstructed forward potentials
   if (pass == 0 ? foa == 3 : foa == 1) continue;
+  if (acoustic_variant == 0) {
+    ensure_acoustic_groups(mp, *nspec_outer_acoustic, *nspec_inner_acoustic);
+    const realw* pot = pass == 0 ? mp->d_potential : mp->d_b_potential;
+    realw* pdd = pass == 0 ? mp->d_potential_dot_dot : mp->d_b_potential_dot_dot;
+    if (mp->use_mesh_coloring_gpu) {
+      const int c0 = (*iphase == 1) ? 0 : mp->num_colors_outer_acoustic;
+      const int c1 = (*iphase == 1) ? mp->num_colors_outer_acoustic : mp->num_colors_outer_acoustic + mp->num_colors_inner_acoustic;
+      for (int ic = c0; ic < c1; ++ic) {
+        launch_acoustic_grp(mp, mp->grp_acoustic, ic, pot, pdd, /*use_atomics=*/0);
+        KERNEL_CHECK(mp, "k_acoustic_forces_row(colour)");
+      }
+    } else {
+      launch_acoustic_grp(mp, mp->grp_acoustic, *iphase - 1, pot, pdd, /*use_atomics=*/1);
+      KERNEL_CHECK(mp, "k_acoustic_forces_row");
+    }
+    continue;
+  }
   AcousticArgs a;
   a.ibool = mp->d_ibool;
   a.irregular_element_number = mp->d_irregular_element_number;
@@ -1086,7 +1135,7 @@ extern "C" void SB200_FC(compute_forces_acoustic_cuda)(long* Mesh_pointer, int* 
       a.nb_elements = mp->h_num_elem_colors_acoustic[icolor];
       a.phase_ispec = nullptr; a.first_ispec = offset; a.use_atomics = 0;
       if (a.nb_elements > 0) {
-        launch_acoustic(mp, a);
+        launch_acoustic(mp, a, acoustic_variant);
         KERNEL_CHECK(mp, "acoustic forces (colour)");
       }
       offset += a.nb_elements;
@@ -1095,7 +1144,7 @@ extern "C" void SB200_FC(compute_forces_acoustic_cuda)(long* Mesh_pointer, int* 
     a.nb_elements = num_elements;
     a.phase_ispec = mp->d_phase_ispec_inner_acoustic + (size_t)mp->num_phase_ispec_acoustic * (*iphase - 1);
     a.first_ispec = 0; a.use_atomics = 1;
-    launch_acoustic(mp, a);
+    launch_acoustic(mp, a, acoustic_variant);
     KERNEL_CHECK(mp, "acoustic forces");
   }
   }

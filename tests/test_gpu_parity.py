@@ -321,6 +321,39 @@ def test_viscoelastic_time_loop_matches_oracle(device_lib, nproc):
     run.cleanup()
 
 
+@pytest.mark.parametrize("variant", [1, 0])  # 1 = one element per CTA, 0 = default (row kernel, three groups per CTA iteration)
+@pytest.mark.parametrize("regular", [False, True])
+@pytest.mark.parametrize("nex", [(7, 5, 4), (4, 4, 2)])  # 140 / 32 fluid elements: ragged groups, empty sub-groups
+def test_acoustic_force_kernel_matches_oracle(device_lib, variant, regular, nex):
+    """a4: one call of compute_forces_acoustic_cuda (both phases) on a smooth potential vs oracle_compute_forces_acoustic."""
+    from oracle.solver import OracleRun
+    from specfem3d_b200.time_loop import DeviceRun
+
+    os.environ["SPECFEM_B200_ACOUSTIC_KERNEL"] = str(variant)
+    water = Material(1020.0, 1500.0, 0.0, 9999.0, 9999.0, 1)
+    if regular:
+        spec = BoxSpec(nex[0], nex[1], nex[2], xmax=1000.0 * nex[0], ymax=1000.0 * nex[1], zmin=-1000.0 * nex[2], materials=(water,))
+    else:
+        spec = BoxSpec(nex[0], nex[1], nex[2], xmax=1100.0 * nex[0], ymax=900.0 * nex[1], zmin=-1000.0 * nex[2], materials=(water,),
+                       deform=0.15)
+    sim = make_simulation(spec, DT=0.01, NSTEP=4, sources=[], stations=[])
+    sim.initial_fields = smooth_fields(sim)
+    run = DeviceRun(sim)
+    r = run.ranks[0]
+    db = r.db
+    for iphase in (1, 2):
+        r.lib.compute_forces_acoustic_cuda(r.Mesh_pointer, iphase, db.nspec_outer_acoustic, db.nspec_inner_acoustic, 1)
+    _, _, pdd = r.fields_ac()
+    o = OracleRun(sim)
+    p = o.parts[0]
+    p.forces_acoustic(1)
+    p.forces_acoustic(2)
+    assert np.abs(p.pot_dot_dot).max() > 0
+    assert relerr(pdd, p.pot_dot_dot) < 2e-5, relerr(pdd, p.pot_dot_dot)
+    run.cleanup()
+    os.environ.pop("SPECFEM_B200_ACOUSTIC_KERNEL")
+
+
 @pytest.mark.parametrize("source_in_water", [False, True])
 @pytest.mark.parametrize("nproc", [(1, 1), (2, 2)])
 def test_coupled_acoustic_elastic_time_loop_matches_oracle(device_lib, nproc, source_in_water):
