@@ -88,6 +88,11 @@ __device__ __forceinline__ void bulk_g2s_hint(uint32_t dst_smem, const void* src
       "l"(src), "r"(bytes), "r"(bar), "l"(pol)
       : "memory");
 }
+// asynchronous prefetch of a contiguous region into L2 (no shared memory, no completion to wait for): keeps DRAM busy
+// while the shared-memory ring is full
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 struct GrpArgs {
@@ -161,6 +166,8 @@ struct GroupStore {
   int nmat = 2;  // material rows per point: 2 = kappa, mu (elastic), 1 = rho (acoustic)
   int ngroups = 0;
   int* d_ibool = nullptr;
+  int* d_slot = nullptr;     // [ngroups][5] 0-based element of every slot, -1 = empty
+  realw* d_att = nullptr;    // attenuation store [ngroups][5][30][128] (kernels_elastic_att_row.cuh), viscoelastic runs only
   realw* d_params = nullptr;
   unsigned* d_row0 = nullptr;
   std::vector<int> seg_first, seg_end;  // launch segments: [phase-1] without colouring, [colour] with colouring
@@ -170,6 +177,8 @@ struct GroupStore {
 inline void group_store_free(GroupStore* gs) {
   if (!gs) return;
   dev_free(gs->d_ibool);
+  dev_free(gs->d_slot);
+  dev_free(gs->d_att);
   dev_free(gs->d_params);
   dev_free(gs->d_row0);
   delete gs;
@@ -224,7 +233,8 @@ inline GroupStore* group_store_build(DeviceMesh* mp, const std::vector<std::vect
     gs->built = true;
     return gs;
   }
-  int* d_slot = dev_copy(slot_ispec.data(), slot_ispec.size());
+  gs->d_slot = dev_copy(slot_ispec.data(), slot_ispec.size());
+  int* d_slot = gs->d_slot;
   int* d_kind = dev_copy(kind.data(), kind.size());
   gs->d_row0 = dev_copy(row0.data(), row0.size());
   gs->d_ibool = dev_alloc<int>((size_t)gs->ngroups * GRP_IB_WORDS);
@@ -234,7 +244,6 @@ inline GroupStore* group_store_build(DeviceMesh* mp, const std::vector<std::vect
                                                                    gs->d_ibool, gs->d_params, lane_map, nmat);
   KERNEL_CHECK(mp, "k_build_group_slabs");
   CUDA_CHECK(cudaStreamSynchronize(mp->compute_stream));
-  dev_free(d_slot);
   dev_free(d_kind);
   gs->built = true;
   return gs;

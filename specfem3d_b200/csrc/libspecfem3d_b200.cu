@@ -14,6 +14,7 @@
 #include "renumber.h"
 #include "kernels_elastic_row.cuh"
 #include "kernels_acoustic_row.cuh"
+#include "kernels_elastic_att_row.cuh"
 #include "kernels_misc.cuh"
 #include "adjoint.cuh"
 #include "pml.cuh"
@@ -82,6 +83,8 @@ static realw* dev_copy_permuted(DeviceMesh* mp, const realw* h) {
 }  // namespace sb200
 
 using namespace sb200;
+
+static void att_store_to_elements(DeviceMesh* mp);  // attenuation store -> per-element arrays (defined with the force kernels)
 
 // =================================================================================================================
 // initialisation (replaces src/gpu/initialize_gpu.cu:100-260)
@@ -678,6 +681,7 @@ extern "C" void SB200_FC(transfer_rmemory_from_device)(long* Mesh_pointer, realw
   DeviceMesh* mp = get_mesh(Mesh_pointer);
   if (!mp->attenuation) exit_on_error("transfer_rmemory_from_device called without ATTENUATION");
   if (*size_R != mp->R_size) exit_on_error("transfer_rmemory_from_device: size_R mismatch");
+  att_store_to_elements(mp);
   download_sls(mp, mp->d_R_xx, R_xx); download_sls(mp, mp->d_R_yy, R_yy); download_sls(mp, mp->d_R_xy, R_xy);
   download_sls(mp, mp->d_R_xz, R_xz); download_sls(mp, mp->d_R_yz, R_yz); download_sls(mp, mp->d_R_trace, R_trace);
 }
@@ -693,6 +697,7 @@ extern "C" void SB200_FC(transfer_strain_from_device)(long* Mesh_pointer, realw*
   DeviceMesh* mp = get_mesh(Mesh_pointer);
   if (!mp->compute_and_store_strain) exit_on_error("transfer_strain_from_device called without COMPUTE_AND_STORE_STRAIN");
   if (*size_epsilondev != NGLL3 * mp->NSPEC_AB) exit_on_error("transfer_strain_from_device: size mismatch");
+  att_store_to_elements(mp);
   download_padded(mp, mp->d_epsilondev_xx, exx); download_padded(mp, mp->d_epsilondev_yy, eyy);
   download_padded(mp, mp->d_epsilondev_xy, exy); download_padded(mp, mp->d_epsilondev_xz, exz);
   download_padded(mp, mp->d_epsilondev_yz, eyz); download_padded(mp, mp->d_epsilondev_trace, etrace);
@@ -909,6 +914,25 @@ static void launch_elastic(DeviceMesh* mp, int nb, const int* phase_list, int fi
   KERNEL_CHECK(mp, "elastic forces");
 }
 
+static AttElementArrays att_element_arrays(DeviceMesh* mp) {
+  AttElementArrays e;
+  e.R[0] = mp->d_R_xx; e.R[1] = mp->d_R_yy; e.R[2] = mp->d_R_xy; e.R[3] = mp->d_R_xz; e.R[4] = mp->d_R_yz; e.R[5] = mp->d_R_trace;
+  e.eps[0] = mp->d_epsilondev_xx; e.eps[1] = mp->d_epsilondev_yy; e.eps[2] = mp->d_epsilondev_xy; e.eps[3] = mp->d_epsilondev_xz;
+  e.eps[4] = mp->d_epsilondev_yz; e.eps[5] = mp->d_epsilondev_trace;
+  e.fc = mp->d_factor_common; e.fck = mp->d_factor_common_kappa;
+  return e;
+}
+// The viscoelastic row kernel keeps memory variables, stored strains and factors in its own store (one contiguous chunk per
+// group and k-plane).  The per-element arrays of the ABI side stay allocated: they are refreshed from the store before
+// transfer_rmemory_from_device / transfer_strain_from_device read them (outside the time loop), and the C-PML kernel keeps
+// writing the strains of its own elements there.
+static void att_store_to_elements(DeviceMesh* mp) {
+  GroupStore* gs = mp->grp_elastic;
+  if (!gs || !gs->d_att || gs->ngroups == 0) return;
+  k_att_slabs<false><<<gs->ngroups, 128, 0, mp->compute_stream>>>(gs->ngroups, gs->d_slot, att_element_arrays(mp), gs->d_att);
+  KERNEL_CHECK(mp, "k_att_slabs(to element arrays)");
+}
+
 // grouped storage for the TMA kernel: segment 0/1 = outer/inner phase lists (atomics mode) or one segment per colour
 static void ensure_elastic_groups(DeviceMesh* mp, int nspec_outer, int nspec_inner) {
   if (mp->grp_elastic) return;
@@ -935,6 +959,33 @@ static void ensure_elastic_groups(DeviceMesh* mp, int nspec_outer, int nspec_inn
     }
   }
   mp->grp_elastic = group_store_build(mp, segs, mp->h_irregular_element_number, mp->d_irregular_element_number, mp->d_kappav, mp->d_muv, /*lane_map=*/1);
+  GroupStore* gs = mp->grp_elastic;
+  if (mp->attenuation && gs->ngroups > 0) {
+    gs->d_att = dev_alloc<realw>((size_t)gs->ngroups * 5 * ATR_CHUNK_WORDS);
+    k_att_slabs<true><<<gs->ngroups, 128, 0, mp->compute_stream>>>(gs->ngroups, gs->d_slot, att_element_arrays(mp), gs->d_att);
+    KERNEL_CHECK(mp, "k_att_slabs(to the attenuation store)");
+    CUDA_CHECK(cudaStreamSynchronize(mp->compute_stream));
+  }
+}
+
+static void launch_elastic_att_grp(DeviceMesh* mp, int segment, realw deltat, int use_atomics) {
+  const GroupStore* gs = mp->grp_elastic;
+  AttGrpArgs aa;
+  GrpArgs& a = aa.g;
+  a.first_group = gs->seg_first[segment];
+  a.end_group = gs->seg_end[segment];
+  const int ng = a.end_group - a.first_group;
+  if (ng <= 0) return;
+  a.ibool = gs->d_ibool; a.params = gs->d_params; a.row0 = gs->d_row0;
+  a.displ = mp->d_displ; a.accel = mp->d_accel;
+  a.xix_regular = mp->xix_regular; a.jacobian_regular = mp->jacobian_regular;
+  a.use_atomics = use_atomics;
+  a.nglob = (size_t)mp->NGLOB_AB;
+  aa.veloc = mp->d_veloc;
+  aa.att = gs->d_att;
+  aa.deltat = deltat;
+  KernelTimer timer(mp, "elastic_forces_attenuation");
+  launch_elastic_att_row(mp, aa, ng);
 }
 
 extern "C" void SB200_FC(compute_forces_viscoelastic_cuda)(long* Mesh_pointer, int* iphase, realw* deltat,
@@ -1014,6 +1065,23 @@ extern "C" void SB200_FC(compute_forces_viscoelastic_cuda)(long* Mesh_pointer, i
         launch_elastic(mp, num_elements, list, 0, *deltat, /*use_atomics=*/1, backward);
       }
     }
+    return;
+  }
+  const bool att_grp = mp->force_kernel_variant == 0 && mp->attenuation;  // viscoelastic row kernel + attenuation store
+  if (num_elements > 0 && att_grp) {
+    ensure_elastic_groups(mp, *nspec_outer_elastic, *nspec_inner_elastic);
+    if (mp->use_mesh_coloring_gpu) {
+      const int c0 = (*iphase == 1) ? 0 : mp->num_colors_outer_elastic;
+      const int c1 = (*iphase == 1) ? mp->num_colors_outer_elastic : mp->num_colors_outer_elastic + mp->num_colors_inner_elastic;
+      for (int ic = c0; ic < c1; ++ic) {
+        launch_elastic_att_grp(mp, ic, *deltat, /*use_atomics=*/0);
+        KERNEL_CHECK(mp, "k_elastic_forces_att_row(colour)");
+      }
+    } else {
+      launch_elastic_att_grp(mp, *iphase - 1, *deltat, /*use_atomics=*/1);
+      KERNEL_CHECK(mp, "k_elastic_forces_att_row");
+    }
+    if (mp->pml_conditions && mp->NSPEC_CPML > 0) pml_compute_forces(mp, *iphase, *nspec_outer_elastic, *nspec_inner_elastic);
     return;
   }
   const bool grp = mp->force_kernel_variant == 0 && !mp->attenuation && !mp->compute_and_store_strain;
