@@ -120,9 +120,10 @@ def partition_grid(n: int):
     return px, py
 
 
-def build_workload(n_gpus: int, rank: int, nex_per_gpu=(128, 128, 64), nstep: int = 100, elem_size=None):
-    """The rank's slab of the weak-scaled halfspace (only this rank's database is built; mass matrices are assembled
-    with the neighbours through torch.distributed in `assemble_mass_distributed`)."""
+def build_workload(n_gpus: int, rank: int, nex_per_gpu=(128, 128, 64), nstep: int = 100, elem_size=None, part=None):
+    """The rank's part of the halfspace (only this rank's database is built; mass matrices are assembled with the
+    neighbours through torch.distributed in `assemble_mass_distributed`).  Default: meshfem3D slabs; `part` (one rank id per
+    element of the whole box): an arbitrary element partition, e.g. the reference's METIS partition (--part-file)."""
     from specfem3d_b200.configs import CMT_DEFAULT, HALFSPACE, courant_dt
     from specfem3d_b200.gll import GLL
     from specfem3d_b200.meshfem import BoxSpec, build_partition, local_mass_matrices
@@ -133,24 +134,65 @@ def build_workload(n_gpus: int, rank: int, nex_per_gpu=(128, 128, 64), nstep: in
     nx, ny, nz = nex_per_gpu
     # element size of config 2 (134 km / 128) kept fixed under weak scaling; config 5 (strong scaling) halves it
     dx, dy, dz = elem_size if elem_size is not None else (134000.0 / 128, 134000.0 / 128, 60000.0 / 64)
-    spec = BoxSpec(nx * px, ny * py, nz, xmax=dx * nx * px, ymax=dy * ny * py, zmin=-dz * nz, nproc_xi=px, nproc_eta=py,
-                   materials=(HALFSPACE,))
+    if part is None:
+        spec = BoxSpec(nx * px, ny * py, nz, xmax=dx * nx * px, ymax=dy * ny * py, zmin=-dz * nz, nproc_xi=px, nproc_eta=py,
+                       materials=(HALFSPACE,))
+    else:  # the same global box, split by `part` (nproc_xi only carries the number of parts)
+        spec = BoxSpec(nx * px, ny * py, nz, xmax=dx * nx * px, ymax=dy * ny * py, zmin=-dz * nz, nproc_xi=n_gpus, nproc_eta=1,
+                       materials=(HALFSPACE,))
+        if len(part) != spec.nspec_total or part.max() != n_gpus - 1:
+            raise SystemExit(f"bench: the partition file holds {len(part)} elements in {part.max() + 1} parts, the mesh has "
+                             f"{spec.nspec_total} elements for {n_gpus} ranks")
     DT = courant_dt(spec, 2800.0)
     gll = GLL()
-    db = build_partition(spec, rank, gll)
+    db = build_partition(spec, rank, gll, part=part)
     loc = local_mass_matrices(spec, db, DT, gll)
     dbs = [None] * spec.nproc
     dbs[rank] = db
     src = CMTSource(x=0.5 * dx * nx + 0.3 * dx, y=0.5 * dy * ny + 0.2 * dy, z=-0.5 * dz * nz + 0.1 * dz,
                     moment_tensor=CMT_DEFAULT.moment_tensor, hdur=max(1.4, 5.0 * DT))
     sts = [Station(f"S{i}", "DB", (0.17 + 0.09 * i) * dx * nx, 0.5 * dy * ny + 0.1 * dy, 0.0) for i in range(4)]
-    # source and stations sit in rank 0's slab by construction
-    if rank == 0:
+    if part is not None:
+        sources = receivers = None  # located by locate_distributed (any rank may own them)
+    elif rank == 0:  # source and stations sit in rank 0's slab by construction
         sources = setup_sources(spec, [db], [src], DT, gll)
         receivers = setup_receivers(spec, [db], sts, gll)
     else:
         sources = receivers = None
     return spec, DT, gll, db, loc, sources, receivers, (src, sts)
+
+
+def locate_distributed(spec, db, rank, src, sts, DT, gll, group):
+    """Source / receiver location when every rank holds only its own part: each rank tries its own elements, the lowest rank
+    that contains the point owns it (locate_source.F90 / locate_receivers.f90 take the best of all slices the same way), the
+    owners' results are gathered on every rank."""
+    import torch.distributed as dist
+
+    from specfem3d_b200.sources_receivers import ReceiverSet, locate_point, setup_receivers, setup_sources
+
+    def mine(p):
+        try:
+            locate_point(spec, [db], p.x, p.y, p.z)
+            return True
+        except ValueError:
+            return False
+
+    found = [mine(src)] + [mine(st) for st in sts]
+    world = dist.get_world_size()
+    allfound = [None] * world
+    dist.all_gather_object(allfound, found, group=group)
+    owner = [min(r for r in range(world) if allfound[r][i]) for i in range(len(found))]
+    piece = {"src": setup_sources(spec, [db], [src], DT, gll) if owner[0] == rank else None,
+             "rec": {i: setup_receivers(spec, [db], [st], gll) for i, st in enumerate(sts) if owner[i + 1] == rank}}
+    pieces = [None] * world
+    dist.all_gather_object(pieces, piece, group=group)
+    sources = pieces[owner[0]]["src"]
+    recs = [pieces[owner[i + 1]]["rec"][i] for i in range(len(sts))]
+    receivers = ReceiverSet(len(sts), np.concatenate([r.islice_selected_rec for r in recs]),
+                            np.concatenate([r.ispec_selected_rec for r in recs]), np.concatenate([r.hxir_store for r in recs]),
+                            np.concatenate([r.hetar_store for r in recs]), np.concatenate([r.hgammar_store for r in recs]),
+                            np.concatenate([r.nu_rec for r in recs]), list(sts), sum((r.local for r in recs), []))
+    return sources, receivers
 
 
 def smooth_state(db, amp=1e-3):
@@ -252,7 +294,12 @@ def run_device(args):
     # warm-up + timed regions 1 (value), 2 (kernel events) and 3 (e2e) all record one seismogram sample per step
     k2 = min(args.steps, 20)
     nstep_total = args.warmup + 2 * args.steps + k2 + 4
-    spec, DT, gll, db, loc, sources, receivers, _ = build_workload(world, rank, nex, nstep_total, elem)
+    part = None
+    if args.part_file:
+        if world == 1:
+            raise SystemExit("bench: --part-file needs N > 1")
+        part = np.load(args.part_file).astype(np.int32)
+    spec, DT, gll, db, loc, sources, receivers, (src_def, sts_def) = build_workload(world, rank, nex, nstep_total, elem, part)
 
     # ---- mass-matrix assembly across ranks (assemble_MPI_scalar_blocking) ---------------------------------------------
     if world > 1:
@@ -264,10 +311,12 @@ def run_device(args):
         setattr(db, key, invert_mass(loc[key]))
 
     # every rank needs the global source list (islice_selected_source) -- rank 0 owns it, broadcast the small arrays
-    if world > 1:
+    if world > 1 and part is None:
         obj = [sources, receivers]
         dist.broadcast_object_list(obj, src=0, group=gloo)
         sources, receivers = obj
+    elif world > 1:
+        sources, receivers = locate_distributed(spec, db, rank, src_def, sts_def, DT, gll, gloo)
     dbs = [None] * spec.nproc
     dbs[rank] = db
     sim = Simulation(spec, DT, nstep_total, dbs, gll, sources, receivers)
@@ -379,7 +428,9 @@ def run_device(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload,
                        "elements_total": nspec_total, "elements_per_gpu": db.NSPEC_AB, "nglob_per_gpu": db.NGLOB_AB,
-                       "partitions": f"{spec.nproc_xi}x{spec.nproc_eta} slabs (meshfem3D NPROC_XI x NPROC_ETA)",
+                       "partitions": (f"{spec.nproc_xi}x{spec.nproc_eta} slabs (meshfem3D NPROC_XI x NPROC_ETA)" if part is None else
+                                      f"{world} parts of xdecompose_mesh PARTITIONING_TYPE 2 (the reference's METIS 4.0.3 on the dual graph, "
+                                      f"{args.part_file}): {db.num_interfaces_ext_mesh} neighbours on rank 0"),
                        "halo": (args.halo if world > 1 else "none"), "dt": DT,
                        "l2_policy": "working set per step (>10 GB) >> 126 MB L2, no flush needed"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * (sources.NSOURCES if sources else 0),
@@ -721,6 +772,8 @@ def main():
                     help="weak: one 128x128x64 slab per GPU (default); strong: config 5's 256x256x128 mesh split into N slabs")
     ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4"],
                     help="cfg2: BASELINE configs[1] (default); cfg3 / cfg4: configs[2] / configs[3] at their stated size, 1 GPU")
+    ap.add_argument("--part-file", default=None,
+                    help="N>1: .npy element partition of the global box (tools/make_metis_partition.py) instead of slabs")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary-kernel rooflines and the config-1 step cost")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip the run of the reference's own CUDA backend")
     ap.add_argument("--ref-cuda-only", action="store_true", help=argparse.SUPPRESS)

@@ -216,13 +216,14 @@ def setup_sources(spec: BoxSpec, dbs: List[Database], sources: Sequence, DT: flo
     is_cmt = isinstance(sources[0], CMTSource)
     local = []
     in_fluid = []
+    by_rank = {db.myrank: db for db in dbs if db is not None}  # the list may hold a subset of the ranks (distributed runs)
     for n, s in enumerate(sources):
         rank, ispec, xi, eta, gam, _ = locate_point(spec, dbs, s.x, s.y, s.z)
         isl[n], isp[n] = rank, ispec
         local.append((xi, eta, gam))
-        in_fluid.append(bool(dbs[rank].ispec_is_acoustic[ispec - 1]))
+        in_fluid.append(bool(by_rank[rank].ispec_is_acoustic[ispec - 1]))
         if is_cmt:
-            sa[..., n] = sourcearray_cmt(dbs[rank], gll, ispec, xi, eta, gam, s)  # fluid: simulation._acoustic_sourcearrays
+            sa[..., n] = sourcearray_cmt(by_rank[rank], gll, ispec, xi, eta, gam, s)  # fluid: simulation._acoustic_sourcearrays
             hdur[n] = max(s.hdur, 5.0 * DT)  # get_cmt.f90:369
         else:
             sa[..., n] = sourcearray_force(gll, xi, eta, gam, s)

@@ -227,3 +227,59 @@ def test_mesh_files_round_trip(tmp_path):
         assert np.allclose(m["nodes_coords"][nodes][..., axis], val)
         for e, nd in zip(els, nodes):
             assert set(nd) <= set(elm[e])
+
+
+# ---- PARTITIONING_TYPE = 2: the reference's own METIS (oracle/_ref/libmetis_ref.so, oracle/build_ref_metis.sh) -----------------
+def metis_box():
+    water = Material(1020.0, 1500.0, 0.0, 9999.0, 9999.0, 1)
+    return BoxSpec(12, 10, 8, xmax=1100.0 * 12, ymax=900.0 * 10, zmin=-8000.0, materials=(HALFSPACE, water),
+                   layer_material=[0] * 6 + [1] * 2)
+
+
+def test_metis_partition_is_the_reference_partition():
+    """`part[]` of xdecompose_mesh with PARTITIONING_TYPE = 2: dual graph + loads of decompose.py handed to the METIS 4.0.3 the
+    reference vendors, through the call of wrap_metis.c (oracle/metis_ref.py).  Pinned bit for bit on a committed fixture
+    (tests/golden/metis_partition.npz: 960 elements with mixed loads, 4 and 7 parts); METIS seeds its own generator, so the
+    result is a pure function of the graph."""
+    import os
+
+    from oracle import metis_ref
+
+    if not metis_ref.available():
+        pytest.skip("oracle/_ref/libmetis_ref.so not built (oracle/build_ref_metis.sh needs /root/reference)")
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "metis_partition.npz"))
+    spec = metis_box()
+    xadj, adjncy, _ = dual_graph(spec, 1)
+    loads = element_loads(spec)
+    for n in (4, 7):
+        part, edgecut = metis_ref.partition_metis(xadj, adjncy, loads, n)
+        assert np.array_equal(part, gold[f"part_{n}"].astype(np.int32)), n
+        assert edgecut == int(gold[f"edgecut_{n}"])
+        # what METIS was asked for: balanced LOADS (10 per fluid element, 41 per elastic one), every part used
+        w = np.bincount(part, weights=loads, minlength=n)
+        assert w.min() > 0 and w.max() / w.mean() < 1.05
+        # the edgecut it reports is the number of dual-graph edges that cross parts
+        src = np.repeat(np.arange(len(xadj) - 1), np.diff(xadj))
+        assert int((part[src] != part[adjncy]).sum()) // 2 == edgecut
+
+
+def test_run_on_the_metis_partition_equals_single_rank_run():
+    """A coupled fluid-solid run on the 4-part METIS partition of the fixture (irregular interfaces, ranks with 3 neighbours)
+    gives the seismograms of the single-rank run."""
+    import os
+
+    from oracle.solver import OracleRun
+
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "metis_partition.npz"))
+    part = gold["part_4"].astype(np.int32)
+    spec = metis_box()
+    src = [CMTSource(0.52 * spec.xmax, 0.47 * spec.ymax, 0.55 * spec.zmin, (1e23, -2e23, 0.5e23, 0.3e23, -0.7e23, 0.2e23), hdur=0.3)]
+    sts = [Station("A", "XX", 0.21 * spec.xmax, 0.33 * spec.ymax, -6500.0), Station("B", "XX", 0.7 * spec.xmax, 0.6 * spec.ymax, -7000.0)]
+    runs = []
+    for p in (None, part):
+        sim = make_simulation(spec, DT=0.01, NSTEP=400, sources=src, stations=sts, part=p)
+        runs.append(OracleRun(sim).run().seis_d)
+        if p is not None:
+            assert max(db.num_interfaces_ext_mesh for db in sim.dbs) >= 3
+    assert np.abs(runs[0]).max() > 0
+    assert np.linalg.norm(runs[1].astype(np.float64) - runs[0]) / np.linalg.norm(runs[0]) <= 2e-5

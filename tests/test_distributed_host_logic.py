@@ -87,3 +87,52 @@ def test_single_rank_view_of_a_partitioned_simulation():
     sim = Simulation(spec, DT, 10, dbs, gll, sources, receivers)
     assert sim.ELASTIC_SIMULATION and not sim.ACOUSTIC_SIMULATION
     assert sim.nlength_seismogram == 10
+
+
+def _worker_part(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import pickle
+
+    import bench
+
+    part = np.load(os.path.join(out_dir, "part.npy"))
+    spec, DT, gll, db, loc, sources, receivers, (src, sts) = bench.build_workload(world, rank, (6, 4, 4), 10, None, part)
+    assert sources is None and receivers is None
+    sources, receivers = bench.locate_distributed(spec, db, rank, src, sts, DT, gll, dist.group.WORLD)
+    with open(os.path.join(out_dir, f"loc_{rank}.pkl"), "wb") as f:
+        pickle.dump((sources, receivers, db.NSPEC_AB), f)
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_arbitrary_partition_and_distributed_location(tmp_path):
+    """bench.py --part-file: an arbitrary element partition (here a ragged two-part one), every rank builds only its own part,
+    sources / receivers are located by whichever rank holds them; the result must equal the all-in-one-process location."""
+    import pickle
+
+    import bench
+    from specfem3d_b200.configs import HALFSPACE
+    from specfem3d_b200.sources_receivers import setup_receivers, setup_sources
+
+    nx, ny, nz = 12, 4, 4  # bench.partition_grid(2) = 2 x 1 slabs of 6 x 4 x 4: the global box of the part-file run
+    e = np.arange(nx * ny * nz)
+    ix, iy, iz = e % nx, (e // nx) % ny, e // (nx * ny)
+    part = ((ix + iy + 2 * iz) % 7 < 3).astype(np.int32)  # interleaved diagonal bands: both ranks own pieces everywhere
+    np.save(tmp_path / "part.npy", part)
+    port = _free_port()
+    mp.spawn(_worker_part, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = [pickle.load(open(tmp_path / f"loc_{r}.pkl", "rb")) for r in range(2)]
+    assert got[0][2] + got[1][2] == nx * ny * nz
+    # reference: both parts in one process
+    spec, DT, gll, db0, _, _, _, (src, sts) = bench.build_workload(2, 0, (6, 4, 4), 10, None, part)
+    _, _, _, db1, _, _, _, _ = bench.build_workload(2, 1, (6, 4, 4), 10, None, part)
+    ref_s = setup_sources(spec, [db0, db1], [src], DT, gll)
+    ref_r = setup_receivers(spec, [db0, db1], sts, gll)
+    for s, r, _ in got:
+        assert np.array_equal(s.islice_selected_source, ref_s.islice_selected_source)
+        assert np.array_equal(s.ispec_selected_source, ref_s.ispec_selected_source)
+        assert np.array_equal(s.sourcearrays, ref_s.sourcearrays)
+        assert np.array_equal(r.islice_selected_rec, ref_r.islice_selected_rec)
+        assert np.array_equal(r.ispec_selected_rec, ref_r.ispec_selected_rec)
+        assert np.allclose(r.hxir_store, ref_r.hxir_store) and np.allclose(r.hgammar_store, ref_r.hgammar_store)
