@@ -15,6 +15,7 @@
 #include "kernels_elastic_row.cuh"
 #include "kernels_acoustic_row.cuh"
 #include "kernels_elastic_att_row.cuh"
+#include "kernels_elastic_kl_row.cuh"
 #include "kernels_misc.cuh"
 #include "adjoint.cuh"
 #include "pml.cuh"
@@ -1007,8 +1008,40 @@ extern "C" void SB200_FC(compute_forces_viscoelastic_cuda)(long* Mesh_pointer, i
     // compute_kernels_elastic_cuda, so the one-thread-per-point kernel is used (the plane-owner kernel stores no strain).
     if (foa != 1) require_backward_fields(mp, "compute_forces_viscoelastic_cuda");
     if (mp->pml_conditions && mp->NSPEC_CPML > 0) exit_on_error("compute_forces_viscoelastic_cuda: C-PML in a kernel run is not implemented");
+    if (foa == 0 && mp->kl_fused && !mp->attenuation && num_elements > 0 && mp->force_kernel_variant == 0 && !mp->anisotropic_kl &&
+        !mp->approximate_hess_kl) {
+      // both wavefields in one launch of the row kernel, mu_kl / kappa_kl accumulated on the spot (kernels_elastic_kl_row.cuh)
+      ensure_elastic_groups(mp, *nspec_outer_elastic, *nspec_inner_elastic);
+      const GroupStore* gs = mp->grp_elastic;
+      KlGrpArgs aa;
+      GrpArgs& g = aa.g;
+      g.ibool = gs->d_ibool; g.params = gs->d_params; g.row0 = gs->d_row0;
+      g.displ = mp->d_displ; g.accel = mp->d_accel;
+      g.xix_regular = mp->xix_regular; g.jacobian_regular = mp->jacobian_regular;
+      g.nglob = (size_t)mp->NGLOB_AB;
+      aa.b_displ = mp->d_b_displ; aa.b_accel = mp->d_b_accel;
+      aa.slot_ispec = gs->d_slot;
+      aa.mu_kl = mp->d_mu_kl; aa.kappa_kl = mp->d_kappa_kl;
+      aa.deltat = *deltat;
+      const int s0 = mp->use_mesh_coloring_gpu ? ((*iphase == 1) ? 0 : mp->num_colors_outer_elastic) : *iphase - 1;
+      const int s1 = mp->use_mesh_coloring_gpu
+                         ? ((*iphase == 1) ? mp->num_colors_outer_elastic : mp->num_colors_outer_elastic + mp->num_colors_inner_elastic)
+                         : *iphase;
+      for (int seg = s0; seg < s1; ++seg) {
+        g.first_group = gs->seg_first[seg];
+        g.end_group = gs->seg_end[seg];
+        g.use_atomics = mp->use_mesh_coloring_gpu ? 0 : 1;
+        const int ng = g.end_group - g.first_group;
+        if (ng <= 0) continue;
+        KernelTimer timer(mp, "elastic_forces_kl_pair");
+        launch_elastic_kl_row(mp, aa, ng);
+        KERNEL_CHECK(mp, "k_elastic_forces_kl_row");
+      }
+      mp->kl_pair_launches++;
+      return;
+    }
     if (foa == 0 && mp->kl_fused && !mp->attenuation && num_elements > 0) {
-      // both wavefields in one launch, mu / kappa (and the Hessian strain terms) accumulated on the spot (adjoint.cuh)
+      // anisotropic / Hessian kernels: both wavefields in one launch of the one-thread-per-point kernel (adjoint.cuh)
       KlPairArgs a;
       a.ibool = mp->d_ibool; a.irregular_element_number = mp->d_irregular_element_number; a.metric = mp->d_metric;
       a.xix_regular = mp->xix_regular; a.jacobian_regular = mp->jacobian_regular;
