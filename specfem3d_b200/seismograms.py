@@ -49,7 +49,7 @@ def write_seismograms(sim, seis: np.ndarray, out_dir: str, which: str = "d") -> 
     os.makedirs(out_dir, exist_ok=True)
     rec = sim.receivers
     t = sim.time_axis()
-    bic = band_instrument_code(sim.DT * sim.NTSTEP_BETWEEN_OUTPUT_SAMPLE)
+    bic = band_instrument_code(sim.DT)  # sampling_rate = DT only (write_seismograms.f90:1077-1078)
     paths = []
     for irec in range(rec.nrec):
         comps = "P" if which == "p" else "XYZ"
@@ -96,8 +96,11 @@ def compare_with_reference(syn_dir: str, ref_dir: str) -> Dict[str, Dict[str, fl
 def write_adjoint_sources(sim, adj: np.ndarray, sem_dir: str) -> List[str]:
     """``SEM/NET.STA.<band>{X,Y,Z}.adj``: two-column ASCII ``time value`` like the seismograms, NSTEP lines per file."""
     os.makedirs(sem_dir, exist_ok=True)
-    rec, t = sim.receivers, sim.time_axis()
-    bic = band_instrument_code(sim.DT * sim.NTSTEP_BETWEEN_OUTPUT_SAMPLE)
+    rec = sim.receivers
+    # adjoint sources have NSTEP samples whatever NTSTEP_BETWEEN_OUTPUT_SAMPLE is
+    t0 = sim.sources.t0 if sim.sources is not None else 0.0
+    t = np.arange(sim.NSTEP) * sim.DT - t0
+    bic = band_instrument_code(sim.DT)  # sampling_rate = DT only (write_seismograms.f90:1077-1078)
     paths = []
     for irec in range(rec.nrec):
         st = rec.stations[irec]
@@ -116,7 +119,7 @@ def read_adjoint_sources(sim, sem_dir: str) -> np.ndarray:
     each (shorter files are an error, like the reference's 'file too short' stop), as (nrec, NSTEP, 3) float32.  The
     reference stores them as read, in mesh x / y / z (SUPPRESS_UTM_PROJECTION) -- no rotation is applied here either."""
     rec = sim.receivers
-    bic = band_instrument_code(sim.DT * sim.NTSTEP_BETWEEN_OUTPUT_SAMPLE)
+    bic = band_instrument_code(sim.DT)  # sampling_rate = DT only (write_seismograms.f90:1077-1078)
     out = np.zeros((rec.nrec, sim.NSTEP, 3), np.float32)
     for irec in range(rec.nrec):
         st = rec.stations[irec]
