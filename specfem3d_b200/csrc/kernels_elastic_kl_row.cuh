@@ -10,7 +10,11 @@
 // Here: persistent CTAs, the element parameters (6 of the 12.6 KB per element) streamed ONCE through the TMA ring for both
 // wavefields, plane-owner contractions (150 tasks = two rounds of 75 for P1 and P3), four tiles.
 //   tiles A,B: adjoint wavefield  U -> T1 -> F1 -> N (A), T2 -> F2 (B);  tiles C,D: the same for the reconstructed one.
-// The anisotropic (21 cijkl planes) and approximate-Hessian accumulations keep using k_elastic_forces_kl_pair.
+// mu_kl / kappa_kl are accumulated with RED.ADD (one owner lane per element point, so it is a plain sum): the first version
+// read-modify-wrote them and 39 % of its warp samples waited for those ten loads (profiles/r02s_kl_row_ncu_summary.txt:
+// 6.08 ms); with the atomics 4.40 ms per 1,048,576 elements = 3.0 TB/s on 12,608 B / element = 0.47 of the HBM roofline
+// (round 1: 6.25 ms = 0.33).  The anisotropic (21 cijkl planes) and approximate-Hessian accumulations keep using
+// k_elastic_forces_kl_pair.
 #pragma once
 #include "kernels_elastic_row.cuh"
 
@@ -31,8 +35,8 @@ struct KlGrpArgs {
   realw deltat;
 };
 
-template <int STAGES>
-__global__ void __launch_bounds__(GRP_THREADS, 3) k_elastic_forces_kl_row(const KlGrpArgs aa) {
+template <int STAGES, int MINB>
+__global__ void __launch_bounds__(GRP_THREADS, MINB) k_elastic_forces_kl_row(const KlGrpArgs aa) {
   const GrpArgs& a = aa.g;
   constexpr int RS = ROW_STRIDE;
   const size_t cs = vstride(a.nglob);
@@ -239,9 +243,11 @@ __global__ void __launch_bounds__(GRP_THREADS, 3) k_elastic_forces_kl_row(const 
       // isotropic kernels (compute_kernels_cudakernel.cu: compute_kernels_cudakernel; compute_kernels.F90: compute_kernels_el)
       if (valid) {
         const size_t o = kl_off + k * NGLL2;
-        aa.mu_kl[o] += aa.deltat * (e[0][0] * e[1][0] + e[0][1] * e[1][1] + (e[0][0] + e[0][1]) * (e[1][0] + e[1][1]) +
-                                    2 * (e[0][2] * e[1][2] + e[0][3] * e[1][3] + e[0][4] * e[1][4]));
-        aa.kappa_kl[o] += aa.deltat * (9 * e[0][5] * e[1][5]);
+        // every (element, point) belongs to exactly one lane: a fire-and-forget RED.ADD is a plain accumulation here, and no
+        // load has to come back (ncu on the read-modify-write version: 39 % of the consumer samples waited for these ten loads)
+        red_add(aa.mu_kl + o, aa.deltat * (e[0][0] * e[1][0] + e[0][1] * e[1][1] + (e[0][0] + e[0][1]) * (e[1][0] + e[1][1]) +
+                                           2 * (e[0][2] * e[1][2] + e[0][3] * e[1][3] + e[0][4] * e[1][4])));
+        red_add(aa.kappa_kl + o, aa.deltat * (9 * e[0][5] * e[1][5]));
       }
     }
     consumer_bar_sync();  // B3
@@ -275,19 +281,23 @@ __global__ void __launch_bounds__(GRP_THREADS, 3) k_elastic_forces_kl_row(const 
   }
 }
 
-inline void launch_elastic_kl_row(DeviceMesh* mp, const KlGrpArgs& aa, int ng) {
-  constexpr int ST = 3;
+template <int ST, int MINB>
+inline void launch_elastic_kl_row_t(DeviceMesh* mp, const KlGrpArgs& aa, int ng) {
   static int ctas[64] = {0};
   int& occ = ctas[mp->device & 63];
   if (!occ) {
-    CUDA_CHECK(cudaFuncSetAttribute(k_elastic_forces_kl_row<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, KLR_SMEM_BYTES(ST)));
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_elastic_forces_kl_row<ST>, GRP_THREADS, KLR_SMEM_BYTES(ST)));
+    CUDA_CHECK(cudaFuncSetAttribute(k_elastic_forces_kl_row<ST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, KLR_SMEM_BYTES(ST)));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_elastic_forces_kl_row<ST, MINB>, GRP_THREADS, KLR_SMEM_BYTES(ST)));
     if (occ < 1) exit_on_error("k_elastic_forces_kl_row does not fit on an SM");
-    if (getenv("SPECFEM_B200_VERBOSE")) fprintf(stderr, "k_elastic_forces_kl_row<%d>: %d CTAs per SM\n", ST, occ);
+    if (getenv("SPECFEM_B200_VERBOSE")) fprintf(stderr, "k_elastic_forces_kl_row<%d,%d>: %d CTAs per SM\n", ST, MINB, occ);
   }
   int grid = mp->num_sms * occ;
   if (ng < grid) grid = ng;
-  k_elastic_forces_kl_row<ST><<<grid, GRP_THREADS, KLR_SMEM_BYTES(ST), mp->compute_stream>>>(aa);
+  k_elastic_forces_kl_row<ST, MINB><<<grid, GRP_THREADS, KLR_SMEM_BYTES(ST), mp->compute_stream>>>(aa);
+}
+inline void launch_elastic_kl_row(DeviceMesh* mp, const KlGrpArgs& aa, int ng) {
+  // 3-stage ring, 125 registers, 3 CTAs / SM: 4.40 ms per 1M elements; 2-stage ring, 96 registers (76 B spilled), 4 CTAs: 4.91 ms
+  launch_elastic_kl_row_t<3, 3>(mp, aa, ng);
 }
 
 }  // namespace sb200

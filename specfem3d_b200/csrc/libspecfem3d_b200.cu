@@ -1070,6 +1070,7 @@ extern "C" void SB200_FC(compute_forces_viscoelastic_cuda)(long* Mesh_pointer, i
         a.nb_elements = num_elements;
         a.phase_ispec = mp->d_phase_ispec_inner_elastic + (size_t)mp->num_phase_ispec_elastic * (*iphase - 1);
         a.first_ispec = 0; a.use_atomics = 1;
+        KernelTimer timer(mp, "elastic_forces_kl_pair");
         k_elastic_forces_kl_pair<<<a.nb_elements, NGLL3_PADDED, 0, mp->compute_stream>>>(a);
         KERNEL_CHECK(mp, "k_elastic_forces_kl_pair");
       }

@@ -25,6 +25,9 @@ def main():
     ap.add_argument("--kernel-run", action="store_true",
                     help="time a SIMULATION_TYPE = 3 run (adjoint + reconstructed wavefield + kernels) instead of a forward run")
     ap.add_argument("--skip-reference", action="store_true", help="time the product library only")
+    ap.add_argument("--only-reference", action="store_true",
+                    help="kernel run: use the reference backend alone in this process (forward run included); the two libraries "
+                         "are best timed in separate processes, the reference resets the device when it initialises")
     args = ap.parse_args()
     import torch
 
@@ -35,7 +38,7 @@ def main():
     from specfem3d_b200.time_loop import DeviceRank, DeviceRun
 
     nex = tuple(int(v) for v in args.nex.split("x"))
-    nstep = args.warmup + args.steps + 2
+    nstep = args.warmup + args.steps + 8
     spec, DT, gll, db, loc, sources, receivers, _ = bench.build_workload(1, 0, nex, nstep)
     for key in ("rmassx", "rmassy", "rmassz"):
         setattr(db, key, invert_mass(loc[key]))
@@ -88,7 +91,8 @@ def kernel_run_bench(args, spec, DT, gll, db, sources, receivers, nstep):
             s.initial_fields = init
         return s
 
-    fwd, prod = run_forward_and_save(sim(1), lib=abi.load())
+    ref_path = os.path.join(ROOT, "oracle", "_ref", "libspecfem_ref_cuda.so")
+    fwd, prod = run_forward_and_save(sim(1), lib=abi.DeviceLibrary(ref_path) if args.only_reference else abi.load())
     fwd.cleanup()
     t = np.arange(nstep) * DT
     adj = np.zeros((receivers.nrec, nstep, 3), np.float32)
@@ -97,6 +101,8 @@ def kernel_run_bench(args, spec, DT, gll, db, sources, receivers, nstep):
     libs = {"specfem3d_b200": abi.LIB_PATH, "reference_cuda_backend": os.path.join(ROOT, "oracle", "_ref", "libspecfem_ref_cuda.so")}
     for name, path in libs.items():
         if args.skip_reference and name != "specfem3d_b200":
+            continue
+        if args.only_reference and name == "specfem3d_b200":
             continue
         if not os.path.exists(path):
             out[name] = {"unavailable": path}
@@ -114,6 +120,16 @@ def kernel_run_bench(args, spec, DT, gll, db, sources, receivers, nstep):
         rho, mu, kappa = k.kernels()[0]
         out[name] = {"ms_per_step": dt / args.steps * 1e3, "element_timesteps_per_s": db.NSPEC_AB * args.steps / dt,
                      "kl_l2": [float(np.linalg.norm(a.astype(np.float64))) for a in (rho, mu, kappa)]}
+        if name == "specfem3d_b200":  # a few more steps with the library's event timers around the two-wavefield force kernel
+            import bench
+            r = k.ranks[0]
+            bench.set_kernel_timing(r.lib, r, True)
+            for _ in range(5):
+                k.step()
+            bench.set_kernel_timing(r.lib, r, False)
+            ms, cnt = bench.kernel_time(r.lib, r, "elastic_forces_kl_pair")
+            out[name]["kl_pair_kernel_ms_per_step"] = ms / 5
+            out[name]["kl_pair_launches_per_step"] = cnt / 5
         if name == "specfem3d_b200":
             k.cleanup()  # the reference library resets the device when it initialises: nothing of ours may be alive then
     out["workload"] = (f"kernel run (SIMULATION_TYPE 3), {db.NSPEC_AB} elastic elements, Stacey replay "
