@@ -533,7 +533,7 @@ def secondary_rooflines(lib, args, cfg3_nex=(96, 96, 48), cfg4_nex=(128, 128, 64
     ms, k, _ = time_config(lib, sim, ("elastic_forces_attenuation", "pml_forces"))
     w = (f"configs[2] scaled to {cfg3_nex[0]}x{cfg3_nex[1]}x{cfg3_nex[2]} = {db.NSPEC_AB} elements: 3 viscoelastic layers "
          f"(3 SLS), C-PML shell 3 elements thick ({ncpml} C-PML elements)")
-    out.append(roofline_entry("k_elastic_forces_pt<ATTENUATION,STRAIN>", "a2", w, db.NSPEC_AB - ncpml, "element",
+    out.append(roofline_entry("k_elastic_forces_att_row<3>", "a2", w, db.NSPEC_AB - ncpml, "element",
                               BYTES_PER_ELEMENT_ATTENUATION, k["elastic_forces_attenuation"]))
     out.append(roofline_entry("k_pml_elastic_forces", "a3", w, ncpml, "C-PML element", BYTES_PER_ELEMENT_PML, k["pml_forces"]))
     out[-1]["ms_per_step_whole_config"] = out[-2]["ms_per_step_whole_config"] = ms
@@ -642,7 +642,7 @@ def run_config(args):
         ncpml = int(sim.pml[0]["NSPEC_CPML"])
         wl = (f"configs[2]: layered viscoelastic model, ATTENUATION (3 SLS), C-PML shell 3 elements thick, "
               f"{nex[0]}x{nex[1]}x{nex[2]} = {db.NSPEC_AB} elements ({ncpml} C-PML), 1 GPU")
-        main = roofline_entry("k_elastic_forces_pt<ATTENUATION,STRAIN>", "a2", wl, db.NSPEC_AB - ncpml, "element",
+        main = roofline_entry("k_elastic_forces_att_row<3>", "a2", wl, db.NSPEC_AB - ncpml, "element",
                               BYTES_PER_ELEMENT_ATTENUATION, k["elastic_forces_attenuation"])
         extra = [roofline_entry("k_pml_elastic_forces", "a3", wl, ncpml, "C-PML element", BYTES_PER_ELEMENT_PML, k["pml_forces"])]
     else:

@@ -107,6 +107,9 @@ struct DeviceMesh {
   realw *d_potential = nullptr, *d_potential_dot = nullptr, *d_potential_dot_dot = nullptr;               // [NGLOB]
   realw *d_rmassx = nullptr, *d_rmassy = nullptr, *d_rmassz = nullptr, *d_rmass_acoustic = nullptr;       // [NGLOB]
   realw* d_rmass_ocean_load = nullptr;  // [NGLOB], inverted like the others
+  realw* d_rmass_c = nullptr;           // compact inverse mass [NGLOB]: value, or -(e + 1) = row e of d_rmass_exc [3][rmass_nexc]
+  realw* d_rmass_exc = nullptr;
+  long long rmass_nexc = 0;
   // APPROXIMATE_OCEAN_LOAD: the free-surface points of elastic faces, each once, in the face order of the CPU loop (the first
   // face that touches a point supplies its normal: compute_coupling_ocean, compute_coupling_viscoelastic_ac.f90:207-247)
   int num_ocean_points = 0;
@@ -214,6 +217,7 @@ struct DeviceMesh {
 
   // options
   int force_kernel_variant = 0;  // 0 = default (grp), 1 = pt, 2 = col
+  int att_prefetch = 0;  // SPECFEM_B200_ATT_PREFETCH: L2 prefetch distance of the viscoelastic row kernel (AttGrpArgs::pf_dist)
   int acoustic_kernel_variant = 0;  // SPECFEM_B200_ACOUSTIC_KERNEL: 0 = row kernel (default), 1 = one element per CTA, n >= 2: prefetch kernel
   long long kernel_launches = 0;
   // optional per-kernel device timing (specfem_b200_kernel_timing): CUDA event pairs around the named launches

@@ -43,6 +43,7 @@ struct AttGrpArgs {
   const realw* veloc;
   realw* att;      // [ngroups][5][ATR_ROWS][128]
   realw deltat;
+  int pf_dist;     // L2 prefetch: 0 = the whole next group at once, d > 0 = chunk by chunk, d chunks ahead of the ring, < 0 = none
 };
 
 // per-element attenuation arrays of the ABI side: R_* / factor_common* [NSPEC][N_SLS][128], epsilondev_* [NSPEC][128]
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(GRP_THREADS, 2) k_elastic_forces_att_row(const
       for (int g = a.first_group + blockIdx.x; g < a.end_group; g += gridDim.x, ++n) {
         if (g + (int)gridDim.x < a.end_group) {
           fetch_ib(n + 1, g + gridDim.x);
-          prefetch_group(g + gridDim.x);
+          if (aa.pf_dist == 0) prefetch_group(g + gridDim.x);
         }
         const int kind = __ldg(a.ibool + (size_t)g * GRP_IB_WORDS + GRP_KIND_LANE);
         const int narr = kind ? GRP_NARR_IRR : GRP_NARR_REG;
@@ -167,6 +168,16 @@ __global__ void __launch_bounds__(GRP_THREADS, 2) k_elastic_forces_att_row(const
           bulk_g2s_hint(smem_u32(s_p + sP * ATR_STAGE_WORDS), src + (size_t)k * narr * GRP_ROW, bytes, fullP(sP), pol);
           bulk_g2s_hint(smem_u32(s_p + sP * ATR_STAGE_WORDS + GRP_CHUNK_WORDS), asrc + (size_t)k * ATR_CHUNK_WORDS,
                         ATR_CHUNK_WORDS * 4, fullP(sP), pol);
+          if (aa.pf_dist > 0) {  // the chunk the ring will ask for STAGES + pf_dist - 1 slots from now
+            int kp = k + STAGES + aa.pf_dist - 1, gp = g;
+            if (kp >= 5) { kp -= 5; gp += gridDim.x; }
+            if (gp < a.end_group) {
+              const int kd = gp == g ? kind : __ldg(a.ibool + (size_t)gp * GRP_IB_WORDS + GRP_KIND_LANE);
+              const int na = kd ? GRP_NARR_IRR : GRP_NARR_REG;
+              bulk_prefetch_l2(a.params + ((size_t)__ldg(a.row0 + gp) + (size_t)kp * na) * GRP_ROW, na * GRP_ROW * 4);
+              bulk_prefetch_l2(aa.att + ((size_t)gp * 5 + kp) * ATR_CHUNK_WORDS, ATR_CHUNK_WORDS * 4);
+            }
+          }
         }
       }
     }

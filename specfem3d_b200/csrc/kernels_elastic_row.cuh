@@ -85,7 +85,9 @@ __device__ __forceinline__ void row_plane_weak(realw* s_A, const realw* s_B, con
     }
 }
 
-template <int STAGES, int MAXREG>
+// PF: the producer pulls chunks 3 and 4 of a group into L2 when it requests the first three (the ring asks for them only
+// while P2 of that group is already running)
+template <int STAGES, int MAXREG, bool PF = false>
 __global__ void __launch_bounds__(GRP_THREADS) __maxnreg__(MAXREG) k_elastic_forces_row(const GrpArgs a) {
   constexpr int RS = ROW_STRIDE;  // words per (comp,k) tile row
   const size_t cs = vstride(a.nglob);  // distance between the components of one point (kernels_common.cuh)
@@ -130,6 +132,7 @@ __global__ void __launch_bounds__(GRP_THREADS) __maxnreg__(MAXREG) k_elastic_for
         const int narr = kind ? GRP_NARR_IRR : GRP_NARR_REG;
         const uint32_t bytes = narr * GRP_ROW * 4;
         const realw* src = a.params + (size_t)__ldg(a.row0 + g) * GRP_ROW;
+        if (PF && STAGES < 5) bulk_prefetch_l2(src + (size_t)STAGES * narr * GRP_ROW, (5 - STAGES) * bytes);
 #pragma unroll 1
         for (int k = 0; k < 5; ++k) {
           const int q = n * 5 + k, sP = q % STAGES;
@@ -314,41 +317,21 @@ __global__ void __launch_bounds__(GRP_THREADS) __maxnreg__(MAXREG) k_elastic_for
   }
 }
 
-template <int STAGES, int MAXREG>
+template <int STAGES, int MAXREG, bool PF = false>
 inline void launch_elastic_row_t(DeviceMesh* mp, const GrpArgs& a, int ng) {
   static int ctas[64] = {0};
   int& occ = ctas[mp->device & 63];
   if (!occ) {
-    CUDA_CHECK(cudaFuncSetAttribute(k_elastic_forces_row<STAGES, MAXREG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_CHECK(cudaFuncSetAttribute(k_elastic_forces_row<STAGES, MAXREG, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     ROW_SMEM_BYTES(STAGES)));
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_elastic_forces_row<STAGES, MAXREG>, GRP_THREADS,
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_elastic_forces_row<STAGES, MAXREG, PF>, GRP_THREADS,
                                                              ROW_SMEM_BYTES(STAGES)));
     if (occ < 1) exit_on_error("k_elastic_forces_row does not fit on an SM");
     if (getenv("SPECFEM_B200_VERBOSE")) fprintf(stderr, "k_elastic_forces_row<%d,%d>: %d CTAs per SM\n", STAGES, MAXREG, occ);
   }
   int grid = mp->num_sms * occ;  // persistent: every resident CTA slot of the device, once
   if (ng < grid) grid = ng;
-  k_elastic_forces_row<STAGES, MAXREG><<<grid, GRP_THREADS, ROW_SMEM_BYTES(STAGES), mp->compute_stream>>>(a);
-}
-
-inline void launch_elastic_grp(DeviceMesh* mp, const GroupStore* gs, int segment, int use_atomics) {
-  GrpArgs a;
-  a.first_group = gs->seg_first[segment];
-  a.end_group = gs->seg_end[segment];
-  const int ng = a.end_group - a.first_group;
-  if (ng <= 0) return;
-  a.ibool = gs->d_ibool;
-  a.params = gs->d_params;
-  a.row0 = gs->d_row0;
-  a.displ = mp->d_displ;
-  a.accel = mp->d_accel;
-  a.xix_regular = mp->xix_regular;
-  a.jacobian_regular = mp->jacobian_regular;
-  a.use_atomics = use_atomics;
-  a.nglob = (size_t)mp->NGLOB_AB;
-  KernelTimer timer(mp, "elastic_forces");
-  // 72 registers keep five CTAs (25 warps) resident per SM; at 80 (no spill) only four fit and the kernel is slower
-  launch_elastic_row_t<3, 72>(mp, a, ng);
+  k_elastic_forces_row<STAGES, MAXREG, PF><<<grid, GRP_THREADS, ROW_SMEM_BYTES(STAGES), mp->compute_stream>>>(a);
 }
 
 }  // namespace sb200

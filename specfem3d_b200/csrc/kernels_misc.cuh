@@ -102,6 +102,58 @@ __global__ void __launch_bounds__(256) k_newmark_corrector_predictor(realw* __re
   }
 }
 
+// Same pass with the COMPACT inverse mass matrix (one plane instead of three: 76 instead of 84 bytes per point).  rmassx, rmassy
+// and rmassz differ only on the absorbing boundary (the Stacey terms, create_mass_matrices.f90: create_mass_matrices_Stacey_duplication_routine),
+// so the library keeps one plane rmass_c[NGLOB] and, for the points where the three differ, a table: rmass_c[p] = -(e + 1) (an
+// inverse mass is positive) points at rmass_exc[c * nexc + e].  Same expressions and order as above: bit-identical wavefields.
+// One point (three components) per thread and iteration, scalar coalesced accesses (the component planes start at multiples of
+// NGLOB words, which need not be 16-byte aligned), four points in flight per thread.
+__global__ void __launch_bounds__(256) k_newmark_corrector_predictor_c(realw* __restrict__ displ, realw* __restrict__ veloc,
+                                                                       realw* __restrict__ accel, const realw* __restrict__ rmass_c,
+                                                                       const realw* __restrict__ rmass_exc, long long nexc,
+                                                                       long long nglob, realw corr_deltatover2, realw deltat,
+                                                                       realw deltatsqover2, realw deltatover2) {
+  constexpr int U = 4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long p0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; p0 < nglob; p0 += U * stride) {
+    realw r[U], a[U][3], v[U][3], d[U][3];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long p = p0 + u * stride;
+      if (p < nglob) {
+        r[u] = __ldg(rmass_c + p);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          a[u][c] = accel[c * nglob + p];
+          v[u][c] = veloc[c * nglob + p];
+          d[u][c] = displ[c * nglob + p];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long p = p0 + u * stride;
+      if (p < nglob) {
+        realw rc[3] = {r[u], r[u], r[u]};
+        if (r[u] < 0.f) {
+          const long long e = (long long)(-r[u]) - 1;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) rc[c] = __ldg(rmass_exc + c * nexc + e);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const realw ac = a[u][c] * rc[c];
+          realw vc = v[u][c];
+          vc += corr_deltatover2 * ac;
+          displ[c * nglob + p] = d[u][c] + deltat * vc + deltatsqover2 * ac;
+          veloc[c * nglob + p] = vc + deltatover2 * ac;
+          accel[c * nglob + p] = 0.f;
+        }
+      }
+    }
+  }
+}
+
 // veloc += dt/2 * accel only (kernel_3_veloc_cuda_device, used by kernel_3_b_cuda after the ocean-load correction)
 __global__ void __launch_bounds__(256) k_newmark_veloc_only(realw* __restrict__ veloc, const realw* __restrict__ accel,
                                                             long long n, realw deltatover2) {

@@ -13,6 +13,7 @@
 #include "group_store.cuh"
 #include "renumber.h"
 #include "kernels_elastic_row.cuh"
+#include "kernels_elastic_rownp.cuh"
 #include "kernels_acoustic_row.cuh"
 #include "kernels_elastic_att_row.cuh"
 #include "kernels_elastic_kl_row.cuh"
@@ -332,6 +333,7 @@ extern "C" void SB200_FC(prepare_constants_device)(
   const char* fk = getenv("SPECFEM_B200_FORCE_KERNEL");
   if (fk) mp->force_kernel_variant = atoi(fk);
   if (const char* ak = getenv("SPECFEM_B200_ACOUSTIC_KERNEL")) mp->acoustic_kernel_variant = atoi(ak);
+  if (const char* ap = getenv("SPECFEM_B200_ATT_PREFETCH")) mp->att_prefetch = atoi(ap);
   const char* fn = getenv("SPECFEM_B200_FUSE_NEWMARK");
   if (fn) mp->fuse_newmark = atoi(fn);
   if (const char* ps = getenv("SPECFEM_B200_PRODUCER_SLEEP")) {
@@ -385,6 +387,32 @@ extern "C" void SB200_FC(prepare_fields_elastic_device)(
       r3[vidx(q, 2, nglob)] = rmassz[i];
     }
     mp->d_rmassx = dev_copy(r3.data(), r3.size());  // d_rmassx holds all three
+    // compact copy for the fused Newmark pass (kernels_misc.cuh: k_newmark_corrector_predictor_c): one plane, and a table for
+    // the points whose three inverse masses differ (absorbing boundary).  Needs SB200_SOA and fewer than 2^24 such points
+    // (their index is carried by a float); SPECFEM_B200_COMPACT_MASS=0 keeps the three planes.
+    const char* cm = getenv("SPECFEM_B200_COMPACT_MASS");
+    if (SB200_SOA && !(cm && atoi(cm) == 0)) {
+      std::vector<realw> rc(nglob), ex[3];
+      bool ok = true;
+      for (size_t i = 0; i < nglob && ok; ++i) {
+        const size_t q = mp->h_perm[i];
+        if (rmassx[i] == rmassz[i] && rmassy[i] == rmassz[i] && rmassz[i] >= 0.f) {
+          rc[q] = rmassz[i];
+        } else {
+          if (ex[0].size() >= (1u << 24) - 1) ok = false;
+          rc[q] = -(realw)(ex[0].size() + 1);
+          ex[0].push_back(rmassx[i]); ex[1].push_back(rmassy[i]); ex[2].push_back(rmassz[i]);
+        }
+      }
+      if (ok) {
+        mp->rmass_nexc = (long long)ex[0].size();
+        std::vector<realw> flat;
+        for (int c = 0; c < 3; ++c) flat.insert(flat.end(), ex[c].begin(), ex[c].end());
+        if (flat.empty()) flat.push_back(0.f);
+        mp->d_rmass_c = dev_copy(rc.data(), rc.size());
+        mp->d_rmass_exc = dev_copy(flat.data(), flat.size());
+      }
+    }
   }
   mp->num_phase_ispec_elastic = *num_phase_ispec_elastic;
   mp->d_phase_ispec_inner_elastic = dev_copy(phase_ispec_inner_elastic, 2 * (size_t)mp->num_phase_ispec_elastic);
@@ -535,6 +563,8 @@ extern "C" void SB200_FC(prepare_cleanup_device)(long* Mesh_pointer, int* ACOUST
   p2p_check_error(mp);
   p2p_destroy(mp);
   dev_free(mp->d_perm);
+  dev_free(mp->d_rmass_c);
+  dev_free(mp->d_rmass_exc);
   pml_destroy(mp);
   group_store_free(mp->grp_elastic);
   group_store_free(mp->grp_acoustic);
@@ -751,9 +781,15 @@ extern "C" void SB200_FC(update_displacement_cuda)(long* Mesh_pointer, realw* de
     require_backward_fields(mp, "update_displacement_cuda");
     if (mp->b_corrector_pending) {  // deferred corrector of the previous step and this predictor in one pass
       mp->b_corrector_pending = false;
-      k_newmark_corrector_predictor<<<streaming_grid(n >> 2), 256, 0, mp->compute_stream>>>(
-          mp->d_b_displ, mp->d_b_veloc, mp->d_b_accel, mp->d_rmassx, n, mp->pending_b_deltatover2, *deltat_F, *deltatsqover2_F,
-          *deltatover2_F);
+      if (mp->d_rmass_c) {
+        k_newmark_corrector_predictor_c<<<streaming_grid(((long long)mp->NGLOB_AB + 3) >> 2), 256, 0, mp->compute_stream>>>(
+            mp->d_b_displ, mp->d_b_veloc, mp->d_b_accel, mp->d_rmass_c, mp->d_rmass_exc, mp->rmass_nexc, (long long)mp->NGLOB_AB,
+            mp->pending_b_deltatover2, *deltat_F, *deltatsqover2_F, *deltatover2_F);
+      } else {
+        k_newmark_corrector_predictor<<<streaming_grid(n >> 2), 256, 0, mp->compute_stream>>>(
+            mp->d_b_displ, mp->d_b_veloc, mp->d_b_accel, mp->d_rmassx, n, mp->pending_b_deltatover2, *deltat_F, *deltatsqover2_F,
+            *deltatover2_F);
+      }
       KERNEL_CHECK(mp, "k_newmark_corrector_predictor(backward)");
       return;
     }
@@ -766,8 +802,14 @@ extern "C" void SB200_FC(update_displacement_cuda)(long* Mesh_pointer, realw* de
     // the corrector kernel_3_a_cuda deferred at the end of the previous step and this predictor in one pass
     mp->corrector_pending = false;
     KernelTimer timer(mp, "newmark");
-    k_newmark_corrector_predictor<<<streaming_grid(n >> 2), 256, 0, mp->compute_stream>>>(
-        mp->d_displ, mp->d_veloc, mp->d_accel, mp->d_rmassx, n, mp->pending_deltatover2, *deltat_F, *deltatsqover2_F, *deltatover2_F);
+    if (mp->d_rmass_c) {
+      k_newmark_corrector_predictor_c<<<streaming_grid(((long long)mp->NGLOB_AB + 3) >> 2), 256, 0, mp->compute_stream>>>(
+          mp->d_displ, mp->d_veloc, mp->d_accel, mp->d_rmass_c, mp->d_rmass_exc, mp->rmass_nexc, (long long)mp->NGLOB_AB,
+          mp->pending_deltatover2, *deltat_F, *deltatsqover2_F, *deltatover2_F);
+    } else {
+      k_newmark_corrector_predictor<<<streaming_grid(n >> 2), 256, 0, mp->compute_stream>>>(
+          mp->d_displ, mp->d_veloc, mp->d_accel, mp->d_rmassx, n, mp->pending_deltatover2, *deltat_F, *deltatsqover2_F, *deltatover2_F);
+    }
     KERNEL_CHECK(mp, "k_newmark_corrector_predictor");
     return;
   }
@@ -985,6 +1027,7 @@ static void launch_elastic_att_grp(DeviceMesh* mp, int segment, realw deltat, in
   aa.veloc = mp->d_veloc;
   aa.att = gs->d_att;
   aa.deltat = deltat;
+  aa.pf_dist = mp->att_prefetch;
   KernelTimer timer(mp, "elastic_forces_attenuation");
   launch_elastic_att_row(mp, aa, ng);
 }
@@ -1101,7 +1144,7 @@ extern "C" void SB200_FC(compute_forces_viscoelastic_cuda)(long* Mesh_pointer, i
     }
     return;
   }
-  const bool att_grp = mp->force_kernel_variant == 0 && mp->attenuation;  // viscoelastic row kernel + attenuation store
+  const bool att_grp = mp->force_kernel_variant != 1 && mp->attenuation;  // viscoelastic row kernel + attenuation store
   if (num_elements > 0 && att_grp) {
     ensure_elastic_groups(mp, *nspec_outer_elastic, *nspec_inner_elastic);
     if (mp->use_mesh_coloring_gpu) {
@@ -1118,7 +1161,7 @@ extern "C" void SB200_FC(compute_forces_viscoelastic_cuda)(long* Mesh_pointer, i
     if (mp->pml_conditions && mp->NSPEC_CPML > 0) pml_compute_forces(mp, *iphase, *nspec_outer_elastic, *nspec_inner_elastic);
     return;
   }
-  const bool grp = mp->force_kernel_variant == 0 && !mp->attenuation && !mp->compute_and_store_strain;
+  const bool grp = mp->force_kernel_variant != 1 && !mp->attenuation && !mp->compute_and_store_strain;
   if (num_elements > 0 && grp) {
     ensure_elastic_groups(mp, *nspec_outer_elastic, *nspec_inner_elastic);
     if (mp->use_mesh_coloring_gpu) {

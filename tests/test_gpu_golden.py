@@ -157,3 +157,51 @@ def test_config2_size_parity_with_oracle(device_lib):
         e = rel_l2(g, c)
         print(f"config 2, three full steps: {name} relative L2 vs oracle = {e:.3e}")
         assert e <= 2e-5, (name, e)
+
+
+def test_database_files_to_gpu_to_seismogram_files_chain(device_lib, tmp_path):
+    """SURVEY section 8(f) ranks 1 and 2 end to end on the device: config 1 on 2 x 2 ranks is written as
+    proc%06d_external_mesh.bin files (save_arrays_solver.F90 record order), read back, prepared the way the solver does after
+    read_mesh_databases, run on the GPU through the C ABI, and its seismograms are written as NET.STA.BXc.semd files.  Those
+    files are compared with the REF_SEIS traces (written in the same format from the golden fixture) with the three numbers of
+    the reference's utils/scripts/compare_seismogram_correlations.py; its CI accepts corr >= 0.999, here the north-star 1e-4
+    relative L2 is asserted as well (first 1000 samples: body and surface waves)."""
+    from specfem3d_b200.configs import CMT_DEFAULT, STATIONS_DEFAULT, cfg1
+    from specfem3d_b200.databases import (DatabaseFlags, mass_records, read_external_mesh, simulation_from_databases,
+                                          write_external_mesh)
+    from specfem3d_b200.seismograms import compare_with_reference, write_seismograms, _fortran_real
+    from specfem3d_b200.time_loop import DeviceRun
+
+    NSTEP = 1000
+    sim = cfg1(2, 2, NSTEP)
+    spec, flags = sim.spec, DatabaseFlags()
+    back = []
+    for db in sim.dbs:
+        path = str(tmp_path / f"proc{db.myrank:06d}_external_mesh.bin")
+        write_external_mesh(path, db, spec, flags, mass_records(spec, db, sim.DT, sim.gll))
+        back.append(read_external_mesh(path, flags, db.myrank, spec.nproc))
+    sim2 = simulation_from_databases(back, spec, sim.DT, NSTEP, sources=[CMT_DEFAULT], stations=STATIONS_DEFAULT)
+    run = DeviceRun(sim2)
+    for _ in range(NSTEP):
+        run.step()
+    sd = run.gather_seismograms("d")
+    run.cleanup()
+    syn_dir, ref_dir = str(tmp_path / "OUTPUT_FILES"), str(tmp_path / "REF_SEIS")
+    paths = write_seismograms(sim2, sd, syn_dir, "d")
+    assert len(paths) == 12 and os.path.basename(paths[0]) == "DB.X20.BXX.semd"
+    gold = np.load(os.path.join(GOLD, "halfspace_ref_seis.npz"))
+    os.makedirs(ref_dir)
+    for st in ("X20", "X30", "X40", "X50"):
+        for ch in "XYZ":
+            with open(os.path.join(ref_dir, f"DB.{st}.BX{ch}.semd"), "w") as f:
+                for ti, vi in zip(gold["time"][:NSTEP], gold[f"{st}_{ch}"][:NSTEP]):
+                    f.write(f"  {_fortran_real(ti):>12}     {_fortran_real(vi):>16}\n")
+    res = compare_with_reference(syn_dir, ref_dir)
+    print("files chain, per trace:", {k: (f"{v['corr']:.6f}", f"{v['rel_l2']:.2e}", v["shift"]) for k, v in res.items()})
+    assert len(res) == 12
+    for name, m in res.items():
+        assert m["corr"] >= 0.999 and m["shift"] == 0, (name, m)
+        assert m["rel_l2"] <= 1e-4, (name, m)
+    # the time column of the written files is the reference's
+    t_syn = np.loadtxt(paths[0])[:, 0]
+    assert np.allclose(t_syn, gold["time"][:NSTEP], atol=1e-4)

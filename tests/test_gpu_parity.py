@@ -62,7 +62,11 @@ def small_sim(deform=0.15, regular=False, nproc=(1, 1), nstep=60, nex=(6, 6, 4),
 
 
 # -------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("variant", [1, 0])  # 1 = one-thread-per-point kernel, 0 = default (row / plane-owner) kernel
+# 1 = one-thread-per-point kernel, 0 = default (row / plane-owner) kernel; SPECFEM_B200_TEST_FORCE_VARIANTS adds A/B variants
+_FORCE_VARIANTS = [1, 0] + [int(v) for v in os.environ.get("SPECFEM_B200_TEST_FORCE_VARIANTS", "").split(",") if v]
+
+
+@pytest.mark.parametrize("variant", _FORCE_VARIANTS)
 @pytest.mark.parametrize("regular", [False, True])
 def test_elastic_force_kernel_matches_oracle(device_lib, variant, regular):
     """a1: one call of compute_forces_viscoelastic_cuda (both phases) vs oracle_compute_forces_viscoelastic."""
