@@ -45,7 +45,9 @@ BYTES_PER_ELEMENT_FORCE_REGULAR = 3804
 BYTES_PER_ELEMENT_ATTENUATION = 36072     # SURVEY.md section 8d (irregular element, 3 SLS)
 BYTES_PER_ELEMENT_ACOUSTIC = 6268
 BYTES_PER_ELEMENT_PML = 82300             # DESIGN.md section 4 (48 memory planes r+w, 41 coefficient planes, ...)
-BYTES_PER_ELEMENT_NEWMARK_FUSED = 5376    # 84 B per point x 64 points per element
+# 76 B per point (compact inverse mass matrix: one plane + a table for the absorbing-boundary points) x 64 points per element;
+# 84 B with SPECFEM_B200_COMPACT_MASS=0 (three planes)
+BYTES_PER_ELEMENT_NEWMARK_FUSED = 5376 if os.environ.get("SPECFEM_B200_COMPACT_MASS") == "0" else 4864
 
 
 def workload_text(nex, nspec_total):
@@ -446,13 +448,13 @@ def run_device(args):
                     "d2h_bytes_per_step": 4 * 148 * 4,
                     "note": "K steps through the C ABI from host buffers: per-step stf upload + blocking norm readback; host wall clock"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "k_elastic_forces_row (compute_forces_viscoelastic_cuda, outer + inner phase)",
+            "roofline": {"bound": "hbm", "kernel": "k_elastic_forces_rownp (compute_forces_viscoelastic_cuda, outer + inner phase)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_element": bytes_per_el,
                          "elements_per_step": nel, "launches_per_step": f_cnt / k2, "kernel_ms": k_ms,
                          "timed": f"CUDA events on the library's compute stream around every launch of {k2} consecutive time steps",
                          "elements_per_s": nel / (k_ms * 1e-3)},
-            "newmark": {"kernel": "k_newmark_corrector_predictor (deferred corrector + predictor)", "kernel_ms": newmark_ms,
+            "newmark": {"kernel": "k_newmark_corrector_predictor_c (deferred corrector + predictor, compact inverse mass matrix)", "kernel_ms": newmark_ms,
                         "achieved": nel * BYTES_PER_ELEMENT_NEWMARK_FUSED / (newmark_ms * 1e-3) / 1e9 if newmark_ms > 0 else None,
                         "unit": "GB/s", "algorithmic_bytes_per_element": BYTES_PER_ELEMENT_NEWMARK_FUSED},
             "clocks": clocks,
@@ -675,7 +677,8 @@ def cpu_baseline_sample(sim, seconds: float = 15.0):
     t0 = time.perf_counter()
     o.step()  # warm-up / page-in
     t_first = time.perf_counter() - t0
-    nsteps = max(1, min(20, int(seconds / max(t_first, 1e-3))))
+    # the run records one seismogram sample per step: stay inside the NSTEP the simulation was built for
+    nsteps = max(1, min(20, int(seconds / max(t_first, 1e-3)), int(sim.NSTEP) - 2))
     t0 = time.perf_counter()
     for _ in range(nsteps):
         o.step()

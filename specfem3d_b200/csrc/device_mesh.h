@@ -217,7 +217,8 @@ struct DeviceMesh {
 
   // options
   int force_kernel_variant = 0;  // 0 = default (grp), 1 = pt, 2 = col
-  int att_prefetch = 0;  // SPECFEM_B200_ATT_PREFETCH: L2 prefetch distance of the viscoelastic row kernel (AttGrpArgs::pf_dist)
+  int kl_kernel_variant = 0;  // SPECFEM_B200_KL_KERNEL: 1 = two-wavefield row kernel without the producer warp (A/B)
+  int att_prefetch = 3;  // SPECFEM_B200_ATT_PREFETCH: L2 prefetch distance of the viscoelastic row kernel (AttGrpArgs::pf_dist)
   int acoustic_kernel_variant = 0;  // SPECFEM_B200_ACOUSTIC_KERNEL: 0 = row kernel (default), 1 = one element per CTA, n >= 2: prefetch kernel
   long long kernel_launches = 0;
   // optional per-kernel device timing (specfem_b200_kernel_timing): CUDA event pairs around the named launches

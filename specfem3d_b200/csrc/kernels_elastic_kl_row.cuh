@@ -16,7 +16,7 @@
 // (round 1: 6.25 ms = 0.33).  The anisotropic (21 cijkl planes) and approximate-Hessian accumulations keep using
 // k_elastic_forces_kl_pair.
 #pragma once
-#include "kernels_elastic_row.cuh"
+#include "kernels_elastic_rownp.cuh"
 
 namespace sb200 {
 
@@ -35,8 +35,10 @@ struct KlGrpArgs {
   realw deltat;
 };
 
-template <int STAGES, int MINB>
-__global__ void __launch_bounds__(GRP_THREADS, MINB) k_elastic_forces_kl_row(const KlGrpArgs aa) {
+// NP: no producer warp (kernels_elastic_rownp.cuh): the warp whose arrival frees a ring slot refills it, thread 0 requests the
+// next index slab after B1; 128 threads per CTA, so four CTAs fit per SM where the producer version holds three.
+template <int STAGES, int MINB, bool NP = false>
+__global__ void __launch_bounds__(NP ? GRP_CONSUMERS : GRP_THREADS, MINB) k_elastic_forces_kl_row(const KlGrpArgs aa) {
   const GrpArgs& a = aa.g;
   constexpr int RS = ROW_STRIDE;
   const size_t cs = vstride(a.nglob);
@@ -52,6 +54,24 @@ __global__ void __launch_bounds__(GRP_THREADS, MINB) k_elastic_forces_kl_row(con
   const uint32_t fullI = bars + 8u * (2 * STAGES), emptyI = bars + 8u * (2 * STAGES + 1);
 
   const int tid = threadIdx.x;
+  // NP: request chunk kq of a group (first parameter row row0g, kind kindg) into ring slot `slot`; the next index slab
+  auto issue_chunk = [&](int slot, unsigned row0g, int kindg, int kq) {
+    const int narr = kindg ? GRP_NARR_IRR : GRP_NARR_REG;
+    const uint32_t bytes = narr * GRP_ROW * 4;
+    mbar_expect_tx(fullP(slot), bytes);
+    bulk_g2s_hint(smem_u32(s_p + slot * GRP_CHUNK_WORDS), a.params + ((size_t)row0g + (size_t)kq * narr) * GRP_ROW, bytes, fullP(slot),
+                  l2_policy_evict_first());
+  };
+  auto issue_slab = [&](int gq) {
+    mbar_expect_tx(fullI, GRP_IB_WORDS * 4);
+    bulk_g2s_hint(smem_u32(s_ib), a.ibool + (size_t)gq * GRP_IB_WORDS, GRP_IB_WORDS * 4, fullI, l2_policy_evict_first());
+  };
+  unsigned cur_row0 = 0, nxt_row0 = 0;
+  int cur_kind = 0, nxt_kind = 0;
+  if (NP) {
+    cur_row0 = __ldg(a.row0 + a.first_group + blockIdx.x);
+    cur_kind = __ldg(a.ibool + (size_t)(a.first_group + blockIdx.x) * GRP_IB_WORDS + GRP_KIND_LANE);
+  }
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(fullP(s), 1);
@@ -61,6 +81,11 @@ __global__ void __launch_bounds__(GRP_THREADS, MINB) k_elastic_forces_kl_row(con
     mbar_init(emptyI, GRP_CONSUMERS / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (NP) {
+      issue_slab(a.first_group + blockIdx.x);
+#pragma unroll
+      for (int s = 0; s < STAGES; ++s) issue_chunk(s, cur_row0, cur_kind, s);
+    }
   }
   if (tid < NGLL2) {
     s_w[tid] = c_wgllwgll_yz[tid];          // [k*5 + j]
@@ -69,7 +94,7 @@ __global__ void __launch_bounds__(GRP_THREADS, MINB) k_elastic_forces_kl_row(con
   __syncthreads();
 
   // ------------------------------------------------------------------------------------------------ producer warp
-  if (tid >= GRP_CONSUMERS) {
+  if (!NP && tid >= GRP_CONSUMERS) {
     if (tid == GRP_CONSUMERS) {
       const uint64_t pol = l2_policy_evict_first();
       int n = 0;
@@ -107,6 +132,12 @@ __global__ void __launch_bounds__(GRP_THREADS, MINB) k_elastic_forces_kl_row(con
 
   int n = 0;
   for (int g = a.first_group + blockIdx.x; g < a.end_group; g += gridDim.x, ++n) {
+    const int gnext = g + (int)gridDim.x;
+    const bool has_next = gnext < a.end_group;
+    if (NP && has_next) {
+      nxt_row0 = __ldg(a.row0 + gnext);
+      nxt_kind = __ldg(a.ibool + (size_t)gnext * GRP_IB_WORDS + GRP_KIND_LANE);
+    }
     // ---- P0: indices, gather of both wavefields, tiles, gamma-direction derivatives ----
     mbar_wait(fullI, n & 1);
     int ig[5];
@@ -114,7 +145,7 @@ __global__ void __launch_bounds__(GRP_THREADS, MINB) k_elastic_forces_kl_row(con
     for (int k = 0; k < 5; ++k) ig[k] = lane_ok ? s_ib[k * GRP_ROW + t] - 1 : -1;
     const int kind = s_ib[GRP_KIND_LANE];
     __syncwarp();
-    if (lane == 0) mbar_arrive(emptyI);
+    if (!NP && lane == 0) mbar_arrive(emptyI);
     const bool valid = ig[0] >= 0;
     // this lane's element and first point (k = 0) in the per-element kernel arrays
     const size_t kl_off = valid ? (size_t)__ldg(aa.slot_ispec + (size_t)g * GRP_ELEMS + el) * NGLL3_PADDED + j * NGLLX + i : 0;
@@ -150,6 +181,7 @@ __global__ void __launch_bounds__(GRP_THREADS, MINB) k_elastic_forces_kl_row(con
         }
     }
     consumer_bar_sync();  // B1
+    if (NP && t == 0 && has_next) issue_slab(gnext);  // every thread has read its indices
 
     // ---- P1: in-plane derivatives of both wavefields (two rounds of 75 plane-owner tasks) ----
     if (plane_task) {
@@ -187,7 +219,13 @@ __global__ void __launch_bounds__(GRP_THREADS, MINB) k_elastic_forces_kl_row(con
         jacobianl = a.jacobian_regular;
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(emptyP(sP));  // the parameters are in registers: ring slot consumed by this warp
+      if (!NP) {
+        if (lane == 0) mbar_arrive(emptyP(sP));  // the parameters are in registers: ring slot consumed by this warp
+      } else if (lane == 0 && mbar_arrive_pending(emptyP(sP)) == 1) {  // last of the four warps: refill the slot
+        const int kk = k + STAGES;
+        if (kk < 5) issue_chunk(sP, cur_row0, cur_kind, kk);
+        else if (has_next) issue_chunk(sP, nxt_row0, nxt_kind, kk - 5);
+      }
       const realw lambdalplus2mul = kappal + 1.33333333333333333333f * mul;
       const realw lambdal = lambdalplus2mul - 2.0f * mul;
       realw e[2][6];  // deviatoric strain xx, yy, xy, xz, yz and trace / 3 of the two wavefields
@@ -278,26 +316,31 @@ __global__ void __launch_bounds__(GRP_THREADS, MINB) k_elastic_forces_kl_row(con
         }
       }
     }
+    cur_row0 = nxt_row0;
+    cur_kind = nxt_kind;
   }
 }
 
-template <int ST, int MINB>
+template <int ST, int MINB, bool NP = false>
 inline void launch_elastic_kl_row_t(DeviceMesh* mp, const KlGrpArgs& aa, int ng) {
+  constexpr int NT = NP ? GRP_CONSUMERS : GRP_THREADS;
   static int ctas[64] = {0};
   int& occ = ctas[mp->device & 63];
   if (!occ) {
-    CUDA_CHECK(cudaFuncSetAttribute(k_elastic_forces_kl_row<ST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, KLR_SMEM_BYTES(ST)));
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_elastic_forces_kl_row<ST, MINB>, GRP_THREADS, KLR_SMEM_BYTES(ST)));
+    CUDA_CHECK(cudaFuncSetAttribute(k_elastic_forces_kl_row<ST, MINB, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, KLR_SMEM_BYTES(ST)));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_elastic_forces_kl_row<ST, MINB, NP>, NT, KLR_SMEM_BYTES(ST)));
     if (occ < 1) exit_on_error("k_elastic_forces_kl_row does not fit on an SM");
-    if (getenv("SPECFEM_B200_VERBOSE")) fprintf(stderr, "k_elastic_forces_kl_row<%d,%d>: %d CTAs per SM\n", ST, MINB, occ);
+    if (getenv("SPECFEM_B200_VERBOSE")) fprintf(stderr, "k_elastic_forces_kl_row<%d,%d,%d>: %d CTAs per SM\n", ST, MINB, (int)NP, occ);
   }
   int grid = mp->num_sms * occ;
   if (ng < grid) grid = ng;
-  k_elastic_forces_kl_row<ST, MINB><<<grid, GRP_THREADS, KLR_SMEM_BYTES(ST), mp->compute_stream>>>(aa);
+  k_elastic_forces_kl_row<ST, MINB, NP><<<grid, NT, KLR_SMEM_BYTES(ST), mp->compute_stream>>>(aa);
 }
 inline void launch_elastic_kl_row(DeviceMesh* mp, const KlGrpArgs& aa, int ng) {
   // 3-stage ring, 125 registers, 3 CTAs / SM: 4.40 ms per 1M elements; 2-stage ring, 96 registers (76 B spilled), 4 CTAs: 4.91 ms
-  launch_elastic_kl_row_t<3, 3>(mp, aa, ng);
+  // without the producer warp four CTAs fit per SM (119 registers) -- and the kernel is slower: 4.80 ms (profiles/r02x_*)
+  if (mp->kl_kernel_variant == 1) launch_elastic_kl_row_t<3, 4, true>(mp, aa, ng);  // SPECFEM_B200_KL_KERNEL=1 (A/B)
+  else launch_elastic_kl_row_t<3, 3>(mp, aa, ng);
 }
 
 }  // namespace sb200

@@ -85,9 +85,7 @@ __device__ __forceinline__ void row_plane_weak(realw* s_A, const realw* s_B, con
     }
 }
 
-// PF: the producer pulls chunks 3 and 4 of a group into L2 when it requests the first three (the ring asks for them only
-// while P2 of that group is already running)
-template <int STAGES, int MAXREG, bool PF = false>
+template <int STAGES, int MAXREG>
 __global__ void __launch_bounds__(GRP_THREADS) __maxnreg__(MAXREG) k_elastic_forces_row(const GrpArgs a) {
   constexpr int RS = ROW_STRIDE;  // words per (comp,k) tile row
   const size_t cs = vstride(a.nglob);  // distance between the components of one point (kernels_common.cuh)
@@ -132,7 +130,6 @@ __global__ void __launch_bounds__(GRP_THREADS) __maxnreg__(MAXREG) k_elastic_for
         const int narr = kind ? GRP_NARR_IRR : GRP_NARR_REG;
         const uint32_t bytes = narr * GRP_ROW * 4;
         const realw* src = a.params + (size_t)__ldg(a.row0 + g) * GRP_ROW;
-        if (PF && STAGES < 5) bulk_prefetch_l2(src + (size_t)STAGES * narr * GRP_ROW, (5 - STAGES) * bytes);
 #pragma unroll 1
         for (int k = 0; k < 5; ++k) {
           const int q = n * 5 + k, sP = q % STAGES;
@@ -317,21 +314,21 @@ __global__ void __launch_bounds__(GRP_THREADS) __maxnreg__(MAXREG) k_elastic_for
   }
 }
 
-template <int STAGES, int MAXREG, bool PF = false>
+template <int STAGES, int MAXREG>
 inline void launch_elastic_row_t(DeviceMesh* mp, const GrpArgs& a, int ng) {
   static int ctas[64] = {0};
   int& occ = ctas[mp->device & 63];
   if (!occ) {
-    CUDA_CHECK(cudaFuncSetAttribute(k_elastic_forces_row<STAGES, MAXREG, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_CHECK(cudaFuncSetAttribute(k_elastic_forces_row<STAGES, MAXREG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     ROW_SMEM_BYTES(STAGES)));
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_elastic_forces_row<STAGES, MAXREG, PF>, GRP_THREADS,
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_elastic_forces_row<STAGES, MAXREG>, GRP_THREADS,
                                                              ROW_SMEM_BYTES(STAGES)));
     if (occ < 1) exit_on_error("k_elastic_forces_row does not fit on an SM");
     if (getenv("SPECFEM_B200_VERBOSE")) fprintf(stderr, "k_elastic_forces_row<%d,%d>: %d CTAs per SM\n", STAGES, MAXREG, occ);
   }
   int grid = mp->num_sms * occ;  // persistent: every resident CTA slot of the device, once
   if (ng < grid) grid = ng;
-  k_elastic_forces_row<STAGES, MAXREG, PF><<<grid, GRP_THREADS, ROW_SMEM_BYTES(STAGES), mp->compute_stream>>>(a);
+  k_elastic_forces_row<STAGES, MAXREG><<<grid, GRP_THREADS, ROW_SMEM_BYTES(STAGES), mp->compute_stream>>>(a);
 }
 
 }  // namespace sb200

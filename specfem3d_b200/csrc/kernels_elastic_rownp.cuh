@@ -34,10 +34,9 @@ struct RowNpLayout {
   __host__ __device__ static constexpr int smem_bytes(int st) { return off_bars(st) + (2 * st + 1) * 8; }
 };
 
-// ROT: the 75 plane-owner tasks sit on three of the four warps; which three rotates with the CTA and the group, so that the
-// four SM sub-partitions (warp w of every 128-thread CTA lives on sub-partition w) issue the same number of instructions.
-// PF: thread 0 pulls chunks STAGES .. 4 of the group into L2 after B1 (the ring asks for them only during P2).
-template <int STAGES, int MAXREG, int RS, bool ROT = false, bool PF = false>
+// Measured and not kept (profiles/r02w_force_np_ab.jsonl): rotating the 75 plane-owner tasks over the four warps with the CTA
+// and group number (to even out the sub-partitions: 1.968 against 1.921 ms), an L2 prefetch of chunks 3 and 4 after B1 (no change).
+template <int STAGES, int MAXREG, int RS>
 __global__ void __launch_bounds__(GRP_CONSUMERS) __maxnreg__(MAXREG) k_elastic_forces_rownp(const GrpArgs a) {
   using L = RowNpLayout<RS>;
   const size_t cs = vstride(a.nglob);
@@ -92,17 +91,11 @@ __global__ void __launch_bounds__(GRP_CONSUMERS) __maxnreg__(MAXREG) k_elastic_f
   const int i = lane_ok ? t % NGLLX : 0;
   const int lane = t & 31;
   const realw fac3 = c_wgllwgll_xy[j * 5 + i];
-  bool plane_task = t < ROW_TASKS;           // task (row r = comp*5 + k, element e) = (t / 5, t % 5)
-  int task_k = (t / GRP_ELEMS) % NGLLX;
-  int task_base = (t / GRP_ELEMS) * RS + (t % GRP_ELEMS) * NGLLX;
+  const bool plane_task = t < ROW_TASKS;           // task (row r = comp*5 + k, element e) = (t / 5, t % 5)
+  const int task_k = (t / GRP_ELEMS) % NGLLX;
+  const int task_base = (t / GRP_ELEMS) * RS + (t % GRP_ELEMS) * NGLLX;
 
   for (int n = 0; g < a.end_group; g += gridDim.x, ++n) {
-    if (ROT) {
-      const int tt = (t + 32 * ((n + (int)blockIdx.x) & 3)) & 127;  // task of this thread in this iteration
-      plane_task = tt < ROW_TASKS;
-      task_k = (tt / GRP_ELEMS) % NGLLX;
-      task_base = (tt / GRP_ELEMS) * RS + (tt % GRP_ELEMS) * NGLLX;
-    }
     // the next group of this CTA: its first parameter row and kind are needed by whichever warp refills the ring in P2
     const int gnext = g + (int)gridDim.x;
     const bool has_next = gnext < a.end_group;
@@ -139,10 +132,6 @@ __global__ void __launch_bounds__(GRP_CONSUMERS) __maxnreg__(MAXREG) k_elastic_f
     }
     __syncthreads();  // B1: every thread has read its indices, so the slab is free
     if (t == 0 && has_next) issue_slab(gnext);
-    if (PF && STAGES < 5 && t == 32) {
-      const int narr = cur_kind ? GRP_NARR_IRR : GRP_NARR_REG;
-      bulk_prefetch_l2(a.params + ((size_t)cur_row0 + (size_t)STAGES * narr) * GRP_ROW, (5 - STAGES) * narr * GRP_ROW * 4);
-    }
 
     // ---- P1: in-plane derivatives by the plane owners ----
     if (plane_task) row_plane_derivatives(s_A, s_B, task_base);
@@ -278,21 +267,21 @@ __global__ void __launch_bounds__(GRP_CONSUMERS) __maxnreg__(MAXREG) k_elastic_f
   }
 }
 
-template <int STAGES, int MAXREG, int RS, bool ROT = false, bool PF = false>
+template <int STAGES, int MAXREG, int RS>
 inline void launch_elastic_rownp_t(DeviceMesh* mp, const GrpArgs& a, int ng) {
   static int ctas[64] = {0};
   int& occ = ctas[mp->device & 63];
   constexpr int smem = RowNpLayout<RS>::smem_bytes(STAGES);
   if (!occ) {
-    CUDA_CHECK(cudaFuncSetAttribute(k_elastic_forces_rownp<STAGES, MAXREG, RS, ROT, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_elastic_forces_rownp<STAGES, MAXREG, RS, ROT, PF>, GRP_CONSUMERS, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(k_elastic_forces_rownp<STAGES, MAXREG, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_elastic_forces_rownp<STAGES, MAXREG, RS>, GRP_CONSUMERS, smem));
     if (occ < 1) exit_on_error("k_elastic_forces_rownp does not fit on an SM");
     if (getenv("SPECFEM_B200_VERBOSE"))
       fprintf(stderr, "k_elastic_forces_rownp<%d,%d,%d>: %d CTAs per SM, %d B of shared memory\n", STAGES, MAXREG, RS, occ, smem);
   }
   int grid = mp->num_sms * occ;  // persistent: every resident CTA slot of the device, once
   if (ng < grid) grid = ng;
-  k_elastic_forces_rownp<STAGES, MAXREG, RS, ROT, PF><<<grid, GRP_CONSUMERS, smem, mp->compute_stream>>>(a);
+  k_elastic_forces_rownp<STAGES, MAXREG, RS><<<grid, GRP_CONSUMERS, smem, mp->compute_stream>>>(a);
 }
 
 inline void launch_elastic_grp(DeviceMesh* mp, const GroupStore* gs, int segment, int use_atomics) {
@@ -312,14 +301,10 @@ inline void launch_elastic_grp(DeviceMesh* mp, const GroupStore* gs, int segment
   a.nglob = (size_t)mp->NGLOB_AB;
   KernelTimer timer(mp, "elastic_forces");
   switch (mp->force_kernel_variant) {  // SPECFEM_B200_FORCE_KERNEL (A/B; 0 = default)
-    case 4: launch_elastic_rownp_t<3, 80, 141>(mp, a, ng); break;  // no producer warp, 6 CTAs / SM
-    case 5: launch_elastic_rownp_t<3, 96, 153>(mp, a, ng); break;  // no producer warp, 5 CTAs / SM, no spill
-    case 6: launch_elastic_rownp_t<3, 96, 153, true>(mp, a, ng); break;         // + plane-task rotation
-    case 7: launch_elastic_rownp_t<3, 96, 153, true, true>(mp, a, ng); break;   // + rotation + L2 prefetch
-    case 9: launch_elastic_rownp_t<3, 80, 141, true, true>(mp, a, ng); break;   // 6 CTAs + rotation + L2 prefetch
-    case 8: launch_elastic_row_t<3, 72, true>(mp, a, ng); break;   // producer warp + L2 prefetch of chunks 3, 4
-    // 72 registers keep five CTAs (25 warps) resident per SM; at 80 (no spill) only four fit and the kernel is slower
-    default: launch_elastic_row_t<3, 72>(mp, a, ng); break;
+    case 2: launch_elastic_row_t<3, 72>(mp, a, ng); break;  // round-2 kernel with a producer warp (A/B)
+    // no producer warp: 96 registers (no spill), five CTAs = 20 working warps per SM.  Six CTAs (80 registers, tile stride
+    // 141 or 125) are slower: 2.06 against 1.92 ms per 1M elements (profiles/r02w_force_np_ab.jsonl)
+    default: launch_elastic_rownp_t<3, 96, 153>(mp, a, ng); break;
   }
 }
 

@@ -334,6 +334,7 @@ extern "C" void SB200_FC(prepare_constants_device)(
   if (fk) mp->force_kernel_variant = atoi(fk);
   if (const char* ak = getenv("SPECFEM_B200_ACOUSTIC_KERNEL")) mp->acoustic_kernel_variant = atoi(ak);
   if (const char* ap = getenv("SPECFEM_B200_ATT_PREFETCH")) mp->att_prefetch = atoi(ap);
+  if (const char* kk = getenv("SPECFEM_B200_KL_KERNEL")) mp->kl_kernel_variant = atoi(kk);
   const char* fn = getenv("SPECFEM_B200_FUSE_NEWMARK");
   if (fn) mp->fuse_newmark = atoi(fn);
   if (const char* ps = getenv("SPECFEM_B200_PRODUCER_SLEEP")) {
