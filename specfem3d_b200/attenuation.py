@@ -201,11 +201,48 @@ def memory_values(tau_s32: np.ndarray, deltat: np.float32):
     return alpha.astype(np.float32), beta.astype(np.float32), gamma.astype(np.float32)
 
 
+def min_resolved_period_from_mesh(dbs) -> float:
+    """check_mesh_resolution's estimate from the mesh arrays themselves (src/shared/check_mesh_resolution.f90:200-271), for
+    databases of ANY mesh: per element ``pmax = (elemsize_max / (NGLLX-1)) / vel_min * NPTS_PER_WAVELENGTH`` with
+    NPTS_PER_WAVELENGTH = 5 (setup/constants.h.in:301); ``elemsize_max`` = the longest of the twelve corner-to-corner edges
+    (get_elem_minmaxsize, :1470-1575), ``vel_min`` = min(vp, vs) over the corner / mid points of the element, vs = 0 ignored
+    (get_vpvs_minmax with MIDPOINT_CHECK_ONLY, :941-1040); maximum over the elements and the ranks (max_all_cr)."""
+    f = np.float32
+    pmax = 0.0
+    for db in dbs:
+        if db is None:
+            continue
+        nspec = db.NSPEC_AB
+        ib = np.asarray(db.ibool).reshape(nspec, 5, 5, 5) - 1  # [ispec, k, j, i]
+        xyz = np.stack([np.asarray(db.xstore, f), np.asarray(db.ystore, f), np.asarray(db.zstore, f)], -1)
+        c = xyz[ib[:, ::4][:, :, ::4][:, :, :, ::4]]           # (nspec, 2, 2, 2, 3) corners [k, j, i]
+        d2 = np.concatenate([((c[:, :, :, 1] - c[:, :, :, 0]) ** 2).sum(-1).reshape(nspec, -1),     # edges along x
+                             ((c[:, :, 1, :] - c[:, :, 0, :]) ** 2).sum(-1).reshape(nspec, -1),     # along y
+                             ((c[:, 1, :, :] - c[:, 0, :, :]) ** 2).sum(-1).reshape(nspec, -1)], 1)  # along z
+        elemsize_max = np.sqrt(d2.max(1).astype(f))  # CUSTOM_REAL arithmetic throughout, like the reference
+        sub = (slice(None), slice(None, None, 2), slice(None, None, 2), slice(None, None, 2))
+        rho = np.asarray(db.rhostore, f).reshape(nspec, 5, 5, 5)[sub].reshape(nspec, -1)
+        mu = np.asarray(db.mustore, f).reshape(nspec, 5, 5, 5)[sub].reshape(nspec, -1)
+        ka = np.asarray(db.kappastore, f).reshape(nspec, 5, 5, 5)[sub].reshape(nspec, -1)
+        ok = rho > 1e-9
+        safe = np.where(ok, rho, f(1))
+        vp_sq = np.where(ok, (f(4.0 / 3.0) * mu + ka) / safe, f(0)).astype(f)
+        vs_sq = np.where(ok, mu / safe, f(0)).astype(f)
+        vpmin = np.sqrt(vp_sq.min(1))
+        vsmin = np.sqrt(np.where(vs_sq > 1e-9, vs_sq, f(np.inf)).min(1))
+        vel_min = np.minimum(vpmin, vsmin)
+        pm = (elemsize_max / f(4.0)) / vel_min * f(5.0)
+        pmax = max(pmax, float(pm.max()))
+    return pmax
+
+
 def min_resolved_period_of(sim) -> float:
-    """check_mesh_resolution's estimate (src/shared/check_mesh_resolution.f90:245-271): per element
-    ``pmax = (elemsize_max / (NGLLX-1)) / vel_min * NPTS_PER_WAVELENGTH`` with NPTS_PER_WAVELENGTH = 5
-    (setup/constants.h.in:301), maximum over elements.  For the harness' box meshes the element size is the
-    largest edge of the undeformed cell (deformed test meshes differ by a few per cent, which only shifts the band)."""
+    """The solver's min_resolved_period: check_mesh_resolution's estimate from the mesh arrays of all ranks
+    (:func:`min_resolved_period_from_mesh`), whether the mesh came from the harness' generator or from database files.
+    When this process holds only some of the ranks (bench.py under torchrun) the structured box gives the same number from
+    its cell size: every rank must use the global maximum (max_all_cr in the reference)."""
+    if all(db is not None for db in sim.dbs):
+        return min_resolved_period_from_mesh(sim.dbs)
     spec = sim.spec
     h = max((spec.xmax - spec.xmin) / spec.nex_xi, (spec.ymax - spec.ymin) / spec.nex_eta,
             (spec.zmax - spec.zmin) / spec.ner)

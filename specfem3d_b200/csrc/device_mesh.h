@@ -164,6 +164,11 @@ struct DeviceMesh {
   realw *d_b_epsilondev_xx = nullptr, *d_b_epsilondev_yy = nullptr, *d_b_epsilondev_xy = nullptr,
         *d_b_epsilondev_xz = nullptr, *d_b_epsilondev_yz = nullptr;                              // [NSPEC][128]
   realw *d_epsilon_trace_over_3 = nullptr, *d_b_epsilon_trace_over_3 = nullptr;                  // [NSPEC][128]
+  // kernel runs with ATTENUATION: memory variables, trace strain and Runge-Kutta constants of the reconstructed wavefield
+  realw *d_b_R_xx = nullptr, *d_b_R_yy = nullptr, *d_b_R_xy = nullptr, *d_b_R_xz = nullptr, *d_b_R_yz = nullptr,
+        *d_b_R_trace = nullptr;                                                                  // [NSPEC][N_SLS][128]
+  realw* d_b_epsilondev_trace = nullptr;                                                         // [NSPEC][128]
+  realw h_b_abg[3 * N_SLS] = {0};  // b_alphaval, b_betaval, b_gammaval
   realw *d_rho_kl = nullptr, *d_mu_kl = nullptr, *d_kappa_kl = nullptr;                          // [NSPEC][128]
   realw* d_cijkl_kl = nullptr;                                                                   // [NSPEC][21][128], ANISOTROPIC_KL
   realw *d_hess_el_kl = nullptr, *d_hess_rho_el_kl = nullptr, *d_hess_kappa_el_kl = nullptr, *d_hess_mu_el_kl = nullptr;

@@ -36,6 +36,10 @@ struct ElasticArgs {
   realw *eps_xx, *eps_yy, *eps_xy, *eps_xz, *eps_yz, *eps_trace;         // [NSPEC][128]
   realw* eps_trace_over_3 = nullptr;  // [NSPEC][128], kernel runs only (SIMULATION_TYPE == 3, Kernel_2_noatt_iso_impl :890-893)
   int att_prefetch;            // 0 = none, 1 = prefetch the element's attenuation planes into L2, 2 = into L1
+  // reconstructed wavefield of a kernel run: its own Runge-Kutta constants (b_alphaval, b_betaval, b_gammaval of
+  // prepare_fields_elastic_adj_dev) instead of the __constant__ ones of the forward / adjoint wavefield
+  int use_abg = 0;
+  realw abg[3 * N_SLS] = {0};
 };
 
 // ncu on the attenuation kernel (profiles/r01g_secondary_kernels.md): 73 % of every issue slot's latency is a long
@@ -274,7 +278,8 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_elastic_forces_pt(const Elasti
                   Sn_xz = a.eps_xz[off], Sn_yz = a.eps_yz[off];
 #pragma unroll
       for (int s = 0; s < N_SLS; ++s) {
-        const realw al = c_alphaval[s], be = c_betaval[s], ga = c_gammaval[s];
+        const realw al = a.use_abg ? a.abg[s] : c_alphaval[s], be = a.use_abg ? a.abg[N_SLS + s] : c_betaval[s],
+                    ga = a.use_abg ? a.abg[2 * N_SLS + s] : c_gammaval[s];
         realw fl = kappal * a.factor_common_kappa[roff + s * NGLL3_PADDED];
         a.R_trace[roff + s * NGLL3_PADDED] = al * Rtr[s] + fl * (be * Sn_tr + ga * e_tr);
         fl = mul * a.factor_common[roff + s * NGLL3_PADDED];
@@ -287,10 +292,70 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_elastic_forces_pt(const Elasti
     }
     if (ATT || STRAIN) {
       if (ATT) a.eps_trace[off] = e_tr;
-      if (!ATT && a.eps_trace_over_3) a.eps_trace_over_3[off] = 0.33333333333333333333f * e_tr;
+      // kernel runs: epsilon_trace_over_3 of the strain this launch stores (with attenuation that of u + dt v,
+      // compute_forces_viscoelastic.F90:503-552)
+      if (a.eps_trace_over_3) a.eps_trace_over_3[off] = 0.33333333333333333333f * e_tr;
       a.eps_xx[off] = e_xx; a.eps_yy[off] = e_yy; a.eps_xy[off] = e_xy; a.eps_xz[off] = e_xz; a.eps_yz[off] = e_yz;
     }
   }
+}
+
+// Strain of a displacement field alone (replaces compute_element_strain_cudakernel, src/gpu/kernels/
+// compute_element_strain_cudakernel.cu, called by compute_strain_cuda.cu:38-140 and compute_kernels_cuda.cu:57-100 when
+// UNDO_ATTENUATION_AND_OR_PML is set; CPU: compute_element_strain, compute_element_strain.F90:33-170): deviatoric strain,
+// trace (= 3 x epsilon_trace_over_3, needed by the bulk attenuation) and epsilon_trace_over_3 of every elastic element.
+struct StrainArgs {
+  int nspec;
+  const int *ispec_is_elastic, *ibool, *irregular_element_number;
+  const realw* metric;
+  realw xix_regular;
+  const realw* displ;
+  size_t nglob;
+  realw *eps_xx, *eps_yy, *eps_xy, *eps_xz, *eps_yz, *eps_trace, *eps_trace_over_3;  // eps_trace may be null
+};
+__global__ void __launch_bounds__(NGLL3_PADDED) k_element_strain(const StrainArgs a) {
+  const size_t cs = vstride(a.nglob);
+  const int ispec = blockIdx.x;
+  if (ispec >= a.nspec || !a.ispec_is_elastic[ispec]) return;
+  const int tx = threadIdx.x;
+  const bool active = tx < NGLL3;
+  const int t = active ? tx : NGLL3 - 1;
+  const int K = t / NGLL2, J = (t - K * NGLL2) / NGLLX, I = t - K * NGLL2 - J * NGLLX;
+  __shared__ realw s_x[NGLL3_PADDED], s_y[NGLL3_PADDED], s_z[NGLL3_PADDED];
+  const size_t off = (size_t)ispec * NGLL3_PADDED + t;
+  const size_t vb = vbase(a.ibool[off] - 1);
+  s_x[t] = a.displ[vb]; s_y[t] = a.displ[vb + cs]; s_z[t] = a.displ[vb + 2 * cs];
+  __syncthreads();
+  realw t1x = 0.f, t2x = 0.f, t3x = 0.f, t1y = 0.f, t2y = 0.f, t3y = 0.f, t1z = 0.f, t2z = 0.f, t3z = 0.f;
+#pragma unroll
+  for (int l = 0; l < NGLLX; ++l) {
+    const realw h1 = c_hprime_xx[l * NGLLX + I], h2 = c_hprime_xx[l * NGLLX + J], h3 = c_hprime_xx[l * NGLLX + K];
+    const int o1 = K * NGLL2 + J * NGLLX + l, o2 = K * NGLL2 + l * NGLLX + I, o3 = l * NGLL2 + J * NGLLX + I;
+    t1x += s_x[o1] * h1; t1y += s_y[o1] * h1; t1z += s_z[o1] * h1;
+    t2x += s_x[o2] * h2; t2y += s_y[o2] * h2; t2z += s_z[o2] * h2;
+    t3x += s_x[o3] * h3; t3y += s_y[o3] * h3; t3z += s_z[o3] * h3;
+  }
+  realw dxx, dxy, dxz, dyx, dyy, dyz, dzx, dzy, dzz;
+  const int irr = a.irregular_element_number[ispec] - 1;
+  if (irr >= 0) {
+    const realw* mp = a.metric + (size_t)irr * 9 * NGLL3_PADDED + t;
+    const realw xix = mp[0], xiy = mp[NGLL3_PADDED], xiz = mp[2 * NGLL3_PADDED], etax = mp[3 * NGLL3_PADDED],
+                etay = mp[4 * NGLL3_PADDED], etaz = mp[5 * NGLL3_PADDED], gammax = mp[6 * NGLL3_PADDED],
+                gammay = mp[7 * NGLL3_PADDED], gammaz = mp[8 * NGLL3_PADDED];
+    dxx = xix * t1x + etax * t2x + gammax * t3x; dxy = xiy * t1x + etay * t2x + gammay * t3x; dxz = xiz * t1x + etaz * t2x + gammaz * t3x;
+    dyx = xix * t1y + etax * t2y + gammax * t3y; dyy = xiy * t1y + etay * t2y + gammay * t3y; dyz = xiz * t1y + etaz * t2y + gammaz * t3y;
+    dzx = xix * t1z + etax * t2z + gammax * t3z; dzy = xiy * t1z + etay * t2z + gammay * t3z; dzz = xiz * t1z + etaz * t2z + gammaz * t3z;
+  } else {
+    dxx = a.xix_regular * t1x; dxy = a.xix_regular * t2x; dxz = a.xix_regular * t3x;
+    dyx = a.xix_regular * t1y; dyy = a.xix_regular * t2y; dyz = a.xix_regular * t3y;
+    dzx = a.xix_regular * t1z; dzy = a.xix_regular * t2z; dzz = a.xix_regular * t3z;
+  }
+  if (!active) return;
+  const realw tr = dxx + dyy + dzz, templ = 0.33333333333333333333f * tr;
+  a.eps_trace_over_3[off] = templ;
+  if (a.eps_trace) a.eps_trace[off] = tr;
+  a.eps_xx[off] = dxx - templ; a.eps_yy[off] = dyy - templ;
+  a.eps_xy[off] = 0.5f * (dxy + dyx); a.eps_xz[off] = 0.5f * (dzx + dxz); a.eps_yz[off] = 0.5f * (dzy + dyz);
 }
 
 }  // namespace sb200

@@ -592,7 +592,8 @@ extern "C" void SB200_FC(prepare_cleanup_device)(long* Mesh_pointer, int* ACOUST
                    mp->d_rmass_ocean_load, mp->d_ocean_iglob, mp->d_ocean_normal,
                    mp->d_b_send_accel_buffer, mp->d_b_potential, mp->d_b_potential_dot, mp->d_b_potential_dot_dot,
                    mp->d_rho_ac_kl, mp->d_kappa_ac_kl, mp->d_b_send_potential_buffer, mp->d_hess_ac_kl, mp->d_hess_rho_ac_kl,
-                   mp->d_hess_kappa_ac_kl};
+                   mp->d_hess_kappa_ac_kl, mp->d_b_R_xx, mp->d_b_R_yy, mp->d_b_R_xy, mp->d_b_R_xz, mp->d_b_R_yz, mp->d_b_R_trace,
+                   mp->d_b_epsilondev_trace};
   for (void* p : dptrs) dev_free(p);
   if (mp->h_absorb_registered) cudaHostUnregister(mp->h_absorb_registered);
   if (mp->h_send_accel_buffer) cudaFreeHost(mp->h_send_accel_buffer);
@@ -935,11 +936,17 @@ static void launch_elastic(DeviceMesh* mp, int nb, const int* phase_list, int fi
   a.eps_xx = mp->d_epsilondev_xx; a.eps_yy = mp->d_epsilondev_yy; a.eps_xy = mp->d_epsilondev_xy;
   a.eps_xz = mp->d_epsilondev_xz; a.eps_yz = mp->d_epsilondev_yz; a.eps_trace = mp->d_epsilondev_trace;
   a.eps_trace_over_3 = mp->d_epsilon_trace_over_3;
-  if (backward) {  // reconstructed forward wavefield of a kernel run (no attenuation there: prepare_fields_elastic_adj_dev)
+  if (backward) {  // reconstructed forward wavefield of a kernel run (arrays of prepare_fields_elastic_adj_dev)
     a.displ = mp->d_b_displ; a.veloc = mp->d_b_veloc; a.accel = mp->d_b_accel;
     a.eps_xx = mp->d_b_epsilondev_xx; a.eps_yy = mp->d_b_epsilondev_yy; a.eps_xy = mp->d_b_epsilondev_xy;
-    a.eps_xz = mp->d_b_epsilondev_xz; a.eps_yz = mp->d_b_epsilondev_yz; a.eps_trace = nullptr;
+    a.eps_xz = mp->d_b_epsilondev_xz; a.eps_yz = mp->d_b_epsilondev_yz; a.eps_trace = mp->d_b_epsilondev_trace;
     a.eps_trace_over_3 = mp->d_b_epsilon_trace_over_3;
+    if (mp->attenuation) {
+      a.R_xx = mp->d_b_R_xx; a.R_yy = mp->d_b_R_yy; a.R_xy = mp->d_b_R_xy; a.R_xz = mp->d_b_R_xz; a.R_yz = mp->d_b_R_yz;
+      a.R_trace = mp->d_b_R_trace;
+      a.use_abg = 1;
+      memcpy(a.abg, mp->h_b_abg, sizeof(a.abg));
+    }
   }
   static int att_prefetch = -1;
   if (att_prefetch < 0) {

@@ -42,6 +42,10 @@ class Simulation:
     SAVE_FORWARD: bool = False   # forward run keeps the absorbed Stacey tractions of every step and the last frame
     APPROXIMATE_HESS_KL: bool = False
     ANISOTROPIC_KL: bool = False  # cijkl_kl (21 per point) instead of mu_kl / kappa_kl
+    # kernel runs with attenuation (undo_att.py): the forward run stores a wavefield snapshot every NT_DUMP_ATTENUATION steps,
+    # the kernel run re-computes the forward wavefield forward in time from them (iterate_time_undoatt.F90)
+    UNDO_ATTENUATION_AND_OR_PML: bool = False
+    NT_DUMP_ATTENUATION: int = 500
 
     @property
     def deltat(self) -> np.float32:

@@ -118,8 +118,8 @@ class DeviceRank:
             int(sim.SAVE_FORWARD), H["hxir"],
             H["hetar"], H["hgammar"], H["nu_rec"], H["nu_source"], H["islice_rec"], sim.nlength_seismogram,
             int(sim.SAVE_SEISMOGRAMS_DISPLACEMENT), int(sim.SAVE_SEISMOGRAMS_VELOCITY),
-            int(sim.SAVE_SEISMOGRAMS_ACCELERATION), int(sim.SAVE_SEISMOGRAMS_PRESSURE), 1, 0, 0,
-            int(sim.PML_CONDITIONS))
+            int(sim.SAVE_SEISMOGRAMS_ACCELERATION), int(sim.SAVE_SEISMOGRAMS_PRESSURE), 1, 0,
+            int(sim.UNDO_ATTENUATION_AND_OR_PML), int(sim.PML_CONDITIONS))
 
         dummy = np.zeros(1, np.float32)
         idummy = np.zeros(1, np.int32)
@@ -179,10 +179,20 @@ class DeviceRank:
                 prepare_fields_elastic_pml(self)
             if sim.SIMULATION_TYPE == 3:  # prepare_gpu.f90:232-262
                 z = np.zeros((nspec, 5, 5, 5), np.float32)
-                L.prepare_fields_elastic_adj_dev(
-                    self.Mesh_pointer, 3 * db.NGLOB_AB, z, z, z, z, z, z, z, R_size, *([dummy] * 7),
-                    np.zeros(N_SLS, np.float32), np.zeros(N_SLS, np.float32), np.zeros(N_SLS, np.float32),
-                    int(sim.ANISOTROPIC_KL), int(sim.APPROXIMATE_HESS_KL))
+                if att is not None:
+                    # b_R_* start at zero; b_alphaval ... = alphaval ... when the forward wavefield is re-computed forward in
+                    # time (prepare_attenuation.f90:169-182, UNDO_ATTENUATION_AND_OR_PML)
+                    if not sim.UNDO_ATTENUATION_AND_OR_PML:
+                        raise NotImplementedError("kernel runs with ATTENUATION need UNDO_ATTENUATION_AND_OR_PML (undo_att.py)")
+                    bR = [np.zeros((nspec, NGLL3, N_SLS), np.float32) for _ in range(6)]
+                    L.prepare_fields_elastic_adj_dev(
+                        self.Mesh_pointer, 3 * db.NGLOB_AB, z, z, z, z, z, z, z, R_size, *bR, z, _f(al), _f(be), _f(ga),
+                        int(sim.ANISOTROPIC_KL), int(sim.APPROXIMATE_HESS_KL))
+                else:
+                    L.prepare_fields_elastic_adj_dev(
+                        self.Mesh_pointer, 3 * db.NGLOB_AB, z, z, z, z, z, z, z, R_size, *([dummy] * 7),
+                        np.zeros(N_SLS, np.float32), np.zeros(N_SLS, np.float32), np.zeros(N_SLS, np.float32),
+                        int(sim.ANISOTROPIC_KL), int(sim.APPROXIMATE_HESS_KL))
         if sim.SIMULATION_TYPE == 3:  # prepare_gpu.f90:264-270
             L.prepare_sim2_or_3_const_device(self.Mesh_pointer, self.nrec_local, sim.NSTEP, H["hxir"], H["hetar"],
                                              H["hgammar"], nrec, H["islice_rec"], H["ispec_rec"])
@@ -333,7 +343,10 @@ class DeviceRun:
                 db, L, M = r.db, r.lib, r.Mesh_pointer
                 L.compute_forces_viscoelastic_cuda(M, iphase, dt, db.nspec_outer_elastic, db.nspec_inner_elastic, att, att, 1)
                 if iphase == 1:
-                    if sim.spec.stacey:
+                    if sim.spec.stacey and sim.UNDO_ATTENUATION_AND_OR_PML:
+                        # no boundary record is kept: the kernel run re-computes the condition (compute_stacey_viscoelastic.F90:453-457)
+                        L.compute_stacey_viscoelastic_undoatt_cuda(M, iphase, 1)
+                    elif sim.spec.stacey:
                         L.compute_stacey_viscoelastic_cuda(M, iphase, r.b_absorb_field, 1)
                         if sim.SAVE_FORWARD:  # write_abs(IOABS, b_absorb_field, b_reclen_field, it)
                             r.absorb_history.append(r.b_absorb_field.copy())

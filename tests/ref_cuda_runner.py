@@ -33,6 +33,8 @@ def factories():
         "kernel_run": lambda: kernel_run_case(),
         "kernel_run_acoustic": lambda: kernel_run_case("acoustic"),
         "kernel_run_coupled": lambda: kernel_run_case("coupled"),
+        "kernel_run_undoatt": lambda: kernel_run_case("undoatt"),
+        "kernel_run_undoatt_visco": lambda: kernel_run_case("undoatt_visco"),
     }
 
 
@@ -55,7 +57,39 @@ def coupled_kernel_sim(nstep, sim_type):
     return sim
 
 
+def undoatt_kernel_sim(nstep, sim_type, visco, nproc=(1, 1), nt_dump=50):
+    """UNDO_ATTENUATION_AND_OR_PML: the elastic kernel-run mesh (test_oracle_kernel_run.kernel_sim) or the two-layer
+    viscoelastic one (test_gpu_parity.visco_sim, 3 SLS), snapshots every ``nt_dump`` steps (which does not divide NSTEP)."""
+    import test_gpu_parity as T
+    import test_oracle_kernel_run as K
+
+    sim = T.visco_sim(nproc, nstep) if visco else K.kernel_sim(nproc, nstep, sim_type=sim_type)
+    sim.SIMULATION_TYPE, sim.SAVE_FORWARD = sim_type, sim_type == 1
+    sim.UNDO_ATTENUATION_AND_OR_PML, sim.NT_DUMP_ATTENUATION = True, nt_dump
+    return sim
+
+
+def run_undoatt_case(lib, visco, adj_path=None, nproc=(1, 1)):
+    from specfem3d_b200.undo_att import UndoAttKernelRun, run_forward_and_save_undoatt
+
+    n = kernel_run_case.NSTEP
+    fwd, prod = run_forward_and_save_undoatt(undoatt_kernel_sim(n, 1, visco, nproc), lib=lib)
+    seis = fwd.gather_seismograms("d")
+    if adj_path is not None and os.path.exists(adj_path):
+        adj = np.load(adj_path)
+    else:
+        adj = ((1e15 / np.abs(seis).max()) * seis).astype(np.float32)
+        if adj_path is not None:
+            np.save(adj_path, adj)
+    k = UndoAttKernelRun(undoatt_kernel_sim(n, 3, visco, nproc), prod, adj, lib=lib).run()
+    rho, mu, kappa = k.kernels()[0]
+    out = {"d_forward": seis, "displ": k.ranks[0].fields_el()[0], "rho_kl": rho.copy(), "mu_kl": mu.copy(), "kappa_kl": kappa.copy()}
+    return k, out
+
+
 def run_kernel_case(lib, kind="elastic", adj_path=None):
+    if kind in ("undoatt", "undoatt_visco"):
+        return run_undoatt_case(lib, kind == "undoatt_visco", adj_path)
     """``adj_path``: .npy with the adjoint sources; written if it does not exist yet (the first library to run derives them
     from its own forward seismograms, the second one must use the same bytes)."""
     import test_oracle_kernel_run as K

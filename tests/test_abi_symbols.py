@@ -65,9 +65,9 @@ def test_out_of_scope_entry_points_fail_loudly(tmp_path):
     """No silent no-ops and no CPU fallback: an entry point outside the implemented set prints its name and exits non-zero
     (like exit_on_error in src/gpu/helper_functions.cu), and so does an implemented one called with a null handle."""
     load = "import ctypes; L = ctypes.CDLL('specfem3d_b200/libspecfem3d_b200.so'); h = ctypes.c_long(0); i = ctypes.c_int(1)\n"
-    res = _run_snippet(load + "L.compute_strain_cuda_(ctypes.byref(h), ctypes.byref(i), ctypes.byref(i))\nprint('survived')")
+    res = _run_snippet(load + "L.get_max_accel_(ctypes.byref(i), ctypes.byref(i), ctypes.byref(h))\nprint('survived')")
     assert res.returncode != 0 and "survived" not in res.stdout
-    assert "compute_strain_cuda" in res.stderr + res.stdout
+    assert "get_max_accel" in res.stderr + res.stdout
     f = "f = ctypes.c_float(0.1)\n"
     res = _run_snippet(load + f + "L.update_displacement_cuda_(ctypes.byref(h), ctypes.byref(f), ctypes.byref(f), ctypes.byref(f), ctypes.byref(i))\nprint('survived')")
     assert res.returncode != 0 and "survived" not in res.stdout

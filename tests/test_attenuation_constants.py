@@ -57,3 +57,25 @@ def test_scale_factors_of_the_viscoelastic_benchmark():
     fc = att.f_c_source_of(tmin, tmax)
     assert abs(att.scale_factor_of(fc, att.tau_eps_of(20.0, ts, tmin, tmax), ts, 20.0, 18.0) - FACTOR_SCALE_MU) < 2e-7
     assert abs(att.scale_factor_of(fc, att.tau_eps_of(10.0, ts, tmin, tmax), ts, 10.0, 18.0) - FACTOR_SCALE_KAPPA) < 2e-7
+
+
+def test_min_resolved_period_from_mesh_matches_reference_log():
+    """check_mesh_resolution restated on the mesh arrays (used for runs from database files): the reference prints
+    '*** Minimum period resolved = 3.12500000' for config 1 (EXAMPLES/applications/homogeneous_halfspace/REF_SEIS/
+    output_solver.txt:72); a deformed, coupled mesh gives a longer period than its undeformed cells would."""
+    from specfem3d_b200.attenuation import min_resolved_period_from_mesh, min_resolved_period_of
+    from specfem3d_b200.configs import HALFSPACE, cfg1
+    from specfem3d_b200.meshfem import BoxSpec, Material
+    from specfem3d_b200.simulation import make_simulation
+
+    sim = cfg1(2, 2, 10)
+    assert abs(min_resolved_period_from_mesh(sim.dbs) - 3.125) < 1e-6
+    assert abs(min_resolved_period_of(sim) - 3.125) < 1e-6
+    water = Material(1020.0, 1500.0, 0.0, 9999.0, 9999.0, 1)
+    spec = BoxSpec(6, 4, 6, xmax=6600.0, ymax=3600.0, zmin=-6000.0, materials=(HALFSPACE, water), layer_material=[0] * 4 + [1] * 2,
+                   deform=0.1)
+    sim = make_simulation(spec, DT=0.01, NSTEP=5)
+    p_mesh = min_resolved_period_from_mesh(sim.dbs)
+    p_box = (1100.0 / 4.0) / 1500.0 * 5.0  # undeformed cell, vs of the solid; the fluid's vs = 0 is ignored
+    assert p_box < p_mesh < 1.1 * p_box
+    assert min_resolved_period_of(sim) == p_mesh

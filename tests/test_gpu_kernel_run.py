@@ -340,3 +340,66 @@ def test_anisotropic_kernels_match_oracle(device_lib, fused, monkeypatch):
     for p21 in range(21):
         assert rel_l2(mine[..., p21], ref[..., p21]) <= 4 * KERNEL_RTOL, p21
     k.cleanup()
+
+
+# ---- UNDO_ATTENUATION_AND_OR_PML (specfem3d_b200/undo_att.py, iterate_time_undoatt.F90) ---------------------------------------
+def _undoatt_run(device_lib, nproc, nstep, visco, nt_dump=50):
+    import ref_cuda_runner as R
+    from specfem3d_b200.undo_att import UndoAttKernelRun, run_forward_and_save_undoatt
+
+    fwd, prod = run_forward_and_save_undoatt(R.undoatt_kernel_sim(nstep, 1, visco, nproc, nt_dump), lib=device_lib)
+    seis_fwd = fwd.gather_seismograms("d")
+    fwd.cleanup()
+    adj = adjoint_source(seis_fwd)
+    k = UndoAttKernelRun(R.undoatt_kernel_sim(nstep, 3, visco, nproc, nt_dump), prod, adj, lib=device_lib).run()
+    return seis_fwd, adj, k
+
+
+@pytest.mark.parametrize("nproc", [(1, 1), (2, 2)])
+def test_undo_attenuation_run_equals_standard_kernel_run(device_lib, nproc):
+    """Elastic medium, no attenuation: both ways of getting the forward wavefield back are exact, so the kernels of the
+    UNDO_ATTENUATION_AND_OR_PML run (snapshots every 50 of 120 steps: subsets of 50, 50 and 20 steps taken in reverse order,
+    wavefield re-computed FORWARD in time from the snapshot, Stacey condition re-evaluated from b_veloc, strain of b_displ
+    re-computed by the library) must equal those of the standard run (time-reversed reconstruction with the boundary record)."""
+    nstep = 120
+    seis_fwd, adj, k = _undoatt_run(device_lib, nproc, nstep, visco=False)
+    _, _, std = device_kernel_run(device_lib, nproc, nstep, adj)
+    # the re-computed wavefield repeats the forward run operation for operation: sample j = forward step NSTEP - j
+    sk = k.gather_seismograms("d")
+    assert np.abs(seis_fwd).max() > 0
+    assert rel_l2(sk, seis_fwd[:, ::-1]) <= 2e-5
+    for r, ((rho, mu, kappa), (rho0, mu0, kappa0)) in enumerate(zip(k.kernels(), std.kernels())):
+        assert rel_l2(k.ranks[r].fields_el()[0], std.ranks[r].fields_el()[0]) <= 1e-4  # adjoint wavefield at the end
+        for mine, ref in ((rho, rho0), (mu, mu0), (kappa, kappa0)):
+            assert np.abs(ref).max() > 0
+            assert rel_l2(mine, ref) <= KERNEL_RTOL
+    k.cleanup()
+    std.cleanup()
+
+
+def test_undo_attenuation_run_viscoelastic(device_lib):
+    """Two viscoelastic layers (3 SLS): the forward run uses the viscoelastic row kernel and its attenuation store, the
+    kernel run restores displ / veloc / accel and R_* from the snapshots and re-computes the wavefield with the b_ arrays
+    (one-thread-per-point kernel, b_alphaval ... = alphaval ...): the re-computed seismograms must repeat the forward ones.
+    The partitioned run (2 x 1 ranks, host-staged b_accel halo) must give the kernels of the single-rank run; the kernels
+    themselves are pinned on the reference's CUDA backend (test_gpu_vs_reference_cuda.py[kernel_run_undoatt_visco])."""
+    nstep = 120
+    seis_fwd, adj, k = _undoatt_run(device_lib, (1, 1), nstep, visco=True)
+    sk = k.gather_seismograms("d")
+    assert np.abs(seis_fwd).max() > 0
+    print("undo_att viscoelastic: re-computed vs forward seismograms, relative L2 =", rel_l2(sk, seis_fwd[:, ::-1]))
+    # forward run: viscoelastic row kernel (1/det from the SFU, plane-owner summation order); kernel run: one-thread-per-point
+    # kernel -- the two agree to the round-off both accumulate over the run, not bit for bit
+    assert rel_l2(sk, seis_fwd[:, ::-1]) <= 1e-4
+    rho, mu, kappa = (a.copy() for a in k.kernels()[0])
+    for a in (rho, mu, kappa):
+        assert np.isfinite(a).all() and np.abs(a).max() > 0
+    k.cleanup()
+    seis2, _, k2 = _undoatt_run(device_lib, (2, 1), nstep, visco=True)
+    print("undo_att viscoelastic: 2 x 1 ranks vs 1 rank, forward seismograms =", rel_l2(seis2, seis_fwd))
+    assert rel_l2(seis2, seis_fwd) <= 1e-4
+    # global element order of the 2 x 1 run: compare through the kernels' L2 norms per rank sum and the station traces
+    tot = [np.sqrt(sum(float((ks[i].astype(np.float64) ** 2).sum()) for ks in k2.kernels())) for i in range(3)]
+    for t, a in zip(tot, (rho, mu, kappa)):
+        assert abs(t - np.linalg.norm(a.astype(np.float64))) <= KERNEL_RTOL * np.linalg.norm(a.astype(np.float64))
+    k2.cleanup()
