@@ -774,6 +774,24 @@ namespace sb200 {
 void (*g_flush_corrector)(DeviceMesh*) = &flush_corrector_impl;
 }
 
+// deferred corrector + predictor with the compact inverse mass matrix (kernels_misc.cuh)
+static void launch_newmark_cp_compact(DeviceMesh* mp, realw* displ, realw* veloc, realw* accel, realw corr_deltatover2, realw deltat,
+                                      realw deltatsqover2, realw deltatover2) {
+  const long long nglob = mp->NGLOB_AB;
+  const int grid = streaming_grid((nglob + 3) >> 2);
+#define SB200_NCP(M)                                                                                                          \
+  k_newmark_corrector_predictor_c<M><<<grid, 256, 0, mp->compute_stream>>>(displ, veloc, accel, mp->d_rmass_c, mp->d_rmass_exc, \
+                                                                           mp->rmass_nexc, nglob, corr_deltatover2, deltat,   \
+                                                                           deltatsqover2, deltatover2)
+  switch ((int)(nglob % 4)) {
+    case 0: SB200_NCP(0); break;
+    case 1: SB200_NCP(1); break;
+    case 2: SB200_NCP(2); break;
+    default: SB200_NCP(3); break;
+  }
+#undef SB200_NCP
+}
+
 extern "C" void SB200_FC(update_displacement_cuda)(long* Mesh_pointer, realw* deltat_F, realw* deltatover2_F,
                                                    realw* deltatsqover2_F, int* FORWARD_OR_ADJOINT) {
   DeviceMesh* mp = get_mesh_keep_pending(Mesh_pointer);
@@ -784,9 +802,8 @@ extern "C" void SB200_FC(update_displacement_cuda)(long* Mesh_pointer, realw* de
     if (mp->b_corrector_pending) {  // deferred corrector of the previous step and this predictor in one pass
       mp->b_corrector_pending = false;
       if (mp->d_rmass_c) {
-        k_newmark_corrector_predictor_c<<<streaming_grid(((long long)mp->NGLOB_AB + 3) >> 2), 256, 0, mp->compute_stream>>>(
-            mp->d_b_displ, mp->d_b_veloc, mp->d_b_accel, mp->d_rmass_c, mp->d_rmass_exc, mp->rmass_nexc, (long long)mp->NGLOB_AB,
-            mp->pending_b_deltatover2, *deltat_F, *deltatsqover2_F, *deltatover2_F);
+        launch_newmark_cp_compact(mp, mp->d_b_displ, mp->d_b_veloc, mp->d_b_accel, mp->pending_b_deltatover2, *deltat_F,
+                                  *deltatsqover2_F, *deltatover2_F);
       } else {
         k_newmark_corrector_predictor<<<streaming_grid(n >> 2), 256, 0, mp->compute_stream>>>(
             mp->d_b_displ, mp->d_b_veloc, mp->d_b_accel, mp->d_rmassx, n, mp->pending_b_deltatover2, *deltat_F, *deltatsqover2_F,
@@ -805,9 +822,8 @@ extern "C" void SB200_FC(update_displacement_cuda)(long* Mesh_pointer, realw* de
     mp->corrector_pending = false;
     KernelTimer timer(mp, "newmark");
     if (mp->d_rmass_c) {
-      k_newmark_corrector_predictor_c<<<streaming_grid(((long long)mp->NGLOB_AB + 3) >> 2), 256, 0, mp->compute_stream>>>(
-          mp->d_displ, mp->d_veloc, mp->d_accel, mp->d_rmass_c, mp->d_rmass_exc, mp->rmass_nexc, (long long)mp->NGLOB_AB,
-          mp->pending_deltatover2, *deltat_F, *deltatsqover2_F, *deltatover2_F);
+      launch_newmark_cp_compact(mp, mp->d_displ, mp->d_veloc, mp->d_accel, mp->pending_deltatover2, *deltat_F, *deltatsqover2_F,
+                                *deltatover2_F);
     } else {
       k_newmark_corrector_predictor<<<streaming_grid(n >> 2), 256, 0, mp->compute_stream>>>(
           mp->d_displ, mp->d_veloc, mp->d_accel, mp->d_rmassx, n, mp->pending_deltatover2, *deltat_F, *deltatsqover2_F, *deltatover2_F);

@@ -73,6 +73,10 @@ struct PmlArgs {
   const realw* coef;
   const realw* wgll_cube;
   int store_strain;
+  // SPECFEM_B200_PML_PREFETCH: 1 (default) = the element's 89 coefficient / memory-variable planes are requested into L2 at
+  // kernel entry, 2 = into L1, 0 = not at all.  Measured on 77,868 C-PML elements: 1.296 -> 1.149 ms (0.78 -> 0.87 of the HBM
+  // roofline), L1 and L2 alike (profiles/r02aa_pml_prefetch_ab.jsonl)
+  int prefetch;
   realw *eps_xx, *eps_yy, *eps_xy, *eps_xz, *eps_yz;
 };
 
@@ -90,6 +94,16 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_pml_elastic_forces(const PmlAr
 
   const int ispec = a.list[bx];
   const int e = a.spec_to_CPML[ispec] - 1;
+  if (a.prefetch) {
+    // 41 + 48 planes of 512 B = 356 lines of 128 B, all of them needed further down by dependent loads: request them now
+    const char* c0 = reinterpret_cast<const char*>(a.coef + (size_t)e * PML_NCOEF * NGLL3_PADDED);
+    const char* r0 = reinterpret_cast<const char*>(a.rmem + (size_t)e * PML_NRMEM * NGLL3_PADDED);
+    for (int line = tx; line < (PML_NCOEF + PML_NRMEM) * 4; line += NGLL3_PADDED) {
+      const char* p = line < PML_NCOEF * 4 ? c0 + (size_t)line * 128 : r0 + (size_t)(line - PML_NCOEF * 4) * 128;
+      if (a.prefetch == 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+      else asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+    }
+  }
   const int irr = a.irregular_element_number[ispec] - 1;
   const size_t off = (size_t)ispec * NGLL3_PADDED + t;
   const int iglob = a.ibool[off] - 1;
@@ -384,6 +398,8 @@ inline void pml_compute_forces(DeviceMesh* mp, int iphase, int nspec_outer, int 
   a.displ_old = P->d_displ_old; a.displ_new = P->d_displ_new;
   a.rmem = P->d_rmem; a.coef = P->d_coef; a.wgll_cube = P->d_wgll_cube;
   a.store_strain = mp->compute_and_store_strain;
+  static const int pml_prefetch = getenv("SPECFEM_B200_PML_PREFETCH") ? atoi(getenv("SPECFEM_B200_PML_PREFETCH")) : 1;
+  a.prefetch = pml_prefetch;
   a.eps_xx = mp->d_epsilondev_xx; a.eps_yy = mp->d_epsilondev_yy; a.eps_xy = mp->d_epsilondev_xy;
   a.eps_xz = mp->d_epsilondev_xz; a.eps_yz = mp->d_epsilondev_yz;
   KernelTimer timer(mp, "pml_forces");
