@@ -338,7 +338,8 @@ inline void launch_elastic_kl_row_t(DeviceMesh* mp, const KlGrpArgs& aa, int ng)
 }
 inline void launch_elastic_kl_row(DeviceMesh* mp, const KlGrpArgs& aa, int ng) {
   // 3-stage ring, 125 registers, 3 CTAs / SM: 4.40 ms per 1M elements; 2-stage ring, 96 registers (76 B spilled), 4 CTAs: 4.91 ms
-  // without the producer warp four CTAs fit per SM (119 registers) -- and the kernel is slower: 4.80 ms (profiles/r02x_*)
+  // without the producer warp four CTAs fit per SM (119 registers) -- and the kernel is slower: 4.80 ms (profiles/r02x_*); held at
+  // three CTAs 4.92 ms, with an L2 prefetch of the next group's gather on top 5.06 ms (profiles/r02ab_kernel_run_kl_v*.json)
   if (mp->kl_kernel_variant == 1) launch_elastic_kl_row_t<3, 4, true>(mp, aa, ng);  // SPECFEM_B200_KL_KERNEL=1 (A/B)
   else launch_elastic_kl_row_t<3, 3>(mp, aa, ng);
 }

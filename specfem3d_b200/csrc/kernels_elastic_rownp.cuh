@@ -35,7 +35,8 @@ struct RowNpLayout {
 };
 
 // Measured and not kept (profiles/r02w_force_np_ab.jsonl): rotating the 75 plane-owner tasks over the four warps with the CTA
-// and group number (to even out the sub-partitions: 1.968 against 1.921 ms), an L2 prefetch of chunks 3 and 4 after B1 (no change).
+// and group number (to even out the sub-partitions: 1.968 against 1.921 ms), an L2 prefetch of chunks 3 and 4 after B1 (no change),
+// an L2 prefetch of the next group's 15 gather words per thread after B2 (2.080 against 1.938 ms, profiles/r02ab_force_gpf_ab.jsonl).
 template <int STAGES, int MAXREG, int RS>
 __global__ void __launch_bounds__(GRP_CONSUMERS) __maxnreg__(MAXREG) k_elastic_forces_rownp(const GrpArgs a) {
   using L = RowNpLayout<RS>;
