@@ -312,7 +312,9 @@ class DeviceRun:
                 db, L, M = r.db, r.lib, r.Mesh_pointer
                 L.compute_forces_acoustic_cuda(M, iphase, db.nspec_outer_acoustic, db.nspec_inner_acoustic, 1)
                 if iphase == 1:
-                    if sim.spec.stacey:
+                    if sim.spec.stacey and sim.UNDO_ATTENUATION_AND_OR_PML:  # compute_stacey_acoustic.f90:369-372: no record kept
+                        L.compute_stacey_acoustic_undoatt_cuda(M, iphase, 1)
+                    elif sim.spec.stacey:
                         L.compute_stacey_acoustic_cuda(M, iphase, r.b_absorb_potential, 1)
                         if sim.SAVE_FORWARD:  # write_abs(IOABS_AC, b_absorb_potential, b_reclen_potential, it)
                             r.absorb_potential_history.append(r.b_absorb_potential.copy())

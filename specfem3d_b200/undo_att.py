@@ -22,8 +22,12 @@ Restated control flow:
 * compute_add_sources_viscoelastic_GPU                  same file :469-726 (adjoint sources; the forward source into b_accel)
 * prepare_timerun / prepare_attenuation                 prepare_timerun.F90:416-430, prepare_attenuation.f90:169-182
 
-Elastic domains (the reference stops for coupled runs: prepare_timerun.F90:236-239), with or without ATTENUATION, Stacey or
-free boundaries, several ranks (host-staged halo), no C-PML, no APPROXIMATE_HESS_KL.  What the Fortran solver keeps in
+* compute_forces_acoustic_backward_calling / _forward_calling   compute_forces_acoustic_calling_routine.f90:344-520, 28-342
+* compute_stacey_acoustic_GPU, UNDO_ATT branch          compute_stacey_acoustic.f90:369-372
+* compute_add_sources_acoustic_backward_GPU             compute_add_sources_acoustic.f90:560-690
+
+Elastic OR acoustic domains (the reference stops for coupled runs: prepare_timerun.F90:236-239), with or without ATTENUATION,
+Stacey or free boundaries, several ranks (host-staged halo), no C-PML, no APPROXIMATE_HESS_KL.  What the Fortran solver keeps in
 ``proc*_save_frame_at*.bin`` files is kept in memory in an :class:`UndoAttProducts` object.
 """
 from __future__ import annotations
@@ -48,24 +52,28 @@ def subset_schedule(NSTEP: int, NT_DUMP_ATTENUATION: int):
 
 @dataclass
 class UndoAttProducts:
-    """frames[ir][s]: what proc%06d_save_frame_at%06d.bin (s + 1) holds for rank ir: displ, veloc, accel (NGLOB, 3) and, with
-    ATTENUATION, R_xx ... R_trace (NSPEC, 125, N_SLS) at the start of forward subset s + 1."""
+    """frames[ir][s]: what proc%06d_save_frame_at%06d.bin (s + 1) holds for rank ir at the start of forward subset s + 1: the
+    potentials (NGLOB) of a fluid rank; displ, veloc, accel (NGLOB, 3) and, with ATTENUATION, R_xx ... R_trace
+    (NSPEC, 125, N_SLS) of a solid one."""
     frames: List[List[dict]] = field(default_factory=list)
 
 
 def run_forward_and_save_undoatt(sim, lib=None, halo: str = "host"):
     """SIMULATION_TYPE = 1, SAVE_FORWARD, UNDO_ATTENUATION_AND_OR_PML: returns (the finished DeviceRun, UndoAttProducts)."""
     assert sim.SIMULATION_TYPE == 1 and sim.SAVE_FORWARD and sim.UNDO_ATTENUATION_AND_OR_PML
-    if sim.ACOUSTIC_SIMULATION or sim.PML_CONDITIONS:
-        raise NotImplementedError("undo-attenuation runs: elastic domains without C-PML")
+    if (sim.ACOUSTIC_SIMULATION and sim.ELASTIC_SIMULATION) or sim.PML_CONDITIONS:
+        raise NotImplementedError("undo-attenuation runs: elastic or acoustic domains (not coupled), no C-PML")
     run = DeviceRun(sim, lib=lib, halo=halo)
     prod = UndoAttProducts(frames=[[] for _ in run.ranks])
     _, nsub, lengths = subset_schedule(sim.NSTEP, sim.NT_DUMP_ATTENUATION)
     for s in range(nsub):
         for ir, r in enumerate(run.ranks):  # save_forward_arrays_undoatt
             f = {}
-            f["displ"], f["veloc"], f["accel"] = r.fields_el()
-            if sim.ATTENUATION:
+            if r.ACOUSTIC:
+                f["pot"], f["pot_dot"], f["pot_dot_dot"] = r.fields_ac()
+            if r.ELASTIC:
+                f["displ"], f["veloc"], f["accel"] = r.fields_el()
+            if r.ELASTIC and sim.ATTENUATION:
                 n = r.db.NSPEC_AB
                 R = [np.zeros((n, NGLL3, N_SLS), np.float32) for _ in range(6)]
                 r.lib.transfer_rmemory_from_device(r.Mesh_pointer, *R, N_SLS * NGLL3 * n)
@@ -81,8 +89,8 @@ class UndoAttKernelRun(DeviceRun):
 
     def __init__(self, sim, products: UndoAttProducts, adj: np.ndarray, lib=None, halo: str = "host"):
         assert sim.SIMULATION_TYPE == 3 and not sim.SAVE_FORWARD and sim.UNDO_ATTENUATION_AND_OR_PML
-        if sim.ACOUSTIC_SIMULATION or sim.PML_CONDITIONS or sim.APPROXIMATE_HESS_KL:
-            raise NotImplementedError("undo-attenuation kernel runs: elastic domains, no C-PML, no approximate Hessian")
+        if (sim.ACOUSTIC_SIMULATION and sim.ELASTIC_SIMULATION) or sim.PML_CONDITIONS or sim.APPROXIMATE_HESS_KL:
+            raise NotImplementedError("undo-attenuation kernel runs: elastic or acoustic domains (not coupled), no C-PML, no approximate Hessian")
         if halo != "host":
             raise NotImplementedError("kernel runs exchange the b_ fields through the host-staged halo")
         super().__init__(sim, lib=lib, halo=halo)
@@ -95,7 +103,9 @@ class UndoAttKernelRun(DeviceRun):
             n = r.db.NSPEC_AB
             r.rho_kl, r.mu_kl, r.kappa_kl = (np.zeros((n, 5, 5, 5), np.float32) for _ in range(3))
             r.cijkl_kl = np.zeros((n, 5, 5, 5, 21), np.float32) if sim.ANISOTROPIC_KL else np.zeros(1, np.float32)
+            r.rho_ac_kl, r.kappa_ac_kl = (np.zeros((n, 5, 5, 5), np.float32) for _ in range(2))
             r.b_displ = np.zeros((r.db.NGLOB_AB, 3), np.float32)
+            r.b_pot, r.b_pot_dot_dot = (np.zeros(r.db.NGLOB_AB, np.float32) for _ in range(2))
         # prepare_timerun.F90:418-422: the reconstructed wavefield moves forward, b_deltat = deltat
         self.dts = (float(sim.deltat), float(sim.deltatover2), float(sim.deltatsqover2))
         self.b_dts = self.dts
@@ -107,14 +117,17 @@ class UndoAttKernelRun(DeviceRun):
         assert nstep is None, "an undo-attenuation kernel run always covers all NSTEP steps"
         sim, NSTEP = self.sim, self.sim.NSTEP
         E = [r for r in self.ranks if r.ELASTIC]
+        A = [r for r in self.ranks if r.ACOUSTIC]
         self.it = 0
         for iteration_on_subset in range(1, self.nsubset + 1):
             # ---- read_forward_arrays_undoatt: frame NSUBSET_ITERATIONS - iteration_on_subset + 1 -> b_ fields ----
             frame = self.nsubset - iteration_on_subset  # 0-based
             for ir, r in enumerate(self.ranks):
+                f, n = self.products.frames[ir][frame], r.db.NGLOB_AB
+                if r.ACOUSTIC:
+                    r.lib.transfer_b_fields_ac_to_device(n, f["pot"], f["pot_dot"], f["pot_dot_dot"], r.Mesh_pointer)
                 if not r.ELASTIC:
                     continue
-                f, n = self.products.frames[ir][frame], r.db.NGLOB_AB
                 r.lib.transfer_b_fields_to_device(3 * n, f["displ"], f["veloc"], f["accel"], r.Mesh_pointer)
                 if self.att:
                     r.lib.transfer_b_rmemory_to_device(r.Mesh_pointer, *f["R"], N_SLS * NGLL3 * r.db.NSPEC_AB)
@@ -123,16 +136,29 @@ class UndoAttKernelRun(DeviceRun):
             it_temp, seismo_temp = self.it, [r.seismo_current for r in self.ranks]
             # forward subsets are full except the LAST one, which the kernel run takes first (:338-346)
             it_subset_end = NSTEP - (self.nsubset - 1) * self.nt_dump if iteration_on_subset == 1 else self.nt_dump
-            buffers = [np.zeros((it_subset_end,) + r.b_displ.shape, np.float32) for r in self.ranks]
+            buffers = [np.zeros((it_subset_end,) + r.b_displ.shape, np.float32) if r.ELASTIC else None for r in self.ranks]
+            # b_potential_acoustic_buffer, b_potential_dot_dot_acoustic_buffer
+            buffers_ac = [np.zeros((2, it_subset_end, r.db.NGLOB_AB), np.float32) if r.ACOUSTIC else None for r in self.ranks]
             # ---- the forward wavefield over this subset, forward in time ----
             for it_of_this_subset in range(1, it_subset_end + 1):
                 self.it += 1
                 b_dt, b_dt2, b_dtsq2 = self.b_dts
-                for r in E:  # update_displ_Newmark_backward
+                for r in A:  # update_displ_Newmark_backward: fluid first
+                    r.lib.update_displacement_ac_cuda(r.Mesh_pointer, b_dt, b_dt2, b_dtsq2, 3)
+                for r in E:
                     r.lib.update_displacement_cuda(r.Mesh_pointer, b_dt, b_dt2, b_dtsq2, 3)
                 it_tmp = NSTEP - (self.nsubset - iteration_on_subset) * self.nt_dump - it_of_this_subset + 1
-                self._elastic_backward(it_tmp)
+                if A:
+                    self._acoustic_one_field(it_tmp, 3)
+                if E:
+                    self._elastic_backward(it_tmp)
                 for ir, r in enumerate(self.ranks):  # b_displ_elastic_buffer(:,:,it_of_this_subset) = b_displ
+                    if r.ACOUSTIC:
+                        n = r.db.NGLOB_AB
+                        r.lib.transfer_b_potential_ac_from_device(n, r.b_pot, r.Mesh_pointer)
+                        r.lib.transfer_b_potential_dot_dot_ac_from_device(n, r.b_pot_dot_dot, r.Mesh_pointer)
+                        buffers_ac[ir][0, it_of_this_subset - 1] = r.b_pot
+                        buffers_ac[ir][1, it_of_this_subset - 1] = r.b_pot_dot_dot
                     if r.ELASTIC:
                         r.lib.transfer_b_displ_from_device(3 * r.db.NGLOB_AB, r.b_displ, r.Mesh_pointer)
                         buffers[ir][it_of_this_subset - 1] = r.b_displ
@@ -146,17 +172,30 @@ class UndoAttKernelRun(DeviceRun):
                 self.it += 1
                 it = self.it
                 for ir, r in enumerate(self.ranks):
+                    if r.ACOUSTIC:
+                        n = r.db.NGLOB_AB
+                        r.b_pot[...] = buffers_ac[ir][0, it_subset_end - it_of_this_subset]
+                        r.b_pot_dot_dot[...] = buffers_ac[ir][1, it_subset_end - it_of_this_subset]
+                        r.lib.transfer_b_potential_ac_to_device(n, r.b_pot, r.Mesh_pointer)
+                        r.lib.transfer_b_potential_dot_dot_ac_to_device(n, r.b_pot_dot_dot, r.Mesh_pointer)
                     if r.ELASTIC:
                         r.b_displ[...] = buffers[ir][it_subset_end - it_of_this_subset]
                         r.lib.transfer_b_displ_to_device(3 * r.db.NGLOB_AB, r.b_displ, r.Mesh_pointer)
                 dt, dt2, dtsq2 = self.dts
-                for r in E:  # update_displ_Newmark
+                for r in A:  # update_displ_Newmark
+                    r.lib.update_displacement_ac_cuda(r.Mesh_pointer, dt, dt2, dtsq2, 1)
+                for r in E:
                     r.lib.update_displacement_cuda(r.Mesh_pointer, dt, dt2, dtsq2, 1)
-                self._elastic_adjoint(it)
+                if A:
+                    self._acoustic_one_field(it, 1)
+                if E:
+                    self._elastic_adjoint(it)
                 if sim.receivers is not None and (it - 1) % sim.NTSTEP_BETWEEN_OUTPUT_SAMPLE == 0:
                     self._seismograms(it)
                 for r in E:  # compute_kernels: the library re-computes the strain of b_displ (compute_kernels_cuda.cu:57-100)
                     r.lib.compute_kernels_elastic_cuda(r.Mesh_pointer, dt)
+                for r in A:
+                    r.lib.compute_kernels_acoustic_cuda(r.Mesh_pointer, dt)
         assert self.it == NSTEP
         return self
 
@@ -186,6 +225,40 @@ class UndoAttKernelRun(DeviceRun):
                 r.lib.transfer_asmbl_accel_to_device(r.Mesh_pointer, r.b_buffer_recv_vector if foa == 3 else r.buffer_recv_vector,
                                                      db.num_interfaces_ext_mesh, db.max_nibool_interfaces_ext_mesh,
                                                      db.nibool_interfaces_ext_mesh, db.ibool_interfaces_ext_mesh, foa)
+
+    def _acoustic_one_field(self, it: int, foa: int):
+        """foa = 3: compute_forces_acoustic_backward_calling on the re-computed potentials (``it`` = it_tmp of the subset);
+        foa = 1: compute_forces_acoustic_forward_calling on the adjoint potentials."""
+        sim, NSTEP = self.sim, self.sim.NSTEP
+        _, dt2, _ = self.dts
+        _, b_dt2, _ = self.b_dts
+        A = [r for r in self.ranks if r.ACOUSTIC]
+        sifs = int(sim.spec.stacey_instead_of_free_surface)
+        for r in A:
+            r.lib.acoustic_enforce_free_surf_cuda(r.Mesh_pointer, sifs, foa)
+        for iphase in (1, 2):
+            for r in A:
+                db, L, M = r.db, r.lib, r.Mesh_pointer
+                L.compute_forces_acoustic_cuda(M, iphase, db.nspec_outer_acoustic, db.nspec_inner_acoustic, foa)
+                if iphase == 1:
+                    if sim.spec.stacey:
+                        L.compute_stacey_acoustic_undoatt_cuda(M, iphase, foa)
+                    zero_runs = np.zeros(sim.sources.NSOURCES, np.int32) if sim.sources is not None else None
+                    if foa == 1 and r.nrec_local > 0 and it < NSTEP:  # compute_add_sources_acoustic_GPU: the adjoint sources only
+                        L.add_sources_ac_sim_2_or_3_cuda(M, r.source_adjoint, sim.receivers.nrec, r.nrec_local, NSTEP, it)
+                    if foa == 3 and sim.sources is not None:  # compute_add_sources_acoustic_backward_GPU: time (NSTEP - it_tmp) DT - t0
+                        L.compute_add_sources_ac_s3_cuda(M, sim.sources.NSOURCES, sim.stf_pre_compute_acoustic(NSTEP - it + 1), zero_runs)
+            if self.NPROC > 1:
+                if iphase == 1:
+                    for r in A:
+                        r.lib.transfer_boun_pot_from_device(r.Mesh_pointer, r.b_buffer_send_scalar if foa == 3 else r.buffer_send_scalar, foa)
+                    self.exchange.exchange("b_scalar" if foa == 3 else "scalar")
+                else:
+                    for r in A:
+                        r.lib.transfer_asmbl_pot_to_device(r.Mesh_pointer, r.b_buffer_recv_scalar if foa == 3 else r.buffer_recv_scalar, foa)
+        for r in A:
+            r.lib.kernel_3_acoustic_cuda(r.Mesh_pointer, dt2, b_dt2, foa)
+            r.lib.acoustic_enforce_free_surf_cuda(r.Mesh_pointer, sifs, foa)
 
     def _elastic_backward(self, it_tmp: int):
         """compute_forces_viscoelastic_backward_calling: the re-computed forward wavefield, FORWARD_OR_ADJOINT = 3."""
@@ -239,4 +312,13 @@ class UndoAttKernelRun(DeviceRun):
             if r.ELASTIC:
                 r.lib.transfer_kernels_el_to_host(r.Mesh_pointer, r.rho_kl, r.mu_kl, r.kappa_kl, r.cijkl_kl, r.db.NSPEC_AB)
             out.append((r.rho_kl, r.cijkl_kl) if self.sim.ANISOTROPIC_KL else (r.rho_kl, r.mu_kl, r.kappa_kl))
+        return out
+
+    def kernels_ac(self):
+        """[(rho_ac_kl, kappa_ac_kl)] per rank."""
+        out = []
+        for r in self.ranks:
+            if r.ACOUSTIC:
+                r.lib.transfer_kernels_ac_to_host(r.Mesh_pointer, r.rho_ac_kl, r.kappa_ac_kl, r.db.NSPEC_AB)
+            out.append((r.rho_ac_kl, r.kappa_ac_kl))
         return out

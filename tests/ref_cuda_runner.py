@@ -35,6 +35,7 @@ def factories():
         "kernel_run_coupled": lambda: kernel_run_case("coupled"),
         "kernel_run_undoatt": lambda: kernel_run_case("undoatt"),
         "kernel_run_undoatt_visco": lambda: kernel_run_case("undoatt_visco"),
+        "kernel_run_undoatt_acoustic": lambda: kernel_run_case("undoatt_acoustic"),
     }
 
 
@@ -55,6 +56,32 @@ def coupled_kernel_sim(nstep, sim_type):
     sim.SAVE_SEISMOGRAMS_PRESSURE = False
     sim.SIMULATION_TYPE, sim.SAVE_FORWARD = sim_type, sim_type == 1
     return sim
+
+
+def undoatt_acoustic_sim(nstep, sim_type, nproc=(1, 1), nt_dump=50):
+    import test_oracle_kernel_run as K
+
+    sim = K.acoustic_kernel_sim(nproc, nstep, sim_type=sim_type)
+    sim.UNDO_ATTENUATION_AND_OR_PML, sim.NT_DUMP_ATTENUATION = True, nt_dump
+    return sim
+
+
+def run_undoatt_acoustic_case(lib, adj_path=None, nproc=(1, 1)):
+    from specfem3d_b200.undo_att import UndoAttKernelRun, run_forward_and_save_undoatt
+
+    n = kernel_run_case.NSTEP
+    fwd, prod = run_forward_and_save_undoatt(undoatt_acoustic_sim(n, 1, nproc), lib=lib)
+    seis = fwd.gather_seismograms("p")
+    if adj_path is not None and os.path.exists(adj_path):
+        adj = np.load(adj_path)
+    else:
+        adj = ((1e3 / np.abs(seis).max()) * seis).astype(np.float32)
+        if adj_path is not None:
+            np.save(adj_path, adj)
+    k = UndoAttKernelRun(undoatt_acoustic_sim(n, 3, nproc), prod, adj, lib=lib).run()
+    rho_ac, kappa_ac = k.kernels_ac()[0]
+    out = {"d_forward": seis, "pot": k.ranks[0].fields_ac()[0], "rho_ac_kl": rho_ac.copy(), "kappa_ac_kl": kappa_ac.copy()}
+    return k, out
 
 
 def undoatt_kernel_sim(nstep, sim_type, visco, nproc=(1, 1), nt_dump=50):
@@ -88,6 +115,8 @@ def run_undoatt_case(lib, visco, adj_path=None, nproc=(1, 1)):
 
 
 def run_kernel_case(lib, kind="elastic", adj_path=None):
+    if kind == "undoatt_acoustic":
+        return run_undoatt_acoustic_case(lib, adj_path)
     if kind in ("undoatt", "undoatt_visco"):
         return run_undoatt_case(lib, kind == "undoatt_visco", adj_path)
     """``adj_path``: .npy with the adjoint sources; written if it does not exist yet (the first library to run derives them

@@ -403,3 +403,37 @@ def test_undo_attenuation_run_viscoelastic(device_lib):
     for t, a in zip(tot, (rho, mu, kappa)):
         assert abs(t - np.linalg.norm(a.astype(np.float64))) <= KERNEL_RTOL * np.linalg.norm(a.astype(np.float64))
     k2.cleanup()
+
+
+@pytest.mark.parametrize("nproc", [(1, 1), (2, 2)])
+def test_undo_attenuation_run_acoustic_equals_standard_kernel_run(device_lib, nproc):
+    """Purely acoustic mesh: potentials restored from the snapshots and re-computed forward in time (Sommerfeld condition
+    re-evaluated from b_potential_dot: compute_stacey_acoustic_undoatt_cuda), b_potential / b_potential_dot_dot buffered per
+    step; rho_ac_kl / kappa_ac_kl must equal those of the standard run (time-reversed reconstruction with the flux record)."""
+    import ref_cuda_runner as R
+    from specfem3d_b200.kernel_run import KernelRun, run_forward_and_save
+    from specfem3d_b200.undo_att import UndoAttKernelRun, run_forward_and_save_undoatt
+    from test_oracle_kernel_run import acoustic_adjoint_source, acoustic_kernel_sim
+
+    nstep = 120
+    fwd, prod = run_forward_and_save_undoatt(R.undoatt_acoustic_sim(nstep, 1, nproc), lib=device_lib)
+    seis_fwd = fwd.gather_seismograms("p")[..., 0]
+    fwd.cleanup()
+    adj = acoustic_adjoint_source(seis_fwd)
+    k = UndoAttKernelRun(R.undoatt_acoustic_sim(nstep, 3, nproc), prod, adj, lib=device_lib).run()
+    sk = k.gather_seismograms("p")[..., 0]
+    assert np.abs(seis_fwd).max() > 0
+    assert rel_l2(sk, seis_fwd[:, ::-1]) <= 2e-5  # the re-computed potentials repeat the forward run
+    fwd0, prod0 = run_forward_and_save(acoustic_kernel_sim(nproc, nstep), lib=device_lib)
+    fwd0.cleanup()
+    std = KernelRun(acoustic_kernel_sim(nproc, nstep, sim_type=3), prod0, adj, lib=device_lib).run()
+    mine, ref = k.kernels_ac(), std.kernels_ac()
+    for r in range(len(mine)):
+        assert rel_l2(k.ranks[r].fields_ac()[0], std.ranks[r].fields_ac()[0]) <= 1e-4
+    for i in range(2):
+        a = np.concatenate([kr[i].reshape(-1, 125) for kr in mine])
+        b = np.concatenate([kr[i].reshape(-1, 125) for kr in ref])
+        assert np.abs(b).max() > 0
+        assert rel_l2(a, b) <= 2 * KERNEL_RTOL, i
+    k.cleanup()
+    std.cleanup()
