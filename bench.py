@@ -479,7 +479,7 @@ def run_device(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def time_config(lib, sim, kernels, steps=12, warmup=3):
+def time_config(lib, sim, kernels, steps=12, warmup=3, sampler=None):
     """A few steps of `sim` on cuda:0 through the ABI; returns ms per step (device events are inside the library) and the
     per-step time of each named kernel."""
     import torch
@@ -490,6 +490,8 @@ def time_config(lib, sim, kernels, steps=12, warmup=3):
     for _ in range(warmup):
         run.step()
     torch.cuda.synchronize()
+    if sampler is not None:  # clocks are sampled under load only (not while the mesh is built)
+        sampler.start()
     t0 = time.perf_counter()
     for _ in range(steps):
         run.step()
@@ -627,7 +629,7 @@ def run_config(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device visible; the device path has no CPU fallback")
     lib = abi.load()
-    sampler = ClockSampler(0).start()
+    sampler = ClockSampler(0)
     if args.config == "cfg3":
         nex = tuple(int(v) for v in args.nex.split("x")) if args.nex != "128x128x64" else (160, 160, 80)
         sim = cfg3(nex, NSTEP=2 * (args.steps + args.warmup) + 8)
@@ -637,7 +639,7 @@ def run_config(args):
         sim = cfg4(nex, NSTEP=2 * (args.steps + args.warmup) + 8)
         names = ("acoustic_forces", "elastic_forces")
     db = sim.dbs[0]
-    ms, k, launches = time_config(lib, sim, names, steps=args.steps, warmup=args.warmup)
+    ms, k, launches = time_config(lib, sim, names, steps=args.steps, warmup=args.warmup, sampler=sampler)
     clocks = sampler.stop()
     peak, peak_src = measured_peaks()
     if args.config == "cfg3":
