@@ -108,7 +108,8 @@ class OraclePartition:
                if a is not None else
                ([None] * 6 + [P(st[k]) for k in ("epsilondev_xx", "epsilondev_yy", "epsilondev_xy", "epsilondev_xz",
                                                  "epsilondev_yz")] + [None] * 6 if st is not None else [None] * 17)),
-            P(st["epsilon_trace_over_3"]) if st is not None else None)
+            P(st["epsilon_trace_over_3"]) if st is not None else None,
+            P(db.cstore) if getattr(sim, "ANISOTROPY", False) else None, c_int(db.NSPEC_AB))
         if sim.PML_CONDITIONS and self.pml is not None:
             from . import pml_oracle
 

@@ -138,7 +138,7 @@ static inline void contract3w(const realw M[5][5], const realw* B1, const realw*
 
 /* -------------------------------------------------------------------------------------------------------------
  * compute_forces_viscoelastic, src/specfem3D/compute_forces_viscoelastic.F90:33-962 (isotropic; no LTS, no moho,
- * no Kelvin-Voigt, no anisotropy) + compute_element_att_memory_second_order_rk, compute_element_att_memory.f90:28-156.
+ * no Kelvin-Voigt; ANISOTROPY through `cstore`) + compute_element_att_memory_second_order_rk, compute_element_att_memory.f90:28-156.
  *
  * phase_ispec : this phase's column of phase_ispec_inner_elastic (1-based element ids), num_elements entries.
  * is_CPML     : may be NULL; PML elements are skipped here (:256).
@@ -157,7 +157,10 @@ void oracle_compute_forces_viscoelastic(
     int compute_and_store_strain, realw* R_xx, realw* R_yy, realw* R_xy, realw* R_xz, realw* R_yz, realw* R_trace,
     realw* epsilondev_xx, realw* epsilondev_yy, realw* epsilondev_xy, realw* epsilondev_xz, realw* epsilondev_yz,
     realw* epsilondev_trace, const realw* factor_common, const realw* factor_common_kappa, const realw* alphaval,
-    const realw* betaval, const realw* gammaval, realw* epsilon_trace_over_3 /* NULL unless SIMULATION_TYPE == 3 (:546,560) */) {
+    const realw* betaval, const realw* gammaval, realw* epsilon_trace_over_3 /* NULL unless SIMULATION_TYPE == 3 (:546,560) */,
+    const realw* cstore /* NULL = isotropic; ANISOTROPY (:578-614): c11,c12,c13,c14,c15,c16,c22,c23,c24,c25,c26,c33,c34,c35,c36,
+                           c44,c45,c46,c55,c56,c66 as [21][NSPEC][125] */,
+    int nspec_ab) {
   realw HP[5][5], HW[5][5]; /* HP[a][l] = hprime_xx(a,l) ; HW[a][l] = hprimewgll_xx(l,a) */
   for (int a = 0; a < 5; ++a)
     for (int l = 0; l < 5; ++l) {
@@ -298,6 +301,20 @@ void oracle_compute_forces_viscoelastic(
       realw sigma_xy = mul * duxdyl_plus_duydxl;
       realw sigma_xz = mul * duzdxl_plus_duxdzl;
       realw sigma_yz = mul * duzdyl_plus_duydzl;
+      if (cstore) { /* full anisotropic case (:580-612) */
+        const size_t P = (size_t)nspec_ab * NGLL3;
+        const realw* c = cstore + eo + p;
+        const realw c11 = c[0], c12 = c[P], c13 = c[2 * P], c14 = c[3 * P], c15 = c[4 * P], c16 = c[5 * P], c22 = c[6 * P],
+                    c23 = c[7 * P], c24 = c[8 * P], c25 = c[9 * P], c26 = c[10 * P], c33 = c[11 * P], c34 = c[12 * P],
+                    c35 = c[13 * P], c36 = c[14 * P], c44 = c[15 * P], c45 = c[16 * P], c46 = c[17 * P], c55 = c[18 * P],
+                    c56 = c[19 * P], c66 = c[20 * P];
+        sigma_xx = c11 * duxdxl + c16 * duxdyl_plus_duydxl + c12 * duydyl + c15 * duzdxl_plus_duxdzl + c14 * duzdyl_plus_duydzl + c13 * duzdzl;
+        sigma_yy = c12 * duxdxl + c26 * duxdyl_plus_duydxl + c22 * duydyl + c25 * duzdxl_plus_duxdzl + c24 * duzdyl_plus_duydzl + c23 * duzdzl;
+        sigma_zz = c13 * duxdxl + c36 * duxdyl_plus_duydxl + c23 * duydyl + c35 * duzdxl_plus_duxdzl + c34 * duzdyl_plus_duydzl + c33 * duzdzl;
+        sigma_xy = c16 * duxdxl + c66 * duxdyl_plus_duydxl + c26 * duydyl + c56 * duzdxl_plus_duxdzl + c46 * duzdyl_plus_duydzl + c36 * duzdzl;
+        sigma_xz = c15 * duxdxl + c56 * duxdyl_plus_duydxl + c25 * duydyl + c55 * duzdxl_plus_duxdzl + c45 * duzdyl_plus_duydzl + c35 * duzdzl;
+        sigma_yz = c14 * duxdxl + c46 * duxdyl_plus_duydxl + c24 * duydyl + c45 * duzdxl_plus_duxdzl + c44 * duzdyl_plus_duydzl + c34 * duzdzl;
+      }
 
       if (attenuation) {
         const size_t ro = (eo + p) * N_SLS;

@@ -91,6 +91,7 @@ struct DeviceMesh {
   int* d_irregular_element_number = nullptr;  // [NSPEC]
   realw* d_metric = nullptr;  // [NSPEC_IRREGULAR][9][128] : xix,xiy,xiz,etax,etay,etaz,gammax,gammay,gammaz planes
   realw *d_kappav = nullptr, *d_muv = nullptr, *d_rhostore = nullptr;  // [NSPEC][128]
+  realw* d_cstore = nullptr;  // ANISOTROPY: the 21 elastic coefficients c11 ... c66 as planes [21][NSPEC][128]
   realw *d_rho_vp = nullptr, *d_rho_vs = nullptr;                      // [NSPEC][125]
   realw* d_kappastore_unpadded = nullptr;                              // [NSPEC][125] (acoustic sources, Stacey)
   int *d_ispec_is_inner = nullptr, *d_ispec_is_elastic = nullptr, *d_ispec_is_acoustic = nullptr;

@@ -40,6 +40,10 @@ struct ElasticArgs {
   // prepare_fields_elastic_adj_dev) instead of the __constant__ ones of the forward / adjoint wavefield
   int use_abg = 0;
   realw abg[3 * N_SLS] = {0};
+  // ANISOTROPY: c11, c12, c13, c14, c15, c16, c22, c23, c24, c25, c26, c33, c34, c35, c36, c44, c45, c46, c55, c56, c66
+  // (the argument order of prepare_fields_elastic_device) as planes [21][NSPEC][128]; cplane = NSPEC * 128
+  const realw* cstore = nullptr;
+  size_t cplane = 0;
 };
 
 // ncu on the attenuation kernel (profiles/r01g_secondary_kernels.md): 73 % of every issue slot's latency is a long
@@ -72,7 +76,9 @@ __device__ __forceinline__ void prefetch_attenuation_planes(const ElasticArgs& a
 }
 
 // One thread per GLL point.  ATT: attenuation (implies strain storage).  STRAIN: store epsilondev without attenuation.
-template <bool ATT, bool STRAIN>
+// ANISO: full 21-coefficient Hooke's law (replaces Kernel_2_noatt_ani_impl, Kernel_2_viscoelastic_impl.cu:1885-2240, and the
+// ANISOTROPY branch of Kernel_2_att_impl; CPU: compute_forces_viscoelastic.F90:578-614).
+template <bool ATT, bool STRAIN, bool ANISO = false>
 __global__ void __launch_bounds__(NGLL3_PADDED) k_elastic_forces_pt(const ElasticArgs a) {
   const size_t cs = vstride(a.nglob);  // distance between the components of one point (kernels_common.cuh)
   const int bx = blockIdx.x;
@@ -181,15 +187,33 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_elastic_forces_pt(const Elasti
     e_xy = 0.5f * (duxdyl + duydxl); e_xz = 0.5f * (duzdxl + duxdzl); e_yz = 0.5f * (duzdyl + duydzl);
   }
 
-  // isotropic stress
-  const realw lambdalplus2mul = kappal + 1.33333333333333333333f * mul;
-  const realw lambdal = lambdalplus2mul - 2.0f * mul;
-  realw sigma_xx = lambdalplus2mul * duxdxl + lambdal * (duydyl + duzdzl);
-  realw sigma_yy = lambdalplus2mul * duydyl + lambdal * (duxdxl + duzdzl);
-  realw sigma_zz = lambdalplus2mul * duzdzl + lambdal * (duxdxl + duydyl);
-  realw sigma_xy = mul * (duxdyl + duydxl);
-  realw sigma_xz = mul * (duzdxl + duxdzl);
-  realw sigma_yz = mul * (duzdyl + duydzl);
+  realw sigma_xx, sigma_yy, sigma_zz, sigma_xy, sigma_xz, sigma_yz;
+  if (ANISO) {
+    // full anisotropic stress, term order of compute_forces_viscoelastic.F90:601-612
+    const realw* cp = a.cstore + off;
+    const size_t P = a.cplane;
+    const realw c11 = cp[0], c12 = cp[P], c13 = cp[2 * P], c14 = cp[3 * P], c15 = cp[4 * P], c16 = cp[5 * P], c22 = cp[6 * P],
+                c23 = cp[7 * P], c24 = cp[8 * P], c25 = cp[9 * P], c26 = cp[10 * P], c33 = cp[11 * P], c34 = cp[12 * P],
+                c35 = cp[13 * P], c36 = cp[14 * P], c44 = cp[15 * P], c45 = cp[16 * P], c46 = cp[17 * P], c55 = cp[18 * P],
+                c56 = cp[19 * P], c66 = cp[20 * P];
+    const realw dxy = duxdyl + duydxl, dzx = duzdxl + duxdzl, dzy = duzdyl + duydzl;
+    sigma_xx = c11 * duxdxl + c16 * dxy + c12 * duydyl + c15 * dzx + c14 * dzy + c13 * duzdzl;
+    sigma_yy = c12 * duxdxl + c26 * dxy + c22 * duydyl + c25 * dzx + c24 * dzy + c23 * duzdzl;
+    sigma_zz = c13 * duxdxl + c36 * dxy + c23 * duydyl + c35 * dzx + c34 * dzy + c33 * duzdzl;
+    sigma_xy = c16 * duxdxl + c66 * dxy + c26 * duydyl + c56 * dzx + c46 * dzy + c36 * duzdzl;
+    sigma_xz = c15 * duxdxl + c56 * dxy + c25 * duydyl + c55 * dzx + c45 * dzy + c35 * duzdzl;
+    sigma_yz = c14 * duxdxl + c46 * dxy + c24 * duydyl + c45 * dzx + c44 * dzy + c34 * duzdzl;
+  } else {
+    // isotropic stress
+    const realw lambdalplus2mul = kappal + 1.33333333333333333333f * mul;
+    const realw lambdal = lambdalplus2mul - 2.0f * mul;
+    sigma_xx = lambdalplus2mul * duxdxl + lambdal * (duydyl + duzdzl);
+    sigma_yy = lambdalplus2mul * duydyl + lambdal * (duxdxl + duzdzl);
+    sigma_zz = lambdalplus2mul * duzdzl + lambdal * (duxdxl + duydyl);
+    sigma_xy = mul * (duxdyl + duydxl);
+    sigma_xz = mul * (duzdxl + duxdzl);
+    sigma_yz = mul * (duzdyl + duydzl);
+  }
 
   realw Rxx[N_SLS], Ryy[N_SLS], Rxy[N_SLS], Rxz[N_SLS], Ryz[N_SLS], Rtr[N_SLS];
   const size_t roff = (size_t)ispec * N_SLS * NGLL3_PADDED + t;

@@ -362,7 +362,6 @@ extern "C" void SB200_FC(prepare_fields_elastic_device)(
     realw* c36store, realw* c44store, realw* c45store, realw* c46store, realw* c55store, realw* c56store,
     realw* c66store) {
   DeviceMesh* mp = get_mesh(Mesh_pointer);
-  if (*ANISOTROPY) exit_on_error("ANISOTROPY is not part of this round's hot path (isotropic elastic / viscoelastic only)");
   if (*NOISE_TOMOGRAPHY) exit_on_error("NOISE_TOMOGRAPHY is out of scope of this library");
   const size_t nglob = mp->NGLOB_AB, nspec = mp->NSPEC_AB;
 
@@ -430,6 +429,21 @@ extern "C" void SB200_FC(prepare_fields_elastic_device)(
   (void)b_absorb_field;
   mp->d_kappav = dev_copy_padded<realw>(h_kappav, nspec, 0.f);
   mp->d_muv = dev_copy_padded<realw>(h_muv, nspec, 0.f);
+  mp->anisotropy = *ANISOTROPY != 0;
+  if (mp->anisotropy) {
+    // the 21 coefficient arrays (each (NGLLX,NGLLY,NGLLZ,NSPEC_ANISO), NSPEC_ANISO = NSPEC_AB) as planes [21][NSPEC][128]
+    if (mp->pml_conditions && mp->NSPEC_CPML > 0) exit_on_error("prepare_fields_elastic_device: ANISOTROPY with C-PML is not implemented");
+    if (mp->simulation_type == 3) exit_on_error("prepare_fields_elastic_device: ANISOTROPY in kernel runs is not implemented");
+    const realw* cs[21] = {c11store, c12store, c13store, c14store, c15store, c16store, c22store, c23store, c24store, c25store, c26store,
+                           c33store, c34store, c35store, c36store, c44store, c45store, c46store, c55store, c56store, c66store};
+    const size_t plane = nspec * NGLL3_PADDED;
+    mp->d_cstore = dev_alloc<realw>(21 * plane);
+    std::vector<realw> tmp(plane, 0.f);
+    for (int c = 0; c < 21; ++c) {
+      for (size_t e = 0; e < nspec; ++e) memcpy(&tmp[e * NGLL3_PADDED], cs[c] + e * NGLL3, NGLL3 * sizeof(realw));
+      CUDA_CHECK(cudaMemcpy(mp->d_cstore + c * plane, tmp.data(), plane * sizeof(realw), cudaMemcpyHostToDevice));
+    }
+  }
 
   mp->compute_and_store_strain = *COMPUTE_AND_STORE_STRAIN;
   if (mp->compute_and_store_strain) {
@@ -569,7 +583,7 @@ extern "C" void SB200_FC(prepare_cleanup_device)(long* Mesh_pointer, int* ACOUST
   pml_destroy(mp);
   group_store_free(mp->grp_elastic);
   group_store_free(mp->grp_acoustic);
-  void* dptrs[] = {mp->d_ibool, mp->d_irregular_element_number, mp->d_metric, mp->d_kappav, mp->d_muv, mp->d_rhostore,
+  void* dptrs[] = {mp->d_ibool, mp->d_irregular_element_number, mp->d_metric, mp->d_kappav, mp->d_muv, mp->d_rhostore, mp->d_cstore,
                    mp->d_rho_vp, mp->d_rho_vs, mp->d_kappastore_unpadded, mp->d_ispec_is_inner, mp->d_ispec_is_elastic,
                    mp->d_ispec_is_acoustic, mp->d_phase_ispec_inner_elastic, mp->d_phase_ispec_inner_acoustic,
                    mp->d_displ, mp->d_veloc, mp->d_accel, mp->d_potential, mp->d_potential_dot, mp->d_potential_dot_dot,
@@ -820,6 +834,10 @@ extern "C" void SB200_FC(update_displacement_cuda)(long* Mesh_pointer, realw* de
   if (mp->corrector_pending) {
     // the corrector kernel_3_a_cuda deferred at the end of the previous step and this predictor in one pass
     mp->corrector_pending = false;
+    const bool pml = mp->pml_conditions && mp->NSPEC_CPML > 0;
+    // C-PML: PML_displ_old from the wavefields as the pending corrector leaves them, PML_displ_new after the predictor
+    if (pml) pml_snapshot_displ(mp, /*which=*/0, *deltat_F, *deltatsqover2_F, *deltatover2_F, true, mp->pending_deltatover2);
+    {
     KernelTimer timer(mp, "newmark");
     if (mp->d_rmass_c) {
       launch_newmark_cp_compact(mp, mp->d_displ, mp->d_veloc, mp->d_accel, mp->pending_deltatover2, *deltat_F, *deltatsqover2_F,
@@ -829,6 +847,8 @@ extern "C" void SB200_FC(update_displacement_cuda)(long* Mesh_pointer, realw* de
           mp->d_displ, mp->d_veloc, mp->d_accel, mp->d_rmassx, n, mp->pending_deltatover2, *deltat_F, *deltatsqover2_F, *deltatover2_F);
     }
     KERNEL_CHECK(mp, "k_newmark_corrector_predictor");
+    }
+    if (pml) pml_snapshot_displ(mp, /*which=*/1, *deltat_F, *deltatsqover2_F, *deltatover2_F);
     return;
   }
   if (mp->pml_conditions && mp->NSPEC_CPML > 0) pml_snapshot_displ(mp, /*which=*/0, *deltat_F, *deltatsqover2_F, *deltatover2_F);
@@ -876,7 +896,7 @@ extern "C" void SB200_FC(kernel_3_a_cuda)(long* Mesh_pointer, realw* deltatover2
     return;
   }
   if (mp->corrector_pending) flush_corrector_impl(mp);
-  if (mp->fuse_newmark && *APPROXIMATE_OCEAN_LOAD == 0 && !(mp->pml_conditions && mp->NSPEC_CPML > 0)) {
+  if (mp->fuse_newmark && *APPROXIMATE_OCEAN_LOAD == 0) {  // C-PML included: the snapshots of the next step apply it on the fly
     // deferred: update_displacement_cuda of the next step applies it together with the predictor; compute_seismograms_cuda
     // evaluates it on the fly at the receivers; every other entry point flushes it first (device_mesh.h: get_mesh)
     mp->corrector_pending = true;
@@ -973,9 +993,15 @@ static void launch_elastic(DeviceMesh* mp, int nb, const int* phase_list, int fi
 
   const bool att = mp->attenuation != 0;
   const bool strain = mp->compute_and_store_strain != 0;
-  // one-thread-per-point path: attenuation / strain storage, and SPECFEM_B200_FORCE_KERNEL=1 (A/B of the default kernel)
+  // one-thread-per-point path: attenuation / strain storage, anisotropy, and SPECFEM_B200_FORCE_KERNEL=1 (A/B of the default kernel)
   KernelTimer timer(mp, att ? "elastic_forces_attenuation" : (strain ? "elastic_forces_strain" : "elastic_forces_pointwise"));
-  if (att) k_elastic_forces_pt<true, true><<<nb, NGLL3_PADDED, 0, mp->compute_stream>>>(a);
+  if (mp->anisotropy) {
+    a.cstore = mp->d_cstore;
+    a.cplane = (size_t)mp->NSPEC_AB * NGLL3_PADDED;
+    if (att) k_elastic_forces_pt<true, true, true><<<nb, NGLL3_PADDED, 0, mp->compute_stream>>>(a);
+    else if (strain) k_elastic_forces_pt<false, true, true><<<nb, NGLL3_PADDED, 0, mp->compute_stream>>>(a);
+    else k_elastic_forces_pt<false, false, true><<<nb, NGLL3_PADDED, 0, mp->compute_stream>>>(a);
+  } else if (att) k_elastic_forces_pt<true, true><<<nb, NGLL3_PADDED, 0, mp->compute_stream>>>(a);
   else if (strain) k_elastic_forces_pt<false, true><<<nb, NGLL3_PADDED, 0, mp->compute_stream>>>(a);
   else k_elastic_forces_pt<false, false><<<nb, NGLL3_PADDED, 0, mp->compute_stream>>>(a);
   KERNEL_CHECK(mp, "elastic forces");
@@ -1168,7 +1194,8 @@ extern "C" void SB200_FC(compute_forces_viscoelastic_cuda)(long* Mesh_pointer, i
     }
     return;
   }
-  const bool att_grp = mp->force_kernel_variant != 1 && mp->attenuation;  // viscoelastic row kernel + attenuation store
+  // ANISOTROPY: the one-thread-per-point kernel (21 coefficient planes per element; the row kernels are isotropic)
+  const bool att_grp = mp->force_kernel_variant != 1 && mp->attenuation && !mp->anisotropy;  // viscoelastic row kernel + attenuation store
   if (num_elements > 0 && att_grp) {
     ensure_elastic_groups(mp, *nspec_outer_elastic, *nspec_inner_elastic);
     if (mp->use_mesh_coloring_gpu) {
@@ -1185,7 +1212,7 @@ extern "C" void SB200_FC(compute_forces_viscoelastic_cuda)(long* Mesh_pointer, i
     if (mp->pml_conditions && mp->NSPEC_CPML > 0) pml_compute_forces(mp, *iphase, *nspec_outer_elastic, *nspec_inner_elastic);
     return;
   }
-  const bool grp = mp->force_kernel_variant != 1 && !mp->attenuation && !mp->compute_and_store_strain;
+  const bool grp = mp->force_kernel_variant != 1 && !mp->attenuation && !mp->compute_and_store_strain && !mp->anisotropy;
   if (num_elements > 0 && grp) {
     ensure_elastic_groups(mp, *nspec_outer_elastic, *nspec_inner_elastic);
     if (mp->use_mesh_coloring_gpu) {

@@ -306,16 +306,25 @@ __global__ void __launch_bounds__(NGLL3_PADDED) k_pml_elastic_forces(const PmlAr
 
 // PML_displ = displ + deltatover2 (1 - 2 theta) veloc + deltatsqover2 (1 - theta) accel, theta = 1/8
 // (update_displ_elastic_PML, update_displacement_scheme.f90:417-455)
+// rmass3 != nullptr: the Newmark corrector of the previous step is still pending (kernel_3_a_cuda deferred it into the next
+// predictor pass): it is applied on the fly, same expressions as k_newmark_corrector, so the snapshot is bit-identical.
 __global__ void __launch_bounds__(NGLL3_PADDED) k_pml_snapshot(const realw* displ, const realw* veloc, const realw* accel,
                                                                 realw* pml_displ, int nspec_cpml, const int* CPML_to_spec,
-                                                                const int* ibool, realw c1, realw c2, size_t nglob) {
+                                                                const int* ibool, realw c1, realw c2, size_t nglob,
+                                                                const realw* __restrict__ rmass3, realw corr_deltatover2) {
   const int e = blockIdx.x, t = threadIdx.x;
   if (e >= nspec_cpml || t >= NGLL3) return;
   const int ispec = CPML_to_spec[e] - 1;
   const size_t g = vbase(ibool[(size_t)ispec * NGLL3_PADDED + t] - 1), cs = vstride(nglob);
 #pragma unroll
-  for (int c = 0; c < 3; ++c)
-    pml_displ[((size_t)e * 3 + c) * NGLL3_PADDED + t] = displ[g + c * cs] + c1 * veloc[g + c * cs] + c2 * accel[g + c * cs];
+  for (int c = 0; c < 3; ++c) {
+    realw a = accel[g + c * cs], v = veloc[g + c * cs];
+    if (rmass3) {
+      a *= rmass3[g + c * cs];
+      v += corr_deltatover2 * a;
+    }
+    pml_displ[((size_t)e * 3 + c) * NGLL3_PADDED + t] = displ[g + c * cs] + c1 * v + c2 * a;
+  }
 }
 
 // Dirichlet condition on the outer faces of the layer (pml_impose_boundary_condition_elastic,
@@ -351,13 +360,15 @@ inline void pml_destroy(DeviceMesh* mp) {
   mp->pml = nullptr;
 }
 
-inline void pml_snapshot_displ(DeviceMesh* mp, int which, realw /*deltat*/, realw deltatsqover2, realw deltatover2) {
+inline void pml_snapshot_displ(DeviceMesh* mp, int which, realw /*deltat*/, realw deltatsqover2, realw deltatover2,
+                               bool corrector_pending = false, realw corr_deltatover2 = 0.f) {
   PML* P = mp->pml;
   if (!P || P->nspec_cpml == 0) return;
   const realw theta = 0.125f;
   k_pml_snapshot<<<P->nspec_cpml, NGLL3_PADDED, 0, mp->compute_stream>>>(
       mp->d_displ, mp->d_veloc, mp->d_accel, which == 0 ? P->d_displ_old : P->d_displ_new, P->nspec_cpml, P->d_CPML_to_spec,
-      mp->d_ibool, deltatover2 * (1.0f - 2.0f * theta), deltatsqover2 * (1.0f - theta), (size_t)mp->NGLOB_AB);
+      mp->d_ibool, deltatover2 * (1.0f - 2.0f * theta), deltatsqover2 * (1.0f - theta), (size_t)mp->NGLOB_AB,
+      corrector_pending ? mp->d_rmassx : nullptr, corr_deltatover2);
   KERNEL_CHECK(mp, "k_pml_snapshot");
 }
 
@@ -455,7 +466,9 @@ extern "C" void SB200_FC(prepare_fields_elastic_pml)(long* Mesh_pointer, int* NS
 
 extern "C" void SB200_FC(pml_impose_boundary_condition_elastic_cuda)(long* Mesh_pointer) {
   using namespace sb200;
-  DeviceMesh* mp = get_mesh(Mesh_pointer);
+  // a pending Newmark corrector (kernel_3_a_cuda) stays pending: accel = veloc = 0 at the boundary points before the corrector
+  // gives accel * rmass = 0 and veloc + dt/2 * 0 = 0, the values the reference's order (corrector, then this) leaves there
+  DeviceMesh* mp = get_mesh_keep_pending(Mesh_pointer);
   PML* P = mp->pml;
   if (!mp->pml_conditions || !P || P->nspec_cpml == 0 || mp->num_abs_boundary_faces == 0) return;
   k_pml_impose_boundary<<<mp->num_abs_boundary_faces, 32, 0, mp->compute_stream>>>(

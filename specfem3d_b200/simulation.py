@@ -42,6 +42,7 @@ class Simulation:
     SAVE_FORWARD: bool = False   # forward run keeps the absorbed Stacey tractions of every step and the last frame
     APPROXIMATE_HESS_KL: bool = False
     ANISOTROPIC_KL: bool = False  # cijkl_kl (21 per point) instead of mu_kl / kappa_kl
+    ANISOTROPY: bool = False     # forward runs with the 21 coefficients db.cstore instead of kappa / mu (add_anisotropy)
     # kernel runs with attenuation (undo_att.py): the forward run stores a wavefield snapshot every NT_DUMP_ATTENUATION steps,
     # the kernel run re-computes the forward wavefield forward in time from them (iterate_time_undoatt.F90)
     UNDO_ATTENUATION_AND_OR_PML: bool = False
@@ -113,6 +114,36 @@ def make_simulation(spec: BoxSpec, DT: float, NSTEP: int, sources: Sequence = ()
 
         sim.PML_CONDITIONS = True
         sim.pml = prepare_pml(sim)
+    return sim
+
+
+C_NAMES = ("c11", "c12", "c13", "c14", "c15", "c16", "c22", "c23", "c24", "c25", "c26", "c33", "c34", "c35", "c36", "c44", "c45",
+           "c46", "c55", "c56", "c66")  # argument order of prepare_fields_elastic_device (c11store ... c66store)
+
+
+def add_anisotropy(sim: Simulation, strength: float = 0.05) -> Simulation:
+    """Switches ``sim`` to ANISOTROPY: per partition ``db.cstore`` (21, NSPEC, 5, 5, 5) float32, the arrays c11store ... c66store
+    the solver reads from the databases (save_arrays_solver.F90: ``if (ANISOTROPY)`` block).  The model is the isotropic tensor
+    of the partition's kappa / mu (c11 = c22 = c33 = lambda + 2 mu, c12 = c13 = c23 = lambda, c44 = c55 = c66 = mu) plus a smooth
+    perturbation of EVERY one of the 21 coefficients of up to ``strength`` * mu, so that each term of the stress (compute_forces_
+    viscoelastic.F90:601-612) carries signal; 6 x 6 perturbations of that size keep the tensor positive definite."""
+    for r, db in enumerate(sim.dbs):
+        if db is None or db.nspec_elastic == 0:
+            continue
+        att = sim.att[r] if sim.att is not None else None
+        kappa = np.asarray(att["kappastore"] if att is not None else db.kappastore, np.float64).reshape(db.NSPEC_AB, 5, 5, 5)
+        mu = np.asarray(att["mustore"] if att is not None else db.mustore, np.float64).reshape(db.NSPEC_AB, 5, 5, 5)
+        lam = kappa - 2.0 / 3.0 * mu
+        ib = db.ibool.reshape(db.NSPEC_AB, 5, 5, 5) - 1
+        x, y, z = (np.asarray(a, np.float64)[ib] for a in (db.xstore, db.ystore, db.zstore))
+        L = max(float(sim.spec.xmax), float(sim.spec.ymax), -float(sim.spec.zmin), 1.0)  # the whole box, not the partition
+        c = np.zeros((21,) + mu.shape, np.float64)
+        for n, name in enumerate(C_NAMES):
+            i, j = int(name[1]), int(name[2])
+            base = (lam + 2.0 * mu) if (i == j and i <= 3) else (lam if (i <= 3 and j <= 3) else (mu if i == j else 0.0))
+            c[n] = base + strength * mu * np.sin(2.0 * np.pi * (x * (1 + n % 3) + y * (1 + n % 4) + z * (1 + n % 5)) / L + 0.7 * n)
+        db.cstore = np.ascontiguousarray(c.astype(np.float32))
+    sim.ANISOTROPY = True
     return sim
 
 

@@ -172,7 +172,8 @@ class DeviceRank:
                 be, ga, int(sim.APPROXIMATE_OCEAN_LOAD), db.rmass_ocean_load if sim.APPROXIMATE_OCEAN_LOAD else dummy, 0,
                 _f(db.free_surface_normal) if sim.APPROXIMATE_OCEAN_LOAD else dummy, db.free_surface_ispec, db.free_surface_ijk,
                 db.num_free_surface_faces,
-                int(sim.ACOUSTIC_SIMULATION), *col["elastic"], 0, *([dummy] * 21))
+                int(sim.ACOUSTIC_SIMULATION), *col["elastic"], int(sim.ANISOTROPY),
+                *([db.cstore[c] for c in range(21)] if sim.ANISOTROPY else [dummy] * 21))
             if sim.PML_CONDITIONS and sim.pml is not None:
                 from .pml import prepare_fields_elastic_pml
 

@@ -30,6 +30,8 @@ def factories():
         "cpml_regular": lambda: T.pml_sim(nstep=300, regular=True),
         "cfg3_small": lambda: T.cfg3_small(nstep=300),
         "ocean_load": lambda: T.ocean_load_sim(nstep=300),
+        "anisotropic": lambda: T.aniso_sim(nstep=300),
+        "anisotropic_visco": lambda: T.aniso_sim(nstep=300, attenuation=True),
         "kernel_run": lambda: kernel_run_case(),
         "kernel_run_acoustic": lambda: kernel_run_case("acoustic"),
         "kernel_run_coupled": lambda: kernel_run_case("coupled"),

@@ -325,6 +325,68 @@ def test_viscoelastic_time_loop_matches_oracle(device_lib, nproc):
     run.cleanup()
 
 
+def aniso_sim(nstep=300, attenuation=False, regular=False, nproc=(1, 1)):
+    """ANISOTROPY: the small elastic (or layered viscoelastic) box with all 21 elastic coefficients perturbed."""
+    from specfem3d_b200.simulation import add_anisotropy
+
+    sim = visco_sim(nstep=nstep, nproc=nproc) if attenuation else small_sim(nstep=nstep, nex=(8, 8, 4), regular=regular, nproc=nproc)
+    return add_anisotropy(sim, strength=0.08)
+
+
+@pytest.mark.parametrize("regular", [False, True])
+def test_anisotropic_force_kernel_matches_oracle(device_lib, regular):
+    """a1 with ANISOTROPY (Kernel_2_noatt_ani_impl / compute_forces_viscoelastic.F90:578-614): one call per phase on a smooth
+    displacement vs the oracle, and the result must differ from the isotropic one (all 21 coefficients are exercised)."""
+    from oracle.solver import OracleRun
+    from specfem3d_b200.time_loop import DeviceRun
+
+    sim = aniso_sim(nstep=4, regular=regular)
+    sim.initial_fields = smooth_fields(sim)
+    run = DeviceRun(sim)
+    r = run.ranks[0]
+    db = r.db
+    for iphase in (1, 2):
+        r.lib.compute_forces_viscoelastic_cuda(r.Mesh_pointer, iphase, float(sim.deltat), db.nspec_outer_elastic,
+                                               db.nspec_inner_elastic, 0, 0, 1)
+    _, _, accel = r.fields_el()
+    run.cleanup()
+    p = OracleRun(sim).parts[0]
+    p.forces_elastic(1)
+    p.forces_elastic(2)
+    assert np.abs(p.accel).max() > 0
+    assert relerr(accel, p.accel) < 2e-5, relerr(accel, p.accel)
+    sim.ANISOTROPY = False
+    q = OracleRun(sim).parts[0]
+    q.forces_elastic(1)
+    q.forces_elastic(2)
+    assert relerr(q.accel, p.accel) > 1e-2  # the anisotropic part is not noise
+
+
+@pytest.mark.parametrize("attenuation", [False, True])
+def test_anisotropic_time_loop_matches_oracle(device_lib, attenuation):
+    """Forward runs with ANISOTROPY (elastic, and viscoelastic with 3 SLS: the ANISOTROPY branch of Kernel_2_att_impl):
+    seismograms within 1e-4 relative L2 of the oracle; 2 x 1 ranks equal 1 rank."""
+    from oracle.solver import OracleRun
+    from specfem3d_b200.time_loop import DeviceRun
+
+    sim = aniso_sim(nstep=300, attenuation=attenuation)
+    o = OracleRun(sim).run()
+    run = DeviceRun(sim).run()
+    sd = run.gather_seismograms("d")
+    run.cleanup()
+    assert np.abs(o.seis_d).max() > 0
+    for irec in range(sim.receivers.nrec):
+        for c in range(3):
+            assert rel_l2(sd[irec, :, c], o.seis_d[irec, :, c]) <= 1e-4
+    sim2 = aniso_sim(nstep=300, attenuation=attenuation, nproc=(2, 1))
+    run2 = DeviceRun(sim2).run()
+    sd2 = run2.gather_seismograms("d")
+    run2.cleanup()
+    for irec in range(sim.receivers.nrec):
+        for c in range(3):
+            assert rel_l2(sd2[irec, :, c], sd[irec, :, c]) <= 2e-5
+
+
 @pytest.mark.parametrize("variant", [1, 0])  # 1 = one element per CTA, 0 = default (row kernel, three groups per CTA iteration)
 @pytest.mark.parametrize("regular", [False, True])
 @pytest.mark.parametrize("nex", [(7, 5, 4), (4, 4, 2)])  # 140 / 32 fluid elements: ragged groups, empty sub-groups
@@ -540,6 +602,32 @@ def test_deferred_corrector(device_lib):
         for a, b in zip(fa, fb):
             assert rel_l2(a, b) <= 1e-4  # accel carries the run-to-run noise of the atomics order (3.6e-5 observed)
     assert out["1"][2] < out["0"][2]
+
+
+def test_deferred_corrector_with_cpml(device_lib):
+    """The deferred corrector in runs with C-PML elements: PML_displ_old is taken from the wavefields with the pending
+    corrector applied on the fly (k_pml_snapshot), PML_displ_new after the fused pass.  Whole runs with and without the
+    deferral agree to the run-to-run noise of the atomics order, with one launch less per step."""
+    from specfem3d_b200.time_loop import DeviceRun
+
+    out = {}
+    for fuse in ("1", "0"):
+        os.environ["SPECFEM_B200_FUSE_NEWMARK"] = fuse
+        sim = pml_sim(nstep=150)
+        run = DeviceRun(sim).run()
+        r = run.ranks[0]
+        n = int(sim.pml[0]["NSPEC_CPML"])
+        old, new = (np.zeros((n, 5, 5, 5, 3), np.float32) for _ in range(2))
+        r.lib.transfer_pml_displ_from_device(3 * 125 * n, old, new, r.Mesh_pointer)
+        out[fuse] = (run.gather_seismograms("d"), r.fields_el(), old, new, run.kernel_launches())
+        run.cleanup()
+    os.environ.pop("SPECFEM_B200_FUSE_NEWMARK")
+    a, b = out["1"], out["0"]
+    assert np.abs(b[0]).max() > 0 and rel_l2(a[0], b[0]) <= 2e-5
+    for x, y in zip(a[1], b[1]):
+        assert rel_l2(x, y) <= 1e-4
+    assert np.abs(b[2]).max() > 0 and rel_l2(a[2], b[2]) <= 2e-5 and rel_l2(a[3], b[3]) <= 2e-5
+    assert a[4] <= b[4] - 140
 
 
 # -------------------------------------------------------------------------------------------------------------------

@@ -28,7 +28,7 @@ def rel_l2(a, b):
 
 
 @pytest.mark.parametrize("name", ["elastic_irregular", "elastic_regular", "viscoelastic", "ocean_source_in_solid",
-                                  "ocean_source_in_water", "cpml_irregular", "cpml_regular", "cfg3_small", "ocean_load", "kernel_run", "kernel_run_acoustic",
+                                  "ocean_source_in_water", "cpml_irregular", "cpml_regular", "cfg3_small", "ocean_load", "anisotropic", "anisotropic_visco", "kernel_run", "kernel_run_acoustic",
                                   "kernel_run_coupled", "kernel_run_undoatt", "kernel_run_undoatt_visco", "kernel_run_undoatt_acoustic"])
 def test_against_reference_cuda_backend(device_lib, name, tmp_path):
     if not os.path.exists(REF_LIB):
