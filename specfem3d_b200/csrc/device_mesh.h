@@ -208,6 +208,15 @@ struct DeviceMesh {
   // library numbering of the global points (renumber.h): perm[host id] = device id, both 0-based; identity when disabled
   std::vector<int> h_perm;
   int* d_perm = nullptr;
+  // Newmark passes restricted to the points of their own domain (coupled fluid-solid meshes; libspecfem3d_b200.cu:
+  // setup_domain_ranges).  The library numbering puts the points of the elastic elements first: [0, el_hi); the points of the
+  // fluid elements are [ac_lo, NGLOB) (ac_lo a multiple of 4) plus the listed fluid-solid interface points below ac_lo.
+  bool domain_ranges = false;       // both domains present, library numbering in use, restriction pays
+  long long el_hi = 0, ac_lo = 0;
+  int* d_ac_list = nullptr;         // points of fluid elements below ac_lo (0-based, library numbering)
+  int n_ac_list = 0;
+  bool el_outside_zero = true, ac_outside_zero = true;  // the wavefields are zero outside their domain (checked on upload)
+  int* d_domain_count = nullptr;    // two counters of the check
   std::vector<int> h_irregular_element_number;   // host copies needed to build it
   std::vector<int> h_phase_ispec_elastic;        // [2][num_phase_ispec_elastic]
   std::vector<int> h_phase_ispec_acoustic;       // [2][num_phase_ispec_acoustic]

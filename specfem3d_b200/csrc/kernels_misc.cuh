@@ -129,9 +129,11 @@ template <int M>
 __global__ void __launch_bounds__(256) k_newmark_corrector_predictor_c(realw* __restrict__ displ, realw* __restrict__ veloc,
                                                                        realw* __restrict__ accel, const realw* __restrict__ rmass_c,
                                                                        const realw* __restrict__ rmass_exc, long long nexc,
-                                                                       long long nglob, realw corr_deltatover2, realw deltat,
-                                                                       realw deltatsqover2, realw deltatover2) {
-  const long long nq = nglob >= 8 ? (nglob - 7) / 4 : 0;  // quads q < nq: 4 q + 7 < nglob
+                                                                       long long nglob, long long npts, realw corr_deltatover2,
+                                                                       realw deltat, realw deltatsqover2, realw deltatover2) {
+  // nglob = plane stride; npts <= nglob = points to update (the elastic points are a prefix of the library numbering; the
+  // wavefields beyond are zero and stay zero, device_mesh.h: domain_ranges)
+  const long long nq = npts >= 8 ? (npts - 7) / 4 : 0;  // quads q < nq: 4 q + 7 < npts
   constexpr int o[3] = {0, (4 - M) % 4, (4 - (2 * M) % 4) % 4};
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
@@ -160,18 +162,53 @@ __global__ void __launch_bounds__(256) k_newmark_corrector_predictor_c(realw* __
       *reinterpret_cast<float4*>(accel + w) = a[c];
     }
   }
-  // points outside the quads: [0, o_c) and [4 nq + o_c, nglob) of every plane
+  // points outside the quads: [0, o_c) and [4 nq + o_c, npts) of every plane
   if (blockIdx.x == 0 && threadIdx.x < 3 * 16) {
     const int c = threadIdx.x / 16, e = threadIdx.x % 16;
     const int oc = c == 0 ? o[0] : c == 1 ? o[1] : o[2];
     const long long p = e < 3 ? (e < oc ? e : -1) : 4 * nq + oc + (e - 3);
-    if (p >= 0 && p < nglob) {
+    if (p >= 0 && p < npts) {
       const long long w = c * nglob + p;
       realw dd = displ[w], vv = veloc[w], aa = accel[w];
       newmark_cp_point(dd, vv, aa, rmass_of(__ldg(rmass_c + p), c, rmass_exc, nexc), corr_deltatover2, deltat, deltatsqover2, deltatover2);
       displ[w] = dd; veloc[w] = vv; accel[w] = aa;
     }
   }
+}
+
+// Scalar predictor / corrector on a list of points (the fluid-solid interface points of a coupled mesh, which the library
+// numbering places among the points of the solid): same expressions as k_newmark_predictor / k_newmark_corrector.
+__global__ void __launch_bounds__(256) k_newmark_predictor_list(realw* __restrict__ displ, realw* __restrict__ veloc,
+                                                                realw* __restrict__ accel, const int* __restrict__ list, int n,
+                                                                realw deltat, realw deltatsqover2, realw deltatover2) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const int i = list[q];
+  const realw a = accel[i];
+  displ[i] = displ[i] + deltat * veloc[i] + deltatsqover2 * a;
+  veloc[i] = veloc[i] + deltatover2 * a;
+  accel[i] = 0.f;
+}
+__global__ void __launch_bounds__(256) k_newmark_corrector_list(realw* __restrict__ veloc, realw* __restrict__ accel,
+                                                                const realw* __restrict__ rmass, const int* __restrict__ list,
+                                                                int n, realw deltatover2) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const int i = list[q];
+  const realw a = accel[i] * rmass[i];
+  accel[i] = a;
+  veloc[i] += deltatover2 * a;
+}
+// number of non-zero values of f[lo, hi) (count[0]) and of f at the listed points (count[1]); the upload entry points use it
+// to verify that the wavefields vanish outside their domain
+__global__ void __launch_bounds__(256) k_count_nonzero(const realw* __restrict__ f, long long lo, long long hi,
+                                                       const int* __restrict__ list, int nlist, int* __restrict__ count) {
+  const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int c0 = 0, c1 = 0;
+  for (long long i = lo + t0; i < hi; i += stride) c0 += f[i] != 0.f;
+  for (long long q = t0; q < nlist; q += stride) c1 += f[list[q]] != 0.f;
+  if (c0) atomicAdd(count, c0);
+  if (c1) atomicAdd(count + 1, c1);
 }
 
 // veloc += dt/2 * accel only (kernel_3_veloc_cuda_device, used by kernel_3_b_cuda after the ocean-load correction)

@@ -6,6 +6,8 @@
 // blocks in (SURVEY.md section 8b "threading / streams") synchronise with the host.
 #include "specfem3d_b200.h"
 
+#include <algorithm>
+
 #include "device_mesh.h"
 #include "kernels_acoustic.cuh"
 #include "kernels_common.cuh"
@@ -72,6 +74,70 @@ static int streaming_grid(long long n4) {
   if (want > cap) want = cap;
   if (want < 1) want = 1;
   return (int)want;
+}
+
+// Coupled fluid-solid meshes: which points the Newmark passes of each domain have to visit (device_mesh.h: domain_ranges).
+// ib: ibool in the library numbering, [nspec][125], 1-based.
+// halo: the MPI interface points (0-based, library numbering).
+static void setup_domain_ranges(DeviceMesh* mp, const std::vector<int>& ib, const std::vector<int>& halo, const int* ispec_is_elastic,
+                                const int* ispec_is_acoustic, bool renumbered) {
+  mp->domain_ranges = false;
+  const char* env = getenv("SPECFEM_B200_DOMAIN_RANGES");
+  if (!renumbered || (env && atoi(env) == 0)) return;
+  long long el_hi = 0;
+  bool any_ac = false;
+  for (int e = 0; e < mp->NSPEC_AB; ++e) {
+    if (ispec_is_acoustic[e]) any_ac = true;
+    if (!ispec_is_elastic[e]) continue;
+    for (int q = 0; q < NGLL3; ++q) el_hi = std::max<long long>(el_hi, ib[(size_t)e * NGLL3 + q]);
+  }
+  if (el_hi == 0 || !any_ac) return;
+  const long long ac_lo = (el_hi / 4) * 4;  // keeps the 128-bit accesses of the range kernels aligned
+  // a halo point beyond the elastic prefix (the neighbour's solid touches a point that is purely fluid here) takes the elastic
+  // restriction away: the prefix must be one range
+  for (int p : halo) el_hi = p >= el_hi ? (long long)mp->NGLOB_AB : el_hi;
+  std::vector<int> list;
+  for (int p : halo)
+    if (p < ac_lo) list.push_back(p);
+  for (int e = 0; e < mp->NSPEC_AB; ++e) {
+    if (!ispec_is_acoustic[e]) continue;
+    for (int q = 0; q < NGLL3; ++q) {
+      const int p = ib[(size_t)e * NGLL3 + q] - 1;
+      if (p < ac_lo) list.push_back(p);
+    }
+  }
+  std::sort(list.begin(), list.end());
+  list.erase(std::unique(list.begin(), list.end()), list.end());
+  mp->el_hi = el_hi;
+  mp->ac_lo = ac_lo;
+  mp->n_ac_list = (int)list.size();
+  mp->d_ac_list = dev_copy(list.data(), list.size());
+  mp->d_domain_count = dev_alloc_zero<int>(2);
+  mp->domain_ranges = true;
+}
+// after an upload of elastic (vector = true) or acoustic wavefields: are they zero outside the domain's points?
+static void check_outside_zero(DeviceMesh* mp, bool vector) {
+  if (!mp->domain_ranges) return;
+  const long long nglob = mp->NGLOB_AB;
+  int h[2] = {0, 0};
+  CUDA_CHECK(cudaMemsetAsync(mp->d_domain_count, 0, 2 * sizeof(int), mp->compute_stream));
+  if (vector) {
+    if (!mp->d_displ) return;
+    const realw* f[3] = {mp->d_displ, mp->d_veloc, mp->d_accel};
+    for (int a = 0; a < 3; ++a)
+      for (int c = 0; c < 3; ++c)
+        k_count_nonzero<<<256, 256, 0, mp->compute_stream>>>(f[a] + (size_t)c * nglob, mp->el_hi, nglob, nullptr, 0, mp->d_domain_count);
+  } else {
+    if (!mp->d_potential) return;
+    const realw* f[3] = {mp->d_potential, mp->d_potential_dot, mp->d_potential_dot_dot};
+    for (int a = 0; a < 3; ++a)
+      k_count_nonzero<<<256, 256, 0, mp->compute_stream>>>(f[a], 0, mp->ac_lo, mp->d_ac_list, mp->n_ac_list, mp->d_domain_count);
+  }
+  KERNEL_CHECK(mp, "k_count_nonzero");
+  CUDA_CHECK(cudaMemcpyAsync(h, mp->d_domain_count, 2 * sizeof(int), cudaMemcpyDeviceToHost, mp->compute_stream));
+  CUDA_CHECK(cudaStreamSynchronize(mp->compute_stream));
+  if (vector) mp->el_outside_zero = h[0] == 0;
+  else mp->ac_outside_zero = h[0] == h[1];
 }
 
 // a host array indexed by global point, uploaded in the library numbering
@@ -212,6 +278,8 @@ extern "C" void SB200_FC(prepare_constants_device)(
   mp->d_irregular_element_number = dev_copy(h_irregular_element_number, nspec);
   mp->h_irregular_element_number.assign(h_irregular_element_number, h_irregular_element_number + nspec);
   // the library's own point numbering (renumber.h); SPECFEM_B200_RENUMBER=0 keeps the host numbering
+  std::vector<int> ib_library;  // ibool in the library numbering
+  bool renumbered = false;
   {
     const char* e = getenv("SPECFEM_B200_RENUMBER");
     const size_t nglob = mp->NGLOB_AB;
@@ -229,6 +297,8 @@ extern "C" void SB200_FC(prepare_constants_device)(
       ib[q] = mp->h_perm[h_ibool[q] - 1] + 1;
     }
     mp->d_ibool = dev_copy_padded<int>(ib.data(), nspec, 1);
+    ib_library = std::move(ib);
+    renumbered = !(e && atoi(e) == 0);
   }
 
   // metric record per irregular element: 9 planes of 128 floats (one contiguous 4.5 KB slab)
@@ -264,6 +334,14 @@ extern "C" void SB200_FC(prepare_constants_device)(
       mp->d_ibool_interfaces_ext_mesh = dev_copy(ifc.data(), ifc.size());
     }
     mp->h_nibool_interfaces.assign(h_nibool_interfaces_ext_mesh, h_nibool_interfaces_ext_mesh + mp->num_interfaces_ext_mesh);
+  }
+  {
+    // halo points receive the neighbour's contributions whatever the local elements are: they belong to both domains' point sets
+    std::vector<int> halo;
+    const size_t mx = mp->max_nibool_interfaces_ext_mesh;
+    for (int n = 0; n < mp->num_interfaces_ext_mesh; ++n)
+      for (int q = 0; q < h_nibool_interfaces_ext_mesh[n]; ++q) halo.push_back(mp->h_perm[h_ibool_interfaces_ext_mesh[n * mx + q] - 1]);
+    setup_domain_ranges(mp, ib_library, halo, ispec_is_elastic, ispec_is_acoustic, renumbered);
   }
   mp->d_ispec_is_inner = dev_copy(h_ispec_is_inner, nspec);
 
@@ -580,6 +658,8 @@ extern "C" void SB200_FC(prepare_cleanup_device)(long* Mesh_pointer, int* ACOUST
   dev_free(mp->d_perm);
   dev_free(mp->d_rmass_c);
   dev_free(mp->d_rmass_exc);
+  dev_free(mp->d_ac_list);
+  dev_free(mp->d_domain_count);
   pml_destroy(mp);
   group_store_free(mp->grp_elastic);
   group_store_free(mp->grp_acoustic);
@@ -682,25 +762,26 @@ static void d2h_pot(DeviceMesh* mp, realw* h, const realw* d, int size) {
 extern "C" void SB200_FC(transfer_fields_el_to_device)(int* size, realw* displ, realw* veloc, realw* accel, long* Mesh_pointer) {
   DeviceMesh* mp = get_mesh(Mesh_pointer);
   h2d_vec(mp, mp->d_displ, displ, *size); h2d_vec(mp, mp->d_veloc, veloc, *size); h2d_vec(mp, mp->d_accel, accel, *size);
+  check_outside_zero(mp, true);
 }
 extern "C" void SB200_FC(transfer_fields_el_from_device)(int* size, realw* displ, realw* veloc, realw* accel, long* Mesh_pointer) {
   DeviceMesh* mp = get_mesh(Mesh_pointer);
   d2h_vec(mp, displ, mp->d_displ, *size); d2h_vec(mp, veloc, mp->d_veloc, *size); d2h_vec(mp, accel, mp->d_accel, *size);
 }
 extern "C" void SB200_FC(transfer_displ_to_device)(int* size, realw* displ, long* Mesh_pointer) {
-  DeviceMesh* mp = get_mesh(Mesh_pointer); h2d_vec(mp, mp->d_displ, displ, *size);
+  DeviceMesh* mp = get_mesh(Mesh_pointer); h2d_vec(mp, mp->d_displ, displ, *size); check_outside_zero(mp, true);
 }
 extern "C" void SB200_FC(transfer_displ_from_device)(int* size, realw* displ, long* Mesh_pointer) {
   DeviceMesh* mp = get_mesh(Mesh_pointer); d2h_vec(mp, displ, mp->d_displ, *size);
 }
 extern "C" void SB200_FC(transfer_veloc_to_device)(int* size, realw* veloc, long* Mesh_pointer) {
-  DeviceMesh* mp = get_mesh(Mesh_pointer); h2d_vec(mp, mp->d_veloc, veloc, *size);
+  DeviceMesh* mp = get_mesh(Mesh_pointer); h2d_vec(mp, mp->d_veloc, veloc, *size); check_outside_zero(mp, true);
 }
 extern "C" void SB200_FC(transfer_veloc_from_device)(int* size, realw* veloc, long* Mesh_pointer) {
   DeviceMesh* mp = get_mesh(Mesh_pointer); d2h_vec(mp, veloc, mp->d_veloc, *size);
 }
 extern "C" void SB200_FC(transfer_accel_to_device)(int* size, realw* accel, long* Mesh_pointer) {
-  DeviceMesh* mp = get_mesh(Mesh_pointer); h2d_vec(mp, mp->d_accel, accel, *size);
+  DeviceMesh* mp = get_mesh(Mesh_pointer); h2d_vec(mp, mp->d_accel, accel, *size); check_outside_zero(mp, true);
 }
 extern "C" void SB200_FC(transfer_accel_from_device)(int* size, realw* accel, long* Mesh_pointer) {
   DeviceMesh* mp = get_mesh(Mesh_pointer); d2h_vec(mp, accel, mp->d_accel, *size);
@@ -708,6 +789,7 @@ extern "C" void SB200_FC(transfer_accel_from_device)(int* size, realw* accel, lo
 extern "C" void SB200_FC(transfer_fields_ac_to_device)(int* size, field* p, field* pd, field* pdd, long* Mesh_pointer) {
   DeviceMesh* mp = get_mesh(Mesh_pointer);
   h2d_pot(mp, mp->d_potential, p, *size); h2d_pot(mp, mp->d_potential_dot, pd, *size); h2d_pot(mp, mp->d_potential_dot_dot, pdd, *size);
+  check_outside_zero(mp, false);
 }
 extern "C" void SB200_FC(transfer_fields_ac_from_device)(int* size, field* p, field* pd, field* pdd, long* Mesh_pointer) {
   DeviceMesh* mp = get_mesh(Mesh_pointer);
@@ -717,7 +799,7 @@ extern "C" void SB200_FC(transfer_potential_ac_from_device)(int* size, field* p,
   DeviceMesh* mp = get_mesh(Mesh_pointer); d2h_pot(mp, p, mp->d_potential, *size);
 }
 extern "C" void SB200_FC(transfer_dot_dot_to_device)(int* size, field* pdd, long* Mesh_pointer) {
-  DeviceMesh* mp = get_mesh(Mesh_pointer); h2d_pot(mp, mp->d_potential_dot_dot, pdd, *size);
+  DeviceMesh* mp = get_mesh(Mesh_pointer); h2d_pot(mp, mp->d_potential_dot_dot, pdd, *size); check_outside_zero(mp, false);
 }
 extern "C" void SB200_FC(transfer_dot_dot_from_device)(int* size, field* pdd, long* Mesh_pointer) {
   DeviceMesh* mp = get_mesh(Mesh_pointer); d2h_pot(mp, pdd, mp->d_potential_dot_dot, *size);
@@ -792,11 +874,13 @@ void (*g_flush_corrector)(DeviceMesh*) = &flush_corrector_impl;
 static void launch_newmark_cp_compact(DeviceMesh* mp, realw* displ, realw* veloc, realw* accel, realw corr_deltatover2, realw deltat,
                                       realw deltatsqover2, realw deltatover2) {
   const long long nglob = mp->NGLOB_AB;
-  const int grid = streaming_grid((nglob + 3) >> 2);
+  // coupled meshes: the forward wavefield is zero (and stays zero) beyond the points of the elastic elements
+  const long long npts = (mp->domain_ranges && mp->el_outside_zero && displ == mp->d_displ) ? mp->el_hi : nglob;
+  const int grid = streaming_grid((npts + 3) >> 2);
 #define SB200_NCP(M)                                                                                                          \
   k_newmark_corrector_predictor_c<M><<<grid, 256, 0, mp->compute_stream>>>(displ, veloc, accel, mp->d_rmass_c, mp->d_rmass_exc, \
-                                                                           mp->rmass_nexc, nglob, corr_deltatover2, deltat,   \
-                                                                           deltatsqover2, deltatover2)
+                                                                           mp->rmass_nexc, nglob, npts, corr_deltatover2,    \
+                                                                           deltat, deltatsqover2, deltatover2)
   switch ((int)(nglob % 4)) {
     case 0: SB200_NCP(0); break;
     case 1: SB200_NCP(1); break;
@@ -870,6 +954,20 @@ extern "C" void SB200_FC(update_displacement_ac_cuda)(long* Mesh_pointer, realw*
     KERNEL_CHECK(mp, "k_newmark_predictor(acoustic, backward)");
     return;
   }
+  if (mp->domain_ranges && mp->ac_outside_zero) {
+    // coupled mesh: only the points of the fluid elements, [ac_lo, NGLOB) and the listed interface points (the potentials are
+    // zero everywhere else and stay zero)
+    const long long lo = mp->ac_lo, m = n - lo;
+    if (m > 0)
+      k_newmark_predictor<<<streaming_grid(m >> 2), 256, 0, mp->compute_stream>>>(
+          mp->d_potential + lo, mp->d_potential_dot + lo, mp->d_potential_dot_dot + lo, m, *deltat_F, *deltatsqover2_F, *deltatover2_F);
+    if (mp->n_ac_list > 0)
+      k_newmark_predictor_list<<<(mp->n_ac_list + 255) / 256, 256, 0, mp->compute_stream>>>(
+          mp->d_potential, mp->d_potential_dot, mp->d_potential_dot_dot, mp->d_ac_list, mp->n_ac_list, *deltat_F, *deltatsqover2_F,
+          *deltatover2_F);
+    KERNEL_CHECK(mp, "k_newmark_predictor(acoustic, fluid points)");
+    return;
+  }
   k_newmark_predictor<<<streaming_grid(n >> 2), 256, 0, mp->compute_stream>>>(
       mp->d_potential, mp->d_potential_dot, mp->d_potential_dot_dot, n, *deltat_F, *deltatsqover2_F, *deltatover2_F);
   KERNEL_CHECK(mp, "k_newmark_predictor(acoustic)");
@@ -936,6 +1034,17 @@ extern "C" void SB200_FC(kernel_3_acoustic_cuda)(long* Mesh_pointer, realw* delt
                                                                                  mp->d_rmass_acoustic, n, *b_deltatover2_F, 1);
     KERNEL_CHECK(mp, "k_newmark_corrector(acoustic, backward)");
     if (foa3 == 3) return;
+  }
+  if (mp->domain_ranges && mp->ac_outside_zero) {
+    const long long lo = mp->ac_lo, m = n - lo;
+    if (m > 0)
+      k_newmark_corrector<<<streaming_grid(m >> 2), 256, 0, mp->compute_stream>>>(mp->d_potential_dot + lo, mp->d_potential_dot_dot + lo,
+                                                                                   mp->d_rmass_acoustic + lo, m, *deltatover2_F, 1);
+    if (mp->n_ac_list > 0)
+      k_newmark_corrector_list<<<(mp->n_ac_list + 255) / 256, 256, 0, mp->compute_stream>>>(
+          mp->d_potential_dot, mp->d_potential_dot_dot, mp->d_rmass_acoustic, mp->d_ac_list, mp->n_ac_list, *deltatover2_F);
+    KERNEL_CHECK(mp, "k_newmark_corrector(acoustic, fluid points)");
+    return;
   }
   k_newmark_corrector<<<streaming_grid(n >> 2), 256, 0, mp->compute_stream>>>(mp->d_potential_dot, mp->d_potential_dot_dot,
                                                                                mp->d_rmass_acoustic, n, *deltatover2_F, 1);
@@ -1865,6 +1974,7 @@ extern "C" void SB200_FC(specfem_b200_set_option)(long* Mesh_pointer, const char
 }
 extern "C" void SB200_FC(specfem_b200_device_pointer)(long* Mesh_pointer, const char* name, void** ptr) {
   DeviceMesh* mp = get_mesh(Mesh_pointer);
+  if (strcmp(name, "compute_stream") != 0) mp->el_outside_zero = mp->ac_outside_zero = false;  // may be written behind our back
   if (!strcmp(name, "displ")) *ptr = mp->d_displ;
   else if (!strcmp(name, "veloc")) *ptr = mp->d_veloc;
   else if (!strcmp(name, "accel")) *ptr = mp->d_accel;

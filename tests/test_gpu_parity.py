@@ -253,7 +253,7 @@ def visco_sim(nproc=(1, 1), nstep=200, nex=(8, 6, 4), deform=0.12, coloring=Fals
     return make_simulation(spec, DT=0.008, NSTEP=nstep, sources=src, stations=sts, attenuation=True)
 
 
-def ocean_sim(nproc=(1, 1), nstep=200, nex=(8, 6, 5), deform=0.1, source_in_water=False, coloring=False):
+def ocean_sim(nproc=(1, 1), nstep=200, nex=(8, 6, 5), deform=0.1, source_in_water=False, coloring=False, part=None):
     """cfg4 in small: top element layer is water (acoustic), the rest elastic; receivers in both media."""
     spec = BoxSpec(nex[0], nex[1], nex[2], xmax=1100.0 * nex[0], ymax=900.0 * nex[1], zmin=-1000.0 * nex[2],
                    nproc_xi=nproc[0], nproc_eta=nproc[1], materials=(HALFSPACE, WATER),
@@ -262,7 +262,7 @@ def ocean_sim(nproc=(1, 1), nstep=200, nex=(8, 6, 5), deform=0.1, source_in_wate
     src = [CMTSource(0.52 * spec.xmax, 0.47 * spec.ymax, zs, CMT_SMALL, hdur=0.4)]
     sts = [Station("W", "XX", 0.31 * spec.xmax, 0.43 * spec.ymax, 0.08 * spec.zmin),   # in the water layer
            Station("S", "XX", 0.67 * spec.xmax, 0.58 * spec.ymax, 0.5 * spec.zmin)]   # in the solid
-    sim = make_simulation(spec, DT=0.006, NSTEP=nstep, sources=src, stations=sts)
+    sim = make_simulation(spec, DT=0.006, NSTEP=nstep, sources=src, stations=sts, part=part)
     sim.SAVE_SEISMOGRAMS_PRESSURE = True
     return sim
 
@@ -628,6 +628,39 @@ def test_deferred_corrector_with_cpml(device_lib):
         assert rel_l2(x, y) <= 1e-4
     assert np.abs(b[2]).max() > 0 and rel_l2(a[2], b[2]) <= 2e-5 and rel_l2(a[3], b[3]) <= 2e-5
     assert a[4] <= b[4] - 140
+
+
+def test_domain_restricted_newmark(device_lib):
+    """Coupled meshes: the Newmark passes visit only the points of their own domain (elastic prefix of the library numbering;
+    fluid range + listed interface points).  (a) one rank: identical seismograms with and without the restriction
+    (SPECFEM_B200_DOMAIN_RANGES=0), fewer bytes but two more launches per step; (b) a partition whose fluid-solid interface
+    lies ON the partition boundary (the solid below a rank's water belongs to the other rank, so the halo carries elastic
+    contributions to points that are purely fluid locally): equal to the single-rank run and to the oracle."""
+    from oracle.solver import OracleRun
+    from specfem3d_b200.time_loop import DeviceRun
+
+    out = {}
+    for flag in ("1", "0"):
+        os.environ["SPECFEM_B200_DOMAIN_RANGES"] = flag
+        run = DeviceRun(ocean_sim(nstep=200)).run()
+        out[flag] = (run.gather_seismograms("d"), run.gather_seismograms("p"), run.kernel_launches())
+        run.cleanup()
+    os.environ.pop("SPECFEM_B200_DOMAIN_RANGES")
+    assert np.abs(out["0"][0]).max() > 0 and np.abs(out["0"][1]).max() > 0
+    assert rel_l2(out["1"][0], out["0"][0]) <= 2e-5 and rel_l2(out["1"][1], out["0"][1]) <= 2e-5
+    assert out["1"][2] > out["0"][2]  # the restriction is in use: one list kernel per acoustic predictor / corrector
+
+    n = 8 * 6 * 5
+    ix, iz = np.arange(n) % 8, np.arange(n) // 48
+    part = (((iz == 4) & (ix >= 2)) | ((iz < 4) & (ix < 2))).astype(np.int32)
+    sim = ocean_sim(nstep=200, part=part)
+    assert all(db.nspec_acoustic > 0 and db.nspec_elastic > 0 for db in sim.dbs)
+    run = DeviceRun(sim).run()
+    sd, sp = run.gather_seismograms("d"), run.gather_seismograms("p")
+    run.cleanup()
+    o = OracleRun(ocean_sim(nstep=200)).run()
+    assert rel_l2(sd, out["1"][0]) <= 1e-4 and rel_l2(sp, out["1"][1]) <= 1e-4
+    assert rel_l2(sd, o.seis_d) <= 1e-4 and rel_l2(sp[:, :, 0], o.seis_p) <= 1e-4
 
 
 # -------------------------------------------------------------------------------------------------------------------
