@@ -85,6 +85,8 @@ struct DeviceMesh {
 
   cudaStream_t compute_stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev_pack_done = nullptr, ev_copy_done = nullptr;
+  // kernel runs: the per-step Stacey record travels on the copy stream (elastic [0], acoustic [1]): copied / consumed
+  cudaEvent_t ev_rec_copied[2] = {nullptr, nullptr}, ev_rec_consumed[2] = {nullptr, nullptr};
 
   // mesh
   int* d_ibool = nullptr;                     // [NSPEC][128]

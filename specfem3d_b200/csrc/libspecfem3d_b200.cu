@@ -696,6 +696,10 @@ extern "C" void SB200_FC(prepare_cleanup_device)(long* Mesh_pointer, int* ACOUST
   if (mp->h_norm_partial) cudaFreeHost(mp->h_norm_partial);
   cudaEventDestroy(mp->ev_pack_done);
   cudaEventDestroy(mp->ev_copy_done);
+  for (int w = 0; w < 2; ++w) {
+    if (mp->ev_rec_copied[w]) cudaEventDestroy(mp->ev_rec_copied[w]);
+    if (mp->ev_rec_consumed[w]) cudaEventDestroy(mp->ev_rec_consumed[w]);
+  }
   cudaStreamDestroy(mp->compute_stream);
   cudaStreamDestroy(mp->copy_stream);
   delete mp;
@@ -1490,6 +1494,24 @@ static void pin_absorb_record(DeviceMesh* mp, realw* b_absorb_field) {
   else (void)cudaGetLastError();
 }
 
+// Kernel runs hand over one Stacey record per step.  The reference copies it with a blocking cudaMemcpy behind everything that
+// is queued; here it travels on the copy stream while the force kernel launched just before is still running: the host waits
+// for the copy only (the caller may overwrite its buffer as soon as we return), the replay kernel waits for it through an
+// event, and the next step's copy waits until the replay kernel has consumed the device buffer.
+static void upload_record_overlapped(DeviceMesh* mp, int which, void* d_dst, const void* h_src, size_t bytes) {
+  if (!mp->ev_rec_copied[which]) {
+    CUDA_CHECK(cudaEventCreateWithFlags(&mp->ev_rec_copied[which], cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&mp->ev_rec_consumed[which], cudaEventDisableTiming));
+  } else {
+    CUDA_CHECK(cudaStreamWaitEvent(mp->copy_stream, mp->ev_rec_consumed[which], 0));
+  }
+  CUDA_CHECK(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, mp->copy_stream));
+  CUDA_CHECK(cudaEventRecord(mp->ev_rec_copied[which], mp->copy_stream));
+  CUDA_CHECK(cudaStreamSynchronize(mp->copy_stream));
+  CUDA_CHECK(cudaStreamWaitEvent(mp->compute_stream, mp->ev_rec_copied[which], 0));
+}
+static void record_consumed(DeviceMesh* mp, int which) { CUDA_CHECK(cudaEventRecord(mp->ev_rec_consumed[which], mp->compute_stream)); }
+
 extern "C" void SB200_FC(compute_stacey_viscoelastic_cuda)(long* Mesh_pointer, int* iphasef, realw* b_absorb_field,
                                                            int* FORWARD_OR_ADJOINT_f) {
   DeviceMesh* mp = get_mesh(Mesh_pointer);
@@ -1502,12 +1524,12 @@ extern "C" void SB200_FC(compute_stacey_viscoelastic_cuda)(long* Mesh_pointer, i
     require_backward_fields(mp, "compute_stacey_viscoelastic_cuda");
     if (!mp->d_b_absorb_field) exit_on_error("compute_stacey_viscoelastic_cuda: b_absorb_field was not prepared");
     pin_absorb_record(mp, b_absorb_field);
-    CUDA_CHECK(cudaMemcpyAsync(mp->d_b_absorb_field, b_absorb_field, mp->b_reclen_field, cudaMemcpyHostToDevice, mp->compute_stream));
-    CUDA_CHECK(cudaStreamSynchronize(mp->compute_stream));  // the caller may overwrite the buffer as soon as we return
+    upload_record_overlapped(mp, 0, mp->d_b_absorb_field, b_absorb_field, mp->b_reclen_field);
     k_stacey_elastic_replay<<<mp->num_abs_boundary_faces, 32, 0, mp->compute_stream>>>(
         mp->d_b_accel, mp->d_abs_boundary_ispec, mp->d_abs_boundary_ijk, mp->d_ibool, mp->d_ispec_is_elastic,
         mp->num_abs_boundary_faces, mp->d_b_absorb_field, (size_t)mp->NGLOB_AB);
     KERNEL_CHECK(mp, "k_stacey_elastic_replay");
+    record_consumed(mp, 0);
     if (foa == 3) return;
   }
   realw* d_b = (mp->simulation_type == 1 && mp->save_forward && mp->d_b_absorb_field) ? mp->d_b_absorb_field : nullptr;
@@ -1532,13 +1554,12 @@ extern "C" void SB200_FC(compute_stacey_acoustic_cuda)(long* Mesh_pointer, int* 
   if (foa != 1) {  // kernel run: put the absorbed flux of this time level back (compute_stacey_acoustic_cuda.cu:75-80,150-170)
     require_backward_potentials(mp, "compute_stacey_acoustic_cuda");
     if (!mp->d_b_absorb_potential) exit_on_error("compute_stacey_acoustic_cuda: b_absorb_potential was not prepared");
-    CUDA_CHECK(cudaMemcpyAsync(mp->d_b_absorb_potential, h_b_absorb_potential, mp->b_reclen_potential, cudaMemcpyHostToDevice,
-                               mp->compute_stream));
-    CUDA_CHECK(cudaStreamSynchronize(mp->compute_stream));
+    upload_record_overlapped(mp, 1, mp->d_b_absorb_potential, h_b_absorb_potential, mp->b_reclen_potential);
     k_stacey_acoustic_replay<<<mp->num_abs_boundary_faces, 32, 0, mp->compute_stream>>>(
         mp->d_b_potential_dot_dot, mp->d_abs_boundary_ispec, mp->d_abs_boundary_ijk, mp->d_ibool, mp->d_ispec_is_acoustic,
         mp->num_abs_boundary_faces, mp->d_b_absorb_potential);
     KERNEL_CHECK(mp, "k_stacey_acoustic_replay");
+    record_consumed(mp, 1);
     if (foa == 3) return;
   }
   realw* d_b = (mp->simulation_type == 1 && mp->save_forward && mp->d_b_absorb_potential) ? mp->d_b_absorb_potential : nullptr;

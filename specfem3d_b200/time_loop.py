@@ -213,6 +213,15 @@ class DeviceRank:
         if self.Mesh_pointer.value:
             self.lib.prepare_cleanup_device(self.Mesh_pointer, int(self.ACOUSTIC), int(self.ELASTIC), 0)
 
+    def __del__(self):
+        # a rank dropped without cleanup() would leave its device memory allocated and -- worse -- its Stacey record buffer
+        # page-locked (cudaHostRegister) after numpy has freed it: later host allocations that land in that range make CUDA
+        # calls fail with 'invalid argument'.  The Fortran solver always ends with prepare_cleanup_device; so does the harness.
+        try:
+            self.cleanup()
+        except Exception:
+            pass
+
     # -- field access for tests ---------------------------------------------------------------------------------------
     def fields_el(self):
         n = self.db.NGLOB_AB
