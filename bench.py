@@ -55,6 +55,30 @@ def workload_text(nex, nspec_total):
             f"({nspec_total} total), irregular elements, Stacey 5 sides, CMT source, 4 receivers, single precision")
 
 
+def arm_config(args, world: int):
+    """`config` of the default (slab) workloads, computable without building a mesh: the b200 arm and the reference arm print
+    the SAME dictionary (the reference arm times a bounded sample of it, named in its cpu_baseline.sample)."""
+    from specfem3d_b200.configs import courant_dt
+    from specfem3d_b200.meshfem import BoxSpec
+
+    px, py = partition_grid(world)
+    if args.scaling == "strong":
+        nex = (256 // px, 256 // py, 128)
+        dx, dy, dz = 134000.0 / 256, 134000.0 / 256, 60000.0 / 128
+        workload = (f"configs[4]: the 256x256x128 = 8388608-element elastic mesh of config 5 in {world} part(s) of "
+                    f"{nex[0]}x{nex[1]}x{nex[2]} elements, irregular elements, Stacey 5 sides, CMT source, 4 receivers, single precision")
+    else:
+        nex = tuple(int(v) for v in args.nex.split("x"))
+        dx, dy, dz = 134000.0 / 128, 134000.0 / 128, 60000.0 / 64
+        workload = workload_text(nex, nex[0] * nex[1] * nex[2] * world)
+    spec = BoxSpec(nex[0] * px, nex[1] * py, nex[2], xmax=dx * nex[0] * px, ymax=dy * nex[1] * py, zmin=-dz * nex[2])
+    return {"workload": workload, "elements_total": nex[0] * nex[1] * nex[2] * world, "elements_per_gpu": nex[0] * nex[1] * nex[2],
+            "nglob_per_gpu": (4 * nex[0] + 1) * (4 * nex[1] + 1) * (4 * nex[2] + 1),
+            "partitions": f"{px}x{py} slabs (meshfem3D NPROC_XI x NPROC_ETA)",
+            "halo": (args.halo if world > 1 else "none"), "dt": courant_dt(spec, 2800.0),
+            "l2_policy": "working set per step (>10 GB) >> 126 MB L2, no flush needed"}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -433,17 +457,19 @@ def run_device(args):
         if args.scaling == "strong":
             workload = (f"configs[4]: the 256x256x128 = 8388608-element elastic mesh of config 5 in {world} part(s) of "
                         f"{nex[0]}x{nex[1]}x{nex[2]} elements, irregular elements, Stacey 5 sides, CMT source, 4 receivers, single precision")
+        config = arm_config(args, world)
+        assert config["workload"] == workload and config["elements_total"] == nspec_total and abs(config["dt"] - DT) <= 1e-12 * DT
+        if part is None:
+            assert config["elements_per_gpu"] == db.NSPEC_AB and config["nglob_per_gpu"] == db.NGLOB_AB
+        else:
+            config.update(elements_per_gpu=db.NSPEC_AB, nglob_per_gpu=db.NGLOB_AB,
+                          partitions=(f"{world} parts of xdecompose_mesh PARTITIONING_TYPE 2 (the reference's METIS 4.0.3 on the dual "
+                                      f"graph, {args.part_file}): {db.num_interfaces_ext_mesh} neighbours on rank 0"))
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload,
-                       "elements_total": nspec_total, "elements_per_gpu": db.NSPEC_AB, "nglob_per_gpu": db.NGLOB_AB,
-                       "partitions": (f"{spec.nproc_xi}x{spec.nproc_eta} slabs (meshfem3D NPROC_XI x NPROC_ETA)" if part is None else
-                                      f"{world} parts of xdecompose_mesh PARTITIONING_TYPE 2 (the reference's METIS 4.0.3 on the dual graph, "
-                                      f"{args.part_file}): {db.num_interfaces_ext_mesh} neighbours on rank 0"),
-                       "halo": (args.halo if world > 1 else "none"), "dt": DT,
-                       "l2_policy": "working set per step (>10 GB) >> 126 MB L2, no flush needed"},
+            "config": config,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * (sources.NSOURCES if sources else 0),
                     "d2h_bytes_per_step": 4 * 148 * 4,
                     "note": "K steps through the C ABI from host buffers: per-step stf upload + blocking norm readback; host wall clock"},
@@ -727,16 +753,16 @@ def run_reference(args):
     el = time.perf_counter() - t0
     nspec = sim.dbs[0].NSPEC_AB
     value = nspec * args.steps / el
-    sample = (f"each step = one full time step of a {nex[0]}x{nex[1]}x{nex[2]} ({nspec}-element) halfspace mesh of the same kind "
-              f"(element-timesteps/s is size-independent on the CPU); oracle port, {cores} OpenMP threads")
+    sample = (f"each step = one full time step of a {nex[0]}x{nex[1]}x{nex[2]} ({nspec}-element) halfspace mesh of the same kind = "
+              f"one GPU's share of the workload or the largest of 128x128x64 / 64x64x32 / ... that keeps the run near 90 s "
+              f"(element-timesteps/s is size-independent on the CPU); CPU restatement of the reference solver (oracle port: no Fortran "
+              f"compiler / MPI in this image), {cores} OpenMP threads; specfem3d_b200/_meshgen.so (host mesh generator, no kernels) "
+              f"is loaded by this arm too")
     emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_text(nex, nspec), "elements_total": nspec,
-                   "note": "reference arm = CPU restatement of the reference solver (oracle port: no Fortran compiler / MPI in "
-                           "this image) on the host cores; the mesh is the largest of 128x128x64 / 64x64x32 / ... that keeps the "
-                           "run near 90 s; specfem3d_b200/_meshgen.so (host mesh generator, no kernels) is loaded by this arm too"},
+        "config": arm_config(args, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
