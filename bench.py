@@ -737,7 +737,8 @@ def run_reference(args):
         cal.step()
     rate = 16384 * 3 / (time.perf_counter() - t0)
     budget_elems = rate * 90.0 / max(total, 1)
-    ladder = [(128, 128, 64), (64, 64, 32), (32, 32, 16), (16, 16, 8)]
+    share = (128, 128, 64) if args.scaling == "strong" else tuple(int(v) for v in args.nex.split("x"))  # one GPU's share
+    ladder = [share] + [c for c in [(128, 128, 64), (64, 64, 32), (32, 32, 16), (16, 16, 8)] if c[0] * c[1] * c[2] < share[0] * share[1] * share[2]]
     nex = ladder[-1]
     for cand in ladder:
         if cand[0] * cand[1] * cand[2] <= budget_elems:
