@@ -505,14 +505,14 @@ def run_device(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def time_config(lib, sim, kernels, steps=12, warmup=3, sampler=None):
+def time_config(lib, sim, kernels, steps=12, warmup=3, sampler=None, halo="host"):
     """A few steps of `sim` on cuda:0 through the ABI; returns ms per step (device events are inside the library) and the
     per-step time of each named kernel."""
     import torch
 
     from specfem3d_b200.time_loop import DeviceRun
 
-    run = DeviceRun(sim, lib=lib)
+    run = DeviceRun(sim, lib=lib, halo=halo)
     for _ in range(warmup):
         run.step()
     torch.cuda.synchronize()
@@ -587,8 +587,13 @@ def config1_step_cost(lib):
 
     sim = cfg1(2, 2, 400)
     ms, _, launches = time_config(lib, sim, (), steps=100, warmup=20)
+    # the same four handles with the peer-store halo (no host staging, no host synchronisation inside the step), and the mesh as
+    # ONE rank: what is left is launch latency (about ten launches of a few microseconds of work each per rank and step)
+    ms_p2p, _, _ = time_config(lib, cfg1(2, 2, 400), (), steps=100, warmup=20, halo="p2p")
+    ms_one, _, _ = time_config(lib, cfg1(1, 1, 400), (), steps=100, warmup=20)
     return {"workload": "configs[0]: homogeneous_halfspace example, 36x36x16 = 20736 elements, 4 ranks (2x2) on one GPU, host-staged halo",
             "ms_per_step": ms, "element_timesteps_per_s": 20736 / (ms * 1e-3),
+            "ms_per_step_peer_store_halo": ms_p2p, "ms_per_step_one_rank": ms_one,
             "reference_cpu_ms_per_step": 73.6,
             "reference_cpu_source": "EXAMPLES/applications/homogeneous_halfspace/REF_SEIS/output_solver.txt: mean elapsed time per time step 7.36e-2 s (4 MPI ranks, 2016)"}
 
