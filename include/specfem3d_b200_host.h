@@ -1,0 +1,76 @@
+/* specfem3d_b200_host.h -- a native (C++) host side above the C ABI of specfem3d_b200.h.
+ *
+ * The reference's host is compiled Fortran: iterate_time (src/specfem3D/iterate_time.F90:219-330) calls the device entry
+ * points once per time step, in the order of update_displ_Newmark (update_displacement_scheme.f90:281-312),
+ * compute_forces_acoustic_calling (compute_forces_acoustic_calling_routine.f90:28-330), compute_forces_viscoelastic_calling
+ * (compute_forces_viscoelastic_calling_routine.F90:30-435) and write_seismograms (write_seismograms.f90:28-200).  No Fortran
+ * compiler exists in this image, so the same control flow is restated here in C++ (csrc/host_loop.cu): it is a CALLER of the ABI
+ * -- nothing in it touches the device except through the entry points of specfem3d_b200.h -- and stands where xspecfem3D's
+ * time loop would stand.  specfem3d_b200/time_loop.py is the same loop in Python (kernel runs, SAVE_FORWARD and the tests'
+ * call-by-call checks use that one); tests/test_gpu_parity.py::test_native_host_loop_equals_python_loop runs both.
+ *
+ * Plain C: pointers and sizes only.  All arrays are the caller's (Fortran layouts, as in specfem3d_b200.h).
+ */
+#ifndef SPECFEM3D_B200_HOST_H
+#define SPECFEM3D_B200_HOST_H
+
+#include "specfem3d_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* one MPI rank of the solver = one Mesh_pointer handle (the ranks of a run may share a GPU or sit on several) */
+typedef struct {
+  long* Mesh_pointer;
+  int myrank;
+  int elastic, acoustic;                 /* the rank owns elements of the domain (ELASTIC / ACOUSTIC of the rank) */
+  int nspec_outer_elastic, nspec_inner_elastic, nspec_outer_acoustic, nspec_inner_acoustic;
+  int num_coupling_ac_el_faces;
+  /* halo (assemble_MPI_vector.f90 / assemble_MPI_scalar.f90): interface tables and the rank's send / receive buffers */
+  int num_interfaces_ext_mesh, max_nibool_interfaces_ext_mesh;
+  const int* nibool_interfaces_ext_mesh; /* (num_interfaces) */
+  const int* ibool_interfaces_ext_mesh;  /* (max_nibool, num_interfaces) */
+  const int* my_neighbors_ext_mesh;      /* (num_interfaces) neighbour rank of every interface */
+  realw *buffer_send_vector, *buffer_recv_vector; /* (NDIM, max_nibool, num_interfaces) */
+  realw *buffer_send_scalar, *buffer_recv_scalar; /* (max_nibool, num_interfaces) */
+  /* Stacey record buffers (one record; this loop keeps no history: forward runs without SAVE_FORWARD) */
+  realw *b_absorb_field, *b_absorb_potential;
+  /* seismograms (NDIM, nrec_local, nlength_seismogram) and the running sample counter of the rank */
+  int nrec_local;
+  realw *seismograms_d, *seismograms_v, *seismograms_a, *seismograms_p;
+  int seismo_current;
+} specfem_b200_host_rank;
+
+typedef struct {
+  int nranks;                            /* ranks driven by this process */
+  specfem_b200_host_rank* ranks;
+  int NPROC;                             /* ranks of the whole run (> 1: the halo entry points are called) */
+  realw deltat, deltatover2, deltatsqover2;
+  int NSTEP;
+  int ELASTIC_SIMULATION, ACOUSTIC_SIMULATION, ATTENUATION, STACEY_ABSORBING_CONDITIONS, STACEY_INSTEAD_OF_FREE_SURFACE,
+      PML_CONDITIONS, APPROXIMATE_OCEAN_LOAD;
+  /* sources: stf_pre_compute of EVERY step, (NSOURCES, NSTEP) doubles, elastic and acoustic tables
+     (compute_add_sources_viscoelastic.F90: get_stf_viscoelastic; compute_add_sources_acoustic.f90) */
+  int NSOURCES;                          /* 0 = no source */
+  const double *stf_elastic, *stf_acoustic;
+  /* seismograms */
+  int has_receivers, NTSTEP_BETWEEN_OUTPUT_SAMPLE, nlength_seismogram;
+  /* halo transport between the ranks of THIS process: 1 = copy send -> receive buffers on the host (what MPI does between
+     processes), 0 = none (single rank, or the library moves the halo itself after specfem_b200_halo_p2p_connect) */
+  int host_exchange;
+  /* check_stability: after every norm_every-th step of the call (0 = never) the maximum displacement norm (potential_dot_dot
+     norm of purely acoustic ranks) over the ranks goes to norms[0], norms[1], ...; a non-finite value stops the run like
+     check_stability.f90:120 does */
+  int norm_every;
+  realw* norms;
+} specfem_b200_host_run;
+
+/* Time steps it_begin .. it_end (1-based, inclusive) of a forward run (SIMULATION_TYPE 1, no SAVE_FORWARD).
+   Replaces the loop body of iterate_time.F90:219-330 in GPU_MODE. */
+void SB200_FC(specfem_b200_iterate_time)(specfem_b200_host_run* run, int* it_begin, int* it_end);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,201 @@
+// host_loop.cu -- the native host side above the C ABI (include/specfem3d_b200_host.h): iterate_time of a forward run.
+//
+// Host code only (it sits in a .cu file so that the one build recipe of csrc/ picks it up): every device action goes through
+// the Fortran-callable entry points, by reference, in the order the Fortran solver calls them:
+//   iterate_time                                        src/specfem3D/iterate_time.F90:219-330
+//   update_displ_Newmark (GPU branch)                   src/specfem3D/update_displacement_scheme.f90:281-312
+//   compute_forces_acoustic_calling (GPU branches)      src/specfem3D/compute_forces_acoustic_calling_routine.f90:28-330
+//   compute_forces_viscoelastic_calling (GPU branches)  src/specfem3D/compute_forces_viscoelastic_calling_routine.F90:30-435
+//   assemble_MPI_vector_send_cuda / _write_cuda         src/specfem3D/assemble_MPI_vector.f90:640-830
+//   write_seismograms (GPU branch)                      src/specfem3D/write_seismograms.f90:28-200
+//   check_stability                                     src/specfem3D/check_stability.f90:85-120
+// specfem3d_b200/time_loop.py is the same loop in Python; this one removes the interpreter from the step (configs[0] as four
+// handles on one GPU is bound by it) and is what a C / C++ application would call.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "specfem3d_b200_host.h"
+
+namespace {
+
+typedef specfem_b200_host_rank Rank;
+typedef specfem_b200_host_run Run;
+
+[[noreturn]] void host_error(const char* msg) {
+  fprintf(stderr, "ERROR (specfem3d_b200 host loop): %s\n", msg);
+  exit(1);
+}
+
+Rank* rank_by_id(Run* run, int id) {
+  for (int r = 0; r < run->nranks; ++r)
+    if (run->ranks[r].myrank == id) return &run->ranks[r];
+  return nullptr;
+}
+
+// The "MPI" between the ranks of this process: the send buffer of interface n of rank r lands in the receive buffer of the
+// interface of the neighbour that points back to r (what isend / irecv pairs do in assemble_MPI_vector_send_cuda).
+void exchange_on_host(Run* run, int ncomp) {
+  for (int ir = 0; ir < run->nranks; ++ir) {
+    Rank& r = run->ranks[ir];
+    const size_t mx = (size_t)r.max_nibool_interfaces_ext_mesh;
+    for (int n = 0; n < r.num_interfaces_ext_mesh; ++n) {
+      Rank* nb = rank_by_id(run, r.my_neighbors_ext_mesh[n]);
+      if (!nb) host_error("host_exchange: a neighbour rank is not driven by this process");
+      int m = -1;
+      for (int q = 0; q < nb->num_interfaces_ext_mesh; ++q)
+        if (nb->my_neighbors_ext_mesh[q] == r.myrank) m = q;
+      if (m < 0) host_error("host_exchange: the neighbour has no interface pointing back");
+      const size_t cnt = (size_t)r.nibool_interfaces_ext_mesh[n];
+      if ((int)cnt != nb->nibool_interfaces_ext_mesh[m]) host_error("host_exchange: interface sizes differ on the two sides");
+      const size_t nbmx = (size_t)nb->max_nibool_interfaces_ext_mesh;
+      if (ncomp == 3)
+        memcpy(nb->buffer_recv_vector + 3 * nbmx * m, r.buffer_send_vector + 3 * mx * n, 3 * cnt * sizeof(realw));
+      else
+        memcpy(nb->buffer_recv_scalar + nbmx * m, r.buffer_send_scalar + mx * n, cnt * sizeof(realw));
+    }
+  }
+}
+
+void acoustic_step(Run* run, int it) {
+  int fwd = 1, sifs = run->STACEY_INSTEAD_OF_FREE_SURFACE;
+  const bool multi = run->NPROC > 1;
+  for (int ir = 0; ir < run->nranks; ++ir) {
+    Rank& r = run->ranks[ir];
+    if (r.acoustic) acoustic_enforce_free_surf_cuda_(r.Mesh_pointer, &sifs, &fwd);
+  }
+  std::vector<int> run_number(run->NSOURCES > 0 ? run->NSOURCES : 1, 0);  // run_number_of_the_source(:) = 0
+  for (int iphase = 1; iphase <= 2; ++iphase) {
+    for (int ir = 0; ir < run->nranks; ++ir) {
+      Rank& r = run->ranks[ir];
+      if (!r.acoustic) continue;
+      compute_forces_acoustic_cuda_(r.Mesh_pointer, &iphase, &r.nspec_outer_acoustic, &r.nspec_inner_acoustic, &fwd);
+      if (iphase == 1) {
+        if (run->STACEY_ABSORBING_CONDITIONS) compute_stacey_acoustic_cuda_(r.Mesh_pointer, &iphase, r.b_absorb_potential, &fwd);
+        if (run->ELASTIC_SIMULATION) compute_coupling_ac_el_cuda_(r.Mesh_pointer, &iphase, &r.num_coupling_ac_el_faces, &fwd);
+        if (run->NSOURCES > 0) {
+          int ns = run->NSOURCES;
+          compute_add_sources_ac_cuda_(r.Mesh_pointer, &ns, const_cast<double*>(run->stf_acoustic + (size_t)(it - 1) * ns), run_number.data());
+        }
+      }
+    }
+    if (multi) {
+      if (iphase == 1) {
+        for (int ir = 0; ir < run->nranks; ++ir) {
+          Rank& r = run->ranks[ir];
+          if (r.acoustic) transfer_boun_pot_from_device_(r.Mesh_pointer, r.buffer_send_scalar, &fwd);
+        }
+        if (run->host_exchange) exchange_on_host(run, 1);
+      } else {
+        for (int ir = 0; ir < run->nranks; ++ir) {
+          Rank& r = run->ranks[ir];
+          if (r.acoustic) transfer_asmbl_pot_to_device_(r.Mesh_pointer, r.buffer_recv_scalar, &fwd);
+        }
+      }
+    }
+  }
+  for (int ir = 0; ir < run->nranks; ++ir) {
+    Rank& r = run->ranks[ir];
+    if (!r.acoustic) continue;
+    kernel_3_acoustic_cuda_(r.Mesh_pointer, &run->deltatover2, &run->deltatover2, &fwd);
+    acoustic_enforce_free_surf_cuda_(r.Mesh_pointer, &sifs, &fwd);
+  }
+}
+
+void elastic_step(Run* run, int it) {
+  int fwd = 1, att = run->ATTENUATION ? 1 : 0;
+  const bool multi = run->NPROC > 1;
+  for (int iphase = 1; iphase <= 2; ++iphase) {
+    for (int ir = 0; ir < run->nranks; ++ir) {
+      Rank& r = run->ranks[ir];
+      if (!r.elastic) continue;
+      // COMPUTE_AND_STORE_STRAIN = ATTENUATION in a forward run (read_mesh_databases.F90)
+      compute_forces_viscoelastic_cuda_(r.Mesh_pointer, &iphase, &run->deltat, &r.nspec_outer_elastic, &r.nspec_inner_elastic, &att, &att, &fwd);
+      if (iphase == 1) {
+        if (run->STACEY_ABSORBING_CONDITIONS) compute_stacey_viscoelastic_cuda_(r.Mesh_pointer, &iphase, r.b_absorb_field, &fwd);
+        if (run->ACOUSTIC_SIMULATION && r.num_coupling_ac_el_faces > 0)
+          compute_coupling_el_ac_cuda_(r.Mesh_pointer, &iphase, &r.num_coupling_ac_el_faces, &fwd);
+        if (run->NSOURCES > 0) {
+          int ns = run->NSOURCES;
+          compute_add_sources_el_cuda_(r.Mesh_pointer, const_cast<double*>(run->stf_elastic + (size_t)(it - 1) * ns), &ns);
+        }
+        if (multi) transfer_boundary_from_device_a_(r.Mesh_pointer, &r.nspec_outer_elastic);
+      }
+    }
+    if (multi && iphase == 2) {
+      for (int ir = 0; ir < run->nranks; ++ir) {
+        Rank& r = run->ranks[ir];
+        if (r.elastic) sync_copy_from_device_(r.Mesh_pointer, &iphase, r.buffer_send_vector);
+      }
+      if (run->host_exchange) exchange_on_host(run, 3);
+      for (int ir = 0; ir < run->nranks; ++ir) {
+        Rank& r = run->ranks[ir];
+        if (r.elastic)
+          transfer_boundary_to_device_a_(r.Mesh_pointer, r.buffer_recv_vector, &r.num_interfaces_ext_mesh, &r.max_nibool_interfaces_ext_mesh);
+      }
+      for (int ir = 0; ir < run->nranks; ++ir) {
+        Rank& r = run->ranks[ir];
+        if (r.elastic)
+          transfer_asmbl_accel_to_device_(r.Mesh_pointer, r.buffer_recv_vector, &r.num_interfaces_ext_mesh, &r.max_nibool_interfaces_ext_mesh,
+                                          r.nibool_interfaces_ext_mesh, r.ibool_interfaces_ext_mesh, &fwd);
+      }
+    }
+  }
+  for (int ir = 0; ir < run->nranks; ++ir) {
+    Rank& r = run->ranks[ir];
+    if (!r.elastic) continue;
+    if (run->PML_CONDITIONS) pml_impose_boundary_condition_elastic_cuda_(r.Mesh_pointer);
+    int ocean = run->APPROXIMATE_OCEAN_LOAD ? 1 : 0;
+    kernel_3_a_cuda_(r.Mesh_pointer, &run->deltatover2, &run->deltatover2, &ocean, &fwd);
+    if (ocean) {  // compute_forces_viscoelastic_calling_routine.F90:380-424
+      compute_coupling_ocean_cuda_(r.Mesh_pointer, &fwd);
+      kernel_3_b_cuda_(r.Mesh_pointer, &run->deltatover2, &run->deltatover2, &fwd);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" void SB200_FC(specfem_b200_iterate_time)(specfem_b200_host_run* run, int* it_begin, int* it_end) {
+  if (!run || run->nranks <= 0 || !run->ranks) host_error("specfem_b200_iterate_time: no ranks");
+  if (*it_begin < 1 || *it_end > run->NSTEP) host_error("specfem_b200_iterate_time: time steps outside 1 .. NSTEP");
+  if (run->NSOURCES > 0 && ((run->ELASTIC_SIMULATION && !run->stf_elastic) || (run->ACOUSTIC_SIMULATION && !run->stf_acoustic)))
+    host_error("specfem_b200_iterate_time: source time function table missing");
+  int fwd = 1, zero = 0;
+  const int every = run->NTSTEP_BETWEEN_OUTPUT_SAMPLE > 0 ? run->NTSTEP_BETWEEN_OUTPUT_SAMPLE : 1;
+  for (int it = *it_begin; it <= *it_end; ++it) {
+    // update_displ_Newmark: acoustic first, then elastic
+    for (int ir = 0; ir < run->nranks; ++ir) {
+      Rank& r = run->ranks[ir];
+      if (r.acoustic) update_displacement_ac_cuda_(r.Mesh_pointer, &run->deltat, &run->deltatover2, &run->deltatsqover2, &fwd);
+      if (r.elastic) update_displacement_cuda_(r.Mesh_pointer, &run->deltat, &run->deltatover2, &run->deltatsqover2, &fwd);
+    }
+    if (run->ACOUSTIC_SIMULATION) acoustic_step(run, it);
+    if (run->ELASTIC_SIMULATION) elastic_step(run, it);
+    if (run->has_receivers && (it - 1) % every == 0) {
+      for (int ir = 0; ir < run->nranks; ++ir) {
+        Rank& r = run->ranks[ir];
+        r.seismo_current += 1;
+        if (r.nrec_local == 0) continue;
+        int itf = it, nl = run->nlength_seismogram;
+        compute_seismograms_cuda_(r.Mesh_pointer, r.seismograms_d, r.seismograms_v, r.seismograms_a, r.seismograms_p, &r.seismo_current, &nl,
+                                  &itf, &run->NSTEP, &run->ACOUSTIC_SIMULATION, &run->ELASTIC_SIMULATION, &zero);
+      }
+    }
+    if (run->norm_every > 0 && run->norms && (it - *it_begin + 1) % run->norm_every == 0) {  // check_stability
+      realw mx = 0.f;
+      for (int ir = 0; ir < run->nranks; ++ir) {
+        Rank& r = run->ranks[ir];
+        realw v = 0.f;
+        int one = 1;
+        if (r.elastic) get_norm_elastic_from_device_(&v, r.Mesh_pointer, &one);
+        else if (r.acoustic) get_norm_acoustic_from_device_(&v, r.Mesh_pointer, &one);
+        mx = v > mx ? v : mx;
+        if (!std::isfinite(v)) host_error("the wavefield became non-finite (check_stability): the simulation blew up");
+      }
+      run->norms[(it - *it_begin + 1) / run->norm_every - 1] = mx;
+    }
+  }
+}

@@ -241,6 +241,41 @@ class DeviceRank:
         return int(c.value)
 
 
+# ---- native host loop (include/specfem3d_b200_host.h, csrc/host_loop.cu) -----------------------------------------------------
+_PF, _PI, _PD = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)
+
+
+class _HostRank(ctypes.Structure):
+    _fields_ = [("Mesh_pointer", ctypes.POINTER(ctypes.c_long)), ("myrank", ctypes.c_int), ("elastic", ctypes.c_int), ("acoustic", ctypes.c_int),
+                ("nspec_outer_elastic", ctypes.c_int), ("nspec_inner_elastic", ctypes.c_int), ("nspec_outer_acoustic", ctypes.c_int),
+                ("nspec_inner_acoustic", ctypes.c_int), ("num_coupling_ac_el_faces", ctypes.c_int),
+                ("num_interfaces_ext_mesh", ctypes.c_int), ("max_nibool_interfaces_ext_mesh", ctypes.c_int),
+                ("nibool_interfaces_ext_mesh", _PI), ("ibool_interfaces_ext_mesh", _PI), ("my_neighbors_ext_mesh", _PI),
+                ("buffer_send_vector", _PF), ("buffer_recv_vector", _PF), ("buffer_send_scalar", _PF), ("buffer_recv_scalar", _PF),
+                ("b_absorb_field", _PF), ("b_absorb_potential", _PF), ("nrec_local", ctypes.c_int),
+                ("seismograms_d", _PF), ("seismograms_v", _PF), ("seismograms_a", _PF), ("seismograms_p", _PF),
+                ("seismo_current", ctypes.c_int)]
+
+
+class _HostRun(ctypes.Structure):
+    _fields_ = [("nranks", ctypes.c_int), ("ranks", ctypes.POINTER(_HostRank)), ("NPROC", ctypes.c_int),
+                ("deltat", ctypes.c_float), ("deltatover2", ctypes.c_float), ("deltatsqover2", ctypes.c_float), ("NSTEP", ctypes.c_int),
+                ("ELASTIC_SIMULATION", ctypes.c_int), ("ACOUSTIC_SIMULATION", ctypes.c_int), ("ATTENUATION", ctypes.c_int),
+                ("STACEY_ABSORBING_CONDITIONS", ctypes.c_int), ("STACEY_INSTEAD_OF_FREE_SURFACE", ctypes.c_int),
+                ("PML_CONDITIONS", ctypes.c_int), ("APPROXIMATE_OCEAN_LOAD", ctypes.c_int),
+                ("NSOURCES", ctypes.c_int), ("stf_elastic", _PD), ("stf_acoustic", _PD),
+                ("has_receivers", ctypes.c_int), ("NTSTEP_BETWEEN_OUTPUT_SAMPLE", ctypes.c_int), ("nlength_seismogram", ctypes.c_int),
+                ("host_exchange", ctypes.c_int), ("norm_every", ctypes.c_int), ("norms", _PF)]
+
+
+def _pf(a):
+    return a.ctypes.data_as(_PF)
+
+
+def _pi(a):
+    return a.ctypes.data_as(_PI)
+
+
 class InProcessExchange:
     """The "MPI" of a run whose ranks are handles inside one process: a send is a numpy copy into the neighbour's
     receive buffer (slot = the interface on the neighbour that points back to the sender)."""
@@ -406,6 +441,75 @@ class DeviceRun:
         for _ in range(n):
             self.step()
         return self
+
+    def run_native(self, nstep: Optional[int] = None, norm_every: int = 0):
+        """The same steps through the NATIVE host loop (specfem_b200_iterate_time, csrc/host_loop.cu): one call runs ``nstep``
+        time steps without the interpreter in between.  Forward runs only (no SAVE_FORWARD record history, no kernel runs).
+        Returns the stability norms recorded every ``norm_every`` steps."""
+        sim = self.sim
+        if sim.SIMULATION_TYPE != 1 or sim.SAVE_FORWARD or sim.UNDO_ATTENUATION_AND_OR_PML:
+            raise NotImplementedError("native host loop: forward runs without SAVE_FORWARD only (use step() / kernel_run.py)")
+        if isinstance(self.exchange, InProcessExchange):
+            host_exchange = 1 if self.NPROC > 1 else 0
+        elif self.exchange is None or type(self.exchange).__name__ == "NoExchange":
+            host_exchange = 0  # one rank, or the library moves the halo itself (specfem_b200_halo_p2p_connect)
+        else:
+            raise NotImplementedError("native host loop: halo transport between processes goes through the Python loop")
+        n = (sim.NSTEP - self.it) if nstep is None else nstep
+        if n <= 0:
+            return np.zeros(0, np.float32)
+        if not hasattr(self, "_native"):
+            ns = sim.sources.NSOURCES if sim.sources is not None else 0
+            keep = {"stf_el": np.zeros((sim.NSTEP, max(ns, 1))), "stf_ac": np.zeros((sim.NSTEP, max(ns, 1)))}
+            for it in range(1, sim.NSTEP + 1):
+                if ns and sim.ELASTIC_SIMULATION:
+                    keep["stf_el"][it - 1] = sim.stf_pre_compute(it)
+                if ns and sim.ACOUSTIC_SIMULATION:
+                    keep["stf_ac"][it - 1] = sim.stf_pre_compute_acoustic(it)
+            arr = (_HostRank * len(self.ranks))()
+            for k, r in enumerate(self.ranks):
+                db, h = r.db, arr[k]
+                keep[k] = [_i(db.nibool_interfaces_ext_mesh), _i(db.ibool_interfaces_ext_mesh), _i(db.my_neighbors_ext_mesh)]
+                h.Mesh_pointer = ctypes.pointer(r.Mesh_pointer)
+                h.myrank, h.elastic, h.acoustic = r.rank, int(r.ELASTIC), int(r.ACOUSTIC)
+                h.nspec_outer_elastic, h.nspec_inner_elastic = db.nspec_outer_elastic, db.nspec_inner_elastic
+                h.nspec_outer_acoustic, h.nspec_inner_acoustic = db.nspec_outer_acoustic, db.nspec_inner_acoustic
+                h.num_coupling_ac_el_faces = db.num_coupling_ac_el_faces
+                h.num_interfaces_ext_mesh, h.max_nibool_interfaces_ext_mesh = db.num_interfaces_ext_mesh, db.max_nibool_interfaces_ext_mesh
+                h.nibool_interfaces_ext_mesh, h.ibool_interfaces_ext_mesh, h.my_neighbors_ext_mesh = (_pi(a) for a in keep[k])
+                h.buffer_send_vector, h.buffer_recv_vector = _pf(r.buffer_send_vector), _pf(r.buffer_recv_vector)
+                h.buffer_send_scalar, h.buffer_recv_scalar = _pf(r.buffer_send_scalar), _pf(r.buffer_recv_scalar)
+                h.b_absorb_field, h.b_absorb_potential = _pf(r.b_absorb_field), _pf(r.b_absorb_potential)
+                h.nrec_local = r.nrec_local
+                h.seismograms_d, h.seismograms_v = _pf(r.seismograms_d), _pf(r.seismograms_v)
+                h.seismograms_a, h.seismograms_p = _pf(r.seismograms_a), _pf(r.seismograms_p)
+            run = _HostRun()
+            run.nranks, run.ranks, run.NPROC = len(self.ranks), arr, self.NPROC
+            run.deltat, run.deltatover2, run.deltatsqover2 = float(sim.deltat), float(sim.deltatover2), float(sim.deltatsqover2)
+            run.NSTEP = sim.NSTEP
+            run.ELASTIC_SIMULATION, run.ACOUSTIC_SIMULATION = int(sim.ELASTIC_SIMULATION), int(sim.ACOUSTIC_SIMULATION)
+            run.ATTENUATION, run.STACEY_ABSORBING_CONDITIONS = int(sim.ATTENUATION), int(sim.spec.stacey)
+            run.STACEY_INSTEAD_OF_FREE_SURFACE = int(sim.spec.stacey_instead_of_free_surface)
+            run.PML_CONDITIONS = int(bool(sim.PML_CONDITIONS and sim.pml is not None))
+            run.APPROXIMATE_OCEAN_LOAD = int(sim.APPROXIMATE_OCEAN_LOAD)
+            run.NSOURCES = ns
+            run.stf_elastic, run.stf_acoustic = keep["stf_el"].ctypes.data_as(_PD), keep["stf_ac"].ctypes.data_as(_PD)
+            run.has_receivers = int(sim.receivers is not None)
+            run.NTSTEP_BETWEEN_OUTPUT_SAMPLE, run.nlength_seismogram = sim.NTSTEP_BETWEEN_OUTPUT_SAMPLE, sim.nlength_seismogram
+            self._native = (run, arr, keep)
+        run, arr, keep = self._native
+        run.host_exchange = host_exchange
+        norms = np.zeros(max(n // norm_every, 1) if norm_every > 0 else 1, np.float32)
+        run.norm_every, run.norms = int(norm_every), _pf(norms)
+        for k, r in enumerate(self.ranks):
+            arr[k].seismo_current = r.seismo_current
+        fn = self.ranks[0].lib.cdll.specfem_b200_iterate_time_
+        fn.restype = None
+        fn(ctypes.byref(run), ctypes.byref(ctypes.c_int(self.it + 1)), ctypes.byref(ctypes.c_int(self.it + n)))
+        self.it += n
+        for k, r in enumerate(self.ranks):
+            r.seismo_current = arr[k].seismo_current
+        return norms if norm_every > 0 else np.zeros(0, np.float32)
 
     def max_norm_displ(self) -> float:
         m = 0.0

@@ -19,8 +19,12 @@ def lib():
 
 
 def declared_symbols():
-    hdr = open(os.path.join(ROOT, "include", "specfem3d_b200.h")).read()
-    return re.findall(r"void\s+SB200_FC\((\w+)\)\s*\(", hdr)
+    names = []
+    inc = os.path.join(ROOT, "include")
+    for f in sorted(os.listdir(inc)):  # specfem3d_b200.h (the reference contract + extensions), specfem3d_b200_host.h (native host loop)
+        if f.endswith(".h"):
+            names += re.findall(r"void\s+SB200_FC\((\w+)\)\s*\(", open(os.path.join(inc, f)).read())
+    return names
 
 
 def test_header_declares_the_full_reference_contract():

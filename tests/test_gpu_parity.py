@@ -663,6 +663,47 @@ def test_domain_restricted_newmark(device_lib):
     assert rel_l2(sd, o.seis_d) <= 1e-4 and rel_l2(sp[:, :, 0], o.seis_p) <= 1e-4
 
 
+@pytest.mark.parametrize("case", ["elastic", "elastic_2x2_host", "elastic_2x2_p2p", "viscoelastic", "ocean_2x1_host", "ocean_p2p", "cpml",
+                                  "ocean_load"])
+def test_native_host_loop_equals_python_loop(device_lib, case):
+    """specfem_b200_iterate_time (csrc/host_loop.cu: the time loop of the Fortran solver restated in C++ above the C ABI) against
+    the Python loop of time_loop.py, which the oracle tests pin: same calls in the same order, so seismograms, final wavefields
+    and launch counts must agree (up to the order of the atomic additions)."""
+    from specfem3d_b200.time_loop import DeviceRun
+
+    make = {"elastic": lambda: small_sim(nstep=150, nex=(8, 8, 4)),
+            "elastic_2x2_host": lambda: small_sim(nproc=(2, 2), nstep=150, nex=(8, 8, 4)),
+            "elastic_2x2_p2p": lambda: small_sim(nproc=(2, 2), nstep=150, nex=(8, 8, 4)),
+            "viscoelastic": lambda: visco_sim(nstep=150),
+            "ocean_2x1_host": lambda: ocean_sim(nproc=(2, 1), nstep=150),
+            "ocean_p2p": lambda: ocean_sim(nproc=(2, 1), nstep=150),
+            "cpml": lambda: pml_sim(nstep=150),
+            "ocean_load": lambda: ocean_load_sim(nstep=150)}[case]
+    halo = "p2p" if case.endswith("p2p") else "host"
+    out = {}
+    for native in (False, True):
+        sim = make()
+        sim.SAVE_SEISMOGRAMS_VELOCITY = True
+        run = DeviceRun(sim, halo=halo)
+        if native:
+            norms = run.run_native(100, norm_every=50)   # two calls: the loop resumes where it stopped
+            run.run_native()
+            assert len(norms) == 2 and np.all(np.isfinite(norms)) and norms[1] > 0
+        else:
+            run.run()
+        which = "dvp" if sim.SAVE_SEISMOGRAMS_PRESSURE else "dv"
+        out[native] = ([run.gather_seismograms(w) for w in which], [r.fields_el()[0] if r.ELASTIC else r.fields_ac()[0] for r in run.ranks],
+                       run.kernel_launches(), run.it, len(run.ranks))
+        run.cleanup()
+    a, b = out[True], out[False]
+    assert a[3] == b[3] == 150
+    for x, y in zip(a[0], b[0]):
+        assert np.abs(y).max() > 0 and rel_l2(x, y) <= 2e-5
+    for x, y in zip(a[1], b[1]):
+        assert rel_l2(x, y) <= 1e-4
+    assert a[2] == b[2] + 2 * a[4]  # the same launches, plus the two stability norms of the native run on every rank
+
+
 # -------------------------------------------------------------------------------------------------------------------
 # USE_MESH_COLORING_GPU: colour-by-colour launches without atomics
 # -------------------------------------------------------------------------------------------------------------------
