@@ -212,6 +212,9 @@ class DeviceRank:
     def cleanup(self):
         if self.Mesh_pointer.value:
             self.lib.prepare_cleanup_device(self.Mesh_pointer, int(self.ACOUSTIC), int(self.ELASTIC), 0)
+            # the reference's prepare_cleanup_device frees the handle but leaves the caller's integer as it was
+            # (prepare_mesh_constants_cuda.cu:1561-1824): a second call (__del__) would free it twice
+            self.Mesh_pointer.value = 0
 
     def __del__(self):
         # a rank dropped without cleanup() would leave its device memory allocated and -- worse -- its Stacey record buffer
@@ -451,7 +454,7 @@ class DeviceRun:
             raise NotImplementedError("native host loop: forward runs without SAVE_FORWARD only (use step() / kernel_run.py)")
         if isinstance(self.exchange, InProcessExchange):
             host_exchange = 1 if self.NPROC > 1 else 0
-        elif self.exchange is None or type(self.exchange).__name__ == "NoExchange":
+        elif self.exchange is None or type(self.exchange).__name__ == "NoExchange" or getattr(self.exchange, "mode", None) == "p2p":
             host_exchange = 0  # one rank, or the library moves the halo itself (specfem_b200_halo_p2p_connect)
         else:
             raise NotImplementedError("native host loop: halo transport between processes goes through the Python loop")
