@@ -219,19 +219,23 @@ def _assemble(parts: List[OraclePartition], name: str, ncomp: int):
     adds what its neighbours sent (assemble_MPI_vector.f90:243-384)."""
     if len(parts) == 1:
         return
-    send = []
+    # `parts` = the ranks that own elements of the domain; in the reference EVERY rank takes part (ELASTIC_SIMULATION /
+    # ACOUSTIC_SIMULATION are global) and a rank without such elements sends the zeros its field holds: adding nothing is the same
+    send = {}
     for p in parts:
         db, f = p.db, getattr(p, name)
         s = {}
         for n in range(db.num_interfaces_ext_mesh):
             ids = db.ibool_interfaces_ext_mesh[n, : db.nibool_interfaces_ext_mesh[n]] - 1
             s[int(db.my_neighbors_ext_mesh[n])] = f[ids].copy()
-        send.append(s)
+        send[int(db.myrank)] = s
     for p in parts:
         db, f = p.db, getattr(p, name)
         for n in range(db.num_interfaces_ext_mesh):
-            ids = db.ibool_interfaces_ext_mesh[n, : db.nibool_interfaces_ext_mesh[n]] - 1
-            f[ids] += send[int(db.my_neighbors_ext_mesh[n])][db.myrank]
+            nb = int(db.my_neighbors_ext_mesh[n])
+            if nb in send:
+                ids = db.ibool_interfaces_ext_mesh[n, : db.nibool_interfaces_ext_mesh[n]] - 1
+                f[ids] += send[nb][int(db.myrank)]
 
 
 class OracleRun:

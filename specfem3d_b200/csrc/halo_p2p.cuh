@@ -32,6 +32,9 @@ struct P2PKind {
   unsigned** d_remote_flag = nullptr;   // [nif] neighbour flag address of my slot, parity 0
   size_t* d_remote_parity_stride = nullptr;  // [nif] floats
   int* d_remote_flag_parity_stride = nullptr;  // [nif] words
+  // [nif] 0 = the neighbour owns no elements of this field's domain: it neither packs nor waits, so this rank neither puts
+  // to it nor waits for it (what it would have sent are zeros).  nullptr = every neighbour takes part.
+  int* d_active = nullptr;
 };
 
 struct P2P {
@@ -77,8 +80,9 @@ __global__ void __launch_bounds__(256) k_halo_pack_put(const realw* __restrict__
                                                        realw* const* __restrict__ remote_data, unsigned* const* __restrict__ remote_flag,
                                                        const size_t* __restrict__ remote_parity_stride,
                                                        const int* __restrict__ remote_flag_parity_stride, unsigned* block_counter,
-                                                       unsigned step, int parity, size_t nglob) {
+                                                       unsigned step, int parity, size_t nglob, const int* __restrict__ active) {
   const int iface = blockIdx.y;
+  if (active && !active[iface]) return;  // block-uniform
   const int ipoin = blockIdx.x * blockDim.x + threadIdx.x;
   if (ipoin < nibool[iface]) {
     const size_t iglob = (size_t)ibool_interfaces[ipoin + (size_t)max_nibool * iface] - 1;
@@ -103,8 +107,10 @@ template <int NCOMP>
 __global__ void __launch_bounds__(256) k_halo_wait_unpack(realw* field, const realw* __restrict__ slab_data /*this parity*/,
                                                           const unsigned* flags /*this parity*/, int max_nibool,
                                                           const int* __restrict__ nibool, const int* __restrict__ ibool_interfaces,
-                                                          unsigned step, int* error_flag, size_t nglob) {
+                                                          unsigned step, int* error_flag, size_t nglob,
+                                                          const int* __restrict__ active) {
   const int iface = blockIdx.y;
+  if (active && !active[iface]) return;  // block-uniform: nothing was sent, nothing to wait for
   __shared__ int ok;
   if (threadIdx.x == 0) {
     ok = 1;
@@ -141,6 +147,7 @@ inline void p2p_destroy(DeviceMesh* mp) {
     dev_free(p->kind[k].d_remote_flag);
     dev_free(p->kind[k].d_remote_parity_stride);
     dev_free(p->kind[k].d_remote_flag_parity_stride);
+    dev_free(p->kind[k].d_active);
   }
   dev_free(p->d_block_counter);
   dev_free(p->d_error);
@@ -171,12 +178,12 @@ inline void p2p_pack_put(DeviceMesh* mp, int k, const realw* field) {
     k_halo_pack_put<3><<<grid, 256, 0, mp->compute_stream>>>(field, p->max_nibool, mp->d_nibool_interfaces_ext_mesh,
                                                              mp->d_ibool_interfaces_ext_mesh, K.d_remote_data, K.d_remote_flag,
                                                              K.d_remote_parity_stride, K.d_remote_flag_parity_stride,
-                                                             p->d_block_counter + (size_t)k * p->nif, K.step, parity, (size_t)mp->NGLOB_AB);
+                                                             p->d_block_counter + (size_t)k * p->nif, K.step, parity, (size_t)mp->NGLOB_AB, K.d_active);
   else
     k_halo_pack_put<1><<<grid, 256, 0, mp->compute_stream>>>(field, p->max_nibool, mp->d_nibool_interfaces_ext_mesh,
                                                              mp->d_ibool_interfaces_ext_mesh, K.d_remote_data, K.d_remote_flag,
                                                              K.d_remote_parity_stride, K.d_remote_flag_parity_stride,
-                                                             p->d_block_counter + (size_t)k * p->nif, K.step, parity, (size_t)mp->NGLOB_AB);
+                                                             p->d_block_counter + (size_t)k * p->nif, K.step, parity, (size_t)mp->NGLOB_AB, K.d_active);
   KERNEL_CHECK(mp, "k_halo_pack_put");
 }
 
@@ -189,10 +196,10 @@ inline void p2p_wait_unpack(DeviceMesh* mp, int k, realw* field) {
   const unsigned* flags = reinterpret_cast<const unsigned*>(p->slab) + K.flag_off + (size_t)parity * p->nif;
   if (k == 0)
     k_halo_wait_unpack<3><<<grid, 256, 0, mp->compute_stream>>>(field, data, flags, p->max_nibool, mp->d_nibool_interfaces_ext_mesh,
-                                                                mp->d_ibool_interfaces_ext_mesh, K.step, p2p_error_flag(mp), (size_t)mp->NGLOB_AB);
+                                                                mp->d_ibool_interfaces_ext_mesh, K.step, p2p_error_flag(mp), (size_t)mp->NGLOB_AB, K.d_active);
   else
     k_halo_wait_unpack<1><<<grid, 256, 0, mp->compute_stream>>>(field, data, flags, p->max_nibool, mp->d_nibool_interfaces_ext_mesh,
-                                                                mp->d_ibool_interfaces_ext_mesh, K.step, p2p_error_flag(mp), (size_t)mp->NGLOB_AB);
+                                                                mp->d_ibool_interfaces_ext_mesh, K.step, p2p_error_flag(mp), (size_t)mp->NGLOB_AB, K.d_active);
   KERNEL_CHECK(mp, "k_halo_wait_unpack");
 }
 
@@ -287,6 +294,27 @@ extern "C" void SB200_FC(specfem_b200_halo_p2p_connect)(long* Mesh_pointer, int*
     p->kind[k].d_remote_flag_parity_stride = dev_copy(rfps[k].data(), nif);
   }
   p->connected = true;
+  CUDA_CHECK(cudaDeviceSynchronize());
+}
+
+// Partitions of fluid-solid meshes usually hold ranks without elastic (or without acoustic) elements.  The reference lets every
+// rank take part in assemble_MPI_* and such a rank sends zeros; here it simply stays out of the exchange of that field, and its
+// neighbours are told so: neighbor_has_elastic[n] / neighbor_has_acoustic[n] != 0 when the neighbour of interface n owns elements
+// of the domain (= launches the pack / wait kernels of that field).  Optional: without this call every neighbour is expected to
+// take part.  Call after specfem_b200_halo_p2p_local_info, before the first time step.
+extern "C" void SB200_FC(specfem_b200_halo_p2p_neighbor_domains)(long* Mesh_pointer, const int* neighbor_has_elastic,
+                                                                 const int* neighbor_has_acoustic) {
+  using namespace sb200;
+  DeviceMesh* mp = get_mesh(Mesh_pointer);
+  P2P* p = mp->p2p;
+  if (!p) exit_on_error("halo_p2p_neighbor_domains: call specfem_b200_halo_p2p_local_info first");
+  const int* src[2] = {neighbor_has_elastic, neighbor_has_acoustic};
+  for (int k = 0; k < 2; ++k) {
+    std::vector<int> a(p->nif);
+    for (int n = 0; n < p->nif; ++n) a[n] = src[k][n] != 0;
+    dev_free(p->kind[k].d_active);
+    p->kind[k].d_active = dev_copy(a.data(), p->nif);
+  }
   CUDA_CHECK(cudaDeviceSynchronize());
 }
 

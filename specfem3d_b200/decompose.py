@@ -1,5 +1,4 @@
-"""Element partitioning of the structured box the way xdecompose_mesh does it, as far as it
-can be restated without SCOTCH:
+"""Element partitioning of the structured box the way xdecompose_mesh does it:
 
 * corner-node connectivity of the hexahedra (what meshfem3D's MESH/ files hold) and the **dual graph** of
   ``mesh2dual_ncommonnodes`` (src/decompose_mesh/part_decompose_mesh.F90:49-149, ``ncommonnodes = 1`` as in
@@ -7,14 +6,18 @@ can be restated without SCOTCH:
 * the integer element loads of ``acoustic_elastic_poro_load`` (:1162-1251: acoustic 10, elastic 41, viscoelastic 59);
 * ``partition_rows``: PARTITIONING_TYPE = 4 of the reference (partition_rows.F90), restated exactly -- a partition array that
   IS the reference's;
-* another partition array ``part[]`` -- **not SCOTCH's**: SCOTCH 5.1.12b is vendored by the reference but needs its flex / bison
-  generated parser sources, which this image cannot produce, so ``partition_graph_growing`` is a plain deterministic
-  load-balanced graph-growing partitioner standing in for ``scotchfgraphpart``.  Everything downstream of ``part[]``
-  (meshfem.build_partition: local numbering, interfaces by ascending neighbour rank with coordinate-ordered points, inner /
-  outer elements) takes any partition array, including one written by the real xdecompose_mesh.
+* the partition arrays of PARTITIONING_TYPE = 1 (SCOTCH, the default) and 2 (METIS) come from the partitioners the reference
+  vendors, compiled unmodified as TEST INFRASTRUCTURE (oracle/build_ref_scotch.sh, oracle/build_ref_metis.sh) and called like
+  partition_scotch.F90 / wrap_metis.c call them (oracle/scotch_ref.py, oracle/metis_ref.py) on the dual graph and loads of this
+  module; the product only ever CONSUMES a ``part[]`` (meshfem.build_partition: local numbering, interfaces by ascending
+  neighbour rank with coordinate-ordered points, inner / outer elements), like the solver consumes xdecompose_mesh's output;
+* ``partition_graph_growing``: a plain deterministic load-balanced graph-growing partitioner for hosts where neither
+  library is built (e.g. the GPU box: oracle/_ref travels, /root/reference does not).
 
-Parity: the dual graph is checked against a brute-force neighbourhood; bit parity of ``part[]`` with SCOTCH is **unpinned**
-(and unpinned by the reference's own tests).
+Parity (tests/test_decompose.py): the dual graph is checked against a brute-force neighbourhood; ``part[]`` of both
+partitioners is pinned bit for bit on committed fixtures, and SCOTCH's partition of the reference's own
+EXAMPLES/applications/homogeneous_halfspace/MESH-default reproduces the element and point counts per rank that the
+reference's solver log of that example reports (REF_SEIS/output_solver.txt:34-42).
 """
 from __future__ import annotations
 
@@ -43,6 +46,13 @@ def corner_connectivity(spec: BoxSpec) -> Tuple[np.ndarray, int]:
 def dual_graph(spec: BoxSpec, ncommonnodes: int = 1):
     """(xadj[nspec+1], adjncy[nb_edges], max_neighbor) of mesh2dual_ncommonnodes, 0-based like the Fortran arrays."""
     elmnts, nnodes = corner_connectivity(spec)
+    return dual_graph_of_elements(elmnts, nnodes, ncommonnodes)
+
+
+def dual_graph_of_elements(elmnts: np.ndarray, nnodes: int, ncommonnodes: int = 1):
+    """The same for any HEX8 connectivity elmnts[nspec][8] (0-based node ids), e.g. the `mesh_file` of a MESH/ directory: the
+    neighbour order inside adjncy follows the node numbering like in the Fortran routine, and partitioners depend on it."""
+    elmnts = np.ascontiguousarray(elmnts, np.int32)
     nspec = elmnts.shape[0]
     nsize, sup_neighbor = 8, 26 if ncommonnodes == 1 else (18 if ncommonnodes == 2 else 6)
     xadj = np.zeros(nspec + 1, np.int32)
@@ -335,7 +345,9 @@ def read_mesh_files(directory: str):
     mat = np.zeros(len(elmnts), np.int32)
     for r in table("materials_file", skip=0):
         mat[int(r[0]) - 1] = int(r[1])
-    mat_prop = np.array([[float(v) for v in r] for r in table("nummaterial_velocity_file", skip=0)])
+    # empty and comment lines ('#', '!') are skipped like read_mesh_files.F90:244-247 does (the reference's own example files
+    # carry a format description below the material lines)
+    mat_prop = np.array([[float(v) for v in r[:8]] for r in table("nummaterial_velocity_file", skip=0) if r[0][0] not in "#!"])
     surfaces = {}
     for fid, name in _SURFACE_FILES.items():
         rows = table(name)

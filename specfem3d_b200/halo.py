@@ -20,17 +20,19 @@ from typing import List
 import numpy as np
 
 
-def check_p2p_domains(rank: int, domains, neighbor_domains: dict) -> None:
-    """The p2p path exchanges a field only between ranks that both launch its pack kernel.  The reference has EVERY rank
-    take part in assemble_MPI_* once ELASTIC_SIMULATION / ACOUSTIC_SIMULATION is set globally (a rank without elements of
-    the domain sends zeros); here a neighbour without the domain has no such field on its device and would never raise the
-    flag this rank waits for.  Such partitions (e.g. a purely acoustic part next to an elastic one) must use the
-    host-staged path; refuse them at connect time instead of timing out inside the time loop."""
-    for nb, dom in neighbor_domains.items():
-        for d in domains:
-            if d not in dom:
-                raise ValueError(f"p2p halo: rank {rank} exchanges its {d} field with rank {nb}, which owns no {d} elements; "
-                                 f"use the host-staged halo (halo='host') for this partition")
+def tell_neighbor_domains(rank_obj, neighbor_domains: dict) -> None:
+    """The p2p path exchanges a field only between ranks that both launch its pack / wait kernels.  The reference has EVERY rank
+    take part in assemble_MPI_* once ELASTIC_SIMULATION / ACOUSTIC_SIMULATION is set globally (a rank without elements of the
+    domain sends zeros); here such a rank has no field of that domain on its device and stays out of the exchange, and its
+    neighbours are told not to put to it nor to wait for it (specfem_b200_halo_p2p_neighbor_domains) -- usual for SCOTCH /
+    METIS parts of a fluid-solid mesh, where whole parts are purely elastic."""
+    db = rank_obj.db
+    nif = db.num_interfaces_ext_mesh
+    nbs = [int(v) for v in db.my_neighbors_ext_mesh[:nif]]
+    has_el = np.array([int("elastic" in neighbor_domains[nb]) for nb in nbs], np.int32)
+    has_ac = np.array([int("acoustic" in neighbor_domains[nb]) for nb in nbs], np.int32)
+    rank_obj.lib.cdll.specfem_b200_halo_p2p_neighbor_domains_(ctypes.byref(rank_obj.Mesh_pointer), has_el.ctypes.data_as(ctypes.c_void_p),
+                                                              has_ac.ctypes.data_as(ctypes.c_void_p))
 
 
 def _domains_of(rank_obj):
@@ -88,7 +90,7 @@ class DistributedExchange:
         allinfo = [None] * self.world
         dist.all_gather_object(allinfo, me, group=self.group)
         by_rank = {d["rank"]: d for d in allinfo}
-        check_p2p_domains(r.rank, me["domains"], {nb: by_rank[nb]["domains"] for nb in me["neighbors"]})
+        tell_neighbor_domains(r, {nb: by_rank[nb]["domains"] for nb in me["neighbors"]})
         handles = (ctypes.c_char * (64 * nif))()
         geom = np.zeros(3 * nif, np.int32)
         nbr = np.zeros(nif, np.int32)
@@ -147,8 +149,7 @@ def connect_p2p_in_process(ranks: List) -> None:
         info[r.rank] = (slab.value, int(dev.value))
     by_rank = {r.rank: r for r in ranks}
     for r in ranks:
-        check_p2p_domains(r.rank, _domains_of(r), {int(nb): _domains_of(by_rank[int(nb)])
-                                                   for nb in r.db.my_neighbors_ext_mesh[: r.db.num_interfaces_ext_mesh]})
+        tell_neighbor_domains(r, {int(nb): _domains_of(by_rank[int(nb)]) for nb in r.db.my_neighbors_ext_mesh[: r.db.num_interfaces_ext_mesh]})
     for r in ranks:
         db, L = r.db, r.lib
         nif = db.num_interfaces_ext_mesh

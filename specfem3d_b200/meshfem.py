@@ -822,12 +822,14 @@ def build_all(spec: BoxSpec, DT: float, gll: Optional[GLL] = None, part: Optiona
         set_local_dampingcoeff(spec, dbs, spec.f0_for_pml)
     loc = [local_mass_matrices(spec, db, DT, gll) for db in dbs]
     for key in ("rmassx", "rmassy", "rmassz", "rmass_acoustic", "rmass_ocean_load"):
-        if all(key in l for l in loc):
-            arrs = [l[key] for l in loc]
+        if any(key in l for l in loc):
+            # a partition without elements of the domain (usual for SCOTCH / METIS parts of a fluid-solid mesh) contributes
+            # zeros to the assembly, like the reference's ranks do (their rmass arrays exist whenever the domain exists
+            # anywhere: ELASTIC_SIMULATION / ACOUSTIC_SIMULATION are global flags), and keeps no mass matrix of its own
+            arrs = [l[key] if key in l else np.zeros(db.NGLOB_AB, np.float32) for db, l in zip(dbs, loc)]
             if len(dbs) > 1:
                 assemble_scalar_in_process(dbs, arrs)
-            for db, a in zip(dbs, arrs):
-                setattr(db, key, invert_mass(a))
-        elif any(key in l for l in loc):
-            raise NotImplementedError("harness: every partition must contain both domains or neither")
+            for db, l, a in zip(dbs, loc, arrs):
+                if key in l:
+                    setattr(db, key, invert_mass(a))
     return dbs

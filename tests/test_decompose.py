@@ -283,3 +283,111 @@ def test_run_on_the_metis_partition_equals_single_rank_run():
             assert max(db.num_interfaces_ext_mesh for db in sim.dbs) >= 3
     assert np.abs(runs[0]).max() > 0
     assert np.linalg.norm(runs[1].astype(np.float64) - runs[0]) / np.linalg.norm(runs[0]) <= 2e-5
+
+
+# ---- PARTITIONING_TYPE = 1 (the default): the reference's own SCOTCH 5.1.12b (oracle/_ref/libscotch_ref.so, oracle/build_ref_scotch.sh)
+def _scotch():
+    from oracle import scotch_ref
+
+    if not scotch_ref.available():
+        pytest.skip("oracle/_ref/libscotch_ref.so not built (oracle/build_ref_scotch.sh needs /root/reference)")
+    return scotch_ref
+
+
+def test_scotch_partition_is_the_reference_partition():
+    """`part[]` of xdecompose_mesh with PARTITIONING_TYPE = 1: dual graph + loads of decompose.py handed to the SCOTCH 5.1.12b
+    the reference vendors through the call sequence of partition_scotch.F90:124-190 (oracle/scotch_ref.py: the library's own
+    Fortran entry points, default strategy, scotchfrandomreset).  Pinned bit for bit on a committed fixture
+    (tests/golden/scotch_partition.npz from tests/golden/make_partition_golden.py: 960 elements with mixed loads, 4 and 7 parts)."""
+    import os
+
+    scotch_ref = _scotch()
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "scotch_partition.npz"))
+    spec = metis_box()
+    xadj, adjncy, _ = dual_graph(spec, 1)
+    loads = element_loads(spec)
+    for n in (4, 7):
+        part = scotch_ref.partition_scotch(xadj, adjncy, loads, n)
+        assert np.array_equal(part, gold[f"part_{n}"].astype(np.int32)), n
+        assert np.array_equal(part, scotch_ref.partition_scotch(xadj, adjncy, loads, n))  # scotchfrandomreset: repeatable
+        # the default strategy balances the LOADS (10 per fluid element, 41 per elastic one) within its 5 % tolerance
+        w = np.bincount(part, weights=loads, minlength=n)
+        assert w.min() > 0 and w.max() / w.mean() < 1.05
+    assert np.array_equal(scotch_ref.partition_scotch(xadj, adjncy, loads, 1), np.zeros(len(loads), np.int32))
+
+
+def mesh_default_connectivity():
+    """HEX8 connectivity of EXAMPLES/applications/homogeneous_halfspace/MESH-default/mesh_file (config 1: 36 x 36 x 16 elements),
+    rebuilt: the file lists the elements of the lattice (x fastest, then y, then z) in four runs -- lattice ids 0..9215,
+    17408..18431, 9216..17407, 18432..20735 -- and numbers the nodes on first touch, corners in HEX8 order.  Checked against the
+    file itself where /root/reference exists."""
+    spec = BoxSpec(36, 36, 16, xmax=134000.0, ymax=134000.0, zmin=-60000.0, materials=(HALFSPACE,))
+    lattice, nnodes = corner_connectivity(spec)
+    order = np.concatenate([np.arange(0, 9216), np.arange(17408, 18432), np.arange(9216, 17408), np.arange(18432, 20736)])
+    el = lattice[order]
+    ids, first = np.unique(el.reshape(-1), return_index=True)
+    new = np.empty(nnodes, np.int64)
+    new[ids[np.argsort(first)]] = np.arange(nnodes)
+    return new[el].astype(np.int32), nnodes, order
+
+
+def points_per_part(elmnts, part, nparts):
+    """NGLOB of every part of a conforming HEX8 mesh with NGLL = 5: corners + 3 per edge + 9 per face + 27 per element."""
+    edges = [(0, 1), (1, 2), (2, 3), (3, 0), (4, 5), (5, 6), (6, 7), (7, 4), (0, 4), (1, 5), (2, 6), (3, 7)]
+    faces = [(0, 1, 2, 3), (4, 5, 6, 7), (0, 1, 5, 4), (1, 2, 6, 5), (2, 3, 7, 6), (3, 0, 4, 7)]
+    out = []
+    for p in range(nparts):
+        e = elmnts[part == p].astype(np.int64)
+        nv = len(np.unique(e))
+        ed = np.sort(np.stack([e[:, [a, b]] for a, b in edges], 1).reshape(-1, 2), axis=1)
+        fa = np.sort(np.stack([e[:, list(f)] for f in faces], 1).reshape(-1, 4), axis=1)
+        out.append(nv + 3 * len(np.unique(ed, axis=0)) + 9 * len(np.unique(fa, axis=0)) + 27 * len(e))
+    return out
+
+
+def test_scotch_partition_of_config1_reproduces_the_reference_solver_log():
+    """KNOWN ANSWER from the reference: its solver log of config 1 (EXAMPLES/applications/homogeneous_halfspace/REF_SEIS/
+    output_solver.txt:34-42, four SCOTCH partitions of MESH-default) reports NSPEC_global_min = NSPEC_global_max = 5184 and
+    NGLOB_global_min = NGLOB_global_max = 346385.  The vendored SCOTCH, called like partition_scotch.F90 on the dual graph of that
+    mesh file, gives exactly these four parts (METIS does not: 5035 ... 5302 elements): the four 18 x 18 x 16 quadrants -- which are
+    meshfem3D's NPROC_XI x NPROC_ETA = 2 x 2 slabs, the partition the config-1 golden runs of this repository use."""
+    import os
+
+    from specfem3d_b200.decompose import dual_graph_of_elements, read_mesh_files
+
+    scotch_ref = _scotch()
+    elmnts, nnodes, order = mesh_default_connectivity()
+    ref_dir = "/root/reference/EXAMPLES/applications/homogeneous_halfspace/MESH-default"
+    if os.path.isdir(ref_dir):
+        assert np.array_equal(read_mesh_files(ref_dir)["elmnts"], elmnts)
+    xadj, adjncy, mx = dual_graph_of_elements(elmnts, nnodes, 1)
+    assert mx == 26
+    part = scotch_ref.partition_scotch(xadj, adjncy, np.full(len(elmnts), 41, np.int32), 4)
+    assert np.bincount(part).tolist() == [5184] * 4  # NSPEC_global_min / max of the log
+    assert points_per_part(elmnts, part, 4) == [346385] * 4  # NGLOB_global_min / max of the log
+    ix, iy = order % 36, (order // 36) % 36
+    quadrant = (ix >= 18).astype(np.int64) + 2 * (iy >= 18)
+    for p in range(4):  # one quadrant per part
+        assert len(np.unique(quadrant[part == p])) == 1
+
+
+def test_run_on_the_scotch_partition_equals_single_rank_run():
+    """A coupled fluid-solid run on the 7-part SCOTCH partition of the fixture (unequal parts: SCOTCH balances loads, not element
+    counts; ranks with up to six neighbours, edge- and corner-only contacts) gives the seismograms of the single-rank run."""
+    import os
+
+    from oracle.solver import OracleRun
+
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "scotch_partition.npz"))
+    part = gold["part_7"].astype(np.int32)
+    spec = metis_box()
+    src = [CMTSource(0.52 * spec.xmax, 0.47 * spec.ymax, 0.55 * spec.zmin, (1e23, -2e23, 0.5e23, 0.3e23, -0.7e23, 0.2e23), hdur=0.3)]
+    sts = [Station("A", "XX", 0.21 * spec.xmax, 0.33 * spec.ymax, -6500.0), Station("B", "XX", 0.7 * spec.xmax, 0.6 * spec.ymax, -7000.0)]
+    runs = []
+    for p in (None, part):
+        sim = make_simulation(spec, DT=0.01, NSTEP=300, sources=src, stations=sts, part=p)
+        runs.append(OracleRun(sim).run().seis_d)
+        if p is not None:
+            assert len(sim.dbs) == 7 and max(db.num_interfaces_ext_mesh for db in sim.dbs) >= 4
+    assert np.abs(runs[0]).max() > 0
+    assert np.linalg.norm(runs[1].astype(np.float64) - runs[0]) / np.linalg.norm(runs[0]) <= 2e-5
