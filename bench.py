@@ -469,8 +469,10 @@ def run_device(args):
             assert config["elements_per_gpu"] == db.NSPEC_AB and config["nglob_per_gpu"] == db.NGLOB_AB
         else:
             config.update(elements_per_gpu=db.NSPEC_AB, nglob_per_gpu=db.NGLOB_AB,
-                          partitions=(f"{world} parts of xdecompose_mesh PARTITIONING_TYPE 2 (the reference's METIS 4.0.3 on the dual "
-                                      f"graph, {args.part_file}): {db.num_interfaces_ext_mesh} neighbours on rank 0"))
+                          partitions=(f"{world} parts of xdecompose_mesh "
+                                      + ("PARTITIONING_TYPE 1 (the reference's SCOTCH 5.1.12b" if "scotch" in os.path.basename(args.part_file)
+                                         else "PARTITIONING_TYPE 2 (the reference's METIS 4.0.3")
+                                      + f" on the dual graph, {args.part_file}): {db.num_interfaces_ext_mesh} neighbours on rank 0"))
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
