@@ -56,6 +56,9 @@ typedef struct {
   const double *stf_elastic, *stf_acoustic;
   /* seismograms */
   int has_receivers, NTSTEP_BETWEEN_OUTPUT_SAMPLE, nlength_seismogram;
+  /* pressure seismograms from -potential (the caller's stf_acoustic table then holds the SECOND DERIVATIVE of the source time
+     function, compute_add_sources_acoustic.f90:736-750); handed to compute_seismograms_cuda like write_seismograms.f90:80 does */
+  int USE_TRICK_FOR_BETTER_PRESSURE;
   /* halo transport between the ranks of THIS process: 1 = copy send -> receive buffers on the host (what MPI does between
      processes), 0 = none (single rank, or the library moves the halo itself after specfem_b200_halo_p2p_connect) */
   int host_exchange;

@@ -353,7 +353,9 @@ class OracleRun:
                         P(g.hprime_xx.ravel(order="F").copy()), P(fld), P(hx), P(hy), P(hz), P(nu), P(o))
                     out[irec, k] = o
                 o = np.zeros(1, np.float32)
-                L.oracle_interpolate_pressure(c_int(ispec), P(p.db.ibool), P(p.pot_dot_dot), P(hx), P(hy), P(hz), P(o))
+                # compute_interpolated_dva.f90:295-299: -potential with USE_TRICK_FOR_BETTER_PRESSURE, else -potential_dot_dot
+                pfld = p.pot if sim.USE_TRICK_FOR_BETTER_PRESSURE else p.pot_dot_dot
+                L.oracle_interpolate_pressure(c_int(ispec), P(p.db.ibool), P(pfld), P(hx), P(hy), P(hz), P(o))
                 self.seis_p[irec, k] = o[0]
 
     def run(self, nstep: Optional[int] = None, progress: bool = False):

@@ -37,6 +37,21 @@ def cfg1(nproc_xi: int = 2, nproc_eta: int = 2, NSTEP: int = 5000) -> Simulation
     return make_simulation(spec, DT=0.05, NSTEP=NSTEP, sources=[CMT_DEFAULT], stations=STATIONS_DEFAULT)
 
 
+def homogeneous_acoustic(NSTEP: int = 1000, nproc_xi: int = 1, nproc_eta: int = 1) -> Simulation:
+    """The reference's purely acoustic example (EXAMPLES/applications/homogeneous_acoustic, MESH-default): the config-1 box
+    (134 km x 134 km x 60 km in 36 x 36 x 16 elements) as a fluid (rho 2300, vp 2800; MESH-default/nummaterial_velocity_file),
+    free surface on top, Stacey on the other five sides, an explosive moment tensor (7.7e27 dyne-cm on the diagonal, half
+    duration 2 s) at (67000, 67000, -30000), the four stations of config 1 buried 50 m, PRESSURE seismograms only with
+    USE_TRICK_FOR_BETTER_PRESSURE; DT 0.1136, NSTEP 1000 (DATA/Par_file, CMTSOLUTION, STATIONS; REF_SEIS/output_solver.txt:
+    20736 acoustic elements, start time -6 s, station x-coordinates "original x")."""
+    fluid = Material(2300.0, 2800.0, 0.0, 9999.0, 9999.0, 1)
+    spec = BoxSpec(36, 36, 16, nproc_xi=nproc_xi, nproc_eta=nproc_eta, materials=(fluid,))
+    src = CMTSource(x=67000.0, y=67000.0, z=-30000.0, moment_tensor=(7.7e27, 7.7e27, 7.7e27, 0.0, 0.0, 0.0), hdur=2.0)
+    sts = [Station(s.name, s.network, s.x, s.y, -50.0) for s in STATIONS_DEFAULT]
+    return make_simulation(spec, DT=0.1136, NSTEP=NSTEP, sources=[src], stations=sts, SAVE_SEISMOGRAMS_DISPLACEMENT=False,
+                           SAVE_SEISMOGRAMS_PRESSURE=True, USE_TRICK_FOR_BETTER_PRESSURE=True)
+
+
 def courant_dt(spec: BoxSpec, vp_max: float, courant: float = 0.3) -> float:
     """DT from the Courant rule on the smallest GLL spacing (0.1727 of the element size for NGLL=5)."""
     dx = min((spec.xmax - spec.xmin) / spec.nex_xi, (spec.ymax - spec.ymin) / spec.nex_eta,

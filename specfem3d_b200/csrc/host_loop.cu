@@ -163,7 +163,7 @@ extern "C" void SB200_FC(specfem_b200_iterate_time)(specfem_b200_host_run* run, 
   if (*it_begin < 1 || *it_end > run->NSTEP) host_error("specfem_b200_iterate_time: time steps outside 1 .. NSTEP");
   if (run->NSOURCES > 0 && ((run->ELASTIC_SIMULATION && !run->stf_elastic) || (run->ACOUSTIC_SIMULATION && !run->stf_acoustic)))
     host_error("specfem_b200_iterate_time: source time function table missing");
-  int fwd = 1, zero = 0;
+  int fwd = 1;
   const int every = run->NTSTEP_BETWEEN_OUTPUT_SAMPLE > 0 ? run->NTSTEP_BETWEEN_OUTPUT_SAMPLE : 1;
   for (int it = *it_begin; it <= *it_end; ++it) {
     // update_displ_Newmark: acoustic first, then elastic
@@ -181,7 +181,8 @@ extern "C" void SB200_FC(specfem_b200_iterate_time)(specfem_b200_host_run* run, 
         if (r.nrec_local == 0) continue;
         int itf = it, nl = run->nlength_seismogram;
         compute_seismograms_cuda_(r.Mesh_pointer, r.seismograms_d, r.seismograms_v, r.seismograms_a, r.seismograms_p, &r.seismo_current, &nl,
-                                  &itf, &run->NSTEP, &run->ACOUSTIC_SIMULATION, &run->ELASTIC_SIMULATION, &zero);
+                                  &itf, &run->NSTEP, &run->ACOUSTIC_SIMULATION, &run->ELASTIC_SIMULATION,
+                                  &run->USE_TRICK_FOR_BETTER_PRESSURE);
       }
     }
     if (run->norm_every > 0 && run->norms && (it - *it_begin + 1) % run->norm_every == 0) {  // check_stability

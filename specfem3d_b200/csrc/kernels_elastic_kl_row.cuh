@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(NP ? GRP_CONSUMERS : GRP_THREADS, MINB) k_elas
       if (!NP) {
         if (lane == 0) mbar_arrive(emptyP(sP));  // the parameters are in registers: ring slot consumed by this warp
       } else if (lane == 0 && mbar_arrive_pending(emptyP(sP)) == 1) {  // last of the four warps: refill the slot
+        mbar_acquire_completed(emptyP(sP), (q / STAGES) & 1);  // acquire the completed phase (kernels_elastic_rownp.cuh)
         const int kk = k + STAGES;
         if (kk < 5) issue_chunk(sP, cur_row0, cur_kind, kk);
         else if (has_next) issue_chunk(sP, nxt_row0, nxt_kind, kk - 5);

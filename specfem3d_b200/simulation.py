@@ -35,6 +35,9 @@ class Simulation:
     SAVE_SEISMOGRAMS_VELOCITY: bool = False
     SAVE_SEISMOGRAMS_ACCELERATION: bool = False
     SAVE_SEISMOGRAMS_PRESSURE: bool = False
+    # pressure seismograms in the fluid from -potential of a run driven by the second derivative of the source time function
+    # (compute_add_sources_acoustic.f90:736-750, compute_interpolated_dva.f90:295); forward runs only (prepare_timerun.F90:233)
+    USE_TRICK_FOR_BETTER_PRESSURE: bool = False
     att: Optional[list] = None  # per-partition attenuation arrays (see attenuation.py)
     pml: Optional[list] = None  # per-partition C-PML arrays (see pml.py)
     initial_fields: Optional[list] = None  # per-partition dict(displ=, veloc=, accel=, pot=...) or None = zero
@@ -84,7 +87,7 @@ class Simulation:
 
     def stf_pre_compute_acoustic(self, it: int) -> np.ndarray:
         s = self.sources
-        return np.array([s.stf_acoustic(i, it, self.DT) for i in range(s.NSOURCES)], dtype=np.float64)
+        return np.array([s.stf_acoustic(i, it, self.DT, self.USE_TRICK_FOR_BETTER_PRESSURE) for i in range(s.NSOURCES)], dtype=np.float64)
 
     def time_axis(self) -> np.ndarray:
         """Seismogram time axis: (it-1)*DT - t0 (write_seismograms.f90)."""

@@ -168,6 +168,12 @@ def comp_source_time_function_gauss(t: float, hdur: float) -> float:
     return math.exp(-a * t * t) / (math.sqrt(math.pi) * hdur)
 
 
+def comp_source_time_function_d2gau(t: float, hdur: float) -> float:
+    """Second derivative of the Gaussian (comp_source_time_function.f90:168-192: comp_source_time_function_d2gau)."""
+    a = 1.0 / (hdur * hdur)
+    return 2.0 * a * (-1.0 + 2.0 * a * t * t) * math.exp(-a * t * t) / (math.sqrt(math.pi) * hdur)
+
+
 @dataclass
 class SourceSet:
     NSOURCES: int
@@ -192,14 +198,17 @@ class SourceSet:
             return comp_source_time_function_gauss(t, self.hdur_Gaussian[isource])
         raise ValueError(self.kind)
 
-    def stf_acoustic(self, isource: int, it: int, DT: float) -> float:
+    def stf_acoustic(self, isource: int, it: int, DT: float, trick: bool = False) -> float:
         """``get_stf_acoustic``: Gaussian for moment-tensor (pressure) sources, Ricker for forces
-        (compute_add_sources_acoustic.f90: get_stf_acoustic)."""
+        (compute_add_sources_acoustic.f90:693-830: get_stf_acoustic).  ``trick`` = USE_TRICK_FOR_BETTER_PRESSURE: the second
+        derivative of the source time function drives the fluid and -potential is recorded as pressure (:743-750, :802-806)."""
         t = (it - 1) * DT - self.t0 - self.tshift_src[isource]
-        if self.kind == "cmt":
-            return comp_source_time_function_gauss(t, self.hdur_Gaussian[isource])
         if self.kind == "force_ricker":
+            if trick:
+                raise NotImplementedError("USE_TRICK_FOR_BETTER_PRESSURE with a Ricker force (comp_source_time_function_d2rck)")
             return comp_source_time_function_rickr(t, self.hdur[isource])
+        if trick:
+            return comp_source_time_function_d2gau(t, self.hdur_Gaussian[isource])
         return comp_source_time_function_gauss(t, self.hdur_Gaussian[isource])
 
 

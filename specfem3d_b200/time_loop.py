@@ -268,7 +268,7 @@ class _HostRun(ctypes.Structure):
                 ("PML_CONDITIONS", ctypes.c_int), ("APPROXIMATE_OCEAN_LOAD", ctypes.c_int),
                 ("NSOURCES", ctypes.c_int), ("stf_elastic", _PD), ("stf_acoustic", _PD),
                 ("has_receivers", ctypes.c_int), ("NTSTEP_BETWEEN_OUTPUT_SAMPLE", ctypes.c_int), ("nlength_seismogram", ctypes.c_int),
-                ("host_exchange", ctypes.c_int), ("norm_every", ctypes.c_int), ("norms", _PF)]
+                ("USE_TRICK_FOR_BETTER_PRESSURE", ctypes.c_int), ("host_exchange", ctypes.c_int), ("norm_every", ctypes.c_int), ("norms", _PF)]
 
 
 def _pf(a):
@@ -436,7 +436,8 @@ class DeviceRun:
                 continue
             r.lib.compute_seismograms_cuda(r.Mesh_pointer, r.seismograms_d, r.seismograms_v, r.seismograms_a,
                                            r.seismograms_p, r.seismo_current, sim.nlength_seismogram, it, sim.NSTEP,
-                                           int(sim.ACOUSTIC_SIMULATION), int(sim.ELASTIC_SIMULATION), 0)
+                                           int(sim.ACOUSTIC_SIMULATION), int(sim.ELASTIC_SIMULATION),
+                                           int(sim.USE_TRICK_FOR_BETTER_PRESSURE))
 
     # --------------------------------------------------------------------------------------------------------------
     def run(self, nstep: Optional[int] = None):
@@ -498,6 +499,7 @@ class DeviceRun:
             run.NSOURCES = ns
             run.stf_elastic, run.stf_acoustic = keep["stf_el"].ctypes.data_as(_PD), keep["stf_ac"].ctypes.data_as(_PD)
             run.has_receivers = int(sim.receivers is not None)
+            run.USE_TRICK_FOR_BETTER_PRESSURE = int(sim.USE_TRICK_FOR_BETTER_PRESSURE)
             run.NTSTEP_BETWEEN_OUTPUT_SAMPLE, run.nlength_seismogram = sim.NTSTEP_BETWEEN_OUTPUT_SAMPLE, sim.nlength_seismogram
             self._native = (run, arr, keep)
         run, arr, keep = self._native

@@ -88,10 +88,34 @@ def waterlayer():
     print("wrote waterlayer_ref_seis.npz", len(out["time"]), "samples,", len(steps), "max-norm lines")
 
 
+REF_ACOUSTIC = "/root/reference/EXAMPLES/applications/homogeneous_acoustic/REF_SEIS"
+
+
+def acoustic():
+    """acoustic_ref_seis.npz: the purely acoustic example (EXAMPLES/applications/homogeneous_acoustic/REF_SEIS): the four
+    PRESSURE traces DB.X{20,30,40,50}.MXP.semp (1000 samples, USE_TRICK_FOR_BETTER_PRESSURE) and the max-norm lines of
+    output_solver.txt (potential_dot_dot)."""
+    out = {}
+    for st in ("X20", "X30", "X40", "X50"):
+        d = np.loadtxt(os.path.join(REF_ACOUSTIC, f"DB.{st}.MXP.semp"))
+        out[f"p_{st}"] = d[:, 1].astype(np.float32)
+        out["time"] = d[:, 0].astype(np.float64)
+    txt = open(os.path.join(REF_ACOUSTIC, "output_solver.txt")).read()
+    steps, na = [], []
+    for m in re.finditer(r"Time step #\s+(\d+).*?Max norm pressure P in all slices \(Pa\) =\s+([0-9.E+-]+)", txt, re.S):
+        steps.append(int(m.group(1)))
+        na.append(float(m.group(2)))
+    out["maxnorm_step"] = np.array(steps, dtype=np.int32)
+    out["maxnorm_pressure"] = np.array(na, dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "acoustic_ref_seis.npz"), **out)
+    print("wrote acoustic_ref_seis.npz", len(out["time"]), "samples,", len(steps), "max-norm lines")
+
+
 def main():
     cpml()
     attenuation()
     waterlayer()
+    acoustic()
     out = {}
     for st in ("X20", "X30", "X40", "X50"):
         for ch in "XYZ":

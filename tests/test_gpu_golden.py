@@ -205,3 +205,37 @@ def test_database_files_to_gpu_to_seismogram_files_chain(device_lib, tmp_path):
     # the time column of the written files is the reference's
     t_syn = np.loadtxt(paths[0])[:, 0]
     assert np.allclose(t_syn, gold["time"][:NSTEP], atol=1e-4)
+
+
+def test_homogeneous_acoustic_against_REF_SEIS(device_lib):
+    """Purely acoustic example (EXAMPLES/applications/homogeneous_acoustic): 20,736 fluid elements on 2 x 2 ranks, acoustic
+    Stacey, free surface, explosive source, PRESSURE seismograms with USE_TRICK_FOR_BETTER_PRESSURE (k_seismogram_pressure on
+    -potential), all 1000 steps through the NATIVE host loop in chunks that end where the reference's log prints its stability
+    norm (before step `it`: iterate_time.F90:221-224).  Bars as in the oracle's test (tests/test_oracle_golden.py)."""
+    from specfem3d_b200.configs import homogeneous_acoustic
+    from specfem3d_b200.time_loop import DeviceRun
+
+    gold = np.load(os.path.join(GOLD, "acoustic_ref_seis.npz"))
+    ref_norm = dict(zip(gold["maxnorm_step"].tolist(), gold["maxnorm_pressure"].tolist()))
+    sim = homogeneous_acoustic(nproc_xi=2, nproc_eta=2)
+    assert abs(sim.time_axis()[0] - gold["time"][0]) < 1e-6
+    run = DeviceRun(sim)
+    norms, done = {}, 0
+    for it in sorted(ref_norm):
+        if it - 1 > done:
+            norms[it] = float(run.run_native(it - 1 - done, norm_every=it - 1 - done)[-1])
+            done = it - 1
+    run.run_native(1000 - done)
+    names = [s.name for s in sim.receivers.stations]
+    sp = np.zeros((len(names), 1000), np.float32)
+    for r in run.ranks:
+        for k, irec in enumerate(r.rec_local):
+            sp[irec] = r.seismograms_p[:, k, 0]
+    run.cleanup()
+    for st in ("X20", "X30", "X40", "X50"):
+        err = rel_l2(sp[names.index(st)], gold[f"p_{st}"])
+        print(f"homogeneous_acoustic on the GPU, {st}.MXP: relative L2 vs REF_SEIS = {err:.3e}")
+        assert err <= 1e-4, (st, err)
+    for it, v in norms.items():
+        if it <= 400:
+            assert abs(v - ref_norm[it]) / ref_norm[it] < 1e-4, (it, v, ref_norm[it])

@@ -186,3 +186,46 @@ def test_waterlayered_halfspace_against_REF_SEIS():
         err = np.linalg.norm(syn - ref) / np.linalg.norm(ref)
         bar = 5e-4 if key in ("v_Y1", "v_Y3") else 1e-4
         assert err <= bar, f"water-layer example {key}: relative L2 {err:.3e}"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# purely acoustic runs and PRESSURE seismograms: the reference's example
+# EXAMPLES/applications/homogeneous_acoustic, fixture tests/golden/acoustic_ref_seis.npz (tests/golden/make_golden.py)
+ACOUSTIC_GOLD = os.path.join(os.path.dirname(__file__), "golden", "acoustic_ref_seis.npz")
+
+
+def test_homogeneous_acoustic_against_REF_SEIS():
+    """Pins the oracle's purely acoustic path on the reference's own golden run: the config-1 box as a fluid (20,736 acoustic
+    elements), explosive moment tensor, acoustic Stacey on five sides + free surface, pressure seismograms of four buried stations
+    with USE_TRICK_FOR_BETTER_PRESSURE (the second derivative of the source time function drives the fluid, -potential is
+    recorded), all 1000 steps.  REF_SEIS/DB.X{20..50}.MXP.semp <= 1e-4 relative L2 (measured 7e-6 ... 1.5e-5), and the
+    `Max norm pressure P` lines of REF_SEIS/output_solver.txt: in that run check_stability precedes the step
+    (iterate_time.F90:221-224), so line `Time step # it` is max |potential_dot_dot| after it - 1 steps."""
+    from oracle.solver import OracleRun, set_num_threads
+    from specfem3d_b200.configs import homogeneous_acoustic
+
+    set_num_threads(os.cpu_count() or 1)
+    gold = np.load(ACOUSTIC_GOLD)
+    ref_norm = dict(zip(gold["maxnorm_step"].tolist(), gold["maxnorm_pressure"].tolist()))
+    sim = homogeneous_acoustic()
+    assert sim.dbs[0].nspec_acoustic == 20736 and sim.dbs[0].nspec_elastic == 0
+    assert abs(sim.time_axis()[0] - gold["time"][0]) < 1e-6  # start time -6 s
+    run = OracleRun(sim)
+    norms = {}
+    for it in range(1, 1001):
+        if it in ref_norm:
+            norms[it] = max(float(np.abs(p.pot_dot_dot).max()) for p in run.parts)
+        run.step()
+    names = [s.name for s in sim.receivers.stations]
+    for st in ("X20", "X30", "X40", "X50"):
+        syn = run.seis_p[names.index(st)].astype(np.float64)
+        ref = gold[f"p_{st}"].astype(np.float64)
+        err = np.linalg.norm(syn - ref) / np.linalg.norm(ref)
+        assert err <= 1e-4, f"homogeneous_acoustic {st}.MXP: relative L2 {err:.3e}"
+    # while the wave is inside the box the single-point maximum agrees to 3e-7 ... 9e-6; after it has left (steps >= 500: 3 % and
+    # less of the peak) the maximum of potential_dot_dot -- zeroth-order accurate in Newmark's scheme, which is what the trick is
+    # about -- sits on rounding noise and differs between two runs of the SAME oracle (OpenMP summation order) by up to 1e-3:
+    # no known answer there, not asserted
+    for it, v in norms.items():
+        if it <= 400:
+            assert abs(v - ref_norm[it]) / ref_norm[it] < 1e-4, (it, v, ref_norm[it])

@@ -5,10 +5,10 @@
 # and both halo paths.      tools/gpu_sanitizer.sh <tag>
 TAG=${1:-sanitizer}
 mkdir -p gpurun_out
-SEL="test_elastic_force_kernel_matches_oracle or test_acoustic_force_kernel_matches_oracle or test_attenuation_force_kernel_matches_oracle or test_newmark_stacey_sources_norm_kernels or test_time_loop_seismograms_match_oracle or test_p2p_halo_matches_host_staged_halo or test_coupled_acoustic_elastic_time_loop_matches_oracle or test_cpml_time_loop_matches_oracle or test_viscoelastic_time_loop_matches_oracle"
-for tool in memcheck synccheck racecheck; do
+SEL="test_elastic_force_kernel_matches_oracle or test_attenuation_force_kernel_matches_oracle or (test_acoustic_force_kernel_matches_oracle and nex0) or test_newmark_stacey_sources_norm_kernels or test_p2p_halo_matches_host_staged_halo or (test_cpml_time_loop_matches_oracle and irregular)"
+for tool in ${TOOLS:-memcheck synccheck racecheck}; do
   t0=$(date +%s)
-  timeout 420 compute-sanitizer --tool $tool --error-exitcode 7 --log-file gpurun_out/${TAG}_${tool}.log \
+  timeout ${LIMIT:-120} compute-sanitizer --tool $tool --error-exitcode 7 --log-file gpurun_out/${TAG}_${tool}.log \
       python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "$SEL" > gpurun_out/${TAG}_${tool}_pytest.log 2>&1
   echo "$tool rc=$? wall=$(( $(date +%s) - t0 )) s: $(grep -E 'passed|failed|error' gpurun_out/${TAG}_${tool}_pytest.log | tail -1)"
   grep -E "ERROR SUMMARY|RACECHECK SUMMARY" gpurun_out/${TAG}_${tool}.log | tail -2
