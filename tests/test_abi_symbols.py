@@ -81,3 +81,25 @@ def test_out_of_scope_entry_points_fail_loudly(tmp_path):
     for n in ("prepare_fields_elastic_adj_dev", "compute_kernels_elastic_cuda", "compute_kernels_acoustic_cuda", "compute_coupling_ocean_cuda",
               "transfer_kernels_el_to_host", "add_sources_el_sim_type_2_or_3", "transfer_b_fields_to_device"):
         assert table[n]["implemented"], n
+
+
+@pytest.mark.parametrize("compiler,std", [("gcc", "-std=c99"), ("g++", "-std=c++11")])
+def test_headers_are_plain_c(tmp_path, compiler, std):
+    """include/*.h is the boundary a C, C++ or Fortran caller binds to: plain pointers and sizes, no CUDA / torch types.  Both
+    headers must compile on their own with a C and a C++ compiler, and a designated-initialiser use of the host-loop structs
+     must type-check."""
+    import subprocess
+
+    src = tmp_path / ("t.c" if compiler == "gcc" else "t.cpp")
+    src.write_text('#include "specfem3d_b200.h"\n#include "specfem3d_b200_host.h"\n'
+                   "int main(void) {\n"
+                   "  specfem_b200_host_rank rank;\n  specfem_b200_host_run run;\n"
+                   "  long handle = 0; int one = 1;\n"
+                   "  rank.Mesh_pointer = &handle; rank.myrank = 0;\n"
+                   "  run.nranks = 1; run.ranks = &rank; run.USE_TRICK_FOR_BETTER_PRESSURE = 0;\n"
+                   "  if (sizeof(realw) != 4) return 1;\n"
+                   "  if (0) specfem_b200_iterate_time_(&run, &one, &one);\n"
+                   "  return 0;\n}\n")
+    res = subprocess.run([compiler, std, "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 0, res.stdout[-3000:]
