@@ -319,7 +319,7 @@ def run_device(args):
         nex = tuple(int(v) for v in args.nex.split("x"))
     # warm-up + timed regions 1 (value), 2 (kernel events) and 3 (e2e) all record one seismogram sample per step
     k2 = min(args.steps, 20)
-    nstep_total = args.warmup + 2 * args.steps + k2 + 4
+    nstep_total = args.warmup + 3 * args.steps + k2 + 6  # + the second end-to-end region (norm after every step) and its priming step
     part = None
     if args.part_file:
         if world == 1:
@@ -415,32 +415,50 @@ def run_device(args):
     newmark_ms = n_ms / max(n_cnt, 1)
 
     # ---- timed region 3: end to end through the ABI with host buffers (e2e) -----------------------------------------------
-    # per step: stf H2D from pinned memory (inside compute_add_sources_el_cuda) and a D2H read of the step's stability
-    # metric (get_norm_elastic_from_device: blocking, like check_stability), host wall clock with syncs on both sides
-    barrier()
+    # per step: stf H2D from pinned memory (inside compute_add_sources_el_cuda) and a blocking D2H read of the step's RESULT --
+    # the seismogram samples recorded so far (compute_seismograms_cuda told that the step is the last one) -- plus the
+    # stability norm at the end of the region (check_stability's cadence: every NTSTEP_BETWEEN_OUTPUT_INFO = 500 steps and at
+    # the last step); host wall clock with syncs on both sides.  A second region reads the norm back after EVERY step
+    # (k_max_norm reads the whole displacement field each time): the definition of this key in earlier lines, kept next to it.
     norm = ctypes.c_float(0)
     e2e_loop = "native host loop (specfem_b200_iterate_time, csrc/host_loop.cu)"
-    t0 = time.perf_counter()
+    e2e_norm_ms = None
     try:
-        norms = run.run_native(args.steps, norm_every=1)  # the loop a C / C++ / Fortran caller runs: no interpreter inside
-        norm.value = float(norms[-1])
+        run.run_native(1)  # rank descriptors and the source-time-function table are built outside the timed region
+        native = True
     except NotImplementedError:  # host-staged halo between processes: the exchange itself is Python (gloo)
-        e2e_loop = "Python loop (time_loop.py)"
+        native = False
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    if native:
+        norms = run.run_native(args.steps, norm_every=args.steps, seismo_flush_every=1)  # what a C / C++ / Fortran caller runs
+        norm.value = float(norms[-1])
+    else:
+        e2e_loop = "Python loop (time_loop.py), norm read back after every step"
         for k in range(args.steps):
             run.step()
             lib.get_norm_elastic_from_device(norm, r.Mesh_pointer, 1)
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     e2e_ms = (t1 - t0) * 1e3
+    if native:
+        barrier()
+        t0 = time.perf_counter()
+        norms = run.run_native(args.steps, norm_every=1)
+        torch.cuda.synchronize()
+        e2e_norm_ms = (time.perf_counter() - t0) * 1e3
+        norm.value = float(norms[-1])
     clocks = sampler.stop() if sampler else None
     if not np.isfinite(norm.value):
         raise SystemExit("bench: wavefield became non-finite")
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([ms_total, e2e_ms, k_ms], device="cuda")
+        t = torch.tensor([ms_total, e2e_ms, k_ms, e2e_norm_ms or 0.0], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_ms, _ = (float(v) for v in t.tolist())
+        ms_total, e2e_ms, _, e2e_norm_max = (float(v) for v in t.tolist())
+        e2e_norm_ms = e2e_norm_max if e2e_norm_ms is not None else None
         tl = torch.tensor([float(launches)], device="cuda")
         dist.all_reduce(tl, op=dist.ReduceOp.SUM)
         launches = int(tl.item())
@@ -479,9 +497,16 @@ def run_device(args):
             "dtype": "f32", "data": "synthetic",
             "config": config,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * (sources.NSOURCES if sources else 0),
-                    "d2h_bytes_per_step": 4 * 148 * 4,
-                    "note": "K steps through the C ABI from host buffers: per-step stf upload + blocking norm readback; host wall clock; "
-                            + e2e_loop},
+                    "d2h_bytes_per_step": (12 * r.nrec_local * sim.nlength_seismogram + (4 * 148 * 4) // args.steps) if native else 4 * 148 * 4,
+                    "note": ("K steps through the C ABI from host buffers: per-step stf upload + per-step blocking read-back of the "
+                             "seismograms recorded so far (displacement of the rank's receivers), stability norm at the end of "
+                             "the region (check_stability's cadence); host wall clock; " if native else
+                             "K steps through the C ABI from host buffers: per-step stf upload + blocking norm readback; host wall clock; ")
+                            + e2e_loop,
+                    "norm_after_every_step": None if e2e_norm_ms is None else {
+                        "value": nspec_total * args.steps / (e2e_norm_ms * 1e-3), "d2h_bytes_per_step": 4 * 148 * 4,
+                        "note": "same loop, blocking get_norm_elastic_from_device after EVERY step (k_max_norm reads the whole "
+                                "displacement field): the definition of e2e.value in earlier lines"}},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "k_elastic_forces_rownp (compute_forces_viscoelastic_cuda, outer + inner phase)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

@@ -59,6 +59,10 @@ typedef struct {
   /* pressure seismograms from -potential (the caller's stf_acoustic table then holds the SECOND DERIVATIVE of the source time
      function, compute_add_sources_acoustic.f90:736-750); handed to compute_seismograms_cuda like write_seismograms.f90:80 does */
   int USE_TRICK_FOR_BETTER_PRESSURE;
+  /* 0: the seismograms come back when the device buffer is full or at NSTEP, like in the reference (write_seismograms.f90:
+     NTSTEP_BETWEEN_OUTPUT_SEISMOS); n > 0: additionally after every n-th step of the call (compute_seismograms_cuda is told
+     that the step is the last one, so it hands back -- blocking -- everything recorded so far): real-time monitoring */
+  int seismo_flush_every;
   /* halo transport between the ranks of THIS process: 1 = copy send -> receive buffers on the host (what MPI does between
      processes), 0 = none (single rank, or the library moves the halo itself after specfem_b200_halo_p2p_connect) */
   int host_exchange;

@@ -180,8 +180,10 @@ extern "C" void SB200_FC(specfem_b200_iterate_time)(specfem_b200_host_run* run, 
         r.seismo_current += 1;
         if (r.nrec_local == 0) continue;
         int itf = it, nl = run->nlength_seismogram;
+        const bool flush = run->seismo_flush_every > 0 && (it - *it_begin + 1) % run->seismo_flush_every == 0;
+        int it_last = flush ? it : run->NSTEP;
         compute_seismograms_cuda_(r.Mesh_pointer, r.seismograms_d, r.seismograms_v, r.seismograms_a, r.seismograms_p, &r.seismo_current, &nl,
-                                  &itf, &run->NSTEP, &run->ACOUSTIC_SIMULATION, &run->ELASTIC_SIMULATION,
+                                  &itf, &it_last, &run->ACOUSTIC_SIMULATION, &run->ELASTIC_SIMULATION,
                                   &run->USE_TRICK_FOR_BETTER_PRESSURE);
       }
     }

@@ -268,7 +268,7 @@ class _HostRun(ctypes.Structure):
                 ("PML_CONDITIONS", ctypes.c_int), ("APPROXIMATE_OCEAN_LOAD", ctypes.c_int),
                 ("NSOURCES", ctypes.c_int), ("stf_elastic", _PD), ("stf_acoustic", _PD),
                 ("has_receivers", ctypes.c_int), ("NTSTEP_BETWEEN_OUTPUT_SAMPLE", ctypes.c_int), ("nlength_seismogram", ctypes.c_int),
-                ("USE_TRICK_FOR_BETTER_PRESSURE", ctypes.c_int), ("host_exchange", ctypes.c_int), ("norm_every", ctypes.c_int), ("norms", _PF)]
+                ("USE_TRICK_FOR_BETTER_PRESSURE", ctypes.c_int), ("seismo_flush_every", ctypes.c_int), ("host_exchange", ctypes.c_int), ("norm_every", ctypes.c_int), ("norms", _PF)]
 
 
 def _pf(a):
@@ -446,7 +446,7 @@ class DeviceRun:
             self.step()
         return self
 
-    def run_native(self, nstep: Optional[int] = None, norm_every: int = 0):
+    def run_native(self, nstep: Optional[int] = None, norm_every: int = 0, seismo_flush_every: int = 0):
         """The same steps through the NATIVE host loop (specfem_b200_iterate_time, csrc/host_loop.cu): one call runs ``nstep``
         time steps without the interpreter in between.  Forward runs only (no SAVE_FORWARD record history, no kernel runs).
         Returns the stability norms recorded every ``norm_every`` steps."""
@@ -504,6 +504,7 @@ class DeviceRun:
             self._native = (run, arr, keep)
         run, arr, keep = self._native
         run.host_exchange = host_exchange
+        run.seismo_flush_every = int(seismo_flush_every)
         norms = np.zeros(max(n // norm_every, 1) if norm_every > 0 else 1, np.float32)
         run.norm_every, run.norms = int(norm_every), _pf(norms)
         for k, r in enumerate(self.ranks):
