@@ -36,7 +36,8 @@ def tell_neighbor_domains(rank_obj, neighbor_domains: dict) -> None:
 
 
 def _domains_of(rank_obj):
-    return tuple(d for d, has in (("elastic", rank_obj.ELASTIC), ("acoustic", rank_obj.ACOUSTIC)) if has)
+    db = rank_obj.db
+    return tuple(d for d, has in (("elastic", db.nspec_elastic > 0), ("acoustic", db.nspec_acoustic > 0)) if has)
 
 
 def assemble_scalar_distributed(db, arr: np.ndarray, group) -> None:
@@ -68,6 +69,13 @@ class DistributedExchange:
 
         self.r, self.group, self.mode = rank_obj, group, mode
         self.world = dist.get_world_size()
+        # the domain flags of the run are global (a rank without fluid elements still takes part in the acoustic exchange of a
+        # coupled run -- with zeros --, otherwise its neighbours would wait for it forever)
+        doms = [None] * self.world
+        dist.all_gather_object(doms, _domains_of(rank_obj), group=group)
+        sim = getattr(rank_obj, "sim", None)
+        if sim is not None:
+            sim.global_domains = (any("elastic" in d for d in doms), any("acoustic" in d for d in doms))
         if mode == "p2p":
             self._connect()
 

@@ -67,12 +67,21 @@ class Simulation:
     def APPROXIMATE_OCEAN_LOAD(self) -> bool:
         return bool(getattr(self.spec, "approximate_ocean_load", False))
 
+    # ELASTIC_SIMULATION / ACOUSTIC_SIMULATION are GLOBAL flags in the reference (any_all_l over the ranks,
+    # initialize_simulation.F90): a process that holds only its own database (one rank per process) must be told what the
+    # other ranks own -- halo.DistributedExchange sets this pair; None = derive it from the databases at hand
+    global_domains: Optional[tuple] = None
+
     @property
     def ELASTIC_SIMULATION(self) -> bool:
+        if self.global_domains is not None:
+            return bool(self.global_domains[0])
         return any(db.nspec_elastic > 0 for db in self.dbs if db is not None)
 
     @property
     def ACOUSTIC_SIMULATION(self) -> bool:
+        if self.global_domains is not None:
+            return bool(self.global_domains[1])
         return any(db.nspec_acoustic > 0 for db in self.dbs if db is not None)
 
     @property
