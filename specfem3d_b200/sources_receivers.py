@@ -33,6 +33,11 @@ class CMTSource:
     moment_tensor: Sequence[float]
     hdur: float = 0.0
     tshift: float = 0.0
+    # A source on an element corner belongs to up to eight elements, and the discrete moment-tensor source (derivatives of the
+    # Lagrange polynomials of ONE element) depends on which of them hosts it; the reference takes whichever its kd-tree search
+    # meets first, which depends on the element numbering of the mesh file.  host_side = (sx, sy, sz), each +1 / -1: host the
+    # source in the element on that side of the point (None: the first element touching it, as config 1's log reports).
+    host_side: Optional[Sequence[float]] = None
 
 
 @dataclass
@@ -65,7 +70,7 @@ def _shape8(xi, eta, gam):
     return sh, np.stack([d1, d2, d3])
 
 
-def locate_point(spec: BoxSpec, dbs: List[Database], x: float, y: float, z: float):
+def locate_point(spec: BoxSpec, dbs: List[Database], x: float, y: float, z: float, host_side=None):
     """Find (rank, ispec (1-based), xi, eta, gamma, located xyz).
 
     Element choice mimics the reference's tie-break: the closest GLL point is searched in ascending (rank, ispec)
@@ -78,6 +83,9 @@ def locate_point(spec: BoxSpec, dbs: List[Database], x: float, y: float, z: floa
         lo, hi = c.min(axis=1), c.max(axis=1)
         tol = 1e-9 * (spec.xmax - spec.xmin)
         inside = np.all((lo - tol <= [x, y, z]) & ([x, y, z] <= hi + tol), axis=1)
+        if host_side is not None:  # only the elements on the requested side of the point (CMTSource.host_side)
+            probe = np.array([x, y, z]) + 1e-6 * (spec.xmax - spec.xmin) * np.asarray(host_side, dtype=np.float64)
+            inside &= np.all((lo <= probe) & (probe <= hi), axis=1)
         cand = np.nonzero(inside)[0]
         for e in cand:
             xi = eta = gam = 0.0
@@ -227,7 +235,7 @@ def setup_sources(spec: BoxSpec, dbs: List[Database], sources: Sequence, DT: flo
     in_fluid = []
     by_rank = {db.myrank: db for db in dbs if db is not None}  # the list may hold a subset of the ranks (distributed runs)
     for n, s in enumerate(sources):
-        rank, ispec, xi, eta, gam, _ = locate_point(spec, dbs, s.x, s.y, s.z)
+        rank, ispec, xi, eta, gam, _ = locate_point(spec, dbs, s.x, s.y, s.z, getattr(s, "host_side", None))
         isl[n], isp[n] = rank, ispec
         local.append((xi, eta, gam))
         in_fluid.append(bool(by_rank[rank].ispec_is_acoustic[ispec - 1]))

@@ -111,8 +111,27 @@ def acoustic():
     print("wrote acoustic_ref_seis.npz", len(out["time"]), "samples,", len(steps), "max-norm lines")
 
 
+REF_NOABS = "/root/reference/EXAMPLES/applications/homogeneous_halfspace_HEX8_elastic_no_absorbing/REF_SEIS"
+
+
+def no_absorbing():
+    """noabs_ref_seis.npz: config 1 without absorbing boundaries (EXAMPLES/applications/
+    homogeneous_halfspace_HEX8_elastic_no_absorbing/REF_SEIS/DB.X{20,30,40,50}.BX{X,Y,Z}.semd, all 5000 samples) and the
+    max-norm lines of its output_solver.txt."""
+    out = {}
+    for st in ("X20", "X30", "X40", "X50"):
+        for ch in "XYZ":
+            d = np.loadtxt(os.path.join(REF_NOABS, f"DB.{st}.BX{ch}.semd"))
+            out[f"{st}_{ch}"] = d[:, 1].astype(np.float32)
+            out["time"] = d[:, 0].astype(np.float32)
+    out["maxnorm_step"], out["maxnorm_value"] = maxnorms(os.path.join(REF_NOABS, "output_solver.txt"))
+    np.savez_compressed(os.path.join(HERE, "noabs_ref_seis.npz"), **out)
+    print("wrote noabs_ref_seis.npz", len(out["time"]), "samples,", len(out["maxnorm_step"]), "max-norm lines")
+
+
 def main():
     cpml()
+    no_absorbing()
     attenuation()
     waterlayer()
     acoustic()

@@ -229,3 +229,44 @@ def test_homogeneous_acoustic_against_REF_SEIS():
     for it, v in norms.items():
         if it <= 400:
             assert abs(v - ref_norm[it]) / ref_norm[it] < 1e-4, (it, v, ref_norm[it])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# config 1 WITHOUT absorbing boundaries: EXAMPLES/applications/homogeneous_halfspace_HEX8_elastic_no_absorbing, fixture
+# tests/golden/noabs_ref_seis.npz.  All six faces free: nothing leaves the box, the wavefield keeps bouncing for 5000 steps.
+NOABS_GOLD = os.path.join(os.path.dirname(__file__), "golden", "noabs_ref_seis.npz")
+NOABS_FULL = os.environ.get("SPECFEM_B200_FULL_GOLDEN", "0") == "1"
+
+
+def test_no_absorbing_example_against_REF_SEIS():
+    """Pins free boundaries on all faces (no Stacey term anywhere) and the choice of the element that hosts a source sitting on
+    an element corner (configs.cfg1_no_absorbing, CMTSource.host_side): the log's first stability line, max |u| = 2.15469551
+    before step 5, comes out to 4e-10, the later ones (the wavefield fills the closed box: 799766.75 from step 600 on) to <= 1e-4;
+    the 12 traces <= 1e-4 over the first 600 steps (measured 2.3e-5; 5.3e-5 over 1000).  Nothing is absorbed, so
+    single-precision differences in summation order keep accumulating: 1.2e-4 over 1500 steps, 3.0e-4 over all 5000
+    (SPECFEM_B200_FULL_GOLDEN=1 runs them, 4 min; bar 5e-4)."""
+    from oracle.solver import OracleRun, set_num_threads
+    from specfem3d_b200.configs import cfg1_no_absorbing
+
+    set_num_threads(os.cpu_count() or 1)
+    gold = np.load(NOABS_GOLD)
+    ref_norm = dict(zip(gold["maxnorm_step"].tolist(), gold["maxnorm_value"].tolist()))
+    nstep = 5000 if NOABS_FULL else 600
+    sim = cfg1_no_absorbing(2, 2, nstep)
+    assert np.allclose(np.abs(sim.sources.local[0]), 1.0, atol=1e-9)  # on an element corner
+    run = OracleRun(sim)
+    norms = {}
+    for it in range(1, nstep + 1):
+        if it in ref_norm:
+            norms[it] = run.max_norm_displ()  # check_stability precedes the step
+        run.step()
+    assert abs(norms[5] - ref_norm[5]) / ref_norm[5] < 1e-6
+    for it in (200, 400, 600):
+        assert abs(norms[it] - ref_norm[it]) / ref_norm[it] < 1e-4, (it, norms[it], ref_norm[it])
+    for n, bar in ((600, 1e-4),) + (((5000, 5e-4),) if NOABS_FULL else ()):
+        for i, st in enumerate(("X20", "X30", "X40", "X50")):
+            for c, ch in enumerate("XYZ"):
+                syn = run.seis_d[i, :n, c].astype(np.float64)
+                ref = gold[f"{st}_{ch}"][:n].astype(np.float64)
+                err = np.linalg.norm(syn - ref) / np.linalg.norm(ref)
+                assert err <= bar, f"no-absorbing example {st}.BX{ch}, {n} steps: relative L2 {err:.3e}"
