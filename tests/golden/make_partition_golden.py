@@ -39,7 +39,16 @@ def compute():
         metis[f"part_{n}"] = part.astype(np.int8)
         metis[f"edgecut_{n}"] = np.int32(edgecut)
         scotch[f"part_{n}"] = scotch_ref.partition_scotch(xadj, adjncy, loads, n).astype(np.int8)
-    return {"metis_partition.npz": metis, "scotch_partition.npz": scotch}
+    # the mesh of the reference's coupled example (EXAMPLES/applications/waterlayered_halfspace/MESH-default: 45 x 45 x 20 HEX8
+    # elements in the file's own element order and node numbering, material id per element, domain per material id): input of the
+    # SCOTCH known answer in tests/test_decompose.py (NSPEC / NGLOB min / max per rank of REF_SEIS/output_solver.txt:45-51)
+    from specfem3d_b200.decompose import read_mesh_files
+
+    m = read_mesh_files("/root/reference/EXAMPLES/applications/waterlayered_halfspace/MESH-default")
+    assert m["elmnts"].max() < 65536
+    mesh = {"elmnts": m["elmnts"].astype(np.uint16), "mat": m["mat"].astype(np.int8), "nnodes": np.int32(len(m["nodes_coords"])),
+            "material_id": m["mat_prop"][:, 1].astype(np.int8), "material_domain": m["mat_prop"][:, 0].astype(np.int8)}
+    return {"metis_partition.npz": metis, "scotch_partition.npz": scotch, "waterlayer_mesh.npz": mesh}
 
 
 def main():

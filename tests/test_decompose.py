@@ -391,3 +391,29 @@ def test_run_on_the_scotch_partition_equals_single_rank_run():
             assert len(sim.dbs) == 7 and max(db.num_interfaces_ext_mesh for db in sim.dbs) >= 4
     assert np.abs(runs[0]).max() > 0
     assert np.linalg.norm(runs[1].astype(np.float64) - runs[0]) / np.linalg.norm(runs[0]) <= 2e-5
+
+
+def test_scotch_partition_of_the_water_layer_example_reproduces_the_reference_solver_log():
+    """Second KNOWN ANSWER from the reference, with unequal loads: the coupled example (EXAMPLES/applications/
+    waterlayered_halfspace: 2,025 fluid elements of load 10 on top of 38,475 solid ones of load 41, four SCOTCH partitions) logs
+    NSPEC_global_min / max = 10100 / 10160 and NGLOB_global_min / max = 669141 / 673353 (REF_SEIS/output_solver.txt:45-51).  The
+    vendored SCOTCH on the dual graph of that mesh file with the loads of acoustic_elastic_poro_load gives parts of 10120, 10120,
+    10100 and 10160 elements with 670437, 670437, 669141 and 673353 points.  Mesh: tests/golden/waterlayer_mesh.npz (the file's own
+    element order and node numbering, tests/golden/make_partition_golden.py)."""
+    import os
+
+    from specfem3d_b200.decompose import ACOUSTIC_LOAD, ELASTIC_LOAD, dual_graph_of_elements
+
+    scotch_ref = _scotch()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "waterlayer_mesh.npz"))
+    elmnts = g["elmnts"].astype(np.int32)
+    domain = dict(zip(g["material_id"].tolist(), g["material_domain"].tolist()))  # 1 = acoustic, 2 = elastic
+    loads = np.array([ACOUSTIC_LOAD if domain[int(k)] == 1 else ELASTIC_LOAD for k in g["mat"]], np.int32)
+    assert int((loads == ACOUSTIC_LOAD).sum()) == 2025 and int((loads == ELASTIC_LOAD).sum()) == 38475  # output_solver.txt:35-36
+    xadj, adjncy, _ = dual_graph_of_elements(elmnts, int(g["nnodes"]), 1)
+    part = scotch_ref.partition_scotch(xadj, adjncy, loads, 4)
+    nspec = np.bincount(part, minlength=4)
+    nglob = points_per_part(elmnts, part, 4)
+    assert (int(nspec.min()), int(nspec.max())) == (10100, 10160)
+    assert (min(nglob), max(nglob)) == (669141, 673353)
+    assert sorted(nspec.tolist()) == [10100, 10120, 10120, 10160] and sorted(nglob) == [669141, 670437, 670437, 673353]
