@@ -46,7 +46,14 @@ def compute():
 
     m = read_mesh_files("/root/reference/EXAMPLES/applications/waterlayered_halfspace/MESH-default")
     assert m["elmnts"].max() < 65536
+    # lattice id (ix + 45 (iy + 45 iz)) of every element of the file, from the element centres: the harness builds its databases
+    # in lattice order
+    c = m["nodes_coords"][m["elmnts"]].mean(axis=1)
+    h = 134000.0 / 45
+    lattice = (np.rint(c[:, 0] / h - 0.5) + 45 * np.rint(c[:, 1] / h - 0.5) + 2025 * np.rint((c[:, 2] + 60000.0) / 3000.0 - 0.5)).astype(np.int64)
+    assert np.array_equal(np.sort(lattice), np.arange(40500))
     mesh = {"elmnts": m["elmnts"].astype(np.uint16), "mat": m["mat"].astype(np.int8), "nnodes": np.int32(len(m["nodes_coords"])),
+            "lattice": lattice.astype(np.uint16),
             "material_id": m["mat_prop"][:, 1].astype(np.int8), "material_domain": m["mat_prop"][:, 0].astype(np.int8)}
     return {"metis_partition.npz": metis, "scotch_partition.npz": scotch, "waterlayer_mesh.npz": mesh}
 
@@ -61,7 +68,7 @@ def main():
             print(name, "identical" if same else "DIFFERENT")
             if not same:
                 raise SystemExit(1)
-        elif os.path.exists(path) and all(np.array_equal(np.load(path)[k], v) for k, v in arrays.items()):
+        elif os.path.exists(path) and all(k in np.load(path).files and np.array_equal(np.load(path)[k], v) for k, v in arrays.items()):
             print("unchanged", path)
         else:
             np.savez_compressed(path, **arrays)

@@ -417,3 +417,49 @@ def test_scotch_partition_of_the_water_layer_example_reproduces_the_reference_so
     assert (int(nspec.min()), int(nspec.max())) == (10100, 10160)
     assert (min(nglob), max(nglob)) == (669141, 673353)
     assert sorted(nspec.tolist()) == [10100, 10120, 10120, 10160] and sorted(nglob) == [669141, 670437, 670437, 673353]
+
+    # ... and the solver databases the harness builds from that part[] reproduce what xgenerate_databases logged for it
+    # (REF_SEIS/output_generate_databases.txt): rank 0 holds 10120 elements / 670437 points (:212-215), `number of MPI partition
+    # interfaces: 10` (:56), `total MPI interface points: 59778`, `total assembled MPI interface points: 59292` (:95-96, get_MPI.f90:
+    # the interface lists of all ranks, and the distinct points on them), rank 0's 1406 absorbing and 506 free-surface faces (:78-104)
+    from specfem3d_b200.configs import waterlayered_halfspace
+    from specfem3d_b200.gll import GLL
+    from specfem3d_b200.meshfem import build_partition
+
+    part_lattice = np.empty(len(part), np.int32)
+    part_lattice[g["lattice"].astype(np.int64)] = part
+    spec = waterlayered_halfspace(2, stations=("X10",)).spec
+    gll = GLL()
+    dbs = [build_partition(spec, r, gll, part=part_lattice) for r in range(4)]
+    assert [db.NSPEC_AB for db in dbs] == nspec.tolist() and [db.NGLOB_AB for db in dbs] == nglob
+    assert (dbs[0].NSPEC_AB, dbs[0].NGLOB_AB) == (10120, 670437)
+    assert sum(db.num_interfaces_ext_mesh for db in dbs) == 10
+    assert sum(int(db.nibool_interfaces_ext_mesh[: db.num_interfaces_ext_mesh].sum()) for db in dbs) == 59778
+    distinct = 0
+    for db in dbs:
+        ids = [db.ibool_interfaces_ext_mesh[n, : db.nibool_interfaces_ext_mesh[n]] for n in range(db.num_interfaces_ext_mesh)]
+        distinct += len(np.unique(np.concatenate(ids)))
+    assert distinct == 59292
+    assert dbs[0].num_abs_boundary_faces == 1406 and dbs[0].num_free_surface_faces == 506
+    assert sum(db.num_coupling_ac_el_faces for db in dbs) == 2025  # acoustic - elastic coupling: total number of faces (:128)
+
+
+def test_config1_interfaces_reproduce_the_reference_mesher_log():
+    """KNOWN ANSWER: for config 1 on its four partitions the reference logs `number of MPI partition interfaces: 12`, `total MPI
+    interface points: 38220` and `total assembled MPI interface points: 37700` (EXAMPLES/applications/homogeneous_halfspace/REF_SEIS/
+    output_mesher.txt:52-65; the same numbers in the logs of homogeneous_acoustic and ..._HEX8_elastic_no_absorbing): every rank
+    has three neighbours (two faces of 73 x 65 points and the vertical edge of 65 points in the middle of the box)."""
+    from specfem3d_b200.gll import GLL
+    from specfem3d_b200.meshfem import build_partition
+
+    spec = BoxSpec(36, 36, 16, nproc_xi=2, nproc_eta=2, materials=(HALFSPACE,))
+    gll = GLL()
+    dbs = [build_partition(spec, r, gll) for r in range(4)]
+    assert [db.NSPEC_AB for db in dbs] == [5184] * 4 and [db.NGLOB_AB for db in dbs] == [346385] * 4
+    assert sum(db.num_interfaces_ext_mesh for db in dbs) == 12
+    assert sum(int(db.nibool_interfaces_ext_mesh[: db.num_interfaces_ext_mesh].sum()) for db in dbs) == 38220
+    distinct = 0
+    for db in dbs:
+        ids = [db.ibool_interfaces_ext_mesh[n, : db.nibool_interfaces_ext_mesh[n]] for n in range(db.num_interfaces_ext_mesh)]
+        distinct += len(np.unique(np.concatenate(ids)))
+    assert distinct == 37700
