@@ -42,6 +42,7 @@ METRIC = "elastic element-timesteps/sec"
 UNIT = "element-timesteps/s"
 BYTES_PER_ELEMENT_FORCE_IRREGULAR = 8304  # SURVEY.md section 8d / BASELINE.md section 3
 BYTES_PER_ELEMENT_FORCE_REGULAR = 3804
+FLOPS_PER_ELEMENT_FORCE = 42590           # the reference's count for Kernel_2_noatt_iso_impl (Kernel_2_viscoelastic_impl.cu:996-997)
 BYTES_PER_ELEMENT_ATTENUATION = 36072     # SURVEY.md section 8d (irregular element, 3 SLS)
 BYTES_PER_ELEMENT_ACOUSTIC = 6268
 BYTES_PER_ELEMENT_PML = 82300             # DESIGN.md section 4 (48 memory planes r+w, 41 coefficient planes, ...)
@@ -513,7 +514,10 @@ def run_device(args):
                          "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_element": bytes_per_el,
                          "elements_per_step": nel, "launches_per_step": f_cnt / k2, "kernel_ms": k_ms,
                          "timed": f"CUDA events on the library's compute stream around every launch of {k2} consecutive time steps",
-                         "elements_per_s": nel / (k_ms * 1e-3)},
+                         "elements_per_s": nel / (k_ms * 1e-3),
+                         # secondary: the reference's own FLOP count for this kernel, 42,590 per element
+                         # (src/gpu/kernels/Kernel_2_viscoelastic_impl.cu:996-997), at the measured kernel time
+                         "fp32_tflops": FLOPS_PER_ELEMENT_FORCE * nel / (k_ms * 1e-3) / 1e12, "flops_per_element": FLOPS_PER_ELEMENT_FORCE},
             "newmark": {"kernel": "k_newmark_corrector_predictor_c (deferred corrector + predictor, compact inverse mass matrix)", "kernel_ms": newmark_ms,
                         "achieved": nel * BYTES_PER_ELEMENT_NEWMARK_FUSED / (newmark_ms * 1e-3) / 1e9 if newmark_ms > 0 else None,
                         "unit": "GB/s", "algorithmic_bytes_per_element": BYTES_PER_ELEMENT_NEWMARK_FUSED},
