@@ -49,12 +49,25 @@ def dual_graph(spec: BoxSpec, ncommonnodes: int = 1):
     return dual_graph_of_elements(elmnts, nnodes, ncommonnodes)
 
 
+def check_valence(elmnts: np.ndarray, nnodes: int):
+    """(nsize, sup_neighbor) of check_valence (src/decompose_mesh/check_valence.F90:29-112): nsize = the largest number of
+    elements meeting at a node (every use of a node in the connectivity counts, all NGNOD nodes of an element), sup_neighbor =
+    8 nsize - (8 + 3 * 6) but at least nsize -- the bound on dual-graph neighbours the reference sizes `adjncy` with before
+    get_max_neighbor tightens it.  An unused node stops the reference; here it raises."""
+    used = np.bincount(np.asarray(elmnts).reshape(-1), minlength=nnodes)
+    if len(used) > nnodes or (used == 0).any():
+        raise ValueError("check_valence: node index out of bounds / found some unused nodes")
+    nsize = int(used.max())
+    return nsize, max(8 * nsize - (8 + 3 * 6), nsize)
+
+
 def dual_graph_of_elements(elmnts: np.ndarray, nnodes: int, ncommonnodes: int = 1):
     """The same for any HEX8 connectivity elmnts[nspec][8] (0-based node ids), e.g. the `mesh_file` of a MESH/ directory: the
     neighbour order inside adjncy follows the node numbering like in the Fortran routine, and partitioners depend on it."""
     elmnts = np.ascontiguousarray(elmnts, np.int32)
     nspec = elmnts.shape[0]
-    nsize, sup_neighbor = 8, 26 if ncommonnodes == 1 else (18 if ncommonnodes == 2 else 6)
+    nsize, sup = check_valence(elmnts, nnodes)  # 8 and 38 for a conforming box: 26 / 18 / 6 real neighbours at most
+    sup_neighbor = min(sup, 26 if ncommonnodes == 1 else (18 if ncommonnodes == 2 else 6)) if nsize <= 8 else sup
     xadj = np.zeros(nspec + 1, np.int32)
     adjncy = np.zeros(sup_neighbor * nspec, np.int32)
     mx = ctypes.c_int32(0)

@@ -463,3 +463,58 @@ def test_config1_interfaces_reproduce_the_reference_mesher_log():
         ids = [db.ibool_interfaces_ext_mesh[n, : db.nibool_interfaces_ext_mesh[n]] for n in range(db.num_interfaces_ext_mesh)]
         distinct += len(np.unique(np.concatenate(ids)))
     assert distinct == 37700
+
+
+# ---- the reference's own unit tests of this path (tests/decompose_mesh/), restated ------------------------------------------
+def _row_of_elements(nspec=12):
+    """The fictitious mesh of tests/decompose_mesh/test_partitioning.f90:32-60: a row of 12 hexahedra, each sharing its
+    nodes 1-4 with nodes 5-8 of the element before (0-based here)."""
+    el = np.zeros((nspec, 8), np.int32)
+    inode = 0
+    for e in range(nspec):
+        for i in range(8):
+            if e > 0 and i < 4:
+                el[e, i] = el[e - 1, i + 4]
+            else:
+                el[e, i] = inode
+                inode += 1
+    return el, inode
+
+
+def test_reference_unit_test_valence():
+    """tests/decompose_mesh/test_valence.f90: 12 disconnected HEX8 elements -> nsize 1; 12 HEX27 elements of which five re-use
+    node 2 -> nsize 6; and the row of test_partitioning.f90:100-108 -> nsize 2."""
+    from specfem3d_b200.decompose import check_valence
+
+    el = np.arange(12 * 8, dtype=np.int32).reshape(12, 8)
+    assert check_valence(el, 96)[0] == 1
+    el27, inode = np.zeros((12, 27), np.int32), 0
+    reuse = {(3, 3), (4, 9), (5, 12), (9, 17), (12, 27)}  # (ispec, i), 1-based as in the Fortran test: these take node 2
+    for e in range(1, 13):
+        for i in range(1, 28):
+            if (e, i) in reuse:
+                el27[e - 1, i - 1] = 2 - 1
+            else:
+                el27[e - 1, i - 1] = inode
+                inode += 1
+    assert check_valence(el27, inode)[0] == 6
+    row, nnodes = _row_of_elements()
+    assert nnodes == 52 and check_valence(row, nnodes)[0] == 2
+
+
+def test_reference_unit_test_partitioning():
+    """tests/decompose_mesh/test_partitioning.f90 without its LTS part: the row of 12 elements (acoustic material: load 10 each),
+    SCOTCH (PARTITIONING_TYPE = 1), 4 parts -- every element gets a valid part, which is all the reference's test asserts; here
+    also: the dual graph is the chain, and SCOTCH cuts it into four contiguous runs of three."""
+    from specfem3d_b200.decompose import ACOUSTIC_LOAD, dual_graph_of_elements
+
+    scotch_ref = _scotch()
+    row, nnodes = _row_of_elements()
+    xadj, adjncy, mx = dual_graph_of_elements(row, nnodes, 1)
+    assert mx == 2 and xadj.tolist() == [0, 1] + list(range(3, 22, 2)) + [22]
+    assert [sorted(adjncy[xadj[e]: xadj[e + 1]].tolist()) for e in (0, 5, 11)] == [[1], [4, 6], [10]]
+    part = scotch_ref.partition_scotch(xadj, adjncy, np.full(12, ACOUSTIC_LOAD, np.int32), 4)
+    assert part.min() >= 0 and part.max() == 3
+    assert np.bincount(part).tolist() == [3, 3, 3, 3]
+    assert all(len(set(np.flatnonzero(part == p).tolist()) ^ set(range(np.flatnonzero(part == p).min(), np.flatnonzero(part == p).min() + 3))) == 0
+               for p in range(4))
