@@ -5,7 +5,7 @@
 # and both halo paths.      tools/gpu_sanitizer.sh <tag>
 TAG=${1:-sanitizer}
 mkdir -p gpurun_out
-SEL="test_elastic_force_kernel_matches_oracle or test_attenuation_force_kernel_matches_oracle or (test_acoustic_force_kernel_matches_oracle and nex0) or test_newmark_stacey_sources_norm_kernels or test_p2p_halo_matches_host_staged_halo or (test_cpml_time_loop_matches_oracle and irregular)"
+SEL=${SEL:-"test_elastic_force_kernel_matches_oracle or test_attenuation_force_kernel_matches_oracle or (test_acoustic_force_kernel_matches_oracle and nex0) or test_newmark_stacey_sources_norm_kernels or test_p2p_halo_matches_host_staged_halo or (test_cpml_time_loop_matches_oracle and irregular)"}
 for tool in ${TOOLS:-memcheck synccheck racecheck}; do
   t0=$(date +%s)
   timeout ${LIMIT:-120} compute-sanitizer --tool $tool --error-exitcode 7 --log-file gpurun_out/${TAG}_${tool}.log \
