@@ -236,6 +236,42 @@ def min_resolved_period_from_mesh(dbs) -> float:
     return pmax
 
 
+def check_mesh_resolution(dbs, DT: float) -> dict:
+    """The numbers check_mesh_resolution prints into output_solver.txt (src/shared/check_mesh_resolution.f90:150-330), from the
+    mesh arrays of all ranks in CUSTOM_REAL arithmetic: min / max distance between neighbouring GLL points along xi, eta, gamma
+    (get_GLL_minmaxdistance, :1390-1468: pairs starting at i, j, k < NGLL), min / max element size (corner-to-corner edges,
+    get_elem_minmaxsize), `Maximum suggested time step` = COURANT_SUGGESTED (0.5) x distance_min / max(vp, vs) minimised over
+    the elements, `Max stability for wave velocities` = DT x vp / distance_min maximised, `Minimum period resolved`."""
+    f = np.float32
+    out = dict(distance_min=np.inf, distance_max=0.0, elemsize_min=np.inf, elemsize_max=0.0, dt_suggested=np.inf, cmax=0.0,
+               pmax=min_resolved_period_from_mesh(dbs))
+    for db in dbs:
+        if db is None:
+            continue
+        nspec = db.NSPEC_AB
+        ib = np.asarray(db.ibool).reshape(nspec, 5, 5, 5) - 1  # [ispec, k, j, i]
+        xyz = np.stack([np.asarray(db.xstore, f), np.asarray(db.ystore, f), np.asarray(db.zstore, f)], -1)[ib]
+        p = xyz[:, :4, :4, :4]
+        d2 = np.stack([((xyz[:, :4, :4, 1:] - p) ** 2).sum(-1), ((xyz[:, :4, 1:, :4] - p) ** 2).sum(-1),
+                       ((xyz[:, 1:, :4, :4] - p) ** 2).sum(-1)], 1).reshape(nspec, -1).astype(f)
+        dmin, dmax = np.sqrt(d2.min(1)), np.sqrt(d2.max(1))
+        c = xyz[:, ::4][:, :, ::4][:, :, :, ::4]
+        e2 = np.concatenate([((c[:, :, :, 1] - c[:, :, :, 0]) ** 2).sum(-1).reshape(nspec, -1),
+                             ((c[:, :, 1, :] - c[:, :, 0, :]) ** 2).sum(-1).reshape(nspec, -1),
+                             ((c[:, 1, :, :] - c[:, 0, :, :]) ** 2).sum(-1).reshape(nspec, -1)], 1).astype(f)
+        rho = np.asarray(db.rhostore, f).reshape(nspec, -1)[:, :125]
+        mu = np.asarray(db.mustore, f).reshape(nspec, -1)[:, :125]
+        ka = np.asarray(db.kappastore, f).reshape(nspec, -1)[:, :125]
+        vp = np.sqrt(((f(4.0 / 3.0) * mu + ka) / rho).max(1).astype(f))  # vs <= vp always
+        out["distance_min"] = min(out["distance_min"], float(dmin.min()))
+        out["distance_max"] = max(out["distance_max"], float(dmax.max()))
+        out["elemsize_min"] = min(out["elemsize_min"], float(np.sqrt(e2.min())))
+        out["elemsize_max"] = max(out["elemsize_max"], float(np.sqrt(e2.max())))
+        out["dt_suggested"] = min(out["dt_suggested"], float((f(0.5) * dmin / vp).min()))
+        out["cmax"] = max(out["cmax"], float((f(DT) * vp / dmin).max()))
+    return out
+
+
 def min_resolved_period_of(sim) -> float:
     """The solver's min_resolved_period: check_mesh_resolution's estimate from the mesh arrays of all ranks
     (:func:`min_resolved_period_from_mesh`), whether the mesh came from the harness' generator or from database files.

@@ -139,3 +139,26 @@ def test_mesh_coloring_permutation_follows_the_reference_rules():
     a, b = OracleRun(sim).run(), OracleRun(make(False)).run()
     assert np.abs(b.seis_d).max() > 0
     assert np.linalg.norm(a.seis_d - b.seis_d) <= 1e-5 * np.linalg.norm(b.seis_d)  # same physics, permuted storage
+
+
+def test_check_mesh_resolution_numbers_of_two_reference_logs():
+    """KNOWN ANSWERS: the lines check_mesh_resolution prints into REF_SEIS/output_solver.txt for config 1
+    (EXAMPLES/applications/homogeneous_halfspace, :64-76) and for the coupled water-layer example (:77-89).  Distances and sizes are
+    single-precision results of the mesh coordinate arrays, so the harness' xstore / ystore / zstore must carry the reference's
+    float32 coordinates for `Min element size = 3722.21875` (not 3722.2222) to come out."""
+    from specfem3d_b200.attenuation import check_mesh_resolution
+    from specfem3d_b200.configs import cfg1, waterlayered_halfspace
+
+    def same_print(value, printed):  # the log shows 9 significant digits of a float32
+        return abs(value - printed) <= 6e-8 * abs(printed) + 1e-12
+
+    r = check_mesh_resolution(cfg1(2, 2, 10).dbs, 0.05)
+    assert same_print(r["distance_max"], 1227.47656) and same_print(r["distance_min"], 642.726562)
+    assert same_print(r["elemsize_max"], 3750.0) and same_print(r["elemsize_min"], 3722.21875)
+    assert same_print(r["pmax"], 3.125)
+    assert abs(r["dt_suggested"] - 0.114772588) < 1e-6 * 0.1148 and abs(r["cmax"] - 0.217822045) < 1e-6 * 0.2178
+    r = check_mesh_resolution(waterlayered_halfspace(10, stations=("X10",)).dbs, 0.005)
+    assert same_print(r["distance_max"], 981.980530) and same_print(r["distance_min"], 514.179688)
+    assert same_print(r["elemsize_max"], 3000.0) and same_print(r["elemsize_min"], 2977.77344)
+    assert abs(r["pmax"] - 2.53378391) < 1e-6 * 2.53
+    assert abs(r["dt_suggested"] - 3.42786461e-02) < 1e-6 * 0.0343 and abs(r["cmax"] - 7.29316995e-02) < 1e-6 * 0.0729
