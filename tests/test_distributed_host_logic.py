@@ -136,3 +136,55 @@ def test_gloo_world2_arbitrary_partition_and_distributed_location(tmp_path):
         assert np.array_equal(r.islice_selected_rec, ref_r.islice_selected_rec)
         assert np.array_equal(r.ispec_selected_rec, ref_r.ispec_selected_rec)
         assert np.allclose(r.hxir_store, ref_r.hxir_store) and np.allclose(r.hgammar_store, ref_r.hgammar_store)
+
+
+def _worker_domains(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from specfem3d_b200.halo import DistributedExchange
+    from specfem3d_b200.meshfem import Material
+    from specfem3d_b200.simulation import Simulation
+
+    water = Material(1020.0, 1500.0, 0.0, 9999.0, 9999.0, 1)
+    rock = Material(2300.0, 2800.0, 1500.0, 9999.0, 9999.0, 2)
+    spec = BoxSpec(4, 2, 4, xmax=4000.0, ymax=2000.0, zmin=-4000.0, materials=(rock, water), layer_material=[0, 0, 0, 1])
+    e = np.arange(spec.nspec_total)
+    part = ((e // 8) < 2).astype(np.int32)  # rank 1: the two bottom layers (rock only); rank 0: rock + the water layer
+    gll = GLL()
+    db = build_partition(spec, rank, gll, part=part)
+    dbs = [None, None]
+    dbs[rank] = db
+    sim = Simulation(spec, 0.01, 10, dbs, gll, None, None)
+    local = (sim.ELASTIC_SIMULATION, sim.ACOUSTIC_SIMULATION)
+
+    class FakeRank:
+        pass
+
+    r = FakeRank()
+    r.db, r.rank, r.sim = db, rank, sim
+    ni, mx = db.num_interfaces_ext_mesh, db.max_nibool_interfaces_ext_mesh
+    r.buffer_send_scalar = np.full((ni, mx), float(rank + 1) if db.nspec_acoustic else 0.0, np.float32)
+    r.buffer_recv_scalar = np.full((ni, mx), -1.0, np.float32)
+    r.buffer_send_vector = np.zeros((ni, mx, 3), np.float32)
+    r.buffer_recv_vector = np.zeros((ni, mx, 3), np.float32)
+    ex = DistributedExchange(r, dist.group.WORLD, mode="host")
+    ex.exchange("scalar")  # both ranks take part: the one without fluid elements sends the zeros its buffer holds
+    cnt = db.nibool_interfaces_ext_mesh[0]
+    np.save(os.path.join(out_dir, f"dom_{rank}.npy"),
+            np.array([local[0], local[1], sim.ELASTIC_SIMULATION, sim.ACOUSTIC_SIMULATION, db.nspec_acoustic > 0,
+                      float(r.buffer_recv_scalar[0, :cnt].max())], dtype=np.float64))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_domain_flags_are_global(tmp_path):
+    """One rank per process: ELASTIC_SIMULATION / ACOUSTIC_SIMULATION are global flags in the reference (any_all_l over the
+    ranks).  A part without fluid elements must still see ACOUSTIC_SIMULATION and take part in the scalar exchange (with zeros),
+    otherwise its neighbour waits for it forever (halo.DistributedExchange sets Simulation.global_domains)."""
+    port = _free_port()
+    mp.spawn(_worker_domains, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    d0, d1 = (np.load(tmp_path / f"dom_{r}.npy") for r in range(2))
+    assert d0[4] == 1 and d1[4] == 0          # rank 0 owns the water, rank 1 none
+    assert list(d1[:2]) == [1, 0]             # what rank 1 sees from its own database alone
+    assert list(d0[2:4]) == [1, 1] and list(d1[2:4]) == [1, 1]  # after the exchange object is set up: global
+    assert d0[5] == 0.0 and d1[5] == 1.0      # rank 0 received rank 1's zeros, rank 1 received rank 0's values
