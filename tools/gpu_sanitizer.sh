@@ -9,7 +9,7 @@ SEL=${SEL:-"test_elastic_force_kernel_matches_oracle or test_attenuation_force_k
 for tool in ${TOOLS:-memcheck synccheck racecheck}; do
   t0=$(date +%s)
   timeout ${LIMIT:-120} compute-sanitizer --tool $tool --error-exitcode 7 --log-file gpurun_out/${TAG}_${tool}.log \
-      python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "$SEL" > gpurun_out/${TAG}_${tool}_pytest.log 2>&1
+      python -m pytest ${FILE:-tests/test_gpu_parity.py} -m gpu -q -x -k "$SEL" > gpurun_out/${TAG}_${tool}_pytest.log 2>&1
   echo "$tool rc=$? wall=$(( $(date +%s) - t0 )) s: $(grep -E 'passed|failed|error' gpurun_out/${TAG}_${tool}_pytest.log | tail -1)"
   grep -E "ERROR SUMMARY|RACECHECK SUMMARY" gpurun_out/${TAG}_${tool}.log | tail -2
   grep -E "Invalid|hazard|Barrier error|divergent" gpurun_out/${TAG}_${tool}.log | sort | uniq -c | sort -rn | head -5
