@@ -518,3 +518,27 @@ def test_reference_unit_test_partitioning():
     assert np.bincount(part).tolist() == [3, 3, 3, 3]
     assert all(len(set(np.flatnonzero(part == p).tolist()) ^ set(range(np.flatnonzero(part == p).min(), np.flatnonzero(part == p).min() + 3))) == 0
                for p in range(4))
+
+
+def test_scotch_partition_of_an_unstructured_reference_mesh_reproduces_its_solver_log():
+    """Third KNOWN ANSWER, on an UNSTRUCTURED mesh: EXAMPLES/applications/layered_halfspace/MESH-default (70,200 HEX8 elements
+    with a tripling layer: up to 16 elements meet at a node, up to 54 dual-graph neighbours per element) was run on 16 SCOTCH
+    partitions, and its log reports NSPEC_global_min / max = 4169 / 4606 (REF_SEIS/output_solver.txt:36-37).  The vendored SCOTCH
+    on the dual graph of that mesh file gives exactly that.  (The log's NGLOB lines belong to a build with another NGLL: 129
+    points per element.)  Reads the mesh from /root/reference (1 MB of text; no fixture): skipped where the tree is absent."""
+    import os
+
+    from specfem3d_b200.decompose import ELASTIC_LOAD, check_valence, dual_graph_of_elements, read_mesh_files
+
+    scotch_ref = _scotch()
+    mesh_dir = "/root/reference/EXAMPLES/applications/layered_halfspace/MESH-default"
+    if not os.path.isdir(mesh_dir):
+        pytest.skip("needs the reference tree (the mesh file is read in place)")
+    m = read_mesh_files(mesh_dir)
+    elmnts, nnodes = m["elmnts"], len(m["nodes_coords"])
+    assert len(elmnts) == 70200 and check_valence(elmnts, nnodes)[0] == 16
+    xadj, adjncy, max_neighbor = dual_graph_of_elements(elmnts, nnodes, 1)
+    assert max_neighbor == 54
+    part = scotch_ref.partition_scotch(xadj, adjncy, np.full(len(elmnts), ELASTIC_LOAD, np.int32), 16)
+    nspec = np.bincount(part, minlength=16)
+    assert (int(nspec.min()), int(nspec.max())) == (4169, 4606)
