@@ -520,25 +520,38 @@ def test_reference_unit_test_partitioning():
                for p in range(4))
 
 
-def test_scotch_partition_of_an_unstructured_reference_mesh_reproduces_its_solver_log():
-    """Third KNOWN ANSWER, on an UNSTRUCTURED mesh: EXAMPLES/applications/layered_halfspace/MESH-default (70,200 HEX8 elements
-    with a tripling layer: up to 16 elements meet at a node, up to 54 dual-graph neighbours per element) was run on 16 SCOTCH
-    partitions, and its log reports NSPEC_global_min / max = 4169 / 4606 (REF_SEIS/output_solver.txt:36-37).  The vendored SCOTCH
-    on the dual graph of that mesh file gives exactly that.  (The log's NGLOB lines belong to a build with another NGLL: 129
-    points per element.)  Reads the mesh from /root/reference (1 MB of text; no fixture): skipped where the tree is absent."""
+@pytest.mark.parametrize("example,nparts,load,nspec_minmax,nglob_minmax,valence,max_neighbor", [
+    # 70,200 elements with a tripling layer, 16 parts (output_solver.txt:36-37; its NGLOB lines belong to a build with another
+    # NGLL: 129 points per element)
+    ("layered_halfspace", 16, 41, (4169, 4606), None, 16, 54),
+    # topography of Mount St. Helens, 32,085 elements, 4 parts (output_solver.txt:54-60)
+    ("Mount_StHelens", 4, 41, (7914, 8325), (526877, 553665), 8, None),
+    # a Gmsh box, 320 viscoelastic elements (ATTENUATION: load 59), 4 parts (output_solver.txt:45-51)
+    ("Gmsh_simple_lddrk", 4, 59, (80, 80), (6137, 6137), 8, None),
+])
+def test_scotch_partitions_of_reference_meshes_reproduce_their_solver_logs(example, nparts, load, nspec_minmax, nglob_minmax,
+                                                                           valence, max_neighbor):
+    """More KNOWN ANSWERS, on meshes the harness cannot generate (a tripling layer with up to 16 elements per node and 54
+    dual-graph neighbours, real topography, a Gmsh export): EXAMPLES/applications/<example>/MESH-default partitioned by the
+    vendored SCOTCH on the dual graph of decompose.py reproduces the NSPEC_global_min / max (and NGLOB_global_min / max) of
+    the example's REF_SEIS/output_solver.txt.  The mesh files are read in place (up to 1 MB of text each; no fixtures): skipped
+    where /root/reference is absent."""
     import os
 
-    from specfem3d_b200.decompose import ELASTIC_LOAD, check_valence, dual_graph_of_elements, read_mesh_files
+    from specfem3d_b200.decompose import check_valence, dual_graph_of_elements, read_mesh_files
 
     scotch_ref = _scotch()
-    mesh_dir = "/root/reference/EXAMPLES/applications/layered_halfspace/MESH-default"
+    mesh_dir = f"/root/reference/EXAMPLES/applications/{example}/MESH-default"
     if not os.path.isdir(mesh_dir):
         pytest.skip("needs the reference tree (the mesh file is read in place)")
     m = read_mesh_files(mesh_dir)
     elmnts, nnodes = m["elmnts"], len(m["nodes_coords"])
-    assert len(elmnts) == 70200 and check_valence(elmnts, nnodes)[0] == 16
-    xadj, adjncy, max_neighbor = dual_graph_of_elements(elmnts, nnodes, 1)
-    assert max_neighbor == 54
-    part = scotch_ref.partition_scotch(xadj, adjncy, np.full(len(elmnts), ELASTIC_LOAD, np.int32), 16)
-    nspec = np.bincount(part, minlength=16)
-    assert (int(nspec.min()), int(nspec.max())) == (4169, 4606)
+    assert check_valence(elmnts, nnodes)[0] == valence
+    xadj, adjncy, mx = dual_graph_of_elements(elmnts, nnodes, 1)
+    assert max_neighbor is None or mx == max_neighbor
+    part = scotch_ref.partition_scotch(xadj, adjncy, np.full(len(elmnts), load, np.int32), nparts)
+    nspec = np.bincount(part, minlength=nparts)
+    assert (int(nspec.min()), int(nspec.max())) == nspec_minmax
+    if nglob_minmax is not None:
+        nglob = points_per_part(elmnts, part, nparts)
+        assert (min(nglob), max(nglob)) == nglob_minmax
