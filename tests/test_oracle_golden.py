@@ -176,7 +176,17 @@ def test_waterlayered_halfspace_against_REF_SEIS():
     sim = waterlayered_halfspace(nstep)
     assert sim.dbs[0].nspec_acoustic == 2025 and sim.dbs[0].nspec_elastic == 38475  # output_solver.txt
     assert abs(sim.time_axis()[0] - gold["time"][0]) < 1e-6  # start time -6 s = 3 x half duration (source in the fluid)
-    run = OracleRun(sim).run()
+    run = OracleRun(sim)
+    # the log's stability lines (`Max norm displacement vector U`, `Max norm pressure P` = max |potential_dot_dot|); in that run
+    # check_stability precedes the step (iterate_time.F90:221-224): line `Time step # it` describes the state after it - 1 steps
+    ref_norm = {int(s): (float(d), float(p)) for s, d, p in zip(gold["maxnorm_step"], gold["maxnorm_displ"], gold["maxnorm_pressure"])}
+    for it in range(1, nstep + 1):
+        if it in ref_norm:
+            nd = run.max_norm_displ()
+            npr = max(float(np.abs(p.pot_dot_dot).max()) for p in run.parts if p.db.nspec_acoustic)
+            assert abs(nd - ref_norm[it][0]) <= 1e-4 * ref_norm[it][0], (it, nd, ref_norm[it][0])   # measured 2e-6
+            assert abs(npr - ref_norm[it][1]) <= 1e-4 * ref_norm[it][1], (it, npr, ref_norm[it][1])  # measured 1e-7
+        run.step()
     names = [s.name for s in sim.receivers.stations]
     early = ("v_X55", "v_X2", "v_X4", "v_X5", "v_X6", "v_X7", "v_X8")
     keys = [k for k in gold.files if k[:2] in ("d_", "v_")] if WATER_FULL else early
