@@ -1,0 +1,85 @@
+"""The two callers of the C ABI -- the Python time loop (specfem3d_b200/time_loop.py, the one the oracle tests pin on the GPU) and the
+native host loop (csrc/host_loop.cu) -- must issue the SAME entry points for the same ranks in the same order.  Checked without a
+GPU: both drive a MOCK library that exports all 124 entry points of the contract (generated from abi_symbols.json; every call is
+recorded as (name, handle, iphase)) together with the compiled host loop.  tests/test_gpu_parity.py::
+test_native_host_loop_equals_python_loop compares the numbers on the device; this compares the call sequences."""
+import ctypes
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def mock_lib(tmp_path_factory):
+    from specfem3d_b200 import abi
+
+    d = tmp_path_factory.mktemp("mock_abi")
+    table = json.load(open(os.path.join(ROOT, "specfem3d_b200", "abi_symbols.json")))
+    src = ['#include "specfem3d_b200.h"', "#include <cstdio>", "static char g_log[1 << 22]; static size_t g_n = 0; static long g_handles = 0;",
+           'static void rec(const char* name, long* h, int iphase) { if (g_n + 128 < sizeof(g_log)) g_n += snprintf(g_log + g_n, 128, "%s:%ld:%d\\n", name, h ? *h : -1L, iphase); }',
+           'extern "C" const char* mock_log() { return g_log; }', 'extern "C" void mock_reset(int handles_too) { g_n = 0; g_log[0] = 0; if (handles_too) g_handles = 0; }']
+    for name, entry in table.items():
+        args = entry["args"]
+        names = [a.replace("*", " ").replace("[]", " ").split()[-1] for a in args]
+        handle = next((n for n in names if n.startswith("Mesh_pointer")), None)
+        iphase = next(("*" + n for n in names if n.lower().startswith("iphase")), "0")
+        body = ""
+        if name == "prepare_constants_device":
+            body += f"*{handle} = ++g_handles; "
+        body += f'rec("{name}", {handle or "nullptr"}, {iphase});'
+        if name.startswith("get_norm"):
+            body += " *norm = 1.0f;"
+        if name == "initialize_gpu_device":
+            body += " *ncuda_devices = 1;"
+        src.append(f'extern "C" void {name}_({", ".join(args) if args else "void"}) {{ {body} }}')
+    (d / "mock.cpp").write_text("\n".join(src) + "\n")
+    so = d / "libmock_abi.so"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-w", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"), "-x", "c++",
+                    os.path.join(ROOT, "specfem3d_b200", "csrc", "host_loop.cu"), str(d / "mock.cpp"), "-o", str(so)], check=True)
+    lib = abi.DeviceLibrary(str(so))
+    lib.cdll.mock_log.restype = ctypes.c_char_p
+    return lib
+
+
+def _calls(lib):
+    return [tuple(x.split(":")) for x in lib.cdll.mock_log().decode().split()]
+
+
+def _cases():
+    import test_gpu_parity as g  # the builders of the GPU tests (importing the module needs no GPU)
+
+    return {"elastic": lambda: g.small_sim(nstep=6, nex=(4, 4, 2)),
+            "elastic_2x2": lambda: g.small_sim(nproc=(2, 2), nstep=6, nex=(4, 4, 2)),
+            "viscoelastic": lambda: g.visco_sim(nstep=6),
+            "coupled_2x1": lambda: g.ocean_sim(nproc=(2, 1), nstep=6),
+            "cpml": lambda: g.pml_sim(nstep=6),
+            "ocean_load": lambda: g.ocean_load_sim(nstep=6)}
+
+
+@pytest.mark.parametrize("case", ["elastic", "elastic_2x2", "viscoelastic", "coupled_2x1", "cpml", "ocean_load"])
+def test_python_and_native_host_loops_issue_the_same_calls(mock_lib, case):
+    from specfem3d_b200.time_loop import DeviceRun
+
+    logs = {}
+    for native in (False, True):
+        sim = _cases()[case]()
+        mock_lib.cdll.mock_reset(1)
+        run = DeviceRun(sim, lib=mock_lib)
+        prepared = _calls(mock_lib)
+        assert prepared[0][0] == "initialize_gpu_device" and any(c[0] == "prepare_constants_device" for c in prepared)
+        mock_lib.cdll.mock_reset(0)
+        if native:
+            run.run_native(4)
+            run.run_native(2)  # resumes where it stopped
+        else:
+            run.run(6)
+        logs[native] = _calls(mock_lib)
+        run.cleanup()
+    a, b = logs[False], logs[True]
+    assert len(a) > 6 * 4 and any(c[0].startswith("compute_forces") for c in a)
+    assert a == b, next((i, x, y) for i, (x, y) in enumerate(zip(a, b)) if x != y)
