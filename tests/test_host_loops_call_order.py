@@ -1,7 +1,7 @@
 """The two callers of the C ABI -- the Python time loop (specfem3d_b200/time_loop.py, the one the oracle tests pin on the GPU) and the
 native host loop (csrc/host_loop.cu) -- must issue the SAME entry points for the same ranks in the same order.  Checked without a
 GPU: both drive a MOCK library that exports all 124 entry points of the contract (generated from abi_symbols.json; every call is
-recorded as (name, handle, iphase)) together with the compiled host loop.  tests/test_gpu_parity.py::
+recorded as (name, handle, iphase, weighted sum of the first elements of its scalar-typed arguments)) together with the compiled host loop.  tests/test_gpu_parity.py::
 test_native_host_loop_equals_python_loop compares the numbers on the device; this compares the call sequences."""
 import ctypes
 import json
@@ -21,7 +21,7 @@ def mock_lib(tmp_path_factory):
     d = tmp_path_factory.mktemp("mock_abi")
     table = json.load(open(os.path.join(ROOT, "specfem3d_b200", "abi_symbols.json")))
     src = ['#include "specfem3d_b200.h"', "#include <cstdio>", "static char g_log[1 << 22]; static size_t g_n = 0; static long g_handles = 0;",
-           'static void rec(const char* name, long* h, int iphase) { if (g_n + 128 < sizeof(g_log)) g_n += snprintf(g_log + g_n, 128, "%s:%ld:%d\\n", name, h ? *h : -1L, iphase); }',
+           'static void rec(const char* name, long* h, int iphase, double args) { if (g_n + 160 < sizeof(g_log)) g_n += snprintf(g_log + g_n, 160, "%s:%ld:%d:%.9e\\n", name, h ? *h : -1L, iphase, args); }',
            'extern "C" const char* mock_log() { return g_log; }', 'extern "C" void mock_reset(int handles_too) { g_n = 0; g_log[0] = 0; if (handles_too) g_handles = 0; }']
     for name, entry in table.items():
         args = entry["args"]
@@ -31,7 +31,16 @@ def mock_lib(tmp_path_factory):
         body = ""
         if name == "prepare_constants_device":
             body += f"*{handle} = ++g_handles; "
-        body += f'rec("{name}", {handle or "nullptr"}, {iphase});'
+        # scalar arguments arrive by reference: the first element of every int / realw / double pointer goes into the record too
+        # (time-step constants, element counts, FORWARD_OR_ADJOINT, the source time function value of the step, ...); in the
+        # time loop every such pointer refers to at least one element
+        first = []
+        if name not in ("initialize_gpu_device", "prepare_constants_device") and not name.startswith(("prepare_", "transfer_", "get_")):
+            for a, n in zip(args, names):
+                t = a.replace("const", " ").replace("*", " ").split()[0]
+                if "*" in a and t in ("int", "realw", "double", "field") and not n.startswith("Mesh_pointer"):
+                    first.append(f"({n} ? (double)*{n} : -12345.0)")
+        body += f'rec("{name}", {handle or "nullptr"}, {iphase}, {" + ".join(f"{k + 1}.0 * {e}" for k, e in enumerate(first)) or "0.0"});'
         if name.startswith("get_norm"):
             body += " *norm = 1.0f;"
         if name == "initialize_gpu_device":
