@@ -34,12 +34,17 @@ typedef struct {
   const int* my_neighbors_ext_mesh;      /* (num_interfaces) neighbour rank of every interface */
   realw *buffer_send_vector, *buffer_recv_vector; /* (NDIM, max_nibool, num_interfaces) */
   realw *buffer_send_scalar, *buffer_recv_scalar; /* (max_nibool, num_interfaces) */
-  /* Stacey record buffers (one record; this loop keeps no history: forward runs without SAVE_FORWARD) */
+  /* Stacey record buffers: one record each, (NDIM, NGLLSQUARE, num_abs_boundary_faces) / (NGLLSQUARE, num_abs_boundary_faces) */
   realw *b_absorb_field, *b_absorb_potential;
   /* seismograms (NDIM, nrec_local, nlength_seismogram) and the running sample counter of the rank */
   int nrec_local;
   realw *seismograms_d, *seismograms_v, *seismograms_a, *seismograms_p;
   int seismo_current;
+  /* SAVE_FORWARD (run->SAVE_FORWARD != 0): what the Fortran solver writes to proc*_absorb_field.bin / proc*_absorb_potential.bin
+     with write_abs(.., it) (compute_stacey_viscoelastic.F90:190-200, compute_stacey_acoustic.f90): record it - 1 of these
+     caller-owned arrays, NSTEP records of 3 * 25 * num_abs_boundary_faces / 25 * num_abs_boundary_faces floats; NULL = not kept */
+  int num_abs_boundary_faces;
+  realw *absorb_field_history, *absorb_potential_history;
 } specfem_b200_host_rank;
 
 typedef struct {
@@ -63,6 +68,8 @@ typedef struct {
      NTSTEP_BETWEEN_OUTPUT_SEISMOS); n > 0: additionally after every n-th step of the call (compute_seismograms_cuda is told
      that the step is the last one, so it hands back -- blocking -- everything recorded so far): real-time monitoring */
   int seismo_flush_every;
+  /* SIMULATION_TYPE 1 with SAVE_FORWARD: the absorbed Stacey tractions / fluxes of every step are kept (rank: *_history) */
+  int SAVE_FORWARD;
   /* halo transport between the ranks of THIS process: 1 = copy send -> receive buffers on the host (what MPI does between
      processes), 0 = none (single rank, or the library moves the halo itself after specfem_b200_halo_p2p_connect) */
   int host_exchange;
@@ -73,7 +80,7 @@ typedef struct {
   realw* norms;
 } specfem_b200_host_run;
 
-/* Time steps it_begin .. it_end (1-based, inclusive) of a forward run (SIMULATION_TYPE 1, no SAVE_FORWARD).
+/* Time steps it_begin .. it_end (1-based, inclusive) of a forward run (SIMULATION_TYPE 1, with or without SAVE_FORWARD).
    Replaces the loop body of iterate_time.F90:219-330 in GPU_MODE. */
 void SB200_FC(specfem_b200_iterate_time)(specfem_b200_host_run* run, int* it_begin, int* it_end);
 

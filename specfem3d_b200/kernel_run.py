@@ -34,10 +34,15 @@ class ForwardProducts:
     absorb_potential: List[List[np.ndarray]] = field(default_factory=list)
 
 
-def run_forward_and_save(sim, lib=None, halo: str = "host"):
-    """SIMULATION_TYPE = 1 with SAVE_FORWARD = .true.: returns (the finished DeviceRun, ForwardProducts)."""
+def run_forward_and_save(sim, lib=None, halo: str = "host", native: bool = False):
+    """SIMULATION_TYPE = 1 with SAVE_FORWARD = .true.: returns (the finished DeviceRun, ForwardProducts).  ``native``: through the
+    native host loop (same calls, same records: tests/test_host_loops_call_order.py)."""
     assert sim.SIMULATION_TYPE == 1 and sim.SAVE_FORWARD
-    run = DeviceRun(sim, lib=lib, halo=halo).run()
+    run = DeviceRun(sim, lib=lib, halo=halo)
+    if native:  # iterate_time in C++ (csrc/host_loop.cu keeps the Stacey records like write_abs does)
+        run.run_native()
+    else:
+        run.run()
     prod = ForwardProducts()
     for r in run.ranks:
         prod.absorb.append(list(r.absorb_history))

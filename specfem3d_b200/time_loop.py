@@ -257,7 +257,8 @@ class _HostRank(ctypes.Structure):
                 ("buffer_send_vector", _PF), ("buffer_recv_vector", _PF), ("buffer_send_scalar", _PF), ("buffer_recv_scalar", _PF),
                 ("b_absorb_field", _PF), ("b_absorb_potential", _PF), ("nrec_local", ctypes.c_int),
                 ("seismograms_d", _PF), ("seismograms_v", _PF), ("seismograms_a", _PF), ("seismograms_p", _PF),
-                ("seismo_current", ctypes.c_int)]
+                ("seismo_current", ctypes.c_int), ("num_abs_boundary_faces", ctypes.c_int),
+                ("absorb_field_history", _PF), ("absorb_potential_history", _PF)]
 
 
 class _HostRun(ctypes.Structure):
@@ -268,7 +269,8 @@ class _HostRun(ctypes.Structure):
                 ("PML_CONDITIONS", ctypes.c_int), ("APPROXIMATE_OCEAN_LOAD", ctypes.c_int),
                 ("NSOURCES", ctypes.c_int), ("stf_elastic", _PD), ("stf_acoustic", _PD),
                 ("has_receivers", ctypes.c_int), ("NTSTEP_BETWEEN_OUTPUT_SAMPLE", ctypes.c_int), ("nlength_seismogram", ctypes.c_int),
-                ("USE_TRICK_FOR_BETTER_PRESSURE", ctypes.c_int), ("seismo_flush_every", ctypes.c_int), ("host_exchange", ctypes.c_int), ("norm_every", ctypes.c_int), ("norms", _PF)]
+                ("USE_TRICK_FOR_BETTER_PRESSURE", ctypes.c_int), ("seismo_flush_every", ctypes.c_int), ("SAVE_FORWARD", ctypes.c_int),
+                ("host_exchange", ctypes.c_int), ("norm_every", ctypes.c_int), ("norms", _PF)]
 
 
 def _pf(a):
@@ -451,8 +453,8 @@ class DeviceRun:
         time steps without the interpreter in between.  Forward runs only (no SAVE_FORWARD record history, no kernel runs).
         Returns the stability norms recorded every ``norm_every`` steps."""
         sim = self.sim
-        if sim.SIMULATION_TYPE != 1 or sim.SAVE_FORWARD or sim.UNDO_ATTENUATION_AND_OR_PML:
-            raise NotImplementedError("native host loop: forward runs without SAVE_FORWARD only (use step() / kernel_run.py)")
+        if sim.SIMULATION_TYPE != 1 or sim.UNDO_ATTENUATION_AND_OR_PML:
+            raise NotImplementedError("native host loop: forward runs only (kernel runs: kernel_run.py, undo_att.py)")
         if isinstance(self.exchange, InProcessExchange):
             host_exchange = 1 if self.NPROC > 1 else 0
         elif self.exchange is None or type(self.exchange).__name__ == "NoExchange" or getattr(self.exchange, "mode", None) == "p2p":
@@ -485,6 +487,11 @@ class DeviceRun:
                 h.buffer_send_scalar, h.buffer_recv_scalar = _pf(r.buffer_send_scalar), _pf(r.buffer_recv_scalar)
                 h.b_absorb_field, h.b_absorb_potential = _pf(r.b_absorb_field), _pf(r.b_absorb_potential)
                 h.nrec_local = r.nrec_local
+                h.num_abs_boundary_faces = db.num_abs_boundary_faces
+                if sim.SAVE_FORWARD:  # the records proc*_absorb_field.bin / proc*_absorb_potential.bin would hold, one per step
+                    nf = max(db.num_abs_boundary_faces, 1)
+                    keep[k] += [np.zeros((sim.NSTEP, nf, 25, 3), np.float32), np.zeros((sim.NSTEP, nf, 25), np.float32)]
+                    h.absorb_field_history, h.absorb_potential_history = _pf(keep[k][3]), _pf(keep[k][4])
                 h.seismograms_d, h.seismograms_v = _pf(r.seismograms_d), _pf(r.seismograms_v)
                 h.seismograms_a, h.seismograms_p = _pf(r.seismograms_a), _pf(r.seismograms_p)
             run = _HostRun()
@@ -500,6 +507,7 @@ class DeviceRun:
             run.stf_elastic, run.stf_acoustic = keep["stf_el"].ctypes.data_as(_PD), keep["stf_ac"].ctypes.data_as(_PD)
             run.has_receivers = int(sim.receivers is not None)
             run.USE_TRICK_FOR_BETTER_PRESSURE = int(sim.USE_TRICK_FOR_BETTER_PRESSURE)
+            run.SAVE_FORWARD = int(sim.SAVE_FORWARD)
             run.NTSTEP_BETWEEN_OUTPUT_SAMPLE, run.nlength_seismogram = sim.NTSTEP_BETWEEN_OUTPUT_SAMPLE, sim.nlength_seismogram
             self._native = (run, arr, keep)
         run, arr, keep = self._native
@@ -512,9 +520,14 @@ class DeviceRun:
         fn = self.ranks[0].lib.cdll.specfem_b200_iterate_time_
         fn.restype = None
         fn(ctypes.byref(run), ctypes.byref(ctypes.c_int(self.it + 1)), ctypes.byref(ctypes.c_int(self.it + n)))
-        self.it += n
         for k, r in enumerate(self.ranks):
             r.seismo_current = arr[k].seismo_current
+            if sim.SAVE_FORWARD and sim.spec.stacey:  # same bookkeeping as step(): one record per step and domain of the rank
+                if r.ELASTIC:
+                    r.absorb_history += [keep[k][3][it].copy() for it in range(self.it, self.it + n)]
+                if r.ACOUSTIC:
+                    r.absorb_potential_history += [keep[k][4][it].copy() for it in range(self.it, self.it + n)]
+        self.it += n
         return norms if norm_every > 0 else np.zeros(0, np.float32)
 
     def max_norm_displ(self) -> float:

@@ -20,9 +20,9 @@ def mock_lib(tmp_path_factory):
 
     d = tmp_path_factory.mktemp("mock_abi")
     table = json.load(open(os.path.join(ROOT, "specfem3d_b200", "abi_symbols.json")))
-    src = ['#include "specfem3d_b200.h"', "#include <cstdio>", "static char g_log[1 << 22]; static size_t g_n = 0; static long g_handles = 0;",
+    src = ['#include "specfem3d_b200.h"', "#include <cstdio>", "static char g_log[1 << 22]; static size_t g_n = 0; static long g_handles = 0; static long g_records = 0;",
            'static void rec(const char* name, long* h, int iphase, double args) { if (g_n + 160 < sizeof(g_log)) g_n += snprintf(g_log + g_n, 160, "%s:%ld:%d:%.9e\\n", name, h ? *h : -1L, iphase, args); }',
-           'extern "C" const char* mock_log() { return g_log; }', 'extern "C" void mock_reset(int handles_too) { g_n = 0; g_log[0] = 0; if (handles_too) g_handles = 0; }']
+           'extern "C" const char* mock_log() { return g_log; }', 'extern "C" void mock_reset(int handles_too) { g_n = 0; g_log[0] = 0; if (handles_too) g_handles = 0; g_records = 0; }']
     for name, entry in table.items():
         args = entry["args"]
         names = [a.replace("*", " ").replace("[]", " ").split()[-1] for a in args]
@@ -43,6 +43,9 @@ def mock_lib(tmp_path_factory):
         body += f'rec("{name}", {handle or "nullptr"}, {iphase}, {" + ".join(f"{k + 1}.0 * {e}" for k, e in enumerate(first)) or "0.0"});'
         if name.startswith("get_norm"):
             body += " *norm = 1.0f;"
+        if name in ("compute_stacey_viscoelastic_cuda", "compute_stacey_acoustic_cuda"):  # the record the device would hand back
+            rec_arg = next(n for n in names if "b_absorb" in n)
+            body += f" {rec_arg}[0] = (float)(++g_records) + 0.25f * (float)*{handle};"
         if name == "initialize_gpu_device":
             body += " *ncuda_devices = 1;"
         src.append(f'extern "C" void {name}_({", ".join(args) if args else "void"}) {{ {body} }}')
@@ -92,3 +95,36 @@ def test_python_and_native_host_loops_issue_the_same_calls(mock_lib, case):
     a, b = logs[False], logs[True]
     assert len(a) > 6 * 4 and any(c[0].startswith("compute_forces") for c in a)
     assert a == b, next((i, x, y) for i, (x, y) in enumerate(zip(a, b)) if x != y)
+
+
+@pytest.mark.parametrize("case", ["elastic_2x2", "coupled_2x1"])
+def test_save_forward_records_are_kept_alike(mock_lib, case):
+    """SIMULATION_TYPE 1 with SAVE_FORWARD: both loops keep the Stacey record every compute_stacey_* call hands back
+    (write_abs(IOABS, b_absorb_field, b_reclen_field, it)) -- the mock numbers the records, so equal histories mean: same calls in
+    the same order, each record stored under its own step."""
+    from specfem3d_b200.time_loop import DeviceRun
+
+    hist = {}
+    for native in (False, True):
+        sim = _cases()[case]()
+        sim.SAVE_FORWARD = True
+        mock_lib.cdll.mock_reset(1)
+        run = DeviceRun(sim, lib=mock_lib)
+        mock_lib.cdll.mock_reset(0)
+        if native:
+            run.run_native(4)
+            run.run_native(2)
+        else:
+            run.run(6)
+        hist[native] = ([np.array(r.absorb_history) for r in run.ranks], [np.array(r.absorb_potential_history) for r in run.ranks],
+                        _calls(mock_lib))
+        run.cleanup()
+    a, b = hist[False], hist[True]
+    assert a[2] == b[2]
+    n_records = 0
+    for x, y in zip(a[0] + a[1], b[0] + b[1]):
+        assert x.shape == y.shape and np.array_equal(x, y)
+        n_records += len(x)
+        if len(x):
+            assert len(x) == 6 and len(np.unique(x.reshape(6, -1)[:, 0])) == 6  # six steps, six different records
+    assert n_records >= 6 * len(a[0])
