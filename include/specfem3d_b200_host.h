@@ -45,6 +45,14 @@ typedef struct {
      caller-owned arrays, NSTEP records of 3 * 25 * num_abs_boundary_faces / 25 * num_abs_boundary_faces floats; NULL = not kept */
   int num_abs_boundary_faces;
   realw *absorb_field_history, *absorb_potential_history;
+  /* kernel runs (SIMULATION_TYPE 3, specfem_b200_iterate_time_kernel_run): the *_history arrays above are READ (read_abs at
+     record NSTEP - it); buffers of the reconstructed wavefield's halo; the adjoint sources of the rank's receivers
+     source_adjoint(NDIM, nadj_rec_local, NSTEP) in forward time order; the last frame of the forward run
+     (proc*_save_forward_arrays.bin, read_forward_arrays: it replaces the b_ fields after the first step) */
+  int NGLOB_AB;
+  realw *b_buffer_send_vector, *b_buffer_recv_vector, *b_buffer_send_scalar, *b_buffer_recv_scalar;
+  realw* source_adjoint;
+  realw *last_displ, *last_veloc, *last_accel, *last_potential, *last_potential_dot, *last_potential_dot_dot;
 } specfem_b200_host_rank;
 
 typedef struct {
@@ -70,6 +78,10 @@ typedef struct {
   int seismo_flush_every;
   /* SIMULATION_TYPE 1 with SAVE_FORWARD: the absorbed Stacey tractions / fluxes of every step are kept (rank: *_history) */
   int SAVE_FORWARD;
+  /* kernel runs: b_deltat = -deltat and its halves (prepare_timerun.F90:425-430), number of receivers of the whole run, and
+     APPROXIMATE_HESS_KL */
+  realw b_deltat, b_deltatover2, b_deltatsqover2;
+  int nrec, APPROXIMATE_HESS_KL;
   /* halo transport between the ranks of THIS process: 1 = copy send -> receive buffers on the host (what MPI does between
      processes), 0 = none (single rank, or the library moves the halo itself after specfem_b200_halo_p2p_connect) */
   int host_exchange;
@@ -83,6 +95,13 @@ typedef struct {
 /* Time steps it_begin .. it_end (1-based, inclusive) of a forward run (SIMULATION_TYPE 1, with or without SAVE_FORWARD).
    Replaces the loop body of iterate_time.F90:219-330 in GPU_MODE. */
 void SB200_FC(specfem_b200_iterate_time)(specfem_b200_host_run* run, int* it_begin, int* it_end);
+
+/* The same for a kernel run (SIMULATION_TYPE 3; elastic, acoustic or coupled domains, no attenuation / C-PML): adjoint wavefield
+   in the forward arrays driven by the adjoint sources, forward wavefield reconstructed backwards in time in the b_ arrays from
+   the last frame and the Stacey records, kernels accumulated every step.  Replaces iterate_time.F90:233-300 with
+   compute_forces_viscoelastic_GPU_calling / compute_forces_acoustic_GPU_calling (FORWARD_OR_ADJOINT 0) or, in coupled runs, the
+   separate forward / backward routines (compute_forces_viscoelastic_calling_routine.F90:61-67). */
+void SB200_FC(specfem_b200_iterate_time_kernel_run)(specfem_b200_host_run* run, int* it_begin, int* it_end);
 
 #ifdef __cplusplus
 }

@@ -168,7 +168,224 @@ void elastic_step(Run* run, int it) {
   }
 }
 
+// ---- kernel runs (SIMULATION_TYPE 3): specfem3d_b200/kernel_run.py is the same loop in Python -------------------------------
+// the halo of the reconstructed wavefield between the ranks of this process (b_buffer_*)
+void exchange_on_host_b(Run* run, int ncomp) {
+  for (int ir = 0; ir < run->nranks; ++ir) {
+    Rank& r = run->ranks[ir];
+    const size_t mx = (size_t)r.max_nibool_interfaces_ext_mesh;
+    for (int n = 0; n < r.num_interfaces_ext_mesh; ++n) {
+      Rank* nb = rank_by_id(run, r.my_neighbors_ext_mesh[n]);
+      if (!nb) host_error("host_exchange: a neighbour rank is not driven by this process");
+      int m = -1;
+      for (int q = 0; q < nb->num_interfaces_ext_mesh; ++q)
+        if (nb->my_neighbors_ext_mesh[q] == r.myrank) m = q;
+      if (m < 0) host_error("host_exchange: the neighbour has no interface pointing back");
+      const size_t cnt = (size_t)r.nibool_interfaces_ext_mesh[n], nbmx = (size_t)nb->max_nibool_interfaces_ext_mesh;
+      if (ncomp == 3)
+        memcpy(nb->b_buffer_recv_vector + 3 * nbmx * m, r.b_buffer_send_vector + 3 * mx * n, 3 * cnt * sizeof(realw));
+      else
+        memcpy(nb->b_buffer_recv_scalar + nbmx * m, r.b_buffer_send_scalar + mx * n, cnt * sizeof(realw));
+    }
+  }
+}
+
+// foa = 0: compute_forces_viscoelastic_GPU_calling (both wavefields); 1 / 3: the separate routines of a coupled run
+void elastic_step_kl(Run* run, int it, int foa) {
+  const bool multi = run->NPROC > 1, fwd = foa != 3, bwd = foa != 1;
+  int one = 1, three = 3, zero = 0, strain = 1, att = 0, NSTEP = run->NSTEP;
+  realw dt_forces = foa == 3 ? run->b_deltat : run->deltat;
+  for (int iphase = 1; iphase <= 2; ++iphase) {
+    for (int ir = 0; ir < run->nranks; ++ir) {
+      Rank& r = run->ranks[ir];
+      if (r.elastic)
+        compute_forces_viscoelastic_cuda_(r.Mesh_pointer, &iphase, &dt_forces, &r.nspec_outer_elastic, &r.nspec_inner_elastic, &strain, &att, &foa);
+    }
+    if (multi && iphase == 2 && fwd) {
+      for (int ir = 0; ir < run->nranks; ++ir) {
+        Rank& r = run->ranks[ir];
+        if (r.elastic) sync_copy_from_device_(r.Mesh_pointer, &iphase, r.buffer_send_vector);
+      }
+      if (run->host_exchange) exchange_on_host(run, 3);
+      for (int ir = 0; ir < run->nranks; ++ir) {
+        Rank& r = run->ranks[ir];
+        if (r.elastic)
+          transfer_boundary_to_device_a_(r.Mesh_pointer, r.buffer_recv_vector, &r.num_interfaces_ext_mesh, &r.max_nibool_interfaces_ext_mesh);
+      }
+    }
+    if (iphase == 1) {
+      for (int ir = 0; ir < run->nranks; ++ir) {
+        Rank& r = run->ranks[ir];
+        if (!r.elastic) continue;
+        if (run->STACEY_ABSORBING_CONDITIONS) {
+          if (bwd && r.num_abs_boundary_faces > 0) {  // read_abs(IOABS, b_absorb_field, b_reclen_field, NSTEP - it + 1)
+            const size_t rec = (size_t)3 * 25 * r.num_abs_boundary_faces;
+            memcpy(r.b_absorb_field, r.absorb_field_history + rec * (NSTEP - it), rec * sizeof(realw));
+          }
+          compute_stacey_viscoelastic_cuda_(r.Mesh_pointer, &iphase, r.b_absorb_field, &foa);
+        }
+        if (run->ACOUSTIC_SIMULATION && r.num_coupling_ac_el_faces > 0)
+          compute_coupling_el_ac_cuda_(r.Mesh_pointer, &iphase, &r.num_coupling_ac_el_faces, &foa);
+        if (fwd && r.nrec_local > 0 && it < NSTEP) {
+          int itf = it;
+          add_sources_el_sim_type_2_or_3_(r.Mesh_pointer, r.source_adjoint, &run->nrec, &r.nrec_local, &NSTEP, &itf);
+        }
+        if (bwd && run->NSOURCES > 0) {
+          int ns = run->NSOURCES;
+          compute_add_sources_el_s3_cuda_(r.Mesh_pointer, const_cast<double*>(run->stf_elastic + (size_t)(NSTEP - it) * ns), &ns);
+        }
+        if (multi) {
+          if (fwd) transfer_boundary_from_device_a_(r.Mesh_pointer, &r.nspec_outer_elastic);
+          if (bwd) transfer_boun_accel_from_device_(r.Mesh_pointer, r.b_buffer_send_vector, &three);
+        }
+      }
+      if (multi && bwd && run->host_exchange) exchange_on_host_b(run, 3);
+    } else if (multi) {
+      for (int ir = 0; ir < run->nranks; ++ir) {
+        Rank& r = run->ranks[ir];
+        if (!r.elastic) continue;
+        if (fwd)
+          transfer_asmbl_accel_to_device_(r.Mesh_pointer, r.buffer_recv_vector, &r.num_interfaces_ext_mesh, &r.max_nibool_interfaces_ext_mesh,
+                                          r.nibool_interfaces_ext_mesh, r.ibool_interfaces_ext_mesh, &one);
+        if (bwd)
+          transfer_asmbl_accel_to_device_(r.Mesh_pointer, r.b_buffer_recv_vector, &r.num_interfaces_ext_mesh, &r.max_nibool_interfaces_ext_mesh,
+                                          r.nibool_interfaces_ext_mesh, r.ibool_interfaces_ext_mesh, &three);
+      }
+    }
+  }
+  for (int ir = 0; ir < run->nranks; ++ir) {
+    Rank& r = run->ranks[ir];
+    if (!r.elastic) continue;
+    if (fwd) kernel_3_a_cuda_(r.Mesh_pointer, &run->deltatover2, &run->b_deltatover2, &zero, &one);
+    if (bwd) kernel_3_a_cuda_(r.Mesh_pointer, &run->deltatover2, &run->b_deltatover2, &zero, &three);
+  }
+}
+
+void acoustic_step_kl(Run* run, int it, int foa) {
+  const bool multi = run->NPROC > 1, fwd = foa != 3, bwd = foa != 1;
+  int one = 1, three = 3, sifs = run->STACEY_INSTEAD_OF_FREE_SURFACE, NSTEP = run->NSTEP;
+  std::vector<int> run_number(run->NSOURCES > 0 ? run->NSOURCES : 1, 0);
+  for (int ir = 0; ir < run->nranks; ++ir) {
+    Rank& r = run->ranks[ir];
+    if (!r.acoustic) continue;
+    if (fwd) acoustic_enforce_free_surf_cuda_(r.Mesh_pointer, &sifs, &one);
+    if (bwd) acoustic_enforce_free_surf_cuda_(r.Mesh_pointer, &sifs, &three);
+  }
+  for (int iphase = 1; iphase <= 2; ++iphase) {
+    for (int ir = 0; ir < run->nranks; ++ir) {
+      Rank& r = run->ranks[ir];
+      if (!r.acoustic) continue;
+      compute_forces_acoustic_cuda_(r.Mesh_pointer, &iphase, &r.nspec_outer_acoustic, &r.nspec_inner_acoustic, &foa);
+      if (iphase != 1) continue;
+      if (run->STACEY_ABSORBING_CONDITIONS) {
+        if (bwd && r.num_abs_boundary_faces > 0) {
+          const size_t rec = (size_t)25 * r.num_abs_boundary_faces;
+          memcpy(r.b_absorb_potential, r.absorb_potential_history + rec * (NSTEP - it), rec * sizeof(realw));
+        }
+        compute_stacey_acoustic_cuda_(r.Mesh_pointer, &iphase, r.b_absorb_potential, &foa);
+      }
+      if (run->ELASTIC_SIMULATION) {
+        if (fwd) compute_coupling_ac_el_cuda_(r.Mesh_pointer, &iphase, &r.num_coupling_ac_el_faces, &one);
+        if (bwd) compute_coupling_ac_el_cuda_(r.Mesh_pointer, &iphase, &r.num_coupling_ac_el_faces, &three);
+      }
+      if (fwd && r.nrec_local > 0 && it < NSTEP) {
+        int itf = it;
+        add_sources_ac_sim_2_or_3_cuda_(r.Mesh_pointer, r.source_adjoint, &run->nrec, &r.nrec_local, &NSTEP, &itf);
+      }
+      if (bwd && run->NSOURCES > 0) {
+        int ns = run->NSOURCES;
+        compute_add_sources_ac_s3_cuda_(r.Mesh_pointer, &ns, const_cast<double*>(run->stf_acoustic + (size_t)(NSTEP - it) * ns), run_number.data());
+      }
+    }
+    if (!multi) continue;
+    if (iphase == 1) {
+      if (fwd) {
+        for (int ir = 0; ir < run->nranks; ++ir) {
+          Rank& r = run->ranks[ir];
+          if (r.acoustic) transfer_boun_pot_from_device_(r.Mesh_pointer, r.buffer_send_scalar, &one);
+        }
+        if (run->host_exchange) exchange_on_host(run, 1);
+      }
+      if (bwd) {
+        for (int ir = 0; ir < run->nranks; ++ir) {
+          Rank& r = run->ranks[ir];
+          if (r.acoustic) transfer_boun_pot_from_device_(r.Mesh_pointer, r.b_buffer_send_scalar, &three);
+        }
+        if (run->host_exchange) exchange_on_host_b(run, 1);
+      }
+    } else {
+      for (int ir = 0; ir < run->nranks; ++ir) {
+        Rank& r = run->ranks[ir];
+        if (!r.acoustic) continue;
+        if (fwd) transfer_asmbl_pot_to_device_(r.Mesh_pointer, r.buffer_recv_scalar, &one);
+        if (bwd) transfer_asmbl_pot_to_device_(r.Mesh_pointer, r.b_buffer_recv_scalar, &three);
+      }
+    }
+  }
+  for (int ir = 0; ir < run->nranks; ++ir) {
+    Rank& r = run->ranks[ir];
+    if (!r.acoustic) continue;
+    kernel_3_acoustic_cuda_(r.Mesh_pointer, &run->deltatover2, &run->b_deltatover2, &foa);
+    if (fwd) acoustic_enforce_free_surf_cuda_(r.Mesh_pointer, &sifs, &one);
+    if (bwd) acoustic_enforce_free_surf_cuda_(r.Mesh_pointer, &sifs, &three);
+  }
+}
+
 }  // namespace
+
+extern "C" void SB200_FC(specfem_b200_iterate_time_kernel_run)(specfem_b200_host_run* run, int* it_begin, int* it_end) {
+  if (!run || run->nranks <= 0 || !run->ranks) host_error("specfem_b200_iterate_time_kernel_run: no ranks");
+  if (*it_begin < 1 || *it_end > run->NSTEP) host_error("specfem_b200_iterate_time_kernel_run: time steps outside 1 .. NSTEP");
+  if (run->ATTENUATION || run->PML_CONDITIONS) host_error("specfem_b200_iterate_time_kernel_run: no attenuation / C-PML (iterate_time_undoatt)");
+  int one = 1, three = 3, zero = 0;
+  const int every = run->NTSTEP_BETWEEN_OUTPUT_SAMPLE > 0 ? run->NTSTEP_BETWEEN_OUTPUT_SAMPLE : 1;
+  for (int it = *it_begin; it <= *it_end; ++it) {
+    for (int ir = 0; ir < run->nranks; ++ir) {  // update_displ_Newmark
+      Rank& r = run->ranks[ir];
+      if (r.acoustic) update_displacement_ac_cuda_(r.Mesh_pointer, &run->deltat, &run->deltatover2, &run->deltatsqover2, &one);
+      if (r.elastic) update_displacement_cuda_(r.Mesh_pointer, &run->deltat, &run->deltatover2, &run->deltatsqover2, &one);
+    }
+    for (int ir = 0; ir < run->nranks; ++ir) {  // update_displ_Newmark_backward
+      Rank& r = run->ranks[ir];
+      if (r.acoustic) update_displacement_ac_cuda_(r.Mesh_pointer, &run->b_deltat, &run->b_deltatover2, &run->b_deltatsqover2, &three);
+      if (r.elastic) update_displacement_cuda_(r.Mesh_pointer, &run->b_deltat, &run->b_deltatover2, &run->b_deltatsqover2, &three);
+    }
+    if (run->ELASTIC_SIMULATION && run->ACOUSTIC_SIMULATION) {
+      // coupled: adjoint wavefield elastic first, then acoustic; reconstructed wavefield acoustic first, then elastic
+      elastic_step_kl(run, it, 1);
+      acoustic_step_kl(run, it, 1);
+      acoustic_step_kl(run, it, 3);
+      elastic_step_kl(run, it, 3);
+    } else {
+      if (run->ACOUSTIC_SIMULATION) acoustic_step_kl(run, it, 0);
+      if (run->ELASTIC_SIMULATION) elastic_step_kl(run, it, 0);
+    }
+    if (it == 1) {  // read_forward_arrays: the last frame of the forward run replaces the b_ fields after the first step
+      for (int ir = 0; ir < run->nranks; ++ir) {
+        Rank& r = run->ranks[ir];
+        int n = r.NGLOB_AB, n3 = 3 * r.NGLOB_AB;
+        if (r.acoustic) transfer_b_fields_ac_to_device_(&n, r.last_potential, r.last_potential_dot, r.last_potential_dot_dot, r.Mesh_pointer);
+        if (r.elastic) transfer_b_fields_to_device_(&n3, r.last_displ, r.last_veloc, r.last_accel, r.Mesh_pointer);
+      }
+    }
+    if (run->has_receivers && (it - 1) % every == 0) {
+      for (int ir = 0; ir < run->nranks; ++ir) {
+        Rank& r = run->ranks[ir];
+        r.seismo_current += 1;
+        if (r.nrec_local == 0) continue;
+        int itf = it, nl = run->nlength_seismogram;
+        compute_seismograms_cuda_(r.Mesh_pointer, r.seismograms_d, r.seismograms_v, r.seismograms_a, r.seismograms_p, &r.seismo_current, &nl,
+                                  &itf, &run->NSTEP, &run->ACOUSTIC_SIMULATION, &run->ELASTIC_SIMULATION, &zero);
+      }
+    }
+    for (int ir = 0; ir < run->nranks; ++ir) {  // compute_kernels
+      Rank& r = run->ranks[ir];
+      if (r.elastic) compute_kernels_elastic_cuda_(r.Mesh_pointer, &run->deltat);
+      if (r.acoustic) compute_kernels_acoustic_cuda_(r.Mesh_pointer, &run->deltat);
+      if (run->APPROXIMATE_HESS_KL) compute_kernels_hess_cuda_(r.Mesh_pointer, &run->deltat, &r.elastic, &r.acoustic);
+    }
+  }
+}
 
 extern "C" void SB200_FC(specfem_b200_iterate_time)(specfem_b200_host_run* run, int* it_begin, int* it_end) {
   if (!run || run->nranks <= 0 || !run->ranks) host_error("specfem_b200_iterate_time: no ranks");

@@ -133,6 +133,53 @@ class KernelRun(DeviceRun):
             if sim.APPROXIMATE_HESS_KL:
                 r.lib.compute_kernels_hess_cuda(r.Mesh_pointer, dt, int(r.ELASTIC), int(r.ACOUSTIC))
 
+    def run_native(self, nstep=None):
+        """The same steps through the NATIVE host loop (specfem_b200_iterate_time_kernel_run, csrc/host_loop.cu): the Stacey
+        records and the last frame of the forward run, the adjoint sources and the b_ halo buffers are handed over as plain
+        arrays.  Same calls in the same order with the same arguments as step() (tests/test_host_loops_call_order.py)."""
+        import ctypes
+
+        from .time_loop import _pf
+
+        sim = self.sim
+        host_exchange = self._native_host_exchange()
+        n = (sim.NSTEP - self.it) if nstep is None else nstep
+        if n <= 0:
+            return self
+        run, arr, keep = self._native_setup()
+        if "kernel_run" not in keep:
+            keep["kernel_run"] = []
+            for k, r in enumerate(self.ranks):
+                db, h, nf = r.db, arr[k], max(r.db.num_abs_boundary_faces, 1)
+                hist_el = np.ascontiguousarray(np.array(self.products.absorb[k], np.float32).reshape(-1, nf, 25, 3)) \
+                    if len(self.products.absorb[k]) else np.zeros((sim.NSTEP, nf, 25, 3), np.float32)
+                hist_ac = np.ascontiguousarray(np.array(self.products.absorb_potential[k], np.float32).reshape(-1, nf, 25)) \
+                    if len(self.products.absorb_potential[k]) else np.zeros((sim.NSTEP, nf, 25), np.float32)
+                last = {key: np.ascontiguousarray(v, np.float32) for key, v in self.products.last[k].items()}
+                adj = np.ascontiguousarray(r.source_adjoint, np.float32)
+                keep["kernel_run"].append((hist_el, hist_ac, last, adj))
+                h.num_abs_boundary_faces, h.NGLOB_AB = db.num_abs_boundary_faces, db.NGLOB_AB
+                h.absorb_field_history, h.absorb_potential_history = _pf(hist_el), _pf(hist_ac)
+                h.b_buffer_send_vector, h.b_buffer_recv_vector = _pf(r.b_buffer_send_vector), _pf(r.b_buffer_recv_vector)
+                h.b_buffer_send_scalar, h.b_buffer_recv_scalar = _pf(r.b_buffer_send_scalar), _pf(r.b_buffer_recv_scalar)
+                h.source_adjoint = _pf(adj)
+                if r.ELASTIC:
+                    h.last_displ, h.last_veloc, h.last_accel = _pf(last["displ"]), _pf(last["veloc"]), _pf(last["accel"])
+                if r.ACOUSTIC:
+                    h.last_potential, h.last_potential_dot, h.last_potential_dot_dot = _pf(last["pot"]), _pf(last["pot_dot"]), _pf(last["pot_dot_dot"])
+            run.b_deltat, run.b_deltatover2, run.b_deltatsqover2 = self.b_dts
+            run.nrec, run.APPROXIMATE_HESS_KL, run.SAVE_FORWARD = sim.receivers.nrec, int(sim.APPROXIMATE_HESS_KL), 0
+        run.host_exchange = host_exchange
+        for k, r in enumerate(self.ranks):
+            arr[k].seismo_current = r.seismo_current
+        fn = self.ranks[0].lib.cdll.specfem_b200_iterate_time_kernel_run_
+        fn.restype = None
+        fn(ctypes.byref(run), ctypes.byref(ctypes.c_int(self.it + 1)), ctypes.byref(ctypes.c_int(self.it + n)))
+        for k, r in enumerate(self.ranks):
+            r.seismo_current = arr[k].seismo_current
+        self.it += n
+        return self
+
     def _elastic(self, it: int, foas):
         """foas = (0,): compute_forces_viscoelastic_GPU_calling (both wavefields); (1,) / (3,): the separate routines."""
         sim, NSTEP = self.sim, self.sim.NSTEP

@@ -258,7 +258,12 @@ class _HostRank(ctypes.Structure):
                 ("b_absorb_field", _PF), ("b_absorb_potential", _PF), ("nrec_local", ctypes.c_int),
                 ("seismograms_d", _PF), ("seismograms_v", _PF), ("seismograms_a", _PF), ("seismograms_p", _PF),
                 ("seismo_current", ctypes.c_int), ("num_abs_boundary_faces", ctypes.c_int),
-                ("absorb_field_history", _PF), ("absorb_potential_history", _PF)]
+                ("absorb_field_history", _PF), ("absorb_potential_history", _PF),
+                # kernel runs (specfem_b200_iterate_time_kernel_run)
+                ("NGLOB_AB", ctypes.c_int), ("b_buffer_send_vector", _PF), ("b_buffer_recv_vector", _PF),
+                ("b_buffer_send_scalar", _PF), ("b_buffer_recv_scalar", _PF), ("source_adjoint", _PF),
+                ("last_displ", _PF), ("last_veloc", _PF), ("last_accel", _PF),
+                ("last_potential", _PF), ("last_potential_dot", _PF), ("last_potential_dot_dot", _PF)]
 
 
 class _HostRun(ctypes.Structure):
@@ -270,7 +275,8 @@ class _HostRun(ctypes.Structure):
                 ("NSOURCES", ctypes.c_int), ("stf_elastic", _PD), ("stf_acoustic", _PD),
                 ("has_receivers", ctypes.c_int), ("NTSTEP_BETWEEN_OUTPUT_SAMPLE", ctypes.c_int), ("nlength_seismogram", ctypes.c_int),
                 ("USE_TRICK_FOR_BETTER_PRESSURE", ctypes.c_int), ("seismo_flush_every", ctypes.c_int), ("SAVE_FORWARD", ctypes.c_int),
-                ("host_exchange", ctypes.c_int), ("norm_every", ctypes.c_int), ("norms", _PF)]
+                ("b_deltat", ctypes.c_float), ("b_deltatover2", ctypes.c_float), ("b_deltatsqover2", ctypes.c_float),
+                ("nrec", ctypes.c_int), ("APPROXIMATE_HESS_KL", ctypes.c_int), ("host_exchange", ctypes.c_int), ("norm_every", ctypes.c_int), ("norms", _PF)]
 
 
 def _pf(a):
@@ -454,16 +460,41 @@ class DeviceRun:
         Returns the stability norms recorded every ``norm_every`` steps."""
         sim = self.sim
         if sim.SIMULATION_TYPE != 1 or sim.UNDO_ATTENUATION_AND_OR_PML:
-            raise NotImplementedError("native host loop: forward runs only (kernel runs: kernel_run.py, undo_att.py)")
-        if isinstance(self.exchange, InProcessExchange):
-            host_exchange = 1 if self.NPROC > 1 else 0
-        elif self.exchange is None or type(self.exchange).__name__ == "NoExchange" or getattr(self.exchange, "mode", None) == "p2p":
-            host_exchange = 0  # one rank, or the library moves the halo itself (specfem_b200_halo_p2p_connect)
-        else:
-            raise NotImplementedError("native host loop: halo transport between processes goes through the Python loop")
+            raise NotImplementedError("native host loop: forward runs only (kernel runs: KernelRun.run_native, undo_att.py)")
+        host_exchange = self._native_host_exchange()
         n = (sim.NSTEP - self.it) if nstep is None else nstep
         if n <= 0:
             return np.zeros(0, np.float32)
+        run, arr, keep = self._native_setup()
+        run.host_exchange = host_exchange
+        run.seismo_flush_every = int(seismo_flush_every)
+        norms = np.zeros(max(n // norm_every, 1) if norm_every > 0 else 1, np.float32)
+        run.norm_every, run.norms = int(norm_every), _pf(norms)
+        for k, r in enumerate(self.ranks):
+            arr[k].seismo_current = r.seismo_current
+        fn = self.ranks[0].lib.cdll.specfem_b200_iterate_time_
+        fn.restype = None
+        fn(ctypes.byref(run), ctypes.byref(ctypes.c_int(self.it + 1)), ctypes.byref(ctypes.c_int(self.it + n)))
+        for k, r in enumerate(self.ranks):
+            r.seismo_current = arr[k].seismo_current
+            if sim.SAVE_FORWARD and sim.spec.stacey:  # same bookkeeping as step(): one record per step and domain of the rank
+                if r.ELASTIC:
+                    r.absorb_history += [keep[k][3][it].copy() for it in range(self.it, self.it + n)]
+                if r.ACOUSTIC:
+                    r.absorb_potential_history += [keep[k][4][it].copy() for it in range(self.it, self.it + n)]
+        self.it += n
+        return norms if norm_every > 0 else np.zeros(0, np.float32)
+
+    def _native_host_exchange(self) -> int:
+        if isinstance(self.exchange, InProcessExchange):
+            return 1 if self.NPROC > 1 else 0
+        if self.exchange is None or type(self.exchange).__name__ == "NoExchange" or getattr(self.exchange, "mode", None) == "p2p":
+            return 0  # one rank, or the library moves the halo itself (specfem_b200_halo_p2p_connect)
+        raise NotImplementedError("native host loop: halo transport between processes goes through the Python loop")
+
+    def _native_setup(self):
+        """The plain-C descriptors of include/specfem3d_b200_host.h for this run (built once; the arrays they point to are kept)."""
+        sim = self.sim
         if not hasattr(self, "_native"):
             ns = sim.sources.NSOURCES if sim.sources is not None else 0
             keep = {"stf_el": np.zeros((sim.NSTEP, max(ns, 1))), "stf_ac": np.zeros((sim.NSTEP, max(ns, 1)))}
@@ -510,25 +541,7 @@ class DeviceRun:
             run.SAVE_FORWARD = int(sim.SAVE_FORWARD)
             run.NTSTEP_BETWEEN_OUTPUT_SAMPLE, run.nlength_seismogram = sim.NTSTEP_BETWEEN_OUTPUT_SAMPLE, sim.nlength_seismogram
             self._native = (run, arr, keep)
-        run, arr, keep = self._native
-        run.host_exchange = host_exchange
-        run.seismo_flush_every = int(seismo_flush_every)
-        norms = np.zeros(max(n // norm_every, 1) if norm_every > 0 else 1, np.float32)
-        run.norm_every, run.norms = int(norm_every), _pf(norms)
-        for k, r in enumerate(self.ranks):
-            arr[k].seismo_current = r.seismo_current
-        fn = self.ranks[0].lib.cdll.specfem_b200_iterate_time_
-        fn.restype = None
-        fn(ctypes.byref(run), ctypes.byref(ctypes.c_int(self.it + 1)), ctypes.byref(ctypes.c_int(self.it + n)))
-        for k, r in enumerate(self.ranks):
-            r.seismo_current = arr[k].seismo_current
-            if sim.SAVE_FORWARD and sim.spec.stacey:  # same bookkeeping as step(): one record per step and domain of the rank
-                if r.ELASTIC:
-                    r.absorb_history += [keep[k][3][it].copy() for it in range(self.it, self.it + n)]
-                if r.ACOUSTIC:
-                    r.absorb_potential_history += [keep[k][4][it].copy() for it in range(self.it, self.it + n)]
-        self.it += n
-        return norms if norm_every > 0 else np.zeros(0, np.float32)
+        return self._native
 
     def max_norm_displ(self) -> float:
         m = 0.0

@@ -35,7 +35,7 @@ def mock_lib(tmp_path_factory):
         # (time-step constants, element counts, FORWARD_OR_ADJOINT, the source time function value of the step, ...); in the
         # time loop every such pointer refers to at least one element
         first = []
-        if name not in ("initialize_gpu_device", "prepare_constants_device") and not name.startswith(("prepare_", "transfer_", "get_")):
+        if name not in ("initialize_gpu_device", "prepare_constants_device") and not name.startswith(("prepare_", "get_")):
             for a, n in zip(args, names):
                 t = a.replace("const", " ").replace("*", " ").split()[0]
                 if "*" in a and t in ("int", "realw", "double", "field") and not n.startswith("Mesh_pointer"):
@@ -128,3 +128,48 @@ def test_save_forward_records_are_kept_alike(mock_lib, case):
         if len(x):
             assert len(x) == 6 and len(np.unique(x.reshape(6, -1)[:, 0])) == 6  # six steps, six different records
     assert n_records >= 6 * len(a[0])
+
+
+@pytest.mark.parametrize("case", ["elastic", "elastic_2x2", "acoustic_2x2", "coupled", "elastic_hess"])
+def test_kernel_run_loops_issue_the_same_calls(mock_lib, case):
+    """SIMULATION_TYPE 3: KernelRun.step (kernel_run.py, the loop the GPU tests pin against the oracle and the reference CUDA backend)
+    and specfem_b200_iterate_time_kernel_run (csrc/host_loop.cu) -- same entry points, ranks, iphase and scalar arguments, incl. the
+    Stacey record replayed at every step (read_abs at NSTEP - it + 1: the mock numbered the records of the forward run), the
+    adjoint-source array, the source time function taken backwards, and the last frame handed over after the first step."""
+    import test_oracle_kernel_run as k
+
+    from specfem3d_b200.kernel_run import KernelRun, run_forward_and_save
+
+    nstep = 6
+    make = {"elastic": lambda t: k.kernel_sim((1, 1), nstep, nex=(4, 4, 2), sim_type=t),
+            "elastic_2x2": lambda t: k.kernel_sim((2, 2), nstep, nex=(4, 4, 2), sim_type=t),
+            "elastic_hess": lambda t: k.kernel_sim((1, 1), nstep, nex=(4, 4, 2), sim_type=t),
+            "acoustic_2x2": lambda t: k.acoustic_kernel_sim((2, 2), nstep, nex=(4, 4, 2), sim_type=t),
+            "coupled": lambda t: k.coupled_kernel_sim(nstep, t)}[case]
+    logs = {}
+    for native in (False, True):
+        mock_lib.cdll.mock_reset(1)
+        fwd, prod = run_forward_and_save(make(1), lib=mock_lib, native=native)
+        fwd.cleanup()
+        for ir, last in enumerate(prod.last):  # a recognisable last frame (the mock's device hands back zeros)
+            for j, key in enumerate(sorted(last)):
+                last[key] = np.full_like(last[key], 10.0 * (ir + 1) + j)
+        sim3 = make(3)
+        sim3.APPROXIMATE_HESS_KL = case == "elastic_hess"
+        rng = np.random.default_rng(5)
+        adj = rng.standard_normal((sim3.receivers.nrec, nstep, 3)).astype(np.float32)
+        mock_lib.cdll.mock_reset(1)
+        run = KernelRun(sim3, prod, adj, lib=mock_lib)
+        mock_lib.cdll.mock_reset(0)
+        if native:
+            run.run_native(4)
+            run.run_native()
+        else:
+            run.run()
+        assert run.it == nstep
+        logs[native] = _calls(mock_lib)
+        run.cleanup()
+    a, b = logs[False], logs[True]
+    names = {c[0] for c in a}
+    assert {"compute_kernels_elastic_cuda", "compute_kernels_acoustic_cuda"} & names and any(n.startswith("transfer_b_fields") for n in names)
+    assert a == b, next((i, x, y) for i, (x, y) in enumerate(zip(a, b)) if x != y)
