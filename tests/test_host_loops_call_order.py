@@ -70,10 +70,17 @@ def _cases():
             "viscoelastic": lambda: g.visco_sim(nstep=6),
             "coupled_2x1": lambda: g.ocean_sim(nproc=(2, 1), nstep=6),
             "cpml": lambda: g.pml_sim(nstep=6),
-            "ocean_load": lambda: g.ocean_load_sim(nstep=6)}
+            "cpml_2x2": lambda: g.pml_sim(nproc=(2, 2), nstep=6),
+            "ocean_load": lambda: g.ocean_load_sim(nstep=6),
+            "ocean_load_2x2": lambda: g.ocean_load_sim(nproc=(2, 2), nstep=6),
+            "coloring": lambda: g.small_sim(nstep=6, nex=(4, 4, 2), coloring=True),
+            "coupled_coloring": lambda: g.ocean_sim(nstep=6, coloring=True),
+            "anisotropic_visco": lambda: g.aniso_sim(nstep=6, attenuation=True, nproc=(2, 1)),
+            "source_in_water": lambda: g.ocean_sim(nproc=(2, 1), nstep=6, source_in_water=True)}
 
 
-@pytest.mark.parametrize("case", ["elastic", "elastic_2x2", "viscoelastic", "coupled_2x1", "cpml", "ocean_load"])
+@pytest.mark.parametrize("case", ["elastic", "elastic_2x2", "viscoelastic", "coupled_2x1", "cpml", "cpml_2x2", "ocean_load", "ocean_load_2x2",
+                                  "coloring", "coupled_coloring", "anisotropic_visco", "source_in_water"])
 def test_python_and_native_host_loops_issue_the_same_calls(mock_lib, case):
     from specfem3d_b200.time_loop import DeviceRun
 
