@@ -53,6 +53,12 @@ typedef struct {
   realw *b_buffer_send_vector, *b_buffer_recv_vector, *b_buffer_send_scalar, *b_buffer_recv_scalar;
   realw* source_adjoint;
   realw *last_displ, *last_veloc, *last_accel, *last_potential, *last_potential_dot, *last_potential_dot_dot;
+  /* undo-attenuation kernel runs (specfem_b200_iterate_time_undoatt): what proc*_save_frame_at*.bin holds at the start of every
+     forward subset s = 0 .. NSUBSET_ITERATIONS - 1 -- frame_displ[s], frame_veloc[s], frame_accel[s] (NDIM, NGLOB), with ATTENUATION
+     frame_R[6 s + {0..5}] = R_xx, R_yy, R_xy, R_xz, R_yz, R_trace (N_SLS, 125, NSPEC); fluid ranks: the three potentials */
+  int NSPEC_AB;
+  realw **frame_displ, **frame_veloc, **frame_accel, **frame_R;
+  realw **frame_potential, **frame_potential_dot, **frame_potential_dot_dot;
 } specfem_b200_host_rank;
 
 typedef struct {
@@ -82,6 +88,8 @@ typedef struct {
      APPROXIMATE_HESS_KL */
   realw b_deltat, b_deltatover2, b_deltatsqover2;
   int nrec, APPROXIMATE_HESS_KL;
+  /* undo-attenuation runs: length of a forward subset (NT_DUMP_ATTENUATION of the Par_file, clipped to NSTEP) */
+  int NT_DUMP_ATTENUATION;
   /* halo transport between the ranks of THIS process: 1 = copy send -> receive buffers on the host (what MPI does between
      processes), 0 = none (single rank, or the library moves the halo itself after specfem_b200_halo_p2p_connect) */
   int host_exchange;
@@ -102,6 +110,13 @@ void SB200_FC(specfem_b200_iterate_time)(specfem_b200_host_run* run, int* it_beg
    compute_forces_viscoelastic_GPU_calling / compute_forces_acoustic_GPU_calling (FORWARD_OR_ADJOINT 0) or, in coupled runs, the
    separate forward / backward routines (compute_forces_viscoelastic_calling_routine.F90:61-67). */
 void SB200_FC(specfem_b200_iterate_time_kernel_run)(specfem_b200_host_run* run, int* it_begin, int* it_end);
+
+/* The whole kernel run of UNDO_ATTENUATION_AND_OR_PML (iterate_time_undoatt.F90:63-470; elastic / viscoelastic OR acoustic domains,
+   no C-PML, no approximate Hessian): the forward subsets are taken in reverse order; for each one the saved frame is restored into the
+   b_ fields, the forward wavefield is re-computed FORWARD in time (b_deltat = deltat) and b_displ (fluid: b_potential,
+   b_potential_dot_dot) of every step is buffered on the host, then the adjoint wavefield advances over the same steps while the
+   buffered frames are handed back in reverse order and the kernels accumulate.  Always all NSTEP steps. */
+void SB200_FC(specfem_b200_iterate_time_undoatt)(specfem_b200_host_run* run);
 
 #ifdef __cplusplus
 }

@@ -331,7 +331,235 @@ void acoustic_step_kl(Run* run, int it, int foa) {
   }
 }
 
+// ---- undo-attenuation kernel runs: specfem3d_b200/undo_att.py is the same loop in Python ----------------------------------
+// the MPI part of one phase for the accel (foa 1) or b_accel (foa 3) field
+void exchange_elastic_undoatt(Run* run, int iphase, int foa) {
+  if (run->NPROC == 1) return;
+  int three = 3;
+  if (iphase == 1) {
+    for (int ir = 0; ir < run->nranks; ++ir) {
+      Rank& r = run->ranks[ir];
+      if (!r.elastic) continue;
+      if (foa == 1) transfer_boundary_from_device_a_(r.Mesh_pointer, &r.nspec_outer_elastic);
+      else transfer_boun_accel_from_device_(r.Mesh_pointer, r.b_buffer_send_vector, &three);
+    }
+    if (foa == 3 && run->host_exchange) exchange_on_host_b(run, 3);
+  } else {
+    if (foa == 1) {
+      for (int ir = 0; ir < run->nranks; ++ir) {
+        Rank& r = run->ranks[ir];
+        if (r.elastic) sync_copy_from_device_(r.Mesh_pointer, &iphase, r.buffer_send_vector);
+      }
+      if (run->host_exchange) exchange_on_host(run, 3);
+      for (int ir = 0; ir < run->nranks; ++ir) {
+        Rank& r = run->ranks[ir];
+        if (r.elastic)
+          transfer_boundary_to_device_a_(r.Mesh_pointer, r.buffer_recv_vector, &r.num_interfaces_ext_mesh, &r.max_nibool_interfaces_ext_mesh);
+      }
+    }
+    for (int ir = 0; ir < run->nranks; ++ir) {
+      Rank& r = run->ranks[ir];
+      if (r.elastic)
+        transfer_asmbl_accel_to_device_(r.Mesh_pointer, foa == 3 ? r.b_buffer_recv_vector : r.buffer_recv_vector, &r.num_interfaces_ext_mesh,
+                                        &r.max_nibool_interfaces_ext_mesh, r.nibool_interfaces_ext_mesh, r.ibool_interfaces_ext_mesh, &foa);
+    }
+  }
+}
+
+// foa = 3: compute_forces_acoustic_backward_calling on the re-computed potentials (it = it_tmp); 1: the adjoint potentials
+void acoustic_one_field_undoatt(Run* run, int it, int foa) {
+  int sifs = run->STACEY_INSTEAD_OF_FREE_SURFACE, NSTEP = run->NSTEP;
+  std::vector<int> run_number(run->NSOURCES > 0 ? run->NSOURCES : 1, 0);
+  for (int ir = 0; ir < run->nranks; ++ir) {
+    Rank& r = run->ranks[ir];
+    if (r.acoustic) acoustic_enforce_free_surf_cuda_(r.Mesh_pointer, &sifs, &foa);
+  }
+  for (int iphase = 1; iphase <= 2; ++iphase) {
+    for (int ir = 0; ir < run->nranks; ++ir) {
+      Rank& r = run->ranks[ir];
+      if (!r.acoustic) continue;
+      compute_forces_acoustic_cuda_(r.Mesh_pointer, &iphase, &r.nspec_outer_acoustic, &r.nspec_inner_acoustic, &foa);
+      if (iphase != 1) continue;
+      if (run->STACEY_ABSORBING_CONDITIONS) compute_stacey_acoustic_undoatt_cuda_(r.Mesh_pointer, &iphase, &foa);
+      if (foa == 1 && r.nrec_local > 0 && it < NSTEP) {
+        int itf = it;
+        add_sources_ac_sim_2_or_3_cuda_(r.Mesh_pointer, r.source_adjoint, &run->nrec, &r.nrec_local, &NSTEP, &itf);
+      }
+      if (foa == 3 && run->NSOURCES > 0) {
+        int ns = run->NSOURCES;
+        compute_add_sources_ac_s3_cuda_(r.Mesh_pointer, &ns, const_cast<double*>(run->stf_acoustic + (size_t)(NSTEP - it) * ns), run_number.data());
+      }
+    }
+    if (run->NPROC > 1) {
+      for (int ir = 0; ir < run->nranks; ++ir) {
+        Rank& r = run->ranks[ir];
+        if (!r.acoustic) continue;
+        if (iphase == 1) transfer_boun_pot_from_device_(r.Mesh_pointer, foa == 3 ? r.b_buffer_send_scalar : r.buffer_send_scalar, &foa);
+        else transfer_asmbl_pot_to_device_(r.Mesh_pointer, foa == 3 ? r.b_buffer_recv_scalar : r.buffer_recv_scalar, &foa);
+      }
+      if (iphase == 1 && run->host_exchange) {
+        if (foa == 3) exchange_on_host_b(run, 1);
+        else exchange_on_host(run, 1);
+      }
+    }
+  }
+  for (int ir = 0; ir < run->nranks; ++ir) {
+    Rank& r = run->ranks[ir];
+    if (!r.acoustic) continue;
+    kernel_3_acoustic_cuda_(r.Mesh_pointer, &run->deltatover2, &run->b_deltatover2, &foa);
+    acoustic_enforce_free_surf_cuda_(r.Mesh_pointer, &sifs, &foa);
+  }
+}
+
+// foa = 3: compute_forces_viscoelastic_backward_calling (it = it_tmp); 1: compute_forces_viscoelastic_calling on the adjoint wavefield
+void elastic_one_field_undoatt(Run* run, int it, int foa) {
+  int strain = 1, att = run->ATTENUATION ? 1 : 0, zero = 0, NSTEP = run->NSTEP;
+  realw dt_forces = foa == 3 ? run->b_deltat : run->deltat;
+  for (int iphase = 1; iphase <= 2; ++iphase) {
+    for (int ir = 0; ir < run->nranks; ++ir) {
+      Rank& r = run->ranks[ir];
+      if (!r.elastic) continue;
+      compute_forces_viscoelastic_cuda_(r.Mesh_pointer, &iphase, &dt_forces, &r.nspec_outer_elastic, &r.nspec_inner_elastic, &strain, &att, &foa);
+      if (iphase != 1) continue;
+      if (run->STACEY_ABSORBING_CONDITIONS) compute_stacey_viscoelastic_undoatt_cuda_(r.Mesh_pointer, &iphase, &foa);
+      if (foa == 1 && r.nrec_local > 0 && it < NSTEP) {
+        int itf = it;
+        add_sources_el_sim_type_2_or_3_(r.Mesh_pointer, r.source_adjoint, &run->nrec, &r.nrec_local, &NSTEP, &itf);
+      }
+      if (run->NSOURCES > 0) {  // foa 1 too: compute_add_sources_viscoelastic_GPU adds the forward source into b_accel (unused here)
+        int ns = run->NSOURCES;
+        compute_add_sources_el_s3_cuda_(r.Mesh_pointer, const_cast<double*>(run->stf_elastic + (size_t)(NSTEP - it) * ns), &ns);
+      }
+    }
+    exchange_elastic_undoatt(run, iphase, foa);
+  }
+  for (int ir = 0; ir < run->nranks; ++ir) {
+    Rank& r = run->ranks[ir];
+    if (r.elastic) kernel_3_a_cuda_(r.Mesh_pointer, &run->deltatover2, &run->b_deltatover2, &zero, &foa);
+  }
+}
+
 }  // namespace
+
+extern "C" void SB200_FC(specfem_b200_iterate_time_undoatt)(specfem_b200_host_run* run) {
+  if (!run || run->nranks <= 0 || !run->ranks) host_error("specfem_b200_iterate_time_undoatt: no ranks");
+  if ((run->ELASTIC_SIMULATION && run->ACOUSTIC_SIMULATION) || run->PML_CONDITIONS || run->APPROXIMATE_HESS_KL)
+    host_error("specfem_b200_iterate_time_undoatt: elastic or acoustic domains (not coupled), no C-PML, no approximate Hessian");
+  const int NSTEP = run->NSTEP;
+  const int nt_dump = run->NT_DUMP_ATTENUATION < NSTEP ? run->NT_DUMP_ATTENUATION : NSTEP;
+  if (nt_dump <= 0) host_error("specfem_b200_iterate_time_undoatt: NT_DUMP_ATTENUATION must be positive");
+  const int nsubset = (NSTEP + nt_dump - 1) / nt_dump;
+  const int every = run->NTSTEP_BETWEEN_OUTPUT_SAMPLE > 0 ? run->NTSTEP_BETWEEN_OUTPUT_SAMPLE : 1;
+  int one = 1, three = 3, zero = 0, it_global = 0;
+  std::vector<std::vector<realw>> buf_displ(run->nranks), buf_pot(run->nranks), buf_pdd(run->nranks);
+  for (int iteration_on_subset = 1; iteration_on_subset <= nsubset; ++iteration_on_subset) {
+    // read_forward_arrays_undoatt: frame NSUBSET_ITERATIONS - iteration_on_subset + 1 -> b_ fields
+    const int frame = nsubset - iteration_on_subset;
+    for (int ir = 0; ir < run->nranks; ++ir) {
+      Rank& r = run->ranks[ir];
+      int n = r.NGLOB_AB, n3 = 3 * r.NGLOB_AB;
+      if (r.acoustic)
+        transfer_b_fields_ac_to_device_(&n, r.frame_potential[frame], r.frame_potential_dot[frame], r.frame_potential_dot_dot[frame], r.Mesh_pointer);
+      if (!r.elastic) continue;
+      transfer_b_fields_to_device_(&n3, r.frame_displ[frame], r.frame_veloc[frame], r.frame_accel[frame], r.Mesh_pointer);
+      if (run->ATTENUATION) {
+        int size_R = 3 * 125 * r.NSPEC_AB;  // N_SLS * NGLL3 * NSPEC
+        realw** R = r.frame_R + 6 * (size_t)frame;
+        transfer_b_rmemory_to_device_(r.Mesh_pointer, R[0], R[1], R[2], R[3], R[4], R[5], &size_R);
+      }
+    }
+    for (int ir = 0; ir < run->nranks; ++ir) {  // compute_strain_att_backward
+      Rank& r = run->ranks[ir];
+      if (r.elastic) compute_strain_cuda_(r.Mesh_pointer, &three);
+    }
+    const int it_temp = it_global;
+    std::vector<int> seismo_temp(run->nranks);
+    for (int ir = 0; ir < run->nranks; ++ir) seismo_temp[ir] = run->ranks[ir].seismo_current;
+    // forward subsets are full except the LAST one, which the kernel run takes first
+    const int it_subset_end = iteration_on_subset == 1 ? NSTEP - (nsubset - 1) * nt_dump : nt_dump;
+    for (int ir = 0; ir < run->nranks; ++ir) {
+      Rank& r = run->ranks[ir];
+      if (r.elastic) buf_displ[ir].assign((size_t)it_subset_end * 3 * r.NGLOB_AB, 0.f);
+      if (r.acoustic) {
+        buf_pot[ir].assign((size_t)it_subset_end * r.NGLOB_AB, 0.f);
+        buf_pdd[ir].assign((size_t)it_subset_end * r.NGLOB_AB, 0.f);
+      }
+    }
+    // ---- the forward wavefield over this subset, forward in time ----
+    for (int its = 1; its <= it_subset_end; ++its) {
+      it_global += 1;
+      for (int ir = 0; ir < run->nranks; ++ir) {  // update_displ_Newmark_backward: fluid first
+        Rank& r = run->ranks[ir];
+        if (r.acoustic) update_displacement_ac_cuda_(r.Mesh_pointer, &run->b_deltat, &run->b_deltatover2, &run->b_deltatsqover2, &three);
+      }
+      for (int ir = 0; ir < run->nranks; ++ir) {
+        Rank& r = run->ranks[ir];
+        if (r.elastic) update_displacement_cuda_(r.Mesh_pointer, &run->b_deltat, &run->b_deltatover2, &run->b_deltatsqover2, &three);
+      }
+      const int it_tmp = NSTEP - (nsubset - iteration_on_subset) * nt_dump - its + 1;
+      if (run->ACOUSTIC_SIMULATION) acoustic_one_field_undoatt(run, it_tmp, 3);
+      if (run->ELASTIC_SIMULATION) elastic_one_field_undoatt(run, it_tmp, 3);
+      for (int ir = 0; ir < run->nranks; ++ir) {  // b_displ_elastic_buffer(:,:,it_of_this_subset) = b_displ
+        Rank& r = run->ranks[ir];
+        int n = r.NGLOB_AB, n3 = 3 * r.NGLOB_AB;
+        if (r.acoustic) {
+          transfer_b_potential_ac_from_device_(&n, buf_pot[ir].data() + (size_t)(its - 1) * n, r.Mesh_pointer);
+          transfer_b_potential_dot_dot_ac_from_device_(&n, buf_pdd[ir].data() + (size_t)(its - 1) * n, r.Mesh_pointer);
+        }
+        if (r.elastic) transfer_b_displ_from_device_(&n3, buf_displ[ir].data() + (size_t)(its - 1) * n3, r.Mesh_pointer);
+      }
+    }
+    it_global = it_temp;
+    for (int ir = 0; ir < run->nranks; ++ir) run->ranks[ir].seismo_current = seismo_temp[ir];
+    for (int ir = 0; ir < run->nranks; ++ir) {  // compute_strain_att
+      Rank& r = run->ranks[ir];
+      if (r.elastic) compute_strain_cuda_(r.Mesh_pointer, &one);
+    }
+    // ---- the adjoint wavefield over the same steps; buffered frames in reverse order ----
+    for (int its = 1; its <= it_subset_end; ++its) {
+      it_global += 1;
+      const int it = it_global;
+      for (int ir = 0; ir < run->nranks; ++ir) {
+        Rank& r = run->ranks[ir];
+        int n = r.NGLOB_AB, n3 = 3 * r.NGLOB_AB;
+        if (r.acoustic) {
+          transfer_b_potential_ac_to_device_(&n, buf_pot[ir].data() + (size_t)(it_subset_end - its) * n, r.Mesh_pointer);
+          transfer_b_potential_dot_dot_ac_to_device_(&n, buf_pdd[ir].data() + (size_t)(it_subset_end - its) * n, r.Mesh_pointer);
+        }
+        if (r.elastic) transfer_b_displ_to_device_(&n3, buf_displ[ir].data() + (size_t)(it_subset_end - its) * n3, r.Mesh_pointer);
+      }
+      for (int ir = 0; ir < run->nranks; ++ir) {  // update_displ_Newmark
+        Rank& r = run->ranks[ir];
+        if (r.acoustic) update_displacement_ac_cuda_(r.Mesh_pointer, &run->deltat, &run->deltatover2, &run->deltatsqover2, &one);
+      }
+      for (int ir = 0; ir < run->nranks; ++ir) {
+        Rank& r = run->ranks[ir];
+        if (r.elastic) update_displacement_cuda_(r.Mesh_pointer, &run->deltat, &run->deltatover2, &run->deltatsqover2, &one);
+      }
+      if (run->ACOUSTIC_SIMULATION) acoustic_one_field_undoatt(run, it, 1);
+      if (run->ELASTIC_SIMULATION) elastic_one_field_undoatt(run, it, 1);
+      if (run->has_receivers && (it - 1) % every == 0) {
+        for (int ir = 0; ir < run->nranks; ++ir) {
+          Rank& r = run->ranks[ir];
+          r.seismo_current += 1;
+          if (r.nrec_local == 0) continue;
+          int itf = it, nl = run->nlength_seismogram;
+          compute_seismograms_cuda_(r.Mesh_pointer, r.seismograms_d, r.seismograms_v, r.seismograms_a, r.seismograms_p, &r.seismo_current, &nl,
+                                    &itf, &run->NSTEP, &run->ACOUSTIC_SIMULATION, &run->ELASTIC_SIMULATION, &zero);
+        }
+      }
+      for (int ir = 0; ir < run->nranks; ++ir) {  // compute_kernels: the library re-computes the strain of b_displ
+        Rank& r = run->ranks[ir];
+        if (r.elastic) compute_kernels_elastic_cuda_(r.Mesh_pointer, &run->deltat);
+      }
+      for (int ir = 0; ir < run->nranks; ++ir) {
+        Rank& r = run->ranks[ir];
+        if (r.acoustic) compute_kernels_acoustic_cuda_(r.Mesh_pointer, &run->deltat);
+      }
+    }
+  }
+  if (it_global != NSTEP) host_error("specfem_b200_iterate_time_undoatt: the subsets do not add up to NSTEP");
+}
 
 extern "C" void SB200_FC(specfem_b200_iterate_time_kernel_run)(specfem_b200_host_run* run, int* it_begin, int* it_end) {
   if (!run || run->nranks <= 0 || !run->ranks) host_error("specfem_b200_iterate_time_kernel_run: no ranks");

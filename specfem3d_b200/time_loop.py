@@ -246,6 +246,7 @@ class DeviceRank:
 
 # ---- native host loop (include/specfem3d_b200_host.h, csrc/host_loop.cu) -----------------------------------------------------
 _PF, _PI, _PD = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)
+_PPF = ctypes.POINTER(_PF)
 
 
 class _HostRank(ctypes.Structure):
@@ -263,7 +264,10 @@ class _HostRank(ctypes.Structure):
                 ("NGLOB_AB", ctypes.c_int), ("b_buffer_send_vector", _PF), ("b_buffer_recv_vector", _PF),
                 ("b_buffer_send_scalar", _PF), ("b_buffer_recv_scalar", _PF), ("source_adjoint", _PF),
                 ("last_displ", _PF), ("last_veloc", _PF), ("last_accel", _PF),
-                ("last_potential", _PF), ("last_potential_dot", _PF), ("last_potential_dot_dot", _PF)]
+                ("last_potential", _PF), ("last_potential_dot", _PF), ("last_potential_dot_dot", _PF),
+                # undo-attenuation kernel runs (specfem_b200_iterate_time_undoatt): one pointer per forward subset
+                ("NSPEC_AB", ctypes.c_int), ("frame_displ", _PPF), ("frame_veloc", _PPF), ("frame_accel", _PPF), ("frame_R", _PPF),
+                ("frame_potential", _PPF), ("frame_potential_dot", _PPF), ("frame_potential_dot_dot", _PPF)]
 
 
 class _HostRun(ctypes.Structure):
@@ -276,7 +280,7 @@ class _HostRun(ctypes.Structure):
                 ("has_receivers", ctypes.c_int), ("NTSTEP_BETWEEN_OUTPUT_SAMPLE", ctypes.c_int), ("nlength_seismogram", ctypes.c_int),
                 ("USE_TRICK_FOR_BETTER_PRESSURE", ctypes.c_int), ("seismo_flush_every", ctypes.c_int), ("SAVE_FORWARD", ctypes.c_int),
                 ("b_deltat", ctypes.c_float), ("b_deltatover2", ctypes.c_float), ("b_deltatsqover2", ctypes.c_float),
-                ("nrec", ctypes.c_int), ("APPROXIMATE_HESS_KL", ctypes.c_int), ("host_exchange", ctypes.c_int), ("norm_every", ctypes.c_int), ("norms", _PF)]
+                ("nrec", ctypes.c_int), ("APPROXIMATE_HESS_KL", ctypes.c_int), ("NT_DUMP_ATTENUATION", ctypes.c_int), ("host_exchange", ctypes.c_int), ("norm_every", ctypes.c_int), ("norms", _PF)]
 
 
 def _pf(a):

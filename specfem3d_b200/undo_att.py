@@ -199,6 +199,57 @@ class UndoAttKernelRun(DeviceRun):
         assert self.it == NSTEP
         return self
 
+    def run_native(self):
+        """The same run through the NATIVE host loop (specfem_b200_iterate_time_undoatt, csrc/host_loop.cu): the saved frames of the
+        forward subsets go over as arrays of pointers, the per-step b_displ / potential buffers live in the C++ loop.  Same calls,
+        in the same order with the same arguments as run() (tests/test_host_loops_call_order.py)."""
+        import ctypes
+
+        from .time_loop import _PF, _pf
+
+        sim = self.sim
+        host_exchange = self._native_host_exchange()
+        run, arr, keep = self._native_setup()
+        keep["undoatt"] = []
+        for k, r in enumerate(self.ranks):
+            db, h = r.db, arr[k]
+            frames = self.products.frames[k]
+            adj = np.ascontiguousarray(r.source_adjoint, np.float32)
+            held = [adj]
+
+            def ptrs(arrays):
+                arrays = [np.ascontiguousarray(a, np.float32) for a in arrays]
+                held.extend(arrays)
+                table = (_PF * len(arrays))(*[_pf(a) for a in arrays])
+                held.append(table)
+                return ctypes.cast(table, ctypes.POINTER(_PF))
+
+            h.NGLOB_AB, h.NSPEC_AB = db.NGLOB_AB, db.NSPEC_AB
+            h.source_adjoint = _pf(adj)
+            h.b_buffer_send_vector, h.b_buffer_recv_vector = _pf(r.b_buffer_send_vector), _pf(r.b_buffer_recv_vector)
+            h.b_buffer_send_scalar, h.b_buffer_recv_scalar = _pf(r.b_buffer_send_scalar), _pf(r.b_buffer_recv_scalar)
+            if r.ELASTIC:
+                h.frame_displ, h.frame_veloc, h.frame_accel = (ptrs([f[key] for f in frames]) for key in ("displ", "veloc", "accel"))
+                if self.att:
+                    h.frame_R = ptrs([R for f in frames for R in f["R"]])
+            if r.ACOUSTIC:
+                h.frame_potential, h.frame_potential_dot, h.frame_potential_dot_dot = (
+                    ptrs([f[key] for f in frames]) for key in ("pot", "pot_dot", "pot_dot_dot"))
+            keep["undoatt"].append(held)
+        run.b_deltat, run.b_deltatover2, run.b_deltatsqover2 = self.b_dts
+        run.nrec, run.APPROXIMATE_HESS_KL, run.SAVE_FORWARD = sim.receivers.nrec, 0, 0
+        run.NT_DUMP_ATTENUATION = int(sim.NT_DUMP_ATTENUATION)
+        run.host_exchange = host_exchange
+        for k, r in enumerate(self.ranks):
+            arr[k].seismo_current = r.seismo_current
+        fn = self.ranks[0].lib.cdll.specfem_b200_iterate_time_undoatt_
+        fn.restype = None
+        fn(ctypes.byref(run))
+        for k, r in enumerate(self.ranks):
+            r.seismo_current = arr[k].seismo_current
+        self.it = sim.NSTEP
+        return self
+
     # --------------------------------------------------------------------------------------------------------------
     def _exchange_elastic(self, E, iphase, foa):
         """The MPI part of one phase for the accel (1) or b_accel (3) field."""

@@ -180,3 +180,50 @@ def test_kernel_run_loops_issue_the_same_calls(mock_lib, case):
     names = {c[0] for c in a}
     assert {"compute_kernels_elastic_cuda", "compute_kernels_acoustic_cuda"} & names and any(n.startswith("transfer_b_fields") for n in names)
     assert a == b, next((i, x, y) for i, (x, y) in enumerate(zip(a, b)) if x != y)
+
+
+@pytest.mark.parametrize("case", ["elastic", "elastic_2x2", "viscoelastic_2x1", "acoustic_2x2"])
+def test_undo_attenuation_loops_issue_the_same_calls(mock_lib, case):
+    """UNDO_ATTENUATION_AND_OR_PML kernel runs: UndoAttKernelRun.run (undo_att.py, iterate_time_undoatt restated; the loop the GPU
+    tests pin) and specfem_b200_iterate_time_undoatt (csrc/host_loop.cu) -- same entry points, ranks, iphase and scalar arguments over
+    the whole run: subsets of 4, 4 and 3 steps taken in reverse order, each re-computed forward and then swept by the adjoint wavefield
+    with the buffered frames handed back in reverse order."""
+    import ref_cuda_runner as R
+
+    from specfem3d_b200.undo_att import UndoAttKernelRun, run_forward_and_save_undoatt
+
+    nstep, nt_dump = 11, 4
+    make = {"elastic": lambda t: R.undoatt_kernel_sim(nstep, t, False, (1, 1), nt_dump),
+            "elastic_2x2": lambda t: R.undoatt_kernel_sim(nstep, t, False, (2, 2), nt_dump),
+            "viscoelastic_2x1": lambda t: R.undoatt_kernel_sim(nstep, t, True, (2, 1), nt_dump),
+            "acoustic_2x2": lambda t: R.undoatt_acoustic_sim(nstep, t, (2, 2), nt_dump)}[case]
+    logs = {}
+    for native in (False, True):
+        mock_lib.cdll.mock_reset(1)
+        fwd, prod = run_forward_and_save_undoatt(make(1), lib=mock_lib)
+        fwd.cleanup()
+        for ir, frames in enumerate(prod.frames):  # recognisable frames (the mock's device hands back zeros)
+            for s, f in enumerate(frames):
+                for j, key in enumerate(sorted(f)):
+                    if key == "R":
+                        f[key] = [np.full_like(a, 100.0 * (ir + 1) + 10.0 * s + m) for m, a in enumerate(f[key])]
+                    else:
+                        f[key] = np.full_like(f[key], 10.0 * (ir + 1) + s + 0.1 * j)
+        sim3 = make(3)
+        rng = np.random.default_rng(7)
+        adj = rng.standard_normal((sim3.receivers.nrec, nstep, 3)).astype(np.float32)
+        mock_lib.cdll.mock_reset(1)
+        run = UndoAttKernelRun(sim3, prod, adj, lib=mock_lib)
+        assert (run.nsubset, run.lengths) == (3, [4, 4, 3])
+        mock_lib.cdll.mock_reset(0)
+        if native:
+            run.run_native()
+        else:
+            run.run()
+        assert run.it == nstep
+        logs[native] = _calls(mock_lib)
+        run.cleanup()
+    a, b = logs[False], logs[True]
+    names = [c[0] for c in a]
+    assert names.count("transfer_b_fields_to_device") + names.count("transfer_b_fields_ac_to_device") == 3 * len({c[1] for c in a})
+    assert a == b, next((i, x, y) for i, (x, y) in enumerate(zip(a, b)) if x != y)
