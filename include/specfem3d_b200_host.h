@@ -90,6 +90,9 @@ typedef struct {
   int nrec, APPROXIMATE_HESS_KL;
   /* undo-attenuation runs: length of a forward subset (NT_DUMP_ATTENUATION of the Par_file, clipped to NSTEP) */
   int NT_DUMP_ATTENUATION;
+  /* forward runs of UNDO_ATTENUATION_AND_OR_PML keep no Stacey record: specfem_b200_iterate_time calls
+     compute_stacey_*_undoatt_cuda instead (compute_stacey_viscoelastic.F90:453-457, compute_stacey_acoustic.f90:369-372) */
+  int UNDO_ATTENUATION_AND_OR_PML;
   /* halo transport between the ranks of THIS process: 1 = copy send -> receive buffers on the host (what MPI does between
      processes), 0 = none (single rank, or the library moves the halo itself after specfem_b200_halo_p2p_connect) */
   int host_exchange;

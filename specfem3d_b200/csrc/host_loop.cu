@@ -73,7 +73,9 @@ void acoustic_step(Run* run, int it) {
       if (!r.acoustic) continue;
       compute_forces_acoustic_cuda_(r.Mesh_pointer, &iphase, &r.nspec_outer_acoustic, &r.nspec_inner_acoustic, &fwd);
       if (iphase == 1) {
-        if (run->STACEY_ABSORBING_CONDITIONS) {
+        if (run->STACEY_ABSORBING_CONDITIONS && run->UNDO_ATTENUATION_AND_OR_PML) {
+          compute_stacey_acoustic_undoatt_cuda_(r.Mesh_pointer, &iphase, &fwd);  // no record kept
+        } else if (run->STACEY_ABSORBING_CONDITIONS) {
           compute_stacey_acoustic_cuda_(r.Mesh_pointer, &iphase, r.b_absorb_potential, &fwd);
           if (run->SAVE_FORWARD && r.absorb_potential_history) {  // write_abs(IOABS_AC, b_absorb_potential, b_reclen_potential, it)
             const size_t rec = (size_t)25 * r.num_abs_boundary_faces;
@@ -120,7 +122,9 @@ void elastic_step(Run* run, int it) {
       // COMPUTE_AND_STORE_STRAIN = ATTENUATION in a forward run (read_mesh_databases.F90)
       compute_forces_viscoelastic_cuda_(r.Mesh_pointer, &iphase, &run->deltat, &r.nspec_outer_elastic, &r.nspec_inner_elastic, &att, &att, &fwd);
       if (iphase == 1) {
-        if (run->STACEY_ABSORBING_CONDITIONS) {
+        if (run->STACEY_ABSORBING_CONDITIONS && run->UNDO_ATTENUATION_AND_OR_PML) {
+          compute_stacey_viscoelastic_undoatt_cuda_(r.Mesh_pointer, &iphase, &fwd);  // no record kept: the kernel run re-computes it
+        } else if (run->STACEY_ABSORBING_CONDITIONS) {
           compute_stacey_viscoelastic_cuda_(r.Mesh_pointer, &iphase, r.b_absorb_field, &fwd);
           if (run->SAVE_FORWARD && r.absorb_field_history) {  // write_abs(IOABS, b_absorb_field, b_reclen_field, it)
             const size_t rec = (size_t)3 * 25 * r.num_abs_boundary_faces;

@@ -280,7 +280,7 @@ class _HostRun(ctypes.Structure):
                 ("has_receivers", ctypes.c_int), ("NTSTEP_BETWEEN_OUTPUT_SAMPLE", ctypes.c_int), ("nlength_seismogram", ctypes.c_int),
                 ("USE_TRICK_FOR_BETTER_PRESSURE", ctypes.c_int), ("seismo_flush_every", ctypes.c_int), ("SAVE_FORWARD", ctypes.c_int),
                 ("b_deltat", ctypes.c_float), ("b_deltatover2", ctypes.c_float), ("b_deltatsqover2", ctypes.c_float),
-                ("nrec", ctypes.c_int), ("APPROXIMATE_HESS_KL", ctypes.c_int), ("NT_DUMP_ATTENUATION", ctypes.c_int), ("host_exchange", ctypes.c_int), ("norm_every", ctypes.c_int), ("norms", _PF)]
+                ("nrec", ctypes.c_int), ("APPROXIMATE_HESS_KL", ctypes.c_int), ("NT_DUMP_ATTENUATION", ctypes.c_int), ("UNDO_ATTENUATION_AND_OR_PML", ctypes.c_int), ("host_exchange", ctypes.c_int), ("norm_every", ctypes.c_int), ("norms", _PF)]
 
 
 def _pf(a):
@@ -463,8 +463,8 @@ class DeviceRun:
         time steps without the interpreter in between.  Forward runs only (no SAVE_FORWARD record history, no kernel runs).
         Returns the stability norms recorded every ``norm_every`` steps."""
         sim = self.sim
-        if sim.SIMULATION_TYPE != 1 or sim.UNDO_ATTENUATION_AND_OR_PML:
-            raise NotImplementedError("native host loop: forward runs only (kernel runs: KernelRun.run_native, undo_att.py)")
+        if sim.SIMULATION_TYPE != 1:
+            raise NotImplementedError("native host loop: forward runs (kernel runs: KernelRun.run_native, UndoAttKernelRun.run_native)")
         host_exchange = self._native_host_exchange()
         n = (sim.NSTEP - self.it) if nstep is None else nstep
         if n <= 0:
@@ -481,7 +481,7 @@ class DeviceRun:
         fn(ctypes.byref(run), ctypes.byref(ctypes.c_int(self.it + 1)), ctypes.byref(ctypes.c_int(self.it + n)))
         for k, r in enumerate(self.ranks):
             r.seismo_current = arr[k].seismo_current
-            if sim.SAVE_FORWARD and sim.spec.stacey:  # same bookkeeping as step(): one record per step and domain of the rank
+            if sim.SAVE_FORWARD and sim.spec.stacey and not sim.UNDO_ATTENUATION_AND_OR_PML:  # bookkeeping of step(): a record per step
                 if r.ELASTIC:
                     r.absorb_history += [keep[k][3][it].copy() for it in range(self.it, self.it + n)]
                 if r.ACOUSTIC:
@@ -523,7 +523,7 @@ class DeviceRun:
                 h.b_absorb_field, h.b_absorb_potential = _pf(r.b_absorb_field), _pf(r.b_absorb_potential)
                 h.nrec_local = r.nrec_local
                 h.num_abs_boundary_faces = db.num_abs_boundary_faces
-                if sim.SAVE_FORWARD:  # the records proc*_absorb_field.bin / proc*_absorb_potential.bin would hold, one per step
+                if sim.SAVE_FORWARD and not sim.UNDO_ATTENUATION_AND_OR_PML:  # the records of proc*_absorb_field.bin / _potential.bin
                     nf = max(db.num_abs_boundary_faces, 1)
                     keep[k] += [np.zeros((sim.NSTEP, nf, 25, 3), np.float32), np.zeros((sim.NSTEP, nf, 25), np.float32)]
                     h.absorb_field_history, h.absorb_potential_history = _pf(keep[k][3]), _pf(keep[k][4])
@@ -542,7 +542,9 @@ class DeviceRun:
             run.stf_elastic, run.stf_acoustic = keep["stf_el"].ctypes.data_as(_PD), keep["stf_ac"].ctypes.data_as(_PD)
             run.has_receivers = int(sim.receivers is not None)
             run.USE_TRICK_FOR_BETTER_PRESSURE = int(sim.USE_TRICK_FOR_BETTER_PRESSURE)
-            run.SAVE_FORWARD = int(sim.SAVE_FORWARD)
+            # a forward run of UNDO_ATTENUATION_AND_OR_PML keeps no Stacey records (its frames are taken by the caller between calls)
+            run.SAVE_FORWARD = int(sim.SAVE_FORWARD and not sim.UNDO_ATTENUATION_AND_OR_PML)
+            run.UNDO_ATTENUATION_AND_OR_PML = int(sim.UNDO_ATTENUATION_AND_OR_PML and sim.SIMULATION_TYPE == 1)
             run.NTSTEP_BETWEEN_OUTPUT_SAMPLE, run.nlength_seismogram = sim.NTSTEP_BETWEEN_OUTPUT_SAMPLE, sim.nlength_seismogram
             self._native = (run, arr, keep)
         return self._native

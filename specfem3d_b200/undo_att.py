@@ -58,8 +58,9 @@ class UndoAttProducts:
     frames: List[List[dict]] = field(default_factory=list)
 
 
-def run_forward_and_save_undoatt(sim, lib=None, halo: str = "host"):
-    """SIMULATION_TYPE = 1, SAVE_FORWARD, UNDO_ATTENUATION_AND_OR_PML: returns (the finished DeviceRun, UndoAttProducts)."""
+def run_forward_and_save_undoatt(sim, lib=None, halo: str = "host", native: bool = False):
+    """SIMULATION_TYPE = 1, SAVE_FORWARD, UNDO_ATTENUATION_AND_OR_PML: returns (the finished DeviceRun, UndoAttProducts).
+    ``native``: the steps of every subset through the native host loop (specfem_b200_iterate_time)."""
     assert sim.SIMULATION_TYPE == 1 and sim.SAVE_FORWARD and sim.UNDO_ATTENUATION_AND_OR_PML
     if (sim.ACOUSTIC_SIMULATION and sim.ELASTIC_SIMULATION) or sim.PML_CONDITIONS:
         raise NotImplementedError("undo-attenuation runs: elastic or acoustic domains (not coupled), no C-PML")
@@ -79,8 +80,11 @@ def run_forward_and_save_undoatt(sim, lib=None, halo: str = "host"):
                 r.lib.transfer_rmemory_from_device(r.Mesh_pointer, *R, N_SLS * NGLL3 * n)
                 f["R"] = R  # xx, yy, xy, xz, yz, trace
             prod.frames[ir].append(f)
-        for _ in range(lengths[s]):
-            run.step()
+        if native:
+            run.run_native(lengths[s])
+        else:
+            for _ in range(lengths[s]):
+                run.step()
     return run, prod
 
 

@@ -197,10 +197,11 @@ def test_undo_attenuation_loops_issue_the_same_calls(mock_lib, case):
             "elastic_2x2": lambda t: R.undoatt_kernel_sim(nstep, t, False, (2, 2), nt_dump),
             "viscoelastic_2x1": lambda t: R.undoatt_kernel_sim(nstep, t, True, (2, 1), nt_dump),
             "acoustic_2x2": lambda t: R.undoatt_acoustic_sim(nstep, t, (2, 2), nt_dump)}[case]
-    logs = {}
+    logs, fwd_logs = {}, {}
     for native in (False, True):
         mock_lib.cdll.mock_reset(1)
-        fwd, prod = run_forward_and_save_undoatt(make(1), lib=mock_lib)
+        fwd, prod = run_forward_and_save_undoatt(make(1), lib=mock_lib, native=native)  # subset by subset, frames saved in between
+        forward_log = [c for c in _calls(mock_lib) if not c[0].startswith(("prepare_", "initialize_"))]
         fwd.cleanup()
         for ir, frames in enumerate(prod.frames):  # recognisable frames (the mock's device hands back zeros)
             for s, f in enumerate(frames):
@@ -222,8 +223,12 @@ def test_undo_attenuation_loops_issue_the_same_calls(mock_lib, case):
             run.run()
         assert run.it == nstep
         logs[native] = _calls(mock_lib)
+        fwd_logs[native] = forward_log
         run.cleanup()
     a, b = logs[False], logs[True]
+    fa, fb = fwd_logs[False], fwd_logs[True]
+    assert any(c[0].endswith("_undoatt_cuda") for c in fa) and not any(c[0] in ("compute_stacey_viscoelastic_cuda", "compute_stacey_acoustic_cuda") for c in fa)
+    assert fa == fb, next((i, x, y) for i, (x, y) in enumerate(zip(fa, fb)) if x != y)
     names = [c[0] for c in a]
     assert names.count("transfer_b_fields_to_device") + names.count("transfer_b_fields_ac_to_device") == 3 * len({c[1] for c in a})
     assert a == b, next((i, x, y) for i, (x, y) in enumerate(zip(a, b)) if x != y)
